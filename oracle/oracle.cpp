@@ -1,0 +1,558 @@
+// oracle/oracle.cpp -- TEST INFRASTRUCTURE ONLY (see oracle/oracle.h header).
+//
+// Single-threaded, obviously-sequential restatement of maelstrom.net
+// (/root/reference/src/maelstrom/net.clj) and the canonical node programs,
+// under the deterministic refinement in DESIGN.md section 2.  Every rule cites
+// the reference line it follows.  Nothing here is tuned for speed beyond what
+// makes it usable as the measured "CPU restatement" baseline.
+//
+// Round structure:
+//   round r runs at virtual time now_r.
+//   (1) injector: host-queued sends (call order), then scheduled ops with
+//       time <= now_r (schedule order) are sent.
+//   (2) endpoints in ascending index: pop every envelope with deadline <= now_r
+//       that was enqueued in a round < r, in (deadline, id) order
+//       (net.clj:39-40,145 orders by deadline only; ties are unspecified in the
+//       JDK heap, the spec breaks them by id); partition check at dequeue
+//       (net.clj:234); journal :recv (net.clj:244); run the node program; the
+//       node's emissions are sent right after its receives.
+//   (3) messages sent in round r become visible to receivers in round r+1.
+//   (4) if anything is due at now_r, the next round is a delta round at the same
+//       time, otherwise time advances by one tick (1 ms).
+#include "oracle.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <queue>
+#include <set>
+#include <string>
+#include <vector>
+
+namespace {
+
+constexpr int64_t kTickNs = 1000000;  // latencies are integer ms (net.clj:187,204)
+constexpr uint32_t kInjector = 0xFFFFFFFFu;
+
+// ---------------------------------------------------------------- Philox4x32-10
+// Salmon et al., "Parallel random numbers: as easy as 1, 2, 3" (SC'11); the
+// same generator cuRAND calls Philox_4x32_10.  Replaces the reference's
+// unseeded (rand) (net.clj:214) and Incanter draws (net.clj:187).
+inline void philox_round(uint32_t c[4], const uint32_t k[2]) {
+  const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+  const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+  const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+  const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+  const uint32_t n0 = hi1 ^ c[1] ^ k[0];
+  const uint32_t n1 = lo1;
+  const uint32_t n2 = hi0 ^ c[3] ^ k[1];
+  const uint32_t n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+
+void philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
+  uint32_t k[2] = {key[0], key[1]};
+  for (int i = 0; i < 10; i++) {
+    if (i) { k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u; }
+    philox_round(c, k);
+  }
+  for (int i = 0; i < 4; i++) out[i] = c[i];
+}
+
+// ------------------------------------------------------------- latency (net.clj:65-77,178-187)
+// Integer-only so CPU and GPU agree bit for bit.
+//   constant     -> mean * scale                         (net.clj:42-49, 51-53)
+//   uniform      -> scale * floor(u * 2*mean), u in [0,1) (integer-distribution 0 (* 2 mean))
+//   exponential  -> floor(scale * mean * -ln(u)), u in (0,1]; (long (* scale (draw d)))
+// -ln(u) is evaluated in fixed point: u = (X+1)/2^64 for 64 random bits X,
+// log2 by normalise + 32 squarings (each squaring keeps the top 64 bits).
+uint64_t neg_log2_q32(uint64_t X) {
+  if (X == ~0ull) return 0;       // u == 1
+  const uint64_t Y = X + 1;       // in [1, 2^64-1]
+  const int n = 63 - __builtin_clzll(Y);
+  uint64_t m = Y << (63 - n);     // Q1.63 in [1,2)
+  uint32_t frac = 0;
+  for (int i = 31; i >= 0; i--) {
+    const uint64_t hi = (uint64_t)(((unsigned __int128)m * m) >> 64);  // Q2.62 in [1,4)
+    if (hi >> 63) { frac |= (1u << i); m = hi; }
+    else          { m = hi << 1; }
+  }
+  const uint64_t log2y = ((uint64_t)n << 32) | frac;
+  return (64ull << 32) - log2y;   // -log2(u), Q32.32
+}
+
+uint64_t exp_coeff(uint32_t mean_ms, uint32_t scale) {
+  // round(mean * scale * ln2 * 2^32); a double multiply and llround, done on
+  // the host CPU by both the oracle and the engine's host side.
+  const double c = (double)mean_ms * (double)scale * 0.693147180559945309417232121458 * 4294967296.0;
+  return (uint64_t)std::llround(c);
+}
+
+uint64_t latency_draw(uint32_t dist, uint32_t mean_ms, uint32_t scale, const uint32_t x[4]) {
+  switch (dist) {
+    case OR_DIST_CONSTANT:
+      return (uint64_t)mean_ms * scale;
+    case OR_DIST_UNIFORM: {
+      const uint64_t span = 2ull * mean_ms;
+      return (((uint64_t)x[1] * span) >> 32) * scale;
+    }
+    case OR_DIST_EXPONENTIAL: {
+      const uint64_t X = ((uint64_t)x[2] << 32) | x[1];
+      const uint64_t L = neg_log2_q32(X);
+      const uint64_t C = exp_coeff(mean_ms, scale);
+      return (uint64_t)(((unsigned __int128)L * C) >> 64);
+    }
+  }
+  return 0;
+}
+
+uint64_t loss_threshold(double p) {
+  // (< (rand) p-loss), net.clj:214, with (rand) := x0 / 2^32.
+  if (!(p > 0.0)) return 0;
+  if (p >= 1.0) return 1ull << 32;
+  return (uint64_t)(p * 4294967296.0);
+}
+
+// ------------------------------------------------------------- topologies (workload/broadcast.clj:40-178)
+std::vector<uint32_t> topology_neighbors(uint32_t topo, uint32_t n, uint32_t k) {
+  std::vector<uint32_t> out;
+  if (k >= n) return out;
+  switch (topo) {
+    case OR_TOPO_GRID: {  // broadcast.clj:40-65
+      const int64_t side = (int64_t)std::ceil(std::sqrt((double)n));
+      const int64_t i = k / side, j = k % side;
+      auto node = [&](int64_t a, int64_t b) -> int64_t {
+        if (a > -1 && b > -1 && b < side) {        // (< -1 i) (< -1 j side)
+          const int64_t idx = a * side + b;
+          if (idx < (int64_t)n) return idx;
+        }
+        return -1;
+      };
+      const int64_t cand[4] = {node(i + 1, j), node(i - 1, j), node(i, j + 1), node(i, j - 1)};
+      for (int64_t c : cand) if (c >= 0) out.push_back((uint32_t)c);
+      break;
+    }
+    case OR_TOPO_LINE: {  // broadcast.clj:67-80
+      if (n < 2) break;
+      if (k == 0) out.push_back(1);
+      else if (k == n - 1) out.push_back(n - 2);
+      else { out.push_back(k - 1); out.push_back(k + 1); }
+      break;
+    }
+    case OR_TOPO_TOTAL: {  // broadcast.clj:82-89
+      for (uint32_t i = 0; i < n; i++) if (i != k) out.push_back(i);
+      break;
+    }
+    case OR_TOPO_TREE2: case OR_TOPO_TREE3: case OR_TOPO_TREE4: {  // broadcast.clj:91-167
+      const uint32_t b = topo == OR_TOPO_TREE2 ? 2 : topo == OR_TOPO_TREE3 ? 3 : 4;
+      // tiers of size 1, b, b^2.. filled in order; children of the p-th node of a
+      // tier are the next b nodes of the tier below => heap layout.
+      if (k > 0) out.push_back((k - 1) / b);         // parent first (:163-165)
+      for (uint32_t c = 0; c < b; c++) {
+        const uint64_t ch = (uint64_t)b * k + 1 + c;
+        if (ch < n) out.push_back((uint32_t)ch);
+      }
+      break;
+    }
+  }
+  return out;
+}
+
+// ------------------------------------------------------------- simulator state
+struct Envelope {           // {:deadline :message}, net.clj:219-220
+  or_msg m;
+  uint64_t sent_round;
+};
+struct EnvCmp {             // latency-compare (net.clj:39-40) + id tie-break
+  bool operator()(const Envelope& a, const Envelope& b) const {
+    if (a.m.deadline_ns != b.m.deadline_ns) return a.m.deadline_ns > b.m.deadline_ns;
+    return a.m.id > b.m.id;
+  }
+};
+typedef std::priority_queue<Envelope, std::vector<Envelope>, EnvCmp> Queue;
+
+struct Emit {                 // one emission of a node program
+  explicit Emit(const or_msg& mm) : m(mm) {}
+  or_msg m;
+  bool has_snap = false;
+  std::vector<uint32_t> snap; // read_ok value list (the set as of the read)
+};
+
+struct Endpoint {
+  std::string name;
+  int kind = OR_KIND_SERVER;
+  bool live = true;
+  Queue q;                              // net.clj:145
+  std::deque<or_msg> mailbox;           // delivered to a host-visible endpoint
+  // node program state
+  uint32_t next_msg_id = 0;             // echo.rb:8,12
+  std::set<uint32_t> values;            // broadcast @messages / g-set @set
+  std::vector<uint32_t> neighbors;      // broadcast @neighbors (topology)
+};
+
+}  // namespace
+
+struct or_sim {
+  or_config cfg;
+  std::vector<Endpoint> eps;
+  int64_t now = 0;
+  uint64_t round = 0;
+  uint64_t next_id = 0;        // next-message-id starts at -1, first id 0 (net.clj:103,197)
+  uint64_t next_event = 0;     // journal next-id (journal.clj:195,228)
+  uint32_t scale = 1;          // slow!/fast! (net.clj:115-119)
+  uint64_t loss_thresh = 0;
+  std::set<std::pair<uint32_t, uint32_t>> partitions;  // (dest, src), net.clj:109-110
+  std::vector<uint32_t> component;                     // bulk partition
+  std::vector<or_event> journal;
+  std::vector<or_body> bodies;                         // body of the message of each event
+  std::deque<or_msg> host_queue;                       // pending host sends
+  std::vector<or_op> schedule;
+  size_t sched_cursor = 0;
+  std::map<uint64_t, std::vector<uint32_t>> snapshots; // read_ok msg id -> set contents
+  uint64_t client_replies = 0;
+  std::string error;
+  uint64_t stats[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+
+  bool is_client(uint32_t e) const { return eps[e].kind == OR_KIND_CLIENT; }   // util.clj:7-10
+  bool involves_client(const or_msg& m) const {                                // util.clj:12-16
+    return is_client(m.src) || is_client(m.dest);
+  }
+  bool partitioned(uint32_t src, uint32_t dest) const {                        // net.clj:234
+    if (partitions.count(std::make_pair(dest, src))) return true;
+    if (!component.empty() && src < component.size() && dest < component.size() &&
+        component[src] != component[dest]) return true;
+    return false;
+  }
+
+  void log_event(bool recv, const or_msg& m) {      // journal.clj:225-239
+    or_event ev;
+    ev.event_id = next_event++ | (recv ? (1ull << 63) : 0);
+    ev.time_ns = now;
+    ev.msg_id = m.id;
+    ev.src = m.src;
+    ev.dest = m.dest;
+    journal.push_back(ev);
+    or_body b;
+    b.type = m.type; b.flags = m.flags; b.msg_id = m.msg_id;
+    b.in_reply_to = m.in_reply_to; b.p0 = m.p0; b.p1 = m.p1;
+    bodies.push_back(b);
+    // net/checker.clj:28-41 folded on the fly
+    const bool cl = involves_client(m);
+    const int k = recv ? 1 : 0;
+    stats[0 + k]++;
+    stats[(cl ? 3 : 6) + k]++;
+  }
+
+  // net.clj:189-221
+  bool send(uint32_t emitter, uint32_t emit_idx, or_msg m, std::vector<Envelope>& pending) {
+    if (m.src >= eps.size() || !eps[m.src].live) { error = "Invalid source for message"; return false; }   // :172
+    if (m.dest >= eps.size() || !eps[m.dest].live) { error = "Invalid dest for message"; return false; }   // :174
+    m.id = next_id++;                                                             // :197
+    const uint32_t ctr[4] = {emit_idx, emitter, (uint32_t)round, (uint32_t)(round >> 32)};
+    const uint32_t key[2] = {cfg.seed_lo, cfg.seed_hi};
+    uint32_t x[4];
+    philox(ctr, key, x);
+    const uint64_t lat_ms = involves_client(m) ? 0                                // :185-186
+                                               : latency_draw(cfg.latency_dist, cfg.latency_mean_ms, scale, x);
+    m.deadline_ns = now + (int64_t)lat_ms * kTickNs;                              // :202-205
+    log_event(false, m);                                                          // :208 (always, before the loss roll)
+    if ((uint64_t)x[0] < loss_thresh) return true;                                // :214-215
+    Envelope env; env.m = m; env.sent_round = round;
+    pending.push_back(env);                                                       // :216-221 (visible next round)
+    return true;
+  }
+
+  // ---- node programs: append emissions (src/dest/body filled) to `out`
+  static or_msg reply_to(const or_msg& req, uint16_t type) {   // node.rb:88-91
+    or_msg r; std::memset(&r, 0, sizeof r);
+    r.src = req.dest; r.dest = req.src; r.type = type;
+    r.flags = OR_F_REPLY; r.in_reply_to = req.msg_id;
+    return r;
+  }
+
+  void node_echo(uint32_t e, const or_msg& m, std::vector<Emit>& out) {
+    Endpoint& ep = eps[e];
+    if (m.type == OR_T_INIT || m.type == OR_T_ECHO) {       // echo.rb:28-39
+      or_msg r = reply_to(m, m.type == OR_T_INIT ? OR_T_INIT_OK : OR_T_ECHO_OK);
+      r.flags |= OR_F_MSG_ID;
+      r.msg_id = ++ep.next_msg_id;                          // echo.rb:12-13
+      if (m.type == OR_T_ECHO) { r.p0 = m.p0; r.p1 = m.p1; }
+      out.push_back(Emit(r));
+    }
+    // any other type: echo.rb's case has no else branch -> ignored
+  }
+
+  void node_common_unknown(const or_msg& m, std::vector<Emit>& out) {
+    // Replies (in_reply_to present) with no callback are ignored (node.rb:159-164).
+    // An unhandled request type gets error 10 "not-supported"
+    // (resources/errors.edn; demo/go/node_test.go:51) when it carries a msg_id.
+    if (m.flags & OR_F_REPLY) return;
+    if (m.flags & OR_F_MSG_ID) {
+      or_msg r = reply_to(m, OR_T_ERROR);
+      r.p0 = 10;
+      out.push_back(Emit(r));
+    }
+  }
+
+  void node_broadcast(uint32_t e, const or_msg& m, std::vector<Emit>& out) {
+    Endpoint& ep = eps[e];
+    if (m.flags & OR_F_REPLY) return;                       // node.rb:159-164
+    switch (m.type) {
+      case OR_T_INIT:      out.push_back(Emit(reply_to(m, OR_T_INIT_OK))); break;      // node.rb:22-36
+      case OR_T_TOPOLOGY:  out.push_back(Emit(reply_to(m, OR_T_TOPOLOGY_OK))); break;  // 01-broadcast.md:286-290
+      case OR_T_READ: {                                                            // broadcast.rb:22-27
+        or_msg r = reply_to(m, OR_T_READ_OK);
+        r.p0 = (uint32_t)ep.values.size();
+        Emit em(r);
+        em.has_snap = true;
+        em.snap.assign(ep.values.begin(), ep.values.end());
+        out.push_back(em);
+        break;
+      }
+      case OR_T_BROADCAST: {                                // 01-broadcast.md:527-544
+        const uint32_t v = m.p0;
+        if (v >= cfg.n_values) { error = "broadcast value out of range"; return; }
+        if (!ep.values.count(v)) {
+          ep.values.insert(v);
+          for (uint32_t nb : ep.neighbors) {
+            if (nb == m.src) continue;                      // 02-performance.md:61-67
+            or_msg g; std::memset(&g, 0, sizeof g);
+            g.src = e; g.dest = nb; g.type = OR_T_BROADCAST; g.p0 = v;
+            out.push_back(Emit(g));                         // fire-and-forget, no msg_id
+          }
+        }
+        if (m.flags & OR_F_MSG_ID) out.push_back(Emit(reply_to(m, OR_T_BROADCAST_OK)));
+        break;
+      }
+      default: node_common_unknown(m, out);
+    }
+  }
+
+  bool run_round() {
+    std::vector<Envelope> pending;
+    // (1) injector
+    uint32_t inj = 0;
+    while (!host_queue.empty()) {
+      or_msg m = host_queue.front(); host_queue.pop_front();
+      if (!send(kInjector, inj++, m, pending)) return false;
+    }
+    while (sched_cursor < schedule.size() && schedule[sched_cursor].time_ns <= now) {
+      const or_op& op = schedule[sched_cursor++];
+      or_msg m; std::memset(&m, 0, sizeof m);
+      m.src = op.src; m.dest = op.dest; m.type = op.body.type; m.flags = op.body.flags;
+      m.msg_id = op.body.msg_id; m.in_reply_to = op.body.in_reply_to;
+      m.p0 = op.body.p0; m.p1 = op.body.p1;
+      if (!send(kInjector, inj++, m, pending)) return false;
+    }
+    // (2) endpoints
+    std::vector<Emit> out;
+    for (uint32_t e = 0; e < eps.size(); e++) {
+      Endpoint& ep = eps[e];
+      if (!ep.live) continue;
+      out.clear();
+      while (!ep.q.empty() && ep.q.top().m.deadline_ns <= now) {   // net.clj:228-229,236-238
+        const or_msg m = ep.q.top().m;
+        ep.q.pop();
+        if (partitioned(m.src, e)) continue;                       // net.clj:234: consumed, no event
+        log_event(true, m);                                        // net.clj:244
+        switch (ep.kind) {
+          case OR_KIND_CLIENT:
+            if (m.flags & OR_F_REPLY) client_replies++;
+            ep.mailbox.push_back(m);
+            break;
+          case OR_KIND_HOST:
+            ep.mailbox.push_back(m);
+            break;
+          default:
+            if (cfg.workload == OR_W_ECHO) node_echo(e, m, out);
+            else if (cfg.workload == OR_W_BROADCAST) node_broadcast(e, m, out);
+            else { error = "workload not implemented in oracle"; return false; }
+        }
+        if (!error.empty()) return false;
+      }
+      for (uint32_t j = 0; j < out.size(); j++) {
+        if (out[j].has_snap) snapshots[next_id] = out[j].snap;   // keyed by the read_ok's net id
+        if (!send(e, j, out[j].m, pending)) return false;
+      }
+    }
+    // (3) visibility
+    bool due_now = false;
+    for (const Envelope& env : pending) {
+      if (env.m.deadline_ns <= now) due_now = true;
+      eps[env.m.dest].q.push(env);
+    }
+    // (4) time advance
+    round++;
+    if (!due_now) now += kTickNs;
+    return true;
+  }
+};
+
+extern "C" {
+
+or_sim* or_create(const or_config* cfg) {
+  or_sim* s = new or_sim();
+  s->cfg = *cfg;
+  if (s->cfg.n_values == 0) s->cfg.n_values = 1u << 20;
+  s->loss_thresh = loss_threshold(cfg->p_loss);
+  s->eps.resize(cfg->n_nodes);
+  for (uint32_t i = 0; i < cfg->n_nodes; i++) {
+    s->eps[i].name = "n" + std::to_string(i);          // core.clj:231-238
+    s->eps[i].kind = OR_KIND_SERVER;
+    s->eps[i].neighbors = topology_neighbors(cfg->topology, cfg->n_nodes, i);
+  }
+  return s;
+}
+
+void or_destroy(or_sim* s) { delete s; }
+const char* or_last_error(or_sim* s) { return s->error.c_str(); }
+
+int or_add_endpoint(or_sim* s, const char* name, int kind) {   // net.clj:139-146
+  Endpoint ep;
+  ep.name = name;
+  ep.kind = kind;
+  s->eps.push_back(ep);
+  return (int)s->eps.size() - 1;
+}
+
+int or_remove_endpoint(or_sim* s, uint32_t idx) {               // net.clj:148-152
+  if (idx >= s->eps.size() || !s->eps[idx].live) return -1;
+  s->eps[idx].live = false;
+  return 0;
+}
+
+int64_t or_send(or_sim* s, uint32_t src, uint32_t dest, const or_body* b) {
+  if (src >= s->eps.size() || !s->eps[src].live) return -1;   // node-not-found, code 1 (net.clj:159-164)
+  if (dest >= s->eps.size() || !s->eps[dest].live) return -1;
+  or_msg m; std::memset(&m, 0, sizeof m);
+  m.src = src; m.dest = dest; m.type = b->type; m.flags = b->flags;
+  m.msg_id = b->msg_id; m.in_reply_to = b->in_reply_to; m.p0 = b->p0; m.p1 = b->p1;
+  s->host_queue.push_back(m);
+  return (int64_t)(s->next_id + s->host_queue.size() - 1);
+}
+
+int or_schedule(or_sim* s, const or_op* ops, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    if (!s->schedule.empty() && ops[i].time_ns < s->schedule.back().time_ns) return -2;
+    s->schedule.push_back(ops[i]);
+  }
+  return 0;
+}
+
+int or_step(or_sim* s, uint64_t n_rounds) {
+  for (uint64_t i = 0; i < n_rounds; i++) if (!s->run_round()) return -3;
+  return 0;
+}
+
+int or_run(or_sim* s, int64_t until_ns) {
+  while (s->now < until_ns) if (!s->run_round()) return -3;
+  return 0;
+}
+
+int or_recv(or_sim* s, uint32_t e, int64_t timeout_ns, or_msg* out) {   // net.clj:223-247
+  if (e >= s->eps.size() || !s->eps[e].live) return -1;
+  // Poll; while nothing is deliverable advance the simulation one round at a
+  // time until the virtual timeout has elapsed (the reference blocks on the
+  // wall clock, net.clj:228-229).
+  const int64_t give_up = s->now + timeout_ns;
+  for (;;) {
+    if (!s->eps[e].mailbox.empty()) {
+      *out = s->eps[e].mailbox.front();
+      s->eps[e].mailbox.pop_front();
+      return 1;
+    }
+    if (s->now >= give_up) return 0;
+    if (!s->run_round()) return -3;
+  }
+}
+
+int64_t or_now(or_sim* s) { return s->now; }
+uint64_t or_round(or_sim* s) { return s->round; }
+
+int or_net_drop(or_sim* s, uint32_t src, uint32_t dest) {        // net.clj:109-110
+  s->partitions.insert(std::make_pair(dest, src));
+  return 0;
+}
+int or_net_heal(or_sim* s) {                                     // net.clj:112-113
+  s->partitions.clear();
+  s->component.clear();
+  return 0;
+}
+int or_net_slow(or_sim* s) { s->scale *= 10; return 0; }         // net.clj:115-116 (stackable)
+int or_net_fast(or_sim* s) {                                     // net.clj:118-119; unwrap one level.
+  if (s->scale >= 10) s->scale /= 10;                            // (nil on unscaled is a latent bug, not replicated)
+  return 0;
+}
+int or_net_flaky(or_sim* s) { s->loss_thresh = loss_threshold(0.5); return 0; }  // net.clj:121-122
+int or_net_set_loss(or_sim* s, double p) { s->loss_thresh = loss_threshold(p); return 0; }
+int or_net_partition(or_sim* s, const uint32_t* c, size_t n) {
+  s->component.assign(c, c + n);
+  return 0;
+}
+
+size_t or_journal_size(or_sim* s) { return s->journal.size(); }
+size_t or_journal_copy(or_sim* s, size_t first, or_event* ev, or_body* bodies, size_t cap) {
+  size_t n = 0;
+  for (size_t i = first; i < s->journal.size() && n < cap; i++, n++) {
+    if (ev) ev[n] = s->journal[i];
+    if (bodies) bodies[n] = s->bodies[i];
+  }
+  return n;
+}
+
+void or_stats(or_sim* s, uint64_t out[9]) {
+  // {all,clients,servers} x {send-count, recv-count, msg-count}; msg-count =
+  // cardinality of message ids over all events of the class (net/checker.clj:34-36)
+  std::vector<uint8_t> seen(s->next_id, 0);
+  uint64_t mc[3] = {0, 0, 0};
+  for (const or_event& ev : s->journal) {
+    or_msg m; m.src = ev.src; m.dest = ev.dest;
+    const bool cl = s->involves_client(m);
+    const uint8_t bit = cl ? 2 : 4;
+    if (!(seen[ev.msg_id] & 1)) { seen[ev.msg_id] |= 1; mc[0]++; }
+    if (!(seen[ev.msg_id] & bit)) { seen[ev.msg_id] |= bit; mc[cl ? 1 : 2]++; }
+  }
+  for (int c = 0; c < 3; c++) {
+    out[c * 3 + 0] = s->stats[c * 3 + 0];
+    out[c * 3 + 1] = s->stats[c * 3 + 1];
+    out[c * 3 + 2] = mc[c];
+  }
+}
+
+size_t or_node_set(or_sim* s, uint32_t node, uint32_t* vals, size_t cap) {
+  if (node >= s->eps.size()) return 0;
+  size_t n = 0;
+  for (uint32_t v : s->eps[node].values) { if (n < cap && vals) vals[n] = v; n++; }
+  return n;
+}
+
+size_t or_read_snapshot(or_sim* s, uint64_t msg_id, uint32_t* vals, size_t cap) {
+  auto it = s->snapshots.find(msg_id);
+  if (it == s->snapshots.end()) return 0;
+  size_t n = 0;
+  for (uint32_t v : it->second) { if (n < cap && vals) vals[n] = v; n++; }
+  return n;
+}
+
+uint64_t or_client_replies(or_sim* s) { return s->client_replies; }
+
+size_t or_topology(uint32_t topo, uint32_t n, uint32_t node, uint32_t* out, size_t cap) {
+  std::vector<uint32_t> nb = topology_neighbors(topo, n, node);
+  for (size_t i = 0; i < nb.size() && i < cap; i++) out[i] = nb[i];
+  return nb.size();
+}
+
+void or_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  philox(ctr, key, out);
+}
+
+uint64_t or_latency_draw(uint32_t dist, uint32_t mean_ms, uint32_t scale, const uint32_t x[4]) {
+  return latency_draw(dist, mean_ms, scale, x);
+}
+
+uint64_t or_loss_threshold(double p) { return loss_threshold(p); }
+
+}  // extern "C"

@@ -1,0 +1,139 @@
+/*
+ * oracle/oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement of the maelstrom.net + maelstrom.process hot path
+ * (/root/reference/src/maelstrom/net.clj, net/message.clj, util.clj,
+ * net/journal.clj:53,225-239, workload/broadcast.clj:40-178) together with the
+ * canonical node programs (demo/ruby/echo.rb:28-40, the tutorial broadcast
+ * node doc/03-broadcast/01-broadcast.md:527-544 + 02-performance.md:61-67,
+ * demo/ruby/g_set.rb:13-39), under the deterministic refinement recorded in
+ * DESIGN.md section 2 ("the spec").
+ *
+ * PARITY STATUS: the reference hot path is nondeterministic and has no tests
+ * (SURVEY.md fact 2/3), and no JVM exists here, so the *delivery order* part
+ * of this oracle is "parity unpinned": it is pinned only by the source text of
+ * net.clj and by the doc/test known-answer vectors listed in
+ * tests/test_oracle_golden.py (topologies, flood counts, echo counts, error
+ * codes, Philox KAT vectors).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this library.  The product
+ * (maelstrom_b200/) never links, imports or calls it.
+ *
+ * The struct layouts below are restated from the spec on purpose (they are
+ * NOT included from include/maelstrom_b200.h) so that the oracle stays an
+ * independent statement of the wire/record formats.
+ */
+#ifndef MAELSTROM_ORACLE_H
+#define MAELSTROM_ORACLE_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* 48-byte message record (net/message.clj:8). */
+typedef struct or_msg {
+  uint64_t id;          /* net-assigned message id (net.clj:197), first id 0 */
+  int64_t  deadline_ns; /* virtual delivery deadline (net.clj:202-205)       */
+  uint32_t src, dest;   /* dense endpoint indices                            */
+  uint32_t msg_id;      /* body.msg_id      (valid iff flags&1)              */
+  uint32_t in_reply_to; /* body.in_reply_to (valid iff flags&2)              */
+  uint16_t type;        /* body.type code, see OR_T_*                        */
+  uint16_t flags;
+  uint32_t p0;          /* payload word (value / element / error code / ...) */
+  uint64_t p1;          /* payload (opaque 8 bytes / blob handle)            */
+} or_msg;
+
+/* 32-byte journal event (net/journal.clj:53). bit 63 of event_id = recv. */
+typedef struct or_event {
+  uint64_t event_id;
+  int64_t  time_ns;
+  uint64_t msg_id;
+  uint32_t src, dest;
+} or_event;
+
+typedef struct or_body {
+  uint16_t type, flags;
+  uint32_t msg_id, in_reply_to, p0;
+  uint64_t p1;
+} or_body;
+
+typedef struct or_op {      /* scheduled client op: message injected at time_ns */
+  int64_t  time_ns;
+  uint32_t src, dest;
+  or_body  body;
+} or_op;
+
+typedef struct or_config {
+  uint32_t n_nodes;         /* servers n0..n{N-1}  (core.clj:231-238)        */
+  uint32_t workload;        /* OR_W_*                                        */
+  uint32_t topology;        /* OR_TOPO_*                                     */
+  uint32_t latency_dist;    /* OR_DIST_*  (net.clj:73-77)                    */
+  uint32_t latency_mean_ms; /* --latency is parse-long, core.clj:171-174     */
+  uint32_t seed_lo, seed_hi;
+  double   p_loss;          /* initial loss probability (net.clj:100 => 0)   */
+  uint32_t n_values;        /* capacity of the per-node value universe       */
+  uint32_t gset_interval_ms;/* g-set replication period (g_set.rb:30: 5 s)   */
+} or_config;
+
+enum { OR_W_ECHO = 0, OR_W_BROADCAST = 1, OR_W_GSET = 2 };
+enum { OR_TOPO_GRID = 0, OR_TOPO_LINE = 1, OR_TOPO_TOTAL = 2,
+       OR_TOPO_TREE2 = 3, OR_TOPO_TREE3 = 4, OR_TOPO_TREE4 = 5 };
+enum { OR_DIST_CONSTANT = 0, OR_DIST_UNIFORM = 1, OR_DIST_EXPONENTIAL = 2 };
+enum { OR_KIND_SERVER = 0, OR_KIND_CLIENT = 1, OR_KIND_HOST = 2 };
+enum {
+  OR_T_INIT = 1, OR_T_INIT_OK = 2, OR_T_ERROR = 3,
+  OR_T_ECHO = 10, OR_T_ECHO_OK = 11,
+  OR_T_TOPOLOGY = 20, OR_T_TOPOLOGY_OK = 21, OR_T_BROADCAST = 22,
+  OR_T_BROADCAST_OK = 23, OR_T_READ = 24, OR_T_READ_OK = 25,
+  OR_T_ADD = 30, OR_T_ADD_OK = 31, OR_T_REPLICATE_ONE = 32,
+  OR_T_REPLICATE_FULL = 33
+};
+enum { OR_F_MSG_ID = 1, OR_F_REPLY = 2 };
+
+typedef struct or_sim or_sim;
+
+or_sim*  or_create(const or_config* cfg);
+void     or_destroy(or_sim*);
+const char* or_last_error(or_sim*);
+
+int      or_add_endpoint(or_sim*, const char* name, int kind);
+int      or_remove_endpoint(or_sim*, uint32_t idx);
+int64_t  or_send(or_sim*, uint32_t src, uint32_t dest, const or_body* b);
+int      or_schedule(or_sim*, const or_op* ops, size_t n);
+int      or_step(or_sim*, uint64_t n_rounds);
+int      or_run(or_sim*, int64_t until_ns);
+int      or_recv(or_sim*, uint32_t endpoint, int64_t timeout_ns, or_msg* out);
+int64_t  or_now(or_sim*);
+uint64_t or_round(or_sim*);
+
+int      or_net_drop(or_sim*, uint32_t src, uint32_t dest);
+int      or_net_heal(or_sim*);
+int      or_net_slow(or_sim*);
+int      or_net_fast(or_sim*);
+int      or_net_flaky(or_sim*);
+int      or_net_set_loss(or_sim*, double p);
+int      or_net_partition(or_sim*, const uint32_t* component, size_t n);
+
+size_t   or_journal_size(or_sim*);
+size_t   or_journal_copy(or_sim*, size_t first, or_event* ev, or_body* bodies, size_t cap);
+/* 9 counters: {all,clients,servers} x {send,recv,msg}  (net/checker.clj:28-41) */
+void     or_stats(or_sim*, uint64_t out[9]);
+size_t   or_node_set(or_sim*, uint32_t node, uint32_t* vals, size_t cap);
+size_t   or_read_snapshot(or_sim*, uint64_t msg_id, uint32_t* vals, size_t cap);
+uint64_t or_client_replies(or_sim*);
+
+/* pure helpers, exported so the tests can pin them to golden vectors */
+size_t   or_topology(uint32_t topo, uint32_t n, uint32_t node, uint32_t* out, size_t cap);
+void     or_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+uint64_t or_latency_draw(uint32_t dist, uint32_t mean_ms, uint32_t scale,
+                         const uint32_t x[4]);
+uint64_t or_loss_threshold(double p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
