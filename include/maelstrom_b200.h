@@ -1,0 +1,216 @@
+/*
+ * maelstrom_b200.h -- C ABI of the B200-native replacement for Maelstrom's hot
+ * path: maelstrom.process (node spawn + STDIN/STDOUT pumps,
+ * src/maelstrom/process.clj:68-256) and maelstrom.net (route / latency / loss /
+ * partition, src/maelstrom/net.clj:79-247).  Everything above that boundary
+ * (maelstrom.client, workload.*, nemesis, core, checkers) keeps calling the same
+ * seven entry points; INTEGRATION.md shows the JNI / Clojure stub a maintainer
+ * would add.  All paths in the comments are relative to /root/reference.
+ *
+ * Plain C types only: no torch, no CUDA types.  The library owns all device
+ * memory; callers own every out-buffer.  Any thread may call; calls on one
+ * ms_sim are serialised by an internal mutex (the reference's state is one atom
+ * plus thread-safe queues, net.clj:92-103).  There is NO CPU fallback: ms_create
+ * fails (NULL + ms_last_error) when no CUDA device is usable.
+ */
+#ifndef MAELSTROM_B200_H
+#define MAELSTROM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MS_ABI_VERSION 1
+
+/* ------------------------------------------------------------------ records */
+
+/* Message: replaces the Message record {^long id src dest body}
+ * (net/message.clj:8-15).  48 bytes = three 16-byte vectors.  Node ids are dense
+ * indices: servers n0..n{N-1} (core.clj:231-238) are 0..N-1, endpoints added
+ * with ms_add_endpoint follow.  body = {type, msg_id, in_reply_to} (the
+ * reserved keys, doc/protocol.md:36-45) + 12 payload bytes. */
+typedef struct ms_msg {
+  uint64_t id;          /* net id, ++next-message-id (net.clj:197); first is 0 */
+  int64_t  deadline_ns; /* virtual deadline = now + latency_ms*1e6 (net.clj:202-205) */
+  uint32_t src, dest;
+  uint32_t msg_id;      /* body.msg_id,      valid iff flags & MS_F_MSG_ID */
+  uint32_t in_reply_to; /* body.in_reply_to, valid iff flags & MS_F_REPLY  */
+  uint16_t type;        /* MS_T_* */
+  uint16_t flags;
+  uint32_t p0;          /* payload: broadcast "message" / g-set "element" / error "code" / read_ok count */
+  uint64_t p1;          /* payload: opaque 8 bytes (echo) or host blob handle */
+} ms_msg;
+
+/* Body as passed by the host data plane (client/send!, client.clj:66-79). */
+typedef struct ms_body {
+  uint16_t type, flags;
+  uint32_t msg_id, in_reply_to, p0;
+  uint64_t p1;
+} ms_body;
+
+/* Journal event: replaces Event{id time type message} (net/journal.clj:53).
+ * bit 63 of event_id is the type: 0 = :send, 1 = :recv. */
+typedef struct ms_event {
+  uint64_t event_id;    /* ++next-id (journal.clj:228,236), dense from 0 */
+  int64_t  time_ns;     /* virtual time of the round (replaces linear-time-nanos, journal.clj:229) */
+  uint64_t msg_id;      /* Message.id */
+  uint32_t src, dest;
+} ms_event;
+#define MS_EVENT_RECV (1ull << 63)
+
+/* Body of the message of a journal event (journal level 2), 32 bytes. */
+typedef struct ms_jbody {
+  uint64_t id;
+  uint32_t msg_id, in_reply_to;
+  uint16_t type, flags;
+  uint32_t p0;
+  uint64_t p1;
+} ms_jbody;
+
+/* Scheduled client op: a message injected when virtual time reaches time_ns
+ * (device-resident stand-in for the Jepsen generator, core.clj:67-80). */
+typedef struct ms_op {
+  int64_t  time_ns;
+  uint32_t src, dest;
+  ms_body  body;
+} ms_op;
+
+enum { MS_F_MSG_ID = 1, MS_F_REPLY = 2 };
+
+/* body.type codes (doc/workloads.md) */
+enum {
+  MS_T_INIT = 1, MS_T_INIT_OK = 2, MS_T_ERROR = 3,
+  MS_T_ECHO = 10, MS_T_ECHO_OK = 11,
+  MS_T_TOPOLOGY = 20, MS_T_TOPOLOGY_OK = 21, MS_T_BROADCAST = 22,
+  MS_T_BROADCAST_OK = 23, MS_T_READ = 24, MS_T_READ_OK = 25,
+  MS_T_ADD = 30, MS_T_ADD_OK = 31, MS_T_REPLICATE_ONE = 32, MS_T_REPLICATE_FULL = 33
+};
+
+enum { MS_W_ECHO = 0, MS_W_BROADCAST = 1, MS_W_GSET = 2 };                  /* --workload, core.clj:36-47 */
+enum { MS_TOPO_GRID = 0, MS_TOPO_LINE = 1, MS_TOPO_TOTAL = 2,                /* --topology, broadcast.clj:169-178 */
+       MS_TOPO_TREE2 = 3, MS_TOPO_TREE3 = 4, MS_TOPO_TREE4 = 5 };
+enum { MS_DIST_CONSTANT = 0, MS_DIST_UNIFORM = 1, MS_DIST_EXPONENTIAL = 2 }; /* --latency-dist, net.clj:73-77 */
+enum { MS_KIND_SERVER = 0,      /* device-resident node program (replaces process/start-node!) */
+       MS_KIND_CLIENT = 1,      /* host-visible client, id "c<k>" (util.clj:7-10): zero latency */
+       MS_KIND_HOST = 2,        /* host-visible non-client endpoint (a JVM service, service.clj:245-263) */
+       MS_KIND_SIM_CLIENT = 3 };/* device-resident client sink (replies are counted, not mailed) */
+
+/* error codes (negative returns); MS_ERR_NODE_NOT_FOUND maps to Maelstrom error
+ * code 1 {:type ::node-not-found :definite? true} (net.clj:159-164) */
+enum {
+  MS_OK = 0,
+  MS_ERR_NODE_NOT_FOUND = -1,
+  MS_ERR_ARG = -2,
+  MS_ERR_SIM = -3,        /* device-side fault latched; see ms_last_error */
+  MS_ERR_CUDA = -4,
+  MS_ERR_CAPACITY = -5
+};
+
+/* ------------------------------------------------------------------ lifecycle */
+
+/* Replaces (net/net latency-map log-send? log-recv?) (net.clj:79-103, called once
+ * from core.clj:57-59) plus the --node-count / --topology / --latency flags. */
+typedef struct ms_config {
+  uint32_t n_nodes;          /* --node-count */
+  uint32_t workload;         /* MS_W_*: built-in transition kernel instead of --bin */
+  uint32_t topology;         /* MS_TOPO_* */
+  uint32_t latency_dist;     /* MS_DIST_* */
+  uint32_t latency_mean_ms;  /* --latency (parse-long, core.clj:171-174) */
+  uint32_t seed_lo, seed_hi; /* Philox key; the reference is unseeded */
+  double   p_loss;           /* net.clj:100 starts at 0; no CLI flag upstream */
+  uint32_t n_values;         /* size of the value universe (seen-set bitmap bits per node) */
+  uint32_t gset_interval_ms; /* g-set replication period (demo/ruby/g_set.rb:34) */
+  /* engine sizing (0 = default) */
+  uint32_t max_endpoints;    /* servers + clients + services */
+  uint32_t ring_cap;         /* per-endpoint inbox ring capacity, power of two */
+  uint32_t max_window;       /* max messages one endpoint consumes per round */
+  uint32_t journal_cap_log2; /* device journal ring = 2^k events */
+  uint32_t journal_level;    /* 0 off, 1 events, 2 events + bodies */
+  uint32_t journal_discard;  /* 1: device journal is overwritten, never drained (kernel-only runs) */
+  uint32_t calendar_slots;   /* timing-wheel slots (ticks), power of two */
+  uint32_t calendar_cap;     /* messages per wheel slot */
+  uint32_t mailbox_cap;      /* host-visible deliveries buffered between syncs */
+  uint32_t inject_cap;       /* host sends staged per round */
+  int32_t  device;           /* CUDA device ordinal */
+  uint32_t threads_per_node; /* CTA size of the round kernel (0 = auto) */
+  uint32_t reserved[8];
+} ms_config;
+
+typedef struct ms_sim ms_sim;
+
+ms_sim*     ms_create(const ms_config* cfg);
+void        ms_destroy(ms_sim* sim);
+/* per-thread text of the last failure (sim may be NULL for ms_create failures) */
+const char* ms_last_error(ms_sim* sim);
+uint32_t    ms_abi_version(void);
+
+/* process/start-node! (process.clj:168-215) / stop-node! (:217-256): select the
+ * built-in node program for all servers / retire them. */
+int ms_start_nodes(ms_sim* sim, uint32_t workload);
+int ms_stop_nodes(ms_sim* sim);
+
+/* net/add-node! / remove-node! (net.clj:139-152).  Returns the dense index. */
+int ms_add_endpoint(ms_sim* sim, const char* id, int kind);
+int ms_remove_endpoint(ms_sim* sim, uint32_t idx);
+int ms_endpoint_index(ms_sim* sim, const char* id);   /* MS_ERR_NODE_NOT_FOUND if absent */
+
+/* ------------------------------------------------------------------ data plane */
+
+/* net/send! (net.clj:189-221) for host-visible endpoints.  The message is sent at
+ * the start of the next round, in call order.  Returns the net id it will get,
+ * or MS_ERR_NODE_NOT_FOUND (net.clj:172-175). */
+int64_t ms_send(ms_sim* sim, uint32_t src, uint32_t dest, const ms_body* body);
+
+/* net/recv! (net.clj:223-247): 1 = message delivered into *out, 0 = virtual
+ * timeout elapsed, <0 error.  Advances the simulation while waiting. */
+int ms_recv(ms_sim* sim, uint32_t endpoint, int64_t timeout_virtual_ns, ms_msg* out);
+
+/* Upload a time-sorted schedule of client ops (appends). */
+int ms_schedule_ops(ms_sim* sim, const ms_op* ops, size_t n);
+
+/* ------------------------------------------------------------------ time */
+int      ms_step(ms_sim* sim, uint64_t n_rounds);       /* exactly n rounds */
+int      ms_run(ms_sim* sim, int64_t until_virtual_ns); /* rounds while now < until */
+int64_t  ms_now(ms_sim* sim);
+uint64_t ms_round(ms_sim* sim);
+
+/* ------------------------------------------------------------------ faults: jepsen-net (net.clj:105-122) */
+int ms_net_drop(ms_sim* sim, uint32_t src, uint32_t dest);   /* partitions[dest] += src */
+int ms_net_heal(ms_sim* sim);
+int ms_net_slow(ms_sim* sim);                                /* latency x10, stackable */
+int ms_net_fast(ms_sim* sim);                                /* unwrap one level; no-op when unscaled */
+int ms_net_flaky(ms_sim* sim);                               /* p-loss = 0.5 */
+/* additions with no upstream equivalent */
+int ms_net_set_loss(ms_sim* sim, double p);
+int ms_net_partition(ms_sim* sim, const uint32_t* component_id, size_t n);
+
+/* ------------------------------------------------------------------ journal: jepsen-os + net.journal */
+/* j/journal + j/close! (net.clj:128-137): stream drained events to a file. */
+int ms_journal_open(ms_sim* sim, const char* path);
+int ms_journal_close(ms_sim* sim);
+/* Copy the next events (event_id order) into caller buffers; bodies may be NULL. */
+int ms_journal_drain(ms_sim* sim, ms_event* events, ms_jbody* bodies, size_t cap, size_t* n_out);
+uint64_t ms_journal_written(ms_sim* sim);
+
+/* net.checker/basic-stats (net/checker.clj:28-41) folded on the device:
+ * out[9] = {all, clients, servers} x {send-count, recv-count, msg-count}. */
+int ms_stats(ms_sim* sim, uint64_t out[9]);
+
+/* ------------------------------------------------------------------ node state read-back */
+size_t   ms_node_set(ms_sim* sim, uint32_t node, uint32_t* values, size_t cap);
+uint64_t ms_client_replies(ms_sim* sim);
+
+/* device-side counters for roofline accounting: out = {rounds, sends, recvs,
+ * kernel launches, lost, partition_drops, max_window, reserved} */
+int ms_counters(ms_sim* sim, uint64_t out[8]);
+
+/* pure helper: neighbors of `node` under workload/broadcast.clj:40-178 */
+size_t ms_topology(uint32_t topology, uint32_t n, uint32_t node, uint32_t* out, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

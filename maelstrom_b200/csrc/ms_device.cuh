@@ -1,0 +1,185 @@
+// ms_device.cuh -- device-side data layout and pure helpers of the sm_100a
+// discrete-event engine.  Mirrors the deterministic spec in DESIGN.md section 2;
+// reference citations are relative to /root/reference.
+#pragma once
+#include <stdint.h>
+#include "../../include/maelstrom_b200.h"
+
+#if defined(__CUDACC__)
+#define MS_HD __host__ __device__ __forceinline__
+#else
+#define MS_HD inline
+#endif
+
+namespace msd {
+
+constexpr int64_t  kTickNs   = 1000000;       // latencies are integer ms (net.clj:187,204)
+constexpr uint32_t kInjector = 0xFFFFFFFFu;   // Philox "emitter" of host/scheduled sends
+constexpr uint8_t  kRemoved  = 0x80;          // endpoint kind after remove-node!
+
+// device-latched error codes (DevState.error)
+enum : uint32_t {
+  E_NONE = 0, E_RING_OVERFLOW = 1, E_WINDOW_OVERFLOW = 2, E_JOURNAL_OVERFLOW = 3,
+  E_INVALID_DEST = 4, E_LOOKBACK_TIMEOUT = 5, E_VALUE_RANGE = 6, E_MAIL_OVERFLOW = 7,
+  E_CALENDAR_OVERFLOW = 8, E_ID_RANGE = 9
+};
+
+// Mutable per-simulation scalars, resident in HBM, updated by the last CTA of
+// every round (net.clj:92-103's atom, minus the queues).
+struct DevState {
+  int64_t  now;              // virtual time, ns
+  int64_t  stop_ns;          // rounds are no-ops once now >= stop_ns
+  uint64_t round;            // round counter
+  uint64_t next_id;          // next-message-id (net.clj:103,197)
+  uint64_t next_event;       // journal next-id (journal.clj:195)
+  uint64_t journal_drained;  // events the host has consumed
+  uint64_t round_ev_total;   // totals of the round in flight (written by the last ticket)
+  uint64_t round_em_total;
+  uint64_t stats[6];         // {all,clients,servers} x {send,recv}  (net/checker.clj:28-41)
+  uint64_t lost;             // sends dropped by the loss roll (net.clj:214-215)
+  uint64_t part_drops;       // receives cut by a partition (net.clj:234)
+  uint64_t client_replies;   // replies consumed by MS_KIND_SIM_CLIENT sinks
+  uint64_t rounds_run;
+  uint32_t ticket;           // dynamic CTA -> ticket assignment
+  uint32_t done;             // CTAs finished this round
+  uint32_t zero_pending;     // messages sent this round that are due at `now`
+  uint32_t error;            // first latched E_* code
+  uint32_t error_arg;
+  uint32_t inj_count;        // host sends staged for the next round
+  uint32_t sched_cursor;     // next unscheduled op
+  uint32_t mail_count;       // host-visible deliveries since the last sync
+  uint32_t time_advanced;    // 1 when the last round moved `now`
+  uint32_t max_window_seen;
+  uint32_t cal_release;      // calendar slot to release before the next round (+1), 0 = none
+  uint32_t pad0;
+};
+
+// Fault / latency knobs mutated by jepsen-net calls between rounds (net.clj:105-122).
+struct NetParams {
+  uint64_t loss_thresh;      // (< (rand) p-loss), net.clj:214; x0 < loss_thresh
+  uint64_t exp_coeff;        // round(mean*scale*ln2*2^32)
+  uint32_t dist;             // MS_DIST_*
+  uint32_t mean_ms;
+  uint32_t scale;            // 10^k after k slow! calls
+  uint32_t pair_active;      // any drop! since the last heal!
+  uint32_t comp_active;      // bulk partition installed
+  uint32_t pad;
+};
+
+// Decoupled look-back status of one ticket (one CTA of the round kernel).
+struct __align__(16) Status {
+  uint32_t flag_agg;         // == round tag when agg_* are valid
+  uint32_t flag_inc;         // == round tag when inc_* are valid
+  uint32_t pad[2];
+  uint64_t agg_ev, agg_em;   // this CTA's events / emissions
+  uint64_t inc_ev, inc_em;   // inclusive prefix over tickets <= this one
+};
+
+struct Params {
+  DevState* st;
+  NetParams* np;
+  // endpoints
+  uint8_t*  kind;
+  uint32_t* tail;            // claim counter per endpoint ring
+  uint32_t* limit;           // snapshot of tail at the start of the round
+  uint32_t* head;            // previous snapshot: window is [head, limit)
+  uint4*    ring;            // n_ep * ring_cap * 3 vectors (48-B records)
+  uint32_t  ring_cap, ring_mask;
+  uint32_t  n_ep, n_servers, n_inj_tickets, max_window;
+  Status*   status;
+  // journal
+  uint4*    jev;             // 2 vectors per event
+  uint4*    jbody;           // 2 vectors per event (level 2)
+  uint64_t  jmask;
+  uint32_t  jlevel, jdiscard;
+  // partitions
+  uint32_t* pair_bits;       // [dest][src] bitmap, row stride pair_words
+  uint32_t  pair_words;
+  uint32_t* comp;
+  uint32_t  seed_lo, seed_hi;
+  // workload state
+  uint32_t  workload, topology, n_values, bm_words;
+  uint32_t* bitmap;          // n_servers * bm_words
+  uint32_t* nbr_off;         // CSR neighbor table (absent for MS_TOPO_TOTAL)
+  uint32_t* nbr;
+  uint32_t* next_msg_id;     // echo.rb:8
+  uint32_t* set_count;
+  // injection
+  ms_msg*   inj_buf;
+  const ms_op* sched;
+  uint32_t  n_sched;
+  const uint32_t* tick_off;  // tick_off[j] = #ops whose injection tick is < j
+  uint32_t  n_tick_off;
+  // host-visible deliveries
+  ms_msg*   mail;
+  uint32_t  mail_cap;
+  // calendar (timing wheel) for latencies > 0
+  uint4*    cal;             // cal_slots * cal_cap records
+  uint32_t* cal_count;       // per slot
+  uint32_t  cal_slots, cal_cap;
+};
+
+// ------------------------------------------------------------- Philox4x32-10
+// Salmon et al. SC'11 (the generator cuRAND names Philox_4x32_10).  Stands in
+// for the reference's unseeded (rand) / Incanter draws (net.clj:187,214).
+MS_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                         uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int i = 0; i < 10; i++) {
+    const uint64_t a = (uint64_t)0xD2511F53u * c0;
+    const uint64_t b = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(b >> 32) ^ c1 ^ k0;
+    const uint32_t n2 = (uint32_t)(a >> 32) ^ c3 ^ k1;
+    c1 = (uint32_t)b;
+    c3 = (uint32_t)a;
+    c0 = n0;
+    c2 = n2;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+MS_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umul64hi(a, b);
+#else
+  return (uint64_t)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+
+MS_HD int clz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+  return __clzll((long long)x);
+#else
+  return __builtin_clzll(x);
+#endif
+}
+
+// -log2(u) in Q32.32 for u = (X+1)/2^64; integer-only.
+MS_HD uint64_t neg_log2_q32(uint64_t X) {
+  if (X == ~0ull) return 0;
+  const uint64_t Y = X + 1;
+  const int n = 63 - clz64(Y);
+  uint64_t m = Y << (63 - n);
+  uint32_t frac = 0;
+  for (int i = 31; i >= 0; i--) {
+    const uint64_t hi = mulhi64(m, m);
+    if (hi >> 63) { frac |= (1u << i); m = hi; }
+    else          { m = hi << 1; }
+  }
+  return (64ull << 32) - (((uint64_t)n << 32) | frac);
+}
+
+// latency in ms for a server<->server message (net.clj:65-77,178-187)
+MS_HD uint64_t latency_ms(const NetParams& np, const uint32_t x[4]) {
+  if (np.dist == MS_DIST_CONSTANT) return (uint64_t)np.mean_ms * np.scale;
+  if (np.dist == MS_DIST_UNIFORM)
+    return (((uint64_t)x[1] * (2ull * np.mean_ms)) >> 32) * np.scale;
+  const uint64_t X = ((uint64_t)x[2] << 32) | x[1];
+  return mulhi64(neg_log2_q32(X), np.exp_coeff);
+}
+
+MS_HD bool kind_is_client(uint8_t k) { return k == MS_KIND_CLIENT || k == MS_KIND_SIM_CLIENT; }
+
+}  // namespace msd

@@ -1,0 +1,722 @@
+// ms_engine.cu -- host side of the C ABI declared in include/maelstrom_b200.h.
+// Owns device memory, the endpoint registry, the fault knobs and the round
+// loop; all simulation work happens in ms_kernels.cu.  There is no CPU
+// fallback: without a usable CUDA device ms_create fails.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <deque>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "ms_device.cuh"
+
+using namespace msd;
+
+extern "C" {
+cudaError_t msk_round_smem_attr(size_t bytes);
+void msk_launch_round(const msd::Params* p, int threads, size_t smem, int with_release, cudaStream_t s);
+void msk_set_bit(uint32_t* words, size_t word, uint32_t bit, cudaStream_t s);
+}
+
+static thread_local std::string g_err;
+
+static void set_err(const std::string& s) { g_err = s; }
+
+#define CK(call)                                                                      \
+  do {                                                                                \
+    cudaError_t e__ = (call);                                                         \
+    if (e__ != cudaSuccess) {                                                         \
+      set_err(std::string(#call) + ": " + cudaGetErrorString(e__));                   \
+      return MS_ERR_CUDA;                                                             \
+    }                                                                                 \
+  } while (0)
+
+static uint32_t pow2_at_least(uint32_t x) {
+  uint32_t p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+static const char* dev_error_text(uint32_t code) {
+  switch (code) {
+    case E_RING_OVERFLOW: return "inbox ring overflow (raise ms_config.ring_cap) at endpoint";
+    case E_WINDOW_OVERFLOW: return "per-round window exceeds ms_config.max_window at endpoint";
+    case E_JOURNAL_OVERFLOW: return "journal ring overflow (drain more often or raise journal_cap_log2)";
+    case E_INVALID_DEST: return "Invalid dest for message (net.clj:174): endpoint";
+    case E_LOOKBACK_TIMEOUT: return "look-back timeout at ticket";
+    case E_VALUE_RANGE: return "broadcast value out of range (raise ms_config.n_values): value";
+    case E_MAIL_OVERFLOW: return "host mailbox overflow (raise ms_config.mailbox_cap) at endpoint";
+    case E_CALENDAR_OVERFLOW: return "timing wheel overflow (raise calendar_slots/calendar_cap): arg";
+    case E_ID_RANGE: return "message id exceeds 2^48 at endpoint";
+  }
+  return "unknown device error";
+}
+
+// workload/broadcast.clj:40-178, restated for the device neighbor table.
+static void topo_neighbors(uint32_t topo, uint32_t n, uint32_t k, std::vector<uint32_t>& out) {
+  out.clear();
+  if (k >= n) return;
+  if (topo == MS_TOPO_GRID) {
+    uint32_t side = (uint32_t)ceil(sqrt((double)n));
+    if (side == 0) side = 1;
+    const int64_t i = k / side, j = k % side;
+    const int64_t di[4] = {1, -1, 0, 0}, dj[4] = {0, 0, 1, -1};   // (i+1,j) (i-1,j) (i,j+1) (i,j-1), :60-63
+    for (int d = 0; d < 4; d++) {
+      const int64_t a = i + di[d], b = j + dj[d];
+      if (a < 0 || b < 0 || b >= (int64_t)side) continue;
+      const int64_t idx = a * side + b;
+      if (idx < (int64_t)n) out.push_back((uint32_t)idx);
+    }
+  } else if (topo == MS_TOPO_LINE) {
+    if (n < 2) return;
+    if (k > 0 && k < n - 1) { out.push_back(k - 1); out.push_back(k + 1); }
+    else if (k == 0) out.push_back(1);
+    else out.push_back(n - 2);
+  } else if (topo == MS_TOPO_TOTAL) {
+    for (uint32_t i = 0; i < n; i++) if (i != k) out.push_back(i);
+  } else {
+    const uint32_t b = topo == MS_TOPO_TREE2 ? 2 : topo == MS_TOPO_TREE3 ? 3 : 4;
+    if (k) out.push_back((k - 1) / b);
+    for (uint32_t c = 1; c <= b; c++) {
+      const uint64_t ch = (uint64_t)b * k + c;
+      if (ch < n) out.push_back((uint32_t)ch);
+    }
+  }
+}
+
+struct ms_sim {
+  std::mutex mu;
+  ms_config cfg;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  Params P;                 // by-value kernel parameters (pointers + sizing)
+  NetParams np;             // host mirror of the device knobs
+  DevState hs;              // host mirror of the device state (valid after sync_state)
+  int threads = 128;
+  size_t smem = 0;
+  bool use_calendar = false;
+  uint64_t launches = 0;
+
+  std::vector<uint8_t> kinds;
+  std::vector<std::string> names;
+  std::unordered_map<std::string, uint32_t> by_name;
+  std::vector<std::deque<ms_msg>> mailbox;
+  std::vector<ms_msg> pending;      // host sends not yet staged
+  std::vector<ms_op> sched;
+  ms_op* d_sched = nullptr;
+  uint32_t* d_tick_off = nullptr;
+  size_t d_sched_cap = 0, d_tick_cap = 0;
+  bool pair_alloc = false;
+  FILE* jfile = nullptr;
+  std::vector<void*> allocs;
+
+  template <typename T>
+  int dalloc(T** out, size_t count) {
+    void* ptr = nullptr;
+    const size_t bytes = std::max<size_t>(count * sizeof(T), 16);
+    CK(cudaMalloc(&ptr, bytes));
+    CK(cudaMemsetAsync(ptr, 0, bytes, stream));
+    allocs.push_back(ptr);
+    *out = (T*)ptr;
+    return MS_OK;
+  }
+
+  int push_np() {
+    CK(cudaMemcpyAsync(P.np, &np, sizeof(np), cudaMemcpyHostToDevice, stream));
+    return MS_OK;
+  }
+
+  int sync_state() {
+    CK(cudaMemcpyAsync(&hs, P.st, sizeof(DevState), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (hs.mail_count) {
+      const uint32_t n = std::min(hs.mail_count, P.mail_cap);
+      std::vector<ms_msg> buf(n);
+      CK(cudaMemcpy(buf.data(), P.mail, (size_t)n * sizeof(ms_msg), cudaMemcpyDeviceToHost));
+      for (const ms_msg& m : buf)
+        if (m.dest < mailbox.size()) mailbox[m.dest].push_back(m);
+      const uint32_t zero = 0;
+      CK(cudaMemcpy(&P.st->mail_count, &zero, sizeof(zero), cudaMemcpyHostToDevice));
+      hs.mail_count = 0;
+    }
+    if (hs.error) {
+      char buf[256];
+      snprintf(buf, sizeof buf, "%s %u (round %llu)", dev_error_text(hs.error), hs.error_arg,
+               (unsigned long long)hs.round);
+      set_err(buf);
+      return MS_ERR_SIM;
+    }
+    return MS_OK;
+  }
+
+  int stage_injections() {
+    if (pending.empty()) return MS_OK;
+    if (pending.size() > cfg.inject_cap) { set_err("too many host sends staged for one round (inject_cap)"); return MS_ERR_CAPACITY; }
+    const uint32_t n = (uint32_t)pending.size();
+    CK(cudaMemcpyAsync(P.inj_buf, pending.data(), (size_t)n * sizeof(ms_msg), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(&P.st->inj_count, &n, sizeof(n), cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));   // `pending` is pageable host memory
+    pending.clear();
+    return MS_OK;
+  }
+
+  int set_stop(int64_t stop) {
+    CK(cudaMemcpyAsync(&P.st->stop_ns, &stop, sizeof(stop), cudaMemcpyHostToDevice, stream));
+    return MS_OK;
+  }
+
+  void launch_rounds(uint64_t n) {
+    for (uint64_t i = 0; i < n; i++) {
+      msk_launch_round(&P, threads, smem, use_calendar ? 1 : 0, stream);
+      launches += use_calendar ? 3 : 2;
+    }
+  }
+
+  int maybe_flush_journal_file() {
+    if (!jfile || cfg.journal_discard || cfg.journal_level == 0) return MS_OK;
+    const uint64_t cap = P.jmask + 1;
+    if (hs.next_event - hs.journal_drained < cap / 2) return MS_OK;
+    return flush_journal_file();
+  }
+
+  int drain(ms_event* ev, ms_jbody* bodies, size_t cap, size_t* n_out) {
+    *n_out = 0;
+    if (cfg.journal_level == 0 || cfg.journal_discard) return MS_OK;
+    const uint64_t avail = hs.next_event - hs.journal_drained;
+    const size_t n = (size_t)std::min<uint64_t>(avail, cap);
+    if (n == 0) return MS_OK;
+    const uint64_t J = P.jmask + 1;
+    const uint64_t start = hs.journal_drained & P.jmask;
+    const size_t first = (size_t)std::min<uint64_t>(n, J - start);
+    CK(cudaMemcpy(ev, (const char*)P.jev + start * 32, first * 32, cudaMemcpyDeviceToHost));
+    if (first < n) CK(cudaMemcpy(ev + first, P.jev, (n - first) * 32, cudaMemcpyDeviceToHost));
+    if (bodies && cfg.journal_level >= 2) {
+      CK(cudaMemcpy(bodies, (const char*)P.jbody + start * 32, first * 32, cudaMemcpyDeviceToHost));
+      if (first < n) CK(cudaMemcpy(bodies + first, P.jbody, (n - first) * 32, cudaMemcpyDeviceToHost));
+    }
+    hs.journal_drained += n;
+    CK(cudaMemcpy(&P.st->journal_drained, &hs.journal_drained, sizeof(uint64_t), cudaMemcpyHostToDevice));
+    *n_out = n;
+    return MS_OK;
+  }
+
+  int flush_journal_file() {
+    if (!jfile) return MS_OK;
+    std::vector<ms_event> ev(1 << 16);
+    std::vector<ms_jbody> bd(cfg.journal_level >= 2 ? (1 << 16) : 0);
+    for (;;) {
+      size_t n = 0;
+      const int rc = drain(ev.data(), bd.empty() ? nullptr : bd.data(), ev.size(), &n);
+      if (rc) return rc;
+      if (!n) break;
+      for (size_t i = 0; i < n; i++) {
+        fwrite(&ev[i], sizeof(ms_event), 1, jfile);
+        if (!bd.empty()) fwrite(&bd[i], sizeof(ms_jbody), 1, jfile);
+      }
+    }
+    fflush(jfile);
+    return MS_OK;
+  }
+
+  int upload_schedule() {
+    const size_t n = sched.size();
+    if (n > d_sched_cap) {
+      const size_t cap = std::max<size_t>(n, d_sched_cap * 2);
+      ms_op* nd = nullptr;
+      CK(cudaMalloc((void**)&nd, cap * sizeof(ms_op)));
+      if (d_sched) cudaFree(d_sched);
+      d_sched = nd;
+      d_sched_cap = cap;
+    }
+    if (n) CK(cudaMemcpy(d_sched, sched.data(), n * sizeof(ms_op), cudaMemcpyHostToDevice));
+    // tick_off[j] = number of ops whose injection tick ceil(time/tick) is < j
+    const int64_t last = n ? sched.back().time_ns : 0;
+    const size_t n_ticks = (size_t)((last + kTickNs - 1) / kTickNs) + 2;
+    std::vector<uint32_t> off(n_ticks + 1, 0);
+    for (const ms_op& op : sched) {
+      const int64_t t = op.time_ns <= 0 ? 0 : (op.time_ns + kTickNs - 1) / kTickNs;
+      off[(size_t)t + 1]++;
+    }
+    for (size_t j = 1; j < off.size(); j++) off[j] += off[j - 1];
+    if (off.size() > d_tick_cap) {
+      const size_t cap = std::max<size_t>(off.size(), d_tick_cap * 2);
+      uint32_t* nd = nullptr;
+      CK(cudaMalloc((void**)&nd, cap * sizeof(uint32_t)));
+      if (d_tick_off) cudaFree(d_tick_off);
+      d_tick_off = nd;
+      d_tick_cap = cap;
+    }
+    CK(cudaMemcpy(d_tick_off, off.data(), off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    P.sched = d_sched;
+    P.n_sched = (uint32_t)n;
+    P.tick_off = d_tick_off;
+    P.n_tick_off = (uint32_t)off.size();
+    return MS_OK;
+  }
+};
+
+static int build_sim(ms_sim* s, const ms_config* in) {
+  ms_config& c = s->cfg;
+  c = *in;
+  if (c.n_nodes == 0) { set_err("n_nodes must be positive (--node-count)"); return MS_ERR_ARG; }
+  if (c.workload > MS_W_GSET || c.topology > MS_TOPO_TREE4 || c.latency_dist > MS_DIST_EXPONENTIAL) {
+    set_err("bad workload/topology/latency_dist");
+    return MS_ERR_ARG;
+  }
+  if (c.latency_dist != MS_DIST_CONSTANT && c.latency_mean_ms == 0) {
+    // (exponential-distribution (/ 0)) divides by zero; (integer-distribution 0 0) is empty (net.clj:76-77)
+    set_err("latency mean 0 is only valid with the constant distribution");
+    return MS_ERR_ARG;
+  }
+  if (!c.n_values) c.n_values = 1u << 16;
+  if (!c.max_endpoints) c.max_endpoints = c.n_nodes + 256;
+  if (c.max_endpoints < c.n_nodes) { set_err("max_endpoints < n_nodes"); return MS_ERR_ARG; }
+  c.ring_cap = pow2_at_least(c.ring_cap ? c.ring_cap : 1024);
+  c.max_window = pow2_at_least(c.max_window ? c.max_window : std::min<uint32_t>(c.ring_cap, 1024));
+  if (c.max_window > 32768) { set_err("max_window must be <= 32768"); return MS_ERR_ARG; }
+  if (c.max_window > c.ring_cap) c.max_window = c.ring_cap;
+  if (!c.journal_cap_log2) c.journal_cap_log2 = 22;
+  if (c.journal_level > 2) c.journal_level = 2;
+  if (!c.mailbox_cap) c.mailbox_cap = 1u << 16;
+  if (!c.inject_cap) c.inject_cap = 1u << 16;
+  if (!c.gset_interval_ms) c.gset_interval_ms = 5000;
+  s->use_calendar = c.latency_mean_ms > 0;
+  if (s->use_calendar) {
+    c.calendar_slots = pow2_at_least(c.calendar_slots ? c.calendar_slots
+                                                      : std::min<uint32_t>(16384u, std::max<uint32_t>(64u, 32u * c.latency_mean_ms)));
+    if (!c.calendar_cap) c.calendar_cap = 1u << 16;
+  }
+  s->threads = c.threads_per_node ? (int)c.threads_per_node
+                                  : (c.max_window >= 2048 ? 512 : c.max_window >= 512 ? 256 : 128);
+  if (s->threads % 32 || s->threads > 512 || s->threads < 32) { set_err("threads_per_node must be a multiple of 32 in [32,512]"); return MS_ERR_ARG; }
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_err("no CUDA device: maelstrom_b200 has no CPU fallback");
+    return MS_ERR_CUDA;
+  }
+  s->device = c.device;
+  CK(cudaSetDevice(s->device));
+  CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+
+  Params& P = s->P;
+  memset(&P, 0, sizeof P);
+  const uint32_t M = c.max_endpoints;
+  int rc;
+  if ((rc = s->dalloc(&P.st, 1))) return rc;
+  if ((rc = s->dalloc(&P.np, 1))) return rc;
+  if ((rc = s->dalloc(&P.kind, M))) return rc;
+  if ((rc = s->dalloc(&P.tail, M))) return rc;
+  if ((rc = s->dalloc(&P.limit, M))) return rc;
+  if ((rc = s->dalloc(&P.head, M))) return rc;
+  {
+    void* ptr = nullptr;
+    CK(cudaMalloc(&ptr, (size_t)M * c.ring_cap * 48));
+    s->allocs.push_back(ptr);
+    P.ring = (uint4*)ptr;
+  }
+  P.ring_cap = c.ring_cap;
+  P.ring_mask = c.ring_cap - 1;
+  P.n_servers = c.n_nodes;
+  P.n_ep = c.n_nodes;
+  P.n_inj_tickets = 8;
+  P.max_window = c.max_window;
+  if ((rc = s->dalloc(&P.status, (size_t)M + P.n_inj_tickets))) return rc;
+  P.jlevel = c.journal_level;
+  P.jdiscard = c.journal_discard;
+  if (c.journal_level) {
+    const uint64_t J = 1ull << c.journal_cap_log2;
+    void* ptr = nullptr;
+    CK(cudaMalloc(&ptr, J * 32));
+    s->allocs.push_back(ptr);
+    P.jev = (uint4*)ptr;
+    P.jmask = J - 1;
+    if (c.journal_level >= 2) {
+      CK(cudaMalloc(&ptr, J * 32));
+      s->allocs.push_back(ptr);
+      P.jbody = (uint4*)ptr;
+    }
+  }
+  if ((rc = s->dalloc(&P.comp, M))) return rc;
+  P.seed_lo = c.seed_lo;
+  P.seed_hi = c.seed_hi;
+  P.workload = c.workload;
+  P.topology = c.topology;
+  P.n_values = c.n_values;
+  P.bm_words = (c.n_values + 31) / 32;
+  if (c.workload != MS_W_ECHO) {
+    if ((rc = s->dalloc(&P.bitmap, (size_t)c.n_nodes * P.bm_words))) return rc;
+    if ((rc = s->dalloc(&P.set_count, c.n_nodes))) return rc;
+    if (c.topology != MS_TOPO_TOTAL) {
+      std::vector<uint32_t> off(c.n_nodes + 1, 0), nbr, tmp;
+      for (uint32_t k = 0; k < c.n_nodes; k++) {
+        topo_neighbors(c.topology, c.n_nodes, k, tmp);
+        nbr.insert(nbr.end(), tmp.begin(), tmp.end());
+        off[k + 1] = (uint32_t)nbr.size();
+      }
+      if ((rc = s->dalloc(&P.nbr_off, off.size()))) return rc;
+      if ((rc = s->dalloc(&P.nbr, nbr.size() + 1))) return rc;
+      CK(cudaMemcpyAsync(P.nbr_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice, s->stream));
+      if (!nbr.empty()) CK(cudaMemcpyAsync(P.nbr, nbr.data(), nbr.size() * 4, cudaMemcpyHostToDevice, s->stream));
+      CK(cudaStreamSynchronize(s->stream));
+    }
+  } else {
+    if ((rc = s->dalloc(&P.next_msg_id, c.n_nodes))) return rc;
+  }
+  if ((rc = s->dalloc(&P.inj_buf, c.inject_cap))) return rc;
+  if ((rc = s->dalloc(&P.mail, c.mailbox_cap))) return rc;
+  P.mail_cap = c.mailbox_cap;
+  if (s->use_calendar) {
+    void* ptr = nullptr;
+    CK(cudaMalloc(&ptr, (size_t)c.calendar_slots * c.calendar_cap * 48));
+    s->allocs.push_back(ptr);
+    P.cal = (uint4*)ptr;
+    if ((rc = s->dalloc(&P.cal_count, c.calendar_slots))) return rc;
+    P.cal_slots = c.calendar_slots;
+    P.cal_cap = c.calendar_cap;
+  }
+
+  // endpoints: servers n0..n{N-1} (core.clj:231-238)
+  s->kinds.assign(M, kRemoved);
+  s->names.resize(c.n_nodes);
+  s->mailbox.resize(c.n_nodes);
+  for (uint32_t i = 0; i < c.n_nodes; i++) {
+    s->kinds[i] = MS_KIND_SERVER;
+    s->names[i] = "n" + std::to_string(i);
+    s->by_name[s->names[i]] = i;
+  }
+  CK(cudaMemcpyAsync(P.kind, s->kinds.data(), M, cudaMemcpyHostToDevice, s->stream));
+
+  memset(&s->np, 0, sizeof s->np);
+  s->np.dist = c.latency_dist;
+  s->np.mean_ms = c.latency_mean_ms;
+  s->np.scale = 1;
+  s->np.exp_coeff = (uint64_t)llround((double)c.latency_mean_ms * 1.0 * 0.693147180559945309417232121458 * 4294967296.0);
+  {
+    const double p = c.p_loss;
+    s->np.loss_thresh = !(p > 0.0) ? 0 : (p >= 1.0 ? (1ull << 32) : (uint64_t)(p * 4294967296.0));
+  }
+  if ((rc = s->push_np())) return rc;
+
+  memset(&s->hs, 0, sizeof s->hs);
+  s->hs.stop_ns = INT64_MAX;
+  CK(cudaMemcpyAsync(P.st, &s->hs, sizeof(DevState), cudaMemcpyHostToDevice, s->stream));
+
+  s->smem = (size_t)c.max_window * (8 + 16 + 16) + 64;
+  CK(msk_round_smem_attr(s->smem));
+  CK(cudaStreamSynchronize(s->stream));
+  return MS_OK;
+}
+
+static void recompute_exp(ms_sim* s) {
+  s->np.exp_coeff = (uint64_t)llround((double)s->np.mean_ms * (double)s->np.scale * 0.693147180559945309417232121458 * 4294967296.0);
+}
+
+extern "C" {
+
+uint32_t ms_abi_version(void) { return MS_ABI_VERSION; }
+
+const char* ms_last_error(ms_sim*) { return g_err.c_str(); }
+
+ms_sim* ms_create(const ms_config* cfg) {
+  if (!cfg) { set_err("null config"); return nullptr; }
+  ms_sim* s = new ms_sim();
+  if (build_sim(s, cfg) != MS_OK) {
+    const std::string keep = g_err;
+    ms_destroy(s);
+    g_err = keep;
+    return nullptr;
+  }
+  return s;
+}
+
+void ms_destroy(ms_sim* s) {
+  if (!s) return;
+  if (s->jfile) ms_journal_close(s);
+  cudaSetDevice(s->device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  for (void* p : s->allocs) cudaFree(p);
+  if (s->d_sched) cudaFree(s->d_sched);
+  if (s->d_tick_off) cudaFree(s->d_tick_off);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+int ms_start_nodes(ms_sim* s, uint32_t workload) {
+  std::lock_guard<std::mutex> g(s->mu);
+  if (workload != s->cfg.workload) {
+    set_err("ms_start_nodes: workload differs from ms_config.workload (node state is sized at ms_create)");
+    return MS_ERR_ARG;
+  }
+  return MS_OK;
+}
+
+int ms_stop_nodes(ms_sim* s) {
+  std::lock_guard<std::mutex> g(s->mu);
+  cudaSetDevice(s->device);
+  for (uint32_t i = 0; i < s->cfg.n_nodes; i++) {
+    if (s->kinds[i] != kRemoved) { s->by_name.erase(s->names[i]); s->kinds[i] = kRemoved; }
+  }
+  CK(cudaMemcpy(s->P.kind, s->kinds.data(), s->cfg.n_nodes, cudaMemcpyHostToDevice));
+  return MS_OK;
+}
+
+int ms_add_endpoint(ms_sim* s, const char* id, int kind) {
+  std::lock_guard<std::mutex> g(s->mu);
+  cudaSetDevice(s->device);
+  if (!id || kind < MS_KIND_CLIENT || kind > MS_KIND_SIM_CLIENT) { set_err("bad endpoint id/kind"); return MS_ERR_ARG; }
+  if (s->by_name.count(id)) { set_err("endpoint already exists"); return MS_ERR_ARG; }
+  const uint32_t idx = s->P.n_ep;
+  if (idx >= s->cfg.max_endpoints) { set_err("max_endpoints exhausted"); return MS_ERR_CAPACITY; }
+  s->kinds[idx] = (uint8_t)kind;
+  s->names.push_back(id);
+  s->mailbox.emplace_back();
+  s->by_name[id] = idx;
+  s->P.n_ep = idx + 1;
+  CK(cudaMemcpy(s->P.kind + idx, &s->kinds[idx], 1, cudaMemcpyHostToDevice));
+  return (int)idx;
+}
+
+int ms_remove_endpoint(ms_sim* s, uint32_t idx) {
+  std::lock_guard<std::mutex> g(s->mu);
+  cudaSetDevice(s->device);
+  if (idx >= s->P.n_ep || s->kinds[idx] == kRemoved) { set_err("No such node in network"); return MS_ERR_NODE_NOT_FOUND; }
+  s->by_name.erase(s->names[idx]);
+  s->kinds[idx] = kRemoved;
+  CK(cudaMemcpy(s->P.kind + idx, &s->kinds[idx], 1, cudaMemcpyHostToDevice));
+  return MS_OK;
+}
+
+int ms_endpoint_index(ms_sim* s, const char* id) {
+  std::lock_guard<std::mutex> g(s->mu);
+  auto it = s->by_name.find(id ? id : "");
+  if (it == s->by_name.end()) { set_err(std::string("No such node in network: ") + (id ? id : "")); return MS_ERR_NODE_NOT_FOUND; }
+  return (int)it->second;
+}
+
+int64_t ms_send(ms_sim* s, uint32_t src, uint32_t dest, const ms_body* b) {
+  std::lock_guard<std::mutex> g(s->mu);
+  if (src >= s->P.n_ep || s->kinds[src] == kRemoved) { set_err("Invalid source for message"); return MS_ERR_NODE_NOT_FOUND; }
+  if (dest >= s->P.n_ep || s->kinds[dest] == kRemoved) { set_err("Invalid dest for message"); return MS_ERR_NODE_NOT_FOUND; }
+  if (!b) { set_err("null body"); return MS_ERR_ARG; }
+  ms_msg m;
+  memset(&m, 0, sizeof m);
+  m.src = src; m.dest = dest; m.type = b->type; m.flags = b->flags;
+  m.msg_id = b->msg_id; m.in_reply_to = b->in_reply_to; m.p0 = b->p0; m.p1 = b->p1;
+  s->pending.push_back(m);
+  return (int64_t)(s->hs.next_id + s->pending.size() - 1);
+}
+
+int ms_schedule_ops(ms_sim* s, const ms_op* ops, size_t n) {
+  std::lock_guard<std::mutex> g(s->mu);
+  cudaSetDevice(s->device);
+  for (size_t i = 0; i < n; i++) {
+    if (!s->sched.empty() && ops[i].time_ns < s->sched.back().time_ns) { set_err("ops must be sorted by time"); return MS_ERR_ARG; }
+    if (ops[i].src >= s->P.n_ep || ops[i].dest >= s->P.n_ep || s->kinds[ops[i].src] == kRemoved ||
+        s->kinds[ops[i].dest] == kRemoved) { set_err("scheduled op names an unknown endpoint"); return MS_ERR_NODE_NOT_FOUND; }
+    s->sched.push_back(ops[i]);
+  }
+  CK(cudaStreamSynchronize(s->stream));
+  return s->upload_schedule();
+}
+
+static int step_locked(ms_sim* s, uint64_t n_rounds, int64_t stop) {
+  cudaSetDevice(s->device);
+  int rc;
+  if ((rc = s->stage_injections())) return rc;
+  if ((rc = s->set_stop(stop))) return rc;
+  s->launch_rounds(n_rounds);
+  if ((rc = s->sync_state())) return rc;
+  return s->maybe_flush_journal_file();
+}
+
+int ms_step(ms_sim* s, uint64_t n_rounds) {
+  std::lock_guard<std::mutex> g(s->mu);
+  // bounded batches so the journal file / mailbox keep up
+  while (n_rounds) {
+    const uint64_t b = std::min<uint64_t>(n_rounds, 64);
+    const int rc = step_locked(s, b, INT64_MAX);
+    if (rc) return rc;
+    n_rounds -= b;
+  }
+  return MS_OK;
+}
+
+int ms_run(ms_sim* s, int64_t until) {
+  std::lock_guard<std::mutex> g(s->mu);
+  while (s->hs.now < until) {
+    const int rc = step_locked(s, 32, until);
+    if (rc) return rc;
+  }
+  return MS_OK;
+}
+
+int ms_recv(ms_sim* s, uint32_t e, int64_t timeout, ms_msg* out) {
+  std::lock_guard<std::mutex> g(s->mu);
+  if (e >= s->P.n_ep || s->kinds[e] == kRemoved) { set_err("No such node in network"); return MS_ERR_NODE_NOT_FOUND; }
+  const int64_t give_up = (timeout > INT64_MAX - s->hs.now) ? INT64_MAX : s->hs.now + timeout;
+  for (;;) {
+    if (!s->mailbox[e].empty()) {
+      *out = s->mailbox[e].front();
+      s->mailbox[e].pop_front();
+      return 1;
+    }
+    if (s->hs.now >= give_up) return 0;
+    const int rc = step_locked(s, 1, INT64_MAX);
+    if (rc) return rc;
+  }
+}
+
+int64_t ms_now(ms_sim* s) { std::lock_guard<std::mutex> g(s->mu); return s->hs.now; }
+uint64_t ms_round(ms_sim* s) { std::lock_guard<std::mutex> g(s->mu); return s->hs.round; }
+
+int ms_net_drop(ms_sim* s, uint32_t src, uint32_t dest) {
+  std::lock_guard<std::mutex> g(s->mu);
+  cudaSetDevice(s->device);
+  const uint32_t M = s->cfg.max_endpoints;
+  if (src >= M || dest >= M) { set_err("drop!: endpoint out of range"); return MS_ERR_ARG; }
+  if (!s->pair_alloc) {
+    if (M > 65536) { set_err("pairwise drop! needs max_endpoints <= 65536; use ms_net_partition"); return MS_ERR_CAPACITY; }
+    s->P.pair_words = (M + 31) / 32;
+    int rc = s->dalloc(&s->P.pair_bits, (size_t)M * s->P.pair_words);
+    if (rc) return rc;
+    s->pair_alloc = true;
+  }
+  msk_set_bit(s->P.pair_bits, (size_t)dest * s->P.pair_words + (src >> 5), src & 31, s->stream);
+  s->np.pair_active = 1;
+  return s->push_np();
+}
+
+int ms_net_heal(ms_sim* s) {
+  std::lock_guard<std::mutex> g(s->mu);
+  cudaSetDevice(s->device);
+  if (s->pair_alloc && s->np.pair_active)
+    CK(cudaMemsetAsync(s->P.pair_bits, 0, (size_t)s->cfg.max_endpoints * s->P.pair_words * 4, s->stream));
+  s->np.pair_active = 0;
+  s->np.comp_active = 0;
+  return s->push_np();
+}
+
+int ms_net_slow(ms_sim* s) {
+  std::lock_guard<std::mutex> g(s->mu);
+  cudaSetDevice(s->device);
+  if (s->np.scale > 100000000u) { set_err("slow!: scale overflow"); return MS_ERR_ARG; }
+  s->np.scale *= 10;
+  recompute_exp(s);
+  return s->push_np();
+}
+
+int ms_net_fast(ms_sim* s) {
+  std::lock_guard<std::mutex> g(s->mu);
+  cudaSetDevice(s->device);
+  if (s->np.scale >= 10) s->np.scale /= 10;
+  recompute_exp(s);
+  return s->push_np();
+}
+
+static int set_loss_locked(ms_sim* s, double p) {
+  cudaSetDevice(s->device);
+  s->np.loss_thresh = !(p > 0.0) ? 0 : (p >= 1.0 ? (1ull << 32) : (uint64_t)(p * 4294967296.0));
+  return s->push_np();
+}
+
+int ms_net_flaky(ms_sim* s) { std::lock_guard<std::mutex> g(s->mu); return set_loss_locked(s, 0.5); }
+int ms_net_set_loss(ms_sim* s, double p) { std::lock_guard<std::mutex> g(s->mu); return set_loss_locked(s, p); }
+
+int ms_net_partition(ms_sim* s, const uint32_t* comp, size_t n) {
+  std::lock_guard<std::mutex> g(s->mu);
+  cudaSetDevice(s->device);
+  if (n > s->cfg.max_endpoints) { set_err("partition vector longer than max_endpoints"); return MS_ERR_ARG; }
+  std::vector<uint32_t> full(s->cfg.max_endpoints, 0);
+  // endpoints not listed (index >= n) carry 0xFFFFFFFF = "never cut" (clients keep talking to every node)
+  for (size_t i = 0; i < n; i++) full[i] = comp[i];
+  for (size_t i = n; i < full.size(); i++) full[i] = 0xFFFFFFFFu;
+  CK(cudaMemcpy(s->P.comp, full.data(), full.size() * 4, cudaMemcpyHostToDevice));
+  s->np.comp_active = 1;
+  return s->push_np();
+}
+
+int ms_journal_open(ms_sim* s, const char* path) {
+  std::lock_guard<std::mutex> g(s->mu);
+  if (s->jfile) fclose(s->jfile);
+  s->jfile = fopen(path, "wb");
+  if (!s->jfile) { set_err(std::string("cannot open journal file ") + path); return MS_ERR_ARG; }
+  const uint32_t hdr[4] = {0x314A534Du /* "MSJ1" */, s->cfg.journal_level, (uint32_t)sizeof(ms_event), (uint32_t)sizeof(ms_jbody)};
+  fwrite(hdr, sizeof hdr, 1, s->jfile);
+  return MS_OK;
+}
+
+int ms_journal_close(ms_sim* s) {
+  std::lock_guard<std::mutex> g(s->mu);
+  if (!s->jfile) return MS_OK;
+  cudaSetDevice(s->device);
+  const int rc = s->flush_journal_file();
+  fclose(s->jfile);
+  s->jfile = nullptr;
+  return rc;
+}
+
+int ms_journal_drain(ms_sim* s, ms_event* ev, ms_jbody* bodies, size_t cap, size_t* n_out) {
+  std::lock_guard<std::mutex> g(s->mu);
+  cudaSetDevice(s->device);
+  size_t n = 0;
+  const int rc = s->drain(ev, bodies, cap, &n);
+  if (n_out) *n_out = n;
+  return rc;
+}
+
+uint64_t ms_journal_written(ms_sim* s) { std::lock_guard<std::mutex> g(s->mu); return s->hs.next_event; }
+
+int ms_stats(ms_sim* s, uint64_t out[9]) {
+  std::lock_guard<std::mutex> g(s->mu);
+  for (int c = 0; c < 3; c++) {
+    out[c * 3 + 0] = s->hs.stats[c * 2 + 0];
+    out[c * 3 + 1] = s->hs.stats[c * 2 + 1];
+    out[c * 3 + 2] = s->hs.stats[c * 2 + 0];   // every id has exactly one :send, so msg-count == send-count
+  }
+  return MS_OK;
+}
+
+size_t ms_node_set(ms_sim* s, uint32_t node, uint32_t* values, size_t cap) {
+  std::lock_guard<std::mutex> g(s->mu);
+  cudaSetDevice(s->device);
+  if (node >= s->cfg.n_nodes || !s->P.bitmap) return 0;
+  std::vector<uint32_t> w(s->P.bm_words);
+  if (cudaMemcpy(w.data(), s->P.bitmap + (size_t)node * s->P.bm_words, w.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return 0;
+  size_t n = 0;
+  for (uint32_t i = 0; i < s->P.bm_words; i++)
+    for (uint32_t b = 0; b < 32; b++)
+      if ((w[i] >> b) & 1u) { if (values && n < cap) values[n] = i * 32 + b; n++; }
+  return n;
+}
+
+uint64_t ms_client_replies(ms_sim* s) { std::lock_guard<std::mutex> g(s->mu); return s->hs.client_replies; }
+
+int ms_counters(ms_sim* s, uint64_t out[8]) {
+  std::lock_guard<std::mutex> g(s->mu);
+  out[0] = s->hs.rounds_run;
+  out[1] = s->hs.stats[0];
+  out[2] = s->hs.stats[1];
+  out[3] = s->launches;
+  out[4] = s->hs.lost;
+  out[5] = s->hs.part_drops;
+  out[6] = s->hs.max_window_seen;
+  out[7] = 0;
+  return MS_OK;
+}
+
+size_t ms_topology(uint32_t topology, uint32_t n, uint32_t node, uint32_t* out, size_t cap) {
+  std::vector<uint32_t> nb;
+  topo_neighbors(topology, n, node, nb);
+  for (size_t i = 0; i < nb.size() && i < cap; i++) out[i] = nb[i];
+  return nb.size();
+}
+
+}  // extern "C"

@@ -1,0 +1,199 @@
+"""Object wrapper over the C ABI (include/maelstrom_b200.h).  Method names
+follow the ABI entry points, which in turn follow maelstrom.net's public
+functions (src/maelstrom/net.clj:79-247)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import Body, Config, EVENT_DTYPE, JBODY_DTYPE, MSG_DTYPE, OP_DTYPE  # noqa: F401
+
+WORKLOADS = {"echo": 0, "broadcast": 1, "g-set": 2}
+TOPOLOGIES = {"grid": 0, "line": 1, "total": 2, "tree": 3, "tree2": 3, "tree3": 4, "tree4": 5}
+DISTS = {"constant": 0, "uniform": 1, "exponential": 2}
+KIND_SERVER, KIND_CLIENT, KIND_HOST, KIND_SIM_CLIENT = 0, 1, 2, 3
+TYPES = dict(init=1, init_ok=2, error=3, echo=10, echo_ok=11, topology=20, topology_ok=21,
+             broadcast=22, broadcast_ok=23, read=24, read_ok=25, add=30, add_ok=31,
+             replicate_one=32, replicate_full=33)
+TYPE_NAMES = {v: k for k, v in TYPES.items()}
+F_MSG_ID, F_REPLY = 1, 2
+RECV_BIT = 1 << 63
+
+
+class SimError(RuntimeError):
+    def __init__(self, code, text):
+        RuntimeError.__init__(self, "maelstrom_b200 error %d: %s" % (code, text))
+        self.code = code
+
+
+def body(type, msg_id=None, in_reply_to=None, p0=0, p1=0):
+    b = Body()
+    b.type = TYPES[type] if isinstance(type, str) else type
+    b.flags = (F_MSG_ID if msg_id is not None else 0) | (F_REPLY if in_reply_to is not None else 0)
+    b.msg_id = msg_id or 0
+    b.in_reply_to = in_reply_to or 0
+    b.p0 = p0
+    b.p1 = p1
+    return b
+
+
+class Sim:
+    def __init__(self, n_nodes, workload="broadcast", topology="grid", latency_dist="constant",
+                 latency_mean_ms=0, seed=0x4D41454C, p_loss=0.0, n_values=1 << 16, **sizing):
+        cfg = Config()
+        cfg.n_nodes = n_nodes
+        cfg.workload = WORKLOADS[workload] if isinstance(workload, str) else workload
+        cfg.topology = TOPOLOGIES[topology]
+        cfg.latency_dist = DISTS[latency_dist]
+        cfg.latency_mean_ms = latency_mean_ms
+        cfg.seed_lo = seed & 0xFFFFFFFF
+        cfg.seed_hi = seed >> 32
+        cfg.p_loss = p_loss
+        cfg.n_values = n_values
+        cfg.journal_level = 2
+        for k, v in sizing.items():
+            if not hasattr(cfg, k):
+                raise TypeError("unknown ms_config field %r" % k)
+            setattr(cfg, k, v)
+        self.L = _lib.lib()
+        self.cfg = cfg
+        self.n_nodes = n_nodes
+        self.h = self.L.ms_create(C.byref(cfg))
+        if not self.h:
+            raise SimError(-4, self.L.ms_last_error(None).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ms_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _chk(self, rc):
+        if rc < 0:
+            raise SimError(rc, self.L.ms_last_error(self.h).decode())
+        return rc
+
+    # endpoints -----------------------------------------------------------
+    def add_endpoint(self, name, kind=KIND_CLIENT):
+        return self._chk(self.L.ms_add_endpoint(self.h, name.encode(), kind))
+
+    def remove_endpoint(self, idx):
+        return self.L.ms_remove_endpoint(self.h, idx)
+
+    def endpoint_index(self, name):
+        return self.L.ms_endpoint_index(self.h, name.encode())
+
+    # data plane ----------------------------------------------------------
+    def send(self, src, dest, b):
+        return self.L.ms_send(self.h, src, dest, C.byref(b))
+
+    def recv(self, endpoint, timeout_ns=0):
+        out = np.zeros(1, dtype=MSG_DTYPE)
+        rc = self._chk(self.L.ms_recv(self.h, endpoint, timeout_ns, out.ctypes.data))
+        return out[0] if rc == 1 else None
+
+    def schedule(self, ops):
+        ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
+        return self._chk(self.L.ms_schedule_ops(self.h, ops.ctypes.data, ops.size))
+
+    # time ----------------------------------------------------------------
+    def step(self, n=1):
+        return self._chk(self.L.ms_step(self.h, n))
+
+    def run(self, until_ns):
+        return self._chk(self.L.ms_run(self.h, until_ns))
+
+    @property
+    def now(self):
+        return self.L.ms_now(self.h)
+
+    @property
+    def round(self):
+        return self.L.ms_round(self.h)
+
+    # faults --------------------------------------------------------------
+    def drop(self, src, dest):
+        return self._chk(self.L.ms_net_drop(self.h, src, dest))
+
+    def heal(self):
+        return self._chk(self.L.ms_net_heal(self.h))
+
+    def slow(self):
+        return self._chk(self.L.ms_net_slow(self.h))
+
+    def fast(self):
+        return self._chk(self.L.ms_net_fast(self.h))
+
+    def flaky(self):
+        return self._chk(self.L.ms_net_flaky(self.h))
+
+    def set_loss(self, p):
+        return self._chk(self.L.ms_net_set_loss(self.h, p))
+
+    def partition(self, comp):
+        comp = np.ascontiguousarray(comp, dtype=np.uint32)
+        return self._chk(self.L.ms_net_partition(self.h, comp.ctypes.data, comp.size))
+
+    # journal -------------------------------------------------------------
+    def journal_open(self, path):
+        return self._chk(self.L.ms_journal_open(self.h, path.encode()))
+
+    def journal_close(self):
+        return self._chk(self.L.ms_journal_close(self.h))
+
+    def drain(self, cap=1 << 20, bodies=True):
+        """Drain everything available; returns (events, bodies)."""
+        evs, bds = [], []
+        while True:
+            ev = np.zeros(cap, dtype=EVENT_DTYPE)
+            bd = np.zeros(cap, dtype=JBODY_DTYPE) if bodies else None
+            n = C.c_size_t(0)
+            self._chk(self.L.ms_journal_drain(self.h, ev.ctypes.data,
+                                              bd.ctypes.data if bodies else None, cap, C.byref(n)))
+            if n.value == 0:
+                break
+            evs.append(ev[:n.value])
+            if bodies:
+                bds.append(bd[:n.value])
+        ev = np.concatenate(evs) if evs else np.zeros(0, dtype=EVENT_DTYPE)
+        bd = (np.concatenate(bds) if bds else np.zeros(0, dtype=JBODY_DTYPE)) if bodies else None
+        return ev, bd
+
+    def journal_written(self):
+        return int(self.L.ms_journal_written(self.h))
+
+    def stats(self):
+        out = np.zeros(9, dtype=np.uint64)
+        self._chk(self.L.ms_stats(self.h, out.ctypes.data))
+        keys = ("send-count", "recv-count", "msg-count")
+        return {cls: {k: int(out[i * 3 + j]) for j, k in enumerate(keys)}
+                for i, cls in enumerate(("all", "clients", "servers"))}
+
+    def counters(self):
+        out = np.zeros(8, dtype=np.uint64)
+        self._chk(self.L.ms_counters(self.h, out.ctypes.data))
+        names = ("rounds", "sends", "recvs", "launches", "lost", "partition_drops", "max_window", "_")
+        return {k: int(v) for k, v in zip(names, out)}
+
+    def node_set(self, node):
+        n = self.L.ms_node_set(self.h, node, None, 0)
+        out = np.zeros(max(n, 1), dtype=np.uint32)
+        self.L.ms_node_set(self.h, node, out.ctypes.data, n)
+        return out[:n]
+
+    def client_replies(self):
+        return int(self.L.ms_client_replies(self.h))
+
+
+def topology(name, n, node):
+    out = np.zeros(max(n, 4), dtype=np.uint32)
+    k = _lib.lib().ms_topology(TOPOLOGIES[name], n, node, out.ctypes.data, out.size)
+    return out[:k].tolist()

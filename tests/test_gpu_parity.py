@@ -1,0 +1,174 @@
+"""GPU parity: the CUDA engine, driven through the C ABI, must produce a journal
+(message ids, event ids, virtual times, delivery order, bodies) bit-identical
+to the CPU oracle on the same seed and op sequence."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from scenarios import assert_same_journal, both, make_pair, ops_array, random_broadcast_ops
+
+pytestmark = pytest.mark.gpu
+
+
+def test_smoke_entry():
+    import __graft_entry__ as G
+    G.smoke()
+
+
+@pytest.mark.parametrize("topo,n,want", [
+    ("grid", 5, 6), ("grid", 25, 56), ("line", 25, 24), ("total", 25, 576), ("tree4", 25, 24),
+    ("grid", 1, 0), ("line", 1, 0), ("tree2", 7, 6), ("tree3", 40, 39),
+])
+def test_flood_counts_and_journal(topo, n, want):
+    g, o = make_pair(n, topology=topo, n_values=8)
+
+    def scenario(s, body):
+        c = s.add_endpoint("c0")
+        s.send(c, n // 3, body("broadcast", msg_id=1, p0=3))
+        s.run(2_000_000)
+        r = s.recv(c)
+        return int(r["type"]), int(r["in_reply_to"]), int(r["id"])
+
+    rg, ro = both(g, o, scenario)
+    assert rg == ro
+    assert_same_journal(g, o)
+    assert g.stats()["servers"]["send-count"] == want
+    for k in range(n):
+        assert g.node_set(k).tolist() == [3]
+
+
+def test_flood_4096_grid():
+    n = 4096
+    g, o = make_pair(n, topology="grid", n_values=64, max_endpoints=n + 8, ring_cap=256, max_window=256,
+                     journal_cap_log2=20)
+
+    def scenario(s, body):
+        c = s.add_endpoint("c0")
+        for v in range(3):
+            s.send(c, (1234 * (v + 1)) % n, body("broadcast", msg_id=v + 1, p0=v))
+        s.run(1_000_000)
+
+    both(g, o, scenario)
+    assert_same_journal(g, o)
+    assert g.stats()["servers"]["send-count"] == 3 * 12033
+
+
+def test_echo_doc_counts():
+    g, o = make_pair(1, workload="echo")
+
+    def scenario(s, body):
+        c0 = s.add_endpoint("c0")
+        first = s.send(c0, 0, body("init", msg_id=1))
+        r = s.recv(c0, 10_000_000_000)
+        out = [first, int(r["type"]), int(r["id"]), int(r["msg_id"])]
+        c1 = s.add_endpoint("c1")
+        for i in range(12):
+            s.send(c1, 0, body("echo", msg_id=i + 1, p0=i, p1=0xABCD0000 + i))
+            r = s.recv(c1, 5_000_000_000)
+            out.append((int(r["type"]), int(r["in_reply_to"]), int(r["p0"]), int(r["p1"]), int(r["msg_id"])))
+        return out
+
+    rg, ro = both(g, o, scenario)
+    assert rg == ro
+    assert_same_journal(g, o)
+    assert g.stats()["all"] == {"send-count": 26, "recv-count": 26, "msg-count": 26}   # doc/02-echo/index.md:379-383
+
+
+def test_many_values_duplicates_same_round():
+    # several clients hit the same nodes with many values in the same round: exercises the
+    # id sort, the first-sight hash and multi-chunk windows
+    n = 25
+    g, o = make_pair(n, topology="grid", n_values=4096, ring_cap=4096, max_window=2048, journal_cap_log2=21)
+
+    def scenario(s, body):
+        cs = [s.add_endpoint("c%d" % i) for i in range(4)]
+        ops, nv = random_broadcast_ops(n, cs, n_ticks=3, per_tick=300, seed=11)
+        s.schedule(ops)
+        s.run(4_000_000)
+        return nv
+
+    both(g, o, scenario)
+    assert_same_journal(g, o)
+    for k in (0, 7, 24):
+        assert g.node_set(k).tolist() == o.node_set(k).tolist() == list(range(900))
+
+
+@pytest.mark.parametrize("dist,mean", [("constant", 1), ("constant", 10), ("uniform", 5), ("exponential", 5)])
+def test_latency_distributions(dist, mean):
+    n = 25
+    g, o = make_pair(n, topology="grid", latency_dist=dist, latency_mean_ms=mean, n_values=256,
+                     ring_cap=1024, max_window=512)
+
+    def scenario(s, body):
+        cs = [s.add_endpoint("c%d" % i) for i in range(2)]
+        ops, nv = random_broadcast_ops(n, cs, n_ticks=20, per_tick=4, seed=5)
+        s.schedule(ops)
+        s.run(400_000_000)
+        return nv
+
+    both(g, o, scenario)
+    ev, _ = assert_same_journal(g, o)
+    assert len(ev) > 1000
+
+
+def test_loss_flaky_slow_fast():
+    n = 16
+    g, o = make_pair(n, topology="grid", latency_dist="uniform", latency_mean_ms=3, n_values=512,
+                     ring_cap=1024, max_window=512, p_loss=0.1)
+
+    def scenario(s, body):
+        cs = [s.add_endpoint("c%d" % i) for i in range(2)]
+        ops, nv = random_broadcast_ops(n, cs, n_ticks=60, per_tick=3, seed=9)
+        s.schedule(ops)
+        s.run(15_000_000)
+        s.flaky()
+        s.run(30_000_000)
+        s.slow()
+        s.run(45_000_000)
+        s.fast()
+        s.set_loss(0.0)
+        s.run(500_000_000)
+
+    both(g, o, scenario)
+    assert_same_journal(g, o)
+    st = g.stats()
+    assert st["all"]["send-count"] > st["all"]["recv-count"]
+
+
+def test_partitions_drop_heal_bulk():
+    n = 9
+    g, o = make_pair(n, topology="grid", latency_dist="constant", latency_mean_ms=2, n_values=256,
+                     ring_cap=512, max_window=256)
+
+    def scenario(s, body):
+        c = s.add_endpoint("c0")
+        ops, nv = random_broadcast_ops(n, [c], n_ticks=40, per_tick=2, seed=3)
+        s.schedule(ops)
+        s.run(5_000_000)
+        for a in range(0, 4):
+            for b in range(4, 9):
+                s.drop(a, b)
+                s.drop(b, a)
+        s.run(15_000_000)
+        s.heal()
+        s.run(25_000_000)
+        s.partition([0, 0, 0, 1, 1, 1, 2, 2, 2])
+        s.run(35_000_000)
+        s.heal()
+        s.run(200_000_000)
+
+    both(g, o, scenario)
+    assert_same_journal(g, o)
+    assert g.counters()["partition_drops"] > 0
+
+
+def test_errors_surface():
+    import maelstrom_b200 as mb
+    g = mb.Sim(4, topology="line", n_values=8, ring_cap=4, max_window=4)
+    c = g.add_endpoint("c0")
+    assert g.send(c, 99, mb.body("read", msg_id=1)) == -1          # node-not-found (net.clj:159-164)
+    for v in range(8):
+        g.send(c, 0, mb.body("broadcast", msg_id=v + 1, p0=v))     # 8 messages into a 4-slot ring
+    with pytest.raises(mb.SimError):
+        g.step(2)
+    g.close()
