@@ -207,6 +207,16 @@ uint64_t ms_client_replies(ms_sim* sim);
  * kernel launches, lost, partition_drops, max_window, reserved} */
 int ms_counters(ms_sim* sim, uint64_t out[8]);
 
+/* Device-side timing on the engine's own CUDA stream (what bench.py reports):
+ * ms_timer_begin records an event; ms_timer_end records another, synchronises and
+ * returns the GPU milliseconds between them.  ms_profile(1) additionally brackets
+ * every round-kernel launch with events; ms_profile_read returns and resets the
+ * accumulated round-kernel milliseconds and launch count. */
+int ms_timer_begin(ms_sim* sim);
+int ms_timer_end(ms_sim* sim, double* elapsed_ms);
+int ms_profile(ms_sim* sim, int enable);
+int ms_profile_read(ms_sim* sim, double* round_kernel_ms, uint64_t* launches);
+
 /* pure helper: neighbors of `node` under workload/broadcast.clj:40-178 */
 size_t ms_topology(uint32_t topology, uint32_t n, uint32_t node, uint32_t* out, size_t cap);
 

@@ -75,6 +75,10 @@ SYMBOLS = {
     "ms_node_set": (C.c_size_t, [_P, C.c_uint32, _P, C.c_size_t]),
     "ms_client_replies": (C.c_uint64, [_P]),
     "ms_counters": (C.c_int, [_P, _P]),
+    "ms_timer_begin": (C.c_int, [_P]),
+    "ms_timer_end": (C.c_int, [_P, C.POINTER(C.c_double)]),
+    "ms_profile": (C.c_int, [_P, C.c_int]),
+    "ms_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "ms_topology": (C.c_size_t, [C.c_uint32, C.c_uint32, C.c_uint32, _P, C.c_size_t]),
 }
 

@@ -51,6 +51,8 @@ struct DevState {
   uint32_t time_advanced;    // 1 when the last round moved `now`
   uint32_t max_window_seen;
   uint32_t cal_release;      // calendar slot to release before the next round (+1), 0 = none
+  uint32_t slot_open;        // k_snapshot ran for this launch slot and no k_round class has run yet
+  uint32_t round_max_window; // largest window of the round in flight (selects the k_round size class)
   uint32_t pad0;
 };
 

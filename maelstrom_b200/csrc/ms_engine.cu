@@ -20,7 +20,9 @@ using namespace msd;
 
 extern "C" {
 cudaError_t msk_round_smem_attr(size_t bytes);
-void msk_launch_round(const msd::Params* p, int threads, size_t smem, int with_release, cudaStream_t s);
+size_t msk_round_smem_bytes(uint32_t cap);
+void msk_launch_round(const msd::Params* p, int n_classes, const uint32_t* caps, const int* threads,
+                      int with_release, cudaStream_t s, cudaEvent_t before_round, cudaEvent_t after_round);
 void msk_set_bit(uint32_t* words, size_t word, uint32_t bit, cudaStream_t s);
 }
 
@@ -98,8 +100,10 @@ struct ms_sim {
   Params P;                 // by-value kernel parameters (pointers + sizing)
   NetParams np;             // host mirror of the device knobs
   DevState hs;              // host mirror of the device state (valid after sync_state)
-  int threads = 128;
-  size_t smem = 0;
+  // window-size classes of the round kernel (ascending caps); exactly one runs per round
+  int n_classes = 0;
+  uint32_t class_cap[4] = {0, 0, 0, 0};
+  int class_threads[4] = {0, 0, 0, 0};
   bool use_calendar = false;
   uint64_t launches = 0;
 
@@ -109,11 +113,19 @@ struct ms_sim {
   std::vector<std::deque<ms_msg>> mailbox;
   std::vector<ms_msg> pending;      // host sends not yet staged
   std::vector<ms_op> sched;
+  std::vector<uint32_t> tick_off;
   ms_op* d_sched = nullptr;
   uint32_t* d_tick_off = nullptr;
   size_t d_sched_cap = 0, d_tick_cap = 0;
   bool pair_alloc = false;
   FILE* jfile = nullptr;
+  // timing
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_ev;   // pairs
+  size_t prof_used = 0;
+  double prof_ms = 0;
+  uint64_t prof_launches = 0;
   std::vector<void*> allocs;
 
   template <typename T>
@@ -135,6 +147,7 @@ struct ms_sim {
   int sync_state() {
     CK(cudaMemcpyAsync(&hs, P.st, sizeof(DevState), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
+    if (prof_used) collect_profile();
     if (hs.mail_count) {
       const uint32_t n = std::min(hs.mail_count, P.mail_cap);
       std::vector<ms_msg> buf(n);
@@ -173,9 +186,27 @@ struct ms_sim {
 
   void launch_rounds(uint64_t n) {
     for (uint64_t i = 0; i < n; i++) {
-      msk_launch_round(&P, threads, smem, use_calendar ? 1 : 0, stream);
-      launches += use_calendar ? 3 : 2;
+      cudaEvent_t a = nullptr, b = nullptr;
+      if (profiling) {
+        if (prof_used + 2 > prof_ev.size()) {
+          prof_ev.resize(prof_used + 2, nullptr);
+          cudaEventCreate(&prof_ev[prof_used]);
+          cudaEventCreate(&prof_ev[prof_used + 1]);
+        }
+        a = prof_ev[prof_used]; b = prof_ev[prof_used + 1];
+        prof_used += 2;
+      }
+      msk_launch_round(&P, n_classes, class_cap, class_threads, use_calendar ? 1 : 0, stream, a, b);
+      launches += (use_calendar ? 2 : 1) + n_classes;
     }
+  }
+
+  void collect_profile() {   // call after the stream is synchronised
+    for (size_t i = 0; i + 1 < prof_used; i += 2) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, prof_ev[i], prof_ev[i + 1]) == cudaSuccess) { prof_ms += ms; prof_launches++; }
+    }
+    prof_used = 0;
   }
 
   int maybe_flush_journal_file() {
@@ -224,39 +255,43 @@ struct ms_sim {
     return MS_OK;
   }
 
-  int upload_schedule() {
+  // Uploads only ops[first..) (the schedule is append-only) and refreshes tick_off.
+  int upload_schedule(size_t first) {
     const size_t n = sched.size();
     if (n > d_sched_cap) {
       const size_t cap = std::max<size_t>(n, d_sched_cap * 2);
       ms_op* nd = nullptr;
       CK(cudaMalloc((void**)&nd, cap * sizeof(ms_op)));
+      if (d_sched && first) CK(cudaMemcpy(nd, d_sched, first * sizeof(ms_op), cudaMemcpyDeviceToDevice));
       if (d_sched) cudaFree(d_sched);
       d_sched = nd;
       d_sched_cap = cap;
     }
-    if (n) CK(cudaMemcpy(d_sched, sched.data(), n * sizeof(ms_op), cudaMemcpyHostToDevice));
+    if (n > first)
+      CK(cudaMemcpy(d_sched + first, sched.data() + first, (n - first) * sizeof(ms_op), cudaMemcpyHostToDevice));
     // tick_off[j] = number of ops whose injection tick ceil(time/tick) is < j
     const int64_t last = n ? sched.back().time_ns : 0;
     const size_t n_ticks = (size_t)((last + kTickNs - 1) / kTickNs) + 2;
-    std::vector<uint32_t> off(n_ticks + 1, 0);
-    for (const ms_op& op : sched) {
-      const int64_t t = op.time_ns <= 0 ? 0 : (op.time_ns + kTickNs - 1) / kTickNs;
-      off[(size_t)t + 1]++;
+    const size_t old_sz = tick_off.size();
+    if (tick_off.size() < n_ticks + 1) tick_off.resize(n_ticks + 1, old_sz ? tick_off.back() : 0);
+    for (size_t i = first; i < n; i++) {
+      const int64_t t = sched[i].time_ns <= 0 ? 0 : (sched[i].time_ns + kTickNs - 1) / kTickNs;
+      // append-only + sorted: every entry above tick t grows by one
+      for (size_t j = (size_t)t + 1; j < tick_off.size(); j++) tick_off[j]++;
     }
-    for (size_t j = 1; j < off.size(); j++) off[j] += off[j - 1];
-    if (off.size() > d_tick_cap) {
-      const size_t cap = std::max<size_t>(off.size(), d_tick_cap * 2);
+    if (tick_off.size() > d_tick_cap) {
+      const size_t cap = std::max<size_t>(tick_off.size(), d_tick_cap * 2);
       uint32_t* nd = nullptr;
       CK(cudaMalloc((void**)&nd, cap * sizeof(uint32_t)));
       if (d_tick_off) cudaFree(d_tick_off);
       d_tick_off = nd;
       d_tick_cap = cap;
     }
-    CK(cudaMemcpy(d_tick_off, off.data(), off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_tick_off, tick_off.data(), tick_off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     P.sched = d_sched;
     P.n_sched = (uint32_t)n;
     P.tick_off = d_tick_off;
-    P.n_tick_off = (uint32_t)off.size();
+    P.n_tick_off = (uint32_t)tick_off.size();
     return MS_OK;
   }
 };
@@ -292,9 +327,22 @@ static int build_sim(ms_sim* s, const ms_config* in) {
                                                       : std::min<uint32_t>(16384u, std::max<uint32_t>(64u, 32u * c.latency_mean_ms)));
     if (!c.calendar_cap) c.calendar_cap = 1u << 16;
   }
-  s->threads = c.threads_per_node ? (int)c.threads_per_node
-                                  : (c.max_window >= 2048 ? 512 : c.max_window >= 512 ? 256 : 128);
-  if (s->threads % 32 || s->threads > 512 || s->threads < 32) { set_err("threads_per_node must be a multiple of 32 in [32,512]"); return MS_ERR_ARG; }
+  if (c.threads_per_node && (c.threads_per_node % 32 || c.threads_per_node > 512)) {
+    set_err("threads_per_node must be a multiple of 32 in [32,512]");
+    return MS_ERR_ARG;
+  }
+  {
+    const uint32_t ladder[3] = {256, 1024, 32768};
+    const int thr[3] = {128, 256, 512};
+    s->n_classes = 0;
+    for (int k = 0; k < 3; k++) {
+      const uint32_t cap = std::min(ladder[k], c.max_window);
+      s->class_cap[s->n_classes] = cap;
+      s->class_threads[s->n_classes] = c.threads_per_node ? (int)c.threads_per_node : thr[k];
+      s->n_classes++;
+      if (cap == c.max_window) break;
+    }
+  }
 
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -408,8 +456,7 @@ static int build_sim(ms_sim* s, const ms_config* in) {
   s->hs.stop_ns = INT64_MAX;
   CK(cudaMemcpyAsync(P.st, &s->hs, sizeof(DevState), cudaMemcpyHostToDevice, s->stream));
 
-  s->smem = (size_t)c.max_window * (8 + 16 + 16) + 64;
-  CK(msk_round_smem_attr(s->smem));
+  CK(msk_round_smem_attr(msk_round_smem_bytes(c.max_window)));
   CK(cudaStreamSynchronize(s->stream));
   return MS_OK;
 }
@@ -444,6 +491,9 @@ void ms_destroy(ms_sim* s) {
   for (void* p : s->allocs) cudaFree(p);
   if (s->d_sched) cudaFree(s->d_sched);
   if (s->d_tick_off) cudaFree(s->d_tick_off);
+  for (cudaEvent_t e : s->prof_ev) if (e) cudaEventDestroy(e);
+  if (s->t0) cudaEventDestroy(s->t0);
+  if (s->t1) cudaEventDestroy(s->t1);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }
@@ -516,6 +566,7 @@ int64_t ms_send(ms_sim* s, uint32_t src, uint32_t dest, const ms_body* b) {
 int ms_schedule_ops(ms_sim* s, const ms_op* ops, size_t n) {
   std::lock_guard<std::mutex> g(s->mu);
   cudaSetDevice(s->device);
+  const size_t first = s->sched.size();
   for (size_t i = 0; i < n; i++) {
     if (!s->sched.empty() && ops[i].time_ns < s->sched.back().time_ns) { set_err("ops must be sorted by time"); return MS_ERR_ARG; }
     if (ops[i].src >= s->P.n_ep || ops[i].dest >= s->P.n_ep || s->kinds[ops[i].src] == kRemoved ||
@@ -523,7 +574,13 @@ int ms_schedule_ops(ms_sim* s, const ms_op* ops, size_t n) {
     s->sched.push_back(ops[i]);
   }
   CK(cudaStreamSynchronize(s->stream));
-  return s->upload_schedule();
+  return s->upload_schedule(first);
+}
+
+// true when the device refuses to run rounds until the host drains the journal
+static bool journal_blocked(const ms_sim* s) {
+  if (!s->cfg.journal_level || s->cfg.journal_discard) return false;
+  return s->hs.next_event - s->hs.journal_drained > (s->P.jmask + 1) / 2;
 }
 
 static int step_locked(ms_sim* s, uint64_t n_rounds, int64_t stop) {
@@ -540,10 +597,14 @@ int ms_step(ms_sim* s, uint64_t n_rounds) {
   std::lock_guard<std::mutex> g(s->mu);
   // bounded batches so the journal file / mailbox keep up
   while (n_rounds) {
-    const uint64_t b = std::min<uint64_t>(n_rounds, 64);
+    if (journal_blocked(s)) { set_err("journal ring half full: drain it (ms_journal_drain) before stepping"); return MS_ERR_CAPACITY; }
+    // one round at a time near the watermark so that "exactly n rounds" holds
+    const uint64_t pending = s->cfg.journal_discard ? 0 : s->hs.next_event - s->hs.journal_drained;
+    const uint64_t b = (s->cfg.journal_level && pending > (s->P.jmask + 1) / 4) ? 1 : std::min<uint64_t>(n_rounds, 64);
+    const uint64_t r0 = s->hs.rounds_run;
     const int rc = step_locked(s, b, INT64_MAX);
     if (rc) return rc;
-    n_rounds -= b;
+    n_rounds -= std::min<uint64_t>(n_rounds, s->hs.rounds_run - r0);
   }
   return MS_OK;
 }
@@ -551,6 +612,7 @@ int ms_step(ms_sim* s, uint64_t n_rounds) {
 int ms_run(ms_sim* s, int64_t until) {
   std::lock_guard<std::mutex> g(s->mu);
   while (s->hs.now < until) {
+    if (journal_blocked(s)) return 1;   // drain (ms_journal_drain) and call again
     const int rc = step_locked(s, 32, until);
     if (rc) return rc;
   }
@@ -568,6 +630,7 @@ int ms_recv(ms_sim* s, uint32_t e, int64_t timeout, ms_msg* out) {
       return 1;
     }
     if (s->hs.now >= give_up) return 0;
+    if (journal_blocked(s)) { set_err("journal ring half full: drain it (ms_journal_drain)"); return MS_ERR_CAPACITY; }
     const int rc = step_locked(s, 1, INT64_MAX);
     if (rc) return rc;
   }
@@ -709,6 +772,42 @@ int ms_counters(ms_sim* s, uint64_t out[8]) {
   out[5] = s->hs.part_drops;
   out[6] = s->hs.max_window_seen;
   out[7] = 0;
+  return MS_OK;
+}
+
+int ms_timer_begin(ms_sim* s) {
+  std::lock_guard<std::mutex> g(s->mu);
+  cudaSetDevice(s->device);
+  if (!s->t0) { CK(cudaEventCreate(&s->t0)); CK(cudaEventCreate(&s->t1)); }
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaEventRecord(s->t0, s->stream));
+  return MS_OK;
+}
+
+int ms_timer_end(ms_sim* s, double* elapsed_ms) {
+  std::lock_guard<std::mutex> g(s->mu);
+  cudaSetDevice(s->device);
+  if (!s->t0) { set_err("ms_timer_end without ms_timer_begin"); return MS_ERR_ARG; }
+  CK(cudaEventRecord(s->t1, s->stream));
+  CK(cudaEventSynchronize(s->t1));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, s->t0, s->t1));
+  if (elapsed_ms) *elapsed_ms = ms;
+  return MS_OK;
+}
+
+int ms_profile(ms_sim* s, int enable) {
+  std::lock_guard<std::mutex> g(s->mu);
+  s->profiling = enable != 0;
+  return MS_OK;
+}
+
+int ms_profile_read(ms_sim* s, double* ms, uint64_t* launches) {
+  std::lock_guard<std::mutex> g(s->mu);
+  if (ms) *ms = s->prof_ms;
+  if (launches) *launches = s->prof_launches;
+  s->prof_ms = 0;
+  s->prof_launches = 0;
   return MS_OK;
 }
 

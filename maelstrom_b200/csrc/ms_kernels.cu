@@ -61,6 +61,15 @@ __device__ __forceinline__ void latch_error(DevState* st, uint32_t code, uint32_
   if (atomicCAS(&st->error, 0u, code) == 0u) st->error_arg = arg;
 }
 
+// A round is skipped (by every kernel of the round alike) when the simulation has
+// reached its stop time, an error is latched, or the journal ring is more than
+// half full and the host has not drained it yet (back-pressure).
+__device__ __forceinline__ bool round_skipped(const Params& p, const DevState* st) {
+  if (st->now >= st->stop_ns || st->error) return true;
+  if (p.jlevel && !p.jdiscard && st->next_event - st->journal_drained > ((p.jmask + 1) >> 1)) return true;
+  return false;
+}
+
 // ------------------------------------------------------------------ record packing
 struct Rec {  // ms_msg in registers
   uint64_t id;
@@ -200,7 +209,7 @@ __device__ void lookback(const Params& p, DevState* st, uint32_t ticket, uint32_
       uint32_t spins = 0;
       for (;;) {
         if (ld_acquire_u32(&s->flag_inc) == tag) { has_inc = true; break; }
-        if (ld_acquire_u32(&s->flag_agg) == tag) { has_agg = true; break; }
+        if (ld_acquire_u32(&s->flag_agg) == tag) break;
         if (++spins > (1u << 22)) { failed = true; break; }
         __nanosleep(64);
       }
@@ -212,7 +221,6 @@ __device__ void lookback(const Params& p, DevState* st, uint32_t ticket, uint32_
     if (lane < first) {               // predecessors closer than the first inclusive one
       const Status* s = p.status + idx;
       cev = ld_relaxed_u64(&s->agg_ev); cem = ld_relaxed_u64(&s->agg_em);
-      (void)has_agg;
     } else if (lane == first && idx >= 0) {
       const Status* s = p.status + idx;
       cev = ld_relaxed_u64(&s->inc_ev); cem = ld_relaxed_u64(&s->inc_em);
@@ -304,24 +312,35 @@ __device__ __forceinline__ void emit_one(const Params& p, DevState* st, const Ne
 __global__ void k_set_bit(uint32_t* words, size_t word, uint32_t bit) { atomicOr(words + word, 1u << bit); }
 
 // ------------------------------------------------------------------ k_snapshot
+// head <- limit, limit <- tail; also finds the largest window of the round so
+// that exactly one size class of k_round runs it.
 __global__ void k_snapshot(Params p) {
   DevState* st = p.st;
-  if (st->now >= st->stop_ns || st->error) return;
+  if (round_skipped(p, st)) return;
   const uint32_t stride = gridDim.x * blockDim.x;
+  uint32_t wmax = 0;
   for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < p.n_ep; e += stride) {
-    p.head[e] = p.limit[e];
-    p.limit[e] = p.tail[e];
+    const uint32_t h = p.limit[e], l = p.tail[e];
+    p.head[e] = h;
+    p.limit[e] = l;
+    if (p.kind[e] != kRemoved) wmax = max(wmax, l - h);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0 && st->cal_release) {
-    p.cal_count[st->cal_release - 1] = 0;
-    st->cal_release = 0;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) wmax = max(wmax, __shfl_xor_sync(FULL, wmax, d));
+  if ((threadIdx.x & 31) == 0 && wmax) atomicMax(&st->round_max_window, wmax);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (st->cal_release) {
+      p.cal_count[st->cal_release - 1] = 0;
+      st->cal_release = 0;
+    }
+    st->slot_open = 1;
   }
 }
 
 // ------------------------------------------------------------------ k_release (timing wheel -> rings)
 __global__ void k_release(Params p) {
   DevState* st = p.st;
-  if (st->now >= st->stop_ns || st->error || st->cal_release == 0) return;
+  if (round_skipped(p, st) || st->cal_release == 0) return;
   const uint32_t slot = st->cal_release - 1;
   const uint32_t n = min(p.cal_count[slot], p.cal_cap);
   const uint32_t stride = gridDim.x * blockDim.x;
@@ -349,14 +368,24 @@ __global__ void k_release(Params p) {
 }
 
 // ------------------------------------------------------------------ node programs
-// Per-message work item kept in shared memory between the count and emit phases.
-struct Work {
+// Fields of a delivered message the node programs look at (2nd and 3rd vector
+// of the 48-B record); re-read from the ring (L1 hit) in every phase.
+struct MsgView {
   uint32_t src, msg_id, p0;
-  uint32_t tf;  // type (low 16) | msg flags (bits 16-17) | W_* (bits 24+)
+  uint32_t tf;   // type | flags << 16
 };
-constexpr uint32_t W_RECV = 1u << 24;   // passed the partition check
-constexpr uint32_t W_NEW = 1u << 25;    // broadcast: first sight of the value
-constexpr uint32_t W_FRESH = 1u << 26;  // broadcast: value unseen before this round
+
+__device__ __forceinline__ MsgView view_load(const uint4* rec) {
+  const uint4 b = rec[1], c = rec[2];
+  MsgView v;
+  v.src = b.x; v.msg_id = b.z; v.tf = c.x; v.p0 = c.y;
+  return v;
+}
+
+// vals[] bits
+constexpr uint32_t V_FRESH = 1u << 31;  // broadcast value unseen before this round
+constexpr uint32_t V_RECV = 1u << 30;   // passed the partition check
+constexpr uint32_t V_MASK = (1u << 30) - 1u;
 
 __device__ __forceinline__ uint32_t hash32(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
@@ -383,7 +412,7 @@ __device__ __forceinline__ uint32_t nbr_pos(const Params& p, uint32_t e, uint32_
 }
 
 // number of emissions of one delivered message (count phase)
-__device__ __forceinline__ uint32_t node_emit_count(const Params& p, uint32_t e, const Work& w) {
+__device__ __forceinline__ uint32_t node_emit_count(const Params& p, uint32_t e, const MsgView& w, bool is_new) {
   const uint32_t type = w.tf & 0xFFFFu;
   const bool has_id = (w.tf >> 16) & MS_F_MSG_ID;
   const bool is_reply = (w.tf >> 16) & MS_F_REPLY;
@@ -396,7 +425,7 @@ __device__ __forceinline__ uint32_t node_emit_count(const Params& p, uint32_t e,
     case MS_T_INIT: case MS_T_TOPOLOGY: case MS_T_READ: return 1;
     case MS_T_BROADCAST: {
       uint32_t n = has_id ? 1u : 0u;
-      if (w.tf & W_NEW) {
+      if (is_new) {
         n += nbr_count(p, e);
         if (nbr_pos(p, e, w.src) != 0xFFFFFFFFu) n -= 1;   // skip whoever sent it to us
       }
@@ -407,7 +436,7 @@ __device__ __forceinline__ uint32_t node_emit_count(const Params& p, uint32_t e,
 }
 
 // k-th emission of a delivered message (emit phase)
-__device__ __forceinline__ void node_emit(const Params& p, uint32_t e, const Work& w, uint32_t k,
+__device__ __forceinline__ void node_emit(const Params& p, uint32_t e, const MsgView& w, uint32_t k,
                                           uint32_t nemit, uint32_t emit_idx, uint32_t msg_id_base,
                                           uint32_t set_before, uint32_t new_before, uint64_t p1, Rec& r) {
   const uint32_t type = w.tf & 0xFFFFu;
@@ -441,15 +470,24 @@ __device__ __forceinline__ void node_emit(const Params& p, uint32_t e, const Wor
 }
 
 // ------------------------------------------------------------------ k_round
-// dynamic shared memory: keys[max_window] | work[max_window] | aux[2*max_window]
-__global__ void __launch_bounds__(512) k_round(Params p) {
+// One CTA per ticket.  Dynamic shared memory, `cap` = window capacity of this
+// size class:  keys u64[cap] | vals u32[cap] | aux u64[cap+1]   (20 B / message)
+// The same kernel is launched once per size class every round; only the class
+// whose (cap_lo, cap] interval contains the round's largest window executes.
+__global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap_lo, uint32_t cap, uint32_t last_class) {
   DevState* st = p.st;
-  if (st->now >= st->stop_ns || st->error) return;
+  if (round_skipped(p, st) || !st->slot_open) return;
+  {
+    const uint32_t rm = st->round_max_window;
+    if (rm <= cap_lo && cap_lo != 0) return;
+    if (rm > cap && !last_class) return;
+  }
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
-  Work* work = reinterpret_cast<Work*>(keys + p.max_window);
-  uint64_t* aux = reinterpret_cast<uint64_t*>(work + p.max_window);   // 2*max_window+1 entries
+  uint32_t* vals = reinterpret_cast<uint32_t*>(keys + cap);
+  uint64_t* aux = reinterpret_cast<uint64_t*>(vals + cap);     // cap+1 entries
+  uint32_t* tab = reinterpret_cast<uint32_t*>(aux);            // dedupe table, 2*npad entries
 
   __shared__ uint32_t s_ticket;
   __shared__ uint64_t s_pref[2];
@@ -523,7 +561,7 @@ __global__ void __launch_bounds__(512) k_round(Params p) {
     const uint8_t kind = p.kind[e];
     const uint32_t head = p.head[e];
     uint32_t n = (kind == kRemoved) ? 0u : (p.limit[e] - head);
-    if (n > p.max_window) {
+    if (n > cap || n > p.max_window) {
       if (tid == 0) latch_error(st, E_WINDOW_OVERFLOW, e);
       n = 0;
     }
@@ -546,20 +584,16 @@ __global__ void __launch_bounds__(512) k_round(Params p) {
     // reference's PriorityBlockingQueue leaves ties unspecified, net.clj:39-40,145)
     if (n > 1) block_bitonic_sort(keys, npad);
 
-    // P3: load messages in id order, partition check at dequeue (net.clj:234)
+    // P3: partition check at dequeue (net.clj:234); broadcast: first-sight dedupe table
     const bool is_server = (kind == MS_KIND_SERVER);
     const bool bcast = is_server && p.workload == MS_W_BROADCAST;
-    const int tab = 2 * npad;   // dedupe hash table size
-    if (bcast) for (int i = tid; i < tab; i += nt) aux[i] = ~0ull;
+    const int tsz = 2 * npad;   // dedupe table size (u32 entries)
+    if (bcast) for (int i = tid; i < tsz; i += nt) tab[i] = 0xFFFFFFFFu;
     __syncthreads();
     const uint32_t* mybits = (is_server && p.bitmap) ? p.bitmap + (size_t)e * p.bm_words : nullptr;
     for (int i = tid; i < (int)n; i += nt) {
       const uint32_t slot = (uint32_t)(keys[i] & 0xFFFFu);
-      const uint4* rp = myring + (size_t)((head + slot) & p.ring_mask) * 3;
-      const uint4 b = ld_v4(rp + 1), c = ld_v4(rp + 2);
-      Work w;
-      w.src = b.x; w.msg_id = b.z; w.p0 = c.y;
-      w.tf = (c.x & 0xFFFFu) | (((c.x >> 16) & 3u) << 16);
+      const MsgView w = view_load(myring + (size_t)((head + slot) & p.ring_mask) * 3);
       bool cut = false;
       if (np.pair_active && p.pair_bits)
         cut = (p.pair_bits[(size_t)e * p.pair_words + (w.src >> 5)] >> (w.src & 31)) & 1u;
@@ -568,59 +602,76 @@ __global__ void __launch_bounds__(512) k_round(Params p) {
         const uint32_t cs = p.comp[w.src], ce = p.comp[e];
         cut = cs != ce && cs != 0xFFFFFFFFu && ce != 0xFFFFFFFFu;
       }
-      if (!cut) w.tf |= W_RECV;
+      uint32_t val = cut ? 0u : V_RECV;
       if (bcast && !cut && (w.tf & 0xFFFFu) == MS_T_BROADCAST && !((w.tf >> 16) & MS_F_REPLY)) {
         const uint32_t v = w.p0;
-        if (v >= p.n_values) {
+        if (v >= p.n_values || v > V_MASK) {
           latch_error(st, E_VALUE_RANGE, v);
-        } else if (!((mybits[v >> 5] >> (v & 31)) & 1u)) {
-          w.tf |= W_FRESH;
-          // smallest sorted index among this round's copies of v wins
-          const uint64_t mine = ((uint64_t)v << 32) | (uint32_t)i;
-          uint32_t h = hash32(v) & (tab - 1);
-          for (;;) {
-            uint64_t cur = *reinterpret_cast<volatile uint64_t*>(&aux[h]);
-            if (cur == ~0ull) {
-              const uint64_t old = atomicCAS(reinterpret_cast<unsigned long long*>(&aux[h]), ~0ull, mine);
-              if (old == ~0ull) break;
-              cur = old;
+        } else {
+          val |= v;
+          if (!((mybits[v >> 5] >> (v & 31)) & 1u)) {
+            val |= V_FRESH;
+            // publish vals[i] before i becomes visible in the table
+            *reinterpret_cast<volatile uint32_t*>(&vals[i]) = val;
+            __threadfence_block();
+            // smallest sorted index among this round's copies of v wins the slot
+            uint32_t h = hash32(v) & (tsz - 1);
+            for (;;) {
+              uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&tab[h]);
+              if (cur == 0xFFFFFFFFu) {
+                const uint32_t old = atomicCAS(&tab[h], 0xFFFFFFFFu, (uint32_t)i);
+                if (old == 0xFFFFFFFFu) break;
+                cur = old;
+              }
+              if ((*reinterpret_cast<volatile uint32_t*>(&vals[cur]) & V_MASK) == v) {
+                atomicMin(&tab[h], (uint32_t)i);
+                break;
+              }
+              h = (h + 1) & (tsz - 1);
             }
-            if ((uint32_t)(cur >> 32) == v) {
-              atomicMin(reinterpret_cast<unsigned long long*>(&aux[h]), mine);
-              break;
-            }
-            h = (h + 1) & (tab - 1);
           }
         }
       }
-      work[i] = w;
+      vals[i] = val;
     }
     __syncthreads();
-    // P3b: resolve first-sight winners, then publish counts (aux is reused)
+    // P3b: resolve first-sight winners (reads the table), keep the result in a register-free
+    // way: V_FRESH stays set only for winners
     if (bcast) {
       for (int i = tid; i < (int)n; i += nt) {
-        Work w = work[i];
-        if (w.tf & W_FRESH) {
-          const uint32_t v = w.p0;
-          uint32_t h = hash32(v) & (tab - 1);
-          while ((uint32_t)(aux[h] >> 32) != v) h = (h + 1) & (tab - 1);
-          if ((uint32_t)aux[h] == (uint32_t)i) {
-            w.tf |= W_NEW;
-            work[i] = w;
+        const uint32_t val = vals[i];
+        if (val & V_FRESH) {
+          const uint32_t v = val & V_MASK;
+          uint32_t h = hash32(v) & (tsz - 1);
+          uint32_t win = tab[h];
+          while (win != 0xFFFFFFFFu && (vals[win] & V_MASK) != v) {   // the entry exists: probing ends on it
+            h = (h + 1) & (tsz - 1);
+            win = tab[h];
+          }
+          if (win == (uint32_t)i) {
             atomicOr(p.bitmap + (size_t)e * p.bm_words + (v >> 5), 1u << (v & 31));
+          } else {
+            // a lower-id copy of v is processed first this round
+            // (cleared after every thread has finished reading vals[])
+            keys[i] |= 0x8000ull;   // slot < 2^15: bit 15 of the key marks "not new"
           }
         }
       }
       __syncthreads();
     }
-    // packed counts: emit (bits 0-31) | recv (32-47) | new (48-63)
+    // packed counts: emit (bits 0-31) | recv (32-47) | new (48-63)   (aux aliases the table)
     for (int i = tid; i < (int)n; i += nt) {
-      const Work w = work[i];
+      const uint32_t val = vals[i];
       uint64_t c = 0;
-      if (w.tf & W_RECV) {
+      if (val & V_RECV) {
         c = 1ull << 32;
-        if (is_server) c |= node_emit_count(p, e, w);
-        if (w.tf & W_NEW) c |= 1ull << 48;
+        const bool is_new = (val & V_FRESH) && !(keys[i] & 0x8000ull);
+        if (is_server) {
+          const uint32_t slot = (uint32_t)(keys[i] & 0x7FFFu);
+          const MsgView w = view_load(myring + (size_t)((head + slot) & p.ring_mask) * 3);
+          c |= node_emit_count(p, e, w, is_new);
+        }
+        if (is_new) c |= 1ull << 48;
       }
       aux[i] = c;
     }
@@ -649,27 +700,25 @@ __global__ void __launch_bounds__(512) k_round(Params p) {
       const uint32_t i = base + tid;
       const bool live = i < n;
       uint32_t my_emit = 0, e_idx0 = 0, new_before = 0;
-      Work w;
+      MsgView w;
       w.src = 0; w.msg_id = 0; w.p0 = 0; w.tf = 0;
       uint64_t p1 = 0;
       if (live) {
-        w = work[i];
         const uint64_t a0 = aux[i], a1 = aux[i + 1];
         e_idx0 = (uint32_t)a0;
         my_emit = (uint32_t)a1 - (uint32_t)a0;
         new_before = (uint32_t)(a0 >> 48);
-        if (w.tf & W_RECV) {
+        if (vals[i] & V_RECV) {
           const uint32_t k = (uint32_t)(a0 >> 32) & 0xFFFFu;
-          const uint32_t slot = (uint32_t)(keys[i] & 0xFFFFu);
+          const uint32_t slot = (uint32_t)(keys[i] & 0x7FFFu);
           const uint4* rp = myring + (size_t)((head + slot) & p.ring_mask) * 3;
+          const uint4 va = rp[0], vb = rp[1], vc = rp[2];
           Rec m;
-          const bool need_full = p.jlevel >= 2 || mailed || (p.workload == MS_W_ECHO);
-          if (need_full) {
-            m = rec_load(rp);
-          } else {
-            m.id = keys[i] >> 16; m.deadline = now; m.src = w.src; m.dest = e; m.msg_id = w.msg_id;
-            m.in_reply_to = 0; m.tf = (w.tf & 0xFFFFu) | (((w.tf >> 16) & 3u) << 16); m.p0 = w.p0; m.p1 = 0;
-          }
+          m.id = (uint64_t)va.x | ((uint64_t)va.y << 32);
+          m.deadline = (int64_t)((uint64_t)va.z | ((uint64_t)va.w << 32));
+          m.src = vb.x; m.dest = vb.y; m.msg_id = vb.z; m.in_reply_to = vb.w;
+          m.tf = vc.x; m.p0 = vc.y; m.p1 = (uint64_t)vc.z | ((uint64_t)vc.w << 32);
+          w.src = m.src; w.msg_id = m.msg_id; w.p0 = m.p0; w.tf = m.tf;
           p1 = m.p1;
           journal_write(p, st, ev_base + k, true, now, m);
           const bool cl = cl_ep || kind_is_client(p.kind[w.src]);
@@ -757,6 +806,8 @@ __global__ void __launch_bounds__(512) k_round(Params p) {
       st->rounds_run += 1;
       st->ticket = 0;
       st->done = 0;
+      st->round_max_window = 0;
+      st->slot_open = 0;
     }
   }
 }
@@ -770,11 +821,16 @@ cudaError_t msk_round_smem_attr(size_t bytes) {
   return cudaFuncSetAttribute(msd::k_round, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+size_t msk_round_smem_bytes(uint32_t cap) { return (size_t)cap * 20 + 16; }
+
 void msk_set_bit(uint32_t* words, size_t word, uint32_t bit, cudaStream_t s) {
   msd::k_set_bit<<<1, 1, 0, s>>>(words, word, bit);
 }
 
-void msk_launch_round(const msd::Params* p, int threads, size_t smem, int with_release, cudaStream_t s) {
+// One round = [k_release] k_snapshot, then k_round once per window-size class
+// (caps[] ascending, threads[] per class); exactly one class executes.
+void msk_launch_round(const msd::Params* p, int n_classes, const uint32_t* caps, const int* threads,
+                      int with_release, cudaStream_t s, cudaEvent_t before_round, cudaEvent_t after_round) {
   const uint32_t n_ep = p->n_ep;
   if (with_release) msd::k_release<<<296, 256, 0, s>>>(*p);
   const int sb = 256;
@@ -782,7 +838,13 @@ void msk_launch_round(const msd::Params* p, int threads, size_t smem, int with_r
   if (sg > 296) sg = 296;
   if (sg < 1) sg = 1;
   msd::k_snapshot<<<sg, sb, 0, s>>>(*p);
-  msd::k_round<<<p->n_inj_tickets + n_ep, threads, smem, s>>>(*p);
+  if (before_round) cudaEventRecord(before_round, s);
+  for (int c = 0; c < n_classes; c++) {
+    const uint32_t lo = c ? caps[c - 1] : 0u;
+    msd::k_round<<<p->n_inj_tickets + n_ep, threads[c], msk_round_smem_bytes(caps[c]), s>>>(
+        *p, lo, caps[c], c == n_classes - 1 ? 1u : 0u);
+  }
+  if (after_round) cudaEventRecord(after_round, s);
 }
 
 }  // extern "C"

@@ -183,6 +183,29 @@ class Sim:
         names = ("rounds", "sends", "recvs", "launches", "lost", "partition_drops", "max_window", "_")
         return {k: int(v) for k, v in zip(names, out)}
 
+    def timer_begin(self):
+        return self._chk(self.L.ms_timer_begin(self.h))
+
+    def timer_end(self):
+        ms = C.c_double(0)
+        self._chk(self.L.ms_timer_end(self.h, C.byref(ms)))
+        return ms.value
+
+    def profile(self, enable=True):
+        return self._chk(self.L.ms_profile(self.h, 1 if enable else 0))
+
+    def profile_read(self):
+        ms = C.c_double(0)
+        n = C.c_uint64(0)
+        self._chk(self.L.ms_profile_read(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, int(n.value)
+
+    def drain_into(self, ev_ptr, cap, body_ptr=None):
+        """Drain up to `cap` events into caller memory (e.g. pinned); returns count."""
+        n = C.c_size_t(0)
+        self._chk(self.L.ms_journal_drain(self.h, ev_ptr, body_ptr, cap, C.byref(n)))
+        return int(n.value)
+
     def node_set(self, node):
         n = self.L.ms_node_set(self.h, node, None, 0)
         out = np.zeros(max(n, 1), dtype=np.uint32)

@@ -216,7 +216,7 @@ struct or_sim {
   std::string error;
   uint64_t stats[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 
-  bool is_client(uint32_t e) const { return eps[e].kind == OR_KIND_CLIENT; }   // util.clj:7-10
+  bool is_client(uint32_t e) const { return eps[e].kind == OR_KIND_CLIENT || eps[e].kind == OR_KIND_SIM_CLIENT; }   // util.clj:7-10
   bool involves_client(const or_msg& m) const {                                // util.clj:12-16
     return is_client(m.src) || is_client(m.dest);
   }
@@ -360,8 +360,10 @@ struct or_sim {
         log_event(true, m);                                        // net.clj:244
         switch (ep.kind) {
           case OR_KIND_CLIENT:
-            if (m.flags & OR_F_REPLY) client_replies++;
             ep.mailbox.push_back(m);
+            break;
+          case OR_KIND_SIM_CLIENT:      // simulated client sink: replies are counted, not mailed
+            if (m.flags & OR_F_REPLY) client_replies++;
             break;
           case OR_KIND_HOST:
             ep.mailbox.push_back(m);

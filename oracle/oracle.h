@@ -83,7 +83,7 @@ enum { OR_W_ECHO = 0, OR_W_BROADCAST = 1, OR_W_GSET = 2 };
 enum { OR_TOPO_GRID = 0, OR_TOPO_LINE = 1, OR_TOPO_TOTAL = 2,
        OR_TOPO_TREE2 = 3, OR_TOPO_TREE3 = 4, OR_TOPO_TREE4 = 5 };
 enum { OR_DIST_CONSTANT = 0, OR_DIST_UNIFORM = 1, OR_DIST_EXPONENTIAL = 2 };
-enum { OR_KIND_SERVER = 0, OR_KIND_CLIENT = 1, OR_KIND_HOST = 2 };
+enum { OR_KIND_SERVER = 0, OR_KIND_CLIENT = 1, OR_KIND_HOST = 2, OR_KIND_SIM_CLIENT = 3 };
 enum {
   OR_T_INIT = 1, OR_T_INIT_OK = 2, OR_T_ERROR = 3,
   OR_T_ECHO = 10, OR_T_ECHO_OK = 11,

@@ -28,7 +28,7 @@ assert BODY_DTYPE.itemsize == 24 and OP_DTYPE.itemsize == 40
 W_ECHO, W_BROADCAST, W_GSET = 0, 1, 2
 TOPO = {"grid": 0, "line": 1, "total": 2, "tree": 3, "tree2": 3, "tree3": 4, "tree4": 5}
 DIST = {"constant": 0, "uniform": 1, "exponential": 2}
-KIND_SERVER, KIND_CLIENT, KIND_HOST = 0, 1, 2
+KIND_SERVER, KIND_CLIENT, KIND_HOST, KIND_SIM_CLIENT = 0, 1, 2, 3
 T = dict(init=1, init_ok=2, error=3, echo=10, echo_ok=11, topology=20, topology_ok=21,
          broadcast=22, broadcast_ok=23, read=24, read_ok=25, add=30, add_ok=31,
          replicate_one=32, replicate_full=33)
