@@ -336,7 +336,7 @@ def gpu_arm(args, rank, world, local_rank):
         "config": {"workload": "broadcast, 4096 nodes, grid 64x64 (BASELINE.json configs[1])",
                    "latency": "constant %d ms" % lat, "values_per_step": V, "step": "1 virtual tick (1 ms)",
                    "delivered_msgs_per_step": recvs // max(K * world, 1), "rounds_per_step": rounds / max(K, 1),
-                   "ring_cap": args.ring_cap, "max_window": args.max_window, "max_window_seen": max_window,
+                   "ring_cap": args.ring_cap, "max_window": args.max_window, "max_window_seen": max_window, "fallback_sorts": c_after["fallback_sorts"] - c_before["fallback_sorts"],
                    "l2_policy": "inputs larger than L2: inbox rings %.1f GB + seen bitmaps, streamed once per round"
                                 % (N_NODES * args.ring_cap * 48 / 1e9),
                    "parallelism": "replicas x%d" % world if world > 1 else "single GPU",

@@ -204,7 +204,7 @@ size_t   ms_node_set(ms_sim* sim, uint32_t node, uint32_t* values, size_t cap);
 uint64_t ms_client_replies(ms_sim* sim);
 
 /* device-side counters for roofline accounting: out = {rounds, sends, recvs,
- * kernel launches, lost, partition_drops, max_window, reserved} */
+ * kernel launches, lost, partition_drops, max_window, windows that needed the full sort} */
 int ms_counters(ms_sim* sim, uint64_t out[8]);
 
 /* Device-side timing on the engine's own CUDA stream (what bench.py reports):

@@ -20,27 +20,28 @@ constexpr uint8_t  kRemoved  = 0x80;          // endpoint kind after remove-node
 // device-latched error codes (DevState.error)
 enum : uint32_t {
   E_NONE = 0, E_RING_OVERFLOW = 1, E_WINDOW_OVERFLOW = 2, E_JOURNAL_OVERFLOW = 3,
-  E_INVALID_DEST = 4, E_LOOKBACK_TIMEOUT = 5, E_VALUE_RANGE = 6, E_MAIL_OVERFLOW = 7,
+  E_INVALID_DEST = 4, E_HISTORY = 5, E_VALUE_RANGE = 6, E_MAIL_OVERFLOW = 7,
   E_CALENDAR_OVERFLOW = 8, E_ID_RANGE = 9
 };
 
-// Mutable per-simulation scalars, resident in HBM, updated by the last CTA of
+// Mutable per-simulation scalars, resident in HBM, committed by the last CTA of
 // every round (net.clj:92-103's atom, minus the queues).
 struct DevState {
   int64_t  now;              // virtual time, ns
   int64_t  stop_ns;          // rounds are no-ops once now >= stop_ns
   uint64_t round;            // round counter
-  uint64_t next_id;          // next-message-id (net.clj:103,197)
-  uint64_t next_event;       // journal next-id (journal.clj:195)
+  uint64_t next_id;          // next-message-id (net.clj:103,197): id base of the round in flight
+  uint64_t next_event;       // journal next-id (journal.clj:195): event base of the round in flight
   uint64_t journal_drained;  // events the host has consumed
-  uint64_t round_ev_total;   // totals of the round in flight (written by the last ticket)
-  uint64_t round_em_total;
+  uint64_t drain_round;      // first round whose events are not fully drained
+  uint64_t jraw_cursor;      // raw journal claim cursor (16-B records)
+  uint64_t jraw_drained;     // raw records below this are free
   uint64_t stats[6];         // {all,clients,servers} x {send,recv}  (net/checker.clj:28-41)
   uint64_t lost;             // sends dropped by the loss roll (net.clj:214-215)
   uint64_t part_drops;       // receives cut by a partition (net.clj:234)
   uint64_t client_replies;   // replies consumed by MS_KIND_SIM_CLIENT sinks
   uint64_t rounds_run;
-  uint32_t ticket;           // dynamic CTA -> ticket assignment
+  uint64_t fallback_sorts;   // windows that needed the full bitonic sort
   uint32_t done;             // CTAs finished this round
   uint32_t zero_pending;     // messages sent this round that are due at `now`
   uint32_t error;            // first latched E_* code
@@ -53,7 +54,20 @@ struct DevState {
   uint32_t cal_release;      // calendar slot to release before the next round (+1), 0 = none
   uint32_t slot_open;        // k_snapshot ran for this launch slot and no k_round class has run yet
   uint32_t round_max_window; // largest window of the round in flight (selects the k_round size class)
-  uint32_t pad0;
+};
+
+// One row per round, kept in a ring of `hist` rounds: what is needed to turn an
+// order key (round, ticket, idx) into the dense message id the reference's
+// global counter would have produced, and raw journal chunks into events.
+struct RoundMeta {
+  uint64_t round;
+  int64_t  now;
+  uint64_t id_base;          // next-message-id at the start of the round
+  uint64_t ev_base;          // journal next-id at the start of the round
+  uint64_t raw_base;         // jraw_cursor at the start of the round
+  uint32_t n_tickets;
+  uint32_t pad;
+  uint64_t ev_total, em_total;
 };
 
 // Fault / latency knobs mutated by jepsen-net calls between rounds (net.clj:105-122).
@@ -68,15 +82,6 @@ struct NetParams {
   uint32_t pad;
 };
 
-// Decoupled look-back status of one ticket (one CTA of the round kernel).
-struct __align__(16) Status {
-  uint32_t flag_agg;         // == round tag when agg_* are valid
-  uint32_t flag_inc;         // == round tag when inc_* are valid
-  uint32_t pad[2];
-  uint64_t agg_ev, agg_em;   // this CTA's events / emissions
-  uint64_t inc_ev, inc_em;   // inclusive prefix over tickets <= this one
-};
-
 struct Params {
   DevState* st;
   NetParams* np;
@@ -88,10 +93,15 @@ struct Params {
   uint4*    ring;            // n_ep * ring_cap * 3 vectors (48-B records)
   uint32_t  ring_cap, ring_mask;
   uint32_t  n_ep, n_servers, n_inj_tickets, max_window;
-  Status*   status;
-  // journal
-  uint4*    jev;             // 2 vectors per event
-  uint4*    jbody;           // 2 vectors per event (level 2)
+  // per-round history (ring of `hist` rows, stride t_max entries)
+  RoundMeta* rmeta;
+  uint32_t* rt_em;           // emissions per ticket, exclusive prefix once the round is committed
+  uint32_t* rt_ev;           // events per ticket, exclusive prefix once committed
+  uint64_t* rt_chunk;        // raw journal position of the ticket's chunk
+  uint32_t  hist, hist_mask, t_max, pad_h;
+  // raw journal: 16-B records, chunk per (round, ticket); bodies (level 2) 32 B at the same index
+  uint4*    jraw;
+  uint4*    jbody;
   uint64_t  jmask;
   uint32_t  jlevel, jdiscard;
   // partitions

@@ -24,6 +24,8 @@ size_t msk_round_smem_bytes(uint32_t cap);
 void msk_launch_round(const msd::Params* p, int n_classes, const uint32_t* caps, const int* threads,
                       int with_release, cudaStream_t s, cudaEvent_t before_round, cudaEvent_t after_round);
 void msk_set_bit(uint32_t* words, size_t word, uint32_t bit, cudaStream_t s);
+void msk_journal_expand(const msd::Params* p, uint64_t r0, uint32_t n_rounds, uint64_t first, uint64_t count,
+                        void* out_ev, void* out_body, cudaStream_t s);
 }
 
 static thread_local std::string g_err;
@@ -51,7 +53,7 @@ static const char* dev_error_text(uint32_t code) {
     case E_WINDOW_OVERFLOW: return "per-round window exceeds ms_config.max_window at endpoint";
     case E_JOURNAL_OVERFLOW: return "journal ring overflow (drain more often or raise journal_cap_log2)";
     case E_INVALID_DEST: return "Invalid dest for message (net.clj:174): endpoint";
-    case E_LOOKBACK_TIMEOUT: return "look-back timeout at ticket";
+    case E_HISTORY: return "message older than the round history (raise ms_config.reserved[0] = history rounds): round";
     case E_VALUE_RANGE: return "broadcast value out of range (raise ms_config.n_values): value";
     case E_MAIL_OVERFLOW: return "host mailbox overflow (raise ms_config.mailbox_cap) at endpoint";
     case E_CALENDAR_OVERFLOW: return "timing wheel overflow (raise calendar_slots/calendar_cap): arg";
@@ -119,6 +121,11 @@ struct ms_sim {
   size_t d_sched_cap = 0, d_tick_cap = 0;
   bool pair_alloc = false;
   FILE* jfile = nullptr;
+  // journal expansion (K3) staging
+  void* stage_ev = nullptr;
+  void* stage_body = nullptr;
+  size_t stage_cap = 0;
+  std::vector<RoundMeta> hmeta;
   // timing
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   bool profiling = false;
@@ -211,28 +218,49 @@ struct ms_sim {
 
   int maybe_flush_journal_file() {
     if (!jfile || cfg.journal_discard || cfg.journal_level == 0) return MS_OK;
-    const uint64_t cap = P.jmask + 1;
-    if (hs.next_event - hs.journal_drained < cap / 2) return MS_OK;
+    if (hs.jraw_cursor - hs.jraw_drained < (P.jmask + 1) / 4 && hs.round - hs.drain_round < P.hist / 4) return MS_OK;
     return flush_journal_file();
   }
 
+  // Expands raw per-(round, ticket) chunks into events in event-id order
+  // (k_journal_expand) in a device staging buffer, then copies them out.
   int drain(ms_event* ev, ms_jbody* bodies, size_t cap, size_t* n_out) {
     *n_out = 0;
     if (cfg.journal_level == 0 || cfg.journal_discard) return MS_OK;
     const uint64_t avail = hs.next_event - hs.journal_drained;
     const size_t n = (size_t)std::min<uint64_t>(avail, cap);
     if (n == 0) return MS_OK;
-    const uint64_t J = P.jmask + 1;
-    const uint64_t start = hs.journal_drained & P.jmask;
-    const size_t first = (size_t)std::min<uint64_t>(n, J - start);
-    CK(cudaMemcpy(ev, (const char*)P.jev + start * 32, first * 32, cudaMemcpyDeviceToHost));
-    if (first < n) CK(cudaMemcpy(ev + first, P.jev, (n - first) * 32, cudaMemcpyDeviceToHost));
-    if (bodies && cfg.journal_level >= 2) {
-      CK(cudaMemcpy(bodies, (const char*)P.jbody + start * 32, first * 32, cudaMemcpyDeviceToHost));
-      if (first < n) CK(cudaMemcpy(bodies + first, P.jbody, (n - first) * 32, cudaMemcpyDeviceToHost));
+    if (!stage_ev) {
+      stage_cap = (size_t)std::min<uint64_t>(P.jmask + 1, 1ull << 22);
+      CK(cudaMalloc(&stage_ev, stage_cap * 32));
+      if (cfg.journal_level >= 2) CK(cudaMalloc(&stage_body, stage_cap * 32));
     }
-    hs.journal_drained += n;
+    hmeta.resize(P.hist);
+    CK(cudaMemcpy(hmeta.data(), P.rmeta, (size_t)P.hist * sizeof(RoundMeta), cudaMemcpyDeviceToHost));
+    auto meta = [&](uint64_t r) -> const RoundMeta& { return hmeta[(size_t)(r & P.hist_mask)]; };
+    size_t done = 0;
+    while (done < n) {
+      const size_t piece = std::min(n - done, stage_cap);
+      const uint64_t first = hs.journal_drained;
+      // committed rounds [drain_round, hs.round) that intersect [first, first + piece)
+      const uint64_t r0 = hs.drain_round;
+      uint64_t r1 = r0;
+      while (r1 < hs.round && meta(r1).round == r1 && meta(r1).ev_base < first + piece) r1++;
+      if (r1 == r0) { set_err("journal drain: round history lost"); return MS_ERR_SIM; }
+      const bool want_body = bodies && cfg.journal_level >= 2;
+      msk_journal_expand(&P, r0, (uint32_t)(r1 - r0), first, piece, stage_ev, want_body ? stage_body : nullptr, stream);
+      CK(cudaStreamSynchronize(stream));
+      CK(cudaMemcpy(ev + done, stage_ev, piece * 32, cudaMemcpyDeviceToHost));
+      if (want_body) CK(cudaMemcpy(bodies + done, stage_body, piece * 32, cudaMemcpyDeviceToHost));
+      done += piece;
+      hs.journal_drained += piece;
+      while (hs.drain_round < hs.round && meta(hs.drain_round).ev_base + meta(hs.drain_round).ev_total <= hs.journal_drained)
+        hs.drain_round++;
+    }
+    hs.jraw_drained = hs.drain_round < hs.round ? meta(hs.drain_round).raw_base : hs.jraw_cursor;
     CK(cudaMemcpy(&P.st->journal_drained, &hs.journal_drained, sizeof(uint64_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(&P.st->drain_round, &hs.drain_round, sizeof(uint64_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(&P.st->jraw_drained, &hs.jraw_drained, sizeof(uint64_t), cudaMemcpyHostToDevice));
     *n_out = n;
     return MS_OK;
   }
@@ -375,15 +403,31 @@ static int build_sim(ms_sim* s, const ms_config* in) {
   P.n_ep = c.n_nodes;
   P.n_inj_tickets = 8;
   P.max_window = c.max_window;
-  if ((rc = s->dalloc(&P.status, (size_t)M + P.n_inj_tickets))) return rc;
+  {
+    // per-round history: 16 B per (round, ticket); keep it under ~1 GB
+    P.t_max = M + P.n_inj_tickets;
+    uint32_t hist = c.reserved[0] ? pow2_at_least(c.reserved[0]) : 4096;
+    while (hist > 64 && (uint64_t)hist * P.t_max * 16 > (1ull << 30)) hist >>= 1;
+    P.hist = hist;
+    P.hist_mask = hist - 1;
+    if ((rc = s->dalloc(&P.rmeta, hist))) return rc;
+    if ((rc = s->dalloc(&P.rt_em, (size_t)hist * P.t_max))) return rc;
+    if ((rc = s->dalloc(&P.rt_ev, (size_t)hist * P.t_max))) return rc;
+    if ((rc = s->dalloc(&P.rt_chunk, (size_t)hist * P.t_max))) return rc;
+    std::vector<RoundMeta> init(hist);
+    memset(init.data(), 0, init.size() * sizeof(RoundMeta));
+    for (uint32_t i = 1; i < hist; i++) init[i].round = ~0ull;
+    CK(cudaMemcpyAsync(P.rmeta, init.data(), init.size() * sizeof(RoundMeta), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+  }
   P.jlevel = c.journal_level;
   P.jdiscard = c.journal_discard;
   if (c.journal_level) {
     const uint64_t J = 1ull << c.journal_cap_log2;
     void* ptr = nullptr;
-    CK(cudaMalloc(&ptr, J * 32));
+    CK(cudaMalloc(&ptr, J * 16));
     s->allocs.push_back(ptr);
-    P.jev = (uint4*)ptr;
+    P.jraw = (uint4*)ptr;
     P.jmask = J - 1;
     if (c.journal_level >= 2) {
       CK(cudaMalloc(&ptr, J * 32));
@@ -489,6 +533,8 @@ void ms_destroy(ms_sim* s) {
   cudaSetDevice(s->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
   for (void* p : s->allocs) cudaFree(p);
+  if (s->stage_ev) cudaFree(s->stage_ev);
+  if (s->stage_body) cudaFree(s->stage_body);
   if (s->d_sched) cudaFree(s->d_sched);
   if (s->d_tick_off) cudaFree(s->d_tick_off);
   for (cudaEvent_t e : s->prof_ev) if (e) cudaEventDestroy(e);
@@ -580,7 +626,8 @@ int ms_schedule_ops(ms_sim* s, const ms_op* ops, size_t n) {
 // true when the device refuses to run rounds until the host drains the journal
 static bool journal_blocked(const ms_sim* s) {
   if (!s->cfg.journal_level || s->cfg.journal_discard) return false;
-  return s->hs.next_event - s->hs.journal_drained > (s->P.jmask + 1) / 2;
+  if (s->hs.jraw_cursor - s->hs.jraw_drained > (s->P.jmask + 1) / 2) return true;
+  return s->hs.round - s->hs.drain_round + 2 >= s->P.hist;
 }
 
 static int step_locked(ms_sim* s, uint64_t n_rounds, int64_t stop) {
@@ -599,8 +646,10 @@ int ms_step(ms_sim* s, uint64_t n_rounds) {
   while (n_rounds) {
     if (journal_blocked(s)) { set_err("journal ring half full: drain it (ms_journal_drain) before stepping"); return MS_ERR_CAPACITY; }
     // one round at a time near the watermark so that "exactly n rounds" holds
-    const uint64_t pending = s->cfg.journal_discard ? 0 : s->hs.next_event - s->hs.journal_drained;
-    const uint64_t b = (s->cfg.journal_level && pending > (s->P.jmask + 1) / 4) ? 1 : std::min<uint64_t>(n_rounds, 64);
+    const bool near_full = s->cfg.journal_level && !s->cfg.journal_discard &&
+                           (s->hs.jraw_cursor - s->hs.jraw_drained > (s->P.jmask + 1) / 4 ||
+                            s->hs.round - s->hs.drain_round + 70 >= s->P.hist);
+    const uint64_t b = near_full ? 1 : std::min<uint64_t>(n_rounds, 64);
     const uint64_t r0 = s->hs.rounds_run;
     const int rc = step_locked(s, b, INT64_MAX);
     if (rc) return rc;
@@ -771,7 +820,7 @@ int ms_counters(ms_sim* s, uint64_t out[8]) {
   out[4] = s->hs.lost;
   out[5] = s->hs.part_drops;
   out[6] = s->hs.max_window_seen;
-  out[7] = 0;
+  out[7] = s->hs.fallback_sorts;
   return MS_OK;
 }
 

@@ -1,22 +1,31 @@
 // ms_kernels.cu -- hand-written sm_100a kernels of the discrete-event engine.
 //
-// One *round* of the simulation is three launches:
+// One *round* of the simulation is:
 //   k_release   (only when a latency distribution can produce latency > 0):
 //               scatters the timing-wheel slot that just became due into the
 //               per-endpoint inbox rings;
 //   k_snapshot  head <- limit, limit <- tail: freezes the window every endpoint
-//               consumes this round, so messages sent in round r are first
-//               visible in round r+1;
+//               consumes this round (messages sent in round r are first visible
+//               in round r+1) and finds the largest window of the round;
 //   k_round     ONE fused kernel replacing process.clj's stdin/stdout pumps,
 //               the node program, net/send! (net.clj:189-221) and net/recv!
-//               (net.clj:223-247): per endpoint CTA
-//                 stage window keys -> bitonic sort by message id (shared memory)
-//                 -> partition check at dequeue -> node transition
+//               (net.clj:223-247).  One CTA per endpoint ("ticket"), CTAs are
+//               independent of each other:
+//                 load window -> order it by (round, sender, emission index),
+//                 which is the order of the reference's global message-id
+//                 counter -> partition check at dequeue -> node transition
 //                 -> block scan of (recv, emit, new) counts
-//                 -> decoupled look-back across CTAs (dense message / event ids)
-//                 -> :recv events, emissions: Philox loss/latency, :send events,
-//                    warp-aggregated scatter into the destination rings.
+//                 -> :recv records, emissions: Philox loss/latency, :send
+//                    records, scatter into the destination rings.
+//               Launched once per window-size class; exactly one class runs.
 // No outbox exists: a message goes HBM ring -> registers -> HBM ring.
+//
+// Dense message ids / event ids (the reference's two global counters,
+// net.clj:197 and journal.clj:228) are prefix sums over (round, ticket, idx).
+// They are NOT computed on the critical path: every CTA records its counts in
+// a per-round table, the last CTA of the round turns them into prefixes, and
+// ids are resolved when a message is received (one table lookup per sender
+// block) or when the journal is drained (k_journal_expand).
 //
 // HBM-bound integer work; tensor cores are deliberately idle.
 #include <cuda_runtime.h>
@@ -26,21 +35,12 @@
 namespace msd {
 
 #define FULL 0xFFFFFFFFu
+constexpr int MAXB = 64;            // sender blocks handled by the fast ordering path
+constexpr int MAXNB = 8;            // neighbor slots handled by per-(CTA, neighbor) claims
+constexpr uint64_t RECV_BIT = 1ull << 63;
 
 // ------------------------------------------------------------------ small PTX helpers
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t* p) {
-  uint64_t v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
+__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) { return __ldcg(p); }
 // streaming 16-byte store: journal / ring records are written once and read by
 // another SM (or the host) later, so keep them out of L1.
 __device__ __forceinline__ void st_v4(uint4* p, uint4 v) {
@@ -48,7 +48,7 @@ __device__ __forceinline__ void st_v4(uint4* p, uint4 v) {
                "r"(v.z), "r"(v.w)
                : "memory");
 }
-__device__ __forceinline__ uint4 ld_v4(const uint4* p) {
+__device__ __forceinline__ uint4 ld_v4_stream(const uint4* p) {
   uint4 v;
   asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
@@ -62,57 +62,53 @@ __device__ __forceinline__ void latch_error(DevState* st, uint32_t code, uint32_
 }
 
 // A round is skipped (by every kernel of the round alike) when the simulation has
-// reached its stop time, an error is latched, or the journal ring is more than
-// half full and the host has not drained it yet (back-pressure).
+// reached its stop time, an error is latched, or the host has to drain the
+// journal first (raw ring half full / round history nearly exhausted).
 __device__ __forceinline__ bool round_skipped(const Params& p, const DevState* st) {
   if (st->now >= st->stop_ns || st->error) return true;
-  if (p.jlevel && !p.jdiscard && st->next_event - st->journal_drained > ((p.jmask + 1) >> 1)) return true;
+  if (p.jlevel && !p.jdiscard) {
+    if (st->jraw_cursor - st->jraw_drained > ((p.jmask + 1) >> 1)) return true;
+    if (st->round - st->drain_round + 2 >= p.hist) return true;
+  }
   return false;
 }
 
-// ------------------------------------------------------------------ record packing
-struct Rec {  // ms_msg in registers
-  uint64_t id;
-  int64_t deadline;
+// ------------------------------------------------------------------ ring records
+// 48-B inbox record: v0 = order key {idx, ticket, round}, v1 = {src, dest,
+// msg_id, in_reply_to}, v2 = {type | flags << 16, p0, p1}.
+struct Rec {
+  uint64_t round;
+  uint32_t ticket, idx;
   uint32_t src, dest, msg_id, in_reply_to;
-  uint32_t tf;  // type | flags << 16
+  uint32_t tf;
   uint32_t p0;
   uint64_t p1;
 };
 
 __device__ __forceinline__ void rec_store(uint4* slot, const Rec& r) {
-  st_v4(slot + 0, make_uint4((uint32_t)r.id, (uint32_t)(r.id >> 32), (uint32_t)r.deadline,
-                             (uint32_t)((uint64_t)r.deadline >> 32)));
+  st_v4(slot + 0, make_uint4(r.idx, r.ticket, (uint32_t)r.round, (uint32_t)(r.round >> 32)));
   st_v4(slot + 1, make_uint4(r.src, r.dest, r.msg_id, r.in_reply_to));
   st_v4(slot + 2, make_uint4(r.tf, r.p0, (uint32_t)r.p1, (uint32_t)(r.p1 >> 32)));
 }
-__device__ __forceinline__ Rec rec_load(const uint4* slot) {
-  const uint4 a = ld_v4(slot + 0), b = ld_v4(slot + 1), c = ld_v4(slot + 2);
+__device__ __forceinline__ Rec rec_unpack(uint4 a, uint4 b, uint4 c) {
   Rec r;
-  r.id = (uint64_t)a.x | ((uint64_t)a.y << 32);
-  r.deadline = (int64_t)((uint64_t)a.z | ((uint64_t)a.w << 32));
+  r.idx = a.x; r.ticket = a.y;
+  r.round = (uint64_t)a.z | ((uint64_t)a.w << 32);
   r.src = b.x; r.dest = b.y; r.msg_id = b.z; r.in_reply_to = b.w;
   r.tf = c.x; r.p0 = c.y;
   r.p1 = (uint64_t)c.z | ((uint64_t)c.w << 32);
   return r;
 }
 
-__device__ __forceinline__ void journal_write(const Params& p, DevState* st, uint64_t ev_pos, bool recv,
-                                              int64_t now, const Rec& r) {
-  if (p.jlevel == 0) return;
-  if (!p.jdiscard && ev_pos - ld_relaxed_u64(&st->journal_drained) > p.jmask) {
-    latch_error(st, E_JOURNAL_OVERFLOW, (uint32_t)ev_pos);
-    return;
+// dense id of (round, ticket, idx): id_base[round] + emit_prefix[round][ticket] + idx
+__device__ __forceinline__ uint64_t dense_base(const Params& p, DevState* st, uint64_t round, uint32_t ticket) {
+  const uint32_t row = (uint32_t)round & p.hist_mask;
+  const RoundMeta* m = p.rmeta + row;
+  if (m->round != round || ticket >= p.t_max) {
+    latch_error(st, E_HISTORY, (uint32_t)round);
+    return 0;
   }
-  const uint64_t eid = ev_pos | (recv ? MS_EVENT_RECV : 0ull);
-  uint4* e = p.jev + (ev_pos & p.jmask) * 2;
-  st_v4(e + 0, make_uint4((uint32_t)eid, (uint32_t)(eid >> 32), (uint32_t)now, (uint32_t)((uint64_t)now >> 32)));
-  st_v4(e + 1, make_uint4((uint32_t)r.id, (uint32_t)(r.id >> 32), r.src, r.dest));
-  if (p.jlevel >= 2) {
-    uint4* b = p.jbody + (ev_pos & p.jmask) * 2;
-    st_v4(b + 0, make_uint4((uint32_t)r.id, (uint32_t)(r.id >> 32), r.msg_id, r.in_reply_to));
-    st_v4(b + 1, make_uint4(r.tf, r.p0, (uint32_t)r.p1, (uint32_t)(r.p1 >> 32)));
-  }
+  return m->id_base + p.rt_em[(size_t)row * p.t_max + ticket];
 }
 
 // ------------------------------------------------------------------ block primitives
@@ -156,108 +152,61 @@ __device__ uint64_t block_excl_scan(uint64_t* a, int n, uint64_t* wtmp /* >= 33 
   return total;
 }
 
-// In-place ascending bitonic sort of keys[0..np) (np a power of two).
-__device__ void block_bitonic_sort(uint64_t* keys, int np) {
+// Fallback ordering: bitonic sort of the index array `ord` (np a power of two,
+// pads = 0xFFFF) by (keyA, keyB) of the records they point to.
+__device__ void block_bitonic_sort_idx(uint16_t* ord, const uint64_t* keyA, const uint32_t* keyB, int np) {
   const int nt = blockDim.x, tid = threadIdx.x;
   for (int k = 2; k <= np; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
       for (int t = tid; t < (np >> 1); t += nt) {
-        // t-th compare-exchange pair of this stage
         const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
         const int l = i | j;
         const bool asc = (i & k) == 0;
-        const uint64_t a = keys[i], b = keys[l];
-        if ((a > b) == asc) { keys[i] = b; keys[l] = a; }
+        const uint16_t a = ord[i], b = ord[l];
+        bool gt;   // key(a) > key(b)
+        if (a == 0xFFFF) gt = (b != 0xFFFF);
+        else if (b == 0xFFFF) gt = false;
+        else gt = keyA[a] > keyA[b] || (keyA[a] == keyA[b] && keyB[a] > keyB[b]);
+        if (gt == asc) { ord[i] = b; ord[l] = a; }
       }
       __syncthreads();
     }
   }
 }
 
-// Decoupled look-back (Merrill & Garland single-pass scan): exclusive prefix of
-// (events, emissions) over all lower tickets.  Executed by warp 0.
-__device__ void lookback(const Params& p, DevState* st, uint32_t ticket, uint32_t tag, uint64_t agg_ev,
-                         uint64_t agg_em, uint64_t* out /* smem [2] */) {
-  const int lane = threadIdx.x & 31;
-  Status* mine = p.status + ticket;
-  if (ticket == 0) {
-    if (lane == 0) {
-      mine->inc_ev = agg_ev; mine->inc_em = agg_em;
-      mine->agg_ev = agg_ev; mine->agg_em = agg_em;
-      __threadfence();
-      st_release_u32(&mine->flag_agg, tag);
-      st_release_u32(&mine->flag_inc, tag);
-      out[0] = 0; out[1] = 0;
-    }
-    return;
-  }
-  if (lane == 0) {
-    mine->agg_ev = agg_ev; mine->agg_em = agg_em;
-    __threadfence();
-    st_release_u32(&mine->flag_agg, tag);
-  }
-  uint64_t ev = 0, em = 0;
-  int64_t pos = (int64_t)ticket - 1;   // nearest predecessor inspected by lane 0
-  bool failed = false;
-  for (;;) {
-    const int64_t idx = pos - lane;
-    bool has_inc = false, has_agg = false;
-    if (idx < 0) {
-      has_inc = true;                 // virtual ticket -1: inclusive prefix 0
-    } else {
-      const Status* s = p.status + idx;
-      uint32_t spins = 0;
-      for (;;) {
-        if (ld_acquire_u32(&s->flag_inc) == tag) { has_inc = true; break; }
-        if (ld_acquire_u32(&s->flag_agg) == tag) break;
-        if (++spins > (1u << 22)) { failed = true; break; }
-        __nanosleep(64);
-      }
-    }
-    if (__any_sync(FULL, failed)) { failed = true; break; }
-    const uint32_t inc_mask = __ballot_sync(FULL, has_inc);
-    const int first = inc_mask ? (__ffs(inc_mask) - 1) : 32;
-    uint64_t cev = 0, cem = 0;
-    if (lane < first) {               // predecessors closer than the first inclusive one
-      const Status* s = p.status + idx;
-      cev = ld_relaxed_u64(&s->agg_ev); cem = ld_relaxed_u64(&s->agg_em);
-    } else if (lane == first && idx >= 0) {
-      const Status* s = p.status + idx;
-      cev = ld_relaxed_u64(&s->inc_ev); cem = ld_relaxed_u64(&s->inc_em);
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      cev += __shfl_xor_sync(FULL, cev, d);
-      cem += __shfl_xor_sync(FULL, cem, d);
-    }
-    ev += cev; em += cem;
-    if (inc_mask) break;
-    pos -= 32;
-  }
-  if (lane == 0) {
-    if (failed) latch_error(st, E_LOOKBACK_TIMEOUT, ticket);
-    mine->inc_ev = ev + agg_ev; mine->inc_em = em + agg_em;
-    __threadfence();
-    st_release_u32(&mine->flag_inc, tag);
-    out[0] = ev; out[1] = em;
-  }
-}
-
 // ------------------------------------------------------------------ emission (net/send!, net.clj:189-221)
 struct EmitCtx {
   int64_t now;
-  uint64_t id0;      // id of this CTA's emission 0
-  uint64_t ev0;      // journal position of this CTA's emission 0
-  uint32_t round_lo, round_hi;
+  uint64_t round;
+  uint64_t chunk;    // raw journal position of this CTA's chunk
+  uint32_t n_recv;   // :recv records precede the :send records in the chunk
+  uint32_t ticket;
   uint32_t emitter;  // Philox stream: endpoint index or kInjector
   uint32_t idx_bias; // added to local_idx for the Philox counter (injector slices)
   // per-thread counters, reduced at the end of the CTA
   uint32_t c_send_cl, c_send_sv, c_lost, c_zero;
 };
 
-// Must be called convergently by all 32 lanes of a warp.
+__device__ __forceinline__ void journal_raw(const Params& p, uint64_t pos, uint64_t id_or_idx, bool recv,
+                                            const Rec& r) {
+  if (p.jlevel == 0) return;
+  const uint64_t v = id_or_idx | (recv ? RECV_BIT : 0ull);
+  st_v4(p.jraw + (pos & p.jmask), make_uint4((uint32_t)v, (uint32_t)(v >> 32), r.src, r.dest));
+  if (p.jlevel >= 2) {
+    uint4* b = p.jbody + (pos & p.jmask) * 2;
+    st_v4(b + 0, make_uint4((uint32_t)v, (uint32_t)(v >> 32), r.msg_id, r.in_reply_to));
+    st_v4(b + 1, make_uint4(r.tf, r.p0, (uint32_t)r.p1, (uint32_t)(r.p1 >> 32)));
+  }
+}
+
+// Must be called convergently by all 32 lanes of a warp.  direct_pos != NO_DIRECT
+// means ring space for this record was already claimed by the CTA (per-neighbor
+// block claim); otherwise slots are claimed here, one atomic per destination
+// per warp.
+constexpr uint32_t NO_DIRECT = 0xFFFFFFFFu;
 __device__ __forceinline__ void emit_one(const Params& p, DevState* st, const NetParams& np, EmitCtx& cx,
-                                         bool valid, Rec& r, uint32_t local_idx) {
+                                         bool valid, Rec& r, uint32_t local_idx, uint32_t direct_pos,
+                                         bool has_direct) {
   const int lane = threadIdx.x & 31;
   bool push = false;
   if (valid && (r.dest >= p.n_ep || p.kind[r.dest] == kRemoved)) {   // net.clj:172-175
@@ -265,22 +214,26 @@ __device__ __forceinline__ void emit_one(const Params& p, DevState* st, const Ne
     valid = false;
   }
   if (valid) {
-    r.id = cx.id0 + local_idx;                                       // net.clj:197
+    r.round = cx.round; r.ticket = cx.ticket; r.idx = local_idx;     // order key == id order (net.clj:197)
     uint32_t x[4];
-    philox4x32_10(local_idx + cx.idx_bias, cx.emitter, cx.round_lo, cx.round_hi, p.seed_lo, p.seed_hi, x);
+    philox4x32_10(local_idx + cx.idx_bias, cx.emitter, (uint32_t)cx.round, (uint32_t)(cx.round >> 32),
+                  p.seed_lo, p.seed_hi, x);
     const bool cl = kind_is_client(p.kind[r.src]) || kind_is_client(p.kind[r.dest]);   // util.clj:12-16
     const uint64_t lat = cl ? 0ull : latency_ms(np, x);              // net.clj:185-187
-    r.deadline = cx.now + (int64_t)lat * kTickNs;                    // net.clj:202-205
-    journal_write(p, st, cx.ev0 + local_idx, false, cx.now, r);      // net.clj:208 (before the loss roll)
+    journal_raw(p, cx.chunk + cx.n_recv + local_idx, local_idx, false, r);   // net.clj:208 (before the loss roll)
     if (cl) cx.c_send_cl++; else cx.c_send_sv++;
     if ((uint64_t)x[0] < np.loss_thresh) {                           // net.clj:214-215
       cx.c_lost++;
-    } else if (r.deadline <= cx.now) {
-      push = true;
+    } else if (lat == 0) {                                           // deadline == now: next delta round
       cx.c_zero++;
+      if (has_direct) {
+        rec_store(p.ring + ((size_t)r.dest * p.ring_cap + (direct_pos & p.ring_mask)) * 3, r);
+      } else {
+        push = true;
+      }
     } else {
-      // timing wheel: slot of the deadline tick
-      const uint64_t tick = (uint64_t)(r.deadline / kTickNs);
+      // timing wheel: slot of the deadline tick (net.clj:202-205)
+      const uint64_t tick = (uint64_t)(cx.now / kTickNs) + lat;
       if (p.cal == nullptr || lat >= p.cal_slots) {
         latch_error(st, E_CALENDAR_OVERFLOW, (uint32_t)lat);
       } else {
@@ -348,21 +301,28 @@ __global__ void k_release(Params p) {
   const uint32_t n_round = (n + 31u) & ~31u;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
     const bool valid = i < n;
-    Rec r;
-    r.dest = 0;
-    if (valid) r = rec_load(p.cal + ((size_t)slot * p.cal_cap + i) * 3);
-    const uint32_t key = valid ? r.dest : (0x80000000u | (uint32_t)lane);
+    uint4 a = make_uint4(0, 0, 0, 0), b = a, c = a;
+    if (valid) {
+      const uint4* src = p.cal + ((size_t)slot * p.cal_cap + i) * 3;
+      a = ld_v4_stream(src); b = ld_v4_stream(src + 1); c = ld_v4_stream(src + 2);
+    }
+    const uint32_t dest = b.y;
+    const uint32_t key = valid ? dest : (0x80000000u | (uint32_t)lane);
     const uint32_t mask = __match_any_sync(FULL, key);
     const int leader = __ffs(mask) - 1;
     const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
     uint32_t base = 0;
-    if (valid && lane == leader) base = atomicAdd(&p.tail[r.dest], (uint32_t)__popc(mask));
+    if (valid && lane == leader) base = atomicAdd(&p.tail[dest], (uint32_t)__popc(mask));
     base = __shfl_sync(FULL, base, leader);
     if (valid) {
       const uint32_t pos = base + rank;
       // the previous window [head, limit) is fully consumed; only limit matters here
-      if ((uint32_t)(pos - p.limit[r.dest]) >= p.ring_cap) latch_error(st, E_RING_OVERFLOW, r.dest);
-      else rec_store(p.ring + ((size_t)r.dest * p.ring_cap + (pos & p.ring_mask)) * 3, r);
+      if ((uint32_t)(pos - p.limit[dest]) >= p.ring_cap) {
+        latch_error(st, E_RING_OVERFLOW, dest);
+      } else {
+        uint4* dst = p.ring + ((size_t)dest * p.ring_cap + (pos & p.ring_mask)) * 3;
+        st_v4(dst, a); st_v4(dst + 1, b); st_v4(dst + 2, c);
+      }
     }
   }
 }
@@ -383,7 +343,7 @@ __device__ __forceinline__ MsgView view_load(const uint4* rec) {
 }
 
 // vals[] bits
-constexpr uint32_t V_FRESH = 1u << 31;  // broadcast value unseen before this round
+constexpr uint32_t V_FRESH = 1u << 31;  // broadcast value unseen so far (after PC: first sight = new)
 constexpr uint32_t V_RECV = 1u << 30;   // passed the partition check
 constexpr uint32_t V_MASK = (1u << 30) - 1u;
 
@@ -435,11 +395,13 @@ __device__ __forceinline__ uint32_t node_emit_count(const Params& p, uint32_t e,
   }
 }
 
-// k-th emission of a delivered message (emit phase)
-__device__ __forceinline__ void node_emit(const Params& p, uint32_t e, const MsgView& w, uint32_t k,
-                                          uint32_t nemit, uint32_t emit_idx, uint32_t msg_id_base,
-                                          uint32_t set_before, uint32_t new_before, uint64_t p1, Rec& r) {
+// k-th emission of a delivered message (emit phase).  Returns the neighbor slot
+// the emission goes to when it is gossip to a topology neighbor, else -1.
+__device__ __forceinline__ int node_emit(const Params& p, uint32_t e, const MsgView& w, uint32_t k,
+                                         uint32_t nemit, uint32_t emit_idx, uint32_t msg_id_base,
+                                         uint32_t set_before, uint32_t new_before, uint64_t p1, Rec& r) {
   const uint32_t type = w.tf & 0xFFFFu;
+  int slot = -1;
   r.src = e; r.dest = w.src; r.msg_id = 0; r.in_reply_to = w.msg_id;
   r.p0 = 0; r.p1 = 0;
   uint32_t otype = MS_T_ERROR, oflags = MS_F_REPLY;
@@ -460,6 +422,7 @@ __device__ __forceinline__ void node_emit(const Params& p, uint32_t e, const Msg
         const uint32_t ps = nbr_pos(p, e, w.src);
         const uint32_t j = (ps != 0xFFFFFFFFu && k >= ps) ? k + 1 : k;
         r.dest = nbr_at(p, e, j);
+        slot = (int)j;
         otype = MS_T_BROADCAST; oflags = 0; r.in_reply_to = 0; r.p0 = w.p0;
         break;
       }
@@ -467,13 +430,15 @@ __device__ __forceinline__ void node_emit(const Params& p, uint32_t e, const Msg
     }
   }
   r.tf = otype | (oflags << 16);
+  return slot;
 }
 
 // ------------------------------------------------------------------ k_round
-// One CTA per ticket.  Dynamic shared memory, `cap` = window capacity of this
-// size class:  keys u64[cap] | vals u32[cap] | aux u64[cap+1]   (20 B / message)
-// The same kernel is launched once per size class every round; only the class
-// whose (cap_lo, cap] interval contains the round's largest window executes.
+// One CTA per ticket: tickets [0, n_inj_tickets) are injector slices, ticket
+// n_inj_tickets + e is endpoint e.  Dynamic shared memory, `cap` = window capacity
+// of this size class:
+//   reg1 u64[cap+1] (order keys -> dedupe table -> packed count scan)
+//   keyB u32[cap] | vals u32[cap] | ord u16[cap]                    = 18 B / message
 __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap_lo, uint32_t cap, uint32_t last_class) {
   DevState* st = p.st;
   if (round_skipped(p, st) || !st->slot_open) return;
@@ -484,37 +449,50 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap_lo, uin
   }
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
-  uint32_t* vals = reinterpret_cast<uint32_t*>(keys + cap);
-  uint64_t* aux = reinterpret_cast<uint64_t*>(vals + cap);     // cap+1 entries
-  uint32_t* tab = reinterpret_cast<uint32_t*>(aux);            // dedupe table, 2*npad entries
+  uint64_t* reg1 = reinterpret_cast<uint64_t*>(smem_raw);          // cap+1 entries
+  uint32_t* keyB = reinterpret_cast<uint32_t*>(reg1 + cap + 1);
+  uint32_t* vals = keyB + cap;
+  uint16_t* ord = reinterpret_cast<uint16_t*>(vals + cap);
+  uint64_t* keyA = reg1;
+  uint32_t* tab = reinterpret_cast<uint32_t*>(reg1);               // dedupe table, 2*npad entries
+  uint64_t* aux = reg1;                                            // packed counts
 
-  __shared__ uint32_t s_ticket;
-  __shared__ uint64_t s_pref[2];
   __shared__ uint64_t s_wtmp[34];
   __shared__ NetParams s_np;
-  __shared__ uint32_t s_mail_base;
+  __shared__ uint32_t s_wcnt[17];
+  __shared__ uint32_t s_misc[8];       // 0: mail base, 1: use_blocks, 3: inj-server-src flag, 4: is_last
+  __shared__ uint64_t s_chunk;
+  // sender blocks of the window (fast ordering path)
+  __shared__ uint16_t s_bstart[MAXB + 1];     // window offset of block r (arrival order)
+  __shared__ uint16_t s_brank[MAXB];          // sorted rank of block r
+  __shared__ uint16_t s_boff[MAXB + 1];       // sorted: first sorted position of block rho
+  __shared__ uint64_t s_bkeyA[MAXB];          // sorted: (round << 24 | ticket)
+  __shared__ uint64_t s_bbase[MAXB];          // sorted: dense id of the block's idx 0
+  __shared__ uint16_t s_S[MAXB + 1][MAXNB];   // sorted: new messages from neighbor j in blocks < rho
+  __shared__ uint32_t s_nbbase[MAXNB];        // ring position claimed for this CTA's gossip to neighbor j
 
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
-  if (tid == 0) {
-    s_ticket = atomicAdd(&st->ticket, 1u);
-    s_np = *p.np;
-  }
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_np = *p.np;
+  if (tid < 8) s_misc[tid] = 0;
   __syncthreads();
-  const uint32_t ticket = s_ticket;
+  const uint32_t ticket = blockIdx.x;
   const NetParams np = s_np;
   const int64_t now = st->now;
   const uint64_t round = st->round;
-  const uint32_t tag = (uint32_t)round + 1u;
   const uint32_t T = p.n_inj_tickets + p.n_ep;
+  const uint32_t row = (uint32_t)round & p.hist_mask;
 
   EmitCtx cx;
   cx.now = now;
-  cx.round_lo = (uint32_t)round; cx.round_hi = (uint32_t)(round >> 32);
+  cx.round = round;
+  cx.ticket = ticket;
   cx.idx_bias = 0;
+  cx.chunk = 0;
+  cx.n_recv = 0;
+  cx.emitter = 0;
   cx.c_send_cl = cx.c_send_sv = cx.c_lost = cx.c_zero = 0;
   uint32_t c_recv_cl = 0, c_recv_sv = 0, c_part = 0, c_replies = 0;
-  uint64_t n_ev_local = 0, n_em_local = 0;
+  uint32_t n_ev_local = 0, n_em_local = 0;
 
   if (ticket < p.n_inj_tickets) {
     // ---------------------------------------------------------- injector slice
@@ -530,10 +508,11 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap_lo, uin
     const uint32_t lo = min(ticket * chunk, K), hi_s = min(lo + chunk, K);
     const uint32_t n_local = hi_s - lo;
     n_ev_local = n_local; n_em_local = n_local;
-    if (tid < 32) lookback(p, st, ticket, tag, n_ev_local, n_em_local, s_pref);
+    if (tid == 0)
+      s_chunk = (n_local && p.jlevel)
+                    ? atomicAdd((unsigned long long*)&st->jraw_cursor, (unsigned long long)n_local) : 0ull;
     __syncthreads();
-    cx.id0 = st->next_id + s_pref[1];
-    cx.ev0 = st->next_event + s_pref[0];
+    cx.chunk = s_chunk;
     cx.emitter = kInjector;
     cx.idx_bias = lo;
     for (uint32_t base = 0; base < n_local; base += nt) {
@@ -553,7 +532,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap_lo, uin
           r.tf = (uint32_t)op.body.type | ((uint32_t)op.body.flags << 16); r.p0 = op.body.p0; r.p1 = op.body.p1;
         }
       }
-      emit_one(p, st, np, cx, valid, r, j);
+      emit_one(p, st, np, cx, valid, r, j, 0, false);
     }
   } else {
     // ---------------------------------------------------------- endpoint CTA
@@ -566,168 +545,291 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap_lo, uin
       n = 0;
     }
     const uint4* myring = p.ring + (size_t)e * p.ring_cap * 3;
-    int npad = 1;
-    while (npad < (int)n) npad <<= 1;
-
-    // P1: stage (id << 16 | slot) keys; slot = offset inside the window
-    for (int i = tid; i < npad; i += nt) {
-      uint64_t k = ~0ull;
-      if (i < (int)n) {
-        const uint64_t id = *reinterpret_cast<const uint64_t*>(myring + (size_t)((head + i) & p.ring_mask) * 3);
-        if (id >> 48) latch_error(st, E_ID_RANGE, e);
-        k = (id << 16) | (uint64_t)i;
-      }
-      keys[i] = k;
-    }
-    __syncthreads();
-    // P2: order the due set by message id (all due deadlines equal `now`; the
-    // reference's PriorityBlockingQueue leaves ties unspecified, net.clj:39-40,145)
-    if (n > 1) block_bitonic_sort(keys, npad);
-
-    // P3: partition check at dequeue (net.clj:234); broadcast: first-sight dedupe table
     const bool is_server = (kind == MS_KIND_SERVER);
     const bool bcast = is_server && p.workload == MS_W_BROADCAST;
-    const int tsz = 2 * npad;   // dedupe table size (u32 entries)
-    if (bcast) for (int i = tid; i < tsz; i += nt) tab[i] = 0xFFFFFFFFu;
-    __syncthreads();
     const uint32_t* mybits = (is_server && p.bitmap) ? p.bitmap + (size_t)e * p.bm_words : nullptr;
+
+    // PA: one pass over the window in arrival order: order keys, partition check
+    //     at dequeue (net.clj:234), first half of the seen-set test
     for (int i = tid; i < (int)n; i += nt) {
-      const uint32_t slot = (uint32_t)(keys[i] & 0xFFFFu);
-      const MsgView w = view_load(myring + (size_t)((head + slot) & p.ring_mask) * 3);
+      const uint4* rp = myring + (size_t)((head + i) & p.ring_mask) * 3;
+      const uint4 a = rp[0], b = rp[1], c = rp[2];
+      const uint64_t rnd = (uint64_t)a.z | ((uint64_t)a.w << 32);
+      keyA[i] = (rnd << 24) | (uint64_t)(a.y & 0xFFFFFFu);
+      keyB[i] = a.x;
+      const uint32_t src = b.x, tf = c.x, v = c.y;
+      if (a.y < p.n_inj_tickets && src < p.n_servers) s_misc[3] = 1;   // injected on behalf of a server
       bool cut = false;
       if (np.pair_active && p.pair_bits)
-        cut = (p.pair_bits[(size_t)e * p.pair_words + (w.src >> 5)] >> (w.src & 31)) & 1u;
+        cut = (p.pair_bits[(size_t)e * p.pair_words + (src >> 5)] >> (src & 31)) & 1u;
       if (!cut && np.comp_active) {
         // bulk partition: endpoints in different components are cut; 0xFFFFFFFF = not listed (never cut)
-        const uint32_t cs = p.comp[w.src], ce = p.comp[e];
+        const uint32_t cs = p.comp[src], ce = p.comp[e];
         cut = cs != ce && cs != 0xFFFFFFFFu && ce != 0xFFFFFFFFu;
       }
       uint32_t val = cut ? 0u : V_RECV;
-      if (bcast && !cut && (w.tf & 0xFFFFu) == MS_T_BROADCAST && !((w.tf >> 16) & MS_F_REPLY)) {
-        const uint32_t v = w.p0;
+      if (bcast && !cut && (tf & 0xFFFFu) == MS_T_BROADCAST && !((tf >> 16) & MS_F_REPLY)) {
         if (v >= p.n_values || v > V_MASK) {
           latch_error(st, E_VALUE_RANGE, v);
         } else {
           val |= v;
-          if (!((mybits[v >> 5] >> (v & 31)) & 1u)) {
-            val |= V_FRESH;
-            // publish vals[i] before i becomes visible in the table
-            *reinterpret_cast<volatile uint32_t*>(&vals[i]) = val;
-            __threadfence_block();
-            // smallest sorted index among this round's copies of v wins the slot
-            uint32_t h = hash32(v) & (tsz - 1);
-            for (;;) {
-              uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&tab[h]);
-              if (cur == 0xFFFFFFFFu) {
-                const uint32_t old = atomicCAS(&tab[h], 0xFFFFFFFFu, (uint32_t)i);
-                if (old == 0xFFFFFFFFu) break;
-                cur = old;
-              }
-              if ((*reinterpret_cast<volatile uint32_t*>(&vals[cur]) & V_MASK) == v) {
-                atomicMin(&tab[h], (uint32_t)i);
-                break;
-              }
-              h = (h + 1) & (tsz - 1);
-            }
-          }
+          if (!((mybits[v >> 5] >> (v & 31)) & 1u)) val |= V_FRESH;
         }
       }
       vals[i] = val;
     }
     __syncthreads();
-    // P3b: resolve first-sight winners (reads the table), keep the result in a register-free
-    // way: V_FRESH stays set only for winners
+
+    // PB: order the due set by (round, ticket, idx) == message id order (all due
+    //     deadlines equal `now`; the reference's PriorityBlockingQueue leaves ties
+    //     unspecified, net.clj:39-40,145).  Senders claim ring space in blocks, so
+    //     the window is a handful of internally ordered blocks: find them, sort
+    //     the blocks, verify; anything else falls back to a bitonic sort.
+    uint32_t R = 0;
+    bool use_blocks = false;
+    if (n > 0) {
+      uint32_t run = 0;
+      for (uint32_t base = 0; base < n; base += nt) {
+        const uint32_t i = base + tid;
+        bool f = false;
+        if (i < n) f = (i == 0) || keyA[i] != keyA[i - 1] || keyB[i] <= keyB[i - 1];
+        const uint32_t bal = __ballot_sync(FULL, f);
+        if (lane == 0) s_wcnt[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+        for (int w = 0; w < (nt >> 5); w++) {
+          const uint32_t cw = s_wcnt[w];
+          if (w < warp) before += cw;
+          total += cw;
+        }
+        if (f) {
+          const uint32_t pos = run + before + __popc(bal & ((1u << lane) - 1u));
+          if (pos < MAXB) s_bstart[pos] = (uint16_t)i;
+        }
+        run += total;
+        __syncthreads();
+      }
+      R = run;
+      if (R <= MAXB) {
+        if (tid == 0) s_bstart[R] = (uint16_t)n;
+        __syncthreads();
+        // rank blocks by their first key
+        for (uint32_t b = tid; b < R; b += nt) {
+          const uint32_t s0 = s_bstart[b];
+          const uint64_t ka = keyA[s0];
+          const uint32_t kb = keyB[s0];
+          uint32_t rk = 0;
+          for (uint32_t q = 0; q < R; q++) {
+            const uint32_t sq = s_bstart[q];
+            const uint64_t qa = keyA[sq];
+            const uint32_t qb = keyB[sq];
+            if (qa < ka || (qa == ka && (qb < kb || (qb == kb && q < b)))) rk++;
+          }
+          s_brank[b] = (uint16_t)rk;
+        }
+        __syncthreads();
+        for (uint32_t b = tid; b < R; b += nt) {
+          const uint32_t rk = s_brank[b];
+          s_bkeyA[rk] = keyA[s_bstart[b]];
+          // temporarily: length of the block, exclusive-scanned below
+          s_boff[rk] = (uint16_t)(s_bstart[b + 1] - s_bstart[b]);
+          // stash (first idx, last idx) of the block for the verification
+          s_bbase[rk] = ((uint64_t)keyB[s_bstart[b]] << 32) | keyB[s_bstart[b + 1] - 1];
+        }
+        __syncthreads();
+        if (tid == 0) {
+          uint32_t acc = 0;
+          bool ok = true;
+          for (uint32_t q = 0; q < R; q++) {
+            const uint32_t len = s_boff[q];
+            s_boff[q] = (uint16_t)acc;
+            acc += len;
+            if (q) {
+              // previous block must end before this one begins
+              const uint64_t pa = s_bkeyA[q - 1], ca = s_bkeyA[q];
+              const uint32_t plast = (uint32_t)s_bbase[q - 1], cfirst = (uint32_t)(s_bbase[q] >> 32);
+              if (!(pa < ca || (pa == ca && plast < cfirst))) ok = false;
+            }
+          }
+          s_boff[R] = (uint16_t)acc;
+          s_misc[1] = ok ? 1u : 0u;
+        }
+        __syncthreads();
+        use_blocks = s_misc[1] != 0;
+      }
+      if (use_blocks) {
+        for (uint32_t i = tid; i < n; i += nt) {
+          // block of window slot i (arrival order): last r with bstart[r] <= i
+          uint32_t lo = 0, hi = R;
+          while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_bstart[mid] <= i) lo = mid; else hi = mid; }
+          ord[s_boff[s_brank[lo]] + (i - s_bstart[lo])] = (uint16_t)i;
+        }
+        __syncthreads();
+      } else {
+        int np2 = 1;
+        while (np2 < (int)n) np2 <<= 1;
+        for (int i = tid; i < np2; i += nt) ord[i] = i < (int)n ? (uint16_t)i : (uint16_t)0xFFFF;
+        __syncthreads();
+        if (n > 1) block_bitonic_sort_idx(ord, keyA, keyB, np2);
+        if (tid == 0 && n > 1) atomicAdd((unsigned long long*)&st->fallback_sorts, 1ull);
+      }
+    }
+    // dense-id base of each sender block (needed only when records are written; issued early)
+    if (use_blocks) {
+      for (uint32_t b = tid; b < R; b += nt) {
+        const uint64_t ka = s_bkeyA[b];
+        s_bbase[b] = dense_base(p, st, ka >> 24, (uint32_t)(ka & 0xFFFFFFu));
+      }
+    }
+    __syncthreads();   // keyA (reg1) is dead from here on
+
+    // PC: first sight of a value among this round's copies: smallest sorted position wins
+    int npad = 1;
+    while (npad < (int)n) npad <<= 1;
+    const int tsz = 2 * npad;
     if (bcast) {
-      for (int i = tid; i < (int)n; i += nt) {
+      for (int i = tid; i < tsz; i += nt) tab[i] = 0xFFFFFFFFu;
+      __syncthreads();
+      for (int pos = tid; pos < (int)n; pos += nt) {
+        const uint32_t val = vals[ord[pos]];
+        if (val & V_FRESH) {
+          const uint32_t v = val & V_MASK;
+          uint32_t h = hash32(v) & (tsz - 1);
+          for (;;) {
+            uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&tab[h]);
+            if (cur == 0xFFFFFFFFu) {
+              const uint32_t old = atomicCAS(&tab[h], 0xFFFFFFFFu, (uint32_t)pos);
+              if (old == 0xFFFFFFFFu) break;
+              cur = old;
+            }
+            if ((vals[ord[cur]] & V_MASK) == v) { atomicMin(&tab[h], (uint32_t)pos); break; }
+            h = (h + 1) & (tsz - 1);
+          }
+        }
+      }
+      __syncthreads();
+      for (int pos = tid; pos < (int)n; pos += nt) {
+        const uint32_t i = ord[pos];
         const uint32_t val = vals[i];
         if (val & V_FRESH) {
           const uint32_t v = val & V_MASK;
           uint32_t h = hash32(v) & (tsz - 1);
           uint32_t win = tab[h];
-          while (win != 0xFFFFFFFFu && (vals[win] & V_MASK) != v) {   // the entry exists: probing ends on it
+          while (win != 0xFFFFFFFFu && (vals[ord[win]] & V_MASK) != v) {   // the entry exists: probing ends on it
             h = (h + 1) & (tsz - 1);
             win = tab[h];
           }
-          if (win == (uint32_t)i) {
-            atomicOr(p.bitmap + (size_t)e * p.bm_words + (v >> 5), 1u << (v & 31));
-          } else {
-            // a lower-id copy of v is processed first this round
-            // (cleared after every thread has finished reading vals[])
-            keys[i] |= 0x8000ull;   // slot < 2^15: bit 15 of the key marks "not new"
-          }
+          if (win == (uint32_t)pos) atomicOr(p.bitmap + (size_t)e * p.bm_words + (v >> 5), 1u << (v & 31));
+          else vals[i] = val & ~V_FRESH;   // a lower-id copy of v is processed first this round
         }
       }
       __syncthreads();
     }
-    // packed counts: emit (bits 0-31) | recv (32-47) | new (48-63)   (aux aliases the table)
-    for (int i = tid; i < (int)n; i += nt) {
+    // packed counts in sorted order: emit (bits 0-31) | recv (32-47) | new (48-63)
+    for (int pos = tid; pos < (int)n; pos += nt) {
+      const uint32_t i = ord[pos];
       const uint32_t val = vals[i];
       uint64_t c = 0;
       if (val & V_RECV) {
         c = 1ull << 32;
-        const bool is_new = (val & V_FRESH) && !(keys[i] & 0x8000ull);
+        const bool is_new = (val & V_FRESH) != 0;
         if (is_server) {
-          const uint32_t slot = (uint32_t)(keys[i] & 0x7FFFu);
-          const MsgView w = view_load(myring + (size_t)((head + slot) & p.ring_mask) * 3);
+          const MsgView w = view_load(myring + (size_t)((head + i) & p.ring_mask) * 3);
           c |= node_emit_count(p, e, w, is_new);
         }
         if (is_new) c |= 1ull << 48;
       }
-      aux[i] = c;
+      aux[pos] = c;
     }
     __syncthreads();
-    // P4
     const uint64_t tot = block_excl_scan(aux, (int)n, s_wtmp);
     const uint32_t n_emit = (uint32_t)tot;
     const uint32_t n_recv = (uint32_t)(tot >> 32) & 0xFFFFu;
     const uint32_t n_new = (uint32_t)(tot >> 48);
-    n_ev_local = (uint64_t)n_recv + n_emit; n_em_local = n_emit;
-    // P5
-    if (tid < 32) lookback(p, st, ticket, tag, n_ev_local, n_em_local, s_pref);
+    n_ev_local = n_recv + n_emit; n_em_local = n_emit;
+
+    // PD: claims: journal chunk, mailbox, per-neighbor ring blocks
     const bool mailed = (kind == MS_KIND_CLIENT || kind == MS_KIND_HOST);
-    if (tid == 0 && mailed && n_recv) s_mail_base = atomicAdd(&st->mail_count, n_recv);
+    const uint32_t deg = bcast ? nbr_count(p, e) : 0;
+    const bool agg = use_blocks && bcast && p.topology != MS_TOPO_TOTAL && deg <= MAXNB && n_new > 0 &&
+                     np.loss_thresh == 0 && np.dist == MS_DIST_CONSTANT && (uint64_t)np.mean_ms * np.scale == 0 &&
+                     s_misc[3] == 0;
+    if (tid == 0) {
+      s_chunk = (n_ev_local && p.jlevel)
+                    ? atomicAdd((unsigned long long*)&st->jraw_cursor, (unsigned long long)n_ev_local) : 0ull;
+      if (mailed && n_recv) s_misc[0] = atomicAdd(&st->mail_count, n_recv);
+    }
+    if (agg && tid < (int)deg) {   // deg <= MAXNB <= 32 <= blockDim
+      // S[rho][j]: new messages, in blocks before rho, that came from neighbor j (they do not go back to j)
+      const uint32_t nb = nbr_at(p, e, tid);
+      uint32_t acc = 0;
+      for (uint32_t q = 0; q < R; q++) {
+        s_S[q][tid] = (uint16_t)acc;
+        const uint64_t ka = s_bkeyA[q];
+        const uint32_t tk = (uint32_t)(ka & 0xFFFFFFu);
+        if (tk >= p.n_inj_tickets && tk - p.n_inj_tickets == nb)
+          acc += (uint32_t)(aux[s_boff[q + 1]] >> 48) - (uint32_t)(aux[s_boff[q]] >> 48);
+      }
+      s_S[R][tid] = (uint16_t)acc;
+      const uint32_t total = n_new - acc;
+      uint32_t base = 0;
+      if (total) {
+        base = atomicAdd(&p.tail[nb], total);
+        if ((uint32_t)(base + total - p.head[nb]) > p.ring_cap) latch_error(st, E_RING_OVERFLOW, nb);
+      }
+      s_nbbase[tid] = base;
+    }
     __syncthreads();
-    const uint64_t ev_base = st->next_event + s_pref[0];
-    cx.id0 = st->next_id + s_pref[1];
-    cx.ev0 = ev_base + n_recv;
+    cx.chunk = s_chunk;
+    cx.n_recv = n_recv;
     cx.emitter = e;
     const bool cl_ep = kind_is_client(kind);
     const uint32_t msg_id_base = (is_server && p.next_msg_id) ? p.next_msg_id[e] : 0;
     const uint32_t set_before = (is_server && p.set_count) ? p.set_count[e] : 0;
 
-    // P6 + P7: :recv events (net.clj:244) and the emissions of each message
+    // PE: :recv records (net.clj:244) and the emissions of each message, in id order
     for (uint32_t base = 0; base < n; base += nt) {
-      const uint32_t i = base + tid;
-      const bool live = i < n;
-      uint32_t my_emit = 0, e_idx0 = 0, new_before = 0;
+      const uint32_t pos = base + tid;
+      const bool live = pos < n;
+      uint32_t my_emit = 0, e_idx0 = 0, new_before = 0, rho = 0;
       MsgView w;
       w.src = 0; w.msg_id = 0; w.p0 = 0; w.tf = 0;
       uint64_t p1 = 0;
+      bool is_new = false;
       if (live) {
-        const uint64_t a0 = aux[i], a1 = aux[i + 1];
+        const uint32_t i = ord[pos];
+        const uint64_t a0 = aux[pos], a1 = aux[pos + 1];
         e_idx0 = (uint32_t)a0;
         my_emit = (uint32_t)a1 - (uint32_t)a0;
         new_before = (uint32_t)(a0 >> 48);
-        if (vals[i] & V_RECV) {
+        const uint32_t val = vals[i];
+        is_new = (val & V_FRESH) != 0;
+        if (use_blocks) {
+          uint32_t lo = 0, hi = R;
+          while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_boff[mid] <= pos) lo = mid; else hi = mid; }
+          rho = lo;
+        }
+        if (val & V_RECV) {
           const uint32_t k = (uint32_t)(a0 >> 32) & 0xFFFFu;
-          const uint32_t slot = (uint32_t)(keys[i] & 0x7FFFu);
-          const uint4* rp = myring + (size_t)((head + slot) & p.ring_mask) * 3;
-          const uint4 va = rp[0], vb = rp[1], vc = rp[2];
-          Rec m;
-          m.id = (uint64_t)va.x | ((uint64_t)va.y << 32);
-          m.deadline = (int64_t)((uint64_t)va.z | ((uint64_t)va.w << 32));
-          m.src = vb.x; m.dest = vb.y; m.msg_id = vb.z; m.in_reply_to = vb.w;
-          m.tf = vc.x; m.p0 = vc.y; m.p1 = (uint64_t)vc.z | ((uint64_t)vc.w << 32);
+          const uint4* rp = myring + (size_t)((head + i) & p.ring_mask) * 3;
+          Rec m = rec_unpack(rp[0], rp[1], rp[2]);
           w.src = m.src; w.msg_id = m.msg_id; w.p0 = m.p0; w.tf = m.tf;
           p1 = m.p1;
-          journal_write(p, st, ev_base + k, true, now, m);
+          const uint64_t id = (use_blocks ? s_bbase[rho] : dense_base(p, st, m.round, m.ticket)) + m.idx;
+          journal_raw(p, cx.chunk + k, id, true, m);
           const bool cl = cl_ep || kind_is_client(p.kind[w.src]);
           if (cl) c_recv_cl++; else c_recv_sv++;
           if (kind == MS_KIND_SIM_CLIENT && ((w.tf >> 16) & MS_F_REPLY)) c_replies++;
           if (mailed) {
-            const uint32_t mpos = s_mail_base + k;
-            if (mpos >= p.mail_cap) latch_error(st, E_MAIL_OVERFLOW, e);
-            else rec_store(reinterpret_cast<uint4*>(p.mail) + (size_t)mpos * 3, m);
+            const uint32_t mpos = s_misc[0] + k;
+            if (mpos >= p.mail_cap) {
+              latch_error(st, E_MAIL_OVERFLOW, e);
+            } else {
+              uint4* dst = reinterpret_cast<uint4*>(p.mail) + (size_t)mpos * 3;   // public ms_msg layout
+              st_v4(dst + 0, make_uint4((uint32_t)id, (uint32_t)(id >> 32), (uint32_t)now, (uint32_t)((uint64_t)now >> 32)));
+              st_v4(dst + 1, make_uint4(m.src, m.dest, m.msg_id, m.in_reply_to));
+              st_v4(dst + 2, make_uint4(m.tf, m.p0, (uint32_t)m.p1, (uint32_t)(m.p1 >> 32)));
+            }
           }
         } else {
           c_part++;
@@ -740,8 +842,16 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap_lo, uin
         const bool valid = k < my_emit;
         Rec r;
         r.dest = 0; r.src = e;
-        if (valid) node_emit(p, e, w, k, my_emit, e_idx0 + k, msg_id_base, set_before, new_before, p1, r);
-        emit_one(p, st, np, cx, valid, r, e_idx0 + k);
+        uint32_t direct = 0;
+        bool has_direct = false;
+        if (valid) {
+          const int slot = node_emit(p, e, w, k, my_emit, e_idx0 + k, msg_id_base, set_before, new_before, p1, r);
+          if (agg && slot >= 0 && is_new) {
+            direct = s_nbbase[slot] + new_before - s_S[rho][slot];
+            has_direct = true;
+          }
+        }
+        emit_one(p, st, np, cx, valid, r, e_idx0 + k, direct, has_direct);
       }
     }
     if (tid == 0 && is_server) {
@@ -774,28 +884,70 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap_lo, uin
   }
   __syncthreads();
   if (tid == 0) {
-    if (ticket == T - 1) {
-      // inclusive prefix of the last ticket = totals of the round
-      st->round_ev_total = s_pref[0] + n_ev_local;
-      st->round_em_total = s_pref[1] + n_em_local;
-    }
+    // this ticket's row entries (turned into prefixes by the last CTA)
+    p.rt_em[(size_t)row * p.t_max + ticket] = n_em_local;
+    p.rt_ev[(size_t)row * p.t_max + ticket] = n_ev_local;
+    p.rt_chunk[(size_t)row * p.t_max + ticket] = cx.chunk;
     __threadfence();
-    const uint32_t d = atomicAdd(&st->done, 1u);
-    if (d == T - 1) {
-      // last CTA of the round: commit the round
-      __threadfence();
-      const uint64_t ev_total = *reinterpret_cast<volatile uint64_t*>(&st->round_ev_total);
-      const uint64_t em_total = *reinterpret_cast<volatile uint64_t*>(&st->round_em_total);
+    s_misc[4] = (atomicAdd(&st->done, 1u) == T - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_misc[4]) {
+    // ---------------------------------------------------------- last CTA: commit the round
+    __threadfence();
+    uint32_t* em = p.rt_em + (size_t)row * p.t_max;
+    uint32_t* ev = p.rt_ev + (size_t)row * p.t_max;
+    const int c = ((int)T + nt - 1) / nt;
+    const int lo = min(tid * c, (int)T), hi = min(lo + c, (int)T);
+    uint64_t sum = 0;   // ev << 32 | em  (per-round totals stay below 2^32)
+    for (int i = lo; i < hi; i++) sum += ((uint64_t)ld_cg_u32(ev + i) << 32) | ld_cg_u32(em + i);
+    uint64_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint64_t y = __shfl_up_sync(FULL, incl, d);
+      if (lane >= d) incl += y;
+    }
+    if (lane == 31) s_wtmp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const int nw = nt >> 5;
+      const uint64_t w = lane < nw ? s_wtmp[lane] : 0;
+      uint64_t wi = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t y = __shfl_up_sync(FULL, wi, d);
+        if (lane >= d) wi += y;
+      }
+      s_wtmp[lane] = wi - w;
+      if (lane == 31) s_wtmp[32] = wi;
+    }
+    __syncthreads();
+    uint64_t run = s_wtmp[warp] + incl - sum;
+    for (int i = lo; i < hi; i++) {
+      const uint32_t ve = ld_cg_u32(ev + i), vm = ld_cg_u32(em + i);
+      ev[i] = (uint32_t)(run >> 32);
+      em[i] = (uint32_t)run;
+      run += ((uint64_t)ve << 32) | vm;
+    }
+    const uint64_t total = s_wtmp[32];
+    __syncthreads();
+    if (tid == 0) {
+      const uint64_t ev_total = total >> 32, em_total = total & 0xFFFFFFFFull;
+      RoundMeta* m = p.rmeta + row;
+      m->ev_total = ev_total;
+      m->em_total = em_total;
+      m->n_tickets = T;
       st->next_event += ev_total;
       st->next_id += em_total;
-      if (p.jdiscard) st->journal_drained = st->next_event;
       const uint64_t tick = (uint64_t)(now / kTickNs);
-      uint32_t hi = (tick + 1 < p.n_tick_off) ? p.tick_off[tick + 1] : p.n_sched;
-      if (hi > st->sched_cursor) st->sched_cursor = hi;
+      uint32_t hi_s = (tick + 1 < p.n_tick_off) ? p.tick_off[tick + 1] : p.n_sched;
+      if (hi_s > st->sched_cursor) st->sched_cursor = hi_s;
       st->inj_count = 0;
       const uint32_t zp = *reinterpret_cast<volatile uint32_t*>(&st->zero_pending);
+      int64_t next_now = now;
       if (zp == 0) {
-        st->now = now + kTickNs;
+        next_now = now + kTickNs;
+        st->now = next_now;
         st->time_advanced = 1;
         if (p.cal) st->cal_release = (((uint32_t)(tick + 1)) & (p.cal_slots - 1)) + 1;
       } else {
@@ -804,10 +956,74 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap_lo, uin
       st->zero_pending = 0;
       st->round = round + 1;
       st->rounds_run += 1;
-      st->ticket = 0;
       st->done = 0;
       st->round_max_window = 0;
       st->slot_open = 0;
+      const uint64_t raw_cur = *reinterpret_cast<volatile uint64_t*>(&st->jraw_cursor);
+      if (p.jdiscard || !p.jlevel) {
+        st->journal_drained = st->next_event;
+        st->jraw_drained = raw_cur;
+        st->drain_round = round + 1;
+      }
+      // open the next round's row
+      RoundMeta* nx = p.rmeta + ((uint32_t)(round + 1) & p.hist_mask);
+      nx->round = round + 1;
+      nx->now = next_now;
+      nx->id_base = st->next_id;
+      nx->ev_base = st->next_event;
+      nx->raw_base = raw_cur;
+      nx->n_tickets = 0;
+      nx->ev_total = 0;
+      nx->em_total = 0;
+      __threadfence();
+    }
+  }
+}
+
+// ------------------------------------------------------------------ k_journal_expand (K3)
+// Turns the raw per-(round, ticket) chunks of rounds [r0, r0 + n_rounds) into
+// journal events in event-id order (journal.clj:225-239) for the event window
+// [first, first + count): one warp per chunk.
+__global__ void k_journal_expand(Params p, uint64_t r0, uint32_t n_rounds, uint64_t first, uint64_t count,
+                                 uint4* out_ev, uint4* out_body) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warp_global = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint64_t n_chunks = (uint64_t)n_rounds * p.t_max;
+  for (uint64_t c = warp_global; c < n_chunks; c += n_warps) {
+    const uint64_t r = r0 + c / p.t_max;
+    const uint32_t t = (uint32_t)(c % p.t_max);
+    const uint32_t row = (uint32_t)r & p.hist_mask;
+    const RoundMeta* m = p.rmeta + row;
+    if (m->round != r || t >= m->n_tickets) continue;
+    const uint32_t* ev = p.rt_ev + (size_t)row * p.t_max;
+    const uint64_t off = ev[t];
+    const uint64_t end = (t + 1 < m->n_tickets) ? ev[t + 1] : m->ev_total;
+    if (end == off) continue;
+    const uint64_t g0 = m->ev_base + off;
+    const uint64_t cnt = end - off;
+    if (g0 + cnt <= first || g0 >= first + count) continue;
+    const uint64_t chunk = p.rt_chunk[(size_t)row * p.t_max + t];
+    const uint64_t send_base = m->id_base + p.rt_em[(size_t)row * p.t_max + t];
+    const int64_t tnow = m->now;
+    for (uint64_t k = lane; k < cnt; k += 32) {
+      const uint64_t g = g0 + k;
+      if (g < first || g >= first + count) continue;
+      const uint4 raw = p.jraw[(chunk + k) & p.jmask];
+      const uint64_t v = (uint64_t)raw.x | ((uint64_t)raw.y << 32);
+      const bool recv = (v & RECV_BIT) != 0;
+      const uint64_t id = recv ? (v & ~RECV_BIT) : send_base + v;
+      const uint64_t eid = g | (recv ? MS_EVENT_RECV : 0ull);
+      uint4* o = out_ev + (g - first) * 2;
+      st_v4(o + 0, make_uint4((uint32_t)eid, (uint32_t)(eid >> 32), (uint32_t)tnow, (uint32_t)((uint64_t)tnow >> 32)));
+      st_v4(o + 1, make_uint4((uint32_t)id, (uint32_t)(id >> 32), raw.z, raw.w));
+      if (out_body) {
+        const uint4* b = p.jbody + ((chunk + k) & p.jmask) * 2;
+        const uint4 b0 = b[0], b1 = b[1];
+        uint4* ob = out_body + (g - first) * 2;
+        st_v4(ob + 0, make_uint4((uint32_t)id, (uint32_t)(id >> 32), b0.z, b0.w));
+        st_v4(ob + 1, b1);
+      }
     }
   }
 }
@@ -821,7 +1037,7 @@ cudaError_t msk_round_smem_attr(size_t bytes) {
   return cudaFuncSetAttribute(msd::k_round, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-size_t msk_round_smem_bytes(uint32_t cap) { return (size_t)cap * 20 + 16; }
+size_t msk_round_smem_bytes(uint32_t cap) { return (size_t)cap * 18 + 32; }
 
 void msk_set_bit(uint32_t* words, size_t word, uint32_t bit, cudaStream_t s) {
   msd::k_set_bit<<<1, 1, 0, s>>>(words, word, bit);
@@ -845,6 +1061,16 @@ void msk_launch_round(const msd::Params* p, int n_classes, const uint32_t* caps,
         *p, lo, caps[c], c == n_classes - 1 ? 1u : 0u);
   }
   if (after_round) cudaEventRecord(after_round, s);
+}
+
+void msk_journal_expand(const msd::Params* p, uint64_t r0, uint32_t n_rounds, uint64_t first, uint64_t count,
+                        void* out_ev, void* out_body, cudaStream_t s) {
+  const uint64_t chunks = (uint64_t)n_rounds * p->t_max;
+  uint64_t blocks = (chunks * 32 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  msd::k_journal_expand<<<(unsigned)blocks, 256, 0, s>>>(*p, r0, n_rounds, first, count, (uint4*)out_ev,
+                                                          (uint4*)out_body);
 }
 
 }  // extern "C"

@@ -180,7 +180,7 @@ class Sim:
     def counters(self):
         out = np.zeros(8, dtype=np.uint64)
         self._chk(self.L.ms_counters(self.h, out.ctypes.data))
-        names = ("rounds", "sends", "recvs", "launches", "lost", "partition_drops", "max_window", "_")
+        names = ("rounds", "sends", "recvs", "launches", "lost", "partition_drops", "max_window", "fallback_sorts")
         return {k: int(v) for k, v in zip(names, out)}
 
     def timer_begin(self):
