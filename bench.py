@@ -207,7 +207,7 @@ def make_sim(mb, args, n_ticks_total, journal_discard, device):
 
 def run_until_tick(sim, tick, drain=None):
     # ms_run returns 1 when the journal ring is half full: drain and continue
-    while sim.run(tick * TICK_NS) == 1:
+    while sim.run_raw(tick * TICK_NS) == 1:
         drain()
 
 

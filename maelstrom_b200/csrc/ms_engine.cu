@@ -626,6 +626,7 @@ int ms_schedule_ops(ms_sim* s, const ms_op* ops, size_t n) {
 // true when the device refuses to run rounds until the host drains the journal
 static bool journal_blocked(const ms_sim* s) {
   if (!s->cfg.journal_level || s->cfg.journal_discard) return false;
+  // mirrors round_skipped(): after a sync no round is in flight, so the next round's raw_base == jraw_cursor
   if (s->hs.jraw_cursor - s->hs.jraw_drained > (s->P.jmask + 1) / 2) return true;
   return s->hs.round - s->hs.drain_round + 2 >= s->P.hist;
 }
@@ -653,6 +654,7 @@ int ms_step(ms_sim* s, uint64_t n_rounds) {
     const uint64_t r0 = s->hs.rounds_run;
     const int rc = step_locked(s, b, INT64_MAX);
     if (rc) return rc;
+    if (s->hs.rounds_run == r0) { set_err("simulation made no progress (device refuses to run rounds)"); return MS_ERR_SIM; }
     n_rounds -= std::min<uint64_t>(n_rounds, s->hs.rounds_run - r0);
   }
   return MS_OK;
@@ -662,8 +664,13 @@ int ms_run(ms_sim* s, int64_t until) {
   std::lock_guard<std::mutex> g(s->mu);
   while (s->hs.now < until) {
     if (journal_blocked(s)) return 1;   // drain (ms_journal_drain) and call again
+    const uint64_t r0 = s->hs.rounds_run;
     const int rc = step_locked(s, 32, until);
     if (rc) return rc;
+    if (s->hs.rounds_run == r0 && s->hs.now < until && !journal_blocked(s)) {
+      set_err("simulation made no progress (device refuses to run rounds)");
+      return MS_ERR_SIM;
+    }
   }
   return MS_OK;
 }
@@ -680,7 +687,9 @@ int ms_recv(ms_sim* s, uint32_t e, int64_t timeout, ms_msg* out) {
     }
     if (s->hs.now >= give_up) return 0;
     if (journal_blocked(s)) { set_err("journal ring half full: drain it (ms_journal_drain)"); return MS_ERR_CAPACITY; }
+    const uint64_t r0 = s->hs.rounds_run;
     const int rc = step_locked(s, 1, INT64_MAX);
+    if (!rc && s->hs.rounds_run == r0) { set_err("simulation made no progress (device refuses to run rounds)"); return MS_ERR_SIM; }
     if (rc) return rc;
   }
 }

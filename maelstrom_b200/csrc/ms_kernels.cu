@@ -67,7 +67,10 @@ __device__ __forceinline__ void latch_error(DevState* st, uint32_t code, uint32_
 __device__ __forceinline__ bool round_skipped(const Params& p, const DevState* st) {
   if (st->now >= st->stop_ns || st->error) return true;
   if (p.jlevel && !p.jdiscard) {
-    if (st->jraw_cursor - st->jraw_drained > ((p.jmask + 1) >> 1)) return true;
+    // only values that are constant while a round is in flight may be used here:
+    // raw_base of the round's row is jraw_cursor as of the START of the round
+    const uint64_t raw_base = p.rmeta[(uint32_t)st->round & p.hist_mask].raw_base;
+    if (raw_base - st->jraw_drained > ((p.jmask + 1) >> 1)) return true;
     if (st->round - st->drain_round + 2 >= p.hist) return true;
   }
   return false;
@@ -199,11 +202,10 @@ __device__ __forceinline__ void journal_raw(const Params& p, uint64_t pos, uint6
   }
 }
 
-// Must be called convergently by all 32 lanes of a warp.  direct_pos != NO_DIRECT
+// Must be called convergently by all 32 lanes of a warp.  has_direct
 // means ring space for this record was already claimed by the CTA (per-neighbor
 // block claim); otherwise slots are claimed here, one atomic per destination
 // per warp.
-constexpr uint32_t NO_DIRECT = 0xFFFFFFFFu;
 __device__ __forceinline__ void emit_one(const Params& p, DevState* st, const NetParams& np, EmitCtx& cx,
                                          bool valid, Rec& r, uint32_t local_idx, uint32_t direct_pos,
                                          bool has_direct) {
@@ -508,9 +510,12 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap_lo, uin
     const uint32_t lo = min(ticket * chunk, K), hi_s = min(lo + chunk, K);
     const uint32_t n_local = hi_s - lo;
     n_ev_local = n_local; n_em_local = n_local;
-    if (tid == 0)
+    if (tid == 0) {
       s_chunk = (n_local && p.jlevel)
                     ? atomicAdd((unsigned long long*)&st->jraw_cursor, (unsigned long long)n_local) : 0ull;
+      if (p.jlevel && !p.jdiscard && s_chunk + n_local - st->jraw_drained > p.jmask + 1)
+        latch_error(st, E_JOURNAL_OVERFLOW, ticket);
+    }
     __syncthreads();
     cx.chunk = s_chunk;
     cx.emitter = kInjector;
@@ -695,7 +700,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap_lo, uin
         if (val & V_FRESH) {
           const uint32_t v = val & V_MASK;
           uint32_t h = hash32(v) & (tsz - 1);
-          for (;;) {
+          for (int probe = 0; probe < tsz; probe++) {   // the table is at most half full
             uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&tab[h]);
             if (cur == 0xFFFFFFFFu) {
               const uint32_t old = atomicCAS(&tab[h], 0xFFFFFFFFu, (uint32_t)pos);
@@ -715,8 +720,8 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap_lo, uin
           const uint32_t v = val & V_MASK;
           uint32_t h = hash32(v) & (tsz - 1);
           uint32_t win = tab[h];
-          while (win != 0xFFFFFFFFu && (vals[ord[win]] & V_MASK) != v) {   // the entry exists: probing ends on it
-            h = (h + 1) & (tsz - 1);
+          for (int probe = 0; probe < tsz && win != 0xFFFFFFFFu && (vals[ord[win]] & V_MASK) != v; probe++) {
+            h = (h + 1) & (tsz - 1);   // the entry exists: probing ends on it
             win = tab[h];
           }
           if (win == (uint32_t)pos) atomicOr(p.bitmap + (size_t)e * p.bm_words + (v >> 5), 1u << (v & 31));
@@ -757,6 +762,8 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap_lo, uin
     if (tid == 0) {
       s_chunk = (n_ev_local && p.jlevel)
                     ? atomicAdd((unsigned long long*)&st->jraw_cursor, (unsigned long long)n_ev_local) : 0ull;
+      if (p.jlevel && !p.jdiscard && s_chunk + n_ev_local - st->jraw_drained > p.jmask + 1)
+        latch_error(st, E_JOURNAL_OVERFLOW, ticket);
       if (mailed && n_recv) s_misc[0] = atomicAdd(&st->mail_count, n_recv);
     }
     if (agg && tid < (int)deg) {   // deg <= MAXNB <= 32 <= blockDim

@@ -56,6 +56,7 @@ class Sim:
                 raise TypeError("unknown ms_config field %r" % k)
             setattr(cfg, k, v)
         self.L = _lib.lib()
+        self._stash = []
         self.cfg = cfg
         self.n_nodes = n_nodes
         self.h = self.L.ms_create(C.byref(cfg))
@@ -108,8 +109,15 @@ class Sim:
     def step(self, n=1):
         return self._chk(self.L.ms_step(self.h, n))
 
-    def run(self, until_ns):
+    def run_raw(self, until_ns):
+        """ms_run as is: 0 = reached until_ns, 1 = journal ring half full (drain, then call again)."""
         return self._chk(self.L.ms_run(self.h, until_ns))
+
+    def run(self, until_ns):
+        """ms_run; when the device asks for a journal drain, stash the events and continue."""
+        while self.run_raw(until_ns) == 1:
+            self._stash.append(self._drain_now())
+        return 0
 
     @property
     def now(self):
@@ -150,7 +158,14 @@ class Sim:
         return self._chk(self.L.ms_journal_close(self.h))
 
     def drain(self, cap=1 << 20, bodies=True):
-        """Drain everything available; returns (events, bodies)."""
+        """Everything journaled since the last call (including events stashed by run()); (events, bodies)."""
+        parts = self._stash + [self._drain_now(cap, bodies)]
+        self._stash = []
+        ev = np.concatenate([p[0] for p in parts])
+        bd = np.concatenate([p[1] for p in parts]) if bodies else None
+        return ev, bd
+
+    def _drain_now(self, cap=1 << 20, bodies=True):
         evs, bds = [], []
         while True:
             ev = np.zeros(cap, dtype=EVENT_DTYPE)

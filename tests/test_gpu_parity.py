@@ -172,3 +172,40 @@ def test_errors_surface():
     with pytest.raises(mb.SimError):
         g.step(2)
     g.close()
+
+
+def test_journal_backpressure_small_ring():
+    # a 4096-record raw journal ring: the device stops running rounds whenever it is half full
+    # (ms_run returns 1) and resumes after ms_journal_drain; the drained journal must be unchanged
+    n = 25
+    g, o = make_pair(n, topology="grid", n_values=2048, ring_cap=512, max_window=256, journal_cap_log2=12)
+
+    def scenario(s, body):
+        cs = [s.add_endpoint("c%d" % i) for i in range(3)]
+        ops, nv = random_broadcast_ops(n, cs, n_ticks=40, per_tick=12, seed=21)
+        s.schedule(ops)
+        s.run(45_000_000)
+
+    both(g, o, scenario)
+    ev, _ = assert_same_journal(g, o)
+    assert len(ev) > 40000
+
+
+def test_sim_clients_and_block_path_counters():
+    # simulated client sinks (bench configuration) + the fast ordering path must be taken
+    from maelstrom_b200.engine import KIND_SIM_CLIENT
+    n = 64
+    g, o = make_pair(n, topology="grid", n_values=4096, ring_cap=2048, max_window=1024, journal_cap_log2=21)
+
+    def scenario(s, body):
+        cs = [s.add_endpoint("c%d" % i, KIND_SIM_CLIENT) for i in range(4)]
+        ops, nv = random_broadcast_ops(n, cs, n_ticks=4, per_tick=400, seed=2)
+        s.schedule(ops)
+        s.run(6_000_000)
+        return s.client_replies()
+
+    rg, ro = both(g, o, scenario)
+    assert rg == ro == 1600
+    assert_same_journal(g, o)
+    c = g.counters()
+    assert c["fallback_sorts"] * 20 < c["rounds"] * (n + 4)   # bitonic fallback is the exception
