@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap_lo, uin
     if (tid == 0) {
       s_chunk = (n_local && p.jlevel)
                     ? atomicAdd((unsigned long long*)&st->jraw_cursor, (unsigned long long)n_local) : 0ull;
-      if (p.jlevel && !p.jdiscard && s_chunk + n_local - st->jraw_drained > p.jmask + 1)
+      if (n_local && p.jlevel && !p.jdiscard && s_chunk + n_local - st->jraw_drained > p.jmask + 1)
         latch_error(st, E_JOURNAL_OVERFLOW, ticket);
     }
     __syncthreads();
@@ -762,7 +762,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap_lo, uin
     if (tid == 0) {
       s_chunk = (n_ev_local && p.jlevel)
                     ? atomicAdd((unsigned long long*)&st->jraw_cursor, (unsigned long long)n_ev_local) : 0ull;
-      if (p.jlevel && !p.jdiscard && s_chunk + n_ev_local - st->jraw_drained > p.jmask + 1)
+      if (n_ev_local && p.jlevel && !p.jdiscard && s_chunk + n_ev_local - st->jraw_drained > p.jmask + 1)
         latch_error(st, E_JOURNAL_OVERFLOW, ticket);
       if (mailed && n_recv) s_misc[0] = atomicAdd(&st->mail_count, n_recv);
     }
