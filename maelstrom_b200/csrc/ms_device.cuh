@@ -52,8 +52,11 @@ struct DevState {
   uint32_t time_advanced;    // 1 when the last round moved `now`
   uint32_t max_window_seen;
   uint32_t cal_release;      // calendar slot to release before the next round (+1), 0 = none
-  uint32_t slot_open;        // k_snapshot ran for this launch slot and no k_round class has run yet
-  uint32_t round_max_window; // largest window of the round in flight (selects the k_round size class)
+  uint32_t slot_open;        // k_snapshot ran for this launch slot and the round has not been committed yet
+  uint32_t pad1;
+  // per-round work lists of the k_round size classes, double-buffered by round parity
+  uint32_t cls_count[2][4];
+  uint32_t cls_cursor[2][4];
 };
 
 // One row per round, kept in a ring of `hist` rounds: what is needed to turn an
@@ -98,7 +101,9 @@ struct Params {
   uint32_t* rt_em;           // emissions per ticket, exclusive prefix once the round is committed
   uint32_t* rt_ev;           // events per ticket, exclusive prefix once committed
   uint64_t* rt_chunk;        // raw journal position of the ticket's chunk
-  uint32_t  hist, hist_mask, t_max, pad_h;
+  uint32_t  hist, hist_mask, t_max, n_classes;
+  uint32_t* cls_list;        // [2][4][t_max] tickets per size class
+  uint32_t  cls_cap[4];      // ascending window capacities of the classes
   // raw journal: 16-B records, chunk per (round, ticket); bodies (level 2) 32 B at the same index
   uint4*    jraw;
   uint4*    jbody;

@@ -21,8 +21,10 @@ using namespace msd;
 extern "C" {
 cudaError_t msk_round_smem_attr(size_t bytes);
 size_t msk_round_smem_bytes(uint32_t cap);
+int msk_round_occupancy(int threads, size_t smem);
 void msk_launch_round(const msd::Params* p, int n_classes, const uint32_t* caps, const int* threads,
-                      int with_release, cudaStream_t s, cudaEvent_t before_round, cudaEvent_t after_round);
+                      const int* grids, int with_release, cudaStream_t s, cudaEvent_t before_round,
+                      cudaEvent_t after_round);
 void msk_set_bit(uint32_t* words, size_t word, uint32_t bit, cudaStream_t s);
 void msk_journal_expand(const msd::Params* p, uint64_t r0, uint32_t n_rounds, uint64_t first, uint64_t count,
                         void* out_ev, void* out_body, cudaStream_t s);
@@ -106,6 +108,8 @@ struct ms_sim {
   int n_classes = 0;
   uint32_t class_cap[4] = {0, 0, 0, 0};
   int class_threads[4] = {0, 0, 0, 0};
+  int class_grid[4] = {0, 0, 0, 0};
+  int n_sms = 148;
   bool use_calendar = false;
   uint64_t launches = 0;
 
@@ -203,7 +207,11 @@ struct ms_sim {
         a = prof_ev[prof_used]; b = prof_ev[prof_used + 1];
         prof_used += 2;
       }
-      msk_launch_round(&P, n_classes, class_cap, class_threads, use_calendar ? 1 : 0, stream, a, b);
+      // persistent grids: one CTA slot per resident block, never more CTAs than tickets
+      const int T = (int)(P.n_inj_tickets + P.n_ep);
+      int grids[4];
+      for (int c = 0; c < n_classes; c++) grids[c] = std::max(1, std::min(class_grid[c], T));
+      msk_launch_round(&P, n_classes, class_cap, class_threads, grids, use_calendar ? 1 : 0, stream, a, b);
       launches += (use_calendar ? 2 : 1) + n_classes;
     }
   }
@@ -360,10 +368,10 @@ static int build_sim(ms_sim* s, const ms_config* in) {
     return MS_ERR_ARG;
   }
   {
-    const uint32_t ladder[3] = {256, 1024, 32768};
-    const int thr[3] = {128, 256, 512};
+    const uint32_t ladder[4] = {128, 512, 2048, 32768};
+    const int thr[4] = {64, 128, 256, 512};
     s->n_classes = 0;
-    for (int k = 0; k < 3; k++) {
+    for (int k = 0; k < 4; k++) {
       const uint32_t cap = std::min(ladder[k], c.max_window);
       s->class_cap[s->n_classes] = cap;
       s->class_threads[s->n_classes] = c.threads_per_node ? (int)c.threads_per_node : thr[k];
@@ -501,6 +509,17 @@ static int build_sim(ms_sim* s, const ms_config* in) {
   CK(cudaMemcpyAsync(P.st, &s->hs, sizeof(DevState), cudaMemcpyHostToDevice, s->stream));
 
   CK(msk_round_smem_attr(msk_round_smem_bytes(c.max_window)));
+  {
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, s->device));
+    s->n_sms = prop.multiProcessorCount;
+    P.n_classes = (uint32_t)s->n_classes;
+    for (int k = 0; k < 4; k++) P.cls_cap[k] = k < s->n_classes ? s->class_cap[k] : 0xFFFFFFFFu;
+    for (int k = 0; k < s->n_classes; k++)
+      s->class_grid[k] = s->n_sms * msk_round_occupancy(s->class_threads[k], msk_round_smem_bytes(s->class_cap[k]));
+    if ((rc = s->dalloc(&P.cls_list, (size_t)2 * 4 * P.t_max))) return rc;
+    CK(cudaStreamSynchronize(s->stream));
+  }
   CK(cudaStreamSynchronize(s->stream));
   return MS_OK;
 }

@@ -267,27 +267,41 @@ __device__ __forceinline__ void emit_one(const Params& p, DevState* st, const Ne
 __global__ void k_set_bit(uint32_t* words, size_t word, uint32_t bit) { atomicOr(words + word, 1u << bit); }
 
 // ------------------------------------------------------------------ k_snapshot
-// head <- limit, limit <- tail; also finds the largest window of the round so
-// that exactly one size class of k_round runs it.
+// head <- limit, limit <- tail, and sorts every ticket into the work list of the
+// k_round size class its window fits.  Lists are double-buffered
+// by round parity; the other parity's counters are cleared here.
+__device__ __forceinline__ uint32_t class_of(const Params& p, uint32_t n) {
+  uint32_t c = 0;
+  while (c + 1 < p.n_classes && n > p.cls_cap[c]) c++;
+  return c;
+}
+
 __global__ void k_snapshot(Params p) {
   DevState* st = p.st;
   if (round_skipped(p, st)) return;
+  const uint32_t par = (uint32_t)st->round & 1u;
   const uint32_t stride = gridDim.x * blockDim.x;
-  uint32_t wmax = 0;
-  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < p.n_ep; e += stride) {
+  const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  for (uint32_t e = gid; e < p.n_ep; e += stride) {
     const uint32_t h = p.limit[e], l = p.tail[e];
     p.head[e] = h;
     p.limit[e] = l;
-    if (p.kind[e] != kRemoved) wmax = max(wmax, l - h);
+    const uint32_t n = (p.kind[e] == kRemoved) ? 0u : l - h;
+    const uint32_t c = class_of(p, n);
+    const uint32_t k = atomicAdd(&st->cls_count[par][c], 1u);
+    p.cls_list[((size_t)par * 4 + c) * p.t_max + k] = p.n_inj_tickets + e;
   }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) wmax = max(wmax, __shfl_xor_sync(FULL, wmax, d));
-  if ((threadIdx.x & 31) == 0 && wmax) atomicMax(&st->round_max_window, wmax);
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (gid < p.n_inj_tickets) {   // injector slices run in the widest class
+    const uint32_t c = p.n_classes - 1;
+    const uint32_t k = atomicAdd(&st->cls_count[par][c], 1u);
+    p.cls_list[((size_t)par * 4 + c) * p.t_max + k] = gid;
+  }
+  if (gid == 0) {
     if (st->cal_release) {
       p.cal_count[st->cal_release - 1] = 0;
       st->cal_release = 0;
     }
+    for (int c = 0; c < 4; c++) { st->cls_count[par ^ 1u][c] = 0; st->cls_cursor[par ^ 1u][c] = 0; }
     st->slot_open = 1;
   }
 }
@@ -354,6 +368,12 @@ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
   return x;
 }
 
+// neighbor list of the node held in shared memory when it is short (nl != nullptr)
+struct NbrList {
+  const uint32_t* nl;
+  uint32_t deg;
+};
+
 __device__ __forceinline__ uint32_t nbr_count(const Params& p, uint32_t e) {
   if (p.topology == MS_TOPO_TOTAL) return p.n_servers - 1;
   return p.nbr_off[e + 1] - p.nbr_off[e];
@@ -374,7 +394,14 @@ __device__ __forceinline__ uint32_t nbr_pos(const Params& p, uint32_t e, uint32_
 }
 
 // number of emissions of one delivered message (count phase)
-__device__ __forceinline__ uint32_t node_emit_count(const Params& p, uint32_t e, const MsgView& w, bool is_new) {
+__device__ __forceinline__ uint32_t nbr_pos_l(const Params& p, uint32_t e, uint32_t src, const NbrList& L) {
+  if (L.nl == nullptr) return nbr_pos(p, e, src);
+  for (uint32_t j = 0; j < L.deg; j++) if (L.nl[j] == src) return j;
+  return 0xFFFFFFFFu;
+}
+
+__device__ __forceinline__ uint32_t node_emit_count(const Params& p, uint32_t e, const MsgView& w, bool is_new,
+                                                    const NbrList& L) {
   const uint32_t type = w.tf & 0xFFFFu;
   const bool has_id = (w.tf >> 16) & MS_F_MSG_ID;
   const bool is_reply = (w.tf >> 16) & MS_F_REPLY;
@@ -388,8 +415,8 @@ __device__ __forceinline__ uint32_t node_emit_count(const Params& p, uint32_t e,
     case MS_T_BROADCAST: {
       uint32_t n = has_id ? 1u : 0u;
       if (is_new) {
-        n += nbr_count(p, e);
-        if (nbr_pos(p, e, w.src) != 0xFFFFFFFFu) n -= 1;   // skip whoever sent it to us
+        n += L.deg;
+        if (nbr_pos_l(p, e, w.src, L) != 0xFFFFFFFFu) n -= 1;   // skip whoever sent it to us
       }
       return n;
     }
@@ -401,7 +428,8 @@ __device__ __forceinline__ uint32_t node_emit_count(const Params& p, uint32_t e,
 // the emission goes to when it is gossip to a topology neighbor, else -1.
 __device__ __forceinline__ int node_emit(const Params& p, uint32_t e, const MsgView& w, uint32_t k,
                                          uint32_t nemit, uint32_t emit_idx, uint32_t msg_id_base,
-                                         uint32_t set_before, uint32_t new_before, uint64_t p1, Rec& r) {
+                                         uint32_t set_before, uint32_t new_before, uint64_t p1, Rec& r,
+                                         const NbrList& L) {
   const uint32_t type = w.tf & 0xFFFFu;
   int slot = -1;
   r.src = e; r.dest = w.src; r.msg_id = 0; r.in_reply_to = w.msg_id;
@@ -421,9 +449,9 @@ __device__ __forceinline__ int node_emit(const Params& p, uint32_t e, const MsgV
         const bool has_id = (w.tf >> 16) & MS_F_MSG_ID;
         if (has_id && k == nemit - 1) { otype = MS_T_BROADCAST_OK; break; }
         // gossip to the k-th neighbor other than the sender, in topology order
-        const uint32_t ps = nbr_pos(p, e, w.src);
+        const uint32_t ps = nbr_pos_l(p, e, w.src, L);
         const uint32_t j = (ps != 0xFFFFFFFFu && k >= ps) ? k + 1 : k;
-        r.dest = nbr_at(p, e, j);
+        r.dest = L.nl ? L.nl[j] : nbr_at(p, e, j);
         slot = (int)j;
         otype = MS_T_BROADCAST; oflags = 0; r.in_reply_to = 0; r.p0 = w.p0;
         break;
@@ -441,20 +469,16 @@ __device__ __forceinline__ int node_emit(const Params& p, uint32_t e, const MsgV
 // of this size class:
 //   reg1 u64[cap+1] (order keys -> dedupe table -> packed count scan)
 //   keyB u32[cap] | vals u32[cap] | ord u16[cap]                    = 18 B / message
-__global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap_lo, uint32_t cap, uint32_t last_class) {
+__global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cls, uint32_t cap) {
   DevState* st = p.st;
   if (round_skipped(p, st) || !st->slot_open) return;
-  {
-    const uint32_t rm = st->round_max_window;
-    if (rm <= cap_lo && cap_lo != 0) return;
-    if (rm > cap && !last_class) return;
-  }
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* reg1 = reinterpret_cast<uint64_t*>(smem_raw);          // cap+1 entries
   uint32_t* keyB = reinterpret_cast<uint32_t*>(reg1 + cap + 1);
   uint32_t* vals = keyB + cap;
   uint16_t* ord = reinterpret_cast<uint16_t*>(vals + cap);
+  uint8_t* blk = reinterpret_cast<uint8_t*>(ord + cap);            // sorted position -> sorted block
   uint64_t* keyA = reg1;
   uint32_t* tab = reinterpret_cast<uint32_t*>(reg1);               // dedupe table, 2*npad entries
   uint64_t* aux = reg1;                                            // packed counts
@@ -462,7 +486,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap_lo, uin
   __shared__ uint64_t s_wtmp[34];
   __shared__ NetParams s_np;
   __shared__ uint32_t s_wcnt[17];
-  __shared__ uint32_t s_misc[8];       // 0: mail base, 1: use_blocks, 3: inj-server-src flag, 4: is_last
+  __shared__ uint32_t s_misc[8];       // 0: mail base, 1: use_blocks, 3: inj-server-src flag, 4: is_last, 5: next list index
   __shared__ uint64_t s_chunk;
   // sender blocks of the window (fast ordering path)
   __shared__ uint16_t s_bstart[MAXB + 1];     // window offset of block r (arrival order)
@@ -472,17 +496,28 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap_lo, uin
   __shared__ uint64_t s_bbase[MAXB];          // sorted: dense id of the block's idx 0
   __shared__ uint16_t s_S[MAXB + 1][MAXNB];   // sorted: new messages from neighbor j in blocks < rho
   __shared__ uint32_t s_nbbase[MAXNB];        // ring position claimed for this CTA's gossip to neighbor j
+  __shared__ uint32_t s_nbr[MAXNB];           // this node's neighbor list (topology order)
 
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_np = *p.np;
-  if (tid < 8) s_misc[tid] = 0;
   __syncthreads();
-  const uint32_t ticket = blockIdx.x;
   const NetParams np = s_np;
   const int64_t now = st->now;
   const uint64_t round = st->round;
   const uint32_t T = p.n_inj_tickets + p.n_ep;
   const uint32_t row = (uint32_t)round & p.hist_mask;
+  const uint32_t par = (uint32_t)round & 1u;
+  const uint32_t my_count = st->cls_count[par][cls];                // final: k_snapshot has completed
+  const uint32_t* my_list = p.cls_list + ((size_t)par * 4 + cls) * p.t_max;
+
+ // persistent CTA: take tickets of this size class until the list is exhausted
+ for (;;) {
+  __syncthreads();                     // the previous ticket is completely done with shared memory
+  if (tid == 0) s_misc[5] = atomicAdd(&st->cls_cursor[par][cls], 1u);
+  if (tid < 5) s_misc[tid] = 0;
+  __syncthreads();
+  if (s_misc[5] >= my_count) break;
+  const uint32_t ticket = my_list[s_misc[5]];
 
   EmitCtx cx;
   cx.now = now;
@@ -553,6 +588,9 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap_lo, uin
     const bool is_server = (kind == MS_KIND_SERVER);
     const bool bcast = is_server && p.workload == MS_W_BROADCAST;
     const uint32_t* mybits = (is_server && p.bitmap) ? p.bitmap + (size_t)e * p.bm_words : nullptr;
+    const uint32_t deg = bcast ? nbr_count(p, e) : 0;
+    const bool nb_smem = bcast && p.topology != MS_TOPO_TOTAL && deg <= MAXNB;
+    if (nb_smem && tid < (int)deg) s_nbr[tid] = p.nbr[p.nbr_off[e] + tid];
 
     // PA: one pass over the window in arrival order: order keys, partition check
     //     at dequeue (net.clj:234), first half of the seen-set test
@@ -667,7 +705,10 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap_lo, uin
           // block of window slot i (arrival order): last r with bstart[r] <= i
           uint32_t lo = 0, hi = R;
           while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_bstart[mid] <= i) lo = mid; else hi = mid; }
-          ord[s_boff[s_brank[lo]] + (i - s_bstart[lo])] = (uint16_t)i;
+          const uint32_t rk = s_brank[lo];
+          const uint32_t pos = s_boff[rk] + (i - s_bstart[lo]);
+          ord[pos] = (uint16_t)i;
+          blk[pos] = (uint8_t)rk;
         }
         __syncthreads();
       } else {
@@ -730,6 +771,9 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap_lo, uin
       }
       __syncthreads();
     }
+    NbrList L;
+    L.nl = nb_smem ? s_nbr : nullptr;
+    L.deg = deg;
     // packed counts in sorted order: emit (bits 0-31) | recv (32-47) | new (48-63)
     for (int pos = tid; pos < (int)n; pos += nt) {
       const uint32_t i = ord[pos];
@@ -740,7 +784,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap_lo, uin
         const bool is_new = (val & V_FRESH) != 0;
         if (is_server) {
           const MsgView w = view_load(myring + (size_t)((head + i) & p.ring_mask) * 3);
-          c |= node_emit_count(p, e, w, is_new);
+          c |= node_emit_count(p, e, w, is_new, L);
         }
         if (is_new) c |= 1ull << 48;
       }
@@ -755,8 +799,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap_lo, uin
 
     // PD: claims: journal chunk, mailbox, per-neighbor ring blocks
     const bool mailed = (kind == MS_KIND_CLIENT || kind == MS_KIND_HOST);
-    const uint32_t deg = bcast ? nbr_count(p, e) : 0;
-    const bool agg = use_blocks && bcast && p.topology != MS_TOPO_TOTAL && deg <= MAXNB && n_new > 0 &&
+    const bool agg = use_blocks && nb_smem && n_new > 0 &&
                      np.loss_thresh == 0 && np.dist == MS_DIST_CONSTANT && (uint64_t)np.mean_ms * np.scale == 0 &&
                      s_misc[3] == 0;
     if (tid == 0) {
@@ -768,7 +811,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap_lo, uin
     }
     if (agg && tid < (int)deg) {   // deg <= MAXNB <= 32 <= blockDim
       // S[rho][j]: new messages, in blocks before rho, that came from neighbor j (they do not go back to j)
-      const uint32_t nb = nbr_at(p, e, tid);
+      const uint32_t nb = s_nbr[tid];
       uint32_t acc = 0;
       for (uint32_t q = 0; q < R; q++) {
         s_S[q][tid] = (uint16_t)acc;
@@ -811,11 +854,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap_lo, uin
         new_before = (uint32_t)(a0 >> 48);
         const uint32_t val = vals[i];
         is_new = (val & V_FRESH) != 0;
-        if (use_blocks) {
-          uint32_t lo = 0, hi = R;
-          while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_boff[mid] <= pos) lo = mid; else hi = mid; }
-          rho = lo;
-        }
+        if (use_blocks) rho = blk[pos];
         if (val & V_RECV) {
           const uint32_t k = (uint32_t)(a0 >> 32) & 0xFFFFu;
           const uint4* rp = myring + (size_t)((head + i) & p.ring_mask) * 3;
@@ -852,7 +891,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap_lo, uin
         uint32_t direct = 0;
         bool has_direct = false;
         if (valid) {
-          const int slot = node_emit(p, e, w, k, my_emit, e_idx0 + k, msg_id_base, set_before, new_before, p1, r);
+          const int slot = node_emit(p, e, w, k, my_emit, e_idx0 + k, msg_id_base, set_before, new_before, p1, r, L);
           if (agg && slot >= 0 && is_new) {
             direct = s_nbbase[slot] + new_before - s_S[rho][slot];
             has_direct = true;
@@ -891,7 +930,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap_lo, uin
   }
   __syncthreads();
   if (tid == 0) {
-    // this ticket's row entries (turned into prefixes by the last CTA)
+    // this ticket's row entries (turned into prefixes by the last CTA of the round)
     p.rt_em[(size_t)row * p.t_max + ticket] = n_em_local;
     p.rt_ev[(size_t)row * p.t_max + ticket] = n_ev_local;
     p.rt_chunk[(size_t)row * p.t_max + ticket] = cx.chunk;
@@ -964,7 +1003,6 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap_lo, uin
       st->round = round + 1;
       st->rounds_run += 1;
       st->done = 0;
-      st->round_max_window = 0;
       st->slot_open = 0;
       const uint64_t raw_cur = *reinterpret_cast<volatile uint64_t*>(&st->jraw_cursor);
       if (p.jdiscard || !p.jlevel) {
@@ -985,6 +1023,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap_lo, uin
       __threadfence();
     }
   }
+ }   // persistent loop
 }
 
 // ------------------------------------------------------------------ k_journal_expand (K3)
@@ -1044,16 +1083,23 @@ cudaError_t msk_round_smem_attr(size_t bytes) {
   return cudaFuncSetAttribute(msd::k_round, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-size_t msk_round_smem_bytes(uint32_t cap) { return (size_t)cap * 18 + 32; }
+size_t msk_round_smem_bytes(uint32_t cap) { return (size_t)cap * 19 + 32; }
 
 void msk_set_bit(uint32_t* words, size_t word, uint32_t bit, cudaStream_t s) {
   msd::k_set_bit<<<1, 1, 0, s>>>(words, word, bit);
 }
 
-// One round = [k_release] k_snapshot, then k_round once per window-size class
-// (caps[] ascending, threads[] per class); exactly one class executes.
+int msk_round_occupancy(int threads, size_t smem) {
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msd::k_round, threads, smem) != cudaSuccess) return 1;
+  return nb < 1 ? 1 : nb;
+}
+
+// One round = [k_release] k_snapshot, then one persistent k_round grid per
+// window-size class (caps ascending); every ticket is taken by exactly one class.
 void msk_launch_round(const msd::Params* p, int n_classes, const uint32_t* caps, const int* threads,
-                      int with_release, cudaStream_t s, cudaEvent_t before_round, cudaEvent_t after_round) {
+                      const int* grids, int with_release, cudaStream_t s, cudaEvent_t before_round,
+                      cudaEvent_t after_round) {
   const uint32_t n_ep = p->n_ep;
   if (with_release) msd::k_release<<<296, 256, 0, s>>>(*p);
   const int sb = 256;
@@ -1062,10 +1108,8 @@ void msk_launch_round(const msd::Params* p, int n_classes, const uint32_t* caps,
   if (sg < 1) sg = 1;
   msd::k_snapshot<<<sg, sb, 0, s>>>(*p);
   if (before_round) cudaEventRecord(before_round, s);
-  for (int c = 0; c < n_classes; c++) {
-    const uint32_t lo = c ? caps[c - 1] : 0u;
-    msd::k_round<<<p->n_inj_tickets + n_ep, threads[c], msk_round_smem_bytes(caps[c]), s>>>(
-        *p, lo, caps[c], c == n_classes - 1 ? 1u : 0u);
+  for (int c = n_classes - 1; c >= 0; c--) {   // big windows first
+    msd::k_round<<<grids[c], threads[c], msk_round_smem_bytes(caps[c]), s>>>(*p, (uint32_t)c, caps[c]);
   }
   if (after_round) cudaEventRecord(after_round, s);
 }
