@@ -414,14 +414,15 @@ static int build_sim(ms_sim* s, const ms_config* in) {
   {
     // per-round history: 16 B per (round, ticket); keep it under ~1 GB
     P.t_max = M + P.n_inj_tickets;
-    uint32_t hist = c.reserved[0] ? pow2_at_least(c.reserved[0]) : 4096;
-    while (hist > 64 && (uint64_t)hist * P.t_max * 16 > (1ull << 30)) hist >>= 1;
+    uint32_t hist = c.reserved[0] ? std::min<uint32_t>(pow2_at_least(c.reserved[0]), 16384u) : 4096;   // < 2^15: entry tags
+    while (hist > 64 && (uint64_t)hist * P.t_max * 24 > (1ull << 30)) hist >>= 1;
     P.hist = hist;
     P.hist_mask = hist - 1;
     if ((rc = s->dalloc(&P.rmeta, hist))) return rc;
     if ((rc = s->dalloc(&P.rt_em, (size_t)hist * P.t_max))) return rc;
     if ((rc = s->dalloc(&P.rt_ev, (size_t)hist * P.t_max))) return rc;
     if ((rc = s->dalloc(&P.rt_chunk, (size_t)hist * P.t_max))) return rc;
+    if ((rc = s->dalloc(&P.rt_cnt, (size_t)hist * P.t_max))) return rc;
     std::vector<RoundMeta> init(hist);
     memset(init.data(), 0, init.size() * sizeof(RoundMeta));
     for (uint32_t i = 1; i < hist; i++) init[i].round = ~0ull;

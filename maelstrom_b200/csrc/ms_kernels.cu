@@ -509,15 +509,20 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cls, uint32
   const uint32_t par = (uint32_t)round & 1u;
   const uint32_t my_count = st->cls_count[par][cls];                // final: k_snapshot has completed
   const uint32_t* my_list = p.cls_list + ((size_t)par * 4 + cls) * p.t_max;
+  const uint32_t tag = ((uint32_t)round & 0x7FFFu) + 1u;            // validates this round's table entries
+  if (tid == 0) s_misc[5] = atomicAdd(&st->cls_cursor[par][cls], 1u);
 
  // persistent CTA: take tickets of this size class until the list is exhausted
  for (;;) {
   __syncthreads();                     // the previous ticket is completely done with shared memory
-  if (tid == 0) s_misc[5] = atomicAdd(&st->cls_cursor[par][cls], 1u);
+  const uint32_t li = s_misc[5];
   if (tid < 5) s_misc[tid] = 0;
   __syncthreads();
-  if (s_misc[5] >= my_count) break;
-  const uint32_t ticket = my_list[s_misc[5]];
+  if (li >= my_count) break;
+  // fetch the index of the NEXT ticket now; it is consumed at the end of this one
+  uint32_t next_li = 0;
+  if (tid == 0) next_li = atomicAdd(&st->cls_cursor[par][cls], 1u);
+  const uint32_t ticket = my_list[li];
 
   EmitCtx cx;
   cx.now = now;
@@ -924,29 +929,45 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cls, uint32
     if (cnt[3]) { atomicAdd((unsigned long long*)&st->stats[1], (unsigned long long)cnt[3]);
                   atomicAdd((unsigned long long*)&st->stats[5], (unsigned long long)cnt[3]); }
     if (cnt[4]) atomicAdd((unsigned long long*)&st->lost, (unsigned long long)cnt[4]);
-    if (cnt[5]) atomicAdd(&st->zero_pending, cnt[5]);
     if (cnt[6]) atomicAdd((unsigned long long*)&st->part_drops, (unsigned long long)cnt[6]);
     if (cnt[7]) atomicAdd((unsigned long long*)&st->client_replies, (unsigned long long)cnt[7]);
   }
-  __syncthreads();
+  const int any_zero = __syncthreads_or(cx.c_zero != 0);
   if (tid == 0) {
-    // this ticket's row entries (turned into prefixes by the last CTA of the round)
-    p.rt_em[(size_t)row * p.t_max + ticket] = n_em_local;
-    p.rt_ev[(size_t)row * p.t_max + ticket] = n_ev_local;
+    // this ticket's table entry, validated by the round tag so that no fence is needed:
+    // tag(16) | zero-latency pending(1) | events(23) | emissions(24); the last CTA turns
+    // the counts into prefixes
+    if (n_ev_local >= (1u << 23) || n_em_local >= (1u << 24)) latch_error(st, E_ID_RANGE, ticket);
     p.rt_chunk[(size_t)row * p.t_max + ticket] = cx.chunk;
-    __threadfence();
+    const uint64_t entry = ((uint64_t)tag << 48) | (any_zero ? (1ull << 47) : 0ull) |
+                           ((uint64_t)(n_ev_local & 0x7FFFFFu) << 24) | (uint64_t)(n_em_local & 0xFFFFFFu);
+    __stcg(reinterpret_cast<unsigned long long*>(p.rt_cnt + (size_t)row * p.t_max + ticket),
+           (unsigned long long)entry);
     s_misc[4] = (atomicAdd(&st->done, 1u) == T - 1) ? 1u : 0u;
+    s_misc[5] = next_li;
   }
   __syncthreads();
   if (s_misc[4]) {
     // ---------------------------------------------------------- last CTA: commit the round
-    __threadfence();
+    const uint64_t* cntp = p.rt_cnt + (size_t)row * p.t_max;
     uint32_t* em = p.rt_em + (size_t)row * p.t_max;
     uint32_t* ev = p.rt_ev + (size_t)row * p.t_max;
     const int c = ((int)T + nt - 1) / nt;
     const int lo = min(tid * c, (int)T), hi = min(lo + c, (int)T);
     uint64_t sum = 0;   // ev << 32 | em  (per-round totals stay below 2^32)
-    for (int i = lo; i < hi; i++) sum += ((uint64_t)ld_cg_u32(ev + i) << 32) | ld_cg_u32(em + i);
+    uint32_t zp_any = 0;
+    for (int i = lo; i < hi; i++) {
+      // every ticket has bumped `done`, so its entry store is in flight at worst: wait for the tag
+      uint64_t v = __ldcg(reinterpret_cast<const unsigned long long*>(cntp + i));
+      for (uint32_t spin = 0; (uint32_t)(v >> 48) != tag && spin < (1u << 24); spin++)
+        v = __ldcg(reinterpret_cast<const unsigned long long*>(cntp + i));
+      if ((uint32_t)(v >> 48) != tag) latch_error(st, E_HISTORY, (uint32_t)i);
+      zp_any |= (uint32_t)(v >> 47) & 1u;
+      const uint32_t ve = (uint32_t)(v >> 24) & 0x7FFFFFu, vm = (uint32_t)v & 0xFFFFFFu;
+      ev[i] = ve; em[i] = vm;   // raw counts; turned into prefixes below (same thread)
+      sum += ((uint64_t)ve << 32) | vm;
+    }
+    zp_any = __syncthreads_or(zp_any);
     uint64_t incl = sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -970,7 +991,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cls, uint32
     __syncthreads();
     uint64_t run = s_wtmp[warp] + incl - sum;
     for (int i = lo; i < hi; i++) {
-      const uint32_t ve = ld_cg_u32(ev + i), vm = ld_cg_u32(em + i);
+      const uint32_t ve = ev[i], vm = em[i];   // written by this thread above
       ev[i] = (uint32_t)(run >> 32);
       em[i] = (uint32_t)run;
       run += ((uint64_t)ve << 32) | vm;
@@ -989,9 +1010,8 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cls, uint32
       uint32_t hi_s = (tick + 1 < p.n_tick_off) ? p.tick_off[tick + 1] : p.n_sched;
       if (hi_s > st->sched_cursor) st->sched_cursor = hi_s;
       st->inj_count = 0;
-      const uint32_t zp = *reinterpret_cast<volatile uint32_t*>(&st->zero_pending);
       int64_t next_now = now;
-      if (zp == 0) {
+      if (zp_any == 0) {
         next_now = now + kTickNs;
         st->now = next_now;
         st->time_advanced = 1;
@@ -999,7 +1019,6 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cls, uint32
       } else {
         st->time_advanced = 0;
       }
-      st->zero_pending = 0;
       st->round = round + 1;
       st->rounds_run += 1;
       st->done = 0;
