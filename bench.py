@@ -229,8 +229,8 @@ def gpu_arm(args, rank, world, local_rank):
     total_ticks = W + K
 
     # ---- arm A: device-resident (value + roofline)
-    sim, c0 = make_sim(mb, args, 2 * total_ticks + 4, True, local_rank)
-    ops = make_ops(OP_DTYPE, 0, 2 * total_ticks + 2, V, c0, N_CLIENTS, TYPES["broadcast"], F_MSG_ID)
+    sim, c0 = make_sim(mb, args, 3 * total_ticks + 4, True, local_rank)
+    ops = make_ops(OP_DTYPE, 0, 3 * total_ticks + 2, V, c0, N_CLIENTS, TYPES["broadcast"], F_MSG_ID)
     sim.schedule(ops)
     tick = 0
     for _ in range(W):
@@ -258,6 +258,18 @@ def gpu_arm(args, rank, world, local_rank):
     launches = c_after["launches"] - c_before["launches"]
     rounds = c_after["rounds"] - c_before["rounds"]
 
+    if args.phases:
+        sim.phase_cycles(True)
+        for _ in range(K):
+            tick += 1
+            run_until_tick(sim, tick)
+        pc = sim.phase_cycles(True)
+        names = ["fetch", "load", "order", "dedupe", "count+scan", "claims", "emit", "epilogue", "commit"]
+        for c in range(4):
+            nt_ = int(pc[c][15])
+            if nt_:
+                sys.stderr.write("class %d: %d tickets; cycles/ticket: %s\n" % (
+                    c, nt_, ", ".join("%s=%d" % (nm, int(pc[c][k]) // nt_) for k, nm in enumerate(names))))
     # roofline pass: same work again (next K ticks) with CUDA events around every round-kernel launch
     sim.profile(True)
     sim.profile_read()
@@ -378,6 +390,7 @@ def main():
     ap.add_argument("--cpu-values", type=int, default=512)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--phases", action="store_true", help="print per-phase cycle counts of the round kernel (stderr)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

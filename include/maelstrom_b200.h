@@ -216,6 +216,11 @@ int ms_timer_begin(ms_sim* sim);
 int ms_timer_end(ms_sim* sim, double* elapsed_ms);
 int ms_profile(ms_sim* sim, int enable);
 int ms_profile_read(ms_sim* sim, double* round_kernel_ms, uint64_t* launches);
+/* Diagnostic: per-phase SM-cycle sums of the round kernel, [4 size classes][16]:
+ * slots 0-8 = ticket fetch, load, ordering, dedupe, count+scan, claims, emit,
+ * epilogue, commit; slot 15 = tickets processed.  enable=1 starts accounting;
+ * every call returns the sums since the previous call and clears them. */
+int ms_debug_phase_cycles(ms_sim* sim, int enable, uint64_t out[64]);
 
 /* pure helper: neighbors of `node` under workload/broadcast.clj:40-178 */
 size_t ms_topology(uint32_t topology, uint32_t n, uint32_t node, uint32_t* out, size_t cap);

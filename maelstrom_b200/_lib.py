@@ -79,6 +79,7 @@ SYMBOLS = {
     "ms_timer_end": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "ms_profile": (C.c_int, [_P, C.c_int]),
     "ms_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "ms_debug_phase_cycles": (C.c_int, [_P, C.c_int, _P]),
     "ms_topology": (C.c_size_t, [C.c_uint32, C.c_uint32, C.c_uint32, _P, C.c_size_t]),
 }
 

@@ -102,6 +102,7 @@ struct Params {
   uint32_t* rt_ev;           // events per ticket, exclusive prefix once committed
   uint64_t* rt_chunk;        // raw journal position of the ticket's chunk
   uint64_t* rt_cnt;          // tagged per-ticket counts of the round in flight (see k_round epilogue)
+  uint64_t* phase_cycles;    // diagnostic: [4 classes][16] cycle sums per k_round phase, or nullptr
   uint32_t  hist, hist_mask, t_max, n_classes;
   uint32_t* cls_list;        // [2][4][t_max] tickets per size class
   uint32_t  cls_cap[4];      // ascending window capacities of the classes

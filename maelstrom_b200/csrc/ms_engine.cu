@@ -816,10 +816,13 @@ uint64_t ms_journal_written(ms_sim* s) { std::lock_guard<std::mutex> g(s->mu); r
 
 int ms_stats(ms_sim* s, uint64_t out[9]) {
   std::lock_guard<std::mutex> g(s->mu);
+  // the device keeps {clients, servers} x {send, recv}; "all" is their sum
+  const uint64_t snd[3] = {s->hs.stats[2] + s->hs.stats[4], s->hs.stats[2], s->hs.stats[4]};
+  const uint64_t rcv[3] = {s->hs.stats[3] + s->hs.stats[5], s->hs.stats[3], s->hs.stats[5]};
   for (int c = 0; c < 3; c++) {
-    out[c * 3 + 0] = s->hs.stats[c * 2 + 0];
-    out[c * 3 + 1] = s->hs.stats[c * 2 + 1];
-    out[c * 3 + 2] = s->hs.stats[c * 2 + 0];   // every id has exactly one :send, so msg-count == send-count
+    out[c * 3 + 0] = snd[c];
+    out[c * 3 + 1] = rcv[c];
+    out[c * 3 + 2] = snd[c];   // every id has exactly one :send, so msg-count == send-count
   }
   return MS_OK;
 }
@@ -843,8 +846,8 @@ uint64_t ms_client_replies(ms_sim* s) { std::lock_guard<std::mutex> g(s->mu); re
 int ms_counters(ms_sim* s, uint64_t out[8]) {
   std::lock_guard<std::mutex> g(s->mu);
   out[0] = s->hs.rounds_run;
-  out[1] = s->hs.stats[0];
-  out[2] = s->hs.stats[1];
+  out[1] = s->hs.stats[2] + s->hs.stats[4];
+  out[2] = s->hs.stats[3] + s->hs.stats[5];
   out[3] = s->launches;
   out[4] = s->hs.lost;
   out[5] = s->hs.part_drops;
@@ -877,6 +880,22 @@ int ms_timer_end(ms_sim* s, double* elapsed_ms) {
 int ms_profile(ms_sim* s, int enable) {
   std::lock_guard<std::mutex> g(s->mu);
   s->profiling = enable != 0;
+  return MS_OK;
+}
+
+int ms_debug_phase_cycles(ms_sim* s, int enable, uint64_t out[64]) {
+  std::lock_guard<std::mutex> g(s->mu);
+  cudaSetDevice(s->device);
+  if (enable && !s->P.phase_cycles) {
+    int rc = s->dalloc(&s->P.phase_cycles, 64);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(s->stream));
+  }
+  if (out) {
+    if (s->P.phase_cycles) CK(cudaMemcpy(out, s->P.phase_cycles, 64 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    else memset(out, 0, 64 * sizeof(uint64_t));
+  }
+  if (s->P.phase_cycles) CK(cudaMemset(s->P.phase_cycles, 0, 64 * sizeof(uint64_t)));
   return MS_OK;
 }
 

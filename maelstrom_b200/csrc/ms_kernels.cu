@@ -186,6 +186,8 @@ struct EmitCtx {
   uint32_t ticket;
   uint32_t emitter;  // Philox stream: endpoint index or kInjector
   uint32_t idx_bias; // added to local_idx for the Philox counter (injector slices)
+  bool need_rng;     // false: no loss and constant latency, the random draw is never looked at
+  uint64_t const_lat;
   // per-thread counters, reduced at the end of the CTA
   uint32_t c_send_cl, c_send_sv, c_lost, c_zero;
 };
@@ -217,11 +219,14 @@ __device__ __forceinline__ void emit_one(const Params& p, DevState* st, const Ne
   }
   if (valid) {
     r.round = cx.round; r.ticket = cx.ticket; r.idx = local_idx;     // order key == id order (net.clj:197)
-    uint32_t x[4];
-    philox4x32_10(local_idx + cx.idx_bias, cx.emitter, (uint32_t)cx.round, (uint32_t)(cx.round >> 32),
-                  p.seed_lo, p.seed_hi, x);
-    const bool cl = kind_is_client(p.kind[r.src]) || kind_is_client(p.kind[r.dest]);   // util.clj:12-16
-    const uint64_t lat = cl ? 0ull : latency_ms(np, x);              // net.clj:185-187
+    uint32_t x[4] = {0xFFFFFFFFu, 0, 0, 0};
+    if (cx.need_rng)
+      philox4x32_10(local_idx + cx.idx_bias, cx.emitter, (uint32_t)cx.round, (uint32_t)(cx.round >> 32),
+                    p.seed_lo, p.seed_hi, x);
+    // util.clj:12-16; servers are the endpoints below n_servers, so most lookups are avoided
+    const bool cl = (r.src >= p.n_servers && kind_is_client(p.kind[r.src])) ||
+                    (r.dest >= p.n_servers && kind_is_client(p.kind[r.dest]));
+    const uint64_t lat = cl ? 0ull : (cx.need_rng ? latency_ms(np, x) : cx.const_lat);   // net.clj:185-187
     journal_raw(p, cx.chunk + cx.n_recv + local_idx, local_idx, false, r);   // net.clj:208 (before the loss roll)
     if (cl) cx.c_send_cl++; else cx.c_send_sv++;
     if ((uint64_t)x[0] < np.loss_thresh) {                           // net.clj:214-215
@@ -246,6 +251,7 @@ __device__ __forceinline__ void emit_one(const Params& p, DevState* st, const Ne
       }
     }
   }
+  if (!__any_sync(FULL, push)) return;
   // warp-aggregated claim of ring slots: one atomic per distinct destination
   const uint32_t key = push ? r.dest : (0x80000000u | (uint32_t)lane);
   const uint32_t mask = __match_any_sync(FULL, key);
@@ -361,7 +367,8 @@ __device__ __forceinline__ MsgView view_load(const uint4* rec) {
 // vals[] bits
 constexpr uint32_t V_FRESH = 1u << 31;  // broadcast value unseen so far (after PC: first sight = new)
 constexpr uint32_t V_RECV = 1u << 30;   // passed the partition check
-constexpr uint32_t V_MASK = (1u << 30) - 1u;
+constexpr uint32_t V_CAND = 1u << 29;   // carries a broadcast value that needs the seen-set test
+constexpr uint32_t V_MASK = (1u << 29) - 1u;
 
 __device__ __forceinline__ uint32_t hash32(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
@@ -464,11 +471,52 @@ __device__ __forceinline__ int node_emit(const Params& p, uint32_t e, const MsgV
 }
 
 // ------------------------------------------------------------------ k_round
-// One CTA per ticket: tickets [0, n_inj_tickets) are injector slices, ticket
-// n_inj_tickets + e is endpoint e.  Dynamic shared memory, `cap` = window capacity
-// of this size class:
-//   reg1 u64[cap+1] (order keys -> dedupe table -> packed count scan)
-//   keyB u32[cap] | vals u32[cap] | ord u16[cap]                    = 18 B / message
+// Persistent CTAs; one ticket at a time: tickets [0, n_inj_tickets) are injector
+// slices, ticket n_inj_tickets + e is endpoint e.  Dynamic shared memory, `cap` =
+// window capacity of this size class (21 B / message):
+//   reg1 u64[cap+1]  order keys (round << 24 | ticket)  ->  packed count scan
+//   keyB u32[cap]    emission index of the key           ->  first-sight table (u16[2*npad])
+//   vals u32[cap]    value | V_* flags        meta u16[cap]  compact message class
+//   ord  u16[cap]    sorted position -> window slot      blk u8[cap]  sorted position -> sender block
+constexpr uint32_t M_SRCSLOT = 0xFu;      // meta bits 0-3: neighbor slot of src + 1, 15 = neighbor (slot unknown), 0 = none
+constexpr uint32_t M_HAS_ID = 1u << 4;
+constexpr uint32_t M_REPLY = 1u << 5;
+constexpr uint32_t M_TC_SHIFT = 6;        // bits 6-8: type class
+enum : uint32_t { TC_OTHER = 0, TC_INIT = 1, TC_TOPOLOGY = 2, TC_READ = 3, TC_BROADCAST = 4, TC_ECHO = 5 };
+
+// emissions of one delivered message from its compact class (count phase, no global access)
+__device__ __forceinline__ uint32_t emit_count_meta(uint32_t workload, uint32_t meta, bool is_new, uint32_t deg) {
+  const uint32_t tc = (meta >> M_TC_SHIFT) & 7u;
+  if (workload == MS_W_ECHO) return (tc == TC_INIT || tc == TC_ECHO) ? 1u : 0u;        // echo.rb:28-39
+  if (meta & M_REPLY) return 0;                                                          // node.rb:159-164
+  if (tc == TC_INIT || tc == TC_TOPOLOGY || tc == TC_READ) return 1;
+  const uint32_t has_id = (meta & M_HAS_ID) ? 1u : 0u;
+  if (tc == TC_BROADCAST) return has_id + (is_new ? deg - ((meta & M_SRCSLOT) ? 1u : 0u) : 0u);
+  return has_id;                                                                         // error 10
+}
+
+// exclusive prefix of one u32 per thread over the CTA; total returned through *total
+__device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t* total, uint32_t* wcnt /* >= 17 */) {
+  const int nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t y = __shfl_up_sync(FULL, incl, d);
+    if (lane >= d) incl += y;
+  }
+  if (lane == 31) wcnt[warp] = incl;
+  __syncthreads();
+  uint32_t before = 0, tot = 0;
+  for (int w = 0; w < (nt >> 5); w++) {
+    const uint32_t cw = wcnt[w];
+    if (w < warp) before += cw;
+    tot += cw;
+  }
+  __syncthreads();
+  *total = tot;
+  return before + incl - v;
+}
+
 __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cls, uint32_t cap) {
   DevState* st = p.st;
   if (round_skipped(p, st) || !st->slot_open) return;
@@ -477,16 +525,18 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cls, uint32
   uint64_t* reg1 = reinterpret_cast<uint64_t*>(smem_raw);          // cap+1 entries
   uint32_t* keyB = reinterpret_cast<uint32_t*>(reg1 + cap + 1);
   uint32_t* vals = keyB + cap;
-  uint16_t* ord = reinterpret_cast<uint16_t*>(vals + cap);
-  uint8_t* blk = reinterpret_cast<uint8_t*>(ord + cap);            // sorted position -> sorted block
+  uint16_t* meta = reinterpret_cast<uint16_t*>(vals + cap);
+  uint16_t* ord = meta + cap;
+  uint8_t* blk = reinterpret_cast<uint8_t*>(ord + cap);
   uint64_t* keyA = reg1;
-  uint32_t* tab = reinterpret_cast<uint32_t*>(reg1);               // dedupe table, 2*npad entries
-  uint64_t* aux = reg1;                                            // packed counts
+  uint64_t* aux = reg1;                                            // packed counts (keyA is dead by then)
+  uint16_t* tab = reinterpret_cast<uint16_t*>(keyB);               // first-sight table (keyB is dead by then)
 
   __shared__ uint64_t s_wtmp[34];
   __shared__ NetParams s_np;
   __shared__ uint32_t s_wcnt[17];
   __shared__ uint32_t s_misc[8];       // 0: mail base, 1: use_blocks, 3: inj-server-src flag, 4: is_last, 5: next list index
+  __shared__ uint32_t s_cnt[8];        // per-ticket counters
   __shared__ uint64_t s_chunk;
   // sender blocks of the window (fast ordering path)
   __shared__ uint16_t s_bstart[MAXB + 1];     // window offset of block r (arrival order)
@@ -510,6 +560,20 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cls, uint32
   const uint32_t my_count = st->cls_count[par][cls];                // final: k_snapshot has completed
   const uint32_t* my_list = p.cls_list + ((size_t)par * 4 + cls) * p.t_max;
   const uint32_t tag = ((uint32_t)round & 0x7FFFu) + 1u;            // validates this round's table entries
+  // with no loss and a constant latency nothing depends on the random draw: skip Philox
+  const bool need_rng = np.loss_thresh != 0 || np.dist != MS_DIST_CONSTANT;
+  const uint64_t const_lat = (uint64_t)np.mean_ms * np.scale;
+  // optional per-phase cycle accounting (diagnostic, ms_debug_phase_cycles)
+  const bool timing = p.phase_cycles != nullptr;
+  long long t_prev = timing ? clock64() : 0;
+#define PHASE_MARK(k)                                                                         \
+  do {                                                                                        \
+    if (timing && tid == 0) {                                                                 \
+      const long long t_now = clock64();                                                      \
+      atomicAdd((unsigned long long*)&p.phase_cycles[cls * 16 + (k)], (unsigned long long)(t_now - t_prev)); \
+      t_prev = t_now;                                                                         \
+    }                                                                                         \
+  } while (0)
   if (tid == 0) s_misc[5] = atomicAdd(&st->cls_cursor[par][cls], 1u);
 
  // persistent CTA: take tickets of this size class until the list is exhausted
@@ -517,12 +581,15 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cls, uint32
   __syncthreads();                     // the previous ticket is completely done with shared memory
   const uint32_t li = s_misc[5];
   if (tid < 5) s_misc[tid] = 0;
+  if (tid < 8) s_cnt[tid] = 0;
   __syncthreads();
   if (li >= my_count) break;
   // fetch the index of the NEXT ticket now; it is consumed at the end of this one
   uint32_t next_li = 0;
   if (tid == 0) next_li = atomicAdd(&st->cls_cursor[par][cls], 1u);
   const uint32_t ticket = my_list[li];
+  PHASE_MARK(0);
+  if (timing && tid == 0) atomicAdd((unsigned long long*)&p.phase_cycles[cls * 16 + 15], 1ull);
 
   EmitCtx cx;
   cx.now = now;
@@ -532,6 +599,8 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cls, uint32
   cx.chunk = 0;
   cx.n_recv = 0;
   cx.emitter = 0;
+  cx.need_rng = need_rng;
+  cx.const_lat = const_lat;
   cx.c_send_cl = cx.c_send_sv = cx.c_lost = cx.c_zero = 0;
   uint32_t c_recv_cl = 0, c_recv_sv = 0, c_part = 0, c_replies = 0;
   uint32_t n_ev_local = 0, n_em_local = 0;
@@ -596,37 +665,86 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cls, uint32
     const uint32_t deg = bcast ? nbr_count(p, e) : 0;
     const bool nb_smem = bcast && p.topology != MS_TOPO_TOTAL && deg <= MAXNB;
     if (nb_smem && tid < (int)deg) s_nbr[tid] = p.nbr[p.nbr_off[e] + tid];
+    __syncthreads();
 
-    // PA: one pass over the window in arrival order: order keys, partition check
-    //     at dequeue (net.clj:234), first half of the seen-set test
-    for (int i = tid; i < (int)n; i += nt) {
-      const uint4* rp = myring + (size_t)((head + i) & p.ring_mask) * 3;
-      const uint4 a = rp[0], b = rp[1], c = rp[2];
-      const uint64_t rnd = (uint64_t)a.z | ((uint64_t)a.w << 32);
-      keyA[i] = (rnd << 24) | (uint64_t)(a.y & 0xFFFFFFu);
-      keyB[i] = a.x;
-      const uint32_t src = b.x, tf = c.x, v = c.y;
-      if (a.y < p.n_inj_tickets && src < p.n_servers) s_misc[3] = 1;   // injected on behalf of a server
-      bool cut = false;
-      if (np.pair_active && p.pair_bits)
-        cut = (p.pair_bits[(size_t)e * p.pair_words + (src >> 5)] >> (src & 31)) & 1u;
-      if (!cut && np.comp_active) {
-        // bulk partition: endpoints in different components are cut; 0xFFFFFFFF = not listed (never cut)
-        const uint32_t cs = p.comp[src], ce = p.comp[e];
-        cut = cs != ce && cs != 0xFFFFFFFFu && ce != 0xFFFFFFFFu;
-      }
-      uint32_t val = cut ? 0u : V_RECV;
-      if (bcast && !cut && (tf & 0xFFFFu) == MS_T_BROADCAST && !((tf >> 16) & MS_F_REPLY)) {
-        if (v >= p.n_values || v > V_MASK) {
-          latch_error(st, E_VALUE_RANGE, v);
-        } else {
-          val |= v;
-          if (!((mybits[v >> 5] >> (v & 31)) & 1u)) val |= V_FRESH;
+    // PA1: one pass over the window in arrival order, loads 2 records deep: order keys,
+    //      partition check at dequeue (net.clj:234), compact message class
+    {
+      uint32_t err_val = 0xFFFFFFFFu;
+      bool inj_srv = false;
+      for (int base = 0; base < (int)n; base += 2 * nt) {
+        uint4 a[2], b[2], c[2];
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+          const int i = base + q * nt + tid;
+          if (i < (int)n) {
+            const uint4* rp = myring + (size_t)((head + i) & p.ring_mask) * 3;
+            a[q] = rp[0]; b[q] = rp[1]; c[q] = rp[2];
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+          const int i = base + q * nt + tid;
+          if (i >= (int)n) continue;
+          const uint64_t rnd = (uint64_t)a[q].z | ((uint64_t)a[q].w << 32);
+          keyA[i] = (rnd << 24) | (uint64_t)(a[q].y & 0xFFFFFFu);
+          keyB[i] = a[q].x;
+          const uint32_t src = b[q].x, tf = c[q].x, v = c[q].y;
+          if (a[q].y < p.n_inj_tickets && src < p.n_servers) inj_srv = true;   // injected on behalf of a server
+          bool cut = false;
+          if (np.pair_active && p.pair_bits)
+            cut = (p.pair_bits[(size_t)e * p.pair_words + (src >> 5)] >> (src & 31)) & 1u;
+          if (!cut && np.comp_active) {
+            // bulk partition: endpoints in different components are cut; 0xFFFFFFFF = not listed (never cut)
+            const uint32_t cs = p.comp[src], ce = p.comp[e];
+            cut = cs != ce && cs != 0xFFFFFFFFu && ce != 0xFFFFFFFFu;
+          }
+          const uint32_t type = tf & 0xFFFFu;
+          const uint32_t fl = tf >> 16;
+          uint32_t tc = TC_OTHER;
+          if (type == MS_T_INIT) tc = TC_INIT;
+          else if (type == MS_T_TOPOLOGY) tc = TC_TOPOLOGY;
+          else if (type == MS_T_READ) tc = TC_READ;
+          else if (type == MS_T_BROADCAST) tc = TC_BROADCAST;
+          else if (type == MS_T_ECHO) tc = TC_ECHO;
+          uint32_t slot = 0;
+          if (nb_smem) {
+            for (uint32_t j = 0; j < deg; j++) if (s_nbr[j] == src) slot = j + 1;
+          } else if (bcast && src < p.n_servers && src != e) {
+            slot = 15;
+          }
+          meta[i] = (uint16_t)(slot | ((fl & MS_F_MSG_ID) ? M_HAS_ID : 0u) | ((fl & MS_F_REPLY) ? M_REPLY : 0u) |
+                               (tc << M_TC_SHIFT));
+          uint32_t val = cut ? 0u : V_RECV;
+          if (bcast && !cut && tc == TC_BROADCAST && !(fl & MS_F_REPLY)) {
+            if (v >= p.n_values || v > V_MASK) err_val = v;
+            else val |= v | V_CAND;
+          }
+          vals[i] = val;
         }
       }
-      vals[i] = val;
+      if (err_val != 0xFFFFFFFFu) latch_error(st, E_VALUE_RANGE, err_val);
+      if (inj_srv) s_misc[3] = 1;
+    }
+    // PA2: seen-set test of the broadcast values (own slots only: no barrier needed in between)
+    if (bcast) {
+      for (int base = 0; base < (int)n; base += 4 * nt) {
+        uint32_t w[4], vv[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int i = base + q * nt + tid;
+          vv[q] = i < (int)n ? vals[i] : 0u;
+          w[q] = (vv[q] & V_CAND) ? mybits[(vv[q] & V_MASK) >> 5] : 0xFFFFFFFFu;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int i = base + q * nt + tid;
+          if (i < (int)n && (vv[q] & V_CAND) && !((w[q] >> (vv[q] & 31)) & 1u)) vals[i] = vv[q] | V_FRESH;
+        }
+      }
     }
     __syncthreads();
+    PHASE_MARK(1);
 
     // PB: order the due set by (round, ticket, idx) == message id order (all due
     //     deadlines equal `now`; the reference's PriorityBlockingQueue leaves ties
@@ -636,29 +754,16 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cls, uint32
     uint32_t R = 0;
     bool use_blocks = false;
     if (n > 0) {
-      uint32_t run = 0;
-      for (uint32_t base = 0; base < n; base += nt) {
-        const uint32_t i = base + tid;
-        bool f = false;
-        if (i < n) f = (i == 0) || keyA[i] != keyA[i - 1] || keyB[i] <= keyB[i - 1];
-        const uint32_t bal = __ballot_sync(FULL, f);
-        if (lane == 0) s_wcnt[warp] = __popc(bal);
-        __syncthreads();
-        uint32_t before = 0, total = 0;
-        for (int w = 0; w < (nt >> 5); w++) {
-          const uint32_t cw = s_wcnt[w];
-          if (w < warp) before += cw;
-          total += cw;
-        }
-        if (f) {
-          const uint32_t pos = run + before + __popc(bal & ((1u << lane) - 1u));
-          if (pos < MAXB) s_bstart[pos] = (uint16_t)i;
-        }
-        run += total;
-        __syncthreads();
-      }
-      R = run;
+      // block starts: each thread scans one contiguous segment of the window
+      const int c = ((int)n + nt - 1) / nt;
+      const int lo = min(tid * c, (int)n), hi = min(lo + c, (int)n);
+      uint32_t nf = 0;
+      for (int i = lo; i < hi; i++)
+        if (i == 0 || keyA[i] != keyA[i - 1] || keyB[i] <= keyB[i - 1]) nf++;
+      uint32_t off = block_excl_scan_u32(nf, &R, s_wcnt);
       if (R <= MAXB) {
+        for (int i = lo; i < hi; i++)
+          if (i == 0 || keyA[i] != keyA[i - 1] || keyB[i] <= keyB[i - 1]) s_bstart[off++] = (uint16_t)i;
         if (tid == 0) s_bstart[R] = (uint16_t)n;
         __syncthreads();
         // rank blocks by their first key
@@ -674,15 +779,11 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cls, uint32
             if (qa < ka || (qa == ka && (qb < kb || (qb == kb && q < b)))) rk++;
           }
           s_brank[b] = (uint16_t)rk;
-        }
-        __syncthreads();
-        for (uint32_t b = tid; b < R; b += nt) {
-          const uint32_t rk = s_brank[b];
-          s_bkeyA[rk] = keyA[s_bstart[b]];
+          s_bkeyA[rk] = ka;
           // temporarily: length of the block, exclusive-scanned below
-          s_boff[rk] = (uint16_t)(s_bstart[b + 1] - s_bstart[b]);
+          s_boff[rk] = (uint16_t)(s_bstart[b + 1] - s0);
           // stash (first idx, last idx) of the block for the verification
-          s_bbase[rk] = ((uint64_t)keyB[s_bstart[b]] << 32) | keyB[s_bstart[b + 1] - 1];
+          s_bbase[rk] = ((uint64_t)kb << 32) | keyB[s_bstart[b + 1] - 1];
         }
         __syncthreads();
         if (tid == 0) {
@@ -706,16 +807,25 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cls, uint32
         use_blocks = s_misc[1] != 0;
       }
       if (use_blocks) {
-        for (uint32_t i = tid; i < n; i += nt) {
-          // block of window slot i (arrival order): last r with bstart[r] <= i
-          uint32_t lo = 0, hi = R;
-          while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_bstart[mid] <= i) lo = mid; else hi = mid; }
-          const uint32_t rk = s_brank[lo];
-          const uint32_t pos = s_boff[rk] + (i - s_bstart[lo]);
+        // sorted position of every slot of this thread's segment
+        uint32_t bi = 0;
+        if (lo < hi) {
+          uint32_t l2 = 0, h2 = R;
+          while (h2 - l2 > 1) { const uint32_t mid = (l2 + h2) >> 1; if (s_bstart[mid] <= (uint32_t)lo) l2 = mid; else h2 = mid; }
+          bi = l2;
+        }
+        for (int i = lo; i < hi; i++) {
+          while (bi + 1 < R && s_bstart[bi + 1] <= (uint32_t)i) bi++;
+          const uint32_t rk = s_brank[bi];
+          const uint32_t pos = s_boff[rk] + ((uint32_t)i - s_bstart[bi]);
           ord[pos] = (uint16_t)i;
           blk[pos] = (uint8_t)rk;
         }
-        __syncthreads();
+        // dense-id base of each sender block (consumed in PE; issued early)
+        for (uint32_t b = tid; b < R; b += nt) {
+          const uint64_t ka = s_bkeyA[b];
+          s_bbase[b] = dense_base(p, st, ka >> 24, (uint32_t)(ka & 0xFFFFFFu));
+        }
       } else {
         int np2 = 1;
         while (np2 < (int)n) np2 <<= 1;
@@ -725,21 +835,15 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cls, uint32
         if (tid == 0 && n > 1) atomicAdd((unsigned long long*)&st->fallback_sorts, 1ull);
       }
     }
-    // dense-id base of each sender block (needed only when records are written; issued early)
-    if (use_blocks) {
-      for (uint32_t b = tid; b < R; b += nt) {
-        const uint64_t ka = s_bkeyA[b];
-        s_bbase[b] = dense_base(p, st, ka >> 24, (uint32_t)(ka & 0xFFFFFFu));
-      }
-    }
-    __syncthreads();   // keyA (reg1) is dead from here on
+    __syncthreads();   // keyA (reg1) and keyB are dead from here on
+    PHASE_MARK(2);
 
     // PC: first sight of a value among this round's copies: smallest sorted position wins
     int npad = 1;
     while (npad < (int)n) npad <<= 1;
     const int tsz = 2 * npad;
-    if (bcast) {
-      for (int i = tid; i < tsz; i += nt) tab[i] = 0xFFFFFFFFu;
+    if (bcast && n > 0) {
+      for (int i = tid; i < tsz; i += nt) tab[i] = 0xFFFF;
       __syncthreads();
       for (int pos = tid; pos < (int)n; pos += nt) {
         const uint32_t val = vals[ord[pos]];
@@ -747,67 +851,68 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cls, uint32
           const uint32_t v = val & V_MASK;
           uint32_t h = hash32(v) & (tsz - 1);
           for (int probe = 0; probe < tsz; probe++) {   // the table is at most half full
-            uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&tab[h]);
-            if (cur == 0xFFFFFFFFu) {
-              const uint32_t old = atomicCAS(&tab[h], 0xFFFFFFFFu, (uint32_t)pos);
-              if (old == 0xFFFFFFFFu) break;
+            uint32_t cur = *reinterpret_cast<volatile uint16_t*>(&tab[h]);
+            if (cur == 0xFFFFu) {
+              const uint32_t old = atomicCAS(&tab[h], (unsigned short)0xFFFF, (unsigned short)pos);
+              if (old == 0xFFFFu) break;
               cur = old;
             }
-            if ((vals[ord[cur]] & V_MASK) == v) { atomicMin(&tab[h], (uint32_t)pos); break; }
+            if ((vals[ord[cur]] & V_MASK) == v) {
+              while ((uint32_t)pos < cur) {              // atomic min on a 16-bit slot
+                const uint32_t old = atomicCAS(&tab[h], (unsigned short)cur, (unsigned short)pos);
+                if (old == cur) break;
+                cur = old;
+              }
+              break;
+            }
             h = (h + 1) & (tsz - 1);
           }
         }
       }
       __syncthreads();
-      for (int pos = tid; pos < (int)n; pos += nt) {
-        const uint32_t i = ord[pos];
-        const uint32_t val = vals[i];
-        if (val & V_FRESH) {
-          const uint32_t v = val & V_MASK;
-          uint32_t h = hash32(v) & (tsz - 1);
-          uint32_t win = tab[h];
-          for (int probe = 0; probe < tsz && win != 0xFFFFFFFFu && (vals[ord[win]] & V_MASK) != v; probe++) {
-            h = (h + 1) & (tsz - 1);   // the entry exists: probing ends on it
-            win = tab[h];
-          }
-          if (win == (uint32_t)pos) atomicOr(p.bitmap + (size_t)e * p.bm_words + (v >> 5), 1u << (v & 31));
-          else vals[i] = val & ~V_FRESH;   // a lower-id copy of v is processed first this round
-        }
-      }
-      __syncthreads();
     }
-    NbrList L;
-    L.nl = nb_smem ? s_nbr : nullptr;
-    L.deg = deg;
-    // packed counts in sorted order: emit (bits 0-31) | recv (32-47) | new (48-63)
+    // resolve winners and publish packed counts in sorted order:
+    //   emit (bits 0-31) | recv (32-47) | new (48-63)
     for (int pos = tid; pos < (int)n; pos += nt) {
       const uint32_t i = ord[pos];
-      const uint32_t val = vals[i];
+      uint32_t val = vals[i];
+      bool is_new = false;
+      if (val & V_FRESH) {
+        const uint32_t v = val & V_MASK;
+        uint32_t h = hash32(v) & (tsz - 1);
+        uint32_t win = tab[h];
+        for (int probe = 0; probe < tsz && win != 0xFFFFu && (vals[ord[win]] & V_MASK) != v; probe++) {
+          h = (h + 1) & (tsz - 1);   // the entry exists: probing ends on it
+          win = tab[h];
+        }
+        if (win == (uint32_t)pos) {
+          is_new = true;
+          atomicOr(p.bitmap + (size_t)e * p.bm_words + (v >> 5), 1u << (v & 31));
+        } else {
+          vals[i] = val & ~V_FRESH;   // a lower-id copy of v is processed first this round
+        }
+      }
       uint64_t c = 0;
       if (val & V_RECV) {
         c = 1ull << 32;
-        const bool is_new = (val & V_FRESH) != 0;
-        if (is_server) {
-          const MsgView w = view_load(myring + (size_t)((head + i) & p.ring_mask) * 3);
-          c |= node_emit_count(p, e, w, is_new, L);
-        }
+        if (is_server) c |= emit_count_meta(p.workload, meta[i], is_new, deg);
         if (is_new) c |= 1ull << 48;
       }
       aux[pos] = c;
     }
     __syncthreads();
+    PHASE_MARK(3);
     const uint64_t tot = block_excl_scan(aux, (int)n, s_wtmp);
     const uint32_t n_emit = (uint32_t)tot;
     const uint32_t n_recv = (uint32_t)(tot >> 32) & 0xFFFFu;
     const uint32_t n_new = (uint32_t)(tot >> 48);
     n_ev_local = n_recv + n_emit; n_em_local = n_emit;
+    PHASE_MARK(4);
 
     // PD: claims: journal chunk, mailbox, per-neighbor ring blocks
     const bool mailed = (kind == MS_KIND_CLIENT || kind == MS_KIND_HOST);
-    const bool agg = use_blocks && nb_smem && n_new > 0 &&
-                     np.loss_thresh == 0 && np.dist == MS_DIST_CONSTANT && (uint64_t)np.mean_ms * np.scale == 0 &&
-                     s_misc[3] == 0;
-    if (tid == 0) {
+    const bool agg = use_blocks && nb_smem && n_new > 0 && !need_rng && const_lat == 0 && s_misc[3] == 0;
+    if (tid == 32 % nt) {
       s_chunk = (n_ev_local && p.jlevel)
                     ? atomicAdd((unsigned long long*)&st->jraw_cursor, (unsigned long long)n_ev_local) : 0ull;
       if (n_ev_local && p.jlevel && !p.jdiscard && s_chunk + n_ev_local - st->jraw_drained > p.jmask + 1)
@@ -841,6 +946,10 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cls, uint32
     const bool cl_ep = kind_is_client(kind);
     const uint32_t msg_id_base = (is_server && p.next_msg_id) ? p.next_msg_id[e] : 0;
     const uint32_t set_before = (is_server && p.set_count) ? p.set_count[e] : 0;
+    NbrList L;
+    L.nl = nb_smem ? s_nbr : nullptr;
+    L.deg = deg;
+    PHASE_MARK(5);
 
     // PE: :recv records (net.clj:244) and the emissions of each message, in id order
     for (uint32_t base = 0; base < n; base += nt) {
@@ -868,7 +977,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cls, uint32
           p1 = m.p1;
           const uint64_t id = (use_blocks ? s_bbase[rho] : dense_base(p, st, m.round, m.ticket)) + m.idx;
           journal_raw(p, cx.chunk + k, id, true, m);
-          const bool cl = cl_ep || kind_is_client(p.kind[w.src]);
+          const bool cl = cl_ep || (w.src >= p.n_servers && kind_is_client(p.kind[w.src]));
           if (cl) c_recv_cl++; else c_recv_sv++;
           if (kind == MS_KIND_SIM_CLIENT && ((w.tf >> 16) & MS_F_REPLY)) c_replies++;
           if (mailed) {
@@ -912,34 +1021,36 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cls, uint32
     }
   }
 
-  // ------------------------------------------------------------ CTA epilogue
-  uint32_t cnt[8] = {cx.c_send_cl, cx.c_send_sv, c_recv_cl, c_recv_sv, cx.c_lost, cx.c_zero, c_part, c_replies};
+  PHASE_MARK(6);
+  // ------------------------------------------------------------ ticket epilogue
+  {
+    uint32_t cnt[8] = {cx.c_send_cl, cx.c_send_sv, c_recv_cl, c_recv_sv, cx.c_lost, cx.c_zero, c_part, c_replies};
 #pragma unroll
-  for (int q = 0; q < 8; q++) {
+    for (int q = 0; q < 8; q++) {
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) cnt[q] += __shfl_xor_sync(FULL, cnt[q], d);
+      for (int d = 16; d > 0; d >>= 1) cnt[q] += __shfl_xor_sync(FULL, cnt[q], d);
+      if (lane == 0 && cnt[q]) atomicAdd(&s_cnt[q], cnt[q]);
+    }
   }
-  if (lane == 0) {
-    if (cnt[0]) { atomicAdd((unsigned long long*)&st->stats[0], (unsigned long long)cnt[0]);
-                  atomicAdd((unsigned long long*)&st->stats[2], (unsigned long long)cnt[0]); }
-    if (cnt[1]) { atomicAdd((unsigned long long*)&st->stats[0], (unsigned long long)cnt[1]);
-                  atomicAdd((unsigned long long*)&st->stats[4], (unsigned long long)cnt[1]); }
-    if (cnt[2]) { atomicAdd((unsigned long long*)&st->stats[1], (unsigned long long)cnt[2]);
-                  atomicAdd((unsigned long long*)&st->stats[3], (unsigned long long)cnt[2]); }
-    if (cnt[3]) { atomicAdd((unsigned long long*)&st->stats[1], (unsigned long long)cnt[3]);
-                  atomicAdd((unsigned long long*)&st->stats[5], (unsigned long long)cnt[3]); }
-    if (cnt[4]) atomicAdd((unsigned long long*)&st->lost, (unsigned long long)cnt[4]);
-    if (cnt[6]) atomicAdd((unsigned long long*)&st->part_drops, (unsigned long long)cnt[6]);
-    if (cnt[7]) atomicAdd((unsigned long long*)&st->client_replies, (unsigned long long)cnt[7]);
+  __syncthreads();
+  if (tid < 8 && s_cnt[tid]) {
+    // stats[2..5] = {clients send, clients recv, servers send, servers recv}; "all" is summed on the host
+    const uint32_t v = s_cnt[tid];
+    if (tid == 0) atomicAdd((unsigned long long*)&st->stats[2], (unsigned long long)v);
+    else if (tid == 1) atomicAdd((unsigned long long*)&st->stats[4], (unsigned long long)v);
+    else if (tid == 2) atomicAdd((unsigned long long*)&st->stats[3], (unsigned long long)v);
+    else if (tid == 3) atomicAdd((unsigned long long*)&st->stats[5], (unsigned long long)v);
+    else if (tid == 4) atomicAdd((unsigned long long*)&st->lost, (unsigned long long)v);
+    else if (tid == 6) atomicAdd((unsigned long long*)&st->part_drops, (unsigned long long)v);
+    else if (tid == 7) atomicAdd((unsigned long long*)&st->client_replies, (unsigned long long)v);
   }
-  const int any_zero = __syncthreads_or(cx.c_zero != 0);
   if (tid == 0) {
     // this ticket's table entry, validated by the round tag so that no fence is needed:
     // tag(16) | zero-latency pending(1) | events(23) | emissions(24); the last CTA turns
     // the counts into prefixes
     if (n_ev_local >= (1u << 23) || n_em_local >= (1u << 24)) latch_error(st, E_ID_RANGE, ticket);
     p.rt_chunk[(size_t)row * p.t_max + ticket] = cx.chunk;
-    const uint64_t entry = ((uint64_t)tag << 48) | (any_zero ? (1ull << 47) : 0ull) |
+    const uint64_t entry = ((uint64_t)tag << 48) | (s_cnt[5] ? (1ull << 47) : 0ull) |
                            ((uint64_t)(n_ev_local & 0x7FFFFFu) << 24) | (uint64_t)(n_em_local & 0xFFFFFFu);
     __stcg(reinterpret_cast<unsigned long long*>(p.rt_cnt + (size_t)row * p.t_max + ticket),
            (unsigned long long)entry);
@@ -947,27 +1058,40 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cls, uint32
     s_misc[5] = next_li;
   }
   __syncthreads();
+  PHASE_MARK(7);
   if (s_misc[4]) {
     // ---------------------------------------------------------- last CTA: commit the round
     const uint64_t* cntp = p.rt_cnt + (size_t)row * p.t_max;
     uint32_t* em = p.rt_em + (size_t)row * p.t_max;
     uint32_t* ev = p.rt_ev + (size_t)row * p.t_max;
+    // pass 1 (strided, loads batched 4 deep): validate the tags, unpack the counts
+    uint32_t zp_any = 0;
+    for (int base = 0; base < (int)T; base += 4 * nt) {
+      uint64_t v[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int i = base + q * nt + tid;
+        v[q] = i < (int)T ? __ldcg(reinterpret_cast<const unsigned long long*>(cntp + i)) : ((uint64_t)tag << 48);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int i = base + q * nt + tid;
+        if (i >= (int)T) continue;
+        // every ticket has bumped `done`, so its entry store is in flight at worst: wait for the tag
+        for (uint32_t spin = 0; (uint32_t)(v[q] >> 48) != tag && spin < (1u << 22); spin++)
+          v[q] = __ldcg(reinterpret_cast<const unsigned long long*>(cntp + i));
+        if ((uint32_t)(v[q] >> 48) != tag) latch_error(st, E_HISTORY, (uint32_t)i);
+        zp_any |= (uint32_t)(v[q] >> 47) & 1u;
+        ev[i] = (uint32_t)(v[q] >> 24) & 0x7FFFFFu;
+        em[i] = (uint32_t)v[q] & 0xFFFFFFu;
+      }
+    }
+    zp_any = __syncthreads_or(zp_any);   // also makes ev[]/em[] visible to the whole CTA
+    // pass 2 (one contiguous chunk per thread): exclusive prefix
     const int c = ((int)T + nt - 1) / nt;
     const int lo = min(tid * c, (int)T), hi = min(lo + c, (int)T);
     uint64_t sum = 0;   // ev << 32 | em  (per-round totals stay below 2^32)
-    uint32_t zp_any = 0;
-    for (int i = lo; i < hi; i++) {
-      // every ticket has bumped `done`, so its entry store is in flight at worst: wait for the tag
-      uint64_t v = __ldcg(reinterpret_cast<const unsigned long long*>(cntp + i));
-      for (uint32_t spin = 0; (uint32_t)(v >> 48) != tag && spin < (1u << 24); spin++)
-        v = __ldcg(reinterpret_cast<const unsigned long long*>(cntp + i));
-      if ((uint32_t)(v >> 48) != tag) latch_error(st, E_HISTORY, (uint32_t)i);
-      zp_any |= (uint32_t)(v >> 47) & 1u;
-      const uint32_t ve = (uint32_t)(v >> 24) & 0x7FFFFFu, vm = (uint32_t)v & 0xFFFFFFu;
-      ev[i] = ve; em[i] = vm;   // raw counts; turned into prefixes below (same thread)
-      sum += ((uint64_t)ve << 32) | vm;
-    }
-    zp_any = __syncthreads_or(zp_any);
+    for (int i = lo; i < hi; i++) sum += ((uint64_t)ev[i] << 32) | em[i];
     uint64_t incl = sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -991,7 +1115,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cls, uint32
     __syncthreads();
     uint64_t run = s_wtmp[warp] + incl - sum;
     for (int i = lo; i < hi; i++) {
-      const uint32_t ve = ev[i], vm = em[i];   // written by this thread above
+      const uint32_t ve = ev[i], vm = em[i];   // written in pass 1, visible after the barrier
       ev[i] = (uint32_t)(run >> 32);
       em[i] = (uint32_t)run;
       run += ((uint64_t)ve << 32) | vm;
@@ -1041,8 +1165,10 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cls, uint32
       nx->em_total = 0;
       __threadfence();
     }
+    PHASE_MARK(8);
   }
  }   // persistent loop
+#undef PHASE_MARK
 }
 
 // ------------------------------------------------------------------ k_journal_expand (K3)
@@ -1102,7 +1228,7 @@ cudaError_t msk_round_smem_attr(size_t bytes) {
   return cudaFuncSetAttribute(msd::k_round, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-size_t msk_round_smem_bytes(uint32_t cap) { return (size_t)cap * 19 + 32; }
+size_t msk_round_smem_bytes(uint32_t cap) { return (size_t)cap * 21 + 32; }
 
 void msk_set_bit(uint32_t* words, size_t word, uint32_t bit, cudaStream_t s) {
   msd::k_set_bit<<<1, 1, 0, s>>>(words, word, bit);

@@ -215,6 +215,11 @@ class Sim:
         self._chk(self.L.ms_profile_read(self.h, C.byref(ms), C.byref(n)))
         return ms.value, int(n.value)
 
+    def phase_cycles(self, enable=True):
+        out = np.zeros(64, dtype=np.uint64)
+        self._chk(self.L.ms_debug_phase_cycles(self.h, 1 if enable else 0, out.ctypes.data))
+        return out.reshape(4, 16)
+
     def drain_into(self, ev_ptr, cap, body_ptr=None):
         """Drain up to `cap` events into caller memory (e.g. pinned); returns count."""
         n = C.c_size_t(0)
