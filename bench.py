@@ -263,13 +263,18 @@ def gpu_arm(args, rank, world, local_rank):
         for _ in range(K):
             tick += 1
             run_until_tick(sim, tick)
-        pc = sim.phase_cycles(True)
+        import ctypes as _C
+        _o = np.zeros(64, dtype=np.uint64)
+        sim.L.ms_debug_phase_cycles(sim.h, 2, _o.ctypes.data)
+        pc = _o.reshape(4, 16)
         names = ["fetch", "load", "order", "dedupe", "count+scan", "claims", "emit", "epilogue", "commit"]
         for c in range(4):
             nt_ = int(pc[c][15])
             if nt_:
                 sys.stderr.write("class %d: %d tickets; cycles/ticket: %s\n" % (
                     c, nt_, ", ".join("%s=%d" % (nm, int(pc[c][k]) // nt_) for k, nm in enumerate(names))))
+                sys.stderr.write("   fallback R>64: %d, verify-fail: %d, agg tickets: %d, non-agg gossip tickets: %d, blocks total: %d\n"
+                                 % tuple(int(pc[c][k]) for k in (9, 10, 11, 12, 13)))
     # roofline pass: same work again (next K ticks) with CUDA events around every round-kernel launch
     sim.profile(True)
     sim.profile_read()

@@ -887,7 +887,7 @@ int ms_debug_phase_cycles(ms_sim* s, int enable, uint64_t out[64]) {
   std::lock_guard<std::mutex> g(s->mu);
   cudaSetDevice(s->device);
   if (enable && !s->P.phase_cycles) {
-    int rc = s->dalloc(&s->P.phase_cycles, 64);
+    int rc = s->dalloc(&s->P.phase_cycles, 512);
     if (rc) return rc;
     CK(cudaStreamSynchronize(s->stream));
   }
@@ -895,7 +895,19 @@ int ms_debug_phase_cycles(ms_sim* s, int enable, uint64_t out[64]) {
     if (s->P.phase_cycles) CK(cudaMemcpy(out, s->P.phase_cycles, 64 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     else memset(out, 0, 64 * sizeof(uint64_t));
   }
-  if (s->P.phase_cycles) CK(cudaMemset(s->P.phase_cycles, 0, 64 * sizeof(uint64_t)));
+  if (s->P.phase_cycles && enable >= 0) CK(cudaMemset(s->P.phase_cycles, 0, 64 * sizeof(uint64_t)));
+  if (enable == 2 && out) {   // diagnostic: first overlapping-block window, written to stderr
+    std::vector<uint64_t> d(448);
+    CK(cudaMemcpy(d.data(), s->P.phase_cycles + 64, 448 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (d[0]) {
+      fprintf(stderr, "overlap window: e=%llu n=%llu R=%llu round=%llu\n", (unsigned long long)d[1], (unsigned long long)d[2],
+              (unsigned long long)d[3], (unsigned long long)d[4]);
+      for (uint64_t q = 0; q < d[3] && q < 64; q++)
+        fprintf(stderr, "  block %llu: round=%llu ticket=%llu first_idx=%llu last_idx=%llu\n", (unsigned long long)q,
+                (unsigned long long)(d[5 + 2 * q] >> 24), (unsigned long long)(d[5 + 2 * q] & 0xFFFFFF),
+                (unsigned long long)(d[6 + 2 * q] >> 32), (unsigned long long)(d[6 + 2 * q] & 0xFFFFFFFFu));
+    }
+  }
   return MS_OK;
 }
 

@@ -473,10 +473,11 @@ __device__ __forceinline__ int node_emit(const Params& p, uint32_t e, const MsgV
 // ------------------------------------------------------------------ k_round
 // Persistent CTAs; one ticket at a time: tickets [0, n_inj_tickets) are injector
 // slices, ticket n_inj_tickets + e is endpoint e.  Dynamic shared memory, `cap` =
-// window capacity of this size class (21 B / message):
+// window capacity of this size class (25 B / message):
 //   reg1 u64[cap+1]  order keys (round << 24 | ticket)  ->  packed count scan
-//   keyB u32[cap]    emission index of the key           ->  first-sight table (u16[2*npad])
-//   vals u32[cap]    value | V_* flags        meta u16[cap]  compact message class
+//   keyB u32[cap]    emission index of the key
+//   vals u32[cap]    value | V_* flags        tab u16[2*cap]  first-sight table
+//   meta u16[cap]    compact message class
 //   ord  u16[cap]    sorted position -> window slot      blk u8[cap]  sorted position -> sender block
 constexpr uint32_t M_SRCSLOT = 0xFu;      // meta bits 0-3: neighbor slot of src + 1, 15 = neighbor (slot unknown), 0 = none
 constexpr uint32_t M_HAS_ID = 1u << 4;
@@ -517,7 +518,31 @@ __device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t* to
   return before + incl - v;
 }
 
-__global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cls, uint32_t cap) {
+// same for one u64 per thread (packed 4 x 16-bit counters)
+__device__ __forceinline__ uint64_t block_excl_scan_u64v(uint64_t v, uint64_t* total, uint64_t* wtmp /* >= 17 */) {
+  const int nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint64_t incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint64_t y = __shfl_up_sync(FULL, incl, d);
+    if (lane >= d) incl += y;
+  }
+  if (lane == 31) wtmp[warp] = incl;
+  __syncthreads();
+  uint64_t before = 0, tot = 0;
+  for (int w = 0; w < (nt >> 5); w++) {
+    const uint64_t cw = wtmp[w];
+    if (w < warp) before += cw;
+    tot += cw;
+  }
+  __syncthreads();
+  *total = tot;
+  return before + incl - v;
+}
+
+template <int CLS>
+__global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
+  constexpr uint32_t cls = CLS;
   DevState* st = p.st;
   if (round_skipped(p, st) || !st->slot_open) return;
 
@@ -525,12 +550,12 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cls, uint32
   uint64_t* reg1 = reinterpret_cast<uint64_t*>(smem_raw);          // cap+1 entries
   uint32_t* keyB = reinterpret_cast<uint32_t*>(reg1 + cap + 1);
   uint32_t* vals = keyB + cap;
-  uint16_t* meta = reinterpret_cast<uint16_t*>(vals + cap);
+  uint16_t* tab = reinterpret_cast<uint16_t*>(vals + cap);         // first-sight table, 2*cap entries
+  uint16_t* meta = tab + 2 * (size_t)cap;
   uint16_t* ord = meta + cap;
   uint8_t* blk = reinterpret_cast<uint8_t*>(ord + cap);
   uint64_t* keyA = reg1;
   uint64_t* aux = reg1;                                            // packed counts (keyA is dead by then)
-  uint16_t* tab = reinterpret_cast<uint16_t*>(keyB);               // first-sight table (keyB is dead by then)
 
   __shared__ uint64_t s_wtmp[34];
   __shared__ NetParams s_np;
@@ -802,6 +827,12 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cls, uint32
           }
           s_boff[R] = (uint16_t)acc;
           s_misc[1] = ok ? 1u : 0u;
+          if (!ok && timing && atomicCAS((unsigned long long*)&p.phase_cycles[64], 0ull, 1ull) == 0ull) {
+            // diagnostic dump of the first window whose blocks overlap
+            unsigned long long* d = (unsigned long long*)p.phase_cycles + 65;
+            d[0] = e; d[1] = n; d[2] = R; d[3] = round;
+            for (uint32_t q = 0; q < R; q++) { d[4 + 2 * q] = s_bkeyA[q]; d[5 + 2 * q] = s_bbase[q]; }
+          }
         }
         __syncthreads();
         use_blocks = s_misc[1] != 0;
@@ -833,9 +864,10 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cls, uint32
         __syncthreads();
         if (n > 1) block_bitonic_sort_idx(ord, keyA, keyB, np2);
         if (tid == 0 && n > 1) atomicAdd((unsigned long long*)&st->fallback_sorts, 1ull);
+        if (timing && tid == 0 && n > 1) atomicAdd((unsigned long long*)&p.phase_cycles[cls * 16 + (R > MAXB ? 9 : 10)], 1ull);
       }
     }
-    __syncthreads();   // keyA (reg1) and keyB are dead from here on
+    __syncthreads();   // keyA (reg1) is dead from here on
     PHASE_MARK(2);
 
     // PC: first sight of a value among this round's copies: smallest sorted position wins
@@ -911,7 +943,35 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cls, uint32
 
     // PD: claims: journal chunk, mailbox, per-neighbor ring blocks
     const bool mailed = (kind == MS_KIND_CLIENT || kind == MS_KIND_HOST);
-    const bool agg = use_blocks && nb_smem && n_new > 0 && !need_rng && const_lat == 0 && s_misc[3] == 0;
+    // per-(CTA, neighbor) ring claims need the rank of every gossip emission among this CTA's
+    // emissions to that neighbor: mode 1 derives it from the sender blocks of the window
+    // (table S), mode 2 (window was sorted the slow way) from a packed scan (deg <= 4)
+    const bool agg_ok = nb_smem && n_new > 0 && !need_rng && const_lat == 0 && s_misc[3] == 0;
+    const int agg_mode = !agg_ok ? 0 : (use_blocks ? 1 : (deg <= 4 ? 2 : 0));
+    const bool agg = agg_mode != 0;
+    uint32_t* F01 = keyB;                                   // mode 2: new-from-neighbor 0/1 before pos (2 x u16)
+    uint32_t* F23 = reinterpret_cast<uint32_t*>(tab);       //         new-from-neighbor 2/3 before pos
+    uint64_t f_total = 0;
+    if (agg_mode == 2) {
+      const int c = ((int)n + nt - 1) / nt;
+      const int lo = min(tid * c, (int)n), hi = min(lo + c, (int)n);
+      uint64_t acc = 0;
+      for (int pos = lo; pos < hi; pos++) {
+        const uint32_t i = ord[pos];
+        const uint32_t ss = meta[i] & M_SRCSLOT;
+        if ((vals[i] & V_FRESH) && ss >= 1 && ss <= 4) acc += 1ull << (16 * (ss - 1));
+      }
+      uint64_t run = block_excl_scan_u64v(acc, &f_total, s_wtmp);
+      for (int pos = lo; pos < hi; pos++) {
+        const uint32_t i = ord[pos];
+        const uint32_t ss = meta[i] & M_SRCSLOT;
+        F01[pos] = (uint32_t)run;
+        F23[pos] = (uint32_t)(run >> 32);
+        if ((vals[i] & V_FRESH) && ss >= 1 && ss <= 4) run += 1ull << (16 * (ss - 1));
+      }
+    }
+    if (timing && tid == 0 && bcast && n_new > 0) atomicAdd((unsigned long long*)&p.phase_cycles[cls * 16 + (agg ? 11 : 12)], 1ull);
+    if (timing && tid == 0 && n > 1) atomicAdd((unsigned long long*)&p.phase_cycles[cls * 16 + 13], (unsigned long long)R);
     if (tid == 32 % nt) {
       s_chunk = (n_ev_local && p.jlevel)
                     ? atomicAdd((unsigned long long*)&st->jraw_cursor, (unsigned long long)n_ev_local) : 0ull;
@@ -920,17 +980,21 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cls, uint32
       if (mailed && n_recv) s_misc[0] = atomicAdd(&st->mail_count, n_recv);
     }
     if (agg && tid < (int)deg) {   // deg <= MAXNB <= 32 <= blockDim
-      // S[rho][j]: new messages, in blocks before rho, that came from neighbor j (they do not go back to j)
       const uint32_t nb = s_nbr[tid];
       uint32_t acc = 0;
-      for (uint32_t q = 0; q < R; q++) {
-        s_S[q][tid] = (uint16_t)acc;
-        const uint64_t ka = s_bkeyA[q];
-        const uint32_t tk = (uint32_t)(ka & 0xFFFFFFu);
-        if (tk >= p.n_inj_tickets && tk - p.n_inj_tickets == nb)
-          acc += (uint32_t)(aux[s_boff[q + 1]] >> 48) - (uint32_t)(aux[s_boff[q]] >> 48);
+      if (agg_mode == 1) {
+        // S[rho][j]: new messages, in blocks before rho, that came from neighbor j (they do not go back to j)
+        for (uint32_t q = 0; q < R; q++) {
+          s_S[q][tid] = (uint16_t)acc;
+          const uint64_t ka = s_bkeyA[q];
+          const uint32_t tk = (uint32_t)(ka & 0xFFFFFFu);
+          if (tk >= p.n_inj_tickets && tk - p.n_inj_tickets == nb)
+            acc += (uint32_t)(aux[s_boff[q + 1]] >> 48) - (uint32_t)(aux[s_boff[q]] >> 48);
+        }
+        s_S[R][tid] = (uint16_t)acc;
+      } else {
+        acc = (uint32_t)(f_total >> (16 * tid)) & 0xFFFFu;
       }
-      s_S[R][tid] = (uint16_t)acc;
       const uint32_t total = n_new - acc;
       uint32_t base = 0;
       if (total) {
@@ -951,68 +1015,91 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cls, uint32
     L.deg = deg;
     PHASE_MARK(5);
 
-    // PE: :recv records (net.clj:244) and the emissions of each message, in id order
-    for (uint32_t base = 0; base < n; base += nt) {
-      const uint32_t pos = base + tid;
-      const bool live = pos < n;
-      uint32_t my_emit = 0, e_idx0 = 0, new_before = 0, rho = 0;
-      MsgView w;
-      w.src = 0; w.msg_id = 0; w.p0 = 0; w.tf = 0;
-      uint64_t p1 = 0;
-      bool is_new = false;
-      if (live) {
-        const uint32_t i = ord[pos];
-        const uint64_t a0 = aux[pos], a1 = aux[pos + 1];
-        e_idx0 = (uint32_t)a0;
-        my_emit = (uint32_t)a1 - (uint32_t)a0;
-        new_before = (uint32_t)(a0 >> 48);
-        const uint32_t val = vals[i];
-        is_new = (val & V_FRESH) != 0;
-        if (use_blocks) rho = blk[pos];
-        if (val & V_RECV) {
-          const uint32_t k = (uint32_t)(a0 >> 32) & 0xFFFFu;
-          const uint4* rp = myring + (size_t)((head + i) & p.ring_mask) * 3;
-          Rec m = rec_unpack(rp[0], rp[1], rp[2]);
-          w.src = m.src; w.msg_id = m.msg_id; w.p0 = m.p0; w.tf = m.tf;
-          p1 = m.p1;
-          const uint64_t id = (use_blocks ? s_bbase[rho] : dense_base(p, st, m.round, m.ticket)) + m.idx;
-          journal_raw(p, cx.chunk + k, id, true, m);
-          const bool cl = cl_ep || (w.src >= p.n_servers && kind_is_client(p.kind[w.src]));
-          if (cl) c_recv_cl++; else c_recv_sv++;
-          if (kind == MS_KIND_SIM_CLIENT && ((w.tf >> 16) & MS_F_REPLY)) c_replies++;
-          if (mailed) {
-            const uint32_t mpos = s_misc[0] + k;
-            if (mpos >= p.mail_cap) {
-              latch_error(st, E_MAIL_OVERFLOW, e);
-            } else {
-              uint4* dst = reinterpret_cast<uint4*>(p.mail) + (size_t)mpos * 3;   // public ms_msg layout
-              st_v4(dst + 0, make_uint4((uint32_t)id, (uint32_t)(id >> 32), (uint32_t)now, (uint32_t)((uint64_t)now >> 32)));
-              st_v4(dst + 1, make_uint4(m.src, m.dest, m.msg_id, m.in_reply_to));
-              st_v4(dst + 2, make_uint4(m.tf, m.p0, (uint32_t)m.p1, (uint32_t)(m.p1 >> 32)));
-            }
+    // PE1: :recv records (net.clj:244), one message per thread.  With journal level 1 and a
+    //      neighbor as the source everything needed is already in shared memory.
+    const bool full_recv = p.jlevel >= 2 || mailed || !use_blocks;
+    for (uint32_t pos = tid; pos < n; pos += nt) {
+      const uint32_t i = ord[pos];
+      const uint32_t val = vals[i];
+      if (!(val & V_RECV)) { c_part++; continue; }
+      const uint32_t k = (uint32_t)(aux[pos] >> 32) & 0xFFFFu;
+      const uint32_t mt = meta[i];
+      const uint32_t sslot = mt & M_SRCSLOT;
+      if (full_recv || !nb_smem || sslot == 0) {
+        const uint4* rp = myring + (size_t)((head + i) & p.ring_mask) * 3;
+        Rec m = rec_unpack(rp[0], rp[1], rp[2]);
+        const uint64_t id = (use_blocks ? s_bbase[blk[pos]] : dense_base(p, st, m.round, m.ticket)) + m.idx;
+        journal_raw(p, cx.chunk + k, id, true, m);
+        const bool cl = cl_ep || (m.src >= p.n_servers && kind_is_client(p.kind[m.src]));
+        if (cl) c_recv_cl++; else c_recv_sv++;
+        if (kind == MS_KIND_SIM_CLIENT && ((m.tf >> 16) & MS_F_REPLY)) c_replies++;
+        if (mailed) {
+          const uint32_t mpos = s_misc[0] + k;
+          if (mpos >= p.mail_cap) {
+            latch_error(st, E_MAIL_OVERFLOW, e);
+          } else {
+            uint4* dst = reinterpret_cast<uint4*>(p.mail) + (size_t)mpos * 3;   // public ms_msg layout
+            st_v4(dst + 0, make_uint4((uint32_t)id, (uint32_t)(id >> 32), (uint32_t)now, (uint32_t)((uint64_t)now >> 32)));
+            st_v4(dst + 1, make_uint4(m.src, m.dest, m.msg_id, m.in_reply_to));
+            st_v4(dst + 2, make_uint4(m.tf, m.p0, (uint32_t)m.p1, (uint32_t)(m.p1 >> 32)));
           }
-        } else {
-          c_part++;
         }
+      } else {
+        // server -> server gossip from topology neighbor sslot-1 (journal level 1)
+        const uint64_t id = s_bbase[blk[pos]] + keyB[i];
+        const uint64_t vrec = id | RECV_BIT;
+        if (p.jlevel)
+          st_v4(p.jraw + ((cx.chunk + k) & p.jmask),
+                make_uint4((uint32_t)vrec, (uint32_t)(vrec >> 32), s_nbr[sslot - 1], e));
+        c_recv_sv++;
       }
-      uint32_t maxk = my_emit;
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) maxk = max(maxk, __shfl_xor_sync(FULL, maxk, d));
-      for (uint32_t k = 0; k < maxk; k++) {
-        const bool valid = k < my_emit;
-        Rec r;
-        r.dest = 0; r.src = e;
-        uint32_t direct = 0;
-        bool has_direct = false;
-        if (valid) {
-          const int slot = node_emit(p, e, w, k, my_emit, e_idx0 + k, msg_id_base, set_before, new_before, p1, r, L);
-          if (agg && slot >= 0 && is_new) {
-            direct = s_nbbase[slot] + new_before - s_S[rho][slot];
+    }
+    // PE2: emissions in id order, one emission per thread: emission j belongs to the last
+    //      sorted position whose exclusive emit prefix is <= j
+    for (uint32_t base = 0; base < n_emit; base += nt) {
+      const uint32_t j = base + tid;
+      const bool valid = j < n_emit;
+      Rec r;
+      r.dest = 0; r.src = e;
+      uint32_t direct = 0;
+      bool has_direct = false;
+      if (valid) {
+        uint32_t lo = 0, hi = n;
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if ((uint32_t)aux[mid] <= j) lo = mid; else hi = mid; }
+        const uint32_t pos = lo;
+        const uint64_t a0 = aux[pos];
+        const uint32_t k = j - (uint32_t)a0;
+        const uint32_t my_emit = (uint32_t)aux[pos + 1] - (uint32_t)a0;
+        const uint32_t new_before = (uint32_t)(a0 >> 48);
+        const uint32_t i = ord[pos];
+        const uint32_t val = vals[i];
+        const uint32_t mt = meta[i];
+        const bool gossip = bcast && ((mt >> M_TC_SHIFT) & 7u) == TC_BROADCAST && !(mt & M_REPLY) &&
+                            !((mt & M_HAS_ID) && k == my_emit - 1);
+        if (gossip && nb_smem) {
+          // k-th neighbor other than the sender, in topology order (02-performance.md:61-67)
+          const uint32_t ss = mt & M_SRCSLOT;
+          const uint32_t js = (ss && k >= ss - 1) ? k + 1 : k;
+          r.dest = s_nbr[js];
+          r.msg_id = 0; r.in_reply_to = 0; r.tf = MS_T_BROADCAST; r.p0 = val & V_MASK; r.p1 = 0;
+          if (agg_mode == 1) {
+            direct = s_nbbase[js] + new_before - s_S[blk[pos]][js];
+            has_direct = true;
+          } else if (agg_mode == 2) {
+            const uint32_t f = js < 2 ? (F01[pos] >> (16 * js)) : (F23[pos] >> (16 * (js - 2)));
+            direct = s_nbbase[js] + new_before - (f & 0xFFFFu);
             has_direct = true;
           }
+        } else {
+          const uint4* rp = myring + (size_t)((head + i) & p.ring_mask) * 3;
+          const uint4 vb = rp[1], vc = rp[2];
+          MsgView w;
+          w.src = vb.x; w.msg_id = vb.z; w.tf = vc.x; w.p0 = vc.y;
+          const uint64_t p1 = (uint64_t)vc.z | ((uint64_t)vc.w << 32);
+          (void)node_emit(p, e, w, k, my_emit, j, msg_id_base, set_before, new_before, p1, r, L);
         }
-        emit_one(p, st, np, cx, valid, r, e_idx0 + k, direct, has_direct);
       }
+      emit_one(p, st, np, cx, valid, r, j, direct, has_direct);
     }
     if (tid == 0 && is_server) {
       if (p.workload == MS_W_ECHO && p.next_msg_id && n_emit) p.next_msg_id[e] = msg_id_base + n_emit;
@@ -1225,10 +1312,14 @@ __global__ void k_journal_expand(Params p, uint64_t r0, uint32_t n_rounds, uint6
 extern "C" {
 
 cudaError_t msk_round_smem_attr(size_t bytes) {
-  return cudaFuncSetAttribute(msd::k_round, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  cudaError_t e = cudaFuncSetAttribute(msd::k_round<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(msd::k_round<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(msd::k_round<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(msd::k_round<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  return e;
 }
 
-size_t msk_round_smem_bytes(uint32_t cap) { return (size_t)cap * 21 + 32; }
+size_t msk_round_smem_bytes(uint32_t cap) { return (size_t)cap * 25 + 32; }
 
 void msk_set_bit(uint32_t* words, size_t word, uint32_t bit, cudaStream_t s) {
   msd::k_set_bit<<<1, 1, 0, s>>>(words, word, bit);
@@ -1236,7 +1327,7 @@ void msk_set_bit(uint32_t* words, size_t word, uint32_t bit, cudaStream_t s) {
 
 int msk_round_occupancy(int threads, size_t smem) {
   int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msd::k_round, threads, smem) != cudaSuccess) return 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msd::k_round<0>, threads, smem) != cudaSuccess) return 1;
   return nb < 1 ? 1 : nb;
 }
 
@@ -1254,7 +1345,11 @@ void msk_launch_round(const msd::Params* p, int n_classes, const uint32_t* caps,
   msd::k_snapshot<<<sg, sb, 0, s>>>(*p);
   if (before_round) cudaEventRecord(before_round, s);
   for (int c = n_classes - 1; c >= 0; c--) {   // big windows first
-    msd::k_round<<<grids[c], threads[c], msk_round_smem_bytes(caps[c]), s>>>(*p, (uint32_t)c, caps[c]);
+    const size_t sm = msk_round_smem_bytes(caps[c]);
+    if (c == 0) msd::k_round<0><<<grids[c], threads[c], sm, s>>>(*p, caps[c]);
+    else if (c == 1) msd::k_round<1><<<grids[c], threads[c], sm, s>>>(*p, caps[c]);
+    else if (c == 2) msd::k_round<2><<<grids[c], threads[c], sm, s>>>(*p, caps[c]);
+    else msd::k_round<3><<<grids[c], threads[c], sm, s>>>(*p, caps[c]);
   }
   if (after_round) cudaEventRecord(after_round, s);
 }

@@ -209,3 +209,23 @@ def test_sim_clients_and_block_path_counters():
     assert_same_journal(g, o)
     c = g.counters()
     assert c["fallback_sorts"] * 20 < c["rounds"] * (n + 4)   # bitonic fallback is the exception
+
+
+@pytest.mark.parametrize("per_tick,max_window", [(1500, 2048), (3500, 4096)])
+def test_large_windows_all_size_classes(per_tick, max_window):
+    # windows of several thousand messages per node: exercises the 256- and 512-thread size
+    # classes, multi-iteration emit loops and per-neighbor block claims with big counts
+    n = 16
+    g, o = make_pair(n, topology="grid", n_values=2 * per_tick + 8, ring_cap=4 * max_window,
+                     max_window=max_window, journal_cap_log2=22, max_endpoints=n + 8)
+
+    def scenario(s, body):
+        cs = [s.add_endpoint("c%d" % i) for i in range(4)]
+        ops, nv = random_broadcast_ops(n, cs, n_ticks=2, per_tick=per_tick, seed=31)
+        s.schedule(ops)
+        s.run(3_000_000)
+
+    both(g, o, scenario)
+    assert_same_journal(g, o)
+    c = g.counters()
+    assert c["max_window"] > 512
