@@ -382,13 +382,13 @@ def gpu_arm(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--values-per-tick", type=int, default=4096)
+    ap.add_argument("--values-per-tick", type=int, default=32768)
     ap.add_argument("--latency-ms", type=int, default=0)
-    ap.add_argument("--ring-cap", type=int, default=4096)
-    ap.add_argument("--max-window", type=int, default=2048)
+    ap.add_argument("--ring-cap", type=int, default=8192)
+    ap.add_argument("--max-window", type=int, default=4096)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--journal-cap-log2", type=int, default=26)
     ap.add_argument("--calendar-cap", type=int, default=1 << 20)

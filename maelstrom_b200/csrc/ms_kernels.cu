@@ -1055,7 +1055,16 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
       }
     }
     // PE2: emissions in id order, one emission per thread: emission j belongs to the last
-    //      sorted position whose exclusive emit prefix is <= j
+    //      sorted position whose exclusive emit prefix is <= j.  When it fits, that map is
+    //      materialised in the (now free) first-sight table instead of searched for.
+    const bool own_map = agg_mode != 2 && n_emit <= 2u * cap;
+    if (own_map) {
+      for (uint32_t pos = tid; pos < n; pos += nt) {
+        const uint32_t e0 = (uint32_t)aux[pos], e1 = (uint32_t)aux[pos + 1];
+        for (uint32_t q = e0; q < e1; q++) tab[q] = (uint16_t)pos;
+      }
+      __syncthreads();
+    }
     for (uint32_t base = 0; base < n_emit; base += nt) {
       const uint32_t j = base + tid;
       const bool valid = j < n_emit;
@@ -1064,9 +1073,14 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
       uint32_t direct = 0;
       bool has_direct = false;
       if (valid) {
-        uint32_t lo = 0, hi = n;
-        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if ((uint32_t)aux[mid] <= j) lo = mid; else hi = mid; }
-        const uint32_t pos = lo;
+        uint32_t pos;
+        if (own_map) {
+          pos = tab[j];
+        } else {
+          uint32_t lo = 0, hi = n;
+          while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if ((uint32_t)aux[mid] <= j) lo = mid; else hi = mid; }
+          pos = lo;
+        }
         const uint64_t a0 = aux[pos];
         const uint32_t k = j - (uint32_t)a0;
         const uint32_t my_emit = (uint32_t)aux[pos + 1] - (uint32_t)a0;
