@@ -175,7 +175,7 @@ def reference_arm(args, rank, world):
     line = {
         "impl": "reference", "metric": "simulated msgs/sec (broadcast, 4096 nodes)", "value": value,
         "unit": "msgs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * t_all / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * t_all / max(args.steps, 1), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "int64", "data": "synthetic",
         "config": {"workload": "broadcast, 4096 nodes, grid 64x64, latency constant 0",
                    "values_per_tick": per_tick, "note": "CPU restatement of net.clj (oracle/), not the JVM: "
@@ -189,14 +189,20 @@ def reference_arm(args, rank, world):
 
 
 # --------------------------------------------------------------------------- GPU arm
-def make_sim(mb, args, n_ticks_total, journal_discard, device):
+def make_sim(mb, args, n_ticks_total, journal_discard, device, world=1):
     V = args.values_per_tick
-    sim = mb.Sim(N_NODES, workload="broadcast", topology="grid", latency_dist="constant",
-                 latency_mean_ms=args.latency_ms, seed=SEED, n_values=V * n_ticks_total + 64,
-                 max_endpoints=N_NODES + N_CLIENTS, ring_cap=args.ring_cap, max_window=args.max_window,
-                 journal_level=1, journal_discard=1 if journal_discard else 0,
-                 journal_cap_log2=args.journal_cap_log2, device=device,
-                 threads_per_node=args.threads, calendar_cap=args.calendar_cap)
+    kw = dict(workload="broadcast", topology="grid", latency_dist="constant",
+              latency_mean_ms=args.latency_ms, seed=SEED, n_values=V * n_ticks_total + 64,
+              max_endpoints=N_NODES + N_CLIENTS, ring_cap=args.ring_cap, max_window=args.max_window,
+              journal_level=1, journal_discard=1 if journal_discard else 0,
+              journal_cap_log2=args.journal_cap_log2,
+              threads_per_node=args.threads, calendar_cap=args.calendar_cap)
+    if world > 1:
+        # one shard per rank; cross-shard messages go over NVLink peer memory (maelstrom_b200/sharded.py)
+        from maelstrom_b200.sharded import ShardedSim
+        sim = ShardedSim(N_NODES, device=device, **kw)
+    else:
+        sim = mb.Sim(N_NODES, device=device, **kw)
     from maelstrom_b200.engine import KIND_SIM_CLIENT
     c0 = None
     for i in range(N_CLIENTS):
@@ -229,14 +235,15 @@ def gpu_arm(args, rank, world, local_rank):
     total_ticks = W + K
 
     # ---- arm A: device-resident (value + roofline)
-    sim, c0 = make_sim(mb, args, 3 * total_ticks + 4, True, local_rank)
+    sim, c0 = make_sim(mb, args, 3 * total_ticks + 4, True, local_rank, world)
+    lstats = (lambda: sim.sim.stats()["all"]) if world > 1 else (lambda: sim.stats()["all"])   # this rank's endpoints
     ops = make_ops(OP_DTYPE, 0, 3 * total_ticks + 2, V, c0, N_CLIENTS, TYPES["broadcast"], F_MSG_ID)
     sim.schedule(ops)
     tick = 0
     for _ in range(W):
         tick += 1
         run_until_tick(sim, tick)
-    before = sim.stats()["all"]
+    before = lstats()
     c_before = sim.counters()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -250,7 +257,7 @@ def gpu_arm(args, rank, world, local_rank):
         run_until_tick(sim, tick)
     ms_value = sim.timer_end()
     torch.cuda.synchronize()
-    after = sim.stats()["all"]
+    after = lstats()
     c_after = sim.counters()
     clocks = sampler.stop()
     recvs = after["recv-count"] - before["recv-count"]
@@ -278,11 +285,11 @@ def gpu_arm(args, rank, world, local_rank):
     # roofline pass: same work again (next K ticks) with CUDA events around every round-kernel launch
     sim.profile(True)
     sim.profile_read()
-    b2 = sim.stats()["all"]
+    b2 = lstats()
     for _ in range(K):
         tick += 1
         run_until_tick(sim, tick)
-    a2 = sim.stats()["all"]
+    a2 = lstats()
     k_ms, k_launches = sim.profile_read()
     sim.profile(False)
     alg_bytes = ALG_SEND_B * (a2["send-count"] - b2["send-count"]) + ALG_RECV_B * (a2["recv-count"] - b2["recv-count"])
@@ -292,7 +299,29 @@ def gpu_arm(args, rank, world, local_rank):
 
     # ---- arm B: end to end through host buffers
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and world > 1:
+        # sharded e2e: host op buffers in every step, result read back every step (the 9 net-stats
+        # counters); the full journal is not drained in sharded runs (per-shard rings, no global back-pressure)
+        sim, c0 = make_sim(mb, args, total_ticks + 2, True, local_rank, world)
+        host_ops = [make_ops(OP_DTYPE, t, 1, V, c0, N_CLIENTS, TYPES["broadcast"], F_MSG_ID)
+                    for t in range(total_ticks)]
+        tick = 0
+        for step in range(total_ticks):
+            if step == W:
+                dist.barrier()
+                torch.cuda.synchronize()
+                s0 = sim.sim.stats()["all"]["recv-count"]
+                t0 = time.perf_counter()
+            sim.schedule(host_ops[step])
+            tick += 1
+            run_until_tick(sim, tick)
+            sim.sim.stats()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t_e2e = time.perf_counter() - t0
+        e2e = {"seconds": t_e2e, "msgs": sim.sim.stats()["all"]["recv-count"] - s0, "h2d": V * 40, "d2h": 72}
+        sim.close()
+    elif not args.no_e2e:
         sim, c0 = make_sim(mb, args, total_ticks + 2, False, local_rank)
         ev_cap = 1 << args.journal_cap_log2
         pinned = torch.empty(ev_cap * 32, dtype=torch.uint8, pin_memory=True)
@@ -349,14 +378,15 @@ def gpu_arm(args, rank, world, local_rank):
     line = {
         "metric": "simulated msgs/sec (broadcast, 4096 nodes)", "value": value, "unit": "msgs/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_value / K, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
         "config": {"workload": "broadcast, 4096 nodes, grid 64x64 (BASELINE.json configs[1])",
                    "latency": "constant %d ms" % lat, "values_per_step": V, "step": "1 virtual tick (1 ms)",
-                   "delivered_msgs_per_step": recvs // max(K * world, 1), "rounds_per_step": rounds / max(K, 1),
+                   "delivered_msgs_per_step": recvs // max(K, 1), "rounds_per_step": rounds / max(K, 1),
                    "ring_cap": args.ring_cap, "max_window": args.max_window, "max_window_seen": max_window, "fallback_sorts": c_after["fallback_sorts"] - c_before["fallback_sorts"],
                    "l2_policy": "inputs larger than L2: inbox rings %.1f GB + seen bitmaps, streamed once per round"
                                 % (N_NODES * args.ring_cap * 48 / 1e9),
-                   "parallelism": "replicas x%d" % world if world > 1 else "single GPU",
+                   "parallelism": ("%d shards by endpoint range, cross-shard messages written into peer inbox rings over NVLink, "
+                                   "2 barriers per round" % world) if world > 1 else "single GPU",
                    "published_reference": "6e4 msgs/s, 48-way Xeon (README.md:39-42), different hardware"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None,

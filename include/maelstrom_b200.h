@@ -136,7 +136,9 @@ typedef struct ms_config {
   uint32_t inject_cap;       /* host sends staged per round */
   int32_t  device;           /* CUDA device ordinal */
   uint32_t threads_per_node; /* CTA size of the round kernel (0 = auto) */
-  uint32_t reserved[8];
+  uint32_t n_shards;         /* GPUs the endpoints are sharded over (0/1 = single GPU), <= 8 */
+  uint32_t shard_id;         /* this process's shard */
+  uint32_t reserved[6];      /* [0] = rounds of id history to keep (0 = default) */
 } ms_config;
 
 typedef struct ms_sim ms_sim;
@@ -206,6 +208,26 @@ uint64_t ms_client_replies(ms_sim* sim);
 /* device-side counters for roofline accounting: out = {rounds, sends, recvs,
  * kernel launches, lost, partition_drops, max_window, windows that needed the full sort} */
 int ms_counters(ms_sim* sim, uint64_t out[8]);
+
+/* ------------------------------------------------------------------ multi-GPU (one process per GPU)
+ * Endpoints are sharded by index range; every shard runs the same rounds in lock step.
+ * A message for an endpoint of another shard is written by the sending kernel straight
+ * into the owner's inbox ring over NVLink peer memory (CUDA IPC), so the only per-round
+ * collectives are two barriers, which the host adapter supplies:
+ *   ms_shard_handles  -> opaque blob (MS_SHARD_BLOB_BYTES) describing this shard's memory
+ *   ms_shard_connect  <- the blob of every peer (exchanged by the caller, e.g. all_gather)
+ *   ms_set_barrier    <- callback(ctx, cuda_stream) that enqueues a cross-shard barrier
+ *                        (e.g. a 1-element NCCL all-reduce) on the given CUDA stream
+ * ms_stream returns the CUDA stream the engine launches on.  In sharded runs ms_journal_drain
+ * fills only the events of this shard's endpoints; the other slots are 0xFF bytes. */
+#define MS_SHARD_BLOB_BYTES 512
+typedef void (*ms_barrier_fn)(void* ctx, void* cuda_stream);
+int   ms_shard_handles(ms_sim* sim, void* blob_out);
+int   ms_shard_connect(ms_sim* sim, uint32_t peer, const void* blob);
+int   ms_set_barrier(ms_sim* sim, ms_barrier_fn fn, void* ctx);
+void* ms_stream(ms_sim* sim);
+/* pure helper: shard that owns endpoint `e` (servers: contiguous index ranges; others round-robin) */
+uint32_t ms_shard_owner(uint32_t e, uint32_t n_servers, uint32_t n_shards);
 
 /* Device-side timing on the engine's own CUDA stream (what bench.py reports):
  * ms_timer_begin records an event; ms_timer_end records another, synchronises and

@@ -33,7 +33,8 @@ class Config(C.Structure):
                 ("journal_cap_log2", C.c_uint32), ("journal_level", C.c_uint32),
                 ("journal_discard", C.c_uint32), ("calendar_slots", C.c_uint32),
                 ("calendar_cap", C.c_uint32), ("mailbox_cap", C.c_uint32), ("inject_cap", C.c_uint32),
-                ("device", C.c_int32), ("threads_per_node", C.c_uint32), ("reserved", C.c_uint32 * 8)]
+                ("device", C.c_int32), ("threads_per_node", C.c_uint32), ("n_shards", C.c_uint32),
+                ("shard_id", C.c_uint32), ("reserved", C.c_uint32 * 6)]
 
 
 class Body(C.Structure):
@@ -79,10 +80,17 @@ SYMBOLS = {
     "ms_timer_end": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "ms_profile": (C.c_int, [_P, C.c_int]),
     "ms_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "ms_shard_handles": (C.c_int, [_P, _P]),
+    "ms_shard_connect": (C.c_int, [_P, C.c_uint32, _P]),
+    "ms_set_barrier": (C.c_int, [_P, _P, _P]),
+    "ms_stream": (_P, [_P]),
+    "ms_shard_owner": (C.c_uint32, [C.c_uint32, C.c_uint32, C.c_uint32]),
     "ms_debug_phase_cycles": (C.c_int, [_P, C.c_int, _P]),
     "ms_topology": (C.c_size_t, [C.c_uint32, C.c_uint32, C.c_uint32, _P, C.c_size_t]),
 }
 
+SHARD_BLOB_BYTES = 512
+BARRIER_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
 _lib = None
 
 

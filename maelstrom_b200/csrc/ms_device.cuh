@@ -103,6 +103,12 @@ struct Params {
   uint64_t* rt_chunk;        // raw journal position of the ticket's chunk
   uint64_t* rt_cnt;          // tagged per-ticket counts of the round in flight (see k_round epilogue)
   uint64_t* phase_cycles;    // diagnostic: [4 classes][16] cycle sums per k_round phase, or nullptr
+  // sharding: arrays of every shard, reachable over NVLink peer memory (index = shard)
+  uint32_t  n_shards, shard_id;
+  uint4*    ring_sh[8];
+  uint32_t* tail_sh[8];
+  uint32_t* head_sh[8];
+  uint64_t* rt_cnt_sh[8];
   uint32_t  hist, hist_mask, t_max, n_classes;
   uint32_t* cls_list;        // [2][4][t_max] tickets per size class
   uint32_t  cls_cap[4];      // ascending window capacities of the classes
@@ -200,5 +206,16 @@ MS_HD uint64_t latency_ms(const NetParams& np, const uint32_t x[4]) {
 }
 
 MS_HD bool kind_is_client(uint8_t k) { return k == MS_KIND_CLIENT || k == MS_KIND_SIM_CLIENT; }
+
+// Shard that owns endpoint e: servers are split into G contiguous index ranges (rows of the
+// grid stay together), every other endpoint round-robin.  Injector tickets belong to shard 0.
+MS_HD uint32_t owner_of(uint32_t e, uint32_t n_servers, uint32_t G) {
+  if (G <= 1) return 0;
+  if (e < n_servers) return (uint32_t)(((uint64_t)e * G) / n_servers);
+  return (e - n_servers) % G;
+}
+MS_HD uint32_t owner_of_ticket(uint32_t t, uint32_t n_inj, uint32_t n_servers, uint32_t G) {
+  return t < n_inj ? 0u : owner_of(t - n_inj, n_servers, G);
+}
 
 }  // namespace msd

@@ -24,7 +24,7 @@ size_t msk_round_smem_bytes(uint32_t cap);
 int msk_round_occupancy(int threads, size_t smem);
 void msk_launch_round(const msd::Params* p, int n_classes, const uint32_t* caps, const int* threads,
                       const int* grids, int with_release, cudaStream_t s, cudaEvent_t before_round,
-                      cudaEvent_t after_round);
+                      cudaEvent_t after_round, int phases);
 void msk_set_bit(uint32_t* words, size_t word, uint32_t bit, cudaStream_t s);
 void msk_journal_expand(const msd::Params* p, uint64_t r0, uint32_t n_rounds, uint64_t first, uint64_t count,
                         void* out_ev, void* out_body, cudaStream_t s);
@@ -130,6 +130,10 @@ struct ms_sim {
   void* stage_body = nullptr;
   size_t stage_cap = 0;
   std::vector<RoundMeta> hmeta;
+  // sharding
+  ms_barrier_fn barrier = nullptr;
+  void* barrier_ctx = nullptr;
+  std::vector<void*> peer_ptrs;     // opened IPC mappings
   // timing
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   bool profiling = false;
@@ -211,8 +215,18 @@ struct ms_sim {
       const int T = (int)(P.n_inj_tickets + P.n_ep);
       int grids[4];
       for (int c = 0; c < n_classes; c++) grids[c] = std::max(1, std::min(class_grid[c], T));
-      msk_launch_round(&P, n_classes, class_cap, class_threads, grids, use_calendar ? 1 : 0, stream, a, b);
-      launches += (use_calendar ? 2 : 1) + n_classes;
+      if (P.n_shards <= 1) {
+        msk_launch_round(&P, n_classes, class_cap, class_threads, grids, use_calendar ? 1 : 0, stream, a, b, 7);
+        launches += (use_calendar ? 2 : 1) + n_classes;
+      } else {
+        // sharded: snapshot | barrier | round kernels (peer writes) | barrier | commit
+        msk_launch_round(&P, n_classes, class_cap, class_threads, grids, use_calendar ? 1 : 0, stream, a, b, 1);
+        barrier(barrier_ctx, (void*)stream);
+        msk_launch_round(&P, n_classes, class_cap, class_threads, grids, 0, stream, a, b, 2);
+        barrier(barrier_ctx, (void*)stream);
+        msk_launch_round(&P, n_classes, class_cap, class_threads, grids, 0, stream, a, b, 4);
+        launches += (use_calendar ? 2 : 1) + n_classes + 1;
+      }
     }
   }
 
@@ -256,6 +270,10 @@ struct ms_sim {
       while (r1 < hs.round && meta(r1).round == r1 && meta(r1).ev_base < first + piece) r1++;
       if (r1 == r0) { set_err("journal drain: round history lost"); return MS_ERR_SIM; }
       const bool want_body = bodies && cfg.journal_level >= 2;
+      if (P.n_shards > 1) {   // only this shard's events are produced; the rest stays 0xFF
+        CK(cudaMemsetAsync(stage_ev, 0xFF, piece * 32, stream));
+        if (want_body) CK(cudaMemsetAsync(stage_body, 0xFF, piece * 32, stream));
+      }
       msk_journal_expand(&P, r0, (uint32_t)(r1 - r0), first, piece, stage_ev, want_body ? stage_body : nullptr, stream);
       CK(cudaStreamSynchronize(stream));
       CK(cudaMemcpy(ev + done, stage_ev, piece * 32, cudaMemcpyDeviceToHost));
@@ -363,6 +381,8 @@ static int build_sim(ms_sim* s, const ms_config* in) {
                                                       : std::min<uint32_t>(16384u, std::max<uint32_t>(64u, 32u * c.latency_mean_ms)));
     if (!c.calendar_cap) c.calendar_cap = 1u << 16;
   }
+  if (c.n_shards == 0) c.n_shards = 1;
+  if (c.n_shards > 8 || c.shard_id >= c.n_shards) { set_err("n_shards must be <= 8 and shard_id < n_shards"); return MS_ERR_ARG; }
   if (c.threads_per_node && (c.threads_per_node % 32 || c.threads_per_node > 512)) {
     set_err("threads_per_node must be a multiple of 32 in [32,512]");
     return MS_ERR_ARG;
@@ -411,6 +431,8 @@ static int build_sim(ms_sim* s, const ms_config* in) {
   P.n_ep = c.n_nodes;
   P.n_inj_tickets = 8;
   P.max_window = c.max_window;
+  P.n_shards = c.n_shards;
+  P.shard_id = c.shard_id;
   {
     // per-round history: 16 B per (round, ticket); keep it under ~1 GB
     P.t_max = M + P.n_inj_tickets;
@@ -519,6 +541,11 @@ static int build_sim(ms_sim* s, const ms_config* in) {
     for (int k = 0; k < s->n_classes; k++)
       s->class_grid[k] = s->n_sms * msk_round_occupancy(s->class_threads[k], msk_round_smem_bytes(s->class_cap[k]));
     if ((rc = s->dalloc(&P.cls_list, (size_t)2 * 4 * P.t_max))) return rc;
+    for (int g = 0; g < 8; g++) { P.ring_sh[g] = nullptr; P.tail_sh[g] = nullptr; P.head_sh[g] = nullptr; P.rt_cnt_sh[g] = nullptr; }
+    P.ring_sh[c.shard_id] = P.ring;
+    P.tail_sh[c.shard_id] = P.tail;
+    P.head_sh[c.shard_id] = P.head;
+    P.rt_cnt_sh[c.shard_id] = P.rt_cnt;
     CK(cudaStreamSynchronize(s->stream));
   }
   CK(cudaStreamSynchronize(s->stream));
@@ -552,6 +579,7 @@ void ms_destroy(ms_sim* s) {
   if (s->jfile) ms_journal_close(s);
   cudaSetDevice(s->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
+  for (void* p : s->peer_ptrs) cudaIpcCloseMemHandle(p);
   for (void* p : s->allocs) cudaFree(p);
   if (s->stage_ev) cudaFree(s->stage_ev);
   if (s->stage_body) cudaFree(s->stage_body);
@@ -654,6 +682,11 @@ static bool journal_blocked(const ms_sim* s) {
 static int step_locked(ms_sim* s, uint64_t n_rounds, int64_t stop) {
   cudaSetDevice(s->device);
   int rc;
+  if (s->P.n_shards > 1) {
+    if (!s->barrier) { set_err("sharded simulation: call ms_set_barrier first"); return MS_ERR_ARG; }
+    for (uint32_t g = 0; g < s->P.n_shards; g++)
+      if (!s->P.ring_sh[g]) { set_err("sharded simulation: ms_shard_connect every peer first"); return MS_ERR_ARG; }
+  }
   if ((rc = s->stage_injections())) return rc;
   if ((rc = s->set_stop(stop))) return rc;
   s->launch_rounds(n_rounds);
@@ -855,6 +888,65 @@ int ms_counters(ms_sim* s, uint64_t out[8]) {
   out[7] = s->hs.fallback_sorts;
   return MS_OK;
 }
+
+struct ShardBlob {   // MS_SHARD_BLOB_BYTES
+  uint32_t magic, shard_id, n_shards, t_max;
+  uint32_t max_endpoints, ring_cap, hist, pad;
+  cudaIpcMemHandle_t ring, tail, head, rt_cnt;
+};
+static_assert(sizeof(ShardBlob) <= MS_SHARD_BLOB_BYTES, "blob too large");
+
+int ms_shard_handles(ms_sim* s, void* blob_out) {
+  std::lock_guard<std::mutex> g(s->mu);
+  cudaSetDevice(s->device);
+  ShardBlob b;
+  memset(&b, 0, sizeof b);
+  b.magic = 0x4253534Du;
+  b.shard_id = s->P.shard_id; b.n_shards = s->P.n_shards; b.t_max = s->P.t_max;
+  b.max_endpoints = s->cfg.max_endpoints; b.ring_cap = s->P.ring_cap; b.hist = s->P.hist;
+  CK(cudaIpcGetMemHandle(&b.ring, s->P.ring));
+  CK(cudaIpcGetMemHandle(&b.tail, s->P.tail));
+  CK(cudaIpcGetMemHandle(&b.head, s->P.head));
+  CK(cudaIpcGetMemHandle(&b.rt_cnt, s->P.rt_cnt));
+  memset(blob_out, 0, MS_SHARD_BLOB_BYTES);
+  memcpy(blob_out, &b, sizeof b);
+  return MS_OK;
+}
+
+int ms_shard_connect(ms_sim* s, uint32_t peer, const void* blob) {
+  std::lock_guard<std::mutex> g(s->mu);
+  cudaSetDevice(s->device);
+  ShardBlob b;
+  memcpy(&b, blob, sizeof b);
+  if (b.magic != 0x4253534Du || b.shard_id != peer || peer >= s->P.n_shards || b.n_shards != s->P.n_shards ||
+      b.t_max != s->P.t_max || b.max_endpoints != s->cfg.max_endpoints || b.ring_cap != s->P.ring_cap ||
+      b.hist != s->P.hist) {
+    set_err("ms_shard_connect: peer blob does not match this simulation's configuration");
+    return MS_ERR_ARG;
+  }
+  if (peer == s->P.shard_id) return MS_OK;
+  void* ptr = nullptr;
+  CK(cudaIpcOpenMemHandle(&ptr, b.ring, cudaIpcMemLazyEnablePeerAccess));
+  s->peer_ptrs.push_back(ptr); s->P.ring_sh[peer] = (uint4*)ptr;
+  CK(cudaIpcOpenMemHandle(&ptr, b.tail, cudaIpcMemLazyEnablePeerAccess));
+  s->peer_ptrs.push_back(ptr); s->P.tail_sh[peer] = (uint32_t*)ptr;
+  CK(cudaIpcOpenMemHandle(&ptr, b.head, cudaIpcMemLazyEnablePeerAccess));
+  s->peer_ptrs.push_back(ptr); s->P.head_sh[peer] = (uint32_t*)ptr;
+  CK(cudaIpcOpenMemHandle(&ptr, b.rt_cnt, cudaIpcMemLazyEnablePeerAccess));
+  s->peer_ptrs.push_back(ptr); s->P.rt_cnt_sh[peer] = (uint64_t*)ptr;
+  return MS_OK;
+}
+
+int ms_set_barrier(ms_sim* s, ms_barrier_fn fn, void* ctx) {
+  std::lock_guard<std::mutex> g(s->mu);
+  s->barrier = fn;
+  s->barrier_ctx = ctx;
+  return MS_OK;
+}
+
+void* ms_stream(ms_sim* s) { return (void*)s->stream; }
+
+uint32_t ms_shard_owner(uint32_t e, uint32_t n_servers, uint32_t n_shards) { return owner_of(e, n_servers, n_shards); }
 
 int ms_timer_begin(ms_sim* s) {
   std::lock_guard<std::mutex> g(s->mu);

@@ -69,8 +69,10 @@ __device__ __forceinline__ bool round_skipped(const Params& p, const DevState* s
   if (p.jlevel && !p.jdiscard) {
     // only values that are constant while a round is in flight may be used here:
     // raw_base of the round's row is jraw_cursor as of the START of the round
+    // (sharded runs: a per-shard condition would desynchronise the shards, so only the
+    // history test below, which is identical on every shard, applies; overflow is an error)
     const uint64_t raw_base = p.rmeta[(uint32_t)st->round & p.hist_mask].raw_base;
-    if (raw_base - st->jraw_drained > ((p.jmask + 1) >> 1)) return true;
+    if (p.n_shards <= 1 && raw_base - st->jraw_drained > ((p.jmask + 1) >> 1)) return true;
     if (st->round - st->drain_round + 2 >= p.hist) return true;
   }
   return false;
@@ -234,7 +236,8 @@ __device__ __forceinline__ void emit_one(const Params& p, DevState* st, const Ne
     } else if (lat == 0) {                                           // deadline == now: next delta round
       cx.c_zero++;
       if (has_direct) {
-        rec_store(p.ring + ((size_t)r.dest * p.ring_cap + (direct_pos & p.ring_mask)) * 3, r);
+        uint4* ring_o = p.ring_sh[owner_of(r.dest, p.n_servers, p.n_shards)];
+        rec_store(ring_o + ((size_t)r.dest * p.ring_cap + (direct_pos & p.ring_mask)) * 3, r);
       } else {
         push = true;
       }
@@ -258,14 +261,15 @@ __device__ __forceinline__ void emit_one(const Params& p, DevState* st, const Ne
   const int leader = __ffs(mask) - 1;
   const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
   uint32_t base = 0;
-  if (push && lane == leader) base = atomicAdd(&p.tail[r.dest], (uint32_t)__popc(mask));
+  const uint32_t o = push ? owner_of(r.dest, p.n_servers, p.n_shards) : 0u;   // NVLink peer memory when o != shard_id
+  if (push && lane == leader) base = atomicAdd(&p.tail_sh[o][r.dest], (uint32_t)__popc(mask));
   base = __shfl_sync(FULL, base, leader);
   if (push) {
     const uint32_t pos = base + rank;
-    if ((uint32_t)(pos - p.head[r.dest]) >= p.ring_cap) {
+    if ((uint32_t)(pos - p.head_sh[o][r.dest]) >= p.ring_cap) {
       latch_error(st, E_RING_OVERFLOW, r.dest);
     } else {
-      rec_store(p.ring + ((size_t)r.dest * p.ring_cap + (pos & p.ring_mask)) * 3, r);
+      rec_store(p.ring_sh[o] + ((size_t)r.dest * p.ring_cap + (pos & p.ring_mask)) * 3, r);
     }
   }
 }
@@ -289,6 +293,7 @@ __global__ void k_snapshot(Params p) {
   const uint32_t stride = gridDim.x * blockDim.x;
   const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
   for (uint32_t e = gid; e < p.n_ep; e += stride) {
+    if (owner_of(e, p.n_servers, p.n_shards) != p.shard_id) continue;   // another shard's endpoint
     const uint32_t h = p.limit[e], l = p.tail[e];
     p.head[e] = h;
     p.limit[e] = l;
@@ -297,7 +302,7 @@ __global__ void k_snapshot(Params p) {
     const uint32_t k = atomicAdd(&st->cls_count[par][c], 1u);
     p.cls_list[((size_t)par * 4 + c) * p.t_max + k] = p.n_inj_tickets + e;
   }
-  if (gid < p.n_inj_tickets) {   // injector slices run in the widest class
+  if (gid < p.n_inj_tickets && p.shard_id == 0) {   // injector slices run in the widest class (shard 0)
     const uint32_t c = p.n_classes - 1;
     const uint32_t k = atomicAdd(&st->cls_count[par][c], 1u);
     p.cls_list[((size_t)par * 4 + c) * p.t_max + k] = gid;
@@ -334,15 +339,16 @@ __global__ void k_release(Params p) {
     const int leader = __ffs(mask) - 1;
     const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
     uint32_t base = 0;
-    if (valid && lane == leader) base = atomicAdd(&p.tail[dest], (uint32_t)__popc(mask));
+    const uint32_t o = valid ? owner_of(dest, p.n_servers, p.n_shards) : 0u;
+    if (valid && lane == leader) base = atomicAdd(&p.tail_sh[o][dest], (uint32_t)__popc(mask));
     base = __shfl_sync(FULL, base, leader);
     if (valid) {
       const uint32_t pos = base + rank;
-      // the previous window [head, limit) is fully consumed; only limit matters here
-      if ((uint32_t)(pos - p.limit[dest]) >= p.ring_cap) {
+      // the previous window is fully consumed by now: the whole ring past `head` is writable
+      if ((uint32_t)(pos - p.head_sh[o][dest]) >= p.ring_cap) {
         latch_error(st, E_RING_OVERFLOW, dest);
       } else {
-        uint4* dst = p.ring + ((size_t)dest * p.ring_cap + (pos & p.ring_mask)) * 3;
+        uint4* dst = p.ring_sh[o] + ((size_t)dest * p.ring_cap + (pos & p.ring_mask)) * 3;
         st_v4(dst, a); st_v4(dst + 1, b); st_v4(dst + 2, c);
       }
     }
@@ -468,6 +474,130 @@ __device__ __forceinline__ int node_emit(const Params& p, uint32_t e, const MsgV
   }
   r.tf = otype | (oflags << 16);
   return slot;
+}
+
+// ------------------------------------------------------------------ round commit
+// Commit of a round, executed by one whole CTA: turn the per-ticket
+// counts of every shard into exclusive prefixes, advance the id / event / time counters and
+// open the next round's row.  Single GPU: called by the last ticket inside k_round; sharded:
+// by k_commit on every shard (all shards compute the same values) after the barrier.
+__device__ void commit_round(const Params& p, DevState* st, uint64_t* s_wtmp) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t now = st->now;
+  const uint64_t round = st->round;
+  const uint32_t T = p.n_inj_tickets + p.n_ep;
+  const uint32_t row = (uint32_t)round & p.hist_mask;
+  const uint32_t tag = ((uint32_t)round & 0x7FFFu) + 1u;
+    uint32_t* em = p.rt_em + (size_t)row * p.t_max;
+    uint32_t* ev = p.rt_ev + (size_t)row * p.t_max;
+    // pass 1 (strided, loads batched 4 deep): validate the tags, unpack the counts
+    uint32_t zp_any = 0;
+    for (int base = 0; base < (int)T; base += 4 * nt) {
+      uint64_t v[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int i = base + q * nt + tid;
+        v[q] = i < (int)T ? __ldcg(reinterpret_cast<const unsigned long long*>(p.rt_cnt_sh[owner_of_ticket((uint32_t)i, p.n_inj_tickets, p.n_servers, p.n_shards)] + (size_t)row * p.t_max + i)) : ((uint64_t)tag << 48);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int i = base + q * nt + tid;
+        if (i >= (int)T) continue;
+        // every ticket has bumped `done`, so its entry store is in flight at worst: wait for the tag
+        for (uint32_t spin = 0; (uint32_t)(v[q] >> 48) != tag && spin < (1u << 22); spin++)
+          v[q] = __ldcg(reinterpret_cast<const unsigned long long*>(p.rt_cnt_sh[owner_of_ticket((uint32_t)i, p.n_inj_tickets, p.n_servers, p.n_shards)] + (size_t)row * p.t_max + i));
+        if ((uint32_t)(v[q] >> 48) != tag) latch_error(st, E_HISTORY, (uint32_t)i);
+        zp_any |= (uint32_t)(v[q] >> 47) & 1u;
+        ev[i] = (uint32_t)(v[q] >> 24) & 0x7FFFFFu;
+        em[i] = (uint32_t)v[q] & 0xFFFFFFu;
+      }
+    }
+    zp_any = __syncthreads_or(zp_any);   // also makes ev[]/em[] visible to the whole CTA
+    // pass 2 (one contiguous chunk per thread): exclusive prefix
+    const int c = ((int)T + nt - 1) / nt;
+    const int lo = min(tid * c, (int)T), hi = min(lo + c, (int)T);
+    uint64_t sum = 0;   // ev << 32 | em  (per-round totals stay below 2^32)
+    for (int i = lo; i < hi; i++) sum += ((uint64_t)ev[i] << 32) | em[i];
+    uint64_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint64_t y = __shfl_up_sync(FULL, incl, d);
+      if (lane >= d) incl += y;
+    }
+    if (lane == 31) s_wtmp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const int nw = nt >> 5;
+      const uint64_t w = lane < nw ? s_wtmp[lane] : 0;
+      uint64_t wi = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t y = __shfl_up_sync(FULL, wi, d);
+        if (lane >= d) wi += y;
+      }
+      s_wtmp[lane] = wi - w;
+      if (lane == 31) s_wtmp[32] = wi;
+    }
+    __syncthreads();
+    uint64_t run = s_wtmp[warp] + incl - sum;
+    for (int i = lo; i < hi; i++) {
+      const uint32_t ve = ev[i], vm = em[i];   // written in pass 1, visible after the barrier
+      ev[i] = (uint32_t)(run >> 32);
+      em[i] = (uint32_t)run;
+      run += ((uint64_t)ve << 32) | vm;
+    }
+    const uint64_t total = s_wtmp[32];
+    __syncthreads();
+    if (tid == 0) {
+      const uint64_t ev_total = total >> 32, em_total = total & 0xFFFFFFFFull;
+      RoundMeta* m = p.rmeta + row;
+      m->ev_total = ev_total;
+      m->em_total = em_total;
+      m->n_tickets = T;
+      st->next_event += ev_total;
+      st->next_id += em_total;
+      const uint64_t tick = (uint64_t)(now / kTickNs);
+      uint32_t hi_s = (tick + 1 < p.n_tick_off) ? p.tick_off[tick + 1] : p.n_sched;
+      if (hi_s > st->sched_cursor) st->sched_cursor = hi_s;
+      st->inj_count = 0;
+      int64_t next_now = now;
+      if (zp_any == 0) {
+        next_now = now + kTickNs;
+        st->now = next_now;
+        st->time_advanced = 1;
+        if (p.cal) st->cal_release = (((uint32_t)(tick + 1)) & (p.cal_slots - 1)) + 1;
+      } else {
+        st->time_advanced = 0;
+      }
+      st->round = round + 1;
+      st->rounds_run += 1;
+      st->done = 0;
+      st->slot_open = 0;
+      const uint64_t raw_cur = *reinterpret_cast<volatile uint64_t*>(&st->jraw_cursor);
+      if (p.jdiscard || !p.jlevel) {
+        st->journal_drained = st->next_event;
+        st->jraw_drained = raw_cur;
+        st->drain_round = round + 1;
+      }
+      // open the next round's row
+      RoundMeta* nx = p.rmeta + ((uint32_t)(round + 1) & p.hist_mask);
+      nx->round = round + 1;
+      nx->now = next_now;
+      nx->id_base = st->next_id;
+      nx->ev_base = st->next_event;
+      nx->raw_base = raw_cur;
+      nx->n_tickets = 0;
+      nx->ev_total = 0;
+      nx->em_total = 0;
+      __threadfence();
+    }
+}
+
+__global__ void __launch_bounds__(512) k_commit(Params p) {
+  __shared__ uint64_t s_wtmp[34];
+  DevState* st = p.st;
+  if (round_skipped(p, st) || !st->slot_open) return;
+  commit_round(p, st, s_wtmp);
 }
 
 // ------------------------------------------------------------------ k_round
@@ -998,8 +1128,9 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
       const uint32_t total = n_new - acc;
       uint32_t base = 0;
       if (total) {
-        base = atomicAdd(&p.tail[nb], total);
-        if ((uint32_t)(base + total - p.head[nb]) > p.ring_cap) latch_error(st, E_RING_OVERFLOW, nb);
+        const uint32_t o = owner_of(nb, p.n_servers, p.n_shards);
+        base = atomicAdd(&p.tail_sh[o][nb], total);
+        if ((uint32_t)(base + total - p.head_sh[o][nb]) > p.ring_cap) latch_error(st, E_RING_OVERFLOW, nb);
       }
       s_nbbase[tid] = base;
     }
@@ -1155,117 +1286,16 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
                            ((uint64_t)(n_ev_local & 0x7FFFFFu) << 24) | (uint64_t)(n_em_local & 0xFFFFFFu);
     __stcg(reinterpret_cast<unsigned long long*>(p.rt_cnt + (size_t)row * p.t_max + ticket),
            (unsigned long long)entry);
-    s_misc[4] = (atomicAdd(&st->done, 1u) == T - 1) ? 1u : 0u;
+    // single GPU: the last ticket commits the round right here; sharded: k_commit does it
+    // after the cross-shard barrier
+    s_misc[4] = (p.n_shards <= 1 && atomicAdd(&st->done, 1u) == T - 1) ? 1u : 0u;
     s_misc[5] = next_li;
   }
   __syncthreads();
   PHASE_MARK(7);
   if (s_misc[4]) {
     // ---------------------------------------------------------- last CTA: commit the round
-    const uint64_t* cntp = p.rt_cnt + (size_t)row * p.t_max;
-    uint32_t* em = p.rt_em + (size_t)row * p.t_max;
-    uint32_t* ev = p.rt_ev + (size_t)row * p.t_max;
-    // pass 1 (strided, loads batched 4 deep): validate the tags, unpack the counts
-    uint32_t zp_any = 0;
-    for (int base = 0; base < (int)T; base += 4 * nt) {
-      uint64_t v[4];
-#pragma unroll
-      for (int q = 0; q < 4; q++) {
-        const int i = base + q * nt + tid;
-        v[q] = i < (int)T ? __ldcg(reinterpret_cast<const unsigned long long*>(cntp + i)) : ((uint64_t)tag << 48);
-      }
-#pragma unroll
-      for (int q = 0; q < 4; q++) {
-        const int i = base + q * nt + tid;
-        if (i >= (int)T) continue;
-        // every ticket has bumped `done`, so its entry store is in flight at worst: wait for the tag
-        for (uint32_t spin = 0; (uint32_t)(v[q] >> 48) != tag && spin < (1u << 22); spin++)
-          v[q] = __ldcg(reinterpret_cast<const unsigned long long*>(cntp + i));
-        if ((uint32_t)(v[q] >> 48) != tag) latch_error(st, E_HISTORY, (uint32_t)i);
-        zp_any |= (uint32_t)(v[q] >> 47) & 1u;
-        ev[i] = (uint32_t)(v[q] >> 24) & 0x7FFFFFu;
-        em[i] = (uint32_t)v[q] & 0xFFFFFFu;
-      }
-    }
-    zp_any = __syncthreads_or(zp_any);   // also makes ev[]/em[] visible to the whole CTA
-    // pass 2 (one contiguous chunk per thread): exclusive prefix
-    const int c = ((int)T + nt - 1) / nt;
-    const int lo = min(tid * c, (int)T), hi = min(lo + c, (int)T);
-    uint64_t sum = 0;   // ev << 32 | em  (per-round totals stay below 2^32)
-    for (int i = lo; i < hi; i++) sum += ((uint64_t)ev[i] << 32) | em[i];
-    uint64_t incl = sum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint64_t y = __shfl_up_sync(FULL, incl, d);
-      if (lane >= d) incl += y;
-    }
-    if (lane == 31) s_wtmp[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      const int nw = nt >> 5;
-      const uint64_t w = lane < nw ? s_wtmp[lane] : 0;
-      uint64_t wi = w;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint64_t y = __shfl_up_sync(FULL, wi, d);
-        if (lane >= d) wi += y;
-      }
-      s_wtmp[lane] = wi - w;
-      if (lane == 31) s_wtmp[32] = wi;
-    }
-    __syncthreads();
-    uint64_t run = s_wtmp[warp] + incl - sum;
-    for (int i = lo; i < hi; i++) {
-      const uint32_t ve = ev[i], vm = em[i];   // written in pass 1, visible after the barrier
-      ev[i] = (uint32_t)(run >> 32);
-      em[i] = (uint32_t)run;
-      run += ((uint64_t)ve << 32) | vm;
-    }
-    const uint64_t total = s_wtmp[32];
-    __syncthreads();
-    if (tid == 0) {
-      const uint64_t ev_total = total >> 32, em_total = total & 0xFFFFFFFFull;
-      RoundMeta* m = p.rmeta + row;
-      m->ev_total = ev_total;
-      m->em_total = em_total;
-      m->n_tickets = T;
-      st->next_event += ev_total;
-      st->next_id += em_total;
-      const uint64_t tick = (uint64_t)(now / kTickNs);
-      uint32_t hi_s = (tick + 1 < p.n_tick_off) ? p.tick_off[tick + 1] : p.n_sched;
-      if (hi_s > st->sched_cursor) st->sched_cursor = hi_s;
-      st->inj_count = 0;
-      int64_t next_now = now;
-      if (zp_any == 0) {
-        next_now = now + kTickNs;
-        st->now = next_now;
-        st->time_advanced = 1;
-        if (p.cal) st->cal_release = (((uint32_t)(tick + 1)) & (p.cal_slots - 1)) + 1;
-      } else {
-        st->time_advanced = 0;
-      }
-      st->round = round + 1;
-      st->rounds_run += 1;
-      st->done = 0;
-      st->slot_open = 0;
-      const uint64_t raw_cur = *reinterpret_cast<volatile uint64_t*>(&st->jraw_cursor);
-      if (p.jdiscard || !p.jlevel) {
-        st->journal_drained = st->next_event;
-        st->jraw_drained = raw_cur;
-        st->drain_round = round + 1;
-      }
-      // open the next round's row
-      RoundMeta* nx = p.rmeta + ((uint32_t)(round + 1) & p.hist_mask);
-      nx->round = round + 1;
-      nx->now = next_now;
-      nx->id_base = st->next_id;
-      nx->ev_base = st->next_event;
-      nx->raw_base = raw_cur;
-      nx->n_tickets = 0;
-      nx->ev_total = 0;
-      nx->em_total = 0;
-      __threadfence();
-    }
+    commit_round(p, st, s_wtmp);
     PHASE_MARK(8);
   }
  }   // persistent loop
@@ -1288,6 +1318,7 @@ __global__ void k_journal_expand(Params p, uint64_t r0, uint32_t n_rounds, uint6
     const uint32_t row = (uint32_t)r & p.hist_mask;
     const RoundMeta* m = p.rmeta + row;
     if (m->round != r || t >= m->n_tickets) continue;
+    if (owner_of_ticket(t, p.n_inj_tickets, p.n_servers, p.n_shards) != p.shard_id) continue;   // chunk lives on another shard
     const uint32_t* ev = p.rt_ev + (size_t)row * p.t_max;
     const uint64_t off = ev[t];
     const uint64_t end = (t + 1 < m->n_tickets) ? ev[t + 1] : m->ev_total;
@@ -1345,27 +1376,34 @@ int msk_round_occupancy(int threads, size_t smem) {
   return nb < 1 ? 1 : nb;
 }
 
-// One round = [k_release] k_snapshot, then one persistent k_round grid per
-// window-size class (caps ascending); every ticket is taken by exactly one class.
+// One round = [k_release] k_snapshot | one persistent k_round grid per window-size class
+// (caps ascending; every ticket is taken by exactly one class) | k_commit (sharded runs only;
+// a single GPU commits inside k_round).  `phases` is a bit mask so that a sharded host can
+// put its barriers in between: 1 = release + snapshot, 2 = round kernels, 4 = commit.
 void msk_launch_round(const msd::Params* p, int n_classes, const uint32_t* caps, const int* threads,
                       const int* grids, int with_release, cudaStream_t s, cudaEvent_t before_round,
-                      cudaEvent_t after_round) {
+                      cudaEvent_t after_round, int phases) {
   const uint32_t n_ep = p->n_ep;
-  if (with_release) msd::k_release<<<296, 256, 0, s>>>(*p);
-  const int sb = 256;
-  int sg = (int)((n_ep + sb - 1) / sb);
-  if (sg > 296) sg = 296;
-  if (sg < 1) sg = 1;
-  msd::k_snapshot<<<sg, sb, 0, s>>>(*p);
-  if (before_round) cudaEventRecord(before_round, s);
-  for (int c = n_classes - 1; c >= 0; c--) {   // big windows first
-    const size_t sm = msk_round_smem_bytes(caps[c]);
-    if (c == 0) msd::k_round<0><<<grids[c], threads[c], sm, s>>>(*p, caps[c]);
-    else if (c == 1) msd::k_round<1><<<grids[c], threads[c], sm, s>>>(*p, caps[c]);
-    else if (c == 2) msd::k_round<2><<<grids[c], threads[c], sm, s>>>(*p, caps[c]);
-    else msd::k_round<3><<<grids[c], threads[c], sm, s>>>(*p, caps[c]);
+  if (phases & 1) {
+    if (with_release) msd::k_release<<<296, 256, 0, s>>>(*p);
+    const int sb = 256;
+    int sg = (int)((n_ep + sb - 1) / sb);
+    if (sg > 296) sg = 296;
+    if (sg < 1) sg = 1;
+    msd::k_snapshot<<<sg, sb, 0, s>>>(*p);
   }
-  if (after_round) cudaEventRecord(after_round, s);
+  if (phases & 2) {
+    if (before_round) cudaEventRecord(before_round, s);
+    for (int c = n_classes - 1; c >= 0; c--) {   // big windows first
+      const size_t sm = msk_round_smem_bytes(caps[c]);
+      if (c == 0) msd::k_round<0><<<grids[c], threads[c], sm, s>>>(*p, caps[c]);
+      else if (c == 1) msd::k_round<1><<<grids[c], threads[c], sm, s>>>(*p, caps[c]);
+      else if (c == 2) msd::k_round<2><<<grids[c], threads[c], sm, s>>>(*p, caps[c]);
+      else msd::k_round<3><<<grids[c], threads[c], sm, s>>>(*p, caps[c]);
+    }
+    if (after_round) cudaEventRecord(after_round, s);
+  }
+  if ((phases & 4) && p->n_shards > 1) msd::k_commit<<<1, 512, 0, s>>>(*p);
 }
 
 void msk_journal_expand(const msd::Params* p, uint64_t r0, uint32_t n_rounds, uint64_t first, uint64_t count,
