@@ -216,8 +216,9 @@ int ms_counters(ms_sim* sim, uint64_t out[8]);
  * collectives are two barriers, which the host adapter supplies:
  *   ms_shard_handles  -> opaque blob (MS_SHARD_BLOB_BYTES) describing this shard's memory
  *   ms_shard_connect  <- the blob of every peer (exchanged by the caller, e.g. all_gather)
- *   ms_set_barrier    <- callback(ctx, cuda_stream) that enqueues a cross-shard barrier
- *                        (e.g. a 1-element NCCL all-reduce) on the given CUDA stream
+ *   ms_set_barrier    <- optional callback(ctx, cuda_stream) that enqueues a cross-shard barrier
+ *                        (e.g. a 1-element NCCL all-reduce) on the given CUDA stream; without it
+ *                        the engine uses its own barrier kernel over NVLink peer flags
  * ms_stream returns the CUDA stream the engine launches on.  In sharded runs ms_journal_drain
  * fills only the events of this shard's endpoints; the other slots are 0xFF bytes. */
 #define MS_SHARD_BLOB_BYTES 512

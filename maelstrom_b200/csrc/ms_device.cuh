@@ -21,7 +21,7 @@ constexpr uint8_t  kRemoved  = 0x80;          // endpoint kind after remove-node
 enum : uint32_t {
   E_NONE = 0, E_RING_OVERFLOW = 1, E_WINDOW_OVERFLOW = 2, E_JOURNAL_OVERFLOW = 3,
   E_INVALID_DEST = 4, E_HISTORY = 5, E_VALUE_RANGE = 6, E_MAIL_OVERFLOW = 7,
-  E_CALENDAR_OVERFLOW = 8, E_ID_RANGE = 9
+  E_CALENDAR_OVERFLOW = 8, E_ID_RANGE = 9, E_BARRIER = 10
 };
 
 // Mutable per-simulation scalars, resident in HBM, committed by the last CTA of
@@ -53,7 +53,7 @@ struct DevState {
   uint32_t max_window_seen;
   uint32_t cal_release;      // calendar slot to release before the next round (+1), 0 = none
   uint32_t slot_open;        // k_snapshot ran for this launch slot and the round has not been committed yet
-  uint32_t pad1;
+  uint32_t bar_epoch;        // cross-shard barriers executed so far
   // per-round work lists of the k_round size classes, double-buffered by round parity
   uint32_t cls_count[2][4];
   uint32_t cls_cursor[2][4];
@@ -109,6 +109,7 @@ struct Params {
   uint32_t* tail_sh[8];
   uint32_t* head_sh[8];
   uint64_t* rt_cnt_sh[8];
+  uint32_t* bar_sh[8];       // bar_sh[g][s] = last barrier epoch shard s signalled to shard g
   uint32_t  hist, hist_mask, t_max, n_classes;
   uint32_t* cls_list;        // [2][4][t_max] tickets per size class
   uint32_t  cls_cap[4];      // ascending window capacities of the classes

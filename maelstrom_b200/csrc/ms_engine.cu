@@ -26,6 +26,7 @@ void msk_launch_round(const msd::Params* p, int n_classes, const uint32_t* caps,
                       const int* grids, int with_release, cudaStream_t s, cudaEvent_t before_round,
                       cudaEvent_t after_round, int phases);
 void msk_set_bit(uint32_t* words, size_t word, uint32_t bit, cudaStream_t s);
+void msk_barrier(const msd::Params* p, cudaStream_t s);
 void msk_journal_expand(const msd::Params* p, uint64_t r0, uint32_t n_rounds, uint64_t first, uint64_t count,
                         void* out_ev, void* out_body, cudaStream_t s);
 }
@@ -59,7 +60,8 @@ static const char* dev_error_text(uint32_t code) {
     case E_VALUE_RANGE: return "broadcast value out of range (raise ms_config.n_values): value";
     case E_MAIL_OVERFLOW: return "host mailbox overflow (raise ms_config.mailbox_cap) at endpoint";
     case E_CALENDAR_OVERFLOW: return "timing wheel overflow (raise calendar_slots/calendar_cap): arg";
-    case E_ID_RANGE: return "message id exceeds 2^48 at endpoint";
+    case E_ID_RANGE: return "per-ticket count exceeds the table entry range at ticket";
+    case E_BARRIER: return "cross-shard barrier timed out waiting for shard";
   }
   return "unknown device error";
 }
@@ -131,8 +133,18 @@ struct ms_sim {
   size_t stage_cap = 0;
   std::vector<RoundMeta> hmeta;
   // sharding
-  ms_barrier_fn barrier = nullptr;
+  ms_barrier_fn barrier = nullptr;     // optional user barrier; default = k_barrier over peer memory
   void* barrier_ctx = nullptr;
+  void do_barrier() {
+    if (barrier) barrier(barrier_ctx, (void*)stream);
+    else msk_barrier(&P, stream);
+  }
+  // CUDA graph of a batch of rounds (the launch sequence of a round is always the same; what a
+  // round does is decided on the device).  Re-captured whenever the kernel parameters change.
+  cudaGraphExec_t graph_exec = nullptr;
+  uint64_t graph_rounds = 0;
+  Params graph_P;
+  bool use_graph = true;
   std::vector<void*> peer_ptrs;     // opened IPC mappings
   // timing
   cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -200,6 +212,40 @@ struct ms_sim {
   }
 
   void launch_rounds(uint64_t n) {
+    // batches of rounds are replayed from a CUDA graph: removes the per-launch host cost
+    if (use_graph && !profiling && !barrier && n >= 8) {
+      if (graph_exec && (graph_rounds != n || memcmp(&graph_P, &P, sizeof(Params)) != 0)) {
+        cudaGraphExecDestroy(graph_exec);
+        graph_exec = nullptr;
+      }
+      if (!graph_exec) {
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+          launch_rounds_direct(n);
+          if (cudaStreamEndCapture(stream, &graph) == cudaSuccess && graph &&
+              cudaGraphInstantiate(&graph_exec, graph, 0) == cudaSuccess) {
+            graph_rounds = n;
+            memcpy(&graph_P, &P, sizeof(Params));
+          } else {
+            graph_exec = nullptr;
+            use_graph = false;          // fall back to direct launches for good
+          }
+          if (graph) cudaGraphDestroy(graph);
+          cudaGetLastError();
+        } else {
+          use_graph = false;
+          cudaGetLastError();
+        }
+      }
+      if (graph_exec && cudaGraphLaunch(graph_exec, stream) == cudaSuccess) {
+        launches += n * ((use_calendar ? 2 : 1) + n_classes + (P.n_shards > 1 ? 3 : 0));
+        return;
+      }
+    }
+    launch_rounds_direct(n);
+  }
+
+  void launch_rounds_direct(uint64_t n) {
     for (uint64_t i = 0; i < n; i++) {
       cudaEvent_t a = nullptr, b = nullptr;
       if (profiling) {
@@ -217,17 +263,23 @@ struct ms_sim {
       for (int c = 0; c < n_classes; c++) grids[c] = std::max(1, std::min(class_grid[c], T));
       if (P.n_shards <= 1) {
         msk_launch_round(&P, n_classes, class_cap, class_threads, grids, use_calendar ? 1 : 0, stream, a, b, 7);
-        launches += (use_calendar ? 2 : 1) + n_classes;
+        if (!capturing()) launches += (use_calendar ? 2 : 1) + n_classes;
       } else {
         // sharded: snapshot | barrier | round kernels (peer writes) | barrier | commit
         msk_launch_round(&P, n_classes, class_cap, class_threads, grids, use_calendar ? 1 : 0, stream, a, b, 1);
-        barrier(barrier_ctx, (void*)stream);
+        do_barrier();
         msk_launch_round(&P, n_classes, class_cap, class_threads, grids, 0, stream, a, b, 2);
-        barrier(barrier_ctx, (void*)stream);
+        do_barrier();
         msk_launch_round(&P, n_classes, class_cap, class_threads, grids, 0, stream, a, b, 4);
-        launches += (use_calendar ? 2 : 1) + n_classes + 1;
+        if (!capturing()) launches += (use_calendar ? 2 : 1) + n_classes + 3;
       }
     }
+  }
+
+  bool capturing() {
+    cudaStreamCaptureStatus st_ = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &st_);
+    return st_ != cudaStreamCaptureStatusNone;
   }
 
   void collect_profile() {   // call after the stream is synchronised
@@ -546,6 +598,8 @@ static int build_sim(ms_sim* s, const ms_config* in) {
     P.tail_sh[c.shard_id] = P.tail;
     P.head_sh[c.shard_id] = P.head;
     P.rt_cnt_sh[c.shard_id] = P.rt_cnt;
+    for (int g = 0; g < 8; g++) P.bar_sh[g] = nullptr;
+    if ((rc = s->dalloc(&P.bar_sh[c.shard_id], 64))) return rc;
     CK(cudaStreamSynchronize(s->stream));
   }
   CK(cudaStreamSynchronize(s->stream));
@@ -585,6 +639,7 @@ void ms_destroy(ms_sim* s) {
   if (s->stage_body) cudaFree(s->stage_body);
   if (s->d_sched) cudaFree(s->d_sched);
   if (s->d_tick_off) cudaFree(s->d_tick_off);
+  if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
   for (cudaEvent_t e : s->prof_ev) if (e) cudaEventDestroy(e);
   if (s->t0) cudaEventDestroy(s->t0);
   if (s->t1) cudaEventDestroy(s->t1);
@@ -683,7 +738,6 @@ static int step_locked(ms_sim* s, uint64_t n_rounds, int64_t stop) {
   cudaSetDevice(s->device);
   int rc;
   if (s->P.n_shards > 1) {
-    if (!s->barrier) { set_err("sharded simulation: call ms_set_barrier first"); return MS_ERR_ARG; }
     for (uint32_t g = 0; g < s->P.n_shards; g++)
       if (!s->P.ring_sh[g]) { set_err("sharded simulation: ms_shard_connect every peer first"); return MS_ERR_ARG; }
   }
@@ -892,7 +946,7 @@ int ms_counters(ms_sim* s, uint64_t out[8]) {
 struct ShardBlob {   // MS_SHARD_BLOB_BYTES
   uint32_t magic, shard_id, n_shards, t_max;
   uint32_t max_endpoints, ring_cap, hist, pad;
-  cudaIpcMemHandle_t ring, tail, head, rt_cnt;
+  cudaIpcMemHandle_t ring, tail, head, rt_cnt, bar;
 };
 static_assert(sizeof(ShardBlob) <= MS_SHARD_BLOB_BYTES, "blob too large");
 
@@ -908,6 +962,7 @@ int ms_shard_handles(ms_sim* s, void* blob_out) {
   CK(cudaIpcGetMemHandle(&b.tail, s->P.tail));
   CK(cudaIpcGetMemHandle(&b.head, s->P.head));
   CK(cudaIpcGetMemHandle(&b.rt_cnt, s->P.rt_cnt));
+  CK(cudaIpcGetMemHandle(&b.bar, s->P.bar_sh[s->P.shard_id]));
   memset(blob_out, 0, MS_SHARD_BLOB_BYTES);
   memcpy(blob_out, &b, sizeof b);
   return MS_OK;
@@ -934,6 +989,8 @@ int ms_shard_connect(ms_sim* s, uint32_t peer, const void* blob) {
   s->peer_ptrs.push_back(ptr); s->P.head_sh[peer] = (uint32_t*)ptr;
   CK(cudaIpcOpenMemHandle(&ptr, b.rt_cnt, cudaIpcMemLazyEnablePeerAccess));
   s->peer_ptrs.push_back(ptr); s->P.rt_cnt_sh[peer] = (uint64_t*)ptr;
+  CK(cudaIpcOpenMemHandle(&ptr, b.bar, cudaIpcMemLazyEnablePeerAccess));
+  s->peer_ptrs.push_back(ptr); s->P.bar_sh[peer] = (uint32_t*)ptr;
   return MS_OK;
 }
 

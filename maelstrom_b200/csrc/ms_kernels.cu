@@ -276,6 +276,32 @@ __device__ __forceinline__ void emit_one(const Params& p, DevState* st, const Ne
 
 __global__ void k_set_bit(uint32_t* words, size_t word, uint32_t bit) { atomicOr(words + word, 1u << bit); }
 
+// ------------------------------------------------------------------ k_barrier (sharded runs)
+// Cross-GPU barrier over NVLink peer memory: every shard stores the epoch into its slot of
+// every peer's flag array, then waits until all peers have stored it into its own.  Kernels
+// of one shard are stream-ordered around it, so everything a shard wrote into peer inbox
+// rings before the barrier is visible to the owner after it.
+__global__ void k_barrier(Params p) {
+  __shared__ uint32_t s_epoch;
+  // the epoch lives on the device so that the launch sequence can be replayed from a CUDA graph;
+  // all shards execute the same number of barriers, so their counters agree
+  if (threadIdx.x == 0) s_epoch = ++p.st->bar_epoch;
+  __syncthreads();
+  const uint32_t epoch = s_epoch;
+  const uint32_t g = threadIdx.x;
+  if (g >= p.n_shards) return;
+  __threadfence_system();
+  *reinterpret_cast<volatile uint32_t*>(&p.bar_sh[g][p.shard_id]) = epoch;
+  __threadfence_system();
+  const volatile uint32_t* mine = p.bar_sh[p.shard_id] + g;
+  uint32_t spins = 0;
+  while ((int32_t)(*mine - epoch) < 0) {
+    if (++spins > (1u << 27)) { latch_error(p.st, E_BARRIER, g); break; }   // a peer died: do not hang the GPU
+    __nanosleep(40);
+  }
+  __threadfence_system();
+}
+
 // ------------------------------------------------------------------ k_snapshot
 // head <- limit, limit <- tail, and sorts every ticket into the work list of the
 // k_round size class its window fits.  Lists are double-buffered
@@ -1405,6 +1431,8 @@ void msk_launch_round(const msd::Params* p, int n_classes, const uint32_t* caps,
   }
   if ((phases & 4) && p->n_shards > 1) msd::k_commit<<<1, 512, 0, s>>>(*p);
 }
+
+void msk_barrier(const msd::Params* p, cudaStream_t s) { msd::k_barrier<<<1, 32, 0, s>>>(*p); }
 
 void msk_journal_expand(const msd::Params* p, uint64_t r0, uint32_t n_rounds, uint64_t first, uint64_t count,
                         void* out_ev, void* out_body, cudaStream_t s) {

@@ -2,8 +2,9 @@
 index range.  The engine's kernels deliver cross-shard messages
 by writing straight into the owner's inbox rings over NVLink peer memory (CUDA IPC,
 include/maelstrom_b200.h "multi-GPU"); this module only supplies the plumbing the C ABI
-asks for: the exchange of the IPC blobs and the per-round barrier (a 1-element NCCL
-all-reduce enqueued on the engine's CUDA stream)."""
+asks for: the exchange of the IPC blobs and, optionally, a per-round NCCL barrier (a
+1-element all-reduce enqueued on the engine's CUDA stream) instead of the engine's own
+peer-memory barrier kernel."""
 import ctypes as C
 
 import numpy as np
@@ -50,7 +51,7 @@ def exchange_blobs(local_blob, group=None):
 class ShardedSim:
     """engine.Sim for this rank's shard + the torch.distributed plumbing."""
 
-    def __init__(self, n_nodes, group=None, device=None, **kw):
+    def __init__(self, n_nodes, group=None, device=None, nccl_barrier=False, **kw):
         import torch
         import torch.distributed as dist
         self.group = group
@@ -74,7 +75,9 @@ class ShardedSim:
                 dist.all_reduce(self._flag, group=group)
 
         self._cb = _lib.BARRIER_FN(_barrier)          # keep a reference: C holds the pointer
-        self.sim._chk(L.ms_set_barrier(h, self._cb, None))
+        if nccl_barrier:
+            self.sim._chk(L.ms_set_barrier(h, self._cb, None))
+        # default: the engine's own k_barrier over NVLink peer flags (no host round trip per round)
         dist.barrier(group)
 
     def __getattr__(self, name):                      # add_endpoint, schedule, run, step, ...
