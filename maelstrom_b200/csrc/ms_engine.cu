@@ -238,7 +238,7 @@ struct ms_sim {
         }
       }
       if (graph_exec && cudaGraphLaunch(graph_exec, stream) == cudaSuccess) {
-        launches += n * ((use_calendar ? 2 : 1) + n_classes + (P.n_shards > 1 ? 3 : 0));
+        launches += n * ((use_calendar ? 2 : 1) + n_classes + (P.n_shards > 1 ? (use_calendar ? 4 : 3) : 0));
         return;
       }
     }
@@ -262,16 +262,20 @@ struct ms_sim {
       int grids[4];
       for (int c = 0; c < n_classes; c++) grids[c] = std::max(1, std::min(class_grid[c], T));
       if (P.n_shards <= 1) {
-        msk_launch_round(&P, n_classes, class_cap, class_threads, grids, use_calendar ? 1 : 0, stream, a, b, 7);
+        msk_launch_round(&P, n_classes, class_cap, class_threads, grids, use_calendar ? 1 : 0, stream, a, b, 15);
         if (!capturing()) launches += (use_calendar ? 2 : 1) + n_classes;
       } else {
-        // sharded: snapshot | barrier | round kernels (peer writes) | barrier | commit
-        msk_launch_round(&P, n_classes, class_cap, class_threads, grids, use_calendar ? 1 : 0, stream, a, b, 1);
+        // sharded: [release (peer writes) | barrier] snapshot | barrier | round kernels (peer writes) | barrier | commit
+        if (use_calendar) {
+          msk_launch_round(&P, n_classes, class_cap, class_threads, grids, 1, stream, a, b, 1);
+          do_barrier();   // released messages must be in the owners' rings before they snapshot
+        }
+        msk_launch_round(&P, n_classes, class_cap, class_threads, grids, 0, stream, a, b, 8);
         do_barrier();
         msk_launch_round(&P, n_classes, class_cap, class_threads, grids, 0, stream, a, b, 2);
         do_barrier();
         msk_launch_round(&P, n_classes, class_cap, class_threads, grids, 0, stream, a, b, 4);
-        if (!capturing()) launches += (use_calendar ? 2 : 1) + n_classes + 3;
+        if (!capturing()) launches += (use_calendar ? 2 : 1) + n_classes + (use_calendar ? 4 : 3);
       }
     }
   }

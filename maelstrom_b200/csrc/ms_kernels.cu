@@ -1405,13 +1405,13 @@ int msk_round_occupancy(int threads, size_t smem) {
 // One round = [k_release] k_snapshot | one persistent k_round grid per window-size class
 // (caps ascending; every ticket is taken by exactly one class) | k_commit (sharded runs only;
 // a single GPU commits inside k_round).  `phases` is a bit mask so that a sharded host can
-// put its barriers in between: 1 = release + snapshot, 2 = round kernels, 4 = commit.
+// put its barriers in between: 1 = timing-wheel release, 8 = snapshot, 2 = round kernels, 4 = commit.
 void msk_launch_round(const msd::Params* p, int n_classes, const uint32_t* caps, const int* threads,
                       const int* grids, int with_release, cudaStream_t s, cudaEvent_t before_round,
                       cudaEvent_t after_round, int phases) {
   const uint32_t n_ep = p->n_ep;
-  if (phases & 1) {
-    if (with_release) msd::k_release<<<296, 256, 0, s>>>(*p);
+  if ((phases & 1) && with_release) msd::k_release<<<296, 256, 0, s>>>(*p);
+  if (phases & 8) {
     const int sb = 256;
     int sg = (int)((n_ep + sb - 1) / sb);
     if (sg > 296) sg = 296;
