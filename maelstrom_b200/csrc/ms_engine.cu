@@ -24,7 +24,7 @@ size_t msk_round_smem_bytes(uint32_t cap);
 int msk_round_occupancy(int threads, size_t smem);
 void msk_launch_round(const msd::Params* p, int n_classes, const uint32_t* caps, const int* threads,
                       const int* grids, int with_release, cudaStream_t s, cudaEvent_t before_round,
-                      cudaEvent_t after_round, int phases);
+                      cudaEvent_t after_round, int phases, const cudaStream_t* aux, const cudaEvent_t* aux_ev);
 void msk_set_bit(uint32_t* words, size_t word, uint32_t bit, cudaStream_t s);
 void msk_barrier(const msd::Params* p, cudaStream_t s);
 void msk_journal_expand(const msd::Params* p, uint64_t r0, uint32_t n_rounds, uint64_t first, uint64_t count,
@@ -141,6 +141,8 @@ struct ms_sim {
   }
   // CUDA graph of a batch of rounds (the launch sequence of a round is always the same; what a
   // round does is decided on the device).  Re-captured whenever the kernel parameters change.
+  cudaStream_t aux_streams[4] = {nullptr, nullptr, nullptr, nullptr};   // size classes run concurrently
+  cudaEvent_t aux_events[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaGraphExec_t graph_exec = nullptr;
   uint64_t graph_rounds = 0;
   Params graph_P;
@@ -262,19 +264,19 @@ struct ms_sim {
       int grids[4];
       for (int c = 0; c < n_classes; c++) grids[c] = std::max(1, std::min(class_grid[c], T));
       if (P.n_shards <= 1) {
-        msk_launch_round(&P, n_classes, class_cap, class_threads, grids, use_calendar ? 1 : 0, stream, a, b, 15);
+        msk_launch_round(&P, n_classes, class_cap, class_threads, grids, use_calendar ? 1 : 0, stream, a, b, 15, aux_streams, aux_events);
         if (!capturing()) launches += (use_calendar ? 2 : 1) + n_classes;
       } else {
         // sharded: [release (peer writes) | barrier] snapshot | barrier | round kernels (peer writes) | barrier | commit
         if (use_calendar) {
-          msk_launch_round(&P, n_classes, class_cap, class_threads, grids, 1, stream, a, b, 1);
+          msk_launch_round(&P, n_classes, class_cap, class_threads, grids, 1, stream, a, b, 1, aux_streams, aux_events);
           do_barrier();   // released messages must be in the owners' rings before they snapshot
         }
-        msk_launch_round(&P, n_classes, class_cap, class_threads, grids, 0, stream, a, b, 8);
+        msk_launch_round(&P, n_classes, class_cap, class_threads, grids, 0, stream, a, b, 8, aux_streams, aux_events);
         do_barrier();
-        msk_launch_round(&P, n_classes, class_cap, class_threads, grids, 0, stream, a, b, 2);
+        msk_launch_round(&P, n_classes, class_cap, class_threads, grids, 0, stream, a, b, 2, aux_streams, aux_events);
         do_barrier();
-        msk_launch_round(&P, n_classes, class_cap, class_threads, grids, 0, stream, a, b, 4);
+        msk_launch_round(&P, n_classes, class_cap, class_threads, grids, 0, stream, a, b, 4, aux_streams, aux_events);
         if (!capturing()) launches += (use_calendar ? 2 : 1) + n_classes + (use_calendar ? 4 : 3);
       }
     }
@@ -464,6 +466,8 @@ static int build_sim(ms_sim* s, const ms_config* in) {
   s->device = c.device;
   CK(cudaSetDevice(s->device));
   CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  for (int k = 0; k < 4; k++) CK(cudaStreamCreateWithFlags(&s->aux_streams[k], cudaStreamNonBlocking));
+  for (int k = 0; k < 5; k++) CK(cudaEventCreateWithFlags(&s->aux_events[k], cudaEventDisableTiming));
 
   Params& P = s->P;
   memset(&P, 0, sizeof P);
@@ -644,6 +648,8 @@ void ms_destroy(ms_sim* s) {
   if (s->d_sched) cudaFree(s->d_sched);
   if (s->d_tick_off) cudaFree(s->d_tick_off);
   if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+  for (int k = 0; k < 4; k++) if (s->aux_streams[k]) cudaStreamDestroy(s->aux_streams[k]);
+  for (int k = 0; k < 5; k++) if (s->aux_events[k]) cudaEventDestroy(s->aux_events[k]);
   for (cudaEvent_t e : s->prof_ev) if (e) cudaEventDestroy(e);
   if (s->t0) cudaEventDestroy(s->t0);
   if (s->t1) cudaEventDestroy(s->t1);

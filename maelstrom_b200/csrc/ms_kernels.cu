@@ -318,16 +318,32 @@ __global__ void k_snapshot(Params p) {
   const uint32_t par = (uint32_t)st->round & 1u;
   const uint32_t stride = gridDim.x * blockDim.x;
   const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t row = (uint32_t)st->round & p.hist_mask;
+  const uint64_t empty_entry = (uint64_t)(((uint32_t)st->round & 0x7FFFu) + 1u) << 48;   // tag | 0 events | 0 emissions
+  uint32_t n_empty = 0;
   for (uint32_t e = gid; e < p.n_ep; e += stride) {
     if (owner_of(e, p.n_servers, p.n_shards) != p.shard_id) continue;   // another shard's endpoint
     const uint32_t h = p.limit[e], l = p.tail[e];
     p.head[e] = h;
     p.limit[e] = l;
     const uint32_t n = (p.kind[e] == kRemoved) ? 0u : l - h;
+    if (n == 0) {
+      // nothing to receive, hence nothing to emit: the ticket is finished right here
+      const uint32_t t = p.n_inj_tickets + e;
+      p.rt_chunk[(size_t)row * p.t_max + t] = 0;
+      __stcg(reinterpret_cast<unsigned long long*>(p.rt_cnt + (size_t)row * p.t_max + t), (unsigned long long)empty_entry);
+      n_empty++;
+      continue;
+    }
     const uint32_t c = class_of(p, n);
     const uint32_t k = atomicAdd(&st->cls_count[par][c], 1u);
     p.cls_list[((size_t)par * 4 + c) * p.t_max + k] = p.n_inj_tickets + e;
   }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) n_empty += __shfl_xor_sync(FULL, n_empty, d);
+  // the injector tickets always run in k_round, so some ticket still finishes after this
+  // kernel and commits the round once `done` reaches the ticket count
+  if ((threadIdx.x & 31) == 0 && n_empty) atomicAdd(&st->done, n_empty);
   if (gid < p.n_inj_tickets && p.shard_id == 0) {   // injector slices run in the widest class (shard 0)
     const uint32_t c = p.n_classes - 1;
     const uint32_t k = atomicAdd(&st->cls_count[par][c], 1u);
@@ -1408,7 +1424,7 @@ int msk_round_occupancy(int threads, size_t smem) {
 // put its barriers in between: 1 = timing-wheel release, 8 = snapshot, 2 = round kernels, 4 = commit.
 void msk_launch_round(const msd::Params* p, int n_classes, const uint32_t* caps, const int* threads,
                       const int* grids, int with_release, cudaStream_t s, cudaEvent_t before_round,
-                      cudaEvent_t after_round, int phases) {
+                      cudaEvent_t after_round, int phases, const cudaStream_t* aux, const cudaEvent_t* aux_ev) {
   const uint32_t n_ep = p->n_ep;
   if ((phases & 1) && with_release) msd::k_release<<<296, 256, 0, s>>>(*p);
   if (phases & 8) {
@@ -1420,13 +1436,22 @@ void msk_launch_round(const msd::Params* p, int n_classes, const uint32_t* caps,
   }
   if (phases & 2) {
     if (before_round) cudaEventRecord(before_round, s);
+    // the size classes are independent of each other: run them concurrently (fork / join on
+    // auxiliary streams; captured into the round graph as parallel branches)
+    const bool fork = aux != nullptr && n_classes > 1;
+    if (fork) cudaEventRecord(aux_ev[0], s);
     for (int c = n_classes - 1; c >= 0; c--) {   // big windows first
       const size_t sm = msk_round_smem_bytes(caps[c]);
-      if (c == 0) msd::k_round<0><<<grids[c], threads[c], sm, s>>>(*p, caps[c]);
-      else if (c == 1) msd::k_round<1><<<grids[c], threads[c], sm, s>>>(*p, caps[c]);
-      else if (c == 2) msd::k_round<2><<<grids[c], threads[c], sm, s>>>(*p, caps[c]);
-      else msd::k_round<3><<<grids[c], threads[c], sm, s>>>(*p, caps[c]);
+      cudaStream_t sc = (fork && c != n_classes - 1) ? aux[c] : s;
+      if (sc != s) cudaStreamWaitEvent(sc, aux_ev[0], 0);
+      if (c == 0) msd::k_round<0><<<grids[c], threads[c], sm, sc>>>(*p, caps[c]);
+      else if (c == 1) msd::k_round<1><<<grids[c], threads[c], sm, sc>>>(*p, caps[c]);
+      else if (c == 2) msd::k_round<2><<<grids[c], threads[c], sm, sc>>>(*p, caps[c]);
+      else msd::k_round<3><<<grids[c], threads[c], sm, sc>>>(*p, caps[c]);
+      if (sc != s) cudaEventRecord(aux_ev[1 + c], sc);
     }
+    if (fork)
+      for (int c = 0; c < n_classes - 1; c++) cudaStreamWaitEvent(s, aux_ev[1 + c], 0);
     if (after_round) cudaEventRecord(after_round, s);
   }
   if ((phases & 4) && p->n_shards > 1) msd::k_commit<<<1, 512, 0, s>>>(*p);
