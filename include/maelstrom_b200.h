@@ -138,7 +138,7 @@ typedef struct ms_config {
   uint32_t threads_per_node; /* CTA size of the round kernel (0 = auto) */
   uint32_t n_shards;         /* GPUs the endpoints are sharded over (0/1 = single GPU), <= 8 */
   uint32_t shard_id;         /* this process's shard */
-  uint32_t reserved[6];      /* [0] = rounds of id history to keep (0 = default) */
+  uint32_t reserved[6];      /* [0] = rounds of id history to keep (0 = default); [1] = 1: replay round batches from a CUDA graph */
 } ms_config;
 
 typedef struct ms_sim ms_sim;

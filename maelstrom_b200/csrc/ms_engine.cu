@@ -146,7 +146,8 @@ struct ms_sim {
   cudaGraphExec_t graph_exec = nullptr;
   uint64_t graph_rounds = 0;
   Params graph_P;
-  bool use_graph = true;
+  bool use_graph = false;   // opt-in (ms_config.reserved[1] = 1): instantiating the forked graph costs more
+                            // than it saves unless the kernel parameters stay fixed for many batches
   std::vector<void*> peer_ptrs;     // opened IPC mappings
   // timing
   cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -491,6 +492,7 @@ static int build_sim(ms_sim* s, const ms_config* in) {
   P.n_ep = c.n_nodes;
   P.n_inj_tickets = 8;
   P.max_window = c.max_window;
+  s->use_graph = c.reserved[1] == 1;
   P.n_shards = c.n_shards;
   P.shard_id = c.shard_id;
   {
