@@ -229,3 +229,32 @@ def test_large_windows_all_size_classes(per_tick, max_window):
     assert_same_journal(g, o)
     c = g.counters()
     assert c["max_window"] > 512
+
+
+def test_drain_into_pinned_memory_in_pieces():
+    # ms_journal_drain into a page-locked caller buffer (what bench.py's e2e leg does), in two
+    # pieces that split a round; the concatenation must equal the oracle
+    import torch
+    n = 25
+    g, o = make_pair(n, topology="grid", n_values=1024, ring_cap=1024, max_window=512, journal_cap_log2=20)
+
+    def scenario(s, body):
+        cs = [s.add_endpoint("c%d" % i) for i in range(2)]
+        ops, nv = random_broadcast_ops(n, cs, n_ticks=5, per_tick=40, seed=4)
+        s.schedule(ops)
+        s.run(7_000_000)
+
+    both(g, o, scenario)
+    ev_o, _ = o.journal()
+    total = len(ev_o)
+    half = total // 2
+    from maelstrom_b200._lib import EVENT_DTYPE
+    pinned = torch.empty(half * 32, dtype=torch.uint8, pin_memory=True)
+    got = g.drain_into(pinned.data_ptr(), half)
+    assert got == half
+    first = np.frombuffer(pinned.numpy().tobytes(), dtype=EVENT_DTYPE)
+    rest, _ = g.drain(bodies=False)
+    ev = np.concatenate([first, rest])
+    assert len(ev) == total
+    for f in ("event_id", "time_ns", "msg_id", "src", "dest"):
+        assert np.array_equal(ev[f], ev_o[f]), f
