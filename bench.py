@@ -160,7 +160,7 @@ def reference_arm(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_tick = args.cpu_values
+    per_tick = max(16, args.cpu_values // 24)     # per replica and step: keeps K+W steps within a few minutes
     # calibrate: 1 value = 12 035 messages; the single-thread port does a few M msgs/s
     vals, times = [], []
     for _ in range(args.warmup):
@@ -389,7 +389,12 @@ def gpu_arm(args, rank, world, local_rank):
                                    "2 barriers per round" % world) if world > 1 else "single GPU",
                    "published_reference": "6e4 msgs/s, 48-way Xeon (README.md:39-42), different hardware"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None,
+                     "frac": achieved / peak,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of the four size-class launches of one
+                     # round, ncu --set full at this configuration (profiles/r1e_summary.md)
+                     "traffic": 532.5e6 if (V == 32768 and lat == 0 and world == 1) else None,
+                     "traffic_unit": "bytes per round (one launch of each size class)",
+                     "algorithmic_bytes_per_round": alg_bytes / max(k_launches, 1),
                      "kernel": "msd::k_round", "launches": k_launches, "avg_launch_us": 1e3 * k_ms / max(k_launches, 1),
                      "algorithmic_bytes_per_msg": ALG_SEND_B + ALG_RECV_B, "peak_source": peak_src},
         "gpu_launches": launches,
@@ -397,7 +402,11 @@ def gpu_arm(args, rank, world, local_rank):
     }
     if e2e:
         line["e2e"] = {"value": e2e_msgs / e2e_s, "unit": "msgs/s", "h2d_bytes_per_step": e2e["h2d"],
-                       "d2h_bytes_per_step": e2e["d2h"]}
+                       "d2h_bytes_per_step": e2e["d2h"],
+                       "note": ("host op buffers in every step; the full journal (64 B/message) drained to pinned host "
+                                "memory every step: PCIe-bound") if world == 1 else
+                               ("host op buffers in every step; per step only the 9 net-stats counters are read back: "
+                                "sharded runs drain the journal per shard, not measured here")}
     if world == 1 and not args.no_cpu:
         t0 = time.perf_counter()
         v, msgs, wall = cpu_run(args.cpu_values, 1, 1)
@@ -422,7 +431,7 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--journal-cap-log2", type=int, default=26)
     ap.add_argument("--calendar-cap", type=int, default=1 << 20)
-    ap.add_argument("--cpu-values", type=int, default=512)
+    ap.add_argument("--cpu-values", type=int, default=1536)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--phases", action="store_true", help="print per-phase cycle counts of the round kernel (stderr)")
