@@ -98,8 +98,16 @@ class Sim:
 
     def recv(self, endpoint, timeout_ns=0):
         out = np.zeros(1, dtype=MSG_DTYPE)
-        rc = self._chk(self.L.ms_recv(self.h, endpoint, timeout_ns, out.ctypes.data))
-        return out[0] if rc == 1 else None
+        deadline = self.now + timeout_ns
+        while True:
+            rc = self.L.ms_recv(self.h, endpoint, max(0, deadline - self.now), out.ctypes.data)
+            if rc == -5 and self.cfg.journal_level and not self.cfg.journal_discard:
+                # MS_ERR_CAPACITY: the device wants the journal drained before it runs more rounds
+                # (nothing was executed); stash the events and wait on
+                self._stash.append(self._drain_now())
+                continue
+            self._chk(rc)
+            return out[0] if rc == 1 else None
 
     def schedule(self, ops):
         ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
@@ -107,7 +115,11 @@ class Sim:
 
     # time ----------------------------------------------------------------
     def step(self, n=1):
-        return self._chk(self.L.ms_step(self.h, n))
+        rc = self.L.ms_step(self.h, n)
+        if rc == -5 and self.cfg.journal_level and not self.cfg.journal_discard and n == 1:
+            self._stash.append(self._drain_now())     # see recv()
+            rc = self.L.ms_step(self.h, n)
+        return self._chk(rc)
 
     def run_raw(self, until_ns):
         """ms_run as is: 0 = reached until_ns, 1 = journal ring half full (drain, then call again)."""
