@@ -417,6 +417,10 @@ static int build_sim(ms_sim* s, const ms_config* in) {
     set_err("bad workload/topology/latency_dist");
     return MS_ERR_ARG;
   }
+  if (c.workload == MS_W_GSET) {
+    set_err("workload g-set is not built yet (SURVEY.md section 8f NEXT-4); the oracle restates it (oracle/oracle.cpp)");
+    return MS_ERR_ARG;
+  }
   if (c.latency_dist != MS_DIST_CONSTANT && c.latency_mean_ms == 0) {
     // (exponential-distribution (/ 0)) divides by zero; (integer-distribution 0 0) is empty (net.clj:76-77)
     set_err("latency mean 0 is only valid with the constant distribution");

@@ -191,6 +191,8 @@ struct Endpoint {
   uint32_t next_msg_id = 0;             // echo.rb:8,12
   std::set<uint32_t> values;            // broadcast @messages / g-set @set
   std::vector<uint32_t> neighbors;      // broadcast @neighbors (topology)
+  bool initialized = false;             // node.rb:22-36: periodic tasks start after init
+  int64_t next_fire = 0;                // g-set: next run of the `every 5` task (g_set.rb:34)
 };
 
 }  // namespace
@@ -212,6 +214,8 @@ struct or_sim {
   std::vector<or_op> schedule;
   size_t sched_cursor = 0;
   std::map<uint64_t, std::vector<uint32_t>> snapshots; // read_ok msg id -> set contents
+  std::map<uint64_t, std::vector<uint32_t>> gset_snaps; // replicate_full p1 handle -> value list
+  uint64_t next_snap = 1;
   uint64_t client_replies = 0;
   std::string error;
   uint64_t stats[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -331,6 +335,60 @@ struct or_sim {
     }
   }
 
+  // g-set node (demo/ruby/g_set.rb:13-39)
+  void node_gset(uint32_t e, const or_msg& m, std::vector<Emit>& out) {
+    Endpoint& ep = eps[e];
+    if (m.flags & OR_F_REPLY) return;                       // node.rb:159-164
+    switch (m.type) {
+      case OR_T_INIT:                                       // node.rb:22-36: reply, then start the periodic task,
+        ep.initialized = true;                              // whose first run is immediate (node.rb:129-137)
+        ep.next_fire = now;
+        out.push_back(Emit(reply_to(m, OR_T_INIT_OK)));
+        break;
+      case OR_T_ADD:                                        // g_set.rb:17-21
+        if (m.p0 >= cfg.n_values) { error = "g-set element out of range"; return; }
+        ep.values.insert(m.p0);
+        out.push_back(Emit(reply_to(m, OR_T_ADD_OK)));
+        break;
+      case OR_T_READ: {                                     // g_set.rb:13-15
+        or_msg r = reply_to(m, OR_T_READ_OK);
+        r.p0 = (uint32_t)ep.values.size();
+        Emit em(r);
+        em.has_snap = true;
+        em.snap.assign(ep.values.begin(), ep.values.end());
+        out.push_back(em);
+        break;
+      }
+      case OR_T_REPLICATE_ONE:                              // g_set.rb:24-26
+        if (m.p0 >= cfg.n_values) { error = "g-set element out of range"; return; }
+        ep.values.insert(m.p0);
+        break;
+      case OR_T_REPLICATE_FULL: {                           // g_set.rb:29-31  @set |= value
+        auto it = gset_snaps.find(m.p1);
+        if (it != gset_snaps.end()) ep.values.insert(it->second.begin(), it->second.end());
+        break;
+      }
+      default: node_common_unknown(m, out);
+    }
+  }
+
+  // g-set periodic task (g_set.rb:34-39): every interval, send the whole set to every other node.
+  // Evaluated at the start of the node's step of a round, before its receives.
+  void gset_timer(uint32_t e, std::vector<Emit>& out) {
+    Endpoint& ep = eps[e];
+    if (!ep.initialized || now < ep.next_fire) return;
+    const uint64_t handle = next_snap++;
+    gset_snaps[handle].assign(ep.values.begin(), ep.values.end());
+    for (uint32_t other = 0; other < cfg.n_nodes; other++) {
+      if (other == e || !eps[other].live) continue;         // node.rb:104-108 other_node_ids
+      or_msg g; std::memset(&g, 0, sizeof g);
+      g.src = e; g.dest = other; g.type = OR_T_REPLICATE_FULL;
+      g.p0 = (uint32_t)ep.values.size(); g.p1 = handle;
+      out.push_back(Emit(g));
+    }
+    ep.next_fire += (int64_t)cfg.gset_interval_ms * kTickNs;
+  }
+
   bool run_round() {
     std::vector<Envelope> pending;
     // (1) injector
@@ -353,6 +411,7 @@ struct or_sim {
       Endpoint& ep = eps[e];
       if (!ep.live) continue;
       out.clear();
+      if (cfg.workload == OR_W_GSET && ep.kind == OR_KIND_SERVER) gset_timer(e, out);
       while (!ep.q.empty() && ep.q.top().m.deadline_ns <= now) {   // net.clj:228-229,236-238
         const or_msg m = ep.q.top().m;
         ep.q.pop();
@@ -371,6 +430,7 @@ struct or_sim {
           default:
             if (cfg.workload == OR_W_ECHO) node_echo(e, m, out);
             else if (cfg.workload == OR_W_BROADCAST) node_broadcast(e, m, out);
+            else if (cfg.workload == OR_W_GSET) node_gset(e, m, out);
             else { error = "workload not implemented in oracle"; return false; }
         }
         if (!error.empty()) return false;
@@ -399,6 +459,7 @@ or_sim* or_create(const or_config* cfg) {
   or_sim* s = new or_sim();
   s->cfg = *cfg;
   if (s->cfg.n_values == 0) s->cfg.n_values = 1u << 20;
+  if (s->cfg.gset_interval_ms == 0) s->cfg.gset_interval_ms = 5000;   // g_set.rb:34
   s->loss_thresh = loss_threshold(cfg->p_loss);
   s->eps.resize(cfg->n_nodes);
   for (uint32_t i = 0; i < cfg->n_nodes; i++) {

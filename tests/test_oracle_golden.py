@@ -206,3 +206,61 @@ def test_read_snapshot_and_unknown_type_error():
     s.send(c, 2, O.body("add", msg_id=3, p0=1))            # not a broadcast-node handler
     r = s.recv(c, 1_000_000_000)
     assert r["type"] == O.T["error"] and r["p0"] == 10 and r["in_reply_to"] == 3   # errors.edn code 10
+
+
+# ------------------------------------------------------------------ g-set (oracle only; engine: next round)
+def gset_cluster(n=5, **kw):
+    s = O.Sim(n, workload=O.W_GSET, n_values=256, **kw)
+    for i in range(n):                                   # db.clj:46-69: one fresh client per node sends init
+        c = s.add_endpoint("c%d" % i)
+        s.send(c, i, O.body("init", msg_id=1))
+    return s
+
+
+def test_gset_full_state_replication_doc_count():
+    # doc/04-crdts/01-g-set.md:200-210: 5 nodes replicating the whole set every 5 s exchange
+    # 80 inter-server messages over the 20 s of the run (4 rounds of 5 x 4 messages)
+    s = gset_cluster()
+    s.run(20_000_000_000)
+    st = s.stats()
+    assert st["servers"] == {"send-count": 80, "recv-count": 80, "msg-count": 80}
+    assert st["clients"]["send-count"] == 10            # 5 init + 5 init_ok
+
+
+def test_gset_add_read_and_convergence():
+    s = gset_cluster()
+    s.run(1_000_000)
+    c = s.add_endpoint("c9")
+    for k, v in enumerate((3, 7, 11)):
+        s.send(c, k, O.body("add", msg_id=k + 1, p0=v))
+        r = s.recv(c, 1_000_000_000)
+        assert r["type"] == O.T["add_ok"] and r["in_reply_to"] == k + 1
+    s.send(c, 4, O.body("read", msg_id=10))
+    r = s.recv(c, 1_000_000_000)
+    assert r["type"] == O.T["read_ok"] and r["p0"] == 0   # nothing replicated yet
+    s.run(5_100_000_000)                                  # next replication round at t = 5 s
+    for k in range(5):
+        assert s.node_set(k).tolist() == [3, 7, 11]
+    s.send(c, 4, O.body("read", msg_id=11))
+    r = s.recv(c, 1_000_000_000)
+    assert r["p0"] == 3 and s.read_snapshot(int(r["id"])).tolist() == [3, 7, 11]
+
+
+def test_gset_converges_despite_loss_and_partition():
+    # CRDT property the workload is about (workload/g_set.clj:52-62 set-full): every add is
+    # eventually visible everywhere once the network heals
+    s = gset_cluster(latency_dist="uniform", latency_mean_ms=20)
+    s.run(100_000_000)                                    # every node initialised (init is not exempt from loss)
+    s.set_loss(0.3)
+    c = s.add_endpoint("c9")
+    for v in range(20):
+        s.send(c, v % 5, O.body("add", msg_id=v + 1, p0=v))
+    s.partition([0, 0, 1, 1, 1])
+    s.run(12_000_000_000)
+    assert any(len(s.node_set(k)) < 20 for k in range(5))
+    s.heal()
+    s.set_loss(0.0)
+    s.run(30_000_000_000)
+    sets = [s.node_set(k).tolist() for k in range(5)]
+    added = sorted(set(sum(sets, [])))
+    assert all(x == added for x in sets) and len(added) >= 10   # lost client adds never reached a node
