@@ -35,6 +35,11 @@
 namespace msd {
 
 #define FULL 0xFFFFFFFFu
+// Kernel launches go through one macro so that tests/native/emul (a CPU SIMT emulator used by
+// the CPU test-suite only) can run these same sources; under nvcc it is the plain <<<>>> launch.
+#ifndef MS_EMUL
+#define MS_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
 constexpr int MAXB = 64;            // sender blocks handled by the fast ordering path
 constexpr int MAXNB = 8;            // neighbor slots handled by per-(CTA, neighbor) claims
 constexpr uint64_t RECV_BIT = 1ull << 63;
@@ -44,16 +49,24 @@ __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) { return __ldcg
 // streaming 16-byte store: journal / ring records are written once and read by
 // another SM (or the host) later, so keep them out of L1.
 __device__ __forceinline__ void st_v4(uint4* p, uint4 v) {
+#ifdef MS_EMUL
+  *p = v;
+#else
   asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
                "r"(v.z), "r"(v.w)
                : "memory");
+#endif
 }
 __device__ __forceinline__ uint4 ld_v4_stream(const uint4* p) {
   uint4 v;
+#ifdef MS_EMUL
+  v = *p;
+#else
   asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                : "l"(p)
                : "memory");
+#endif
   return v;
 }
 
@@ -718,7 +731,11 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
   DevState* st = p.st;
   if (round_skipped(p, st) || !st->slot_open) return;
 
+#ifdef MS_EMUL
+  unsigned char* smem_raw = simt::dyn_smem();
+#else
   extern __shared__ __align__(16) unsigned char smem_raw[];
+#endif
   uint64_t* reg1 = reinterpret_cast<uint64_t*>(smem_raw);          // cap+1 entries
   uint32_t* keyB = reinterpret_cast<uint32_t*>(reg1 + cap + 1);
   uint32_t* vals = keyB + cap;
@@ -1409,7 +1426,7 @@ cudaError_t msk_round_smem_attr(size_t bytes) {
 size_t msk_round_smem_bytes(uint32_t cap) { return (size_t)cap * 25 + 32; }
 
 void msk_set_bit(uint32_t* words, size_t word, uint32_t bit, cudaStream_t s) {
-  msd::k_set_bit<<<1, 1, 0, s>>>(words, word, bit);
+  MS_LAUNCH(msd::k_set_bit, 1, 1, 0, s, words, word, bit);
 }
 
 int msk_round_occupancy(int threads, size_t smem) {
@@ -1426,13 +1443,13 @@ void msk_launch_round(const msd::Params* p, int n_classes, const uint32_t* caps,
                       const int* grids, int with_release, cudaStream_t s, cudaEvent_t before_round,
                       cudaEvent_t after_round, int phases, const cudaStream_t* aux, const cudaEvent_t* aux_ev) {
   const uint32_t n_ep = p->n_ep;
-  if ((phases & 1) && with_release) msd::k_release<<<296, 256, 0, s>>>(*p);
+  if ((phases & 1) && with_release) MS_LAUNCH(msd::k_release, 296, 256, 0, s, *p);
   if (phases & 8) {
     const int sb = 256;
     int sg = (int)((n_ep + sb - 1) / sb);
     if (sg > 296) sg = 296;
     if (sg < 1) sg = 1;
-    msd::k_snapshot<<<sg, sb, 0, s>>>(*p);
+    MS_LAUNCH(msd::k_snapshot, sg, sb, 0, s, *p);
   }
   if (phases & 2) {
     if (before_round) cudaEventRecord(before_round, s);
@@ -1444,20 +1461,20 @@ void msk_launch_round(const msd::Params* p, int n_classes, const uint32_t* caps,
       const size_t sm = msk_round_smem_bytes(caps[c]);
       cudaStream_t sc = (fork && c != n_classes - 1) ? aux[c] : s;
       if (sc != s) cudaStreamWaitEvent(sc, aux_ev[0], 0);
-      if (c == 0) msd::k_round<0><<<grids[c], threads[c], sm, sc>>>(*p, caps[c]);
-      else if (c == 1) msd::k_round<1><<<grids[c], threads[c], sm, sc>>>(*p, caps[c]);
-      else if (c == 2) msd::k_round<2><<<grids[c], threads[c], sm, sc>>>(*p, caps[c]);
-      else msd::k_round<3><<<grids[c], threads[c], sm, sc>>>(*p, caps[c]);
+      if (c == 0) MS_LAUNCH(msd::k_round<0>, grids[c], threads[c], sm, sc, *p, caps[c]);
+      else if (c == 1) MS_LAUNCH(msd::k_round<1>, grids[c], threads[c], sm, sc, *p, caps[c]);
+      else if (c == 2) MS_LAUNCH(msd::k_round<2>, grids[c], threads[c], sm, sc, *p, caps[c]);
+      else MS_LAUNCH(msd::k_round<3>, grids[c], threads[c], sm, sc, *p, caps[c]);
       if (sc != s) cudaEventRecord(aux_ev[1 + c], sc);
     }
     if (fork)
       for (int c = 0; c < n_classes - 1; c++) cudaStreamWaitEvent(s, aux_ev[1 + c], 0);
     if (after_round) cudaEventRecord(after_round, s);
   }
-  if ((phases & 4) && p->n_shards > 1) msd::k_commit<<<1, 512, 0, s>>>(*p);
+  if ((phases & 4) && p->n_shards > 1) MS_LAUNCH(msd::k_commit, 1, 512, 0, s, *p);
 }
 
-void msk_barrier(const msd::Params* p, cudaStream_t s) { msd::k_barrier<<<1, 32, 0, s>>>(*p); }
+void msk_barrier(const msd::Params* p, cudaStream_t s) { MS_LAUNCH(msd::k_barrier, 1, 32, 0, s, *p); }
 
 void msk_journal_expand(const msd::Params* p, uint64_t r0, uint32_t n_rounds, uint64_t first, uint64_t count,
                         void* out_ev, void* out_body, cudaStream_t s) {
@@ -1465,8 +1482,8 @@ void msk_journal_expand(const msd::Params* p, uint64_t r0, uint32_t n_rounds, ui
   uint64_t blocks = (chunks * 32 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
-  msd::k_journal_expand<<<(unsigned)blocks, 256, 0, s>>>(*p, r0, n_rounds, first, count, (uint4*)out_ev,
-                                                          (uint4*)out_body);
+  MS_LAUNCH(msd::k_journal_expand, (unsigned)blocks, 256, 0, s, *p, r0, n_rounds, first, count, (uint4*)out_ev,
+            (uint4*)out_body);
 }
 
 }  // extern "C"

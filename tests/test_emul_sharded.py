@@ -1,0 +1,87 @@
+"""Sharded engine under the CPU SIMT emulator (tests/native/emul): G shards of ONE process, one
+host thread per shard, mapping each other's rings through the emulator's pointer-carrying IPC
+handles.  Exercises the multi-shard kernel paths (owner map, peer-ring claims, k_barrier,
+k_commit over all shards' tables) without GPUs; the merged journal must equal the oracle's and
+therefore the single-shard journal.  The GPU twin is tests/test_gpu_sharded.py."""
+import ctypes as C
+import threading
+
+import numpy as np
+import pytest
+
+import emul_lib
+import oracle_lib as O
+from scenarios import random_broadcast_ops
+
+
+def run_sharded(world, n, per_tick, latency_ms, until_ns, n_ticks=3, seed=17, **kw):
+    from maelstrom_b200 import _lib
+    from maelstrom_b200.engine import KIND_SIM_CLIENT, Sim
+    from maelstrom_b200.sharded import merge_journals
+    n_values = n_ticks * per_tick + 8
+    blobs = [None] * world
+    out = [None] * world
+    errs = []
+    sync = threading.Barrier(world)
+    ops_box = {}
+
+    def shard(rank):
+        try:
+            g = Sim(n, workload="broadcast", topology="grid", n_values=n_values, ring_cap=4096, max_window=2048,
+                    journal_cap_log2=20, max_endpoints=n + 8, latency_dist="constant",
+                    latency_mean_ms=latency_ms, journal_level=1, n_shards=world, shard_id=rank, **kw)
+            blob = (C.c_ubyte * _lib.SHARD_BLOB_BYTES)()
+            g._chk(g.L.ms_shard_handles(g.h, blob))
+            blobs[rank] = bytes(blob)
+            sync.wait()
+            for peer in range(world):
+                buf = (C.c_ubyte * _lib.SHARD_BLOB_BYTES).from_buffer_copy(blobs[peer])
+                g._chk(g.L.ms_shard_connect(g.h, peer, buf))
+            sync.wait()
+            cs = [g.add_endpoint("c%d" % i, KIND_SIM_CLIENT) for i in range(3)]
+            ops, _ = random_broadcast_ops(n, cs, n_ticks=n_ticks, per_tick=per_tick, seed=seed)
+            ops_box[rank] = ops
+            g.schedule(ops)
+            g.run(until_ns)
+            ev, _ = g.drain(bodies=False)
+            out[rank] = (ev, g.stats(), g.now, g.round)
+            sync.wait()          # nobody frees rings a peer may still be writing to
+            g.close()
+        except Exception as e:   # noqa: BLE001
+            errs.append((rank, repr(e)))
+            sync.abort()
+
+    with emul_lib.use():
+        ts = [threading.Thread(target=shard, args=(r,)) for r in range(world)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join(timeout=600)
+    assert not errs, errs
+    merged = merge_journals([o[0] for o in out])
+    stats = {}
+    for _, st, _, _ in out:
+        for c, d in st.items():
+            for k, v in d.items():
+                stats.setdefault(c, {}).setdefault(k, 0)
+                stats[c][k] += v
+    assert len({(o[2], o[3]) for o in out}) == 1      # every shard ends at the same time and round
+    return merged, stats, out[0][2], out[0][3], ops_box[0]
+
+
+@pytest.mark.parametrize("world,n,per_tick,latency_ms", [(2, 64, 120, 0), (4, 64, 60, 0), (3, 100, 40, 2)])
+def test_emulated_shards_equal_oracle(world, n, per_tick, latency_ms):
+    until = 30_000_000 if latency_ms else 4_000_000
+    ev, st, now, rnd, ops = run_sharded(world, n, per_tick, latency_ms, until)
+    o = O.Sim(n, workload=O.W_BROADCAST, topology="grid", n_values=3 * per_tick + 8,
+              latency_dist="constant", latency_mean_ms=latency_ms)
+    for i in range(3):
+        o.add_endpoint("c%d" % i, O.KIND_SIM_CLIENT)
+    o.schedule(ops)
+    o.run(until)
+    ev_o, _ = o.journal()
+    assert len(ev) == len(ev_o), (len(ev), len(ev_o))
+    for f in ("event_id", "time_ns", "msg_id", "src", "dest"):
+        assert np.array_equal(ev[f], ev_o[f]), f
+    assert st == o.stats()
+    assert now == o.now and rnd == o.round

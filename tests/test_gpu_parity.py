@@ -7,10 +7,14 @@ import pytest
 import oracle_lib as O
 from scenarios import assert_same_journal, both, make_pair, ops_array, random_broadcast_ops
 
-pytestmark = pytest.mark.gpu
+# every test runs twice: [cuda] on the GPU box (gpu-marked) and [emul] in the CPU suite
+pytestmark = pytest.mark.usefixtures("engine_backend")
 
 
-def test_smoke_entry():
+@pytest.mark.gpu
+def test_smoke_entry(engine_backend):
+    if engine_backend != "cuda":
+        pytest.skip("smoke() is the CUDA entry point")
     import __graft_entry__ as G
     G.smoke()
 
@@ -231,7 +235,9 @@ def test_large_windows_all_size_classes(per_tick, max_window):
     assert c["max_window"] > 512
 
 
-def test_drain_into_pinned_memory_in_pieces():
+def test_drain_into_pinned_memory_in_pieces(engine_backend):
+    if engine_backend != "cuda":
+        pytest.skip("needs page-locked memory from the CUDA driver")
     # ms_journal_drain into a page-locked caller buffer (what bench.py's e2e leg does), in two
     # pieces that split a round; the concatenation must equal the oracle
     import torch

@@ -1,6 +1,7 @@
 """The host-side mirror of maelstrom.net / maelstrom.client (maelstrom_b200/net.py, client.py),
 driven the way the reference's tutorial drives the real thing (doc/02-echo, doc/03-broadcast).
-CPU: over the oracle backend; GPU: the same scenarios over the CUDA engine."""
+CPU: over the oracle backend and over the engine's kernels on the SIMT emulator; GPU: the same
+scenarios over the CUDA engine."""
 import json
 
 import pytest
@@ -21,7 +22,15 @@ def engine_backend(n, workload, **kw):
     return Net(mb.Sim(n, workload=name, **kw), mb.body)
 
 
+def emul_backend(n, workload, **kw):
+    # the engine's kernel sources on the CPU SIMT emulator (tests/native/emul)
+    import emul_lib
+    with emul_lib.use():
+        return engine_backend(n, workload, **kw)
+
+
 BACKENDS = [pytest.param(oracle_backend, id="oracle"),
+            pytest.param(emul_backend, id="emul"),
             pytest.param(engine_backend, id="cuda", marks=pytest.mark.gpu)]
 
 
