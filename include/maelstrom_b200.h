@@ -187,6 +187,9 @@ int ms_net_fast(ms_sim* sim);                                /* unwrap one level
 int ms_net_flaky(ms_sim* sim);                               /* p-loss = 0.5 */
 /* additions with no upstream equivalent */
 int ms_net_set_loss(ms_sim* sim, double p);
+/* Bulk partition: endpoints i, j < n with different component ids cannot hear each other (both
+ * directions, checked at dequeue like drop!).  Endpoints >= n, or listed as 0xFFFFFFFF, are never
+ * cut.  Cleared by ms_net_heal. */
 int ms_net_partition(ms_sim* sim, const uint32_t* component_id, size_t n);
 
 /* ------------------------------------------------------------------ journal: jepsen-os + net.journal */

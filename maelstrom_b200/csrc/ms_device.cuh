@@ -21,7 +21,7 @@ constexpr uint8_t  kRemoved  = 0x80;          // endpoint kind after remove-node
 enum : uint32_t {
   E_NONE = 0, E_RING_OVERFLOW = 1, E_WINDOW_OVERFLOW = 2, E_JOURNAL_OVERFLOW = 3,
   E_INVALID_DEST = 4, E_HISTORY = 5, E_VALUE_RANGE = 6, E_MAIL_OVERFLOW = 7,
-  E_CALENDAR_OVERFLOW = 8, E_ID_RANGE = 9, E_BARRIER = 10
+  E_CALENDAR_OVERFLOW = 8, E_ID_RANGE = 9, E_BARRIER = 10, E_SNAPSHOT = 11
 };
 
 // Mutable per-simulation scalars, resident in HBM, committed by the last CTA of
@@ -143,6 +143,14 @@ struct Params {
   uint4*    cal;             // cal_slots * cal_cap records
   uint32_t* cal_count;       // per slot
   uint32_t  cal_slots, cal_cap;
+  // g-set node program (demo/ruby/g_set.rb): the set is `bitmap`; replicate_full payloads are
+  // snapshots of it, kept in gs_slots rotating rows per node (row = node * gs_slots + run % gs_slots)
+  uint8_t*  gs_init;         // init received: the periodic task is running (node.rb:22-36,129-137)
+  int64_t*  gs_next_fire;    // virtual time of the task's next run (g_set.rb:34)
+  uint32_t* gs_fires;        // runs so far; run k (1-based) is the p1 of its replicate_full messages
+  uint32_t* gs_tag;          // [row] run number whose snapshot the row holds
+  uint32_t* gs_snap;         // [row][bm_words]
+  uint32_t  gs_slots, gs_interval_ms;
 };
 
 // ------------------------------------------------------------- Philox4x32-10

@@ -62,6 +62,7 @@ static const char* dev_error_text(uint32_t code) {
     case E_CALENDAR_OVERFLOW: return "timing wheel overflow (raise calendar_slots/calendar_cap): arg";
     case E_ID_RANGE: return "per-ticket count exceeds the table entry range at ticket";
     case E_BARRIER: return "cross-shard barrier timed out waiting for shard";
+    case E_SNAPSHOT: return "replicate_full names a set snapshot that is not resident (in flight longer than calendar_slots, or forged): sender";
   }
   return "unknown device error";
 }
@@ -417,8 +418,8 @@ static int build_sim(ms_sim* s, const ms_config* in) {
     set_err("bad workload/topology/latency_dist");
     return MS_ERR_ARG;
   }
-  if (c.workload == MS_W_GSET) {
-    set_err("workload g-set is not built yet (SURVEY.md section 8f NEXT-4); the oracle restates it (oracle/oracle.cpp)");
+  if (c.workload == MS_W_GSET && c.n_shards > 1) {
+    set_err("workload g-set runs on one GPU for now (set snapshots are not yet mapped across shards)");
     return MS_ERR_ARG;
   }
   if (c.latency_dist != MS_DIST_CONSTANT && c.latency_mean_ms == 0) {
@@ -557,6 +558,18 @@ static int build_sim(ms_sim* s, const ms_config* in) {
     }
   } else {
     if ((rc = s->dalloc(&P.next_msg_id, c.n_nodes))) return rc;
+  }
+  if (c.workload == MS_W_GSET) {
+    // replicate_full payloads: a snapshot stays resident while its messages can be in flight,
+    // i.e. at most calendar_slots ticks; one run every gset_interval_ms (g_set.rb:34)
+    P.gs_interval_ms = c.gset_interval_ms;
+    P.gs_slots = pow2_at_least((s->use_calendar ? c.calendar_slots / c.gset_interval_ms : 0u) + 2u);
+    const size_t rows = (size_t)c.n_nodes * P.gs_slots;
+    if ((rc = s->dalloc(&P.gs_init, c.n_nodes))) return rc;
+    if ((rc = s->dalloc(&P.gs_next_fire, c.n_nodes))) return rc;
+    if ((rc = s->dalloc(&P.gs_fires, c.n_nodes))) return rc;
+    if ((rc = s->dalloc(&P.gs_tag, rows))) return rc;
+    if ((rc = s->dalloc(&P.gs_snap, rows * P.bm_words))) return rc;
   }
   if ((rc = s->dalloc(&P.inj_buf, c.inject_cap))) return rc;
   if ((rc = s->dalloc(&P.mail, c.mailbox_cap))) return rc;

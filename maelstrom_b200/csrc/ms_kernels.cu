@@ -340,7 +340,10 @@ __global__ void k_snapshot(Params p) {
     p.head[e] = h;
     p.limit[e] = l;
     const uint32_t n = (p.kind[e] == kRemoved) ? 0u : l - h;
-    if (n == 0) {
+    // g-set: a node whose periodic replication task is due emits even with an empty window
+    const bool timer_due = p.workload == MS_W_GSET && e < p.n_servers && p.kind[e] == MS_KIND_SERVER &&
+                           p.gs_init[e] && st->now >= p.gs_next_fire[e];
+    if (n == 0 && !timer_due) {
       // nothing to receive, hence nothing to emit: the ticket is finished right here
       const uint32_t t = p.n_inj_tickets + e;
       p.rt_chunk[(size_t)row * p.t_max + t] = 0;
@@ -725,7 +728,26 @@ __device__ __forceinline__ uint64_t block_excl_scan_u64v(uint64_t v, uint64_t* t
   return before + incl - v;
 }
 
-template <int CLS>
+// g-set node program (demo/ruby/g_set.rb:13-39): message classes in meta bits 6-8
+enum : uint32_t { GT_OTHER = 0, GT_INIT = 1, GT_ADD = 2, GT_READ = 3, GT_REPL_ONE = 4, GT_REPL_FULL = 5 };
+
+__device__ __forceinline__ uint32_t gset_emit_count(uint32_t meta) {
+  if (meta & M_REPLY) return 0;                                                          // node.rb:159-164
+  const uint32_t tc = (meta >> M_TC_SHIFT) & 7u;
+  if (tc == GT_INIT || tc == GT_ADD || tc == GT_READ) return 1;                          // g_set.rb:13-21
+  if (tc == GT_REPL_ONE || tc == GT_REPL_FULL) return 0;                                 // g_set.rb:24-31: no reply
+  return (meta & M_HAS_ID) ? 1u : 0u;                                                    // error 10
+}
+
+// sum of one u32 per thread over the CTA
+__device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t* wcnt /* >= 17 */) {
+  uint32_t total;
+  (void)block_excl_scan_u32(v, &total, wcnt);
+  return total;
+}
+
+// WL selects the node program family compiled in: 0 = echo / broadcast, 1 = g-set.
+template <int CLS, int WL>
 __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
   constexpr uint32_t cls = CLS;
   DevState* st = p.st;
@@ -874,7 +896,16 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
     }
     const uint4* myring = p.ring + (size_t)e * p.ring_cap * 3;
     const bool is_server = (kind == MS_KIND_SERVER);
-    const bool bcast = is_server && p.workload == MS_W_BROADCAST;
+    const bool bcast = WL == 0 && is_server && p.workload == MS_W_BROADCAST;
+    // g-set periodic task (g_set.rb:34-39), evaluated before the node's receives: when due, the
+    // node snapshots its set and sends it to every other node (emissions 0 .. n_servers-2)
+    uint32_t n_timer = 0, fire_seq = 0, fire_p0 = 0;
+    if constexpr (WL == 1) {
+      if (is_server && p.gs_init[e] && now >= p.gs_next_fire[e]) {
+        n_timer = p.n_servers - 1;
+        fire_seq = p.gs_fires[e] + 1;
+      }
+    }
     const uint32_t* mybits = (is_server && p.bitmap) ? p.bitmap + (size_t)e * p.bm_words : nullptr;
     const uint32_t deg = bcast ? nbr_count(p, e) : 0;
     const bool nb_smem = bcast && p.topology != MS_TOPO_TOTAL && deg <= MAXNB;
@@ -885,6 +916,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
     //      partition check at dequeue (net.clj:234), compact message class
     {
       uint32_t err_val = 0xFFFFFFFFu;
+      uint32_t snap_gone = 0xFFFFFFFFu;
       bool inj_srv = false;
       for (int base = 0; base < (int)n; base += 2 * nt) {
         uint4 a[2], b[2], c[2];
@@ -916,11 +948,19 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
           const uint32_t type = tf & 0xFFFFu;
           const uint32_t fl = tf >> 16;
           uint32_t tc = TC_OTHER;
+          if constexpr (WL == 1) {
+            if (type == MS_T_INIT) tc = GT_INIT;
+            else if (type == MS_T_ADD) tc = GT_ADD;
+            else if (type == MS_T_READ) tc = GT_READ;
+            else if (type == MS_T_REPLICATE_ONE) tc = GT_REPL_ONE;
+            else if (type == MS_T_REPLICATE_FULL) tc = GT_REPL_FULL;
+          } else {
           if (type == MS_T_INIT) tc = TC_INIT;
           else if (type == MS_T_TOPOLOGY) tc = TC_TOPOLOGY;
           else if (type == MS_T_READ) tc = TC_READ;
           else if (type == MS_T_BROADCAST) tc = TC_BROADCAST;
           else if (type == MS_T_ECHO) tc = TC_ECHO;
+          }
           uint32_t slot = 0;
           if (nb_smem) {
             for (uint32_t j = 0; j < deg; j++) if (s_nbr[j] == src) slot = j + 1;
@@ -934,10 +974,24 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
             if (v >= p.n_values || v > V_MASK) err_val = v;
             else val |= v | V_CAND;
           }
+          if constexpr (WL == 1) {
+            if (is_server && !cut && !(fl & MS_F_REPLY)) {
+              if (tc == GT_ADD || tc == GT_REPL_ONE) {           // the element (g_set.rb:17-26)
+                if (v >= p.n_values || v > V_MASK) err_val = v;
+                else val |= v;
+              } else if (tc == GT_REPL_FULL) {                   // the snapshot row of (src, run p1)
+                const uint32_t run = c[q].z;
+                const uint32_t rowi = src * p.gs_slots + (run & (p.gs_slots - 1));
+                if (src >= p.n_servers || p.gs_tag[rowi] != run) snap_gone = src;
+                else val |= rowi;
+              }
+            }
+          }
           vals[i] = val;
         }
       }
       if (err_val != 0xFFFFFFFFu) latch_error(st, E_VALUE_RANGE, err_val);
+      if (snap_gone != 0xFFFFFFFFu) latch_error(st, E_SNAPSHOT, snap_gone);
       if (inj_srv) s_misc[3] = 1;
     }
     // PA2: seen-set test of the broadcast values (own slots only: no barrier needed in between)
@@ -1116,19 +1170,90 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
       uint64_t c = 0;
       if (val & V_RECV) {
         c = 1ull << 32;
+        if constexpr (WL == 1) {
+          if (is_server) {
+            const uint32_t mt = meta[i];
+            c |= gset_emit_count(mt);
+            if (!(mt & M_REPLY)) {
+              const uint32_t tc = (mt >> M_TC_SHIFT) & 7u;
+              if (tc == GT_READ) c |= 1ull << 48;          // bits 48-63 count the reads (cut points of the merge)
+              if (tc == GT_INIT) s_misc[2] = 1;            // node.rb:22-36: starts the periodic task
+            }
+          }
+        } else {
         if (is_server) c |= emit_count_meta(p.workload, meta[i], is_new, deg);
         if (is_new) c |= 1ull << 48;
+        }
       }
       aux[pos] = c;
     }
     __syncthreads();
     PHASE_MARK(3);
     const uint64_t tot = block_excl_scan(aux, (int)n, s_wtmp);
-    const uint32_t n_emit = (uint32_t)tot;
+    const uint32_t n_emit_msgs = (uint32_t)tot;          // replies / gossip caused by the window
+    const uint32_t n_emit = n_emit_msgs + n_timer;       // the periodic task's emissions come first
     const uint32_t n_recv = (uint32_t)(tot >> 32) & 0xFFFFu;
     const uint32_t n_new = (uint32_t)(tot >> 48);
     n_ev_local = n_recv + n_emit; n_em_local = n_emit;
     PHASE_MARK(4);
+
+    if constexpr (WL == 1) {
+      if (is_server) {
+        // ---- g-set state: snapshot for the periodic task, then the window in id order.  Unions
+        //      commute, so the window is applied in segments cut at the reads; each read sees
+        //      the set as of its place in the sequence (g_set.rb:13-15).
+        uint32_t* myset = p.bitmap + (size_t)e * p.bm_words;
+        const uint32_t n_reads = n_new;
+        if (n_timer) {
+          uint32_t* snap = p.gs_snap + (size_t)(e * p.gs_slots + (fire_seq & (p.gs_slots - 1))) * p.bm_words;
+          uint32_t cnt = 0;
+          for (uint32_t w = tid; w < p.bm_words; w += nt) {
+            const uint32_t x = myset[w];
+            snap[w] = x;
+            cnt += __popc(x);
+          }
+          fire_p0 = block_sum_u32(cnt, s_wcnt);
+        }
+        for (uint32_t pos = tid; pos < n; pos += nt)       // sorted positions of the reads
+          if ((uint32_t)(aux[pos + 1] >> 48) != (uint32_t)(aux[pos] >> 48)) tab[(uint32_t)(aux[pos] >> 48)] = (uint16_t)pos;
+        __syncthreads();
+        uint32_t seg_lo = 0;
+        for (uint32_t k = 0; k <= n_reads; k++) {
+          const uint32_t seg_hi = k < n_reads ? (uint32_t)tab[k] : n;
+          bool any_full = false;
+          for (uint32_t pos = seg_lo + tid; pos < seg_hi; pos += nt) {
+            const uint32_t i = ord[pos];
+            const uint32_t val = vals[i], mt = meta[i];
+            if (!(val & V_RECV) || (mt & M_REPLY)) continue;
+            const uint32_t tc = (mt >> M_TC_SHIFT) & 7u;
+            if (tc == GT_ADD || tc == GT_REPL_ONE) atomicOr(myset + ((val & V_MASK) >> 5), 1u << (val & 31));
+            else if (tc == GT_REPL_FULL) any_full = true;
+          }
+          if (__syncthreads_or(any_full ? 1 : 0)) {
+            // @set |= value (g_set.rb:29-31): every thread owns a strided set of words
+            for (uint32_t w = tid; w < p.bm_words; w += nt) {
+              uint32_t acc = 0;
+              for (uint32_t pos = seg_lo; pos < seg_hi; pos++) {
+                const uint32_t i = ord[pos];
+                const uint32_t val = vals[i], mt = meta[i];
+                if ((val & V_RECV) && !(mt & M_REPLY) && ((mt >> M_TC_SHIFT) & 7u) == GT_REPL_FULL)
+                  acc |= p.gs_snap[(size_t)(val & V_MASK) * p.bm_words + w];
+              }
+              if (acc) myset[w] |= acc;
+            }
+            __syncthreads();
+          }
+          if (k < n_reads) {
+            uint32_t cnt = 0;
+            for (uint32_t w = tid; w < p.bm_words; w += nt) cnt += __popc(myset[w]);
+            const uint32_t total = block_sum_u32(cnt, s_wcnt);
+            if (tid == 0) keyB[seg_hi] = total;            // keyB is free after the ordering phase
+            seg_lo = seg_hi + 1;
+          }
+        }
+        __syncthreads();
+      }
+    }
 
     // PD: claims: journal chunk, mailbox, per-neighbor ring blocks
     const bool mailed = (kind == MS_KIND_CLIENT || kind == MS_KIND_HOST);
@@ -1247,7 +1372,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
     // PE2: emissions in id order, one emission per thread: emission j belongs to the last
     //      sorted position whose exclusive emit prefix is <= j.  When it fits, that map is
     //      materialised in the (now free) first-sight table instead of searched for.
-    const bool own_map = agg_mode != 2 && n_emit <= 2u * cap;
+    const bool own_map = agg_mode != 2 && n_emit_msgs <= 2u * cap;
     if (own_map) {
       for (uint32_t pos = tid; pos < n; pos += nt) {
         const uint32_t e0 = (uint32_t)aux[pos], e1 = (uint32_t)aux[pos + 1];
@@ -1262,17 +1387,27 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
       r.dest = 0; r.src = e;
       uint32_t direct = 0;
       bool has_direct = false;
-      if (valid) {
+      bool timer_emission = false;
+      if constexpr (WL == 1) {
+        if (valid && j < n_timer) {
+          // replicate_full to the j-th other node (node.rb:104-108 other_node_ids, g_set.rb:36-38)
+          timer_emission = true;
+          r.dest = j < e ? j : j + 1;
+          r.msg_id = 0; r.in_reply_to = 0; r.tf = MS_T_REPLICATE_FULL; r.p0 = fire_p0; r.p1 = fire_seq;
+        }
+      }
+      if (valid && !timer_emission) {
+        const uint32_t jm = j - n_timer;       // index among the emissions caused by messages
         uint32_t pos;
         if (own_map) {
-          pos = tab[j];
+          pos = tab[jm];
         } else {
           uint32_t lo = 0, hi = n;
-          while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if ((uint32_t)aux[mid] <= j) lo = mid; else hi = mid; }
+          while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if ((uint32_t)aux[mid] <= jm) lo = mid; else hi = mid; }
           pos = lo;
         }
         const uint64_t a0 = aux[pos];
-        const uint32_t k = j - (uint32_t)a0;
+        const uint32_t k = jm - (uint32_t)a0;
         const uint32_t my_emit = (uint32_t)aux[pos + 1] - (uint32_t)a0;
         const uint32_t new_before = (uint32_t)(a0 >> 48);
         const uint32_t i = ord[pos];
@@ -1300,14 +1435,39 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
           MsgView w;
           w.src = vb.x; w.msg_id = vb.z; w.tf = vc.x; w.p0 = vc.y;
           const uint64_t p1 = (uint64_t)vc.z | ((uint64_t)vc.w << 32);
-          (void)node_emit(p, e, w, k, my_emit, j, msg_id_base, set_before, new_before, p1, r, L);
+          if constexpr (WL == 1) {
+            // g_set.rb:13-21: replies only; the set size a read reports was computed at its cut point
+            const uint32_t tc = (mt >> M_TC_SHIFT) & 7u;
+            r.src = e; r.dest = w.src; r.msg_id = 0; r.in_reply_to = w.msg_id; r.p0 = 0; r.p1 = 0;
+            uint32_t otype = MS_T_ERROR;
+            if (tc == GT_INIT) otype = MS_T_INIT_OK;
+            else if (tc == GT_ADD) otype = MS_T_ADD_OK;
+            else if (tc == GT_READ) { otype = MS_T_READ_OK; r.p0 = keyB[pos]; }
+            else r.p0 = 10;                                  // not-supported (errors.edn)
+            r.tf = otype | ((uint32_t)MS_F_REPLY << 16);
+          } else {
+          (void)node_emit(p, e, w, k, my_emit, jm, msg_id_base, set_before, new_before, p1, r, L);
+          }
         }
       }
       emit_one(p, st, np, cx, valid, r, j, direct, has_direct);
     }
     if (tid == 0 && is_server) {
       if (p.workload == MS_W_ECHO && p.next_msg_id && n_emit) p.next_msg_id[e] = msg_id_base + n_emit;
+      if constexpr (WL == 0) {
       if (p.set_count && n_new) p.set_count[e] = set_before + n_new;
+      } else {
+        // periodic task bookkeeping: the run advances its schedule first, an init received this
+        // round (re)starts it at `now` (oracle/oracle.cpp node_gset / gset_timer)
+        int64_t nf = p.gs_next_fire[e];
+        if (n_timer) {
+          nf += (int64_t)p.gs_interval_ms * kTickNs;
+          p.gs_fires[e] = fire_seq;
+          p.gs_tag[e * p.gs_slots + (fire_seq & (p.gs_slots - 1))] = fire_seq;
+        }
+        if (s_misc[2]) { p.gs_init[e] = 1; nf = now; }
+        p.gs_next_fire[e] = nf;
+      }
       if (n > st->max_window_seen) atomicMax(&st->max_window_seen, n);
     }
   }
@@ -1415,11 +1575,20 @@ __global__ void k_journal_expand(Params p, uint64_t r0, uint32_t n_rounds, uint6
 // ------------------------------------------------------------------ host-callable launchers
 extern "C" {
 
+typedef void (*msk_round_fn)(msd::Params, uint32_t);
+// round kernel of (node program family, window-size class)
+static msk_round_fn msk_round_kernel(uint32_t workload, int cls) {
+  static const msk_round_fn tab[2][4] = {
+      {msd::k_round<0, 0>, msd::k_round<1, 0>, msd::k_round<2, 0>, msd::k_round<3, 0>},
+      {msd::k_round<0, 1>, msd::k_round<1, 1>, msd::k_round<2, 1>, msd::k_round<3, 1>}};
+  return tab[workload == MS_W_GSET ? 1 : 0][cls];
+}
+
 cudaError_t msk_round_smem_attr(size_t bytes) {
-  cudaError_t e = cudaFuncSetAttribute(msd::k_round<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(msd::k_round<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(msd::k_round<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(msd::k_round<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  cudaError_t e = cudaSuccess;
+  for (uint32_t wl = MS_W_ECHO; wl <= MS_W_GSET && e == cudaSuccess; wl += 2)   // one workload of each family
+    for (int c = 0; c < 4 && e == cudaSuccess; c++)
+      e = cudaFuncSetAttribute(msk_round_kernel(wl, c), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   return e;
 }
 
@@ -1431,7 +1600,7 @@ void msk_set_bit(uint32_t* words, size_t word, uint32_t bit, cudaStream_t s) {
 
 int msk_round_occupancy(int threads, size_t smem) {
   int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msd::k_round<0>, threads, smem) != cudaSuccess) return 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msk_round_kernel(MS_W_BROADCAST, 0), threads, smem) != cudaSuccess) return 1;
   return nb < 1 ? 1 : nb;
 }
 
@@ -1461,10 +1630,8 @@ void msk_launch_round(const msd::Params* p, int n_classes, const uint32_t* caps,
       const size_t sm = msk_round_smem_bytes(caps[c]);
       cudaStream_t sc = (fork && c != n_classes - 1) ? aux[c] : s;
       if (sc != s) cudaStreamWaitEvent(sc, aux_ev[0], 0);
-      if (c == 0) MS_LAUNCH(msd::k_round<0>, grids[c], threads[c], sm, sc, *p, caps[c]);
-      else if (c == 1) MS_LAUNCH(msd::k_round<1>, grids[c], threads[c], sm, sc, *p, caps[c]);
-      else if (c == 2) MS_LAUNCH(msd::k_round<2>, grids[c], threads[c], sm, sc, *p, caps[c]);
-      else MS_LAUNCH(msd::k_round<3>, grids[c], threads[c], sm, sc, *p, caps[c]);
+      const msk_round_fn kern = msk_round_kernel(p->workload, c < 3 ? c : 3);
+      MS_LAUNCH(kern, grids[c], threads[c], sm, sc, *p, caps[c]);
       if (sc != s) cudaEventRecord(aux_ev[1 + c], sc);
     }
     if (fork)

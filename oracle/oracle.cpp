@@ -193,6 +193,7 @@ struct Endpoint {
   std::vector<uint32_t> neighbors;      // broadcast @neighbors (topology)
   bool initialized = false;             // node.rb:22-36: periodic tasks start after init
   int64_t next_fire = 0;                // g-set: next run of the `every 5` task (g_set.rb:34)
+  uint64_t fires = 0;                   // g-set: replication runs so far
 };
 
 }  // namespace
@@ -214,8 +215,8 @@ struct or_sim {
   std::vector<or_op> schedule;
   size_t sched_cursor = 0;
   std::map<uint64_t, std::vector<uint32_t>> snapshots; // read_ok msg id -> set contents
-  std::map<uint64_t, std::vector<uint32_t>> gset_snaps; // replicate_full p1 handle -> value list
-  uint64_t next_snap = 1;
+  // replicate_full payloads: (sender, p1 = sender's replication run, 1-based) -> value list
+  std::map<std::pair<uint32_t, uint64_t>, std::vector<uint32_t>> gset_snaps;
   uint64_t client_replies = 0;
   std::string error;
   uint64_t stats[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -226,8 +227,10 @@ struct or_sim {
   }
   bool partitioned(uint32_t src, uint32_t dest) const {                        // net.clj:234
     if (partitions.count(std::make_pair(dest, src))) return true;
+    // bulk partition: endpoints beyond the list, or listed as 0xFFFFFFFF, are never cut
     if (!component.empty() && src < component.size() && dest < component.size() &&
-        component[src] != component[dest]) return true;
+        component[src] != component[dest] && component[src] != 0xFFFFFFFFu && component[dest] != 0xFFFFFFFFu)
+      return true;
     return false;
   }
 
@@ -364,7 +367,7 @@ struct or_sim {
         ep.values.insert(m.p0);
         break;
       case OR_T_REPLICATE_FULL: {                           // g_set.rb:29-31  @set |= value
-        auto it = gset_snaps.find(m.p1);
+        auto it = gset_snaps.find(std::make_pair(m.src, m.p1));
         if (it != gset_snaps.end()) ep.values.insert(it->second.begin(), it->second.end());
         break;
       }
@@ -377,10 +380,12 @@ struct or_sim {
   void gset_timer(uint32_t e, std::vector<Emit>& out) {
     Endpoint& ep = eps[e];
     if (!ep.initialized || now < ep.next_fire) return;
-    const uint64_t handle = next_snap++;
-    gset_snaps[handle].assign(ep.values.begin(), ep.values.end());
+    const uint64_t handle = ++ep.fires;
+    gset_snaps[std::make_pair(e, handle)].assign(ep.values.begin(), ep.values.end());
     for (uint32_t other = 0; other < cfg.n_nodes; other++) {
-      if (other == e || !eps[other].live) continue;         // node.rb:104-108 other_node_ids
+      // node.rb:104-108 other_node_ids: every node named by init, alive or not -- a send to a
+      // removed node trips net.clj:172-175 like any other
+      if (other == e) continue;
       or_msg g; std::memset(&g, 0, sizeof g);
       g.src = e; g.dest = other; g.type = OR_T_REPLICATE_FULL;
       g.p0 = (uint32_t)ep.values.size(); g.p1 = handle;

@@ -140,7 +140,7 @@ class Sim:
     """Thin object wrapper; method names follow the C ABI (include/maelstrom_b200.h)."""
 
     def __init__(self, n_nodes, workload=W_BROADCAST, topology="grid", latency_dist="constant",
-                 latency_mean_ms=0, seed=0x4D41454C, p_loss=0.0, n_values=1 << 16):
+                 latency_mean_ms=0, seed=0x4D41454C, p_loss=0.0, n_values=1 << 16, gset_interval_ms=5000):
         cfg = Config()
         cfg.n_nodes = n_nodes
         cfg.workload = workload
@@ -151,7 +151,7 @@ class Sim:
         cfg.seed_hi = seed >> 32
         cfg.p_loss = p_loss
         cfg.n_values = n_values
-        cfg.gset_interval_ms = 5000
+        cfg.gset_interval_ms = gset_interval_ms
         self.L = lib()
         self.h = self.L.or_create(C.byref(cfg))
         self.n_nodes = n_nodes
