@@ -147,3 +147,16 @@ def test_out_of_range_element_is_an_error():
     g.send(c, 0, mb.body("add", msg_id=1, p0=64))
     with pytest.raises(mb.SimError):
         g.run(3_000_000)
+
+
+def test_committed_golden_journal():
+    # tests/golden/journals.json["gset_five_nodes"], generated from the oracle
+    import json
+    import os
+    import golden_cases as G
+    import maelstrom_b200 as mb
+    want = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "journals.json")))
+    g = G.make_engine("gset_five_nodes")
+    G.CASES["gset_five_nodes"][1](g, mb.body)
+    ev, bd = g.drain()
+    assert G.digest(ev, bd, g.stats(), g.now, g.round) == want["gset_five_nodes"]
