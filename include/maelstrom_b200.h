@@ -78,7 +78,8 @@ typedef struct ms_op {
   ms_body  body;
 } ms_op;
 
-enum { MS_F_MSG_ID = 1, MS_F_REPLY = 2 };
+enum { MS_F_MSG_ID = 1, MS_F_REPLY = 2,
+       MS_F_CREATE = 4 };   /* cas: create_if_not_exists (service.clj:50-54) */
 
 /* body.type codes (doc/workloads.md) */
 enum {
@@ -86,7 +87,12 @@ enum {
   MS_T_ECHO = 10, MS_T_ECHO_OK = 11,
   MS_T_TOPOLOGY = 20, MS_T_TOPOLOGY_OK = 21, MS_T_BROADCAST = 22,
   MS_T_BROADCAST_OK = 23, MS_T_READ = 24, MS_T_READ_OK = 25,
-  MS_T_ADD = 30, MS_T_ADD_OK = 31, MS_T_REPLICATE_ONE = 32, MS_T_REPLICATE_FULL = 33
+  MS_T_ADD = 30, MS_T_ADD_OK = 31, MS_T_REPLICATE_ONE = 32, MS_T_REPLICATE_FULL = 33,
+  /* services (doc/services.md, service.clj:31-141).  read = MS_T_READ with p0 = key and read_ok
+   * p1 = value; write p0 = key, p1 = value; cas p0 = key, p1 = from | to << 32 (+ MS_F_CREATE);
+   * ts_ok p1 = timestamp; errors: MS_T_ERROR with p0 = 20 / 22 (errors.edn).  Keys are integers
+   * below ms_config.reserved[2]; values are 32-bit on the device. */
+  MS_T_WRITE = 40, MS_T_WRITE_OK = 41, MS_T_CAS = 42, MS_T_CAS_OK = 43, MS_T_TS = 44, MS_T_TS_OK = 45
 };
 
 enum { MS_W_ECHO = 0, MS_W_BROADCAST = 1, MS_W_GSET = 2 };                  /* --workload, core.clj:36-47 */
@@ -96,7 +102,10 @@ enum { MS_DIST_CONSTANT = 0, MS_DIST_UNIFORM = 1, MS_DIST_EXPONENTIAL = 2 }; /* 
 enum { MS_KIND_SERVER = 0,      /* device-resident node program (replaces process/start-node!) */
        MS_KIND_CLIENT = 1,      /* host-visible client, id "c<k>" (util.clj:7-10): zero latency */
        MS_KIND_HOST = 2,        /* host-visible non-client endpoint (a JVM service, service.clj:245-263) */
-       MS_KIND_SIM_CLIENT = 3 };/* device-resident client sink (replies are counted, not mailed) */
+       MS_KIND_SIM_CLIENT = 3,  /* device-resident client sink (replies are counted, not mailed) */
+       MS_KIND_SERVICE = 4 };   /* device-resident service; the id picks it: "lin-kv", "seq-kv", "lww-kv",
+                                   "lin-tso" (service/default-services, service.clj:290-296) */
+enum { MS_SVC_LIN_KV = 0, MS_SVC_SEQ_KV = 1, MS_SVC_LWW_KV = 2, MS_SVC_LIN_TSO = 3 };
 
 /* error codes (negative returns); MS_ERR_NODE_NOT_FOUND maps to Maelstrom error
  * code 1 {:type ::node-not-found :definite? true} (net.clj:159-164) */
@@ -138,7 +147,7 @@ typedef struct ms_config {
   uint32_t threads_per_node; /* CTA size of the round kernel (0 = auto) */
   uint32_t n_shards;         /* GPUs the endpoints are sharded over (0/1 = single GPU), <= 8 */
   uint32_t shard_id;         /* this process's shard */
-  uint32_t reserved[6];      /* [0] = rounds of id history to keep (0 = default); [1] = 1: replay round batches from a CUDA graph */
+  uint32_t reserved[6];      /* [0] = rounds of id history to keep (0 = default); [1] = 1: replay round batches from a CUDA graph; [2] = keys per service store (0 = 4096) */
 } ms_config;
 
 typedef struct ms_sim ms_sim;

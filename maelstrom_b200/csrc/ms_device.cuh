@@ -151,7 +151,24 @@ struct Params {
   uint32_t* gs_tag;          // [row] run number whose snapshot the row holds
   uint32_t* gs_snap;         // [row][bm_words]
   uint32_t  gs_slots, gs_interval_ms;
+  // services (service.clj): device-resident lin-kv / seq-kv / lww-kv / lin-tso endpoints
+  uint32_t  family;          // node-program families compiled into the round kernel in use: bit 0 g-set, bit 1 services
+  uint32_t  sv_ep[4];        // endpoint index of service MS_SVC_*, 0xFFFFFFFF = not started
+  uint32_t  sv_n_keys;       // keys per store
+  uint32_t* sv_lin_val;      // lin-kv: Linearizable(PersistentKV), service.clj:31-58,147-156
+  uint8_t*  sv_lin_has;
+  uint32_t* sv_lww_val;      // lww-kv: two replicas (service.clj:218-251; they never merge, see oracle)
+  uint8_t*  sv_lww_has;
+  uint64_t* sv_scalars;      // [0] lin-tso counter (service.clj:123-129), [1] seq-kv last-index
+  uint32_t* sv_seq_cli;      // seq-kv: per client (endpoint) last observed state index (service.clj:162-166)
+  uint32_t* sv_seq_vidx;     // seq-kv: per key a ring of kSeqHist versions {state index, value, present}
+  uint32_t* sv_seq_vval;
+  uint8_t*  sv_seq_vhas;
+  uint32_t* sv_seq_vcnt;     // versions written per key
 };
+
+constexpr uint32_t kSeqBuffer = 32;             // (sequential 32 ...), service.clj:206-208
+constexpr uint32_t kSeqHist = kSeqBuffer + 1;   // versions per key that can matter to a resident state
 
 // ------------------------------------------------------------- Philox4x32-10
 // Salmon et al. SC'11 (the generator cuRAND names Philox_4x32_10).  Stands in

@@ -559,6 +559,8 @@ static int build_sim(ms_sim* s, const ms_config* in) {
   } else {
     if ((rc = s->dalloc(&P.next_msg_id, c.n_nodes))) return rc;
   }
+  P.family = c.workload == MS_W_GSET ? 1u : 0u;
+  for (int k = 0; k < 4; k++) P.sv_ep[k] = 0xFFFFFFFFu;
   if (c.workload == MS_W_GSET) {
     // replicate_full payloads: a snapshot stays resident while its messages can be in flight,
     // i.e. at most calendar_slots ticks; one run every gset_interval_ms (g_set.rb:34)
@@ -698,10 +700,33 @@ int ms_stop_nodes(ms_sim* s) {
 int ms_add_endpoint(ms_sim* s, const char* id, int kind) {
   std::lock_guard<std::mutex> g(s->mu);
   cudaSetDevice(s->device);
-  if (!id || kind < MS_KIND_CLIENT || kind > MS_KIND_SIM_CLIENT) { set_err("bad endpoint id/kind"); return MS_ERR_ARG; }
+  if (!id || kind < MS_KIND_CLIENT || kind > MS_KIND_SERVICE) { set_err("bad endpoint id/kind"); return MS_ERR_ARG; }
   if (s->by_name.count(id)) { set_err("endpoint already exists"); return MS_ERR_ARG; }
   const uint32_t idx = s->P.n_ep;
   if (idx >= s->cfg.max_endpoints) { set_err("max_endpoints exhausted"); return MS_ERR_CAPACITY; }
+  if (kind == MS_KIND_SERVICE) {
+    // service/default-services (service.clj:290-296): the id names the service
+    static const char* const names[4] = {"lin-kv", "seq-kv", "lww-kv", "lin-tso"};
+    int svc = -1;
+    for (int k = 0; k < 4; k++) if (!strcmp(id, names[k])) svc = k;
+    if (svc < 0) { set_err("service endpoints are lin-kv, seq-kv, lww-kv or lin-tso (service.clj:290-296)"); return MS_ERR_ARG; }
+    if (s->P.n_shards > 1) { set_err("device-resident services run on one GPU for now"); return MS_ERR_ARG; }
+    if (!s->P.sv_scalars) {
+      int rc;
+      Params& P = s->P;
+      P.sv_n_keys = s->cfg.reserved[2] ? s->cfg.reserved[2] : 4096u;
+      const size_t K = P.sv_n_keys;
+      if ((rc = s->dalloc(&P.sv_lin_val, K)) || (rc = s->dalloc(&P.sv_lin_has, K)) ||
+          (rc = s->dalloc(&P.sv_lww_val, 2 * K)) || (rc = s->dalloc(&P.sv_lww_has, 2 * K)) ||
+          (rc = s->dalloc(&P.sv_scalars, 2)) || (rc = s->dalloc(&P.sv_seq_cli, s->cfg.max_endpoints)) ||
+          (rc = s->dalloc(&P.sv_seq_vidx, K * kSeqHist)) || (rc = s->dalloc(&P.sv_seq_vval, K * kSeqHist)) ||
+          (rc = s->dalloc(&P.sv_seq_vhas, K * kSeqHist)) || (rc = s->dalloc(&P.sv_seq_vcnt, K)))
+        return rc;
+      CK(cudaStreamSynchronize(s->stream));
+    }
+    s->P.sv_ep[svc] = idx;
+    s->P.family |= 2u;   // from now on the round kernels with the service program compiled in
+  }
   s->kinds[idx] = (uint8_t)kind;
   s->names.push_back(id);
   s->mailbox.emplace_back();

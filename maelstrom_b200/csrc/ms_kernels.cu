@@ -746,10 +746,108 @@ __device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t* wcnt /* 
   return total;
 }
 
-// WL selects the node program family compiled in: 0 = echo / broadcast, 1 = g-set.
+// ------------------------------------------------------------------ services (service.clj)
+struct SvReq {
+  uint32_t type, flags, key, src;
+  uint64_t p1;
+};
+struct SvRep {
+  bool reply;          // false: no clause of the service's `case` matches -> exception, logged, no reply (service.clj:262-263)
+  uint32_t otype, code, value;
+};
+// service reply kept in vals[] between the sequential pass and the emit phase
+constexpr uint32_t SV_REPLY = 1u << 24;   // bits 0-15 reply type, 16-23 error code
+
+// PersistentKV/handle (service.clj:31-58) on one key's binding; lww = LWWKV/handle (service.clj:66-95),
+// whose cas has no create_if_not_exists branch
+__device__ __forceinline__ void kv_eval(bool present, uint32_t cur, const SvReq& q, bool lww, SvRep& r,
+                                        bool& n_present, uint32_t& n_val) {
+  r.reply = false; r.otype = MS_T_ERROR; r.code = 0; r.value = 0;
+  n_present = present; n_val = cur;
+  if (q.type == MS_T_READ) {
+    r.reply = true;
+    if (present) { r.otype = MS_T_READ_OK; r.value = cur; } else r.code = 20;
+  } else if (q.type == MS_T_WRITE) {
+    r.reply = true; r.otype = MS_T_WRITE_OK;
+    n_present = true; n_val = (uint32_t)q.p1;
+  } else if (q.type == MS_T_CAS) {
+    const uint32_t from = (uint32_t)q.p1, to = (uint32_t)(q.p1 >> 32);
+    r.reply = true;
+    if (present) {
+      if (cur == from) { n_val = to; r.otype = MS_T_CAS_OK; } else r.code = 22;
+    } else if (!lww && (q.flags & MS_F_CREATE)) {
+      n_present = true; n_val = to; r.otype = MS_T_CAS_OK;
+    } else r.code = 20;
+  }
+}
+
+// seq-kv: the binding of `key` in state `index` = newest version written at or before it
+__device__ __forceinline__ bool seq_lookup(const Params& p, uint32_t key, uint32_t index, uint32_t& v) {
+  const uint32_t cnt = p.sv_seq_vcnt[key];
+  const uint32_t m = cnt < kSeqHist ? cnt : kSeqHist;
+  for (uint32_t j = 1; j <= m; j++) {
+    const size_t sl = (size_t)key * kSeqHist + (cnt - j) % kSeqHist;
+    if (p.sv_seq_vidx[sl] <= index) { v = p.sv_seq_vval[sl]; return p.sv_seq_vhas[sl] != 0; }
+  }
+  v = 0;
+  return false;
+}
+
+// One request against service `svc` (MS_SVC_*), executed by one thread: requests of a service are
+// handled one at a time (an atom, service.clj:147-156).  rnd = the draw behind rand-int.
+__device__ void service_handle(const Params& p, uint32_t svc, const SvReq& q, uint32_t rnd, SvRep& r) {
+  bool np_; uint32_t nv;
+  if (svc == MS_SVC_LIN_TSO) {                                       // service.clj:123-129
+    r.reply = q.type == MS_T_TS; r.otype = MS_T_TS_OK; r.code = 0; r.value = 0;
+    if (r.reply) r.value = (uint32_t)(p.sv_scalars[0]++);
+    return;
+  }
+  if (svc == MS_SVC_LIN_KV) {
+    kv_eval(p.sv_lin_has[q.key] != 0, p.sv_lin_val[q.key], q, false, r, np_, nv);
+    if (r.reply) { p.sv_lin_has[q.key] = np_ ? 1 : 0; p.sv_lin_val[q.key] = nv; }
+    return;
+  }
+  if (svc == MS_SVC_LWW_KV) {                                        // replica (rand-int 2), never merged
+    const size_t o = (size_t)(rnd >> 31) * p.sv_n_keys + q.key;
+    kv_eval(p.sv_lww_has[o] != 0, p.sv_lww_val[o], q, true, r, np_, nv);
+    if (r.reply) { p.sv_lww_has[o] = np_ ? 1 : 0; p.sv_lww_val[o] = nv; }
+    return;
+  }
+  // Sequential (service.clj:168-214)
+  const uint32_t last = (uint32_t)p.sv_scalars[1];
+  const uint32_t ci = p.sv_seq_cli[q.src];
+  uint32_t index = ci + (uint32_t)(((uint64_t)rnd * (uint64_t)(last - ci + 1u)) >> 32);
+  const uint32_t resident = last + 1u < kSeqBuffer ? last + 1u : kSeqBuffer;
+  const uint32_t oldest = last + 1u - resident;
+  if (index < oldest) index = oldest;                                // states older than the ring buffer are gone
+  uint32_t cur;
+  const bool present = seq_lookup(p, q.key, index, cur);
+  kv_eval(present, cur, q, false, r, np_, nv);
+  if (!r.reply) return;
+  if (np_ == present && (!np_ || nv == cur)) {                       // state unchanged: stay on that timeline point
+    p.sv_seq_cli[q.src] = index;
+    return;
+  }
+  uint32_t lcur;
+  const bool lpresent = seq_lookup(p, q.key, last, lcur);            // redo on the newest state, append the result
+  kv_eval(lpresent, lcur, q, false, r, np_, nv);
+  const uint32_t li = last + 1u;
+  p.sv_scalars[1] = li;
+  p.sv_seq_cli[q.src] = li;
+  if (np_ != lpresent || (np_ && nv != lcur)) {
+    const uint32_t cnt = p.sv_seq_vcnt[q.key];
+    const size_t sl = (size_t)q.key * kSeqHist + cnt % kSeqHist;
+    p.sv_seq_vidx[sl] = li; p.sv_seq_vval[sl] = nv; p.sv_seq_vhas[sl] = np_ ? 1 : 0;
+    p.sv_seq_vcnt[q.key] = cnt + 1u;
+  }
+}
+
+// WL = node-program families compiled in: bit 0 g-set (else echo / broadcast), bit 1 services.
 template <int CLS, int WL>
 __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
   constexpr uint32_t cls = CLS;
+  constexpr bool GS = (WL & 1) != 0;
+  constexpr bool SV = (WL & 2) != 0;
   DevState* st = p.st;
   if (round_skipped(p, st) || !st->slot_open) return;
 
@@ -896,11 +994,11 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
     }
     const uint4* myring = p.ring + (size_t)e * p.ring_cap * 3;
     const bool is_server = (kind == MS_KIND_SERVER);
-    const bool bcast = WL == 0 && is_server && p.workload == MS_W_BROADCAST;
+    const bool bcast = !GS && is_server && p.workload == MS_W_BROADCAST;
     // g-set periodic task (g_set.rb:34-39), evaluated before the node's receives: when due, the
     // node snapshots its set and sends it to every other node (emissions 0 .. n_servers-2)
     uint32_t n_timer = 0, fire_seq = 0, fire_p0 = 0;
-    if constexpr (WL == 1) {
+    if constexpr (GS) {
       if (is_server && p.gs_init[e] && now >= p.gs_next_fire[e]) {
         n_timer = p.n_servers - 1;
         fire_seq = p.gs_fires[e] + 1;
@@ -948,7 +1046,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
           const uint32_t type = tf & 0xFFFFu;
           const uint32_t fl = tf >> 16;
           uint32_t tc = TC_OTHER;
-          if constexpr (WL == 1) {
+          if constexpr (GS) {
             if (type == MS_T_INIT) tc = GT_INIT;
             else if (type == MS_T_ADD) tc = GT_ADD;
             else if (type == MS_T_READ) tc = GT_READ;
@@ -974,7 +1072,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
             if (v >= p.n_values || v > V_MASK) err_val = v;
             else val |= v | V_CAND;
           }
-          if constexpr (WL == 1) {
+          if constexpr (GS) {
             if (is_server && !cut && !(fl & MS_F_REPLY)) {
               if (tc == GT_ADD || tc == GT_REPL_ONE) {           // the element (g_set.rb:17-26)
                 if (v >= p.n_values || v > V_MASK) err_val = v;
@@ -1146,6 +1244,39 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
       }
       __syncthreads();
     }
+    if constexpr (SV) {
+      // ---- service endpoint: requests are handled one at a time in dequeue order (service.clj:147-156,
+      //      245-263) by one thread; the reply is parked in vals[] / keyB[] for the emit phase
+      if (kind == MS_KIND_SERVICE) {
+        if (tid == 0) {
+          uint32_t svc = 0;
+          while (svc < 4 && p.sv_ep[svc] != e) svc++;
+          uint32_t n_rep = 0;
+          for (uint32_t pos = 0; pos < n && svc < 4; pos++) {
+            const uint32_t i = ord[pos];
+            if (!(vals[i] & V_RECV)) continue;
+            const uint4* rp = myring + (size_t)((head + i) & p.ring_mask) * 3;
+            const uint4 vb = rp[1], vc = rp[2];
+            SvReq q;
+            q.src = vb.x; q.type = vc.x & 0xFFFFu; q.flags = vc.x >> 16; q.key = vc.y;
+            q.p1 = (uint64_t)vc.z | ((uint64_t)vc.w << 32);
+            const bool keyed = q.type == MS_T_READ || q.type == MS_T_WRITE || q.type == MS_T_CAS;
+            if (svc != MS_SVC_LIN_TSO && keyed && q.key >= p.sv_n_keys) { latch_error(st, E_VALUE_RANGE, q.key); continue; }
+            uint32_t x[4] = {0, 0, 0, 0};
+            if (svc == MS_SVC_SEQ_KV || svc == MS_SVC_LWW_KV)      // rand-int = word 3 of the reply's own draw
+              philox4x32_10(n_rep, e, (uint32_t)round, (uint32_t)(round >> 32), p.seed_lo, p.seed_hi, x);
+            SvRep r;
+            service_handle(p, svc, q, x[3], r);
+            if (r.reply) {
+              vals[i] |= SV_REPLY | (r.code << 16) | r.otype;
+              keyB[pos] = r.value;
+              n_rep++;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
     // resolve winners and publish packed counts in sorted order:
     //   emit (bits 0-31) | recv (32-47) | new (48-63)
     for (int pos = tid; pos < (int)n; pos += nt) {
@@ -1170,7 +1301,10 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
       uint64_t c = 0;
       if (val & V_RECV) {
         c = 1ull << 32;
-        if constexpr (WL == 1) {
+        if constexpr (SV) {
+          if (kind == MS_KIND_SERVICE && (val & SV_REPLY)) c |= 1;
+        }
+        if constexpr (GS) {
           if (is_server) {
             const uint32_t mt = meta[i];
             c |= gset_emit_count(mt);
@@ -1197,7 +1331,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
     n_ev_local = n_recv + n_emit; n_em_local = n_emit;
     PHASE_MARK(4);
 
-    if constexpr (WL == 1) {
+    if constexpr (GS) {
       if (is_server) {
         // ---- g-set state: snapshot for the periodic task, then the window in id order.  Unions
         //      commute, so the window is applied in segments cut at the reads; each read sees
@@ -1239,13 +1373,13 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
                 if ((val & V_RECV) && !(mt & M_REPLY) && ((mt >> M_TC_SHIFT) & 7u) == GT_REPL_FULL)
                   acc |= p.gs_snap[(size_t)(val & V_MASK) * p.bm_words + w];
               }
-              if (acc) myset[w] |= acc;
+              if (acc) myset[w] = __ldcg(myset + w) | acc;   // the adds above were atomics: read at L2
             }
             __syncthreads();
           }
           if (k < n_reads) {
             uint32_t cnt = 0;
-            for (uint32_t w = tid; w < p.bm_words; w += nt) cnt += __popc(myset[w]);
+            for (uint32_t w = tid; w < p.bm_words; w += nt) cnt += __popc(__ldcg(myset + w));
             const uint32_t total = block_sum_u32(cnt, s_wcnt);
             if (tid == 0) keyB[seg_hi] = total;            // keyB is free after the ordering phase
             seg_lo = seg_hi + 1;
@@ -1388,7 +1522,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
       uint32_t direct = 0;
       bool has_direct = false;
       bool timer_emission = false;
-      if constexpr (WL == 1) {
+      if constexpr (GS) {
         if (valid && j < n_timer) {
           // replicate_full to the j-th other node (node.rb:104-108 other_node_ids, g_set.rb:36-38)
           timer_emission = true;
@@ -1435,7 +1569,19 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
           MsgView w;
           w.src = vb.x; w.msg_id = vb.z; w.tf = vc.x; w.p0 = vc.y;
           const uint64_t p1 = (uint64_t)vc.z | ((uint64_t)vc.w << 32);
-          if constexpr (WL == 1) {
+          bool svc_emission = false;
+          if constexpr (SV) {
+            if (kind == MS_KIND_SERVICE) {
+              // the reply computed by the sequential pass + :in_reply_to (service.clj:255-258)
+              svc_emission = true;
+              r.src = e; r.dest = w.src; r.msg_id = 0; r.in_reply_to = w.msg_id;
+              r.tf = (val & 0xFFFFu) | ((uint32_t)MS_F_REPLY << 16);
+              r.p0 = (val >> 16) & 0xFFu;
+              r.p1 = keyB[pos];
+            }
+          }
+          if (svc_emission) {
+          } else if constexpr (GS) {
             // g_set.rb:13-21: replies only; the set size a read reports was computed at its cut point
             const uint32_t tc = (mt >> M_TC_SHIFT) & 7u;
             r.src = e; r.dest = w.src; r.msg_id = 0; r.in_reply_to = w.msg_id; r.p0 = 0; r.p1 = 0;
@@ -1454,7 +1600,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
     }
     if (tid == 0 && is_server) {
       if (p.workload == MS_W_ECHO && p.next_msg_id && n_emit) p.next_msg_id[e] = msg_id_base + n_emit;
-      if constexpr (WL == 0) {
+      if constexpr (!GS) {
       if (p.set_count && n_new) p.set_count[e] = set_before + n_new;
       } else {
         // periodic task bookkeeping: the run advances its schedule first, an init received this
@@ -1576,19 +1722,21 @@ __global__ void k_journal_expand(Params p, uint64_t r0, uint32_t n_rounds, uint6
 extern "C" {
 
 typedef void (*msk_round_fn)(msd::Params, uint32_t);
-// round kernel of (node program family, window-size class)
-static msk_round_fn msk_round_kernel(uint32_t workload, int cls) {
-  static const msk_round_fn tab[2][4] = {
+// round kernel of (node-program families: bit 0 g-set, bit 1 services; window-size class)
+static msk_round_fn msk_round_kernel(uint32_t family, int cls) {
+  static const msk_round_fn tab[4][4] = {
       {msd::k_round<0, 0>, msd::k_round<1, 0>, msd::k_round<2, 0>, msd::k_round<3, 0>},
-      {msd::k_round<0, 1>, msd::k_round<1, 1>, msd::k_round<2, 1>, msd::k_round<3, 1>}};
-  return tab[workload == MS_W_GSET ? 1 : 0][cls];
+      {msd::k_round<0, 1>, msd::k_round<1, 1>, msd::k_round<2, 1>, msd::k_round<3, 1>},
+      {msd::k_round<0, 2>, msd::k_round<1, 2>, msd::k_round<2, 2>, msd::k_round<3, 2>},
+      {msd::k_round<0, 3>, msd::k_round<1, 3>, msd::k_round<2, 3>, msd::k_round<3, 3>}};
+  return tab[family & 3u][cls];
 }
 
 cudaError_t msk_round_smem_attr(size_t bytes) {
   cudaError_t e = cudaSuccess;
-  for (uint32_t wl = MS_W_ECHO; wl <= MS_W_GSET && e == cudaSuccess; wl += 2)   // one workload of each family
+  for (uint32_t f = 0; f < 4 && e == cudaSuccess; f++)
     for (int c = 0; c < 4 && e == cudaSuccess; c++)
-      e = cudaFuncSetAttribute(msk_round_kernel(wl, c), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+      e = cudaFuncSetAttribute(msk_round_kernel(f, c), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   return e;
 }
 
@@ -1600,7 +1748,7 @@ void msk_set_bit(uint32_t* words, size_t word, uint32_t bit, cudaStream_t s) {
 
 int msk_round_occupancy(int threads, size_t smem) {
   int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msk_round_kernel(MS_W_BROADCAST, 0), threads, smem) != cudaSuccess) return 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msk_round_kernel(0, 0), threads, smem) != cudaSuccess) return 1;
   return nb < 1 ? 1 : nb;
 }
 
@@ -1630,7 +1778,7 @@ void msk_launch_round(const msd::Params* p, int n_classes, const uint32_t* caps,
       const size_t sm = msk_round_smem_bytes(caps[c]);
       cudaStream_t sc = (fork && c != n_classes - 1) ? aux[c] : s;
       if (sc != s) cudaStreamWaitEvent(sc, aux_ev[0], 0);
-      const msk_round_fn kern = msk_round_kernel(p->workload, c < 3 ? c : 3);
+      const msk_round_fn kern = msk_round_kernel(p->family, c < 3 ? c : 3);
       MS_LAUNCH(kern, grids[c], threads[c], sm, sc, *p, caps[c]);
       if (sc != s) cudaEventRecord(aux_ev[1 + c], sc);
     }

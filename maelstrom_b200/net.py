@@ -8,7 +8,7 @@ the reference's own net).  Node ids are strings: "n<i>" are the simulated server
 ids starting with "c" are clients (util.clj:7-10), anything else is a host endpoint.
 """
 from . import errors
-from .engine import F_MSG_ID, F_REPLY, KIND_CLIENT, KIND_HOST, TYPES, TYPE_NAMES
+from .engine import F_MSG_ID, F_REPLY, KIND_CLIENT, KIND_HOST, KIND_SERVICE, SERVICES, TYPES, TYPE_NAMES
 
 
 class NodeNotFound(Exception):
@@ -42,6 +42,16 @@ class Net:
             self.names[idx] = node_id
         return self
 
+    def start_services(self, names=SERVICES):
+        """service/start-services! with service/default-services (service.clj:265-296): the four
+        Maelstrom-provided services join the network as device-resident endpoints."""
+        for name in names:
+            if name not in self.ids:
+                idx = self.sim.add_endpoint(name, KIND_SERVICE)
+                self.ids[name] = idx
+                self.names[idx] = name
+        return self
+
     def remove_node(self, node_id):                                   # remove-node!  net.clj:148-152
         idx = self.ids.pop(node_id, None)
         if idx is not None:
@@ -70,6 +80,16 @@ class Net:
             p0 = int(body.get("code", 13))
         elif t == "add":
             p0 = int(body["element"])
+        create = False
+        if "key" in body and t in ("read", "write", "cas"):           # service requests (doc/services.md)
+            p0 = int(body["key"])
+            if t == "write":
+                p1 = int(body["value"])
+            elif t == "cas":
+                p1 = int(body["from"]) | (int(body["to"]) << 32)
+                create = bool(body.get("create_if_not_exists"))
+            return self._body(self._type_code(t), msg_id=body.get("msg_id"), in_reply_to=body.get("in_reply_to"),
+                              p0=p0, p1=p1, create=create)
         extra = {k: v for k, v in body.items()
                  if k not in ("type", "msg_id", "in_reply_to", "message", "echo", "code", "text", "element")}
         if extra and p1 == 0:
@@ -94,6 +114,10 @@ class Net:
         elif t == "error":
             body["code"] = int(m["p0"])
             body["text"] = errors.name(int(m["p0"]))
+        elif t == "read_ok" and self.names.get(int(m["src"])) in SERVICES:
+            body["value"] = int(m["p1"])                                # service.clj:38-40
+        elif t == "ts_ok":
+            body["ts"] = int(m["p1"])                                   # service.clj:127-128
         elif t == "read_ok":
             # the device message carries the set size; the members are read back from the node
             src = int(m["src"])

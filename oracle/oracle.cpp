@@ -181,6 +181,112 @@ struct Emit {                 // one emission of a node program
   std::vector<uint32_t> snap; // read_ok value list (the set as of the read)
 };
 
+// ------------------------------------------------------------- services (service.clj)
+struct KVMap {                // PersistentKV's / LWWKV's :m (values only: timestamps never decide anything, see Service)
+  std::map<uint32_t, uint32_t> m;
+  bool operator==(const KVMap& o) const { return m == o.m; }
+};
+
+struct SvcReply {
+  bool reply = false;         // false: `case` had no matching clause -> exception, logged, no reply (service.clj:262-263)
+  uint16_t type = 0;
+  uint32_t p0 = 0;
+  uint64_t p1 = 0;
+};
+
+// PersistentKV/handle (service.clj:31-58); lww = LWWKV/handle (service.clj:66-95), whose cas has no
+// create_if_not_exists branch.  Returns the new state.
+static KVMap kv_handle(const KVMap& st, const or_body& q, bool lww, SvcReply& r) {
+  KVMap out = st;
+  const uint32_t k = q.p0;
+  auto it = st.m.find(k);
+  r = SvcReply();
+  switch (q.type) {
+    case OR_T_READ:
+      r.reply = true;
+      if (it != st.m.end()) { r.type = OR_T_READ_OK; r.p1 = it->second; }
+      else { r.type = OR_T_ERROR; r.p0 = 20; }                           // key does not exist
+      break;
+    case OR_T_WRITE:
+      r.reply = true; r.type = OR_T_WRITE_OK;
+      out.m[k] = (uint32_t)q.p1;
+      break;
+    case OR_T_CAS: {
+      const uint32_t from = (uint32_t)q.p1, to = (uint32_t)(q.p1 >> 32);
+      r.reply = true;
+      if (it != st.m.end()) {
+        if (it->second == from) { out.m[k] = to; r.type = OR_T_CAS_OK; }
+        else { r.type = OR_T_ERROR; r.p0 = 22; }                         // precondition failed
+      } else if (!lww && (q.flags & OR_F_CREATE)) {
+        out.m[k] = to; r.type = OR_T_CAS_OK;
+      } else { r.type = OR_T_ERROR; r.p0 = 20; }
+      break;
+    }
+    default: break;
+  }
+  return out;
+}
+
+struct Service {
+  int type = OR_SVC_LIN_KV;
+  KVMap lin;                               // Linearizable(PersistentKV): one state in an atom (service.clj:147-156)
+  uint64_t ts = 0;                         // PersistentTSO (service.clj:123-129)
+  // Sequential (service.clj:168-214): ring buffer of states, last index, per-client last observed index
+  std::deque<KVMap> buffer;
+  uint32_t buffer_size = 32;
+  uint64_t last_index = 0;
+  std::map<uint32_t, uint64_t> clients;
+  // Eventual(2 x LWWKV) (service.clj:218-251).  The merged replica computed at :229-232 is
+  // dropped: the second `replicas'` binding (:236) rebuilds from the unmerged vector.  So the
+  // replicas never exchange state and LWW timestamps never decide anything; a request is
+  // handled by replica (rand-int 2).
+  KVMap replicas[2];
+
+  SvcReply handle(uint32_t client, const or_body& q, uint32_t rnd) {
+    SvcReply r;
+    switch (type) {
+      case OR_SVC_LIN_KV: {
+        KVMap st2 = kv_handle(lin, q, false, r);
+        if (r.reply) lin = st2;
+        return r;
+      }
+      case OR_SVC_LIN_TSO:
+        if (q.type == OR_T_TS) { r.reply = true; r.type = OR_T_TS_OK; r.p1 = ts++; }
+        return r;
+      case OR_SVC_LWW_KV: {
+        const uint32_t i = rnd >> 31;                                    // (rand-int 2)
+        KVMap st2 = kv_handle(replicas[i], q, true, r);
+        if (r.reply) replicas[i] = st2;
+        return r;
+      }
+      default: break;
+    }
+    // Sequential
+    if (buffer.empty()) buffer.push_back(KVMap());
+    auto ci_it = clients.find(client);
+    const uint64_t ci = ci_it == clients.end() ? 0 : ci_it->second;
+    uint64_t index = ci + (((uint64_t)rnd * (last_index - ci + 1)) >> 32);   // :182-186
+    // states older than the ring buffer are gone; the reference indexes the buffer with a
+    // negative offset (:190) whose out-of-range behaviour belongs to amalloy/ring-buffer
+    // (third party, absent).  Spec: use the oldest resident state.
+    const uint64_t oldest = last_index + 1 - buffer.size();
+    if (index < oldest) index = oldest;
+    const KVMap& st = buffer[(size_t)(index - oldest)];
+    KVMap st2 = kv_handle(st, q, false, r);
+    if (!r.reply) return r;                                             // exception inside swap!: nothing changes
+    if (st2 == st) {                                                    // :195-199
+      clients[client] = index;
+      return r;
+    }
+    KVMap latest2 = kv_handle(buffer.back(), q, false, r);              // :203-209
+    last_index++;
+    clients[client] = last_index;
+    buffer.push_back(latest2);
+    if (buffer.size() > buffer_size) buffer.pop_front();
+    return r;
+  }
+};
+
 struct Endpoint {
   std::string name;
   int kind = OR_KIND_SERVER;
@@ -194,6 +300,7 @@ struct Endpoint {
   bool initialized = false;             // node.rb:22-36: periodic tasks start after init
   int64_t next_fire = 0;                // g-set: next run of the `every 5` task (g_set.rb:34)
   uint64_t fires = 0;                   // g-set: replication runs so far
+  Service svc;                          // OR_KIND_SERVICE
 };
 
 }  // namespace
@@ -432,6 +539,23 @@ struct or_sim {
           case OR_KIND_HOST:
             ep.mailbox.push_back(m);
             break;
+          case OR_KIND_SERVICE: {         // service-thread (service.clj:245-263)
+            or_body q;
+            q.type = m.type; q.flags = m.flags; q.msg_id = m.msg_id; q.in_reply_to = m.in_reply_to;
+            q.p0 = m.p0; q.p1 = m.p1;
+            // rand-int: word 3 of the Philox draw of the reply this request would emit
+            const uint32_t ctr[4] = {(uint32_t)out.size(), e, (uint32_t)round, (uint32_t)(round >> 32)};
+            const uint32_t key[2] = {cfg.seed_lo, cfg.seed_hi};
+            uint32_t x[4];
+            philox(ctr, key, x);
+            const SvcReply r = ep.svc.handle(m.src, q, x[3]);
+            if (r.reply) {
+              or_msg rm = reply_to(m, r.type);          // body + :in_reply_to (service.clj:255-258)
+              rm.p0 = r.p0; rm.p1 = r.p1;
+              out.push_back(Emit(rm));
+            }
+            break;
+          }
           default:
             if (cfg.workload == OR_W_ECHO) node_echo(e, m, out);
             else if (cfg.workload == OR_W_BROADCAST) node_broadcast(e, m, out);
@@ -482,6 +606,13 @@ int or_add_endpoint(or_sim* s, const char* name, int kind) {   // net.clj:139-14
   Endpoint ep;
   ep.name = name;
   ep.kind = kind;
+  if (kind == OR_KIND_SERVICE) {                                  // service.clj:290-296
+    if (ep.name == "lin-kv") ep.svc.type = OR_SVC_LIN_KV;
+    else if (ep.name == "seq-kv") ep.svc.type = OR_SVC_SEQ_KV;
+    else if (ep.name == "lww-kv") ep.svc.type = OR_SVC_LWW_KV;
+    else if (ep.name == "lin-tso") ep.svc.type = OR_SVC_LIN_TSO;
+    else return -2;
+  }
   s->eps.push_back(ep);
   return (int)s->eps.size() - 1;
 }
@@ -606,6 +737,23 @@ size_t or_read_snapshot(or_sim* s, uint64_t msg_id, uint32_t* vals, size_t cap) 
 }
 
 uint64_t or_client_replies(or_sim* s) { return s->client_replies; }
+
+struct or_service { Service s; };
+or_service* or_service_new(int svc_type, uint32_t buffer_size) {
+  or_service* p = new or_service();
+  p->s.type = svc_type;
+  if (buffer_size) p->s.buffer_size = buffer_size;
+  return p;
+}
+void or_service_free(or_service* p) { delete p; }
+int or_service_handle(or_service* p, uint32_t client, const or_body* req, uint32_t rnd, or_body* reply) {
+  const SvcReply r = p->s.handle(client, *req, rnd);
+  if (!r.reply) return 0;
+  std::memset(reply, 0, sizeof *reply);
+  reply->type = r.type; reply->flags = OR_F_REPLY; reply->in_reply_to = req->msg_id;
+  reply->p0 = r.p0; reply->p1 = r.p1;
+  return 1;
+}
 
 size_t or_topology(uint32_t topo, uint32_t n, uint32_t node, uint32_t* out, size_t cap) {
   std::vector<uint32_t> nb = topology_neighbors(topo, n, node);

@@ -83,16 +83,21 @@ enum { OR_W_ECHO = 0, OR_W_BROADCAST = 1, OR_W_GSET = 2 };
 enum { OR_TOPO_GRID = 0, OR_TOPO_LINE = 1, OR_TOPO_TOTAL = 2,
        OR_TOPO_TREE2 = 3, OR_TOPO_TREE3 = 4, OR_TOPO_TREE4 = 5 };
 enum { OR_DIST_CONSTANT = 0, OR_DIST_UNIFORM = 1, OR_DIST_EXPONENTIAL = 2 };
-enum { OR_KIND_SERVER = 0, OR_KIND_CLIENT = 1, OR_KIND_HOST = 2, OR_KIND_SIM_CLIENT = 3 };
+enum { OR_KIND_SERVER = 0, OR_KIND_CLIENT = 1, OR_KIND_HOST = 2, OR_KIND_SIM_CLIENT = 3,
+       OR_KIND_SERVICE = 4 };  /* lin-kv / seq-kv / lww-kv / lin-tso by name (service.clj:290-296) */
+enum { OR_SVC_LIN_KV = 0, OR_SVC_SEQ_KV = 1, OR_SVC_LWW_KV = 2, OR_SVC_LIN_TSO = 3 };
 enum {
   OR_T_INIT = 1, OR_T_INIT_OK = 2, OR_T_ERROR = 3,
   OR_T_ECHO = 10, OR_T_ECHO_OK = 11,
   OR_T_TOPOLOGY = 20, OR_T_TOPOLOGY_OK = 21, OR_T_BROADCAST = 22,
   OR_T_BROADCAST_OK = 23, OR_T_READ = 24, OR_T_READ_OK = 25,
   OR_T_ADD = 30, OR_T_ADD_OK = 31, OR_T_REPLICATE_ONE = 32,
-  OR_T_REPLICATE_FULL = 33
+  OR_T_REPLICATE_FULL = 33,
+  /* services (service.clj:31-141): read = OR_T_READ with p0 = key, read_ok p1 = value;
+   * write p0 = key, p1 = value; cas p0 = key, p1 = from | to << 32; ts_ok p1 = ts */
+  OR_T_WRITE = 40, OR_T_WRITE_OK = 41, OR_T_CAS = 42, OR_T_CAS_OK = 43, OR_T_TS = 44, OR_T_TS_OK = 45
 };
-enum { OR_F_MSG_ID = 1, OR_F_REPLY = 2 };
+enum { OR_F_MSG_ID = 1, OR_F_REPLY = 2, OR_F_CREATE = 4 /* cas create_if_not_exists */ };
 
 typedef struct or_sim or_sim;
 
@@ -125,6 +130,14 @@ void     or_stats(or_sim*, uint64_t out[9]);
 size_t   or_node_set(or_sim*, uint32_t node, uint32_t* vals, size_t cap);
 size_t   or_read_snapshot(or_sim*, uint64_t msg_id, uint32_t* vals, size_t cap);
 uint64_t or_client_replies(or_sim*);
+
+/* A service on its own, driven like the reference's unit test drives handle!
+ * (test/maelstrom/service_test.clj:6-53): `rnd` is the 32-bit draw standing in for rand-int. */
+typedef struct or_service or_service;
+or_service* or_service_new(int svc_type, uint32_t buffer_size);
+void     or_service_free(or_service*);
+/* returns 1 and fills the reply (type, p0, p1) or 0 when the service throws (unknown request) */
+int      or_service_handle(or_service*, uint32_t client, const or_body* req, uint32_t rnd, or_body* reply);
 
 /* pure helpers, exported so the tests can pin them to golden vectors */
 size_t   or_topology(uint32_t topo, uint32_t n, uint32_t node, uint32_t* out, size_t cap);

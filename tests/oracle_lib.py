@@ -28,11 +28,12 @@ assert BODY_DTYPE.itemsize == 24 and OP_DTYPE.itemsize == 40
 W_ECHO, W_BROADCAST, W_GSET = 0, 1, 2
 TOPO = {"grid": 0, "line": 1, "total": 2, "tree": 3, "tree2": 3, "tree3": 4, "tree4": 5}
 DIST = {"constant": 0, "uniform": 1, "exponential": 2}
-KIND_SERVER, KIND_CLIENT, KIND_HOST, KIND_SIM_CLIENT = 0, 1, 2, 3
+KIND_SERVER, KIND_CLIENT, KIND_HOST, KIND_SIM_CLIENT, KIND_SERVICE = 0, 1, 2, 3, 4
+SVC = {"lin-kv": 0, "seq-kv": 1, "lww-kv": 2, "lin-tso": 3}
 T = dict(init=1, init_ok=2, error=3, echo=10, echo_ok=11, topology=20, topology_ok=21,
          broadcast=22, broadcast_ok=23, read=24, read_ok=25, add=30, add_ok=31,
-         replicate_one=32, replicate_full=33)
-F_MSG_ID, F_REPLY = 1, 2
+         replicate_one=32, replicate_full=33, write=40, write_ok=41, cas=42, cas_ok=43, ts=44, ts_ok=45)
+F_MSG_ID, F_REPLY, F_CREATE = 1, 2, 4
 RECV_BIT = 1 << 63
 
 
@@ -102,6 +103,10 @@ def lib():
         L.or_latency_draw.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         L.or_loss_threshold.restype = C.c_uint64
         L.or_loss_threshold.argtypes = [C.c_double]
+        L.or_service_new.restype = C.c_void_p
+        L.or_service_new.argtypes = [C.c_int, C.c_uint32]
+        L.or_service_free.argtypes = [C.c_void_p]
+        L.or_service_handle.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(Body), C.c_uint32, C.POINTER(Body)]
         _lib = L
     return _lib
 
@@ -125,10 +130,11 @@ def latency_draw(dist, mean_ms, scale, x):
     return int(lib().or_latency_draw(DIST[dist], mean_ms, scale, xs.ctypes.data))
 
 
-def body(type, msg_id=None, in_reply_to=None, p0=0, p1=0):
+def body(type, msg_id=None, in_reply_to=None, p0=0, p1=0, create=False):
     b = Body()
     b.type = T[type] if isinstance(type, str) else type
-    b.flags = (F_MSG_ID if msg_id is not None else 0) | (F_REPLY if in_reply_to is not None else 0)
+    b.flags = ((F_MSG_ID if msg_id is not None else 0) | (F_REPLY if in_reply_to is not None else 0) |
+               (F_CREATE if create else 0))
     b.msg_id = msg_id or 0
     b.in_reply_to = in_reply_to or 0
     b.p0 = p0
@@ -252,3 +258,23 @@ class Sim:
 
     def client_replies(self):
         return int(self.L.or_client_replies(self.h))
+
+
+class Service:
+    """One service on its own (oracle's restatement of service.clj), driven the way
+    test/maelstrom/service_test.clj drives handle!; rnd = the 32-bit draw behind rand-int."""
+
+    def __init__(self, name, buffer_size=0):
+        self.L = lib()
+        self.h = self.L.or_service_new(SVC[name], buffer_size)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.or_service_free(self.h)
+            self.h = None
+
+    def handle(self, client, req, rnd=0):
+        out = Body()
+        if not self.L.or_service_handle(self.h, client, C.byref(req), rnd & 0xFFFFFFFF, C.byref(out)):
+            return None
+        return out
