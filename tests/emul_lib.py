@@ -38,7 +38,8 @@ def load():
     global _lib
     if _lib is None:
         from maelstrom_b200._lib import SYMBOLS
-        L = C.CDLL(build())
+        # MS_EMUL_LIB: a prebuilt variant of the same library (tools/emul_asan.sh: ASan + UBSan)
+        L = C.CDLL(os.environ.get("MS_EMUL_LIB") or build())
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)
             fn.restype = res
