@@ -180,8 +180,13 @@ uint64_t warp_op(int op, unsigned mask, uint64_t v, int arg) {
 }
 
 void relax() {
-  if (g_s) g_s->progress++;
+  // a spin-wait (k_barrier polling a peer's flag): let the other host threads (shards) run AND
+  // the other fibers of this CTA, which on a GPU would be running concurrently
   std::this_thread::yield();
+  if (g_s && g_s->body) {
+    g_s->progress++;
+    yield_to_scheduler();
+  }
 }
 
 unsigned char* dyn_smem() { return sched()->smem; }
@@ -208,9 +213,25 @@ static void run_cta(Sched* s, unsigned nt) {
     for (int r = 3; r <= 8; r++) p[-r] = nullptr;   // rbp rbx r12-r15
     s->sp[t] = (void*)(p - 8);
   }
+  // MS_EMUL_ORDER: 0 = threads resume in index order (default), 1 = reverse, 2 = a different
+  // pseudo-random order every sweep.  Results must not depend on it: a missing barrier usually does.
+  static const int order_mode = getenv("MS_EMUL_ORDER") ? atoi(getenv("MS_EMUL_ORDER")) : 0;
+  static thread_local uint32_t lcg = 12345u;
   while (s->live) {
     const uint64_t before = s->progress;
-    for (unsigned t = 0; t < nt; t++) {
+    uint32_t mul = 1, add = 0;
+    if (order_mode == 2) {            // t -> (t * odd + add) mod 2^k is a permutation of [0, 2^k)
+      lcg = lcg * 1664525u + 1013904223u;
+      mul = (lcg >> 8) | 1u;
+      add = lcg >> 20;
+    }
+    unsigned span = 1;
+    while (span < nt) span <<= 1;
+    for (unsigned u = 0; u < span; u++) {
+      unsigned t = u;
+      if (order_mode == 1) t = span - 1 - u;
+      else if (order_mode == 2) t = (u * mul + add) & (span - 1);
+      if (t >= nt) continue;
       if (s->done[t]) continue;
       s->cur = t;
       tls.tid.x = t;
@@ -229,7 +250,9 @@ void launch(unsigned grid, unsigned block, size_t dyn, const std::function<void(
   tls.bdim = dim3{block, 1, 1};
   tls.gdim = dim3{grid, 1, 1};
   tls.tid = uint3{0, 0, 0};
-  for (unsigned b = 0; b < grid; b++) {
+  static const int order_mode = getenv("MS_EMUL_ORDER") ? atoi(getenv("MS_EMUL_ORDER")) : 0;
+  for (unsigned bb = 0; bb < grid; bb++) {
+    const unsigned b = order_mode ? grid - 1 - bb : bb;     // CTAs must not depend on launch order either
     tls.bid = uint3{b, 0, 0};
     memset(s->smem, 0xCD, dyn);
     run_cta(s, block);
