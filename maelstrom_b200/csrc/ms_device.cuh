@@ -165,6 +165,10 @@ struct Params {
   uint32_t* sv_seq_vval;
   uint8_t*  sv_seq_vhas;
   uint32_t* sv_seq_vcnt;     // versions written per key
+  // g-set snapshots of every shard (index = shard): a replicate_full is merged by reading the
+  // sender's snapshot row where it lives, over NVLink peer memory when the sender is remote
+  uint32_t* gs_snap_sh[8];
+  uint32_t* gs_tag_sh[8];
 };
 
 constexpr uint32_t kSeqBuffer = 32;             // (sequential 32 ...), service.clj:206-208

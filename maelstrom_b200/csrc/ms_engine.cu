@@ -418,10 +418,6 @@ static int build_sim(ms_sim* s, const ms_config* in) {
     set_err("bad workload/topology/latency_dist");
     return MS_ERR_ARG;
   }
-  if (c.workload == MS_W_GSET && c.n_shards > 1) {
-    set_err("workload g-set runs on one GPU for now (set snapshots are not yet mapped across shards)");
-    return MS_ERR_ARG;
-  }
   if (c.latency_dist != MS_DIST_CONSTANT && c.latency_mean_ms == 0) {
     // (exponential-distribution (/ 0)) divides by zero; (integer-distribution 0 0) is empty (net.clj:76-77)
     set_err("latency mean 0 is only valid with the constant distribution");
@@ -572,6 +568,8 @@ static int build_sim(ms_sim* s, const ms_config* in) {
     if ((rc = s->dalloc(&P.gs_fires, c.n_nodes))) return rc;
     if ((rc = s->dalloc(&P.gs_tag, rows))) return rc;
     if ((rc = s->dalloc(&P.gs_snap, rows * P.bm_words))) return rc;
+    P.gs_snap_sh[c.shard_id] = P.gs_snap;
+    P.gs_tag_sh[c.shard_id] = P.gs_tag;
   }
   if ((rc = s->dalloc(&P.inj_buf, c.inject_cap))) return rc;
   if ((rc = s->dalloc(&P.mail, c.mailbox_cap))) return rc;
@@ -710,7 +708,6 @@ int ms_add_endpoint(ms_sim* s, const char* id, int kind) {
     int svc = -1;
     for (int k = 0; k < 4; k++) if (!strcmp(id, names[k])) svc = k;
     if (svc < 0) { set_err("service endpoints are lin-kv, seq-kv, lww-kv or lin-tso (service.clj:290-296)"); return MS_ERR_ARG; }
-    if (s->P.n_shards > 1) { set_err("device-resident services run on one GPU for now"); return MS_ERR_ARG; }
     if (!s->P.sv_scalars) {
       int rc;
       Params& P = s->P;
@@ -1001,6 +998,7 @@ struct ShardBlob {   // MS_SHARD_BLOB_BYTES
   uint32_t magic, shard_id, n_shards, t_max;
   uint32_t max_endpoints, ring_cap, hist, pad;
   cudaIpcMemHandle_t ring, tail, head, rt_cnt, bar;
+  cudaIpcMemHandle_t gs_snap, gs_tag;   // g-set only (pad = 1)
 };
 static_assert(sizeof(ShardBlob) <= MS_SHARD_BLOB_BYTES, "blob too large");
 
@@ -1017,6 +1015,11 @@ int ms_shard_handles(ms_sim* s, void* blob_out) {
   CK(cudaIpcGetMemHandle(&b.head, s->P.head));
   CK(cudaIpcGetMemHandle(&b.rt_cnt, s->P.rt_cnt));
   CK(cudaIpcGetMemHandle(&b.bar, s->P.bar_sh[s->P.shard_id]));
+  if (s->P.gs_snap) {
+    b.pad = 1;
+    CK(cudaIpcGetMemHandle(&b.gs_snap, s->P.gs_snap));
+    CK(cudaIpcGetMemHandle(&b.gs_tag, s->P.gs_tag));
+  }
   memset(blob_out, 0, MS_SHARD_BLOB_BYTES);
   memcpy(blob_out, &b, sizeof b);
   return MS_OK;
@@ -1045,6 +1048,13 @@ int ms_shard_connect(ms_sim* s, uint32_t peer, const void* blob) {
   s->peer_ptrs.push_back(ptr); s->P.rt_cnt_sh[peer] = (uint64_t*)ptr;
   CK(cudaIpcOpenMemHandle(&ptr, b.bar, cudaIpcMemLazyEnablePeerAccess));
   s->peer_ptrs.push_back(ptr); s->P.bar_sh[peer] = (uint32_t*)ptr;
+  if ((b.pad == 1) != (s->P.gs_snap != nullptr)) { set_err("ms_shard_connect: peer runs another workload"); return MS_ERR_ARG; }
+  if (b.pad == 1) {
+    CK(cudaIpcOpenMemHandle(&ptr, b.gs_snap, cudaIpcMemLazyEnablePeerAccess));
+    s->peer_ptrs.push_back(ptr); s->P.gs_snap_sh[peer] = (uint32_t*)ptr;
+    CK(cudaIpcOpenMemHandle(&ptr, b.gs_tag, cudaIpcMemLazyEnablePeerAccess));
+    s->peer_ptrs.push_back(ptr); s->P.gs_tag_sh[peer] = (uint32_t*)ptr;
+  }
   return MS_OK;
 }
 

@@ -1080,7 +1080,8 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
               } else if (tc == GT_REPL_FULL) {                   // the snapshot row of (src, run p1)
                 const uint32_t run = c[q].z;
                 const uint32_t rowi = src * p.gs_slots + (run & (p.gs_slots - 1));
-                if (src >= p.n_servers || p.gs_tag[rowi] != run) snap_gone = src;
+                if (src >= p.n_servers ||
+                    __ldcg(p.gs_tag_sh[owner_of(src, p.n_servers, p.n_shards)] + rowi) != run) snap_gone = src;
                 else val |= rowi;
               }
             }
@@ -1370,8 +1371,11 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
               for (uint32_t pos = seg_lo; pos < seg_hi; pos++) {
                 const uint32_t i = ord[pos];
                 const uint32_t val = vals[i], mt = meta[i];
-                if ((val & V_RECV) && !(mt & M_REPLY) && ((mt >> M_TC_SHIFT) & 7u) == GT_REPL_FULL)
-                  acc |= p.gs_snap[(size_t)(val & V_MASK) * p.bm_words + w];
+                if ((val & V_RECV) && !(mt & M_REPLY) && ((mt >> M_TC_SHIFT) & 7u) == GT_REPL_FULL) {
+                  const uint32_t srow = val & V_MASK;      // sender = srow / gs_slots; its shard holds the row
+                  const uint32_t* rows = p.gs_snap_sh[owner_of(srow / p.gs_slots, p.n_servers, p.n_shards)];
+                  acc |= __ldcg(rows + (size_t)srow * p.bm_words + w);
+                }
               }
               if (acc) myset[w] = __ldcg(myset + w) | acc;   // the adds above were atomics: read at L2
             }

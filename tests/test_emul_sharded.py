@@ -85,3 +85,89 @@ def test_emulated_shards_equal_oracle(world, n, per_tick, latency_ms):
         assert np.array_equal(ev[f], ev_o[f]), f
     assert st == o.stats()
     assert now == o.now and rnd == o.round
+
+
+def run_sharded_scenario(world, n, sim_kw, scenario):
+    """scenario(sim, body) runs identically on every shard (one host thread each); returns the
+    merged level-1 journal, summed stats and the common (now, round)."""
+    from maelstrom_b200 import _lib, body
+    from maelstrom_b200.engine import Sim
+    from maelstrom_b200.sharded import merge_journals
+    blobs, out, errs = [None] * world, [None] * world, []
+    sync = threading.Barrier(world)
+
+    def shard(rank):
+        try:
+            g = Sim(n, journal_level=1, n_shards=world, shard_id=rank, **sim_kw)
+            blob = (C.c_ubyte * _lib.SHARD_BLOB_BYTES)()
+            g._chk(g.L.ms_shard_handles(g.h, blob))
+            blobs[rank] = bytes(blob)
+            sync.wait()
+            for peer in range(world):
+                buf = (C.c_ubyte * _lib.SHARD_BLOB_BYTES).from_buffer_copy(blobs[peer])
+                g._chk(g.L.ms_shard_connect(g.h, peer, buf))
+            sync.wait()
+            scenario(g, body)
+            ev, _ = g.drain(bodies=False)
+            out[rank] = (ev, g.stats(), g.now, g.round)
+            sync.wait()
+            g.close()
+        except Exception:   # noqa: BLE001
+            import traceback
+            errs.append((rank, traceback.format_exc()))
+            sync.abort()
+
+    with emul_lib.use():
+        ts = [threading.Thread(target=shard, args=(r,)) for r in range(world)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join(timeout=600)
+    assert not errs, errs
+    stats = {}
+    for _, st, _, _ in out:
+        for c, d in st.items():
+            for k, v in d.items():
+                stats.setdefault(c, {}).setdefault(k, 0)
+                stats[c][k] += v
+    assert len({(o[2], o[3]) for o in out}) == 1
+    return merge_journals([o[0] for o in out]), stats, out[0][2], out[0][3]
+
+
+def check_against_oracle(o, scenario, ev, st, now, rnd):
+    scenario(o, O.body)
+    ev_o, _ = o.journal()
+    assert len(ev) == len(ev_o), (len(ev), len(ev_o))
+    for f in ("event_id", "time_ns", "msg_id", "src", "dest"):
+        assert np.array_equal(ev[f], ev_o[f]), f
+    assert st == o.stats()
+    assert now == o.now and rnd == o.round
+
+
+@pytest.mark.parametrize("world,dist,mean", [(2, "constant", 0), (3, "uniform", 3)])
+def test_emulated_shards_gset_and_services(world, dist, mean):
+    # g-set nodes merge snapshots that live on other shards; service endpoints live on whichever
+    # shard owns them; sim clients talk to both
+    from test_workload_gset import scheduled_adds_and_reads
+    from test_workload_services import SVC, random_service_ops
+    n = 12
+    kw = dict(n_values=512, gset_interval_ms=9, latency_dist=dist, latency_mean_ms=mean)
+
+    def scenario(s, body):
+        sv = {name: s.add_endpoint(name, O.KIND_SERVICE) for name in SVC}
+        cs = [s.add_endpoint("c%d" % i, O.KIND_SIM_CLIENT) for i in range(4)]
+        for i in range(n):
+            s.send(cs[0], i, body("init", msg_id=1000 + i))
+        a, _ = scheduled_adds_and_reads(n, 4, n_ticks=25, per_tick=4, seed=8)
+        a["src"] = a["src"] - n + cs[0]                 # the helper assumes clients start at index n
+        b = random_service_ops(4, cs[0], sv, n_ticks=25, per_tick=6, seed=9)
+        ops = np.concatenate([a, b])
+        ops = ops[np.argsort(ops["time_ns"], kind="stable")]
+        s.schedule(ops)
+        s.run(60_000_000)
+
+    ev, st, now, rnd = run_sharded_scenario(
+        world, n, dict(workload="g-set", ring_cap=512, max_window=512, journal_cap_log2=20, max_endpoints=n + 16, **kw),
+        scenario)
+    o = O.Sim(n, workload=O.W_GSET, **kw)
+    check_against_oracle(o, scenario, ev, st, now, rnd)
