@@ -92,10 +92,16 @@ enum {
    * p1 = value; write p0 = key, p1 = value; cas p0 = key, p1 = from | to << 32 (+ MS_F_CREATE);
    * ts_ok p1 = timestamp; errors: MS_T_ERROR with p0 = 20 / 22 (errors.edn).  Keys are integers
    * below ms_config.reserved[2]; values are 32-bit on the device. */
-  MS_T_WRITE = 40, MS_T_WRITE_OK = 41, MS_T_CAS = 42, MS_T_CAS_OK = 43, MS_T_TS = 44, MS_T_TS_OK = 45
+  MS_T_WRITE = 40, MS_T_WRITE_OK = 41, MS_T_CAS = 42, MS_T_CAS_OK = 43, MS_T_TS = 44, MS_T_TS_OK = 45,
+  /* Raft (raft.py:270-281,405-432,460-545): request_vote p0 = term, p1 = last_log_index |
+   * last_log_term << 32; *_res p0 = term, p1 = vote_granted / success; append_entries p0 = term,
+   * p1 = k: the sender's k-th append_entries; {prev_log_index, prev_log_term, leader_commit,
+   * entries} stay in the sender's payload heap on the device */
+  MS_T_REQUEST_VOTE = 50, MS_T_REQUEST_VOTE_RES = 51, MS_T_APPEND_ENTRIES = 52, MS_T_APPEND_ENTRIES_RES = 53
 };
 
-enum { MS_W_ECHO = 0, MS_W_BROADCAST = 1, MS_W_GSET = 2 };                  /* --workload, core.clj:36-47 */
+enum { MS_W_ECHO = 0, MS_W_BROADCAST = 1, MS_W_GSET = 2,                     /* --workload, core.clj:36-47 */
+       MS_W_RAFT = 3 };  /* lin-kv served by Raft nodes (demo/python/raft.py) */
 enum { MS_TOPO_GRID = 0, MS_TOPO_LINE = 1, MS_TOPO_TOTAL = 2,                /* --topology, broadcast.clj:169-178 */
        MS_TOPO_TREE2 = 3, MS_TOPO_TREE3 = 4, MS_TOPO_TREE4 = 5 };
 enum { MS_DIST_CONSTANT = 0, MS_DIST_UNIFORM = 1, MS_DIST_EXPONENTIAL = 2 }; /* --latency-dist, net.clj:73-77 */
@@ -147,7 +153,7 @@ typedef struct ms_config {
   uint32_t threads_per_node; /* CTA size of the round kernel (0 = auto) */
   uint32_t n_shards;         /* GPUs the endpoints are sharded over (0/1 = single GPU), <= 8 */
   uint32_t shard_id;         /* this process's shard */
-  uint32_t reserved[6];      /* [0] = rounds of id history to keep (0 = default); [1] = 1: replay round batches from a CUDA graph; [2] = keys per service store (0 = 4096) */
+  uint32_t reserved[6];      /* [0] = rounds of id history to keep (0 = default); [1] = 1: replay round batches from a CUDA graph; [2] = keys per service store / Raft KV (0 = 4096); [3] = Raft log capacity per node (0 = 4096) */
 } ms_config;
 
 typedef struct ms_sim ms_sim;
@@ -216,6 +222,10 @@ int ms_stats(ms_sim* sim, uint64_t out[9]);
 /* ------------------------------------------------------------------ node state read-back */
 size_t   ms_node_set(ms_sim* sim, uint32_t node, uint32_t* values, size_t cap);
 uint64_t ms_client_replies(ms_sim* sim);
+/* MS_W_RAFT: out = {state (0 nascent, 1 follower, 2 candidate, 3 leader), current_term,
+ * voted_for + 1, commit_index, last_applied, leader + 1, log size, keys in the KV store}
+ * (the fields of RaftNode, demo/python/raft.py:196-221) */
+int      ms_raft_state(ms_sim* sim, uint32_t node, uint64_t out[8]);
 
 /* device-side counters for roofline accounting: out = {rounds, sends, recvs,
  * kernel launches, lost, partition_drops, max_window, windows that needed the full sort} */

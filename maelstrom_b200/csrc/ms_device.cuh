@@ -21,7 +21,8 @@ constexpr uint8_t  kRemoved  = 0x80;          // endpoint kind after remove-node
 enum : uint32_t {
   E_NONE = 0, E_RING_OVERFLOW = 1, E_WINDOW_OVERFLOW = 2, E_JOURNAL_OVERFLOW = 3,
   E_INVALID_DEST = 4, E_HISTORY = 5, E_VALUE_RANGE = 6, E_MAIL_OVERFLOW = 7,
-  E_CALENDAR_OVERFLOW = 8, E_ID_RANGE = 9, E_BARRIER = 10, E_SNAPSHOT = 11
+  E_CALENDAR_OVERFLOW = 8, E_ID_RANGE = 9, E_BARRIER = 10, E_SNAPSHOT = 11,
+  E_RAFT_CAPACITY = 12
 };
 
 // Mutable per-simulation scalars, resident in HBM, committed by the last CTA of
@@ -169,6 +170,38 @@ struct Params {
   // sender's snapshot row where it lives, over NVLink peer memory when the sender is remote
   uint32_t* gs_snap_sh[8];
   uint32_t* gs_tag_sh[8];
+  // Raft nodes (MS_W_RAFT, demo/python/raft.py); layouts in ms_raft.cuh
+  struct RaftDev* rf_node;   // [n_servers] scalar state
+  uint4*    rf_log;          // [n_servers][rf_log_cap] entries, 2 vectors each
+  uint32_t* rf_kv_val;       // [n_servers][rf_n_keys] KVStore (raft.py:151-192)
+  uint8_t*  rf_kv_has;
+  int32_t*  rf_next;         // [n_servers][n_servers] next_index / match_index (leader state)
+  int32_t*  rf_match;
+  int32_t*  rf_scratch;      // [n_servers][n_servers] median scratch
+  uint4*    rf_cb;           // [n_servers][kRaftCallbacks] pending RPC closures, 2 vectors each
+  uint32_t* rf_votes;        // [n_servers][ceil(n_servers / 32)]
+  uint4*    rf_stage;        // [n_servers][rf_stage_cap] emissions of the node's step, 3 vectors each
+  uint4*    rf_heap;         // append_entries payloads: ring of vectors
+  unsigned long long* rf_heap_cursor;
+  uint64_t* rf_ext_off;      // [n_servers][kRaftExt] heap offset of the sender's k-th append_entries
+  uint32_t* rf_ext_tag;      // [n_servers][kRaftExt] k
+  uint32_t  rf_log_cap, rf_n_keys, rf_stage_cap, rf_heap_mask, rf_vote_words;
+};
+
+constexpr uint32_t kRaftCallbacks = 4096;       // pending-RPC table slots per node (oracle: same constant)
+constexpr uint32_t kRaftExt = 1024;             // append_entries payload handles kept per sender
+constexpr int64_t  kElectionTimeoutNs = 2000000000;   // raft.py:199
+constexpr int64_t  kHeartbeatNs = 1000000000;         // raft.py:200
+constexpr int64_t  kMinReplicationNs = 50000000;      // raft.py:201
+enum : int32_t { RAFT_NASCENT = 0, RAFT_FOLLOWER = 1, RAFT_CANDIDATE = 2, RAFT_LEADER = 3 };
+
+struct RaftDev {
+  int32_t  state;
+  uint32_t term;
+  int32_t  voted_for, leader;          // -1 = none
+  uint32_t commit_index, last_applied;
+  int64_t  election_deadline, step_down_deadline, last_replication;
+  uint32_t next_msg_id, log_size, appends, n_votes, kv_size, pad;
 };
 
 constexpr uint32_t kSeqBuffer = 32;             // (sequential 32 ...), service.clj:206-208

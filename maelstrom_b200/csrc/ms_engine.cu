@@ -62,6 +62,7 @@ static const char* dev_error_text(uint32_t code) {
     case E_CALENDAR_OVERFLOW: return "timing wheel overflow (raise calendar_slots/calendar_cap): arg";
     case E_ID_RANGE: return "per-ticket count exceeds the table entry range at ticket";
     case E_BARRIER: return "cross-shard barrier timed out waiting for shard";
+    case E_RAFT_CAPACITY: return "Raft node out of log / staging / payload-heap capacity (raise ms_config.reserved[3]) at node";
     case E_SNAPSHOT: return "replicate_full names a set snapshot that is not resident (in flight longer than calendar_slots, or forged): sender";
   }
   return "unknown device error";
@@ -414,7 +415,7 @@ static int build_sim(ms_sim* s, const ms_config* in) {
   ms_config& c = s->cfg;
   c = *in;
   if (c.n_nodes == 0) { set_err("n_nodes must be positive (--node-count)"); return MS_ERR_ARG; }
-  if (c.workload > MS_W_GSET || c.topology > MS_TOPO_TREE4 || c.latency_dist > MS_DIST_EXPONENTIAL) {
+  if (c.workload > MS_W_RAFT || c.topology > MS_TOPO_TREE4 || c.latency_dist > MS_DIST_EXPONENTIAL) {
     set_err("bad workload/topology/latency_dist");
     return MS_ERR_ARG;
   }
@@ -536,7 +537,7 @@ static int build_sim(ms_sim* s, const ms_config* in) {
   P.topology = c.topology;
   P.n_values = c.n_values;
   P.bm_words = (c.n_values + 31) / 32;
-  if (c.workload != MS_W_ECHO) {
+  if (c.workload == MS_W_BROADCAST || c.workload == MS_W_GSET) {
     if ((rc = s->dalloc(&P.bitmap, (size_t)c.n_nodes * P.bm_words))) return rc;
     if ((rc = s->dalloc(&P.set_count, c.n_nodes))) return rc;
     if (c.topology != MS_TOPO_TOTAL) {
@@ -552,10 +553,36 @@ static int build_sim(ms_sim* s, const ms_config* in) {
       if (!nbr.empty()) CK(cudaMemcpyAsync(P.nbr, nbr.data(), nbr.size() * 4, cudaMemcpyHostToDevice, s->stream));
       CK(cudaStreamSynchronize(s->stream));
     }
-  } else {
+  } else if (c.workload == MS_W_ECHO) {
     if ((rc = s->dalloc(&P.next_msg_id, c.n_nodes))) return rc;
   }
-  P.family = c.workload == MS_W_GSET ? 1u : 0u;
+  P.family = c.workload == MS_W_GSET ? 1u : (c.workload == MS_W_RAFT ? 4u : 0u);
+  if (c.workload == MS_W_RAFT) {
+    // Raft nodes (csrc/ms_raft.cuh): per-node log, KV store, leader tables, pending-RPC closures,
+    // the staging rows of the sequential step and the heap of append_entries payloads
+    if (c.n_shards > 1) { set_err("workload lin-kv (Raft) runs on one GPU for now"); return MS_ERR_ARG; }
+    const size_t N = c.n_nodes;
+    P.rf_n_keys = c.reserved[2] ? c.reserved[2] : 4096u;
+    P.rf_log_cap = c.reserved[3] ? c.reserved[3] : 4096u;
+    P.rf_stage_cap = c.max_window + 2u * c.n_nodes + P.rf_log_cap + 16u;
+    P.rf_vote_words = (c.n_nodes + 31u) / 32u;
+    const uint32_t heap_words = pow2_at_least(std::max<uint32_t>(1u << 16, 8u * P.rf_log_cap));
+    P.rf_heap_mask = heap_words - 1u;
+    if ((rc = s->dalloc(&P.rf_node, N)) || (rc = s->dalloc(&P.rf_log, N * P.rf_log_cap * 2)) ||
+        (rc = s->dalloc(&P.rf_kv_val, N * P.rf_n_keys)) || (rc = s->dalloc(&P.rf_kv_has, N * P.rf_n_keys)) ||
+        (rc = s->dalloc(&P.rf_next, N * N)) || (rc = s->dalloc(&P.rf_match, N * N)) ||
+        (rc = s->dalloc(&P.rf_scratch, N * N)) || (rc = s->dalloc(&P.rf_cb, N * kRaftCallbacks * 2)) ||
+        (rc = s->dalloc(&P.rf_votes, N * P.rf_vote_words)) || (rc = s->dalloc(&P.rf_stage, N * P.rf_stage_cap * 3)) ||
+        (rc = s->dalloc(&P.rf_heap, (size_t)heap_words)) || (rc = s->dalloc(&P.rf_heap_cursor, 1)) ||
+        (rc = s->dalloc(&P.rf_ext_off, N * kRaftExt)) || (rc = s->dalloc(&P.rf_ext_tag, N * kRaftExt)))
+      return rc;
+    // fresh nodes: nascent, empty log but for the default entry {term 0, op None} (raft.py:121), last_applied 1
+    std::vector<RaftDev> init(N);
+    memset(init.data(), 0, N * sizeof(RaftDev));
+    for (size_t i = 0; i < N; i++) { init[i].voted_for = -1; init[i].leader = -1; init[i].last_applied = 1; init[i].log_size = 1; }
+    CK(cudaMemcpyAsync(P.rf_node, init.data(), N * sizeof(RaftDev), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+  }
   for (int k = 0; k < 4; k++) P.sv_ep[k] = 0xFFFFFFFFu;
   if (c.workload == MS_W_GSET) {
     // replicate_full payloads: a snapshot stays resident while its messages can be in flight,
@@ -980,6 +1007,18 @@ size_t ms_node_set(ms_sim* s, uint32_t node, uint32_t* values, size_t cap) {
 }
 
 uint64_t ms_client_replies(ms_sim* s) { std::lock_guard<std::mutex> g(s->mu); return s->hs.client_replies; }
+
+int ms_raft_state(ms_sim* s, uint32_t node, uint64_t out[8]) {
+  std::lock_guard<std::mutex> g(s->mu);
+  cudaSetDevice(s->device);
+  if (!s->P.rf_node || node >= s->cfg.n_nodes) { set_err("ms_raft_state: not a Raft node"); return MS_ERR_ARG; }
+  RaftDev r;
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaMemcpy(&r, s->P.rf_node + node, sizeof r, cudaMemcpyDeviceToHost));
+  out[0] = (uint64_t)r.state; out[1] = r.term; out[2] = (uint64_t)(r.voted_for + 1); out[3] = r.commit_index;
+  out[4] = r.last_applied; out[5] = (uint64_t)(r.leader + 1); out[6] = r.log_size; out[7] = r.kv_size;
+  return MS_OK;
+}
 
 int ms_counters(ms_sim* s, uint64_t out[8]) {
   std::lock_guard<std::mutex> g(s->mu);

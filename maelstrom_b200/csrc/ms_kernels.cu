@@ -341,8 +341,10 @@ __global__ void k_snapshot(Params p) {
     p.limit[e] = l;
     const uint32_t n = (p.kind[e] == kRemoved) ? 0u : l - h;
     // g-set: a node whose periodic replication task is due emits even with an empty window
-    const bool timer_due = p.workload == MS_W_GSET && e < p.n_servers && p.kind[e] == MS_KIND_SERVER &&
-                           p.gs_init[e] && st->now >= p.gs_next_fire[e];
+    // Raft: a node's election / heartbeat / commit actions are evaluated every round
+    const bool timer_due = e < p.n_servers && p.kind[e] == MS_KIND_SERVER &&
+                           ((p.workload == MS_W_GSET && p.gs_init[e] && st->now >= p.gs_next_fire[e]) ||
+                            p.workload == MS_W_RAFT);
     if (n == 0 && !timer_due) {
       // nothing to receive, hence nothing to emit: the ticket is finished right here
       const uint32_t t = p.n_inj_tickets + e;
@@ -842,12 +844,15 @@ __device__ void service_handle(const Params& p, uint32_t svc, const SvReq& q, ui
   }
 }
 
-// WL = node-program families compiled in: bit 0 g-set (else echo / broadcast), bit 1 services.
+#include "ms_raft.cuh"
+
+// WL = node-program families compiled in: bit 0 g-set, bit 2 Raft (else echo / broadcast), bit 1 services.
 template <int CLS, int WL>
 __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
   constexpr uint32_t cls = CLS;
   constexpr bool GS = (WL & 1) != 0;
   constexpr bool SV = (WL & 2) != 0;
+  constexpr bool RF = (WL & 4) != 0;
   DevState* st = p.st;
   if (round_skipped(p, st) || !st->slot_open) return;
 
@@ -1245,6 +1250,25 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
       }
       __syncthreads();
     }
+    if constexpr (RF) {
+      // ---- Raft node: the step is sequential (ms_raft.cuh); its sends are staged and emitted below
+      if (is_server) {
+        if (tid == 0) {
+          RaftCtx c{p, st, e, now, round, p.rf_node + e, p.rf_log + (size_t)e * p.rf_log_cap * 2,
+                    p.rf_cb + (size_t)e * kRaftCallbacks * 2, p.rf_stage + (size_t)e * p.rf_stage_cap * 3, 0u, 0u};
+          for (uint32_t pos = 0; pos < n; pos++) {
+            const uint32_t i = ord[pos];
+            if (!(vals[i] & V_RECV)) continue;
+            const uint4* rp = myring + (size_t)((head + i) & p.ring_mask) * 3;
+            rf_handle(c, rec_unpack(rp[0], rp[1], rp[2]));
+          }
+          rf_actions(c);
+          s_misc[2] = c.n_stage;
+        }
+        __syncthreads();
+        n_timer = s_misc[2];
+      }
+    }
     if constexpr (SV) {
       // ---- service endpoint: requests are handled one at a time in dequeue order (service.clj:147-156,
       //      245-263) by one thread; the reply is parked in vals[] / keyB[] for the emit phase
@@ -1305,7 +1329,9 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
         if constexpr (SV) {
           if (kind == MS_KIND_SERVICE && (val & SV_REPLY)) c |= 1;
         }
-        if constexpr (GS) {
+        if constexpr (RF) {
+          // a Raft node's emissions are those staged by its sequential step
+        } else if constexpr (GS) {
           if (is_server) {
             const uint32_t mt = meta[i];
             c |= gset_emit_count(mt);
@@ -1534,6 +1560,15 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
           r.msg_id = 0; r.in_reply_to = 0; r.tf = MS_T_REPLICATE_FULL; r.p0 = fire_p0; r.p1 = fire_seq;
         }
       }
+      if constexpr (RF) {
+        if (valid && j < n_timer) {          // staged by the node's sequential step, in program order
+          timer_emission = true;
+          const uint4* at = p.rf_stage + ((size_t)e * p.rf_stage_cap + j) * 3;
+          const uint4 a = at[0], b = at[1];
+          r.src = a.x; r.dest = a.y; r.msg_id = a.z; r.in_reply_to = a.w;
+          r.tf = b.x; r.p0 = b.y; r.p1 = (uint64_t)b.z | ((uint64_t)b.w << 32);
+        }
+      }
       if (valid && !timer_emission) {
         const uint32_t jm = j - n_timer;       // index among the emissions caused by messages
         uint32_t pos;
@@ -1728,19 +1763,24 @@ extern "C" {
 typedef void (*msk_round_fn)(msd::Params, uint32_t);
 // round kernel of (node-program families: bit 0 g-set, bit 1 services; window-size class)
 static msk_round_fn msk_round_kernel(uint32_t family, int cls) {
-  static const msk_round_fn tab[4][4] = {
+  static const msk_round_fn tab[8][4] = {
       {msd::k_round<0, 0>, msd::k_round<1, 0>, msd::k_round<2, 0>, msd::k_round<3, 0>},
       {msd::k_round<0, 1>, msd::k_round<1, 1>, msd::k_round<2, 1>, msd::k_round<3, 1>},
       {msd::k_round<0, 2>, msd::k_round<1, 2>, msd::k_round<2, 2>, msd::k_round<3, 2>},
-      {msd::k_round<0, 3>, msd::k_round<1, 3>, msd::k_round<2, 3>, msd::k_round<3, 3>}};
-  return tab[family & 3u][cls];
+      {msd::k_round<0, 3>, msd::k_round<1, 3>, msd::k_round<2, 3>, msd::k_round<3, 3>},
+      {msd::k_round<0, 4>, msd::k_round<1, 4>, msd::k_round<2, 4>, msd::k_round<3, 4>},
+      {nullptr, nullptr, nullptr, nullptr},     // g-set and Raft are different workloads
+      {msd::k_round<0, 6>, msd::k_round<1, 6>, msd::k_round<2, 6>, msd::k_round<3, 6>},
+      {nullptr, nullptr, nullptr, nullptr}};
+  return tab[family & 7u][cls];
 }
 
 cudaError_t msk_round_smem_attr(size_t bytes) {
   cudaError_t e = cudaSuccess;
-  for (uint32_t f = 0; f < 4 && e == cudaSuccess; f++)
+  for (uint32_t f = 0; f < 8 && e == cudaSuccess; f++)
     for (int c = 0; c < 4 && e == cudaSuccess; c++)
-      e = cudaFuncSetAttribute(msk_round_kernel(f, c), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+      if (msk_round_kernel(f, c))
+        e = cudaFuncSetAttribute(msk_round_kernel(f, c), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   return e;
 }
 
@@ -1764,7 +1804,8 @@ void msk_launch_round(const msd::Params* p, int n_classes, const uint32_t* caps,
                       const int* grids, int with_release, cudaStream_t s, cudaEvent_t before_round,
                       cudaEvent_t after_round, int phases, const cudaStream_t* aux, const cudaEvent_t* aux_ev) {
   const uint32_t n_ep = p->n_ep;
-  if ((phases & 1) && with_release) MS_LAUNCH(msd::k_release, 296, 256, 0, s, *p);
+  // two CTAs per SM on a B200 (the class-0 grid is SMs x occupancy >= 296 there)
+  if ((phases & 1) && with_release) MS_LAUNCH(msd::k_release, grids[0] < 296 ? grids[0] : 296, 256, 0, s, *p);
   if (phases & 8) {
     const int sb = 256;
     int sg = (int)((n_ep + sb - 1) / sb);

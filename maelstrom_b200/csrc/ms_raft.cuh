@@ -1,0 +1,338 @@
+// ms_raft.cuh -- the Raft node program of the lin-kv workload,
+// following demo/python/raft.py, the reference's single-threaded poll-loop node.  A node's step
+// in a round is inherently sequential (one handler at a time, raft.py:577-584), so it is run by
+// one thread of the node's CTA: every due message in id order through process_msg and the
+// handlers, then one pass of the loop's actions in its own priority order.  What the step
+// sends is staged in the node's row of `rf_stage`; the CTA then emits the staged records in
+// parallel through the common path (Philox loss / latency, journal, ring scatter).
+//
+// Included by ms_kernels.cu inside namespace msd, after Rec / latch_error.
+#pragma once
+
+struct RaftCtx {
+  const Params& p;
+  DevState* st;
+  uint32_t e;          // this node
+  int64_t now;
+  uint64_t round;
+  RaftDev* r;
+  uint4* log;          // this node's log (entry i, 1-based, at log[2 * (i - 1)])
+  uint4* cb;           // this node's callback table
+  uint4* stage;
+  uint32_t n_stage;
+  uint32_t draws;
+};
+
+struct RaftEntry {     // {'term': t, 'op': body + 'client'}  (raft.py:118-121,553-556)
+  uint32_t term, tf, key, client;
+  uint64_t p1;
+  uint32_t msg_id;
+};
+
+__device__ __forceinline__ RaftEntry rf_entry_unpack(uint4 a, uint4 b) {
+  RaftEntry en;
+  en.term = a.x; en.tf = a.y; en.key = a.z; en.client = a.w;
+  en.p1 = (uint64_t)b.x | ((uint64_t)b.y << 32);
+  en.msg_id = b.z;
+  return en;
+}
+__device__ __forceinline__ void rf_entry_store(uint4* at, const RaftEntry& en) {
+  at[0] = make_uint4(en.term, en.tf, en.key, en.client);
+  at[1] = make_uint4((uint32_t)en.p1, (uint32_t)(en.p1 >> 32), en.msg_id, 0u);
+}
+__device__ __forceinline__ uint32_t rf_log_term(const RaftCtx& c, uint32_t index /* 1-based */) {
+  return c.log[2 * (size_t)(index - 1)].x;
+}
+
+__device__ __forceinline__ void rf_emit(RaftCtx& c, const Rec& r) {
+  if (c.n_stage >= c.p.rf_stage_cap) { latch_error(c.st, E_RAFT_CAPACITY, c.e); return; }
+  uint4* at = c.stage + (size_t)c.n_stage * 3;
+  at[0] = make_uint4(r.src, r.dest, r.msg_id, r.in_reply_to);
+  at[1] = make_uint4(r.tf, r.p0, (uint32_t)r.p1, (uint32_t)(r.p1 >> 32));
+  c.n_stage++;
+}
+
+// net.reply (raft.py:72-75): body + in_reply_to, back to the sender; no msg_id
+__device__ __forceinline__ Rec rf_reply_to(const RaftCtx& c, const Rec& req, uint32_t type) {
+  Rec r;
+  r.round = 0; r.ticket = 0; r.idx = 0;
+  r.src = c.e; r.dest = req.src; r.msg_id = 0; r.in_reply_to = req.msg_id;
+  r.tf = type | ((uint32_t)MS_F_REPLY << 16);
+  r.p0 = 0; r.p1 = 0;
+  return r;
+}
+
+// random.random() (raft.py:251): word 0 of Philox(0x80000000 | k, node, round), k-th draw of this step
+__device__ __forceinline__ uint32_t rf_draw(RaftCtx& c) {
+  uint32_t x[4];
+  philox4x32_10(0x80000000u | c.draws++, c.e, (uint32_t)c.round, (uint32_t)(c.round >> 32), c.p.seed_lo,
+                c.p.seed_hi, x);
+  return x[0];
+}
+__device__ __forceinline__ void rf_reset_election_deadline(RaftCtx& c) {          // raft.py:249-251
+  const uint32_t x = rf_draw(c);
+  c.r->election_deadline = c.now + kElectionTimeoutNs + (int64_t)(((uint64_t)x * (uint64_t)kElectionTimeoutNs) >> 32);
+}
+__device__ __forceinline__ void rf_reset_step_down_deadline(RaftCtx& c) {         // :253-255
+  c.r->step_down_deadline = c.now + kElectionTimeoutNs;
+}
+__device__ __forceinline__ void rf_become_follower(RaftCtx& c) {                  // :307-314
+  c.r->state = RAFT_FOLLOWER;
+  c.r->leader = -1;
+  rf_reset_election_deadline(c);
+}
+__device__ __forceinline__ void rf_maybe_step_down(RaftCtx& c, uint32_t remote_term) {   // :257-270
+  if (c.r->term < remote_term) {
+    c.r->term = remote_term;
+    c.r->voted_for = -1;
+    rf_become_follower(c);
+  }
+}
+
+// net.rpc (raft.py:77-82): fresh msg_id, remember the closure, send
+__device__ __forceinline__ void rf_rpc(RaftCtx& c, uint32_t dest, uint32_t type, uint32_t p0, uint64_t p1,
+                                       uint32_t kind, uint32_t cb_node, int32_t cb_ni, uint32_t cb_n) {
+  const uint32_t id = c.r->next_msg_id++;
+  uint4* slot = c.cb + 2 * (size_t)(id % kRaftCallbacks);
+  slot[0] = make_uint4(id, kind, c.r->term, cb_node);
+  slot[1] = make_uint4((uint32_t)cb_ni, cb_n, 0u, 0u);
+  Rec r;
+  r.round = 0; r.ticket = 0; r.idx = 0;
+  r.src = c.e; r.dest = dest; r.msg_id = id; r.in_reply_to = 0;
+  r.tf = type | ((uint32_t)MS_F_MSG_ID << 16);
+  r.p0 = p0; r.p1 = p1;
+  rf_emit(c, r);
+}
+
+__device__ void rf_become_candidate(RaftCtx& c) {                                 // :316-325 + request_votes :272-303
+  RaftDev* r = c.r;
+  r->state = RAFT_CANDIDATE;
+  r->term += 1;
+  r->voted_for = (int32_t)c.e;
+  r->leader = -1;
+  rf_reset_election_deadline(c);
+  rf_reset_step_down_deadline(c);
+  uint32_t* votes = c.p.rf_votes + (size_t)c.e * c.p.rf_vote_words;
+  for (uint32_t w = 0; w < c.p.rf_vote_words; w++) votes[w] = 0;
+  votes[c.e >> 5] |= 1u << (c.e & 31);
+  r->n_votes = 1;
+  const uint64_t last = (uint64_t)r->log_size | ((uint64_t)rf_log_term(c, r->log_size) << 32);
+  for (uint32_t n = 0; n < c.p.n_servers; n++)                                    // brpc, :243-246
+    if (n != c.e) rf_rpc(c, n, MS_T_REQUEST_VOTE, r->term, last, 1u, 0u, 0, 0u);
+}
+
+__device__ void rf_become_leader(RaftCtx& c) {                                    // :327-339
+  RaftDev* r = c.r;
+  r->state = RAFT_LEADER;
+  r->leader = -1;
+  r->last_replication = 0;
+  int32_t* next = c.p.rf_next + (size_t)c.e * c.p.n_servers;
+  int32_t* match = c.p.rf_match + (size_t)c.e * c.p.n_servers;
+  for (uint32_t n = 0; n < c.p.n_servers; n++) { next[n] = (int32_t)r->log_size + 1; match[n] = 0; }
+  rf_reset_step_down_deadline(c);
+}
+
+// process_msg + handlers (raft.py:84-111, 443-573).  `return` where the reference raises: the
+// main loop catches, the message is consumed and nothing else happens (raft.py:585-588).
+__device__ void rf_handle(RaftCtx& c, const Rec& m) {
+  RaftDev* r = c.r;
+  const uint32_t type = m.tf & 0xFFFFu, flags = m.tf >> 16;
+  if (flags & MS_F_REPLY) {                                                       // :97-101
+    uint4* slot = c.cb + 2 * (size_t)(m.in_reply_to % kRaftCallbacks);
+    const uint4 s0 = slot[0], s1 = slot[1];
+    if (s0.y == 0 || s0.x != m.in_reply_to) return;                               // KeyError
+    slot[0] = make_uint4(0u, 0u, 0u, 0u);                                         // del self.callbacks[m]
+    const uint32_t cb_term = s0.z, cb_node = s0.w;
+    if (s0.y == 1) {                                                              // request_votes' handle, :282-303
+      rf_reset_step_down_deadline(c);
+      rf_maybe_step_down(c, m.p0);
+      if (r->state == RAFT_CANDIDATE && r->term == cb_term && m.p0 == r->term && m.p1 != 0 && m.src < c.p.n_servers) {
+        uint32_t* votes = c.p.rf_votes + (size_t)c.e * c.p.rf_vote_words;
+        const uint32_t bit = 1u << (m.src & 31);
+        if (!(votes[m.src >> 5] & bit)) { votes[m.src >> 5] |= bit; r->n_votes++; }
+        if (c.p.n_servers / 2 + 1 <= r->n_votes) rf_become_leader(c);
+      }
+    } else {                                                                      // replicate_log's handler, :413-426
+      rf_maybe_step_down(c, m.p0);
+      if (r->state == RAFT_LEADER && cb_term == r->term) {
+        rf_reset_step_down_deadline(c);
+        int32_t* next = c.p.rf_next + (size_t)c.e * c.p.n_servers;
+        int32_t* match = c.p.rf_match + (size_t)c.e * c.p.n_servers;
+        const int32_t ni = (int32_t)s1.x, ne = (int32_t)s1.y;
+        if (m.p1 != 0) {
+          if (next[cb_node] < ni + ne) next[cb_node] = ni + ne;
+          if (match[cb_node] < ni - 1 + ne) match[cb_node] = ni - 1 + ne;
+        } else {
+          next[cb_node] -= 1;
+        }
+      }
+    }
+    return;
+  }
+  if (type == MS_T_INIT) {                                                        // :447-459
+    if (r->state != RAFT_NASCENT) return;                                         // "Can't init twice!"
+    rf_become_follower(c);
+    rf_emit(c, rf_reply_to(c, m, MS_T_INIT_OK));
+    return;
+  }
+  if (type == MS_T_REQUEST_VOTE) {                                                // :464-495
+    rf_maybe_step_down(c, m.p0);
+    bool grant = false;
+    const uint32_t last_log_index = (uint32_t)m.p1, last_log_term = (uint32_t)(m.p1 >> 32);
+    const uint32_t my_last_term = rf_log_term(c, r->log_size);
+    if (m.p0 < r->term) {
+    } else if (r->voted_for >= 0) {
+    } else if (last_log_term < my_last_term) {
+    } else if (last_log_term == my_last_term && last_log_index < r->log_size) {
+    } else {
+      grant = true;
+      r->voted_for = (int32_t)m.src;
+      rf_reset_election_deadline(c);
+    }
+    Rec res = rf_reply_to(c, m, MS_T_REQUEST_VOTE_RES);
+    res.p0 = r->term; res.p1 = grant ? 1u : 0u;
+    rf_emit(c, res);
+    return;
+  }
+  if (type == MS_T_APPEND_ENTRIES) {                                              // :499-545
+    rf_maybe_step_down(c, m.p0);
+    Rec res = rf_reply_to(c, m, MS_T_APPEND_ENTRIES_RES);
+    res.p0 = r->term; res.p1 = 0;
+    if (m.p0 < r->term) { rf_emit(c, res); return; }
+    r->leader = (int32_t)m.src;
+    rf_reset_election_deadline(c);
+    // the payload: the sender's k-th append_entries, in the payload heap
+    const uint32_t k = (uint32_t)m.p1;
+    if (m.src >= c.p.n_servers || c.p.rf_ext_tag[(size_t)m.src * kRaftExt + k % kRaftExt] != k) return;   // forged handle
+    const uint64_t off = c.p.rf_ext_off[(size_t)m.src * kRaftExt + k % kRaftExt];
+    const uint4 guard = c.p.rf_heap[off & c.p.rf_heap_mask];
+    if (guard.x != m.src || guard.y != k) { latch_error(c.st, E_SNAPSHOT, m.src); return; }               // overwritten
+    const uint4 hd = c.p.rf_heap[(off + 1) & c.p.rf_heap_mask];
+    const uint32_t prev_log_index = hd.x, prev_log_term = hd.y, leader_commit = hd.z, n_entries = hd.w;
+    if (prev_log_index == 0) return;                                              // "Out of bounds previous log index"
+    if (prev_log_index > r->log_size || rf_log_term(c, prev_log_index) != prev_log_term) {
+      rf_emit(c, res);                                                            // we disagree on the previous term
+      return;
+    }
+    if (prev_log_index + n_entries > c.p.rf_log_cap) { latch_error(c.st, E_RAFT_CAPACITY, c.e); return; }
+    for (uint32_t q = 0; q < n_entries; q++) {                                    // truncate + append, :533-534
+      c.log[2 * (size_t)(prev_log_index + q)] = c.p.rf_heap[(off + 2 + 2 * (uint64_t)q) & c.p.rf_heap_mask];
+      c.log[2 * (size_t)(prev_log_index + q) + 1] = c.p.rf_heap[(off + 3 + 2 * (uint64_t)q) & c.p.rf_heap_mask];
+    }
+    r->log_size = prev_log_index + n_entries;
+    if (r->commit_index < leader_commit) r->commit_index = leader_commit < r->log_size ? leader_commit : r->log_size;
+    res.p1 = 1;
+    rf_emit(c, res);
+    return;
+  }
+  if (type == MS_T_READ || type == MS_T_WRITE || type == MS_T_CAS) {              // kv_req, :550-570
+    if (r->state == RAFT_LEADER) {
+      if (m.p0 >= c.p.rf_n_keys) { latch_error(c.st, E_VALUE_RANGE, m.p0); return; }
+      if (r->log_size >= c.p.rf_log_cap) { latch_error(c.st, E_RAFT_CAPACITY, c.e); return; }
+      RaftEntry en;
+      en.term = r->term; en.tf = m.tf; en.key = m.p0; en.client = m.src; en.p1 = m.p1; en.msg_id = m.msg_id;
+      rf_entry_store(c.log + 2 * (size_t)r->log_size, en);
+      r->log_size++;
+    } else if (r->leader >= 0) {
+      Rec f = m;                                                                  // msg['dest'] = leader; send_msg(msg)
+      f.dest = (uint32_t)r->leader;
+      rf_emit(c, f);
+    } else {
+      Rec res = rf_reply_to(c, m, MS_T_ERROR);
+      res.p0 = 11;                                                                // not a leader
+      rf_emit(c, res);
+    }
+    return;
+  }
+  // 'No callback or handler': RuntimeError, message consumed
+}
+
+// KVStore.apply (raft.py:158-192)
+__device__ Rec rf_apply(RaftCtx& c, const RaftEntry& op) {
+  Rec res;
+  res.round = 0; res.ticket = 0; res.idx = 0;
+  res.src = c.e; res.dest = op.client; res.msg_id = 0; res.in_reply_to = op.msg_id;
+  res.p0 = 0; res.p1 = 0;
+  uint32_t otype = MS_T_ERROR;
+  uint32_t* val = c.p.rf_kv_val + (size_t)c.e * c.p.rf_n_keys + op.key;
+  uint8_t* has = c.p.rf_kv_has + (size_t)c.e * c.p.rf_n_keys + op.key;
+  const uint32_t type = op.tf & 0xFFFFu;
+  if (type == MS_T_READ) {
+    if (*has) { otype = MS_T_READ_OK; res.p1 = *val; } else res.p0 = 20;
+  } else if (type == MS_T_WRITE) {
+    if (!*has) c.r->kv_size++;
+    *val = (uint32_t)op.p1; *has = 1;
+    otype = MS_T_WRITE_OK;
+  } else {
+    if (!*has) res.p0 = 20;
+    else if (*val != (uint32_t)op.p1) res.p0 = 22;
+    else { *val = (uint32_t)(op.p1 >> 32); otype = MS_T_CAS_OK; }
+  }
+  res.tf = otype | ((uint32_t)MS_F_REPLY << 16);
+  return res;
+}
+
+// One pass of the main loop's actions once the inbox is empty (raft.py:577-584), in the loop's
+// priority order; time is frozen inside a round, so each is idle again right after it ran.
+__device__ void rf_actions(RaftCtx& c) {
+  RaftDev* r = c.r;
+  const uint32_t N = c.p.n_servers;
+  if (r->state == RAFT_LEADER && r->step_down_deadline < c.now) rf_become_follower(c);   // :371-376
+  {                                                                                       // replicate_log, :387-441
+    const int64_t elapsed = c.now - r->last_replication;
+    bool replicated = false;
+    if (r->state == RAFT_LEADER && kMinReplicationNs < elapsed) {
+      const int32_t* next = c.p.rf_next + (size_t)c.e * N;
+      for (uint32_t n = 0; n < N; n++) {
+        if (n == c.e) continue;
+        const int32_t ni = next[n];
+        if (ni <= 0) return;                                                              // from_index raises (:147-148): the
+                                                                                          // iteration ends, later ones raise again
+        const int32_t n_entries = (int32_t)r->log_size - ni + 1 > 0 ? (int32_t)r->log_size - ni + 1 : 0;
+        if (0 < n_entries || kHeartbeatNs < elapsed) {
+          // log.get(ni - 1) = entries[ni - 2]; Python's entries[-1] when ni == 1 is the last entry
+          const int32_t pi = ni - 2;
+          if (pi >= (int32_t)r->log_size) return;                                         // IndexError
+          const uint32_t prev_term = pi < 0 ? rf_log_term(c, r->log_size) : rf_log_term(c, (uint32_t)pi + 1);
+          const uint32_t k = ++r->appends;
+          const uint64_t words = 2 + 2 * (uint64_t)n_entries;
+          if (words > c.p.rf_heap_mask) { latch_error(c.st, E_RAFT_CAPACITY, c.e); return; }
+          const uint64_t off = atomicAdd(c.p.rf_heap_cursor, (unsigned long long)words);
+          c.p.rf_heap[off & c.p.rf_heap_mask] = make_uint4(c.e, k, 0u, 0u);
+          c.p.rf_heap[(off + 1) & c.p.rf_heap_mask] = make_uint4((uint32_t)(ni - 1), prev_term, r->commit_index, (uint32_t)n_entries);
+          for (int32_t q = 0; q < n_entries; q++) {
+            c.p.rf_heap[(off + 2 + 2 * (uint64_t)q) & c.p.rf_heap_mask] = c.log[2 * (size_t)(ni - 1 + q)];
+            c.p.rf_heap[(off + 3 + 2 * (uint64_t)q) & c.p.rf_heap_mask] = c.log[2 * (size_t)(ni - 1 + q) + 1];
+          }
+          c.p.rf_ext_off[(size_t)c.e * kRaftExt + k % kRaftExt] = off;
+          c.p.rf_ext_tag[(size_t)c.e * kRaftExt + k % kRaftExt] = k;
+          rf_rpc(c, n, MS_T_APPEND_ENTRIES, r->term, k, 2u, n, ni, (uint32_t)n_entries);
+          replicated = true;
+        }
+      }
+    }
+    if (replicated) r->last_replication = c.now;
+  }
+  if (r->election_deadline < c.now) {                                                     // election, :358-367
+    if (r->state == RAFT_FOLLOWER || r->state == RAFT_CANDIDATE) rf_become_candidate(c);
+    else rf_reset_election_deadline(c);
+  }
+  if (r->state == RAFT_LEADER) {                                                          // advance_commit_index, :378-385
+    int32_t* xs = c.p.rf_scratch + (size_t)c.e * N;
+    const int32_t* match = c.p.rf_match + (size_t)c.e * N;
+    for (uint32_t n = 0; n < N; n++) {                                                    // insertion sort of match_index()
+      const int32_t v = n == c.e ? (int32_t)r->log_size : match[n];
+      uint32_t j = n;
+      while (j > 0 && xs[j - 1] > v) { xs[j] = xs[j - 1]; j--; }
+      xs[j] = v;
+    }
+    const int32_t nmed = xs[N - (N / 2 + 1)];                                             // median, :29-33
+    if ((int32_t)r->commit_index < nmed && rf_log_term(c, (uint32_t)nmed) == r->term) r->commit_index = (uint32_t)nmed;
+  }
+  while (r->last_applied < r->commit_index) {                                             // advance_state_machine, :343-354
+    r->last_applied += 1;
+    const RaftEntry op = rf_entry_unpack(c.log[2 * (size_t)(r->last_applied - 1)], c.log[2 * (size_t)(r->last_applied - 1) + 1]);
+    const Rec res = rf_apply(c, op);
+    if (r->state == RAFT_LEADER) rf_emit(c, res);
+  }
+}

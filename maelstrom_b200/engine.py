@@ -8,14 +8,15 @@ import numpy as np
 from . import _lib
 from ._lib import Body, Config, EVENT_DTYPE, JBODY_DTYPE, MSG_DTYPE, OP_DTYPE  # noqa: F401
 
-WORKLOADS = {"echo": 0, "broadcast": 1, "g-set": 2}
+WORKLOADS = {"echo": 0, "broadcast": 1, "g-set": 2, "lin-kv": 3}
 TOPOLOGIES = {"grid": 0, "line": 1, "total": 2, "tree": 3, "tree2": 3, "tree3": 4, "tree4": 5}
 DISTS = {"constant": 0, "uniform": 1, "exponential": 2}
 KIND_SERVER, KIND_CLIENT, KIND_HOST, KIND_SIM_CLIENT, KIND_SERVICE = 0, 1, 2, 3, 4
 SERVICES = ("lin-kv", "seq-kv", "lww-kv", "lin-tso")      # service/default-services, service.clj:290-296
 TYPES = dict(init=1, init_ok=2, error=3, echo=10, echo_ok=11, topology=20, topology_ok=21,
              broadcast=22, broadcast_ok=23, read=24, read_ok=25, add=30, add_ok=31,
-             replicate_one=32, replicate_full=33, write=40, write_ok=41, cas=42, cas_ok=43, ts=44, ts_ok=45)
+             replicate_one=32, replicate_full=33, write=40, write_ok=41, cas=42, cas_ok=43, ts=44, ts_ok=45,
+             request_vote=50, request_vote_res=51, append_entries=52, append_entries_res=53)
 TYPE_NAMES = {v: k for k, v in TYPES.items()}
 F_MSG_ID, F_REPLY, F_CREATE = 1, 2, 4
 RECV_BIT = 1 << 63
@@ -248,6 +249,18 @@ class Sim:
 
     def client_replies(self):
         return int(self.L.ms_client_replies(self.h))
+
+    RAFT_FIELDS = ("state", "term", "voted_for", "commit_index", "last_applied", "leader", "log_size", "kv_size")
+
+    def raft_state(self, node):
+        """RaftNode fields (demo/python/raft.py:196-221); state 0 nascent / 1 follower / 2 candidate /
+        3 leader; voted_for and leader are -1 when unset."""
+        out = np.zeros(8, dtype=np.uint64)
+        self._chk(self.L.ms_raft_state(self.h, node, out.ctypes.data))
+        d = dict(zip(self.RAFT_FIELDS, (int(x) for x in out)))
+        d["voted_for"] -= 1
+        d["leader"] -= 1
+        return d
 
 
 def topology(name, n, node):

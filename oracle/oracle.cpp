@@ -287,6 +287,46 @@ struct Service {
   }
 };
 
+// ------------------------------------------------------------- Raft node (demo/python/raft.py)
+constexpr uint32_t kRaftCallbacks = 4096;      // pending-RPC table slots (the reference's dict is unbounded)
+constexpr int64_t kElectionTimeoutNs = 2000000000;     // raft.py:199
+constexpr int64_t kHeartbeatNs = 1000000000;           // raft.py:200
+constexpr int64_t kMinReplicationNs = 50000000;        // raft.py:201
+enum { RAFT_NASCENT = 0, RAFT_FOLLOWER = 1, RAFT_CANDIDATE = 2, RAFT_LEADER = 3 };
+
+struct RaftEntry {             // {'term': t, 'op': body + 'client'}  (raft.py:118-121,553-556)
+  uint32_t term = 0;
+  uint16_t type = 0, flags = 0;
+  uint32_t key = 0, client = 0, msg_id = 0;
+  uint64_t p1 = 0;
+};
+struct RaftCb {                // what the RPC's closure captured (raft.py:282-303, 413-432)
+  uint32_t msg_id = 0;
+  int kind = 0;                // 0 free, 1 request_vote, 2 append_entries
+  uint32_t term = 0, node = 0;
+  int64_t ni = 0;
+  uint32_t n_entries = 0;
+};
+struct RaftAppend {            // body of one append_entries (raft.py:424-431)
+  uint32_t prev_log_index = 0, prev_log_term = 0, leader_commit = 0;
+  std::vector<RaftEntry> entries;
+};
+struct RaftNode {
+  int state = RAFT_NASCENT;
+  uint32_t term = 0;
+  int64_t voted_for = -1, leader = -1;
+  uint32_t commit_index = 0, last_applied = 1;                   // raft.py:214-215
+  int64_t election_deadline = 0, step_down_deadline = 0, last_replication = 0;
+  uint32_t next_msg_id = 0;                                      // raft.py:42
+  std::vector<RaftEntry> log = std::vector<RaftEntry>(1);        // the default entry {term 0, op None} (raft.py:121)
+  std::map<uint32_t, uint32_t> kv;
+  std::vector<int64_t> next_index, match_index;
+  std::vector<RaftCb> callbacks = std::vector<RaftCb>(kRaftCallbacks);
+  std::set<uint32_t> votes;
+  uint64_t appends = 0;
+  uint32_t draws = 0;                                            // random draws made in the current round
+};
+
 struct Endpoint {
   std::string name;
   int kind = OR_KIND_SERVER;
@@ -301,6 +341,7 @@ struct Endpoint {
   int64_t next_fire = 0;                // g-set: next run of the `every 5` task (g_set.rb:34)
   uint64_t fires = 0;                   // g-set: replication runs so far
   Service svc;                          // OR_KIND_SERVICE
+  RaftNode rn;                          // OR_W_RAFT servers
 };
 
 }  // namespace
@@ -501,6 +542,258 @@ struct or_sim {
     ep.next_fire += (int64_t)cfg.gset_interval_ms * kTickNs;
   }
 
+  // ------------------------------------------------------------- Raft (demo/python/raft.py)
+  std::map<std::pair<uint32_t, uint64_t>, RaftAppend> raft_appends;   // (sender, k) -> append_entries payload
+
+  uint32_t raft_majority() const { return cfg.n_nodes / 2 + 1; }                 // raft.py:25-27
+  // random.random() (raft.py:251): word 0 of Philox(0x80000000 | k, node, round), k-th draw of the node's step
+  uint32_t raft_draw(uint32_t e) {
+    RaftNode& r = eps[e].rn;
+    const uint32_t ctr[4] = {0x80000000u | r.draws++, e, (uint32_t)round, (uint32_t)(round >> 32)};
+    const uint32_t key[2] = {cfg.seed_lo, cfg.seed_hi};
+    uint32_t x[4];
+    philox(ctr, key, x);
+    return x[0];
+  }
+  void raft_reset_election_deadline(uint32_t e) {                                 // raft.py:249-251
+    const uint32_t x = raft_draw(e);
+    eps[e].rn.election_deadline = now + kElectionTimeoutNs + (int64_t)(((uint64_t)x * (uint64_t)kElectionTimeoutNs) >> 32);
+  }
+  void raft_reset_step_down_deadline(uint32_t e) { eps[e].rn.step_down_deadline = now + kElectionTimeoutNs; }   // :253-255
+  void raft_become_follower(uint32_t e) {                                         // :307-314
+    RaftNode& r = eps[e].rn;
+    r.state = RAFT_FOLLOWER;
+    r.next_index.clear(); r.match_index.clear();
+    r.leader = -1;
+    raft_reset_election_deadline(e);
+  }
+  void raft_maybe_step_down(uint32_t e, uint32_t remote_term) {                   // :265-270 (+ advance_term :257-263)
+    RaftNode& r = eps[e].rn;
+    if (r.term < remote_term) {
+      r.term = remote_term;
+      r.voted_for = -1;
+      raft_become_follower(e);
+    }
+  }
+  // net.rpc (raft.py:77-82): fresh msg_id, remember the closure, send
+  void raft_rpc(uint32_t e, uint32_t dest, or_msg m, const RaftCb& closure, std::vector<Emit>& out) {
+    RaftNode& r = eps[e].rn;
+    const uint32_t id = r.next_msg_id++;
+    RaftCb cb = closure;
+    cb.msg_id = id;
+    r.callbacks[id % kRaftCallbacks] = cb;
+    m.src = e; m.dest = dest; m.flags = OR_F_MSG_ID; m.msg_id = id;
+    out.push_back(Emit(m));
+  }
+  void raft_request_votes(uint32_t e, std::vector<Emit>& out) {                   // :272-303
+    RaftNode& r = eps[e].rn;
+    r.votes.clear();
+    r.votes.insert(e);
+    for (uint32_t n = 0; n < cfg.n_nodes; n++) {                                  // brpc, :243-246
+      if (n == e) continue;
+      or_msg m; std::memset(&m, 0, sizeof m);
+      m.type = OR_T_REQUEST_VOTE;
+      m.p0 = r.term;
+      m.p1 = (uint64_t)r.log.size() | ((uint64_t)r.log.back().term << 32);
+      RaftCb cb; cb.kind = 1; cb.term = r.term;
+      raft_rpc(e, n, m, cb, out);
+    }
+  }
+  void raft_become_candidate(uint32_t e, std::vector<Emit>& out) {                // :316-325
+    RaftNode& r = eps[e].rn;
+    r.state = RAFT_CANDIDATE;
+    r.term += 1; r.voted_for = -1;                                                // advance_term
+    r.voted_for = e;
+    r.leader = -1;
+    raft_reset_election_deadline(e);
+    raft_reset_step_down_deadline(e);
+    raft_request_votes(e, out);
+  }
+  void raft_become_leader(uint32_t e) {                                           // :327-339
+    RaftNode& r = eps[e].rn;
+    r.state = RAFT_LEADER;
+    r.leader = -1;
+    r.last_replication = 0;
+    r.next_index.assign(cfg.n_nodes, (int64_t)r.log.size() + 1);
+    r.match_index.assign(cfg.n_nodes, 0);
+    raft_reset_step_down_deadline(e);
+  }
+  // KVStore.apply (raft.py:158-192); the reply goes to op['client'] with in_reply_to = op['msg_id']
+  or_msg raft_apply(uint32_t e, const RaftEntry& op) {
+    RaftNode& r = eps[e].rn;
+    or_msg res; std::memset(&res, 0, sizeof res);
+    res.src = e; res.dest = op.client; res.flags = OR_F_REPLY; res.in_reply_to = op.msg_id;
+    auto it = r.kv.find(op.key);
+    if (op.type == OR_T_READ) {
+      if (it != r.kv.end()) { res.type = OR_T_READ_OK; res.p1 = it->second; }
+      else { res.type = OR_T_ERROR; res.p0 = 20; }
+    } else if (op.type == OR_T_WRITE) {
+      r.kv[op.key] = (uint32_t)op.p1;
+      res.type = OR_T_WRITE_OK;
+    } else {                                                                      // cas
+      if (it == r.kv.end()) { res.type = OR_T_ERROR; res.p0 = 20; }
+      else if (it->second != (uint32_t)op.p1) { res.type = OR_T_ERROR; res.p0 = 22; }
+      else { it->second = (uint32_t)(op.p1 >> 32); res.type = OR_T_CAS_OK; }
+    }
+    return res;
+  }
+
+  // net.process_msg + the handlers (raft.py:84-111, 443-573).  An exception inside a handler is
+  // caught by the main loop (raft.py:585-588): the message is consumed, nothing else happens.
+  void node_raft(uint32_t e, const or_msg& m, std::vector<Emit>& out) {
+    RaftNode& r = eps[e].rn;
+    if (m.flags & OR_F_REPLY) {                                                   // :97-101 callback lookup
+      RaftCb& slot = r.callbacks[m.in_reply_to % kRaftCallbacks];
+      if (slot.kind == 0 || slot.msg_id != m.in_reply_to) return;                 // KeyError
+      const RaftCb cb = slot;
+      slot.kind = 0;                                                              // del self.callbacks[m]
+      if (cb.kind == 1) {                                                         // request_votes' handle, :282-303
+        raft_reset_step_down_deadline(e);
+        raft_maybe_step_down(e, m.p0);
+        if (r.state == RAFT_CANDIDATE && r.term == cb.term && m.p0 == r.term && m.p1 != 0) {
+          r.votes.insert(m.src);
+          if (raft_majority() <= r.votes.size()) raft_become_leader(e);
+        }
+      } else {                                                                    // replicate_log's handler, :413-426
+        raft_maybe_step_down(e, m.p0);
+        if (r.state == RAFT_LEADER && cb.term == r.term) {
+          raft_reset_step_down_deadline(e);
+          if (m.p1 != 0) {
+            r.next_index[cb.node] = std::max(r.next_index[cb.node], cb.ni + (int64_t)cb.n_entries);
+            r.match_index[cb.node] = std::max(r.match_index[cb.node], cb.ni - 1 + (int64_t)cb.n_entries);
+          } else {
+            r.next_index[cb.node] -= 1;
+          }
+        }
+      }
+      return;
+    }
+    switch (m.type) {
+      case OR_T_INIT: {                                                           // :447-459
+        if (r.state != RAFT_NASCENT) return;                                      // "Can't init twice!"
+        raft_become_follower(e);
+        out.push_back(Emit(reply_to(m, OR_T_INIT_OK)));
+        return;
+      }
+      case OR_T_REQUEST_VOTE: {                                                   // :464-495
+        raft_maybe_step_down(e, m.p0);
+        bool grant = false;
+        const uint32_t last_log_index = (uint32_t)m.p1, last_log_term = (uint32_t)(m.p1 >> 32);
+        if (m.p0 < r.term) {
+        } else if (r.voted_for >= 0) {
+        } else if (last_log_term < r.log.back().term) {
+        } else if (last_log_term == r.log.back().term && last_log_index < r.log.size()) {
+        } else {
+          grant = true;
+          r.voted_for = m.src;                                                    // body['candidate_id']
+          raft_reset_election_deadline(e);
+        }
+        or_msg res = reply_to(m, OR_T_REQUEST_VOTE_RES);
+        res.p0 = r.term; res.p1 = grant ? 1 : 0;
+        out.push_back(Emit(res));
+        return;
+      }
+      case OR_T_APPEND_ENTRIES: {                                                 // :499-545
+        raft_maybe_step_down(e, m.p0);
+        or_msg res = reply_to(m, OR_T_APPEND_ENTRIES_RES);
+        res.p0 = r.term; res.p1 = 0;
+        if (m.p0 < r.term) { out.push_back(Emit(res)); return; }
+        r.leader = m.src;                                                         // body['leader_id']
+        raft_reset_election_deadline(e);
+        auto it = raft_appends.find(std::make_pair(m.src, m.p1));
+        if (it == raft_appends.end()) return;                                     // forged handle: KeyError
+        const RaftAppend& a = it->second;
+        if (a.prev_log_index == 0) return;                                        // "Out of bounds previous log index"
+        if (a.prev_log_index > r.log.size() || r.log[a.prev_log_index - 1].term != a.prev_log_term) {
+          out.push_back(Emit(res));                                               // we disagree on the previous term
+          return;
+        }
+        r.log.resize(a.prev_log_index);                                           // truncate, :533
+        r.log.insert(r.log.end(), a.entries.begin(), a.entries.end());
+        if (r.commit_index < a.leader_commit)
+          r.commit_index = std::min<uint32_t>(a.leader_commit, (uint32_t)r.log.size());
+        res.p1 = 1;
+        out.push_back(Emit(res));
+        return;
+      }
+      case OR_T_READ: case OR_T_WRITE: case OR_T_CAS: {                           // kv_req, :550-570
+        if (r.state == RAFT_LEADER) {
+          RaftEntry en;
+          en.term = r.term; en.type = m.type; en.flags = m.flags; en.key = m.p0; en.client = m.src;
+          en.msg_id = m.msg_id; en.p1 = m.p1;
+          r.log.push_back(en);
+        } else if (r.leader >= 0) {
+          or_msg f = m;                                                           // msg['dest'] = leader; send_msg(msg)
+          f.dest = (uint32_t)r.leader;
+          out.push_back(Emit(f));
+        } else {
+          or_msg res = reply_to(m, OR_T_ERROR);
+          res.p0 = 11;                                                            // not a leader
+          out.push_back(Emit(res));
+        }
+        return;
+      }
+      default: return;                                                            // 'No callback or handler'
+    }
+  }
+
+  // One pass of the main loop's actions after the inbox is empty (raft.py:577-584), in the
+  // loop's own priority order; every action is idle again right after it ran (time is frozen
+  // inside a round), and the state machine catches up to the commit index.
+  void raft_actions(uint32_t e, std::vector<Emit>& out) {
+    RaftNode& r = eps[e].rn;
+    if (r.state == RAFT_LEADER && r.step_down_deadline < now) raft_become_follower(e);    // :371-376
+    {                                                                                      // replicate_log, :387-441
+      const int64_t elapsed = now - r.last_replication;
+      bool replicated = false, aborted = false;
+      if (r.state == RAFT_LEADER && kMinReplicationNs < elapsed) {
+        for (uint32_t n = 0; n < cfg.n_nodes && !aborted; n++) {
+          if (n == e) continue;
+          const int64_t ni = r.next_index[n];
+          if (ni <= 0) { aborted = true; break; }                                          // from_index raises, :147-148
+          const int64_t n_entries = (int64_t)r.log.size() - ni + 1 > 0 ? (int64_t)r.log.size() - ni + 1 : 0;
+          if (0 < n_entries || kHeartbeatNs < elapsed) {
+            RaftAppend a;
+            a.prev_log_index = (uint32_t)(ni - 1);
+            // log.get(ni - 1): entries[ni - 2]; Python's entries[-1] when ni == 1 is the last entry
+            const int64_t pi = ni - 2;
+            if (pi >= (int64_t)r.log.size()) { aborted = true; break; }                    // IndexError
+            a.prev_log_term = pi < 0 ? r.log.back().term : r.log[(size_t)pi].term;
+            a.leader_commit = r.commit_index;
+            if (n_entries > 0) a.entries.assign(r.log.begin() + (ni - 1), r.log.end());
+            const uint64_t k = ++r.appends;
+            raft_appends[std::make_pair(e, k)] = a;
+            or_msg m; std::memset(&m, 0, sizeof m);
+            m.type = OR_T_APPEND_ENTRIES; m.p0 = r.term; m.p1 = k;
+            RaftCb cb; cb.kind = 2; cb.term = r.term; cb.node = n; cb.ni = ni; cb.n_entries = (uint32_t)n_entries;
+            raft_rpc(e, n, m, cb, out);
+            replicated = true;
+          }
+        }
+      }
+      // an exception inside replicate_log ends this iteration of the main loop; every later
+      // iteration raises again before it gets to the actions below (raft.py:577-588)
+      if (aborted) return;
+      if (replicated) r.last_replication = now;
+    }
+    if (r.election_deadline < now) {                                                       // election, :358-367
+      if (r.state == RAFT_FOLLOWER || r.state == RAFT_CANDIDATE) raft_become_candidate(e, out);
+      else raft_reset_election_deadline(e);
+    }
+    if (r.state == RAFT_LEADER) {                                                          // advance_commit_index, :378-385
+      std::vector<int64_t> xs = r.match_index;
+      xs[e] = (int64_t)r.log.size();
+      std::sort(xs.begin(), xs.end());
+      const int64_t n = xs[xs.size() - raft_majority()];                                  // median, :29-33
+      if ((int64_t)r.commit_index < n && r.log[(size_t)n - 1].term == r.term) r.commit_index = (uint32_t)n;
+    }
+    while (r.last_applied < r.commit_index) {                                              // advance_state_machine, :343-354
+      r.last_applied += 1;
+      const or_msg res = raft_apply(e, r.log[r.last_applied - 1]);
+      if (r.state == RAFT_LEADER) out.push_back(Emit(res));
+    }
+  }
+
   bool run_round() {
     std::vector<Envelope> pending;
     // (1) injector
@@ -524,6 +817,7 @@ struct or_sim {
       if (!ep.live) continue;
       out.clear();
       if (cfg.workload == OR_W_GSET && ep.kind == OR_KIND_SERVER) gset_timer(e, out);
+      if (cfg.workload == OR_W_RAFT && ep.kind == OR_KIND_SERVER) ep.rn.draws = 0;
       while (!ep.q.empty() && ep.q.top().m.deadline_ns <= now) {   // net.clj:228-229,236-238
         const or_msg m = ep.q.top().m;
         ep.q.pop();
@@ -560,10 +854,12 @@ struct or_sim {
             if (cfg.workload == OR_W_ECHO) node_echo(e, m, out);
             else if (cfg.workload == OR_W_BROADCAST) node_broadcast(e, m, out);
             else if (cfg.workload == OR_W_GSET) node_gset(e, m, out);
+            else if (cfg.workload == OR_W_RAFT) node_raft(e, m, out);
             else { error = "workload not implemented in oracle"; return false; }
         }
         if (!error.empty()) return false;
       }
+      if (cfg.workload == OR_W_RAFT && ep.kind == OR_KIND_SERVER) raft_actions(e, out);
       for (uint32_t j = 0; j < out.size(); j++) {
         if (out[j].has_snap) snapshots[next_id] = out[j].snap;   // keyed by the read_ok's net id
         if (!send(e, j, out[j].m, pending)) return false;
@@ -737,6 +1033,21 @@ size_t or_read_snapshot(or_sim* s, uint64_t msg_id, uint32_t* vals, size_t cap) 
 }
 
 uint64_t or_client_replies(or_sim* s) { return s->client_replies; }
+
+int or_raft_state(or_sim* s, uint32_t node, uint64_t out[8]) {
+  if (node >= s->cfg.n_nodes) return -1;
+  const RaftNode& r = s->eps[node].rn;
+  out[0] = (uint64_t)r.state; out[1] = r.term; out[2] = (uint64_t)(r.voted_for + 1); out[3] = r.commit_index;
+  out[4] = r.last_applied; out[5] = (uint64_t)(r.leader + 1); out[6] = r.log.size(); out[7] = r.kv.size();
+  return 0;
+}
+int or_raft_append(or_sim* s, uint32_t sender, uint64_t k, uint32_t out[4]) {
+  auto it = s->raft_appends.find(std::make_pair(sender, k));
+  if (it == s->raft_appends.end()) return 0;
+  out[0] = it->second.prev_log_index; out[1] = it->second.prev_log_term;
+  out[2] = it->second.leader_commit; out[3] = (uint32_t)it->second.entries.size();
+  return 1;
+}
 
 struct or_service { Service s; };
 or_service* or_service_new(int svc_type, uint32_t buffer_size) {

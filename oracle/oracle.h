@@ -79,7 +79,8 @@ typedef struct or_config {
   uint32_t gset_interval_ms;/* g-set replication period (g_set.rb:30: 5 s)   */
 } or_config;
 
-enum { OR_W_ECHO = 0, OR_W_BROADCAST = 1, OR_W_GSET = 2 };
+enum { OR_W_ECHO = 0, OR_W_BROADCAST = 1, OR_W_GSET = 2,
+       OR_W_RAFT = 3 };   /* lin-kv workload served by Raft nodes (demo/python/raft.py) */
 enum { OR_TOPO_GRID = 0, OR_TOPO_LINE = 1, OR_TOPO_TOTAL = 2,
        OR_TOPO_TREE2 = 3, OR_TOPO_TREE3 = 4, OR_TOPO_TREE4 = 5 };
 enum { OR_DIST_CONSTANT = 0, OR_DIST_UNIFORM = 1, OR_DIST_EXPONENTIAL = 2 };
@@ -95,7 +96,12 @@ enum {
   OR_T_REPLICATE_FULL = 33,
   /* services (service.clj:31-141): read = OR_T_READ with p0 = key, read_ok p1 = value;
    * write p0 = key, p1 = value; cas p0 = key, p1 = from | to << 32; ts_ok p1 = ts */
-  OR_T_WRITE = 40, OR_T_WRITE_OK = 41, OR_T_CAS = 42, OR_T_CAS_OK = 43, OR_T_TS = 44, OR_T_TS_OK = 45
+  OR_T_WRITE = 40, OR_T_WRITE_OK = 41, OR_T_CAS = 42, OR_T_CAS_OK = 43, OR_T_TS = 44, OR_T_TS_OK = 45,
+  /* Raft (raft.py:270-281,405-432,460-545): request_vote p0 = term, p1 = last_log_index |
+   * last_log_term << 32; *_res p0 = term, p1 = vote_granted / success; append_entries p0 = term,
+   * p1 = k, the sender's k-th append_entries, naming {prev_log_index, prev_log_term,
+   * leader_commit, entries} (or_raft_append) */
+  OR_T_REQUEST_VOTE = 50, OR_T_REQUEST_VOTE_RES = 51, OR_T_APPEND_ENTRIES = 52, OR_T_APPEND_ENTRIES_RES = 53
 };
 enum { OR_F_MSG_ID = 1, OR_F_REPLY = 2, OR_F_CREATE = 4 /* cas create_if_not_exists */ };
 
@@ -130,6 +136,13 @@ void     or_stats(or_sim*, uint64_t out[9]);
 size_t   or_node_set(or_sim*, uint32_t node, uint32_t* vals, size_t cap);
 size_t   or_read_snapshot(or_sim*, uint64_t msg_id, uint32_t* vals, size_t cap);
 uint64_t or_client_replies(or_sim*);
+
+/* Raft node inspection: out[0..7] = state (0 nascent, 1 follower, 2 candidate, 3 leader), term,
+ * voted_for + 1, commit_index, last_applied, leader + 1, log size, kv entries */
+int      or_raft_state(or_sim*, uint32_t node, uint64_t out[8]);
+/* the payload of append_entries k of `sender`: out[0..3] = prev_log_index, prev_log_term,
+ * leader_commit, n_entries; returns 0 when unknown */
+int      or_raft_append(or_sim*, uint32_t sender, uint64_t k, uint32_t out[4]);
 
 /* A service on its own, driven like the reference's unit test drives handle!
  * (test/maelstrom/service_test.clj:6-53): `rnd` is the 32-bit draw standing in for rand-int. */

@@ -25,14 +25,15 @@ OP_DTYPE = np.dtype([("time_ns", "<i8"), ("src", "<u4"), ("dest", "<u4"), ("body
 assert MSG_DTYPE.itemsize == 48 and EVENT_DTYPE.itemsize == 32
 assert BODY_DTYPE.itemsize == 24 and OP_DTYPE.itemsize == 40
 
-W_ECHO, W_BROADCAST, W_GSET = 0, 1, 2
+W_ECHO, W_BROADCAST, W_GSET, W_RAFT = 0, 1, 2, 3
 TOPO = {"grid": 0, "line": 1, "total": 2, "tree": 3, "tree2": 3, "tree3": 4, "tree4": 5}
 DIST = {"constant": 0, "uniform": 1, "exponential": 2}
 KIND_SERVER, KIND_CLIENT, KIND_HOST, KIND_SIM_CLIENT, KIND_SERVICE = 0, 1, 2, 3, 4
 SVC = {"lin-kv": 0, "seq-kv": 1, "lww-kv": 2, "lin-tso": 3}
 T = dict(init=1, init_ok=2, error=3, echo=10, echo_ok=11, topology=20, topology_ok=21,
          broadcast=22, broadcast_ok=23, read=24, read_ok=25, add=30, add_ok=31,
-         replicate_one=32, replicate_full=33, write=40, write_ok=41, cas=42, cas_ok=43, ts=44, ts_ok=45)
+         replicate_one=32, replicate_full=33, write=40, write_ok=41, cas=42, cas_ok=43, ts=44, ts_ok=45,
+         request_vote=50, request_vote_res=51, append_entries=52, append_entries_res=53)
 F_MSG_ID, F_REPLY, F_CREATE = 1, 2, 4
 RECV_BIT = 1 << 63
 
@@ -103,6 +104,8 @@ def lib():
         L.or_latency_draw.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         L.or_loss_threshold.restype = C.c_uint64
         L.or_loss_threshold.argtypes = [C.c_double]
+        L.or_raft_state.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        L.or_raft_append.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p]
         L.or_service_new.restype = C.c_void_p
         L.or_service_new.argtypes = [C.c_int, C.c_uint32]
         L.or_service_free.argtypes = [C.c_void_p]
@@ -255,6 +258,17 @@ class Sim:
         out = np.zeros(n, dtype=np.uint32)
         self.L.or_read_snapshot(self.h, msg_id, out.ctypes.data, n)
         return out
+
+    RAFT_FIELDS = ("state", "term", "voted_for", "commit_index", "last_applied", "leader", "log_size", "kv_size")
+
+    def raft_state(self, node):
+        """state 0 nascent / 1 follower / 2 candidate / 3 leader; voted_for and leader are -1 when unset"""
+        out = np.zeros(8, dtype=np.uint64)
+        self._chk(self.L.or_raft_state(self.h, node, out.ctypes.data))
+        d = dict(zip(self.RAFT_FIELDS, (int(x) for x in out)))
+        d["voted_for"] -= 1
+        d["leader"] -= 1
+        return d
 
     def client_replies(self):
         return int(self.L.or_client_replies(self.h))
