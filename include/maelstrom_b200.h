@@ -79,7 +79,8 @@ typedef struct ms_op {
 } ms_op;
 
 enum { MS_F_MSG_ID = 1, MS_F_REPLY = 2,
-       MS_F_CREATE = 4 };   /* cas: create_if_not_exists (service.clj:50-54) */
+       MS_F_CREATE = 4,     /* cas: create_if_not_exists (service.clj:50-54) */
+       MS_F_APPENDS = 8 };  /* txn: the micro-op list contains an append */
 
 /* body.type codes (doc/workloads.md) */
 enum {
@@ -97,11 +98,18 @@ enum {
    * last_log_term << 32; *_res p0 = term, p1 = vote_granted / success; append_entries p0 = term,
    * p1 = k: the sender's k-th append_entries; {prev_log_index, prev_log_term, leader_commit,
    * entries} stay in the sender's payload heap on the device */
-  MS_T_REQUEST_VOTE = 50, MS_T_REQUEST_VOTE_RES = 51, MS_T_APPEND_ENTRIES = 52, MS_T_APPEND_ENTRIES_RES = 53
+  MS_T_REQUEST_VOTE = 50, MS_T_REQUEST_VOTE_RES = 51, MS_T_APPEND_ENTRIES = 52, MS_T_APPEND_ENTRIES_RES = 53,
+  /* txn-list-append: txn p1 = the caller's handle of the micro-op list, flag MS_F_APPENDS when it
+   * contains an append; txn_ok p1 = version read | version written << 32.  Database values are
+   * carried as version ids: 0 = nil (no root yet), 1 = the empty database, others minted by the
+   * node whose cas installs them; the caller replays apply-txn (single_key_txn.clj:115-127) over them */
+  MS_T_TXN = 60, MS_T_TXN_OK = 61
 };
 
 enum { MS_W_ECHO = 0, MS_W_BROADCAST = 1, MS_W_GSET = 2,                     /* --workload, core.clj:36-47 */
-       MS_W_RAFT = 3 };  /* lin-kv served by Raft nodes (demo/python/raft.py) */
+       MS_W_RAFT = 3,    /* lin-kv served by Raft nodes (demo/python/raft.py) */
+       MS_W_TXN = 4 };   /* txn-list-append, whole database in one lin-kv key (demo/clojure/single_key_txn.clj);
+                            needs the "lin-kv" service endpoint */
 enum { MS_TOPO_GRID = 0, MS_TOPO_LINE = 1, MS_TOPO_TOTAL = 2,                /* --topology, broadcast.clj:169-178 */
        MS_TOPO_TREE2 = 3, MS_TOPO_TREE3 = 4, MS_TOPO_TREE4 = 5 };
 enum { MS_DIST_CONSTANT = 0, MS_DIST_UNIFORM = 1, MS_DIST_EXPONENTIAL = 2 }; /* --latency-dist, net.clj:73-77 */

@@ -415,7 +415,7 @@ static int build_sim(ms_sim* s, const ms_config* in) {
   ms_config& c = s->cfg;
   c = *in;
   if (c.n_nodes == 0) { set_err("n_nodes must be positive (--node-count)"); return MS_ERR_ARG; }
-  if (c.workload > MS_W_RAFT || c.topology > MS_TOPO_TREE4 || c.latency_dist > MS_DIST_EXPONENTIAL) {
+  if (c.workload > MS_W_TXN || c.topology > MS_TOPO_TREE4 || c.latency_dist > MS_DIST_EXPONENTIAL) {
     set_err("bad workload/topology/latency_dist");
     return MS_ERR_ARG;
   }
@@ -556,7 +556,17 @@ static int build_sim(ms_sim* s, const ms_config* in) {
   } else if (c.workload == MS_W_ECHO) {
     if ((rc = s->dalloc(&P.next_msg_id, c.n_nodes))) return rc;
   }
-  P.family = c.workload == MS_W_GSET ? 1u : (c.workload == MS_W_RAFT ? 4u : 0u);
+  P.family = c.workload == MS_W_GSET ? 1u : (c.workload >= MS_W_RAFT ? 4u : 0u);
+  if (c.workload == MS_W_TXN) {
+    // txn-list-append nodes: message ids, the table of pending RPC closures and the staging rows of
+    // the sequential step (csrc/ms_raft.cuh)
+    if (c.n_shards > 1) { set_err("workload txn-list-append runs on one GPU for now"); return MS_ERR_ARG; }
+    const size_t N = c.n_nodes;
+    P.rf_stage_cap = c.max_window + 16u;
+    if ((rc = s->dalloc(&P.rf_node, N)) || (rc = s->dalloc(&P.rf_cb, N * kRaftCallbacks * 2)) ||
+        (rc = s->dalloc(&P.rf_stage, N * P.rf_stage_cap * 3)))
+      return rc;
+  }
   if (c.workload == MS_W_RAFT) {
     // Raft nodes (csrc/ms_raft.cuh): per-node log, KV store, leader tables, pending-RPC closures,
     // the staging rows of the sequential step and the heap of append_entries payloads

@@ -1251,7 +1251,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
       __syncthreads();
     }
     if constexpr (RF) {
-      // ---- Raft node: the step is sequential (ms_raft.cuh); its sends are staged and emitted below
+      // ---- Raft / txn-list-append node: the step is sequential (ms_raft.cuh); its sends are staged and emitted below
       if (is_server) {
         if (tid == 0) {
           RaftCtx c{p, st, e, now, round, p.rf_node + e, p.rf_log + (size_t)e * p.rf_log_cap * 2,
@@ -1260,9 +1260,10 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
             const uint32_t i = ord[pos];
             if (!(vals[i] & V_RECV)) continue;
             const uint4* rp = myring + (size_t)((head + i) & p.ring_mask) * 3;
-            rf_handle(c, rec_unpack(rp[0], rp[1], rp[2]));
+            if (p.workload == MS_W_RAFT) rf_handle(c, rec_unpack(rp[0], rp[1], rp[2]));
+            else txn_handle(c, rec_unpack(rp[0], rp[1], rp[2]));
           }
-          rf_actions(c);
+          if (p.workload == MS_W_RAFT) rf_actions(c);
           s_misc[2] = c.n_stage;
         }
         __syncthreads();

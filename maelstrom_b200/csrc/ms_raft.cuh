@@ -336,3 +336,74 @@ __device__ void rf_actions(RaftCtx& c) {
     if (r->state == RAFT_LEADER) rf_emit(c, res);
   }
 }
+
+// ------------------------------------------------------------------ txn-list-append, single key
+// demo/clojure/single_key_txn.clj: the whole database is one value under key "root" (key 0) of
+// the lin-kv service (:134-141).  handle-txn! (:163-173) = read the root, apply-txn, cas the
+// root from what was read to the result (create_if_not_exists), answer txn_ok -- or error 30
+// when the cas fails with 22.  Database values travel as version ids (include/maelstrom_b200.h):
+// apply-txn (:115-127) is a pure function of (value, txn), so the node only has to know whether
+// the txn appends.  Every request runs in its own future (:93-95): the two RPCs of a txn are
+// closures in the node's table, like Raft's.  Uses RaftDev.next_msg_id / .appends (versions minted).
+__device__ void txn_handle(RaftCtx& c, const Rec& m) {
+  RaftDev* r = c.r;
+  const uint32_t type = m.tf & 0xFFFFu, flags = m.tf >> 16;
+  const uint32_t lin_kv = c.p.sv_ep[MS_SVC_LIN_KV];
+  if (flags & MS_F_REPLY) {                                                       // handle-reply!, :60-68
+    uint4* slot = c.cb + 2 * (size_t)(m.in_reply_to % kRaftCallbacks);
+    const uint4 s0 = slot[0], s1 = slot[1];
+    if (s0.y == 0 || s0.x != m.in_reply_to) return;                               // no such future
+    slot[0] = make_uint4(0u, 0u, 0u, 0u);
+    Rec req;                                                                      // the txn request being served
+    req.round = 0; req.ticket = 0; req.idx = 0;
+    req.src = s0.w; req.dest = c.e; req.msg_id = s0.z; req.in_reply_to = 0; req.tf = MS_T_TXN; req.p0 = 0; req.p1 = 0;
+    if (s0.y == 3) {                                                              // read-service, :143-150
+      uint32_t old_v;
+      if (type == MS_T_READ_OK) old_v = (uint32_t)m.p1;
+      else if (type == MS_T_ERROR && m.p0 == 20) old_v = 0;                       // not found: nil
+      else { Rec er = rf_reply_to(c, req, MS_T_ERROR); er.p0 = m.p0; rf_emit(c, er); return; }   // :99-103
+      uint32_t new_v;
+      if (s1.y) new_v = 2u + c.e + c.p.n_servers * (r->appends++);               // an append: a value nobody has seen
+      else new_v = old_v == 0 ? 1u : old_v;                                       // reads only: unchanged ({} for nil)
+      const uint32_t id = ++r->next_msg_id;                                       // (swap! next-message-id inc), :54
+      uint4* s2 = c.cb + 2 * (size_t)(id % kRaftCallbacks);
+      s2[0] = make_uint4(id, 4u, s0.z, s0.w);
+      s2[1] = make_uint4(old_v, new_v, 0u, 0u);
+      Rec q;                                                                      // cas-service!, :152-161
+      q.round = 0; q.ticket = 0; q.idx = 0;
+      q.src = c.e; q.dest = lin_kv; q.msg_id = id; q.in_reply_to = 0;
+      q.tf = MS_T_CAS | ((uint32_t)(MS_F_MSG_ID | MS_F_CREATE) << 16);
+      q.p0 = 0; q.p1 = (uint64_t)old_v | ((uint64_t)new_v << 32);
+      rf_emit(c, q);
+    } else if (s0.y == 4) {                                                       // :168-173
+      if (type == MS_T_CAS_OK) {
+        Rec ok = rf_reply_to(c, req, MS_T_TXN_OK);
+        ok.p1 = (uint64_t)s1.x | ((uint64_t)s1.y << 32);
+        rf_emit(c, ok);
+      } else {
+        Rec er = rf_reply_to(c, req, MS_T_ERROR);
+        er.p0 = (type == MS_T_ERROR && m.p0 == 22) ? 30u : m.p0;                  // "root altered"
+        rf_emit(c, er);
+      }
+    }
+    return;
+  }
+  if (type == MS_T_INIT) { rf_emit(c, rf_reply_to(c, m, MS_T_INIT_OK)); return; }   // :70-77
+  if (type == MS_T_TXN) {                                                         // handle-txn!, :163-173
+    if (lin_kv == 0xFFFFFFFFu) { latch_error(c.st, E_INVALID_DEST, lin_kv); return; }   // no lin-kv service
+    const uint32_t id = ++r->next_msg_id;
+    uint4* s2 = c.cb + 2 * (size_t)(id % kRaftCallbacks);
+    s2[0] = make_uint4(id, 3u, m.msg_id, m.src);
+    s2[1] = make_uint4(0u, (flags & MS_F_APPENDS) ? 1u : 0u, 0u, 0u);
+    Rec q;
+    q.round = 0; q.ticket = 0; q.idx = 0;
+    q.src = c.e; q.dest = lin_kv; q.msg_id = id; q.in_reply_to = 0;
+    q.tf = MS_T_READ | ((uint32_t)MS_F_MSG_ID << 16);
+    q.p0 = 0; q.p1 = 0;
+    rf_emit(c, q);
+    return;
+  }
+  Rec er = rf_reply_to(c, m, MS_T_ERROR);                                         // "Unknown request type", :85-88
+  er.p0 = 10;
+  rf_emit(c, er);
+}

@@ -31,6 +31,10 @@ class Net:
         self._next_blob = 1
         self._types = dict(TYPES)
         self._type_names = dict(TYPE_NAMES)
+        # txn-list-append: database values travel as version ids (include/maelstrom_b200.h); the
+        # contents are replayed here with apply-txn (demo/clojure/single_key_txn.clj:115-127)
+        self._versions = {0: {}, 1: {}}
+        self._txn_of = {}                                             # (client, msg_id) -> micro-ops
 
     # ---------------------------------------------------------------- endpoints
     def add_node(self, node_id):                                      # add-node!  net.clj:139-146
@@ -81,6 +85,13 @@ class Net:
         elif t == "add":
             p0 = int(body["element"])
         create = False
+        if t == "txn":                                                # workload/txn_list_append.clj
+            ops = [list(op) for op in body["txn"]]
+            p1 = self._next_blob
+            self._next_blob += 1
+            self._blobs[p1] = ops
+            return self._body(self._type_code(t), msg_id=body.get("msg_id"), p1=p1,
+                              appends=any(op[0] == "append" for op in ops))
         if "key" in body and t in ("read", "write", "cas"):           # service requests (doc/services.md)
             p0 = int(body["key"])
             if t == "write":
@@ -116,6 +127,20 @@ class Net:
             body["text"] = errors.name(int(m["p0"]))
         elif t == "read_ok" and self.names.get(int(m["src"])) in SERVICES:
             body["value"] = int(m["p1"])                                # service.clj:38-40
+        elif t == "txn_ok":
+            old, new = int(m["p1"]) & 0xFFFFFFFF, int(m["p1"]) >> 32
+            ops = self._txn_of.pop((int(m["dest"]), int(m["in_reply_to"])), None)
+            if ops is not None and old in self._versions:
+                state, done = dict(self._versions[old]), []
+                for f, k, v in ops:                                   # apply-txn
+                    if f == "r":
+                        done.append([f, k, list(state[k]) if k in state else None])
+                    else:
+                        state[k] = list(state.get(k, [])) + [v]
+                        done.append([f, k, v])
+                self._versions[new] = state
+                body["txn"] = done
+            body["versions"] = [old, new]
         elif t == "ts_ok":
             body["ts"] = int(m["p1"])                                   # service.clj:127-128
         elif t == "read_ok":
@@ -135,6 +160,8 @@ class Net:
         assert dest, "No destination for message %r" % (message,)
         assert src in self.ids, "Invalid source for message %r" % (message,)      # net.clj:172-173
         assert dest in self.ids, "Invalid dest for message %r" % (message,)       # net.clj:174-175
+        if message["body"].get("type") == "txn" and "msg_id" in message["body"]:
+            self._txn_of[(self.ids[src], int(message["body"]["msg_id"]))] = [list(op) for op in message["body"]["txn"]]
         rc = self.sim.send(self.ids[src], self.ids[dest], self._encode(message["body"]))
         if rc < 0:
             raise NodeNotFound("No such node in network: %r" % (dest,))

@@ -794,6 +794,76 @@ struct or_sim {
     }
   }
 
+  // ------------------------------------------------------------- txn-list-append (demo/clojure/single_key_txn.clj)
+  // The whole database is one value under key "root" (key 0 here) of lin-kv (:134-141).  A
+  // database value is carried as a version id (see oracle.h); apply-txn (:115-127) is a pure
+  // function of (value, txn), so the node only has to know whether the txn changes the value.
+  void node_txn(uint32_t e, const or_msg& m, std::vector<Emit>& out) {
+    RaftNode& r = eps[e].rn;                       // next_msg_id, callbacks, appends (= versions minted)
+    int lin_kv = -1;
+    for (uint32_t i = cfg.n_nodes; i < eps.size(); i++)
+      if (eps[i].live && eps[i].kind == OR_KIND_SERVICE && eps[i].svc.type == OR_SVC_LIN_KV) lin_kv = (int)i;
+    if (m.flags & OR_F_REPLY) {                                                  // handle-reply!, :60-68
+      RaftCb& slot = r.callbacks[m.in_reply_to % kRaftCallbacks];
+      if (slot.kind == 0 || slot.msg_id != m.in_reply_to) return;                 // no such future
+      const RaftCb cb = slot;
+      slot.kind = 0;
+      or_msg req; std::memset(&req, 0, sizeof req);                              // the txn request being served
+      req.src = cb.node; req.dest = e; req.msg_id = cb.term;
+      if (cb.kind == 3) {                                                         // read-service, :143-150
+        uint32_t old_v;
+        if (m.type == OR_T_READ_OK) old_v = (uint32_t)m.p1;
+        else if (m.type == OR_T_ERROR && m.p0 == 20) old_v = 0;                   // not found: nil
+        else { or_msg er = reply_to(req, OR_T_ERROR); er.p0 = m.p0; out.push_back(Emit(er)); return; }   // :99-103
+        // apply-txn: an append makes a value nobody has seen; reads leave it as it is ({} for nil)
+        uint32_t new_v;
+        if (cb.n_entries) new_v = 2u + e + cfg.n_nodes * (uint32_t)(r.appends++);
+        else new_v = old_v == 0 ? 1u : old_v;
+        if (lin_kv < 0) { error = "txn-list-append needs the lin-kv service"; return; }
+        or_msg c; std::memset(&c, 0, sizeof c);                                   // cas-service!, :152-161
+        c.type = OR_T_CAS; c.p0 = 0; c.p1 = (uint64_t)old_v | ((uint64_t)new_v << 32);
+        RaftCb n2; n2.kind = 4; n2.node = cb.node; n2.term = cb.term; n2.ni = (int64_t)old_v; n2.n_entries = new_v;
+        const uint32_t id = ++r.next_msg_id;                                      // (swap! next-message-id inc), :54
+        n2.msg_id = id;
+        r.callbacks[id % kRaftCallbacks] = n2;
+        c.src = e; c.dest = (uint32_t)lin_kv; c.flags = OR_F_MSG_ID | OR_F_CREATE; c.msg_id = id;
+        out.push_back(Emit(c));
+      } else if (cb.kind == 4) {                                                  // :168-173
+        if (m.type == OR_T_CAS_OK) {
+          or_msg ok = reply_to(req, OR_T_TXN_OK);
+          ok.p1 = (uint64_t)(uint32_t)cb.ni | ((uint64_t)cb.n_entries << 32);
+          out.push_back(Emit(ok));
+        } else {
+          or_msg er = reply_to(req, OR_T_ERROR);
+          er.p0 = (m.type == OR_T_ERROR && m.p0 == 22) ? 30 : m.p0;              // "root altered"
+          out.push_back(Emit(er));
+        }
+      }
+      return;
+    }
+    switch (m.type) {
+      case OR_T_INIT: out.push_back(Emit(reply_to(m, OR_T_INIT_OK))); return;     // :70-77
+      case OR_T_TXN: {                                                            // handle-txn!, :163-173
+        if (lin_kv < 0) { error = "txn-list-append needs the lin-kv service"; return; }
+        or_msg q; std::memset(&q, 0, sizeof q);
+        q.type = OR_T_READ; q.p0 = 0;
+        RaftCb cb; cb.kind = 3; cb.node = m.src; cb.term = m.msg_id; cb.n_entries = (m.flags & OR_F_APPENDS) ? 1 : 0;
+        const uint32_t id = ++r.next_msg_id;
+        cb.msg_id = id;
+        r.callbacks[id % kRaftCallbacks] = cb;
+        q.src = e; q.dest = (uint32_t)lin_kv; q.flags = OR_F_MSG_ID; q.msg_id = id;
+        out.push_back(Emit(q));
+        return;
+      }
+      default: {                                                                  // "Unknown request type", :85-88
+        or_msg er = reply_to(m, OR_T_ERROR);
+        er.p0 = 10;
+        out.push_back(Emit(er));
+        return;
+      }
+    }
+  }
+
   bool run_round() {
     std::vector<Envelope> pending;
     // (1) injector
@@ -855,6 +925,7 @@ struct or_sim {
             else if (cfg.workload == OR_W_BROADCAST) node_broadcast(e, m, out);
             else if (cfg.workload == OR_W_GSET) node_gset(e, m, out);
             else if (cfg.workload == OR_W_RAFT) node_raft(e, m, out);
+            else if (cfg.workload == OR_W_TXN) node_txn(e, m, out);
             else { error = "workload not implemented in oracle"; return false; }
         }
         if (!error.empty()) return false;

@@ -80,7 +80,8 @@ typedef struct or_config {
 } or_config;
 
 enum { OR_W_ECHO = 0, OR_W_BROADCAST = 1, OR_W_GSET = 2,
-       OR_W_RAFT = 3 };   /* lin-kv workload served by Raft nodes (demo/python/raft.py) */
+       OR_W_RAFT = 3,     /* lin-kv workload served by Raft nodes (demo/python/raft.py) */
+       OR_W_TXN = 4 };    /* txn-list-append, whole database in one lin-kv key (demo/clojure/single_key_txn.clj) */
 enum { OR_TOPO_GRID = 0, OR_TOPO_LINE = 1, OR_TOPO_TOTAL = 2,
        OR_TOPO_TREE2 = 3, OR_TOPO_TREE3 = 4, OR_TOPO_TREE4 = 5 };
 enum { OR_DIST_CONSTANT = 0, OR_DIST_UNIFORM = 1, OR_DIST_EXPONENTIAL = 2 };
@@ -101,9 +102,14 @@ enum {
    * last_log_term << 32; *_res p0 = term, p1 = vote_granted / success; append_entries p0 = term,
    * p1 = k, the sender's k-th append_entries, naming {prev_log_index, prev_log_term,
    * leader_commit, entries} (or_raft_append) */
-  OR_T_REQUEST_VOTE = 50, OR_T_REQUEST_VOTE_RES = 51, OR_T_APPEND_ENTRIES = 52, OR_T_APPEND_ENTRIES_RES = 53
+  OR_T_REQUEST_VOTE = 50, OR_T_REQUEST_VOTE_RES = 51, OR_T_APPEND_ENTRIES = 52, OR_T_APPEND_ENTRIES_RES = 53,
+  /* txn-list-append: txn p1 = handle of the micro-op list (host side), flag OR_F_APPENDS when it
+   * appends; txn_ok p1 = version read | version written << 32.  Database values travel as
+   * version ids: 0 = nil (no root yet), 1 = the empty database, others minted by the writer. */
+  OR_T_TXN = 60, OR_T_TXN_OK = 61
 };
-enum { OR_F_MSG_ID = 1, OR_F_REPLY = 2, OR_F_CREATE = 4 /* cas create_if_not_exists */ };
+enum { OR_F_MSG_ID = 1, OR_F_REPLY = 2, OR_F_CREATE = 4 /* cas create_if_not_exists */,
+       OR_F_APPENDS = 8 /* txn contains an append */ };
 
 typedef struct or_sim or_sim;
 

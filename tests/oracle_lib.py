@@ -25,7 +25,7 @@ OP_DTYPE = np.dtype([("time_ns", "<i8"), ("src", "<u4"), ("dest", "<u4"), ("body
 assert MSG_DTYPE.itemsize == 48 and EVENT_DTYPE.itemsize == 32
 assert BODY_DTYPE.itemsize == 24 and OP_DTYPE.itemsize == 40
 
-W_ECHO, W_BROADCAST, W_GSET, W_RAFT = 0, 1, 2, 3
+W_ECHO, W_BROADCAST, W_GSET, W_RAFT, W_TXN = 0, 1, 2, 3, 4
 TOPO = {"grid": 0, "line": 1, "total": 2, "tree": 3, "tree2": 3, "tree3": 4, "tree4": 5}
 DIST = {"constant": 0, "uniform": 1, "exponential": 2}
 KIND_SERVER, KIND_CLIENT, KIND_HOST, KIND_SIM_CLIENT, KIND_SERVICE = 0, 1, 2, 3, 4
@@ -33,8 +33,9 @@ SVC = {"lin-kv": 0, "seq-kv": 1, "lww-kv": 2, "lin-tso": 3}
 T = dict(init=1, init_ok=2, error=3, echo=10, echo_ok=11, topology=20, topology_ok=21,
          broadcast=22, broadcast_ok=23, read=24, read_ok=25, add=30, add_ok=31,
          replicate_one=32, replicate_full=33, write=40, write_ok=41, cas=42, cas_ok=43, ts=44, ts_ok=45,
-         request_vote=50, request_vote_res=51, append_entries=52, append_entries_res=53)
-F_MSG_ID, F_REPLY, F_CREATE = 1, 2, 4
+         request_vote=50, request_vote_res=51, append_entries=52, append_entries_res=53,
+         txn=60, txn_ok=61)
+F_MSG_ID, F_REPLY, F_CREATE, F_APPENDS = 1, 2, 4, 8
 RECV_BIT = 1 << 63
 
 
@@ -133,11 +134,11 @@ def latency_draw(dist, mean_ms, scale, x):
     return int(lib().or_latency_draw(DIST[dist], mean_ms, scale, xs.ctypes.data))
 
 
-def body(type, msg_id=None, in_reply_to=None, p0=0, p1=0, create=False):
+def body(type, msg_id=None, in_reply_to=None, p0=0, p1=0, create=False, appends=False):
     b = Body()
     b.type = T[type] if isinstance(type, str) else type
     b.flags = ((F_MSG_ID if msg_id is not None else 0) | (F_REPLY if in_reply_to is not None else 0) |
-               (F_CREATE if create else 0))
+               (F_CREATE if create else 0) | (F_APPENDS if appends else 0))
     b.msg_id = msg_id or 0
     b.in_reply_to = in_reply_to or 0
     b.p0 = p0

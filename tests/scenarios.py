@@ -13,7 +13,7 @@ def make_pair(n_nodes, **kw):
         "calendar_slots", "calendar_cap", "mailbox_cap", "inject_cap", "threads_per_node")}
     workload = kw.pop("workload", "broadcast")
     g = mb.Sim(n_nodes, workload=workload, **kw, **sizing)
-    o = O.Sim(n_nodes, workload={"echo": O.W_ECHO, "broadcast": O.W_BROADCAST, "g-set": O.W_GSET, "lin-kv": O.W_RAFT}[workload], **kw)
+    o = O.Sim(n_nodes, workload={"echo": O.W_ECHO, "broadcast": O.W_BROADCAST, "g-set": O.W_GSET, "lin-kv": O.W_RAFT, "txn-list-append": O.W_TXN}[workload], **kw)
     return g, o
 
 
