@@ -186,6 +186,10 @@ struct Params {
   uint64_t* rf_ext_off;      // [n_servers][kRaftExt] heap offset of the sender's k-th append_entries
   uint32_t* rf_ext_tag;      // [n_servers][kRaftExt] k
   uint32_t  rf_log_cap, rf_n_keys, rf_stage_cap, rf_heap_mask, rf_vote_words;
+  // append_entries payloads of every shard (index = shard): read where the sender wrote them
+  uint4*    rf_heap_sh[8];
+  uint64_t* rf_ext_off_sh[8];
+  uint32_t* rf_ext_tag_sh[8];
 };
 
 constexpr uint32_t kRaftCallbacks = 4096;       // pending-RPC table slots per node (oracle: same constant)

@@ -560,7 +560,7 @@ static int build_sim(ms_sim* s, const ms_config* in) {
   if (c.workload == MS_W_TXN) {
     // txn-list-append nodes: message ids, the table of pending RPC closures and the staging rows of
     // the sequential step (csrc/ms_raft.cuh)
-    if (c.n_shards > 1) { set_err("workload txn-list-append runs on one GPU for now"); return MS_ERR_ARG; }
+    // (nothing here is read across nodes: sharded runs need no extra mapping)
     const size_t N = c.n_nodes;
     P.rf_stage_cap = c.max_window + 16u;
     if ((rc = s->dalloc(&P.rf_node, N)) || (rc = s->dalloc(&P.rf_cb, N * kRaftCallbacks * 2)) ||
@@ -570,7 +570,6 @@ static int build_sim(ms_sim* s, const ms_config* in) {
   if (c.workload == MS_W_RAFT) {
     // Raft nodes (csrc/ms_raft.cuh): per-node log, KV store, leader tables, pending-RPC closures,
     // the staging rows of the sequential step and the heap of append_entries payloads
-    if (c.n_shards > 1) { set_err("workload lin-kv (Raft) runs on one GPU for now"); return MS_ERR_ARG; }
     const size_t N = c.n_nodes;
     P.rf_n_keys = c.reserved[2] ? c.reserved[2] : 4096u;
     P.rf_log_cap = c.reserved[3] ? c.reserved[3] : 4096u;
@@ -584,8 +583,12 @@ static int build_sim(ms_sim* s, const ms_config* in) {
         (rc = s->dalloc(&P.rf_scratch, N * N)) || (rc = s->dalloc(&P.rf_cb, N * kRaftCallbacks * 2)) ||
         (rc = s->dalloc(&P.rf_votes, N * P.rf_vote_words)) || (rc = s->dalloc(&P.rf_stage, N * P.rf_stage_cap * 3)) ||
         (rc = s->dalloc(&P.rf_heap, (size_t)heap_words)) || (rc = s->dalloc(&P.rf_heap_cursor, 1)) ||
-        (rc = s->dalloc(&P.rf_ext_off, N * kRaftExt)) || (rc = s->dalloc(&P.rf_ext_tag, N * kRaftExt)))
+        (rc = s->dalloc(&P.rf_ext_off, N * kRaftExt + (N * kRaftExt + 1) / 2)))   // offsets, then the u32 tags
       return rc;
+    P.rf_ext_tag = reinterpret_cast<uint32_t*>(P.rf_ext_off + N * kRaftExt);    // one allocation: one IPC handle
+    P.rf_heap_sh[c.shard_id] = P.rf_heap;
+    P.rf_ext_off_sh[c.shard_id] = P.rf_ext_off;
+    P.rf_ext_tag_sh[c.shard_id] = P.rf_ext_tag;
     // fresh nodes: nascent, empty log but for the default entry {term 0, op None} (raft.py:121), last_applied 1
     std::vector<RaftDev> init(N);
     memset(init.data(), 0, N * sizeof(RaftDev));
@@ -1047,7 +1050,7 @@ struct ShardBlob {   // MS_SHARD_BLOB_BYTES
   uint32_t magic, shard_id, n_shards, t_max;
   uint32_t max_endpoints, ring_cap, hist, pad;
   cudaIpcMemHandle_t ring, tail, head, rt_cnt, bar;
-  cudaIpcMemHandle_t gs_snap, gs_tag;   // g-set only (pad = 1)
+  cudaIpcMemHandle_t gs_snap, gs_tag;   // pad = 1: g-set snapshot rows, tags; pad = 2: Raft payload heap, handle table
 };
 static_assert(sizeof(ShardBlob) <= MS_SHARD_BLOB_BYTES, "blob too large");
 
@@ -1068,6 +1071,10 @@ int ms_shard_handles(ms_sim* s, void* blob_out) {
     b.pad = 1;
     CK(cudaIpcGetMemHandle(&b.gs_snap, s->P.gs_snap));
     CK(cudaIpcGetMemHandle(&b.gs_tag, s->P.gs_tag));
+  } else if (s->P.rf_heap) {
+    b.pad = 2;
+    CK(cudaIpcGetMemHandle(&b.gs_snap, s->P.rf_heap));
+    CK(cudaIpcGetMemHandle(&b.gs_tag, s->P.rf_ext_off));
   }
   memset(blob_out, 0, MS_SHARD_BLOB_BYTES);
   memcpy(blob_out, &b, sizeof b);
@@ -1097,7 +1104,18 @@ int ms_shard_connect(ms_sim* s, uint32_t peer, const void* blob) {
   s->peer_ptrs.push_back(ptr); s->P.rt_cnt_sh[peer] = (uint64_t*)ptr;
   CK(cudaIpcOpenMemHandle(&ptr, b.bar, cudaIpcMemLazyEnablePeerAccess));
   s->peer_ptrs.push_back(ptr); s->P.bar_sh[peer] = (uint32_t*)ptr;
-  if ((b.pad == 1) != (s->P.gs_snap != nullptr)) { set_err("ms_shard_connect: peer runs another workload"); return MS_ERR_ARG; }
+  if ((b.pad == 1) != (s->P.gs_snap != nullptr) || (b.pad == 2) != (s->P.rf_heap != nullptr)) {
+    set_err("ms_shard_connect: peer runs another workload");
+    return MS_ERR_ARG;
+  }
+  if (b.pad == 2) {
+    const size_t N = s->cfg.n_nodes;
+    CK(cudaIpcOpenMemHandle(&ptr, b.gs_snap, cudaIpcMemLazyEnablePeerAccess));
+    s->peer_ptrs.push_back(ptr); s->P.rf_heap_sh[peer] = (uint4*)ptr;
+    CK(cudaIpcOpenMemHandle(&ptr, b.gs_tag, cudaIpcMemLazyEnablePeerAccess));
+    s->peer_ptrs.push_back(ptr); s->P.rf_ext_off_sh[peer] = (uint64_t*)ptr;
+    s->P.rf_ext_tag_sh[peer] = reinterpret_cast<uint32_t*>((uint64_t*)ptr + N * kRaftExt);
+  }
   if (b.pad == 1) {
     CK(cudaIpcOpenMemHandle(&ptr, b.gs_snap, cudaIpcMemLazyEnablePeerAccess));
     s->peer_ptrs.push_back(ptr); s->P.gs_snap_sh[peer] = (uint32_t*)ptr;

@@ -203,11 +203,15 @@ __device__ void rf_handle(RaftCtx& c, const Rec& m) {
     rf_reset_election_deadline(c);
     // the payload: the sender's k-th append_entries, in the payload heap
     const uint32_t k = (uint32_t)m.p1;
-    if (m.src >= c.p.n_servers || c.p.rf_ext_tag[(size_t)m.src * kRaftExt + k % kRaftExt] != k) return;   // forged handle
-    const uint64_t off = c.p.rf_ext_off[(size_t)m.src * kRaftExt + k % kRaftExt];
-    const uint4 guard = c.p.rf_heap[off & c.p.rf_heap_mask];
+    if (m.src >= c.p.n_servers) return;
+    // the payload lives in the heap of the sender's shard (NVLink peer memory when that is not ours)
+    const uint32_t o = owner_of(m.src, c.p.n_servers, c.p.n_shards);
+    const uint4* heap = c.p.rf_heap_sh[o];
+    if (__ldcg(c.p.rf_ext_tag_sh[o] + (size_t)m.src * kRaftExt + k % kRaftExt) != k) return;             // forged handle
+    const uint64_t off = __ldcg(c.p.rf_ext_off_sh[o] + (size_t)m.src * kRaftExt + k % kRaftExt);
+    const uint4 guard = __ldcg(heap + (off & c.p.rf_heap_mask));
     if (guard.x != m.src || guard.y != k) { latch_error(c.st, E_SNAPSHOT, m.src); return; }               // overwritten
-    const uint4 hd = c.p.rf_heap[(off + 1) & c.p.rf_heap_mask];
+    const uint4 hd = __ldcg(heap + ((off + 1) & c.p.rf_heap_mask));
     const uint32_t prev_log_index = hd.x, prev_log_term = hd.y, leader_commit = hd.z, n_entries = hd.w;
     if (prev_log_index == 0) return;                                              // "Out of bounds previous log index"
     if (prev_log_index > r->log_size || rf_log_term(c, prev_log_index) != prev_log_term) {
@@ -216,8 +220,8 @@ __device__ void rf_handle(RaftCtx& c, const Rec& m) {
     }
     if (prev_log_index + n_entries > c.p.rf_log_cap) { latch_error(c.st, E_RAFT_CAPACITY, c.e); return; }
     for (uint32_t q = 0; q < n_entries; q++) {                                    // truncate + append, :533-534
-      c.log[2 * (size_t)(prev_log_index + q)] = c.p.rf_heap[(off + 2 + 2 * (uint64_t)q) & c.p.rf_heap_mask];
-      c.log[2 * (size_t)(prev_log_index + q) + 1] = c.p.rf_heap[(off + 3 + 2 * (uint64_t)q) & c.p.rf_heap_mask];
+      c.log[2 * (size_t)(prev_log_index + q)] = __ldcg(heap + ((off + 2 + 2 * (uint64_t)q) & c.p.rf_heap_mask));
+      c.log[2 * (size_t)(prev_log_index + q) + 1] = __ldcg(heap + ((off + 3 + 2 * (uint64_t)q) & c.p.rf_heap_mask));
     }
     r->log_size = prev_log_index + n_entries;
     if (r->commit_index < leader_commit) r->commit_index = leader_commit < r->log_size ? leader_commit : r->log_size;

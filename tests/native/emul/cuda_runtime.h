@@ -86,7 +86,11 @@ static inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned lo
 static inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) {
   return (unsigned long long)(((unsigned __int128)a * b) >> 64);
 }
-template <class T> static inline T __ldcg(const T* p) { return *(const volatile T*)p; }
+template <class T> static inline T __ldcg(const T* p) {
+  T v;
+  __builtin_memcpy(&v, (const void*)p, sizeof(T));   // a plain load (volatile does not copy structs)
+  return v;
+}
 template <class T, class U> static inline void __stcg(T* p, U v) { *(volatile T*)p = (T)v; }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }

@@ -171,3 +171,67 @@ def test_emulated_shards_gset_and_services(world, dist, mean):
         scenario)
     o = O.Sim(n, workload=O.W_GSET, **kw)
     check_against_oracle(o, scenario, ev, st, now, rnd)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_emulated_shards_txn_list_append(world):
+    # txn nodes on different shards race for the root held by the lin-kv service on yet another one
+    n = 5
+    kw = dict(latency_dist="uniform", latency_mean_ms=2, p_loss=0.05)
+
+    def scenario(s, body):
+        s.add_endpoint("lin-kv", O.KIND_SERVICE)
+        cs = [s.add_endpoint("c%d" % i, O.KIND_SIM_CLIENT) for i in range(5)]
+        rng = np.random.default_rng(31)
+        rows = np.zeros(240, dtype=O.OP_DTYPE)
+        for k in range(240):
+            r = rows[k]
+            r["time_ns"] = (k // 4) * 1_000_000
+            r["src"] = cs[k % 5]
+            r["dest"] = int(rng.integers(n))
+            b = r["body"]
+            b["type"] = O.T["txn"]
+            b["flags"] = O.F_MSG_ID | (O.F_APPENDS if rng.integers(3) else 0)
+            b["msg_id"] = k + 1
+            b["p1"] = 1000 + k
+        s.schedule(rows)
+        s.run(110_000_000)
+
+    ev, st, now, rnd = run_sharded_scenario(
+        world, n, dict(workload="txn-list-append", ring_cap=256, max_window=256, journal_cap_log2=18,
+                       max_endpoints=n + 16, **kw), scenario)
+    check_against_oracle(O.Sim(n, workload=O.W_TXN, **kw), scenario, ev, st, now, rnd)
+
+
+def test_emulated_shards_raft():
+    # a 5-node Raft cluster over 2 shards: votes and append_entries cross shards, followers copy
+    # entries out of the leader shard's payload heap
+    n = 5
+    kw = dict(latency_dist="constant", latency_mean_ms=1)
+
+    def scenario(s, body):
+        cs = [s.add_endpoint("c%d" % i, O.KIND_SIM_CLIENT) for i in range(3)]
+        for i in range(n):
+            s.send(cs[0], i, body("init", msg_id=900 + i))
+        rng = np.random.default_rng(41)
+        rows = np.zeros(90, dtype=O.OP_DTYPE)
+        for k in range(90):
+            r = rows[k]
+            r["time_ns"] = 4_300_000_000 + (k // 2) * 1_000_000
+            r["src"] = cs[k % 3]
+            r["dest"] = int(rng.integers(n))
+            b = r["body"]
+            b["flags"] = O.F_MSG_ID
+            b["msg_id"] = k + 1
+            b["p0"] = int(rng.integers(3))
+            kind = int(rng.integers(3))
+            b["type"] = (O.T["read"], O.T["write"], O.T["cas"])[kind]
+            b["p1"] = int(rng.integers(3)) | ((int(rng.integers(3)) << 32) if kind == 2 else 0)
+        s.schedule(rows)
+        s.run(4_600_000_000)
+
+    ev, st, now, rnd = run_sharded_scenario(
+        2, n, dict(workload="lin-kv", ring_cap=256, max_window=256, journal_cap_log2=18, max_endpoints=n + 16, **kw),
+        scenario)
+    check_against_oracle(O.Sim(n, workload=O.W_RAFT, **kw), scenario, ev, st, now, rnd)
+    assert st["servers"]["send-count"] > 30 and st["clients"]["recv-count"] > 150
