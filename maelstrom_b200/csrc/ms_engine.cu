@@ -28,7 +28,7 @@ void msk_launch_round(const msd::Params* p, int n_classes, const uint32_t* caps,
 void msk_set_bit(uint32_t* words, size_t word, uint32_t bit, cudaStream_t s);
 void msk_barrier(const msd::Params* p, cudaStream_t s);
 void msk_journal_expand(const msd::Params* p, uint64_t r0, uint32_t n_rounds, uint64_t first, uint64_t count,
-                        void* out_ev, void* out_body, cudaStream_t s);
+                        void* out_ev, void* out_body, int n_sms, cudaStream_t s);
 }
 
 static thread_local std::string g_err;
@@ -335,7 +335,7 @@ struct ms_sim {
         CK(cudaMemsetAsync(stage_ev, 0xFF, piece * 32, stream));
         if (want_body) CK(cudaMemsetAsync(stage_body, 0xFF, piece * 32, stream));
       }
-      msk_journal_expand(&P, r0, (uint32_t)(r1 - r0), first, piece, stage_ev, want_body ? stage_body : nullptr, stream);
+      msk_journal_expand(&P, r0, (uint32_t)(r1 - r0), first, piece, stage_ev, want_body ? stage_body : nullptr, n_sms, stream);
       CK(cudaStreamSynchronize(stream));
       CK(cudaMemcpy(ev + done, stage_ev, piece * 32, cudaMemcpyDeviceToHost));
       if (want_body) CK(cudaMemcpy(bodies + done, stage_body, piece * 32, cudaMemcpyDeviceToHost));

@@ -1838,10 +1838,10 @@ void msk_launch_round(const msd::Params* p, int n_classes, const uint32_t* caps,
 void msk_barrier(const msd::Params* p, cudaStream_t s) { MS_LAUNCH(msd::k_barrier, 1, 32, 0, s, *p); }
 
 void msk_journal_expand(const msd::Params* p, uint64_t r0, uint32_t n_rounds, uint64_t first, uint64_t count,
-                        void* out_ev, void* out_body, cudaStream_t s) {
+                        void* out_ev, void* out_body, int n_sms, cudaStream_t s) {
   const uint64_t chunks = (uint64_t)n_rounds * p->t_max;
   uint64_t blocks = (chunks * 32 + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > (uint64_t)n_sms * 16) blocks = (uint64_t)n_sms * 16;   // 2368 on a B200
   if (blocks < 1) blocks = 1;
   MS_LAUNCH(msd::k_journal_expand, (unsigned)blocks, 256, 0, s, *p, r0, n_rounds, first, count, (uint4*)out_ev,
             (uint4*)out_body);

@@ -286,7 +286,7 @@ cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
   memset(p, 0, sizeof(*p));
   strcpy(p->name, "simt-emulator");
   const char* e = getenv("MS_EMUL_SMS");
-  p->multiProcessorCount = e ? atoi(e) : 2;
+  p->multiProcessorCount = e ? atoi(e) : 1;
   p->sharedMemPerBlockOptin = 227 << 10;
   p->totalGlobalMem = (size_t)8 << 30;
   p->major = 10;
