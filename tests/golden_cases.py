@@ -61,16 +61,89 @@ def _gset_five_nodes(s, body):
     s.run(75_000_000)
 
 
+def _services_mixed(s, body):
+    sv = {name: s.add_endpoint(name, O.KIND_SERVICE) for name in ("lin-kv", "seq-kv", "lww-kv", "lin-tso")}
+    cs = [s.add_endpoint("c%d" % i, O.KIND_SIM_CLIENT) for i in range(3)]
+    rng = np.random.default_rng(77)
+    rows = np.zeros(150, dtype=O.OP_DTYPE)
+    names = list(sv)
+    for k in range(150):
+        r = rows[k]
+        r["time_ns"] = (k // 10) * 1_000_000
+        r["src"] = cs[k % 3]
+        name = names[int(rng.integers(4))]
+        r["dest"] = sv[name]
+        b = r["body"]
+        b["flags"] = O.F_MSG_ID
+        b["msg_id"] = k + 1
+        if name == "lin-tso":
+            b["type"] = O.T["ts"]
+            continue
+        b["p0"] = int(rng.integers(4))
+        kind = int(rng.integers(3))
+        b["type"] = (O.T["read"], O.T["write"], O.T["cas"])[kind]
+        b["p1"] = int(rng.integers(4)) | ((int(rng.integers(4)) << 32) if kind == 2 else 0)
+        if kind == 2 and rng.integers(2):
+            b["flags"] |= O.F_CREATE
+    s.schedule(rows)
+    s.run(20_000_000)
+
+
+def _txn_three_nodes(s, body):
+    s.add_endpoint("lin-kv", O.KIND_SERVICE)
+    cs = [s.add_endpoint("c%d" % i, O.KIND_SIM_CLIENT) for i in range(3)]
+    rows = np.zeros(60, dtype=O.OP_DTYPE)
+    for k in range(60):
+        r = rows[k]
+        r["time_ns"] = (k // 3) * 1_000_000
+        r["src"] = cs[k % 3]
+        r["dest"] = (k * 7) % 3
+        b = r["body"]
+        b["type"] = O.T["txn"]
+        b["flags"] = O.F_MSG_ID | (O.F_APPENDS if k % 4 else 0)
+        b["msg_id"] = k + 1
+        b["p1"] = 500 + k
+    s.schedule(rows)
+    s.run(40_000_000)
+
+
+def _raft_three_nodes(s, body):
+    cs = [s.add_endpoint("c%d" % i, O.KIND_SIM_CLIENT) for i in range(2)]
+    for i in range(3):
+        s.send(cs[0], i, body("init", msg_id=100 + i))
+    rows = np.zeros(24, dtype=O.OP_DTYPE)
+    for k in range(24):
+        r = rows[k]
+        r["time_ns"] = 4_100_000_000 + (k // 2) * 1_000_000
+        r["src"] = cs[k % 2]
+        r["dest"] = k % 3
+        b = r["body"]
+        b["flags"] = O.F_MSG_ID
+        b["msg_id"] = k + 1
+        b["p0"] = k % 2
+        b["type"] = (O.T["write"], O.T["read"], O.T["cas"])[k % 3]
+        b["p1"] = (k % 5) | (((k + 1) % 5) << 32 if k % 3 == 2 else 0)
+    s.schedule(rows)
+    s.run(4_250_000_000)
+
+
 CASES = {
     "flood_grid25": (dict(n_nodes=25, workload="broadcast", topology="grid", n_values=8), _flood_grid25),
     "echo_12_ops": (dict(n_nodes=1, workload="echo"), _echo_12_ops),
     "latency_loss_partition": (dict(n_nodes=36, workload="broadcast", topology="grid", n_values=128,
                                     latency_dist="exponential", latency_mean_ms=4), _latency_loss_partition),
     "gset_five_nodes": (dict(n_nodes=5, workload="g-set", n_values=256, gset_interval_ms=30), _gset_five_nodes),
+    "services_mixed": (dict(n_nodes=2, workload="echo", latency_dist="uniform", latency_mean_ms=2), _services_mixed),
+    "txn_three_nodes": (dict(n_nodes=3, workload="txn-list-append", latency_dist="constant", latency_mean_ms=1),
+                        _txn_three_nodes),
+    "raft_three_nodes": (dict(n_nodes=3, workload="lin-kv"), _raft_three_nodes),
 }
+# cases checked against the engine by tests/test_golden_fixtures.py; the others by their workload's test file
+CORE_CASES = ("flood_grid25", "echo_12_ops", "latency_loss_partition")
 ENGINE_SIZING = dict(ring_cap=256, max_window=256, journal_cap_log2=18, max_endpoints=64,
                      calendar_slots=1024, calendar_cap=2048)
-W = {"echo": O.W_ECHO, "broadcast": O.W_BROADCAST, "g-set": O.W_GSET}
+W = {"echo": O.W_ECHO, "broadcast": O.W_BROADCAST, "g-set": O.W_GSET, "lin-kv": O.W_RAFT,
+     "txn-list-append": O.W_TXN}
 
 
 def make_oracle(name):
@@ -101,3 +174,15 @@ def digest(events, bodies, stats, now, rnd):
         "now_ns": int(now),
         "rounds": int(rnd),
     }
+
+
+def check_engine_against_fixture(name):
+    """Run case `name` on the engine (whatever backend is active) and compare with journals.json."""
+    import json
+    import os
+    import maelstrom_b200 as mb
+    want = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "journals.json")))
+    g = make_engine(name)
+    CASES[name][1](g, mb.body)
+    ev, bd = g.drain()
+    assert digest(ev, bd, g.stats(), g.now, g.round) == want[name]

@@ -88,8 +88,8 @@ def test_oracle_reproduces_committed_journals(name):
     assert G.digest(ev, bd, o.stats(), o.now, o.round) == JOURNALS[name]
 
 
-# (the g-set case is checked in tests/test_workload_gset.py with the rest of that workload)
-@pytest.mark.parametrize("name", sorted(n for n in G.CASES if not n.startswith("gset")))
+# (the cases of the later workloads are checked in their tests/test_workload_*.py)
+@pytest.mark.parametrize("name", sorted(G.CORE_CASES))
 def test_engine_reproduces_committed_journals(name, engine_backend):
     import maelstrom_b200 as mb
     g = G.make_engine(name)

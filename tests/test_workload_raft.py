@@ -152,3 +152,9 @@ def test_open_loop_clients_loss_and_services():
     kinds = set(int(t) for t in bd["type"])
     assert {O.T["append_entries"], O.T["append_entries_res"], O.T["request_vote"], O.T["ts_ok"],
             O.T["read_ok"], O.T["write_ok"]} <= kinds
+
+
+def test_committed_golden_journal():
+    # tests/golden/journals.json["raft_three_nodes"], generated from the oracle (tests/golden/make_golden.py)
+    import golden_cases as G
+    G.check_engine_against_fixture("raft_three_nodes")

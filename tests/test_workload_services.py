@@ -153,3 +153,9 @@ def test_mirror_rpcs_read_like_the_reference():
     with pytest.raises(C.RPCError) as e:
         c.rpc("seq-kv", {"type": "read", "key": 9})
     assert e.value.code == 20
+
+
+def test_committed_golden_journal():
+    # tests/golden/journals.json["services_mixed"], generated from the oracle (tests/golden/make_golden.py)
+    import golden_cases as G
+    G.check_engine_against_fixture("services_mixed")

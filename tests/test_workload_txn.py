@@ -113,3 +113,9 @@ def test_mirror_replays_apply_txn():
     assert c.rpc("n1", {"type": "txn", "txn": [["append", 1, 11], ["append", 2, 5]]})["txn"] == [["append", 1, 11], ["append", 2, 5]]
     assert c.rpc("n0", {"type": "txn", "txn": [["r", 1, None], ["r", 2, None], ["r", 3, None]]})["txn"] == \
         [["r", 1, [10, 11]], ["r", 2, [5]], ["r", 3, None]]
+
+
+def test_committed_golden_journal():
+    # tests/golden/journals.json["txn_three_nodes"], generated from the oracle (tests/golden/make_golden.py)
+    import golden_cases as G
+    G.check_engine_against_fixture("txn_three_nodes")
