@@ -146,3 +146,64 @@ def test_random_scenario(seed):
         rg, ro = both(g, o, scenario)
         assert rg == ro
         assert_same_journal(g, o)
+
+
+def heavy_seeds():
+    spec = os.environ.get("MS_FUZZ_HEAVY_SEEDS", "0:2")
+    a, b = (int(x) for x in spec.split(":"))
+    return list(range(a, b))
+
+
+@pytest.mark.parametrize("seed", heavy_seeds())
+def test_random_heavy_broadcast(seed):
+    # the measured path under load: hundreds of values per tick, windows spanning the size classes,
+    # sender-block ordering with its verify / bitonic fallbacks, per-neighbor block claims
+    rng = np.random.default_rng(5000 + seed)
+    n = int(rng.integers(30, 260))
+    topo = ("grid", "grid", "line", "tree2", "tree4")[int(rng.integers(5))]
+    mean = int(rng.choice([0, 0, 1, 2]))
+    n_clients = int(rng.integers(1, 6))
+    ticks = int(rng.integers(2, 6))
+    per_tick = int(rng.integers(20, 400))
+    max_window = int(rng.choice([1024, 2048, 4096]))
+    if rng.integers(3) == 0:                                  # burst: few nodes, windows of thousands (classes 2-3)
+        n, per_tick, ticks, max_window = int(rng.integers(9, 50)), int(rng.integers(800, 3000)), 2, 4096
+    kw = dict(topology=topo, latency_dist="constant", latency_mean_ms=mean, n_values=ticks * per_tick + 64,
+              p_loss=float(rng.choice([0.0, 0.0, 0.02])), seed=int(rng.integers(1 << 40)))
+    sizing = dict(max_endpoints=n + 16, ring_cap=8192, max_window=max_window, journal_cap_log2=21,
+                  calendar_slots=64, calendar_cap=1 << 16, journal_level=int(rng.choice([1, 2])))
+
+    def scenario(s, body):
+        clients = [s.add_endpoint("c%d" % i, O.KIND_SIM_CLIENT) for i in range(n_clients)]
+        r2 = np.random.default_rng(seed)
+        rows = np.zeros(ticks * per_tick, dtype=O.OP_DTYPE)
+        hot = int(r2.integers(n))
+        for k in range(len(rows)):
+            r = rows[k]
+            r["time_ns"] = (k // per_tick) * 1_000_000
+            r["src"] = clients[int(r2.integers(n_clients))]
+            r["dest"] = hot if r2.integers(4) == 0 else int(r2.integers(n))     # a hot node: big windows
+            b = r["body"]
+            b["type"] = O.T["broadcast"]
+            b["flags"] = O.F_MSG_ID
+            b["msg_id"] = k + 1
+            b["p0"] = k if r2.integers(10) else int(r2.integers(max(k, 1)))       # some duplicates
+        s.schedule(rows)
+        s.run((ticks + 2) * 1_000_000)
+        if mean:
+            s.run((ticks + 2 + 600 * mean) * 1_000_000)
+
+    with emul_lib.use():
+        g, o = make_pair(n, workload="broadcast", **kw, **sizing)
+        both(g, o, scenario)
+        if sizing["journal_level"] == 2:
+            assert_same_journal(g, o)
+        else:
+            ev_g, _ = g.drain(bodies=False)
+            ev_o, _ = o.journal()
+            assert len(ev_g) == len(ev_o)
+            for f in ("event_id", "time_ns", "msg_id", "src", "dest"):
+                assert np.array_equal(ev_g[f], ev_o[f]), f
+            assert g.stats() == o.stats()
+        c = g.counters()
+        assert c["max_window"] <= max_window
