@@ -207,3 +207,48 @@ def test_random_heavy_broadcast(seed):
             assert g.stats() == o.stats()
         c = g.counters()
         assert c["max_window"] <= max_window
+
+
+def sharded_seeds():
+    spec = os.environ.get("MS_FUZZ_SHARDED_SEEDS", "0:1")
+    a, b = (int(x) for x in spec.split(":"))
+    return list(range(a, b))
+
+
+@pytest.mark.parametrize("seed", sharded_seeds())
+def test_random_sharded(seed):
+    # 2-4 emulated shards (one host thread each) against the oracle: owner map, peer-ring claims,
+    # barriers, k_commit over all shards' tables, workload state read across shards
+    from test_emul_sharded import check_against_oracle, run_sharded_scenario
+    rng = np.random.default_rng(9000 + seed)
+    world = int(rng.integers(2, 5))
+    workload = ("broadcast", "broadcast", "g-set", "txn-list-append")[int(rng.integers(4))]
+    n = int(rng.integers(world, 60))
+    mean = int(rng.choice([0, 1, 3]))
+    dist = "constant" if mean == 0 else ("constant", "uniform")[int(rng.integers(2))]
+    kw = dict(topology=("grid", "line", "tree3")[int(rng.integers(3))], latency_dist=dist, latency_mean_ms=mean,
+              n_values=1024, p_loss=float(rng.choice([0.0, 0.03])), seed=int(rng.integers(1 << 40)))
+    if workload == "g-set":
+        kw["gset_interval_ms"] = int(rng.integers(4, 12))
+    n_clients = int(rng.integers(1, 5))
+    ticks, per_tick = int(rng.integers(3, 10)), int(rng.integers(5, 60))
+
+    def scenario(s, body):
+        services = {}
+        if workload == "txn-list-append" or rng_services:
+            for name in ("lin-kv", "seq-kv", "lin-tso"):
+                services[name] = s.add_endpoint(name, O.KIND_SERVICE)
+        clients = [s.add_endpoint("c%d" % i, O.KIND_SIM_CLIENT) for i in range(n_clients)]
+        if workload == "g-set":
+            for i in range(n):
+                s.send(clients[0], i, body("init", msg_id=9000 + i))
+        r2 = np.random.default_rng(seed)
+        s.schedule(random_ops(r2, n, clients, services, workload, 0, ticks, per_tick, [0] * n_clients))
+        s.run((ticks + 30 + 12 * mean) * 1_000_000)
+
+    rng_services = bool(rng.integers(2))
+    wl = {"broadcast": O.W_BROADCAST, "g-set": O.W_GSET, "txn-list-append": O.W_TXN}[workload]
+    ev, st, now, rnd = run_sharded_scenario(
+        world, n, dict(workload=workload, ring_cap=2048, max_window=1024, journal_cap_log2=20, max_endpoints=n + 24,
+                       calendar_slots=256, calendar_cap=8192, **kw), scenario)
+    check_against_oracle(O.Sim(n, workload=wl, **kw), scenario, ev, st, now, rnd)
