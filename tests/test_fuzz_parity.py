@@ -252,3 +252,62 @@ def test_random_sharded(seed):
         world, n, dict(workload=workload, ring_cap=2048, max_window=1024, journal_cap_log2=20, max_endpoints=n + 24,
                        calendar_slots=256, calendar_cap=8192, **kw), scenario)
     check_against_oracle(O.Sim(n, workload=wl, **kw), scenario, ev, st, now, rnd)
+
+
+def raft_seeds():
+    spec = os.environ.get("MS_FUZZ_RAFT_SEEDS", "0:0")        # slow (seconds of virtual time): off by default
+    a, b = (int(x) for x in spec.split(":"))
+    return list(range(a, b))
+
+
+@pytest.mark.parametrize("seed", raft_seeds())
+def test_random_raft(seed):
+    # elections under loss / latency / partitions that come and go, client traffic through every node
+    rng = np.random.default_rng(7000 + seed)
+    n = int(rng.integers(2, 8))
+    mean = int(rng.choice([0, 1, 4]))
+    kw = dict(latency_dist="constant" if mean == 0 else ("constant", "exponential")[int(rng.integers(2))],
+              latency_mean_ms=mean, p_loss=float(rng.choice([0.0, 0.02, 0.15])), seed=int(rng.integers(1 << 40)))
+    n_clients = 3
+    phases = [(int(rng.integers(4)), int(rng.integers(300, 2600))) for _ in range(int(rng.integers(3, 6)))]
+    masks = rng.integers(1, 1 << 16, size=len(phases))
+
+    def scenario(s, body):
+        clients = [s.add_endpoint("c%d" % i, O.KIND_SIM_CLIENT) for i in range(n_clients)]
+        for i in range(n):
+            s.send(clients[0], i, body("init", msg_id=9000 + i))
+        r2 = np.random.default_rng(seed)
+        t_ms, mid = 0, 0
+        for (fault, dur), mask in zip(phases, masks):
+            if fault == 1:
+                s.partition([(int(mask) >> i) & 1 for i in range(n)])
+            elif fault == 2:
+                s.heal()
+            elif fault == 3 and n > 1:
+                s.drop(int(mask) % n, (int(mask) >> 4) % n)
+            rows = np.zeros(int(r2.integers(0, 40)), dtype=O.OP_DTYPE)
+            for k in range(len(rows)):
+                r = rows[k]
+                mid += 1
+                r["time_ns"] = (t_ms + int(r2.integers(dur))) * 1_000_000
+                r["src"] = clients[int(r2.integers(n_clients))]
+                r["dest"] = int(r2.integers(n))
+                b = r["body"]
+                b["flags"] = O.F_MSG_ID
+                b["msg_id"] = mid
+                b["p0"] = int(r2.integers(4))
+                kind = int(r2.integers(3))
+                b["type"] = (O.T["read"], O.T["write"], O.T["cas"])[kind]
+                b["p1"] = int(r2.integers(4)) | ((int(r2.integers(4)) << 32) if kind == 2 else 0)
+            rows = rows[np.argsort(rows["time_ns"], kind="stable")]
+            s.schedule(rows)
+            t_ms += dur
+            s.run(t_ms * 1_000_000)
+        return [s.raft_state(i) for i in range(n)], s.client_replies()
+
+    with emul_lib.use():
+        g, o = make_pair(n, workload="lin-kv", max_endpoints=n + 8, ring_cap=1024, max_window=512,
+                         journal_cap_log2=19, calendar_slots=256, calendar_cap=4096, **kw)
+        rg, ro = both(g, o, scenario)
+        assert rg == ro
+        assert_same_journal(g, o)
