@@ -887,7 +887,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
   __shared__ uint32_t s_nbbase[MAXNB];        // ring position claimed for this CTA's gossip to neighbor j
   __shared__ uint32_t s_nbr[MAXNB];           // this node's neighbor list (topology order)
 
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
   if (tid == 0) s_np = *p.np;
   __syncthreads();
   const NetParams np = s_np;
