@@ -241,7 +241,33 @@ static void run_cta(Sched* s, unsigned nt) {
   }
 }
 
+// MS_EMUL_PROFILE=1: wall time per (grid, block) launch shape, printed at exit
+struct ProfRow { unsigned grid, block; uint64_t n; double sec; };
+static ProfRow g_prof[64];
+static int g_nprof = 0;
+static void prof_dump() {
+  for (int i = 0; i < g_nprof; i++)
+    fprintf(stderr, "simt profile: grid %5u block %4u launches %8llu total %.3f s (%.1f us each)\n", g_prof[i].grid,
+            g_prof[i].block, (unsigned long long)g_prof[i].n, g_prof[i].sec, 1e6 * g_prof[i].sec / (double)g_prof[i].n);
+}
+static void launch_impl(unsigned grid, unsigned block, size_t dyn, const std::function<void()>& body);
 void launch(unsigned grid, unsigned block, size_t dyn, const std::function<void()>& body) {
+  static const bool profile = getenv("MS_EMUL_PROFILE") != nullptr;
+  if (!profile) { launch_impl(grid, block, dyn, body); return; }
+  const auto t0 = std::chrono::steady_clock::now();
+  launch_impl(grid, block, dyn, body);
+  const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  int i = 0;
+  while (i < g_nprof && !(g_prof[i].grid == grid && g_prof[i].block == block)) i++;
+  if (i == g_nprof) {
+    if (g_nprof == 64) return;
+    if (g_nprof == 0) atexit(prof_dump);
+    g_prof[g_nprof++] = ProfRow{grid, block, 0, 0.0};
+  }
+  g_prof[i].n++;
+  g_prof[i].sec += dt;
+}
+static void launch_impl(unsigned grid, unsigned block, size_t dyn, const std::function<void()>& body) {
   Sched* s = sched();
   if (s->body) die("nested kernel launch");
   if (block == 0 || block > kMaxThreads) die("bad block size");
