@@ -284,23 +284,26 @@ __device__ void rf_actions(RaftCtx& c) {
   if (r->state == RAFT_LEADER && r->step_down_deadline < c.now) rf_become_follower(c);   // :371-376
   {                                                                                       // replicate_log, :387-441
     const int64_t elapsed = c.now - r->last_replication;
-    bool replicated = false;
+    bool replicated = false, aborted = false;
+    const uint32_t first_rpc = r->next_msg_id;          // RPCs of this pass: ids first_rpc .. next_msg_id - 1
+    uint32_t last_node = 0, last_n = 0;
+    int32_t last_ni = 0;
     if (r->state == RAFT_LEADER && kMinReplicationNs < elapsed) {
       const int32_t* next = c.p.rf_next + (size_t)c.e * N;
       for (uint32_t n = 0; n < N; n++) {
         if (n == c.e) continue;
         const int32_t ni = next[n];
-        if (ni <= 0) return;                                                              // from_index raises (:147-148): the
+        if (ni <= 0) { aborted = true; break; }                                           // from_index raises (:147-148): the
                                                                                           // iteration ends, later ones raise again
         const int32_t n_entries = (int32_t)r->log_size - ni + 1 > 0 ? (int32_t)r->log_size - ni + 1 : 0;
         if (0 < n_entries || kHeartbeatNs < elapsed) {
           // log.get(ni - 1) = entries[ni - 2]; Python's entries[-1] when ni == 1 is the last entry
           const int32_t pi = ni - 2;
-          if (pi >= (int32_t)r->log_size) return;                                         // IndexError
+          if (pi >= (int32_t)r->log_size) { aborted = true; break; }                      // IndexError
           const uint32_t prev_term = pi < 0 ? rf_log_term(c, r->log_size) : rf_log_term(c, (uint32_t)pi + 1);
           const uint32_t k = ++r->appends;
           const uint64_t words = 2 + 2 * (uint64_t)n_entries;
-          if (words > c.p.rf_heap_mask) { latch_error(c.st, E_RAFT_CAPACITY, c.e); return; }
+          if (words > c.p.rf_heap_mask) { latch_error(c.st, E_RAFT_CAPACITY, c.e); aborted = true; break; }
           const uint64_t off = atomicAdd(c.p.rf_heap_cursor, (unsigned long long)words);
           c.p.rf_heap[off & c.p.rf_heap_mask] = make_uint4(c.e, k, 0u, 0u);
           c.p.rf_heap[(off + 1) & c.p.rf_heap_mask] = make_uint4((uint32_t)(ni - 1), prev_term, r->commit_index, (uint32_t)n_entries);
@@ -311,10 +314,22 @@ __device__ void rf_actions(RaftCtx& c) {
           c.p.rf_ext_off[(size_t)c.e * kRaftExt + k % kRaftExt] = off;
           c.p.rf_ext_tag[(size_t)c.e * kRaftExt + k % kRaftExt] = k;
           rf_rpc(c, n, MS_T_APPEND_ENTRIES, r->term, k, 2u, n, ni, (uint32_t)n_entries);
+          last_node = n; last_ni = ni; last_n = (uint32_t)n_entries;
           replicated = true;
         }
       }
     }
+    // Python closures bind late: `handler` reads _ni / _entries / _node (raft.py:408-426) from the
+    // frame of this replicate_log call when the reply arrives, i.e. the values of the LAST node the
+    // pass sent to, for every RPC of the pass (pinned by tests/test_raft_reference.py)
+    for (uint32_t id = first_rpc; id != r->next_msg_id; id++) {
+      uint4* slot = c.cb + 2 * (size_t)(id % kRaftCallbacks);
+      if (slot[0].y == 2u && slot[0].x == id) {
+        slot[0].w = last_node;
+        slot[1] = make_uint4((uint32_t)last_ni, last_n, 0u, 0u);
+      }
+    }
+    if (aborted) return;
     if (replicated) r->last_replication = c.now;
   }
   if (r->election_deadline < c.now) {                                                     // election, :358-367

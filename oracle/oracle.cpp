@@ -746,6 +746,8 @@ struct or_sim {
     {                                                                                      // replicate_log, :387-441
       const int64_t elapsed = now - r.last_replication;
       bool replicated = false, aborted = false;
+      const uint32_t first_rpc = r.next_msg_id;            // RPCs of this pass: ids first_rpc .. next_msg_id - 1
+      RaftCb last;                                          // what the pass's closures end up seeing (see below)
       if (r.state == RAFT_LEADER && kMinReplicationNs < elapsed) {
         for (uint32_t n = 0; n < cfg.n_nodes && !aborted; n++) {
           if (n == e) continue;
@@ -767,9 +769,18 @@ struct or_sim {
             m.type = OR_T_APPEND_ENTRIES; m.p0 = r.term; m.p1 = k;
             RaftCb cb; cb.kind = 2; cb.term = r.term; cb.node = n; cb.ni = ni; cb.n_entries = (uint32_t)n_entries;
             raft_rpc(e, n, m, cb, out);
+            last = cb;
             replicated = true;
           }
         }
+      }
+      // Python closures bind late: `handler` reads _ni / _entries / _node (raft.py:408-426) from the
+      // frame of this replicate_log call when the reply arrives, i.e. the values of the LAST node the
+      // pass sent to, for every RPC of the pass.  (A follower that is not last in other_nodes() only
+      // advances in a pass where it alone has something to receive.)
+      for (uint32_t id = first_rpc; id != r.next_msg_id; id++) {
+        RaftCb& slot = r.callbacks[id % kRaftCallbacks];
+        if (slot.kind == 2 && slot.msg_id == id) { slot.node = last.node; slot.ni = last.ni; slot.n_entries = last.n_entries; }
       }
       // an exception inside replicate_log ends this iteration of the main loop; every later
       // iteration raises again before it gets to the actions below (raft.py:577-588)

@@ -1,0 +1,143 @@
+"""Pins the oracle's Raft restatement to the reference's own code.  tests/golden/
+raft_reference_trace.json is every message sent by a 3-node cluster of the UNMODIFIED
+/root/reference/demo/python/raft.py, executed by tests/golden/raft_reference_harness.py under the
+schedule of DESIGN.md section 2.8 (virtual clock, Philox draws).  The oracle, given the same
+client operations, must send the same messages with the same ids at the same times, and end in
+the same node states.  Where /root/reference is mounted the fixture is also regenerated and
+compared, so it cannot drift from the reference."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+FIXTURE = os.path.join(HERE, "golden", "raft_reference_trace.json")
+
+
+def canonical_from_oracle(sim, ev, bd):
+    names = {v: k for k, v in O.T.items()}
+    out = []
+    for e, b in zip(ev, bd):
+        if int(e["event_id"]) >> 63:
+            continue                                           # :recv events
+        t = names[int(b["type"])]
+        p0, p1, mid, irt = int(b["p0"]), int(b["p1"]), int(b["msg_id"]), int(b["in_reply_to"])
+        if t == "request_vote":
+            f = (p0, p1 & 0xFFFFFFFF, p1 >> 32, mid)
+        elif t in ("request_vote_res", "append_entries_res"):
+            f = (p0, p1, irt)
+        elif t == "append_entries":
+            a = np.zeros(4, dtype=np.uint32)
+            assert sim.L.or_raft_append(sim.h, int(e["src"]), p1, a.ctypes.data) == 1
+            f = (p0, int(a[0]), int(a[1]), int(a[3]), int(a[2]), mid)
+        elif t == "init":
+            f = (mid,)
+        elif t in ("init_ok", "write_ok", "cas_ok"):
+            f = (irt,)
+        elif t == "read_ok":
+            f = (p1, irt)
+        elif t == "error":
+            f = (p0, irt)
+        elif t == "read":
+            f = (p0, mid)
+        elif t == "write":
+            f = (p0, p1, mid)
+        elif t == "cas":
+            f = (p0, p1 & 0xFFFFFFFF, p1 >> 32, mid)
+        else:
+            raise AssertionError(t)
+        out.append((int(e["msg_id"]), int(e["time_ns"]) // 1_000_000, int(e["src"]), int(e["dest"]), t) + f)
+    return out
+
+
+def run_oracle(fix, ops, events=()):
+    n = fix["n"]
+    s = O.Sim(n, workload=O.W_RAFT, seed=fix["seed"])
+    clients = [s.add_endpoint("c%d" % i) for i in range(n)]
+    rows = np.zeros(len(ops), dtype=O.OP_DTYPE)
+    for r, (t_ms, src, dest, body) in zip(rows, ops):
+        r["time_ns"] = t_ms * 1_000_000
+        r["src"] = clients[int(src[1:])]
+        r["dest"] = int(dest[1:])
+        b = r["body"]
+        b["type"] = O.T[body["type"]]
+        b["flags"] = O.F_MSG_ID
+        b["msg_id"] = body["msg_id"]
+        if "key" in body:
+            b["p0"] = body["key"]
+            if body["type"] == "write":
+                b["p1"] = body["value"]
+            elif body["type"] == "cas":
+                b["p1"] = (body["from"] & 0xFFFFFFFF) | (body["to"] << 32)
+    s.schedule(rows)
+    for t_ms, what in events:
+        s.run(t_ms * 1_000_000)
+        if what == "heal":
+            s.heal()
+        else:                                                  # cut whoever leads now off from the other nodes
+            lead = [i for i in range(n) if s.raft_state(i)["state"] == 3]
+            s.partition([1 if i in lead[:1] else 0 for i in range(n)])
+    s.run(fix["until_ms"] * 1_000_000)
+    return s
+
+
+def check(fix, s):
+    n = fix["n"]
+    ev, bd = s.journal()
+    want = [tuple(m) for m in fix["messages"]]
+    got = canonical_from_oracle(s, ev, bd)
+    for g, w in zip(got, want):
+        assert g == w, (g, w)
+    assert len(got) == len(want)
+    assert s.round == fix["rounds"]
+    state_code = {"nascent": 0, "follower": 1, "candidate": 2, "leader": 3}
+    for i, f in enumerate(fix["final"]):
+        st = s.raft_state(i)
+        assert (st["state"], st["term"], st["commit_index"], st["log_size"], st["kv_size"]) == \
+            (state_code[f["state"]], f["term"], f["commit_index"], f["log_size"], len(f["kv"]))
+    return want
+
+
+def test_oracle_sends_what_the_reference_raft_sends():
+    import raft_reference_harness as H
+    fix = json.load(open(FIXTURE))
+    ops, until = H.scenario(None, fix["n"])
+    assert until == fix["until_ms"]
+    want = check(fix, run_oracle(fix, ops))
+    types = {w[4] for w in want}
+    assert {"request_vote", "request_vote_res", "append_entries", "append_entries_res", "read_ok", "write_ok",
+            "cas_ok", "error", "init_ok"} <= types                          # the trace exercises every handler
+    # ...and the proxy path: a follower re-sends the client's message, src unchanged, to the leader
+    assert sum(1 for w in want if w[4] in ("read", "write", "cas")) > 24
+
+
+def test_oracle_matches_the_reference_through_a_partition():
+    # 5 nodes, the first leader isolated for 5 s: step-down, a second election, the old leader's
+    # uncommitted entries truncated after the heal, late-bound closures slowing its catch-up
+    import raft_reference_harness as H
+    fix = json.load(open(FIXTURE.replace(".json", "_partition.json")))
+    ops, events, until = H.partition_scenario(fix["n"])
+    assert until == fix["until_ms"] and [list(e) for e in events] == fix["events"]
+    want = check(fix, run_oracle(fix, ops, events))
+    terms = {w[5] for w in want if w[4] == "request_vote"}
+    assert len(terms) >= 2                                                   # more than one election
+    assert any(w[4] == "append_entries_res" and w[6] == 0 for w in want)     # a follower rejected an append
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/demo/python/raft.py"),
+                    reason="the reference tree is only mounted in the build container")
+def test_fixtures_are_what_the_reference_produces():
+    import raft_reference_harness as H
+    fix = json.load(open(FIXTURE))
+    ops, until = H.scenario(None, fix["n"])
+    c = H.run(fix["n"], ops, [], until)
+    assert [H.canonical(m, fix["n"]) for m in c.trace] == fix["messages"] and c.round == fix["rounds"]
+    fix = json.load(open(FIXTURE.replace(".json", "_partition.json")))
+    ops, events, until = H.partition_scenario(fix["n"])
+    c = H.run(fix["n"], ops, events, until)
+    assert [H.canonical(m, fix["n"]) for m in c.trace] == fix["messages"] and c.round == fix["rounds"]
