@@ -6,15 +6,19 @@
  * net/journal.clj:53,225-239, workload/broadcast.clj:40-178) together with the
  * canonical node programs (demo/ruby/echo.rb:28-40, the tutorial broadcast
  * node doc/03-broadcast/01-broadcast.md:527-544 + 02-performance.md:61-67,
- * demo/ruby/g_set.rb:13-39), under the deterministic refinement recorded in
- * DESIGN.md section 2 ("the spec").
+ * demo/ruby/g_set.rb:13-39, demo/python/raft.py, demo/clojure/single_key_txn.clj)
+ * and services (src/maelstrom/service.clj), under the deterministic refinement
+ * recorded in DESIGN.md section 2 ("the spec").
  *
  * PARITY STATUS: the reference hot path is nondeterministic and has no tests
  * (SURVEY.md fact 2/3), and no JVM exists here, so the *delivery order* part
  * of this oracle is "parity unpinned": it is pinned only by the source text of
  * net.clj and by the doc/test known-answer vectors listed in
  * tests/test_oracle_golden.py (topologies, flood counts, echo counts, error
- * codes, Philox KAT vectors).
+ * codes, Philox KAT vectors).  Pinned harder: the services, to the properties of
+ * the reference's own test/maelstrom/service_test.clj (tests/test_oracle_services.py);
+ * the Raft node, to message traces of the reference's demo/python/raft.py executed
+ * here unmodified (tests/test_raft_reference.py, tests/golden/raft_reference_harness.py).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load this library.  The product
