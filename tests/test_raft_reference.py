@@ -141,3 +141,93 @@ def test_fixtures_are_what_the_reference_produces():
     ops, events, until = H.partition_scenario(fix["n"])
     c = H.run(fix["n"], ops, events, until)
     assert [H.canonical(m, fix["n"]) for m in c.trace] == fix["messages"] and c.round == fix["rounds"]
+
+
+def fuzz_seeds():
+    a, b = (int(x) for x in os.environ.get("MS_FUZZ_RAFTREF_SEEDS", "0:2").split(":"))
+    return list(range(a, b))
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/demo/python/raft.py"),
+                    reason="the reference tree is only mounted in the build container")
+@pytest.mark.parametrize("seed", fuzz_seeds())
+def test_random_scenarios_against_the_executed_reference(seed):
+    # random cluster size, client traffic and partitions (arbitrary sides, repeated, healed or not):
+    # the reference's raft.py under the harness and the oracle must send the same messages
+    import raft_reference_harness as H
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(1, 6))
+    ops = [(0, "c%d" % i, "n%d" % i, {"type": "init", "msg_id": 1, "node_id": "n%d" % i,
+                                      "node_ids": ["n%d" % k for k in range(n)]}) for i in range(n)]
+    until = int(rng.integers(5000, 12000))
+    k = 1
+    times = sorted(int(t) for t in rng.integers(0, until, size=int(rng.integers(5, 60))))
+    for t in times:
+        k += 1
+        dest = int(rng.integers(n))
+        kind = int(rng.integers(4))
+        body = {"msg_id": k, "key": int(rng.integers(3))}
+        if kind == 0:
+            body.update(type="read")
+        elif kind == 1:
+            body.update(type="write", value=int(rng.integers(5)))
+        elif kind == 2:
+            body.update({"type": "cas", "from": int(rng.integers(5)), "to": int(rng.integers(5))})
+        else:
+            body = {"msg_id": k, "type": "init", "node_id": "n%d" % dest, "node_ids": []}    # "Can't init twice!"
+        ops.append((t, "c%d" % int(rng.integers(n)), "n%d" % dest, body))
+    events = []
+    for t in sorted(int(t) for t in rng.integers(2000, until, size=int(rng.integers(0, 5)))):
+        events.append((t, "heal" if rng.integers(3) == 0 else [int(x) for x in rng.integers(0, 2, size=n)]))
+
+    # reference
+    c = H.Cluster(n)
+    i = j = 0
+    while c.now_ns < until * 1_000_000:
+        while j < len(events) and events[j][0] * 1_000_000 <= c.now_ns:
+            c.component = None if events[j][1] == "heal" else list(events[j][1])
+            j += 1
+        while i < len(ops) and ops[i][0] * 1_000_000 <= c.now_ns:
+            c.client_send(ops[i][1], ops[i][2], ops[i][3])
+            i += 1
+        c.run_round()
+    want = [tuple(H.canonical(m, n)) for m in c.trace]
+
+    # oracle
+    fix = {"n": n, "seed": H.SEED, "until_ms": until}
+    s = O.Sim(n, workload=O.W_RAFT, seed=H.SEED)
+    clients = [s.add_endpoint("c%d" % q) for q in range(n)]
+    rows = np.zeros(len(ops), dtype=O.OP_DTYPE)
+    for r, (t_ms, src, dest, body) in zip(rows, ops):
+        r["time_ns"] = t_ms * 1_000_000
+        r["src"] = clients[int(src[1:])]
+        r["dest"] = int(dest[1:])
+        b = r["body"]
+        b["type"] = O.T[body["type"]]
+        b["flags"] = O.F_MSG_ID
+        b["msg_id"] = body["msg_id"]
+        if "key" in body:
+            b["p0"] = body["key"]
+            if body["type"] == "write":
+                b["p1"] = body["value"]
+            elif body["type"] == "cas":
+                b["p1"] = (body["from"] & 0xFFFFFFFF) | (body["to"] << 32)
+    s.schedule(rows)
+    for t_ms, what in events:
+        s.run(t_ms * 1_000_000)
+        if what == "heal":
+            s.heal()
+        else:
+            s.heal()                                         # a new bulk partition replaces the old one
+            s.partition(list(what))
+    s.run(until * 1_000_000)
+    ev, bd = s.journal()
+    got = canonical_from_oracle(s, ev, bd)
+    for g, w in zip(got, want):
+        assert g == w, (g, w)
+    assert len(got) == len(want) and s.round == c.round
+    code = {"nascent": 0, "follower": 1, "candidate": 2, "leader": 3}
+    for q, nd in enumerate(c.nodes):
+        st = s.raft_state(q)
+        assert (st["state"], st["term"], st["commit_index"], st["log_size"], st["last_applied"]) == \
+            (code[nd.raft.state], nd.raft.current_term, nd.raft.commit_index, nd.raft.log.size(), nd.raft.last_applied)
