@@ -858,13 +858,29 @@ int ms_step(ms_sim* s, uint64_t n_rounds) {
   return MS_OK;
 }
 
+// Virtual time only advances in a round that leaves nothing due "now" (DESIGN.md 2.3).  A node that
+// sends zero-latency messages in every round forever (e.g. raft.py's replicate_log once a
+// next_index has gone non-positive: it raises before recording the replication, so it replicates
+// again in the next loop iteration) freezes it: report that instead of spinning.
+static const uint64_t kMaxDeltaRounds = 1ull << 20;
+static int time_stalled(ms_sim* s, int64_t now0, uint64_t round0) {
+  if (s->hs.now != now0 || s->hs.rounds_run - round0 <= kMaxDeltaRounds) return 0;
+  set_err("virtual time is not advancing: 2^20 delta rounds at the same instant (a node sends zero-latency "
+          "messages in every round)");
+  return 1;
+}
+
 int ms_run(ms_sim* s, int64_t until) {
   std::lock_guard<std::mutex> g(s->mu);
+  int64_t stall_now = s->hs.now;
+  uint64_t stall_round = s->hs.rounds_run;
   while (s->hs.now < until) {
     if (journal_blocked(s)) return 1;   // drain (ms_journal_drain) and call again
     const uint64_t r0 = s->hs.rounds_run;
     const int rc = step_locked(s, 32, until);
     if (rc) return rc;
+    if (s->hs.now != stall_now) { stall_now = s->hs.now; stall_round = s->hs.rounds_run; }
+    else if (time_stalled(s, stall_now, stall_round)) return MS_ERR_SIM;
     if (s->hs.rounds_run == r0 && s->hs.now < until && !journal_blocked(s)) {
       set_err("simulation made no progress (device refuses to run rounds)");
       return MS_ERR_SIM;

@@ -1025,7 +1025,15 @@ int or_step(or_sim* s, uint64_t n_rounds) {
 }
 
 int or_run(or_sim* s, int64_t until_ns) {
-  while (s->now < until_ns) if (!s->run_round()) return -3;
+  // a node that sends zero-latency messages in every round freezes virtual time:
+  // give up after 2^20 delta rounds at one instant, like the engine
+  int64_t stall_now = s->now;
+  uint64_t stall_round = s->round;
+  while (s->now < until_ns) {
+    if (!s->run_round()) return -3;
+    if (s->now != stall_now) { stall_now = s->now; stall_round = s->round; }
+    else if (s->round - stall_round > (1ull << 20)) { s->error = "virtual time is not advancing"; return -3; }
+  }
   return 0;
 }
 
