@@ -893,7 +893,11 @@ int ms_recv(ms_sim* s, uint32_t e, int64_t timeout, ms_msg* out) {
   std::lock_guard<std::mutex> g(s->mu);
   if (e >= s->P.n_ep || s->kinds[e] == kRemoved) { set_err("No such node in network"); return MS_ERR_NODE_NOT_FOUND; }
   const int64_t give_up = (timeout > INT64_MAX - s->hs.now) ? INT64_MAX : s->hs.now + timeout;
+  int64_t stall_now = s->hs.now;
+  uint64_t stall_round = s->hs.rounds_run;
   for (;;) {
+    if (s->hs.now != stall_now) { stall_now = s->hs.now; stall_round = s->hs.rounds_run; }
+    else if (time_stalled(s, stall_now, stall_round)) return MS_ERR_SIM;
     if (!s->mailbox[e].empty()) {
       *out = s->mailbox[e].front();
       s->mailbox[e].pop_front();

@@ -1043,7 +1043,11 @@ int or_recv(or_sim* s, uint32_t e, int64_t timeout_ns, or_msg* out) {   // net.c
   // time until the virtual timeout has elapsed (the reference blocks on the
   // wall clock, net.clj:228-229).
   const int64_t give_up = s->now + timeout_ns;
+  int64_t stall_now = s->now;
+  uint64_t stall_round = s->round;
   for (;;) {
+    if (s->now != stall_now) { stall_now = s->now; stall_round = s->round; }
+    else if (s->round - stall_round > (1ull << 20)) { s->error = "virtual time is not advancing"; return -3; }
     if (!s->eps[e].mailbox.empty()) {
       *out = s->eps[e].mailbox.front();
       s->eps[e].mailbox.pop_front();
