@@ -143,18 +143,9 @@ def test_fixtures_are_what_the_reference_produces():
     assert [H.canonical(m, fix["n"]) for m in c.trace] == fix["messages"] and c.round == fix["rounds"]
 
 
-def fuzz_seeds():
-    a, b = (int(x) for x in os.environ.get("MS_FUZZ_RAFTREF_SEEDS", "0:2").split(":"))
-    return list(range(a, b))
-
-
-@pytest.mark.skipif(not os.path.exists("/root/reference/demo/python/raft.py"),
-                    reason="the reference tree is only mounted in the build container")
-@pytest.mark.parametrize("seed", fuzz_seeds())
-def test_random_scenarios_against_the_executed_reference(seed):
-    # random cluster size, client traffic and partitions (arbitrary sides, repeated, healed or not):
-    # the reference's raft.py under the harness and the oracle must send the same messages
-    import raft_reference_harness as H
+def random_raft_scenario(seed):
+    """(n, ops, events, until_ms): random cluster size, client traffic (with a second `init` now and
+    then) and bulk partitions that come, change and sometimes heal."""
     rng = np.random.default_rng(seed)
     n = int(rng.integers(1, 6))
     ops = [(0, "c%d" % i, "n%d" % i, {"type": "init", "msg_id": 1, "node_id": "n%d" % i,
@@ -179,6 +170,64 @@ def test_random_scenarios_against_the_executed_reference(seed):
     events = []
     for t in sorted(int(t) for t in rng.integers(2000, until, size=int(rng.integers(0, 5)))):
         events.append((t, "heal" if rng.integers(3) == 0 else [int(x) for x in rng.integers(0, 2, size=n)]))
+    return n, ops, events, until
+
+
+def oracle_for(n, ops, seed):
+    s = O.Sim(n, workload=O.W_RAFT, seed=seed)
+    clients = [s.add_endpoint("c%d" % q) for q in range(n)]
+    rows = np.zeros(len(ops), dtype=O.OP_DTYPE)
+    for r, (t_ms, src, dest, body) in zip(rows, ops):
+        r["time_ns"] = t_ms * 1_000_000
+        r["src"] = clients[int(src[1:])]
+        r["dest"] = int(dest[1:])
+        b = r["body"]
+        b["type"] = O.T[body["type"]]
+        b["flags"] = O.F_MSG_ID
+        b["msg_id"] = body["msg_id"]
+        if "key" in body:
+            b["p0"] = body["key"]
+            if body["type"] == "write":
+                b["p1"] = body["value"]
+            elif body["type"] == "cas":
+                b["p1"] = (body["from"] & 0xFFFFFFFF) | (body["to"] << 32)
+    s.schedule(rows)
+    return s
+
+
+def run_events(s, events, until):
+    for t_ms, what in events:
+        s.run(t_ms * 1_000_000)
+        s.heal()                                             # a new bulk partition replaces the old one
+        if what != "heal":
+            s.partition(list(what))
+    s.run(until * 1_000_000)
+
+
+def test_frozen_virtual_time_is_reported_not_spun_on():
+    # seed 132 of the scenario generator drives a next_index non-positive: the reference's
+    # replicate_log then raises before recording the replication and replicates again in every loop
+    # iteration -- at latency 0 a message is always due "now" and virtual time stops
+    n, ops, events, until = random_raft_scenario(132)
+    s = oracle_for(n, ops, 0x4D41454C)
+    with pytest.raises(RuntimeError, match="not advancing"):
+        run_events(s, events, until)
+    assert s.now < until * 1_000_000
+
+
+def fuzz_seeds():
+    a, b = (int(x) for x in os.environ.get("MS_FUZZ_RAFTREF_SEEDS", "0:2").split(":"))
+    return list(range(a, b))
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/demo/python/raft.py"),
+                    reason="the reference tree is only mounted in the build container")
+@pytest.mark.parametrize("seed", fuzz_seeds())
+def test_random_scenarios_against_the_executed_reference(seed):
+    # random cluster size, client traffic and partitions (arbitrary sides, repeated, healed or not):
+    # the reference's raft.py under the harness and the oracle must send the same messages
+    import raft_reference_harness as H
+    n, ops, events, until = random_raft_scenario(seed)
 
     # reference
     c = H.Cluster(n)
@@ -198,34 +247,8 @@ def test_random_scenarios_against_the_executed_reference(seed):
             pytest.skip("the reference spins at a frozen instant in this scenario")
     want = [tuple(H.canonical(m, n)) for m in c.trace]
 
-    # oracle
-    fix = {"n": n, "seed": H.SEED, "until_ms": until}
-    s = O.Sim(n, workload=O.W_RAFT, seed=H.SEED)
-    clients = [s.add_endpoint("c%d" % q) for q in range(n)]
-    rows = np.zeros(len(ops), dtype=O.OP_DTYPE)
-    for r, (t_ms, src, dest, body) in zip(rows, ops):
-        r["time_ns"] = t_ms * 1_000_000
-        r["src"] = clients[int(src[1:])]
-        r["dest"] = int(dest[1:])
-        b = r["body"]
-        b["type"] = O.T[body["type"]]
-        b["flags"] = O.F_MSG_ID
-        b["msg_id"] = body["msg_id"]
-        if "key" in body:
-            b["p0"] = body["key"]
-            if body["type"] == "write":
-                b["p1"] = body["value"]
-            elif body["type"] == "cas":
-                b["p1"] = (body["from"] & 0xFFFFFFFF) | (body["to"] << 32)
-    s.schedule(rows)
-    for t_ms, what in events:
-        s.run(t_ms * 1_000_000)
-        if what == "heal":
-            s.heal()
-        else:
-            s.heal()                                         # a new bulk partition replaces the old one
-            s.partition(list(what))
-    s.run(until * 1_000_000)
+    s = oracle_for(n, ops, H.SEED)
+    run_events(s, events, until)
     ev, bd = s.journal()
     got = canonical_from_oracle(s, ev, bd)
     for g, w in zip(got, want):
