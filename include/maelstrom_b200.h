@@ -149,7 +149,7 @@ typedef struct ms_config {
   /* engine sizing (0 = default) */
   uint32_t max_endpoints;    /* servers + clients + services */
   uint32_t ring_cap;         /* per-endpoint inbox ring capacity, power of two */
-  uint32_t max_window;       /* max messages one endpoint consumes per round */
+  uint32_t max_window;       /* max messages one endpoint consumes per round (<= 8192) */
   uint32_t journal_cap_log2; /* device journal ring = 2^k events */
   uint32_t journal_level;    /* 0 off, 1 events, 2 events + bodies */
   uint32_t journal_discard;  /* 1: device journal is overwritten, never drained (kernel-only runs) */

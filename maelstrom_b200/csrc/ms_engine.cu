@@ -429,7 +429,8 @@ static int build_sim(ms_sim* s, const ms_config* in) {
   if (c.max_endpoints < c.n_nodes) { set_err("max_endpoints < n_nodes"); return MS_ERR_ARG; }
   c.ring_cap = pow2_at_least(c.ring_cap ? c.ring_cap : 1024);
   c.max_window = pow2_at_least(c.max_window ? c.max_window : std::min<uint32_t>(c.ring_cap, 1024));
-  if (c.max_window > 32768) { set_err("max_window must be <= 32768"); return MS_ERR_ARG; }
+  // 25 B of dynamic shared memory per window slot + ~3 KB static, 227 KB per CTA on sm_100a
+  if (c.max_window > 8192) { set_err("max_window must be <= 8192 (25 B of shared memory per slot, 227 KB per CTA)"); return MS_ERR_ARG; }
   if (c.max_window > c.ring_cap) c.max_window = c.ring_cap;
   if (!c.journal_cap_log2) c.journal_cap_log2 = 22;
   if (c.journal_level > 2) c.journal_level = 2;
