@@ -8,6 +8,26 @@
 #include <thread>
 #include <vector>
 
+// MS_TSAN (tools/emul_tsan.sh): kernels + engine are compiled with -fsanitize=thread, this file is
+// not.  Every emulated thread is a TSan fiber; the scheduler's context switches carry no
+// synchronisation, __syncthreads() and warp collectives are release/acquire pairs, a kernel launch
+// is ordered after the host code before it and before the host code after it, and CTAs of a launch
+// are chained (their __shared__ statics are the same host memory).  What TSan then reports is two
+// threads of ONE CTA touching the same shared / global location with no barrier in between.
+#ifdef MS_TSAN
+extern "C" {
+void* __tsan_get_current_fiber(void);
+void* __tsan_create_fiber(unsigned flags);
+void __tsan_destroy_fiber(void* fiber);
+void __tsan_switch_to_fiber(void* fiber, unsigned flags);
+void __tsan_acquire(void* addr);
+void __tsan_release(void* addr);
+}
+#define TSAN(x) x
+#else
+#define TSAN(x)
+#endif
+
 namespace simt {
 
 thread_local Tls tls;
@@ -63,6 +83,11 @@ struct Sched {
   const std::function<void()>* body = nullptr;
   unsigned char* smem = nullptr;
   uint64_t progress = 0;
+  void* fib[kMaxThreads];            // MS_TSAN: TSan fiber of each emulated thread
+  void* main_fib = nullptr;
+  char sync_bar, sync_launch_begin, sync_launch_end, sync_cta_chain;   // MS_TSAN: addresses to release / acquire on
+  char sync_warp[kMaxThreads / 32];
+  unsigned bar_calls[kMaxThreads];   // MS_TSAN self-test
 };
 static thread_local Sched* g_s = nullptr;
 
@@ -85,6 +110,7 @@ static Sched* sched() {
 static void yield_to_scheduler() {
   Sched* s = g_s;
   const unsigned me = s->cur;
+  TSAN(__tsan_switch_to_fiber(s->main_fib, 1);)
   simt_switch(&s->sp[me], s->main_sp);
   tls.tid.x = me;   // resumed
 }
@@ -100,7 +126,9 @@ static void finish_collective(Warp& w);
 
 static void fiber_main() {
   Sched* s = g_s;
+  TSAN(__tsan_acquire(&s->sync_launch_begin); __tsan_acquire(&s->sync_cta_chain);)
   (*s->body)();
+  TSAN(__tsan_release(&s->sync_launch_end); __tsan_release(&s->sync_cta_chain);)
   const unsigned me = s->cur;
   s->done[me] = true;
   s->live--;
@@ -111,20 +139,31 @@ static void fiber_main() {
   if (s->bar_count && s->bar_count == s->live) release_barrier(s);
   if (w.count && w.count == w.live) finish_collective(w);
   void* dummy;
+  TSAN(__tsan_switch_to_fiber(s->main_fib, 1);)
   simt_switch(&dummy, s->main_sp);
   die("resumed a finished thread");
 }
 
-void sync_threads() { (void)sync_threads_or(0); }
+static int barrier(int pred, bool plain);
+void sync_threads() { (void)barrier(0, true); }
+int sync_threads_or(int pred) { return barrier(pred, false); }
 
-int sync_threads_or(int pred) {
+static int barrier(int pred, bool plain) {
   Sched* s = g_s;
+#ifdef MS_TSAN
+  // self-test of the race check: MS_TSAN_SKIP_BARRIER=k turns every k-th barrier of every CTA into
+  // a no-op (the same one for all its threads), which TSan must then report
+  static const unsigned skip = getenv("MS_TSAN_SKIP_BARRIER") ? (unsigned)atoi(getenv("MS_TSAN_SKIP_BARRIER")) : 0;
+  if (skip && plain && (++s->bar_calls[s->cur] % skip) == 0) return 0;
+#endif
   const unsigned gen = s->bar_gen;
   if (pred) s->bar_or[gen & 1] = 1;
   s->bar_count++;
   s->progress++;
+  TSAN(__tsan_release(&s->sync_bar);)
   if (s->bar_count == s->live) release_barrier(s);
   while (s->bar_gen == gen) yield_to_scheduler();
+  TSAN(__tsan_acquire(&s->sync_bar);)
   return s->bar_or[gen & 1];
 }
 
@@ -174,8 +213,10 @@ uint64_t warp_op(int op, unsigned mask, uint64_t v, int arg) {
   w.arg[lane] = arg;
   w.count++;
   s->progress++;
+  TSAN(__tsan_release(&s->sync_warp[me >> 5]);)
   if (w.count == w.live) finish_collective(w);
   while (w.gen == gen) yield_to_scheduler();
+  TSAN(__tsan_acquire(&s->sync_warp[me >> 5]);)
   return w.out[gen & 1][lane];
 }
 
@@ -206,13 +247,16 @@ static void run_cta(Sched* s, unsigned nt) {
   }
   for (unsigned t = 0; t < nt; t++) {
     s->done[t] = false;
+    s->bar_calls[t] = 0;
     uintptr_t top = (uintptr_t)(s->stacks + (size_t)(t + 1) * kStack) & ~(uintptr_t)15;
     void** p = (void**)top;
     p[-1] = nullptr;                  // return address slot of fiber_main (never used)
     p[-2] = (void*)&fiber_main;       // popped by simt_switch's ret
     for (int r = 3; r <= 8; r++) p[-r] = nullptr;   // rbp rbx r12-r15
     s->sp[t] = (void*)(p - 8);
+    TSAN(s->fib[t] = __tsan_create_fiber(0);)
   }
+  TSAN(s->main_fib = __tsan_get_current_fiber();)
   // MS_EMUL_ORDER: 0 = threads resume in index order (default), 1 = reverse, 2 = a different
   // pseudo-random order every sweep.  Results must not depend on it: a missing barrier usually does.
   static const int order_mode = getenv("MS_EMUL_ORDER") ? atoi(getenv("MS_EMUL_ORDER")) : 0;
@@ -235,10 +279,12 @@ static void run_cta(Sched* s, unsigned nt) {
       if (s->done[t]) continue;
       s->cur = t;
       tls.tid.x = t;
+      TSAN(__tsan_switch_to_fiber(s->fib[t], 1);)
       simt_switch(&s->main_sp, s->sp[t]);
     }
     if (s->live && s->progress == before) die("deadlock: no thread of the CTA can make progress");
   }
+  TSAN(for (unsigned t = 0; t < nt; t++) __tsan_destroy_fiber(s->fib[t]);)
 }
 
 // MS_EMUL_PROFILE=1: wall time per (grid, block) launch shape, printed at exit
@@ -277,12 +323,14 @@ static void launch_impl(unsigned grid, unsigned block, size_t dyn, const std::fu
   tls.gdim = dim3{grid, 1, 1};
   tls.tid = uint3{0, 0, 0};
   static const int order_mode = getenv("MS_EMUL_ORDER") ? atoi(getenv("MS_EMUL_ORDER")) : 0;
+  TSAN(__tsan_release(&s->sync_launch_begin);)
   for (unsigned bb = 0; bb < grid; bb++) {
     const unsigned b = order_mode ? grid - 1 - bb : bb;     // CTAs must not depend on launch order either
     tls.bid = uint3{b, 0, 0};
     memset(s->smem, 0xCD, dyn);
     run_cta(s, block);
   }
+  TSAN(__tsan_acquire(&s->sync_launch_end);)
   s->body = nullptr;
 }
 
