@@ -21,8 +21,8 @@ static ms_sim* make(uint32_t n, uint32_t workload, uint32_t latency_ms) {
   c.n_nodes = n; c.workload = workload; c.topology = MS_TOPO_GRID;
   c.latency_dist = MS_DIST_CONSTANT; c.latency_mean_ms = latency_ms;
   c.seed_lo = 0x4D41454C; c.n_values = 4096; c.gset_interval_ms = 7;
-  c.max_endpoints = n + 16; c.ring_cap = 4096; c.max_window = 2048; c.journal_cap_log2 = 18; c.journal_level = 2;
-  c.calendar_slots = 64; c.calendar_cap = 1 << 14;
+  c.max_endpoints = n + 16; c.ring_cap = 8192; c.max_window = 4096; c.journal_cap_log2 = 18; c.journal_level = 2;
+  c.calendar_slots = 16; c.calendar_cap = 1 << 17;
   ms_sim* s = ms_create(&c);
   if (!s) { fprintf(stderr, "ms_create failed: %s\n", ms_last_error(nullptr)); }
   return s;
@@ -46,11 +46,11 @@ int main() {
       ms_sim* s = make(36, MS_W_BROADCAST, lat);
       const int c = ms_add_endpoint(s, "c0", MS_KIND_SIM_CLIENT);
       std::vector<ms_op> ops;
-      for (uint32_t k = 0; k < 900; k++) {
+      for (uint32_t k = 0; k < 3600; k++) {                 // windows of > 512 messages at the hot nodes: classes 0-2
         ms_op op;
         memset(&op, 0, sizeof op);
-        op.time_ns = (int64_t)(k / 300) * 1000000; op.src = (uint32_t)c; op.dest = (k * 7) % 36;
-        op.body = body(MS_T_BROADCAST, k + 1, k % 800);
+        op.time_ns = (int64_t)(k / 1200) * 1000000; op.src = (uint32_t)c; op.dest = (k % 5 == 0) ? 14u : (k * 7) % 36;
+        op.body = body(MS_T_BROADCAST, k + 1, k % 3300);
         ops.push_back(op);
       }
       ms_schedule_ops(s, ops.data(), ops.size());
@@ -59,7 +59,7 @@ int main() {
     }
   }
   {  // g-set: snapshots, merges, reads in the same windows
-    ms_sim* s = make(9, MS_W_GSET, 0);
+    ms_sim* s = make(9, MS_W_GSET, 2);                       // latency 2 ms: replicate_full through the timing wheel
     const int c = ms_add_endpoint(s, "c0", MS_KIND_SIM_CLIENT);
     ms_body b;
     for (uint32_t i = 0; i < 9; i++) { b = body(MS_T_INIT, 100 + i); ms_send(s, (uint32_t)c, i, &b); }
