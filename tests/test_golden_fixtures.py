@@ -1,8 +1,8 @@
 """Committed fixtures (tests/golden/): reference_vectors.json = known answers transcribed from the
 reference's docs and resources (each with its file:line); journals.json = the oracle's journals
 for the named scenarios of tests/golden_cases.py (regenerate: python tests/golden/make_golden.py).
-CPU: the oracle must reproduce both; the engine must reproduce journals.json on the CPU
-emulator ([emul]) and on a B200 ([cuda])."""
+Here the oracle must reproduce both; the engine is held to journals.json by
+tests/test_sim_lifecycle.py and tests/test_workload_*.py ([emul] on the CPU emulator, [cuda] on a B200)."""
 import json
 import os
 import re
@@ -88,11 +88,5 @@ def test_oracle_reproduces_committed_journals(name):
     assert G.digest(ev, bd, o.stats(), o.now, o.round) == JOURNALS[name]
 
 
-# (the cases of the later workloads are checked in their tests/test_workload_*.py)
-@pytest.mark.parametrize("name", sorted(G.CORE_CASES))
-def test_engine_reproduces_committed_journals(name, engine_backend):
-    import maelstrom_b200 as mb
-    g = G.make_engine(name)
-    G.CASES[name][1](g, mb.body)
-    ev, bd = g.drain()
-    assert G.digest(ev, bd, g.stats(), g.now, g.round) == JOURNALS[name]
+# The engine is checked against journals.json in tests/test_sim_lifecycle.py (core cases) and in the
+# tests/test_workload_*.py files (the later workloads).
