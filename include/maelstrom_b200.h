@@ -230,6 +230,11 @@ int ms_stats(ms_sim* sim, uint64_t out[9]);
 /* ------------------------------------------------------------------ node state read-back */
 size_t   ms_node_set(ms_sim* sim, uint32_t node, uint32_t* values, size_t cap);
 uint64_t ms_client_replies(ms_sim* sim);
+/* Sends whose src or dest was not a registered endpoint when they were made (a reply to a closed
+ * client, gossip to a stopped node).  The reference's assert (net.clj:166-176) throws only inside
+ * the sending node's stdout thread (process.clj:148-150): the id is consumed, the network keeps
+ * running.  Here the :send is journaled, the message dropped and counted; a warning, not an error. */
+uint64_t ms_undeliverable(ms_sim* sim);
 /* MS_W_RAFT: out = {state (0 nascent, 1 follower, 2 candidate, 3 leader), current_term,
  * voted_for + 1, commit_index, last_applied, leader + 1, log size, keys in the KV store}
  * (the fields of RaftNode, demo/python/raft.py:196-221) */

@@ -75,6 +75,7 @@ SYMBOLS = {
     "ms_stats": (C.c_int, [_P, _P]),
     "ms_node_set": (C.c_size_t, [_P, C.c_uint32, _P, C.c_size_t]),
     "ms_client_replies": (C.c_uint64, [_P]),
+    "ms_undeliverable": (C.c_uint64, [_P]),
     "ms_raft_state": (C.c_int, [_P, C.c_uint32, _P]),
     "ms_counters": (C.c_int, [_P, _P]),
     "ms_timer_begin": (C.c_int, [_P]),

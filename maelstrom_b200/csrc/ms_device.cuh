@@ -15,7 +15,7 @@ namespace msd {
 
 constexpr int64_t  kTickNs   = 1000000;       // latencies are integer ms (net.clj:187,204)
 constexpr uint32_t kInjector = 0xFFFFFFFFu;   // Philox "emitter" of host/scheduled sends
-constexpr uint8_t  kRemoved  = 0x80;          // endpoint kind after remove-node!
+constexpr uint8_t  kRemoved  = 0x80;          // flag or-ed into the endpoint kind by remove-node!
 
 // device-latched error codes (DevState.error)
 enum : uint32_t {
@@ -43,6 +43,7 @@ struct DevState {
   uint64_t client_replies;   // replies consumed by MS_KIND_SIM_CLIENT sinks
   uint64_t rounds_run;
   uint64_t fallback_sorts;   // windows that needed the full bitonic sort
+  uint64_t undeliverable;    // sends whose src / dest was not a registered endpoint: journaled, then dropped
   uint32_t done;             // CTAs finished this round
   uint32_t zero_pending;     // messages sent this round that are due at `now`
   uint32_t error;            // first latched E_* code
@@ -53,6 +54,8 @@ struct DevState {
   uint32_t time_advanced;    // 1 when the last round moved `now`
   uint32_t max_window_seen;
   uint32_t cal_release;      // calendar slot to release before the next round (+1), 0 = none
+  uint32_t cal_free_n;       // free blocks of the timing-wheel pool
+  uint32_t cal_ret_n;        // entries of Params.cal_ret
   uint32_t slot_open;        // k_snapshot ran for this launch slot and the round has not been committed yet
   uint32_t bar_epoch;        // cross-shard barriers executed so far
   // per-round work lists of the k_round size classes, double-buffered by round parity
@@ -94,6 +97,7 @@ struct Params {
   uint32_t* tail;            // claim counter per endpoint ring
   uint32_t* limit;           // snapshot of tail at the start of the round
   uint32_t* head;            // previous snapshot: window is [head, limit)
+  uint64_t* ep_born;         // next-message-id when the endpoint slot was (re)registered: wheel records with a smaller id are not for it
   uint4*    ring;            // n_ep * ring_cap * 3 vectors (48-B records)
   uint32_t  ring_cap, ring_mask;
   uint32_t  n_ep, n_servers, n_inj_tickets, max_window;
@@ -141,9 +145,18 @@ struct Params {
   ms_msg*   mail;
   uint32_t  mail_cap;
   // calendar (timing wheel) for latencies > 0
-  uint4*    cal;             // cal_slots * cal_cap records
-  uint32_t* cal_count;       // per slot
-  uint32_t  cal_slots, cal_cap;
+  // Slot s holds the messages whose deadline tick is == s (mod cal_slots).  A slot is a chain
+  // of fixed-size blocks taken from one pool, so memory follows the messages in flight, not
+  // slots x worst case; a latency of cal_slots ticks or more stays in its slot for `laps` more
+  // turns of the wheel (kept in the record while it waits).  Two generations per slot: the one
+  // being released and the one being filled (a release re-files the records with laps left).
+  uint4*    cal;             // pool: cal_blocks blocks of (1 << cal_blk_log2) 48-B records
+  uint32_t* cal_count;       // [2][cal_slots] records filed under (generation, slot)
+  uint32_t* cal_tab;         // [2][cal_slots][cal_tab_cap] block id + 1 of the j-th block of the chain, 0 = none yet
+  uint32_t* cal_par;         // [cal_slots] generation new records of the slot go to
+  uint32_t* cal_free;        // stack of free block ids (DevState.cal_free_n entries): popped while rounds run
+  uint32_t* cal_ret;         // blocks popped but not needed (lost a publish race); pushed back by k_snapshot
+  uint32_t  cal_slots, cal_blk_log2, cal_blocks, cal_tab_cap;
   // g-set node program (demo/ruby/g_set.rb): the set is `bitmap`; replicate_full payloads are
   // snapshots of it, kept in gs_slots rotating rows per node (row = node * gs_slots + run % gs_slots)
   uint8_t*  gs_init;         // init received: the periodic task is running (node.rb:22-36,129-137)
@@ -272,7 +285,7 @@ MS_HD uint64_t latency_ms(const NetParams& np, const uint32_t x[4]) {
   return mulhi64(neg_log2_q32(X), np.exp_coeff);
 }
 
-MS_HD bool kind_is_client(uint8_t k) { return k == MS_KIND_CLIENT || k == MS_KIND_SIM_CLIENT; }
+MS_HD bool kind_is_client(uint8_t k) { k &= 0x7F; return k == MS_KIND_CLIENT || k == MS_KIND_SIM_CLIENT; }
 
 // Shard that owns endpoint e: servers are split into G contiguous index ranges (rows of the
 // grid stay together), every other endpoint round-robin.  Injector tickets belong to shard 0.

@@ -59,7 +59,7 @@ static const char* dev_error_text(uint32_t code) {
     case E_HISTORY: return "message older than the round history (raise ms_config.reserved[0] = history rounds): round";
     case E_VALUE_RANGE: return "broadcast value out of range (raise ms_config.n_values): value";
     case E_MAIL_OVERFLOW: return "host mailbox overflow (raise ms_config.mailbox_cap) at endpoint";
-    case E_CALENDAR_OVERFLOW: return "timing wheel overflow (raise calendar_slots/calendar_cap): arg";
+    case E_CALENDAR_OVERFLOW: return "timing wheel out of blocks (raise calendar_cap; 4294967295 = pool empty, else the slot whose chain is full or a latency beyond 65535 turns):";
     case E_ID_RANGE: return "per-ticket count exceeds the table entry range at ticket";
     case E_BARRIER: return "cross-shard barrier timed out waiting for shard";
     case E_RAFT_CAPACITY: return "Raft node out of log / staging / payload-heap capacity (raise ms_config.reserved[3]) at node";
@@ -384,15 +384,23 @@ struct ms_sim {
     }
     if (n > first)
       CK(cudaMemcpy(d_sched + first, sched.data() + first, (n - first) * sizeof(ms_op), cudaMemcpyHostToDevice));
-    // tick_off[j] = number of ops whose injection tick ceil(time/tick) is < j
+    // tick_off[j] = number of ops whose injection tick ceil(time/tick) is < j.  The schedule is
+    // append-only and sorted: count the new ops per tick, then one running sum from the first
+    // tick they touch (entries below it are unchanged).
     const int64_t last = n ? sched.back().time_ns : 0;
     const size_t n_ticks = (size_t)((last + kTickNs - 1) / kTickNs) + 2;
     const size_t old_sz = tick_off.size();
     if (tick_off.size() < n_ticks + 1) tick_off.resize(n_ticks + 1, old_sz ? tick_off.back() : 0);
-    for (size_t i = first; i < n; i++) {
-      const int64_t t = sched[i].time_ns <= 0 ? 0 : (sched[i].time_ns + kTickNs - 1) / kTickNs;
-      // append-only + sorted: every entry above tick t grows by one
-      for (size_t j = (size_t)t + 1; j < tick_off.size(); j++) tick_off[j]++;
+    if (n > first) {
+      std::vector<uint32_t> add(tick_off.size() + 1, 0);
+      size_t lo = tick_off.size();
+      for (size_t i = first; i < n; i++) {
+        const int64_t t = sched[i].time_ns <= 0 ? 0 : (sched[i].time_ns + kTickNs - 1) / kTickNs;
+        add[(size_t)t + 1]++;
+        lo = std::min(lo, (size_t)t + 1);
+      }
+      uint32_t run = 0;
+      for (size_t j = lo; j < tick_off.size(); j++) { run += add[j]; tick_off[j] += run; }
     }
     if (tick_off.size() > d_tick_cap) {
       const size_t cap = std::max<size_t>(tick_off.size(), d_tick_cap * 2);
@@ -483,6 +491,7 @@ static int build_sim(ms_sim* s, const ms_config* in) {
   if ((rc = s->dalloc(&P.tail, M))) return rc;
   if ((rc = s->dalloc(&P.limit, M))) return rc;
   if ((rc = s->dalloc(&P.head, M))) return rc;
+  if ((rc = s->dalloc(&P.ep_born, M))) return rc;
   {
     void* ptr = nullptr;
     CK(cudaMalloc(&ptr, (size_t)M * c.ring_cap * 48));
@@ -616,13 +625,30 @@ static int build_sim(ms_sim* s, const ms_config* in) {
   if ((rc = s->dalloc(&P.mail, c.mailbox_cap))) return rc;
   P.mail_cap = c.mailbox_cap;
   if (s->use_calendar) {
+    // timing wheel = chains of pooled blocks (ms_device.cuh): calendar_cap is the AVERAGE number of
+    // messages per slot the pool is sized for; a single slot may hold up to cal_tab_cap blocks
+    const uint32_t cap_p2 = pow2_at_least(c.calendar_cap);
+    uint32_t blk_log2 = 4;
+    while ((1u << blk_log2) < cap_p2 / 16 && blk_log2 < 12) blk_log2++;
+    const uint64_t blocks64 = (((uint64_t)c.calendar_slots * c.calendar_cap) >> blk_log2) + 2ull * c.calendar_slots + 64;
+    if (blocks64 > (1ull << 30)) { set_err("timing wheel: calendar_slots x calendar_cap too large"); return MS_ERR_ARG; }
+    P.cal_blk_log2 = blk_log2;
+    P.cal_blocks = (uint32_t)blocks64;
+    P.cal_tab_cap = std::min<uint32_t>(P.cal_blocks, 4096u);
+    P.cal_slots = c.calendar_slots;
     void* ptr = nullptr;
-    CK(cudaMalloc(&ptr, (size_t)c.calendar_slots * c.calendar_cap * 48));
+    CK(cudaMalloc(&ptr, ((size_t)P.cal_blocks << blk_log2) * 48));
     s->allocs.push_back(ptr);
     P.cal = (uint4*)ptr;
-    if ((rc = s->dalloc(&P.cal_count, c.calendar_slots))) return rc;
-    P.cal_slots = c.calendar_slots;
-    P.cal_cap = c.calendar_cap;
+    if ((rc = s->dalloc(&P.cal_count, 2 * (size_t)c.calendar_slots))) return rc;
+    if ((rc = s->dalloc(&P.cal_tab, 2 * (size_t)c.calendar_slots * P.cal_tab_cap))) return rc;
+    if ((rc = s->dalloc(&P.cal_par, c.calendar_slots))) return rc;
+    if ((rc = s->dalloc(&P.cal_free, P.cal_blocks))) return rc;
+    if ((rc = s->dalloc(&P.cal_ret, P.cal_blocks))) return rc;
+    std::vector<uint32_t> ids(P.cal_blocks);
+    for (uint32_t i = 0; i < P.cal_blocks; i++) ids[i] = P.cal_blocks - 1 - i;   // block 0 is popped first
+    CK(cudaMemcpyAsync(P.cal_free, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
   }
 
   // endpoints: servers n0..n{N-1} (core.clj:231-238)
@@ -649,6 +675,7 @@ static int build_sim(ms_sim* s, const ms_config* in) {
 
   memset(&s->hs, 0, sizeof s->hs);
   s->hs.stop_ns = INT64_MAX;
+  s->hs.cal_free_n = P.cal_blocks;
   CK(cudaMemcpyAsync(P.st, &s->hs, sizeof(DevState), cudaMemcpyHostToDevice, s->stream));
 
   CK(msk_round_smem_attr(msk_round_smem_bytes(c.max_window)));
@@ -730,7 +757,7 @@ int ms_stop_nodes(ms_sim* s) {
   std::lock_guard<std::mutex> g(s->mu);
   cudaSetDevice(s->device);
   for (uint32_t i = 0; i < s->cfg.n_nodes; i++) {
-    if (s->kinds[i] != kRemoved) { s->by_name.erase(s->names[i]); s->kinds[i] = kRemoved; }
+    if (!(s->kinds[i] & kRemoved)) { s->by_name.erase(s->names[i]); s->kinds[i] |= kRemoved; }
   }
   CK(cudaMemcpy(s->P.kind, s->kinds.data(), s->cfg.n_nodes, cudaMemcpyHostToDevice));
   return MS_OK;
@@ -741,7 +768,15 @@ int ms_add_endpoint(ms_sim* s, const char* id, int kind) {
   cudaSetDevice(s->device);
   if (!id || kind < MS_KIND_CLIENT || kind > MS_KIND_SERVICE) { set_err("bad endpoint id/kind"); return MS_ERR_ARG; }
   if (s->by_name.count(id)) { set_err("endpoint already exists"); return MS_ERR_ARG; }
-  const uint32_t idx = s->P.n_ep;
+  // Slot of a removed non-server endpoint is recycled, lowest index first (Jepsen closes and reopens its
+  // clients after every indefinite op, client.clj:55-59): the new endpoint starts with an empty
+  // queue like any fresh one (net.clj:139-146).  Not while pairwise drop! entries exist: they
+  // are keyed by index and must not leak onto another name.
+  uint32_t idx = s->P.n_ep;
+  bool reuse = false;
+  if (kind != MS_KIND_SERVICE && !s->np.pair_active)
+    for (uint32_t i = s->cfg.n_nodes; i < s->P.n_ep; i++)
+      if ((s->kinds[i] & kRemoved) && (s->kinds[i] & 0x7F) != MS_KIND_SERVICE) { idx = i; reuse = true; break; }
   if (idx >= s->cfg.max_endpoints) { set_err("max_endpoints exhausted"); return MS_ERR_CAPACITY; }
   if (kind == MS_KIND_SERVICE) {
     // service/default-services (service.clj:290-296): the id names the service
@@ -766,10 +801,24 @@ int ms_add_endpoint(ms_sim* s, const char* id, int kind) {
     s->P.family |= 2u;   // from now on the round kernels with the service program compiled in
   }
   s->kinds[idx] = (uint8_t)kind;
-  s->names.push_back(id);
-  s->mailbox.emplace_back();
+  if (reuse) {
+    // whatever was still queued for the old endpoint is gone with its queue: empty the ring, and
+    // let the timing wheel drop what it still holds for the old name (sent before `born`)
+    CK(cudaStreamSynchronize(s->stream));
+    uint32_t tail = 0;
+    CK(cudaMemcpy(&tail, s->P.tail + idx, 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(s->P.limit + idx, &tail, 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->P.head + idx, &tail, 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->P.ep_born + idx, &s->hs.next_id, 8, cudaMemcpyHostToDevice));
+    if (s->P.sv_seq_cli) { const uint32_t zero = 0; CK(cudaMemcpy(s->P.sv_seq_cli + idx, &zero, 4, cudaMemcpyHostToDevice)); }
+    s->names[idx] = id;
+    s->mailbox[idx].clear();
+  } else {
+    s->names.push_back(id);
+    s->mailbox.emplace_back();
+    s->P.n_ep = idx + 1;
+  }
   s->by_name[id] = idx;
-  s->P.n_ep = idx + 1;
   CK(cudaMemcpy(s->P.kind + idx, &s->kinds[idx], 1, cudaMemcpyHostToDevice));
   return (int)idx;
 }
@@ -777,9 +826,9 @@ int ms_add_endpoint(ms_sim* s, const char* id, int kind) {
 int ms_remove_endpoint(ms_sim* s, uint32_t idx) {
   std::lock_guard<std::mutex> g(s->mu);
   cudaSetDevice(s->device);
-  if (idx >= s->P.n_ep || s->kinds[idx] == kRemoved) { set_err("No such node in network"); return MS_ERR_NODE_NOT_FOUND; }
+  if (idx >= s->P.n_ep || (s->kinds[idx] & kRemoved)) { set_err("No such node in network"); return MS_ERR_NODE_NOT_FOUND; }
   s->by_name.erase(s->names[idx]);
-  s->kinds[idx] = kRemoved;
+  s->kinds[idx] |= kRemoved;   // the kind stays readable: a removed "c*" endpoint is still a client by name (util.clj:7-16)
   CK(cudaMemcpy(s->P.kind + idx, &s->kinds[idx], 1, cudaMemcpyHostToDevice));
   return MS_OK;
 }
@@ -793,8 +842,8 @@ int ms_endpoint_index(ms_sim* s, const char* id) {
 
 int64_t ms_send(ms_sim* s, uint32_t src, uint32_t dest, const ms_body* b) {
   std::lock_guard<std::mutex> g(s->mu);
-  if (src >= s->P.n_ep || s->kinds[src] == kRemoved) { set_err("Invalid source for message"); return MS_ERR_NODE_NOT_FOUND; }
-  if (dest >= s->P.n_ep || s->kinds[dest] == kRemoved) { set_err("Invalid dest for message"); return MS_ERR_NODE_NOT_FOUND; }
+  if (src >= s->P.n_ep || (s->kinds[src] & kRemoved)) { set_err("Invalid source for message"); return MS_ERR_NODE_NOT_FOUND; }
+  if (dest >= s->P.n_ep || (s->kinds[dest] & kRemoved)) { set_err("Invalid dest for message"); return MS_ERR_NODE_NOT_FOUND; }
   if (!b) { set_err("null body"); return MS_ERR_ARG; }
   ms_msg m;
   memset(&m, 0, sizeof m);
@@ -808,14 +857,19 @@ int ms_schedule_ops(ms_sim* s, const ms_op* ops, size_t n) {
   std::lock_guard<std::mutex> g(s->mu);
   cudaSetDevice(s->device);
   const size_t first = s->sched.size();
+  // validate the whole batch before anything is appended: a rejected batch leaves no orphans
+  int64_t prev = first ? s->sched.back().time_ns : INT64_MIN;
   for (size_t i = 0; i < n; i++) {
-    if (!s->sched.empty() && ops[i].time_ns < s->sched.back().time_ns) { set_err("ops must be sorted by time"); return MS_ERR_ARG; }
-    if (ops[i].src >= s->P.n_ep || ops[i].dest >= s->P.n_ep || s->kinds[ops[i].src] == kRemoved ||
-        s->kinds[ops[i].dest] == kRemoved) { set_err("scheduled op names an unknown endpoint"); return MS_ERR_NODE_NOT_FOUND; }
-    s->sched.push_back(ops[i]);
+    if (ops[i].time_ns < prev) { set_err("ops must be sorted by time"); return MS_ERR_ARG; }
+    prev = ops[i].time_ns;
+    if (ops[i].src >= s->P.n_ep || ops[i].dest >= s->P.n_ep || (s->kinds[ops[i].src] & kRemoved) ||
+        (s->kinds[ops[i].dest] & kRemoved)) { set_err("scheduled op names an unknown endpoint"); return MS_ERR_NODE_NOT_FOUND; }
   }
   CK(cudaStreamSynchronize(s->stream));
-  return s->upload_schedule(first);
+  s->sched.insert(s->sched.end(), ops, ops + n);
+  const int rc = s->upload_schedule(first);
+  if (rc != MS_OK) s->sched.resize(first);   // keep host and device schedules identical
+  return rc;
 }
 
 // true when the device refuses to run rounds until the host drains the journal
@@ -892,7 +946,7 @@ int ms_run(ms_sim* s, int64_t until) {
 
 int ms_recv(ms_sim* s, uint32_t e, int64_t timeout, ms_msg* out) {
   std::lock_guard<std::mutex> g(s->mu);
-  if (e >= s->P.n_ep || s->kinds[e] == kRemoved) { set_err("No such node in network"); return MS_ERR_NODE_NOT_FOUND; }
+  if (e >= s->P.n_ep || (s->kinds[e] & kRemoved)) { set_err("No such node in network"); return MS_ERR_NODE_NOT_FOUND; }
   const int64_t give_up = (timeout > INT64_MAX - s->hs.now) ? INT64_MAX : s->hs.now + timeout;
   int64_t stall_now = s->hs.now;
   uint64_t stall_round = s->hs.rounds_run;
@@ -946,7 +1000,11 @@ int ms_net_heal(ms_sim* s) {
 int ms_net_slow(ms_sim* s) {
   std::lock_guard<std::mutex> g(s->mu);
   cudaSetDevice(s->device);
-  if (s->np.scale > 100000000u) { set_err("slow!: scale overflow"); return MS_ERR_ARG; }
+  // scale stays a u32 and round(mean * scale * ln2 * 2^32) must fit the u64 exp_coeff
+  if (s->np.scale > 100000000u || (double)s->np.mean_ms * (double)s->np.scale * 10.0 > 4.0e9) {
+    set_err("slow!: latency scale overflow");
+    return MS_ERR_ARG;
+  }
   s->np.scale *= 10;
   recompute_exp(s);
   return s->push_np();
@@ -1041,6 +1099,7 @@ size_t ms_node_set(ms_sim* s, uint32_t node, uint32_t* values, size_t cap) {
 }
 
 uint64_t ms_client_replies(ms_sim* s) { std::lock_guard<std::mutex> g(s->mu); return s->hs.client_replies; }
+uint64_t ms_undeliverable(ms_sim* s) { std::lock_guard<std::mutex> g(s->mu); return s->hs.undeliverable; }
 
 int ms_raft_state(ms_sim* s, uint32_t node, uint64_t out[8]) {
   std::lock_guard<std::mutex> g(s->mu);

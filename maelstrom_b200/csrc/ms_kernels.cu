@@ -43,6 +43,7 @@ namespace msd {
 constexpr int MAXB = 64;            // sender blocks handled by the fast ordering path
 constexpr int MAXNB = 8;            // neighbor slots handled by per-(CTA, neighbor) claims
 constexpr uint64_t RECV_BIT = 1ull << 63;
+constexpr uint32_t kResolvedTicket = 0xFFFFFFu;   // order key of a record that carries its dense id: (id >> 32, this, id & 0xFFFFFFFF)
 
 // ------------------------------------------------------------------ small PTX helpers
 __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) { return __ldcg(p); }
@@ -120,6 +121,7 @@ __device__ __forceinline__ Rec rec_unpack(uint4 a, uint4 b, uint4 c) {
 
 // dense id of (round, ticket, idx): id_base[round] + emit_prefix[round][ticket] + idx
 __device__ __forceinline__ uint64_t dense_base(const Params& p, DevState* st, uint64_t round, uint32_t ticket) {
+  if (ticket == kResolvedTicket) return round << 32;   // the record already carries its id (k_release)
   const uint32_t row = (uint32_t)round & p.hist_mask;
   const RoundMeta* m = p.rmeta + row;
   if (m->round != round || ticket >= p.t_max) {
@@ -219,6 +221,59 @@ __device__ __forceinline__ void journal_raw(const Params& p, uint64_t pos, uint6
   }
 }
 
+// ------------------------------------------------------------------ timing wheel (pooled chains)
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+
+// Block `j` of the chain of (generation, slot): its pool index, allocating it on first use.  The
+// thread that filed the first record of the block is its designated allocator; everybody else
+// polls briefly for the published id and then allocates too (whoever publishes first wins, the
+// others hand their block back through cal_ret), so no thread ever waits on another one.
+__device__ uint32_t wheel_block(const Params& p, DevState* st, uint32_t* entry, bool designated) {
+  uint32_t b = ld_volatile_u32(entry);
+  if (b) return b - 1;
+  if (!designated) {
+    for (int spin = 0; spin < 64; spin++) {
+      __nanosleep(64);
+      b = ld_volatile_u32(entry);
+      if (b) return b - 1;
+    }
+  }
+  const uint32_t n = atomicAdd(&st->cal_free_n, 0xFFFFFFFFu);          // pop
+  if (n == 0 || n > p.cal_blocks) {                                     // pool exhausted
+    atomicAdd(&st->cal_free_n, 1u);
+    latch_error(st, E_CALENDAR_OVERFLOW, 0xFFFFFFFFu);
+    return 0xFFFFFFFFu;
+  }
+  const uint32_t mine = p.cal_free[n - 1];
+  const uint32_t old = atomicCAS(entry, 0u, mine + 1u);
+  if (old == 0u) return mine;
+  p.cal_ret[atomicAdd(&st->cal_ret_n, 1u)] = mine;                       // somebody else published first
+  return old - 1u;
+}
+
+// Files record r into wheel slot `slot`.  Convergent: all 32 lanes call, `valid` selects.
+__device__ __forceinline__ void wheel_file(const Params& p, DevState* st, bool valid, uint32_t slot, const Rec& r) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t key = valid ? slot : (0x80000000u | (uint32_t)lane);
+  const uint32_t mask = __match_any_sync(FULL, key);
+  const int leader = __ffs(mask) - 1;
+  const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
+  uint32_t gen = 0, base = 0;
+  if (valid && lane == leader) {
+    gen = p.cal_par[slot];
+    base = atomicAdd(&p.cal_count[(size_t)gen * p.cal_slots + slot], (uint32_t)__popc(mask));
+  }
+  gen = __shfl_sync(FULL, gen, leader);
+  base = __shfl_sync(FULL, base, leader);
+  if (!valid) return;
+  const uint32_t k = base + rank;
+  const uint32_t j = k >> p.cal_blk_log2, off = k & ((1u << p.cal_blk_log2) - 1u);
+  if (j >= p.cal_tab_cap) { latch_error(st, E_CALENDAR_OVERFLOW, slot); return; }
+  const uint32_t b = wheel_block(p, st, p.cal_tab + ((size_t)gen * p.cal_slots + slot) * p.cal_tab_cap + j, off == 0);
+  if (b == 0xFFFFFFFFu) return;
+  rec_store(p.cal + (((size_t)b << p.cal_blk_log2) + off) * 3, r);
+}
+
 // Must be called convergently by all 32 lanes of a warp.  has_direct
 // means ring space for this record was already claimed by the CTA (per-neighbor
 // block claim); otherwise slots are claimed here, one atomic per destination
@@ -227,11 +282,14 @@ __device__ __forceinline__ void emit_one(const Params& p, DevState* st, const Ne
                                          bool valid, Rec& r, uint32_t local_idx, uint32_t direct_pos,
                                          bool has_direct) {
   const int lane = threadIdx.x & 31;
-  bool push = false;
-  if (valid && (r.dest >= p.n_ep || p.kind[r.dest] == kRemoved)) {   // net.clj:172-175
-    latch_error(st, E_INVALID_DEST, r.dest);
-    valid = false;
-  }
+  bool push = false, wheel = false;
+  uint32_t wslot = 0;
+  // A message whose src or dest is not a registered endpoint (net.clj:166-176) never reaches a queue.
+  // In the reference the assert only throws inside the sending node's stdout thread
+  // (process.clj:148-150), after the id was taken (net.clj:197); the network keeps running.  Here
+  // the id is consumed, the :send is journaled, the message is dropped and counted.
+  const bool undeliverable = valid && (r.dest >= p.n_ep || (p.kind[r.dest] & kRemoved) ||
+                                       r.src >= p.n_ep || (p.kind[r.src] & kRemoved));
   if (valid) {
     r.round = cx.round; r.ticket = cx.ticket; r.idx = local_idx;     // order key == id order (net.clj:197)
     uint32_t x[4] = {0xFFFFFFFFu, 0, 0, 0};
@@ -239,12 +297,14 @@ __device__ __forceinline__ void emit_one(const Params& p, DevState* st, const Ne
       philox4x32_10(local_idx + cx.idx_bias, cx.emitter, (uint32_t)cx.round, (uint32_t)(cx.round >> 32),
                     p.seed_lo, p.seed_hi, x);
     // util.clj:12-16; servers are the endpoints below n_servers, so most lookups are avoided
-    const bool cl = (r.src >= p.n_servers && kind_is_client(p.kind[r.src])) ||
-                    (r.dest >= p.n_servers && kind_is_client(p.kind[r.dest]));
+    const bool cl = (r.src >= p.n_servers && r.src < p.n_ep && kind_is_client(p.kind[r.src])) ||
+                    (r.dest >= p.n_servers && r.dest < p.n_ep && kind_is_client(p.kind[r.dest]));
     const uint64_t lat = cl ? 0ull : (cx.need_rng ? latency_ms(np, x) : cx.const_lat);   // net.clj:185-187
     journal_raw(p, cx.chunk + cx.n_recv + local_idx, local_idx, false, r);   // net.clj:208 (before the loss roll)
     if (cl) cx.c_send_cl++; else cx.c_send_sv++;
-    if ((uint64_t)x[0] < np.loss_thresh) {                           // net.clj:214-215
+    if (undeliverable) {
+      atomicAdd((unsigned long long*)&st->undeliverable, 1ull);
+    } else if ((uint64_t)x[0] < np.loss_thresh) {                    // net.clj:214-215
       cx.c_lost++;
     } else if (lat == 0) {                                           // deadline == now: next delta round
       cx.c_zero++;
@@ -255,18 +315,20 @@ __device__ __forceinline__ void emit_one(const Params& p, DevState* st, const Ne
         push = true;
       }
     } else {
-      // timing wheel: slot of the deadline tick (net.clj:202-205)
+      // timing wheel: slot of the deadline tick (net.clj:202-205); a latency of cal_slots ticks or
+      // more waits `laps` further turns in that slot
       const uint64_t tick = (uint64_t)(cx.now / kTickNs) + lat;
-      if (p.cal == nullptr || lat >= p.cal_slots) {
+      const uint64_t laps = (lat - 1) / p.cal_slots;
+      if (p.cal == nullptr || laps > 0xFFFFu) {
         latch_error(st, E_CALENDAR_OVERFLOW, (uint32_t)lat);
       } else {
-        const uint32_t slot = (uint32_t)tick & (p.cal_slots - 1);
-        const uint32_t k = atomicAdd(&p.cal_count[slot], 1u);
-        if (k >= p.cal_cap) latch_error(st, E_CALENDAR_OVERFLOW, slot);
-        else rec_store(p.cal + ((size_t)slot * p.cal_cap + k) * 3, r);
+        wheel = true;
+        wslot = (uint32_t)tick & (p.cal_slots - 1);
+        r.round |= laps << 48;
       }
     }
   }
+  if (__any_sync(FULL, wheel)) wheel_file(p, st, wheel, wslot, r);
   if (!__any_sync(FULL, push)) return;
   // warp-aggregated claim of ring slots: one atomic per distinct destination
   const uint32_t key = push ? r.dest : (0x80000000u | (uint32_t)lane);
@@ -339,7 +401,7 @@ __global__ void k_snapshot(Params p) {
     const uint32_t h = p.limit[e], l = p.tail[e];
     p.head[e] = h;
     p.limit[e] = l;
-    const uint32_t n = (p.kind[e] == kRemoved) ? 0u : l - h;
+    const uint32_t n = ((p.kind[e] & kRemoved)) ? 0u : l - h;
     // g-set: a node whose periodic replication task is due emits even with an empty window
     // Raft: a node's election / heartbeat / commit actions are evaluated every round
     const bool timer_due = e < p.n_servers && p.kind[e] == MS_KIND_SERVER &&
@@ -367,11 +429,30 @@ __global__ void k_snapshot(Params p) {
     const uint32_t k = atomicAdd(&st->cls_count[par][c], 1u);
     p.cls_list[((size_t)par * 4 + c) * p.t_max + k] = gid;
   }
-  if (gid == 0) {
-    if (st->cal_release) {
-      p.cal_count[st->cal_release - 1] = 0;
-      st->cal_release = 0;
+  if (blockIdx.x == 0) {
+    // timing wheel housekeeping, one CTA (nothing pops blocks while this kernel runs): the chain
+    // k_release has just emptied goes back to the pool, and so do blocks that lost a publish race
+    if (p.cal && st->cal_release) {
+      const uint32_t slot = st->cal_release - 1;
+      const uint32_t gen = p.cal_par[slot] ^ 1u;                        // the generation that was released
+      uint32_t* cnt = p.cal_count + (size_t)gen * p.cal_slots + slot;
+      uint32_t* tab = p.cal_tab + ((size_t)gen * p.cal_slots + slot) * p.cal_tab_cap;
+      const uint32_t nb = min((*cnt + (1u << p.cal_blk_log2) - 1u) >> p.cal_blk_log2, p.cal_tab_cap);
+      for (uint32_t j = threadIdx.x; j < nb; j += blockDim.x) {
+        const uint32_t b = tab[j];
+        if (b) { p.cal_free[atomicAdd(&st->cal_free_n, 1u)] = b - 1u; tab[j] = 0; }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) { *cnt = 0; st->cal_release = 0; }
     }
+    if (p.cal) {
+      const uint32_t nr = st->cal_ret_n;
+      for (uint32_t i = threadIdx.x; i < nr; i += blockDim.x) p.cal_free[atomicAdd(&st->cal_free_n, 1u)] = p.cal_ret[i];
+      __syncthreads();
+      if (threadIdx.x == 0) st->cal_ret_n = 0;
+    }
+  }
+  if (gid == 0) {
     for (int c = 0; c < 4; c++) { st->cls_count[par ^ 1u][c] = 0; st->cls_cursor[par ^ 1u][c] = 0; }
     st->slot_open = 1;
   }
@@ -382,18 +463,46 @@ __global__ void k_release(Params p) {
   DevState* st = p.st;
   if (round_skipped(p, st) || st->cal_release == 0) return;
   const uint32_t slot = st->cal_release - 1;
-  const uint32_t n = min(p.cal_count[slot], p.cal_cap);
+  const uint32_t gen = p.cal_par[slot] ^ 1u;           // the commit that scheduled this release flipped the slot
+  const uint32_t n = p.cal_count[(size_t)gen * p.cal_slots + slot];
+  const uint32_t* tab = p.cal_tab + ((size_t)gen * p.cal_slots + slot) * p.cal_tab_cap;
   const uint32_t stride = gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
   const uint32_t n_round = (n + 31u) & ~31u;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-    const bool valid = i < n;
+    bool valid = i < n;
     uint4 a = make_uint4(0, 0, 0, 0), b = a, c = a;
     if (valid) {
-      const uint4* src = p.cal + ((size_t)slot * p.cal_cap + i) * 3;
-      a = ld_v4_stream(src); b = ld_v4_stream(src + 1); c = ld_v4_stream(src + 2);
+      const uint32_t j = i >> p.cal_blk_log2;
+      const uint32_t blk = j < p.cal_tab_cap ? tab[j] : 0u;
+      if (blk == 0) {
+        valid = false;                                 // never filed: the overflow was latched by the sender
+      } else {
+        const uint4* src = p.cal + ((((size_t)(blk - 1u)) << p.cal_blk_log2) + (i & ((1u << p.cal_blk_log2) - 1u))) * 3;
+        a = ld_v4_stream(src); b = ld_v4_stream(src + 1); c = ld_v4_stream(src + 2);
+      }
     }
+    // The sender's round is committed by now: turn the order key (round, ticket, idx) into the
+    // dense message id once, here, so that a message may stay in flight for any number of rounds
+    // without pinning the per-round history.  A released window holds only such records (time
+    // advances only after a round without zero-latency sends), ordered by id.
+    const uint32_t laps = a.w >> 16;
+    if (valid && (a.y & 0xFFFFFFu) != kResolvedTicket) {
+      const uint64_t id = dense_base(p, st, (uint64_t)a.z | ((uint64_t)(a.w & 0xFFFFu) << 32), a.y) + a.x;
+      a = make_uint4((uint32_t)id, kResolvedTicket, (uint32_t)(id >> 32), laps << 16);
+    }
+    // a record with laps left stays in the slot for another turn of the wheel
+    const bool again = valid && laps > 0;
+    if (__any_sync(FULL, again)) {
+      Rec r = rec_unpack(a, b, c);
+      r.round = (r.round & 0xFFFFFFFFFFFFull) | ((uint64_t)(laps - 1u) << 48);
+      wheel_file(p, st, again, slot, r);
+    }
+    if (again) valid = false;
     const uint32_t dest = b.y;
+    // the endpoint slot was handed to a new endpoint after this message was sent: its queue went
+    // with the old one (net.clj:148-152)
+    if (valid && (((uint64_t)a.x | ((uint64_t)a.z << 32)) < p.ep_born[dest])) valid = false;
     const uint32_t key = valid ? dest : (0x80000000u | (uint32_t)lane);
     const uint32_t mask = __match_any_sync(FULL, key);
     const int leader = __ffs(mask) - 1;
@@ -625,7 +734,13 @@ __device__ void commit_round(const Params& p, DevState* st, uint64_t* s_wtmp) {
         next_now = now + kTickNs;
         st->now = next_now;
         st->time_advanced = 1;
-        if (p.cal) st->cal_release = (((uint32_t)(tick + 1)) & (p.cal_slots - 1)) + 1;
+        if (p.cal) {
+          // the slot of the new tick is released before the next round; what is filed into it from
+          // now on (latencies of whole turns, re-filed laps) belongs to its next generation
+          const uint32_t slot = ((uint32_t)(tick + 1)) & (p.cal_slots - 1);
+          st->cal_release = slot + 1;
+          p.cal_par[slot] ^= 1u;
+        }
       } else {
         st->time_advanced = 0;
       }
@@ -992,7 +1107,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
     const uint32_t e = ticket - p.n_inj_tickets;
     const uint8_t kind = p.kind[e];
     const uint32_t head = p.head[e];
-    uint32_t n = (kind == kRemoved) ? 0u : (p.limit[e] - head);
+    uint32_t n = ((kind & kRemoved)) ? 0u : (p.limit[e] - head);
     if (n > cap || n > p.max_window) {
       if (tid == 0) latch_error(st, E_WINDOW_OVERFLOW, e);
       n = 0;

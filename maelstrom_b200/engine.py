@@ -63,6 +63,7 @@ class Sim:
         self._stash = []
         self.cfg = cfg
         self.n_nodes = n_nodes
+        self.workload = int(cfg.workload)
         self.h = self.L.ms_create(C.byref(cfg))
         if not self.h:
             raise SimError(-4, self.L.ms_last_error(None).decode())
@@ -250,6 +251,10 @@ class Sim:
 
     def client_replies(self):
         return int(self.L.ms_client_replies(self.h))
+
+    def undeliverable(self):
+        """Sends dropped because src / dest was not a registered endpoint (warning counter)."""
+        return int(self.L.ms_undeliverable(self.h))
 
     RAFT_FIELDS = ("state", "term", "voted_for", "commit_index", "last_applied", "leader", "log_size", "kv_size")
 

@@ -7,8 +7,13 @@ tests also drive the CPU oracle through it, which is what makes them read like t
 the reference's own net).  Node ids are strings: "n<i>" are the simulated servers,
 ids starting with "c" are clients (util.clj:7-10), anything else is a host endpoint.
 """
+import logging
+
 from . import errors
 from .engine import F_MSG_ID, F_REPLY, KIND_CLIENT, KIND_HOST, KIND_SERVICE, SERVICES, TYPES, TYPE_NAMES
+
+
+log = logging.getLogger("maelstrom.net")
 
 
 class NodeNotFound(Exception):
@@ -143,11 +148,15 @@ class Net:
             body["versions"] = [old, new]
         elif t == "ts_ok":
             body["ts"] = int(m["p1"])                                   # service.clj:127-128
+        elif t == "read_ok" and getattr(self.sim, "workload", 1) == 3:
+            body["value"] = int(m["p1"])                                # lin-kv served by Raft: raft.py:171
         elif t == "read_ok":
-            # the device message carries the set size; the members are read back from the node
+            # the device message carries the set size; the members are read back from the node.
+            # broadcast replies `messages` (workload/broadcast.clj:33-35), g-set `value` (g_set.rb:14)
             src = int(m["src"])
             members = sorted(int(v) for v in self.sim.node_set(src)) if src < self.sim.n_nodes else []
-            body["messages"] = members[:int(m["p0"])]
+            key = "value" if getattr(self.sim, "workload", 1) == 2 else "messages"
+            body[key] = members[:int(m["p0"])]
         elif int(m["p1"]) in self._blobs and isinstance(self._blobs[int(m["p1"])], dict):
             body.update(self._blobs[int(m["p1"])])
         return {"id": int(m["id"]), "src": self.names.get(int(m["src"]), str(int(m["src"]))),
@@ -165,13 +174,20 @@ class Net:
         rc = self.sim.send(self.ids[src], self.ids[dest], self._encode(message["body"]))
         if rc < 0:
             raise NodeNotFound("No such node in network: %r" % (dest,))
+        if self.log_send:                                             # (when log-send? (info :send ...))  net.clj:211
+            log.info(":send %r", dict(message, id=rc))
         return self
 
     def recv(self, node_id, timeout_ms):                              # recv!  net.clj:223-247
         if node_id not in self.ids:
             raise NodeNotFound("No such node in network: %r" % (node_id,))
         m = self.sim.recv(self.ids[node_id], int(timeout_ms * 1_000_000))
-        return None if m is None else self._decode(m)
+        if m is None:
+            return None
+        out = self._decode(m)
+        if self.log_recv:                                             # (when log-recv? (info :recv ...))  net.clj:241
+            log.info(":recv %r", out)
+        return out
 
     # ---------------------------------------------------------------- jepsen.net.proto/Net  (net.clj:105-122)
     def drop(self, test, src, dest):

@@ -366,10 +366,14 @@ struct or_sim {
   // replicate_full payloads: (sender, p1 = sender's replication run, 1-based) -> value list
   std::map<std::pair<uint32_t, uint64_t>, std::vector<uint32_t>> gset_snaps;
   uint64_t client_replies = 0;
+  uint64_t undelivered = 0;    // sends whose src / dest was not a registered endpoint
   std::string error;
   uint64_t stats[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 
-  bool is_client(uint32_t e) const { return eps[e].kind == OR_KIND_CLIENT || eps[e].kind == OR_KIND_SIM_CLIENT; }   // util.clj:7-10
+  // util.clj:7-10 goes by the name ("c..."): a removed client is still a client
+  bool is_client(uint32_t e) const {
+    return e < eps.size() && (eps[e].kind == OR_KIND_CLIENT || eps[e].kind == OR_KIND_SIM_CLIENT);
+  }
   bool involves_client(const or_msg& m) const {                                // util.clj:12-16
     return is_client(m.src) || is_client(m.dest);
   }
@@ -403,8 +407,10 @@ struct or_sim {
 
   // net.clj:189-221
   bool send(uint32_t emitter, uint32_t emit_idx, or_msg m, std::vector<Envelope>& pending) {
-    if (m.src >= eps.size() || !eps[m.src].live) { error = "Invalid source for message"; return false; }   // :172
-    if (m.dest >= eps.size() || !eps[m.dest].live) { error = "Invalid dest for message"; return false; }   // :174
+    // :166-176: the asserts throw inside the sender's own thread (process.clj:148-150) after the id
+    // was taken (:197); the network keeps running.  Spec: the id is consumed, the
+    // :send is journaled, the message is dropped and counted.
+    const bool undeliverable = m.src >= eps.size() || !eps[m.src].live || m.dest >= eps.size() || !eps[m.dest].live;
     m.id = next_id++;                                                             // :197
     const uint32_t ctr[4] = {emit_idx, emitter, (uint32_t)round, (uint32_t)(round >> 32)};
     const uint32_t key[2] = {cfg.seed_lo, cfg.seed_hi};
@@ -414,6 +420,7 @@ struct or_sim {
                                                : latency_draw(cfg.latency_dist, cfg.latency_mean_ms, scale, x);
     m.deadline_ns = now + (int64_t)lat_ms * kTickNs;                              // :202-205
     log_event(false, m);                                                          // :208 (always, before the loss roll)
+    if (undeliverable) { undelivered++; return true; }
     if ((uint64_t)x[0] < loss_thresh) return true;                                // :214-215
     Envelope env; env.m = m; env.sent_round = round;
     pending.push_back(env);                                                       // :216-221 (visible next round)
@@ -991,6 +998,15 @@ int or_add_endpoint(or_sim* s, const char* name, int kind) {   // net.clj:139-14
     else if (ep.name == "lin-tso") ep.svc.type = OR_SVC_LIN_TSO;
     else return -2;
   }
+  // the slot of a removed non-server, non-service endpoint is recycled, lowest index first, unless pairwise
+  // drop! entries (keyed by index) exist; the newcomer starts with an empty queue (net.clj:139-146)
+  if (kind != OR_KIND_SERVICE && s->partitions.empty())
+    for (uint32_t i = s->cfg.n_nodes; i < s->eps.size(); i++)
+      if (!s->eps[i].live && s->eps[i].kind != OR_KIND_SERVICE) {
+        s->eps[i] = ep;
+        for (Endpoint& other : s->eps) other.svc.clients.erase(i);   // seq-kv's per-client index (service.clj:162-166)
+        return (int)i;
+      }
   s->eps.push_back(ep);
   return (int)s->eps.size() - 1;
 }
@@ -1127,6 +1143,7 @@ size_t or_read_snapshot(or_sim* s, uint64_t msg_id, uint32_t* vals, size_t cap) 
 }
 
 uint64_t or_client_replies(or_sim* s) { return s->client_replies; }
+uint64_t or_undeliverable(or_sim* s) { return s->undelivered; }
 
 int or_raft_state(or_sim* s, uint32_t node, uint64_t out[8]) {
   if (node >= s->cfg.n_nodes) return -1;

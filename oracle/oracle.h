@@ -146,6 +146,7 @@ void     or_stats(or_sim*, uint64_t out[9]);
 size_t   or_node_set(or_sim*, uint32_t node, uint32_t* vals, size_t cap);
 size_t   or_read_snapshot(or_sim*, uint64_t msg_id, uint32_t* vals, size_t cap);
 uint64_t or_client_replies(or_sim*);
+uint64_t or_undeliverable(or_sim*);   /* sends dropped because src / dest was not a registered endpoint */
 
 /* Raft node inspection: out[0..7] = state (0 nascent, 1 follower, 2 candidate, 3 leader), term,
  * voted_for + 1, commit_index, last_applied, leader + 1, log size, kv entries */

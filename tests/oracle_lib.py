@@ -98,6 +98,8 @@ def lib():
         L.or_read_snapshot.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t]
         L.or_client_replies.restype = C.c_uint64
         L.or_client_replies.argtypes = [C.c_void_p]
+        L.or_undeliverable.restype = C.c_uint64
+        L.or_undeliverable.argtypes = [C.c_void_p]
         L.or_topology.restype = C.c_size_t
         L.or_topology.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]
         L.or_philox4x32_10.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -165,6 +167,7 @@ class Sim:
         self.L = lib()
         self.h = self.L.or_create(C.byref(cfg))
         self.n_nodes = n_nodes
+        self.workload = int(workload)
 
     def close(self):
         if self.h:
@@ -273,6 +276,9 @@ class Sim:
 
     def client_replies(self):
         return int(self.L.or_client_replies(self.h))
+
+    def undeliverable(self):
+        return int(self.L.or_undeliverable(self.h))
 
 
 class Service:

@@ -123,3 +123,77 @@ def test_error_registry_matches_errors_edn():
     assert [c for c in errors.ERRORS if not errors.definite(c)] == [0, 13]
     assert errors.name(22) == "precondition-failed" and errors.name(30) == "txn-conflict"
     assert errors.name(999) == "unknown" and not errors.definite(999)
+
+
+# ---------------------------------------------------------------- round 2: reads of the other workloads
+def _backend_for(kind, n, workload_code, **kw):
+    import maelstrom_b200 as mb
+    name = {O.W_GSET: "g-set", O.W_RAFT: "lin-kv", O.W_ECHO: "echo", O.W_BROADCAST: "broadcast"}[workload_code]
+    if kind == "oracle":
+        return Net(O.Sim(n, workload=workload_code, **kw), O.body)
+    if kind == "emul":
+        import emul_lib
+        with emul_lib.use():
+            return Net(mb.Sim(n, workload=name, **kw), mb.body)
+    return Net(mb.Sim(n, workload=name, **kw), mb.body)
+
+
+KINDS = [pytest.param("oracle"), pytest.param("emul"), pytest.param("cuda", marks=pytest.mark.gpu)]
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_gset_read_returns_value(kind):
+    # demo/ruby/g_set.rb:13-15: read_ok {value: @set.to_a}; workload/g_set.clj:20-26
+    net = _backend_for(kind, 3, O.W_GSET, n_values=64, gset_interval_ms=50)
+    nodes = ["n0", "n1", "n2"]
+    for n in nodes:
+        init_node(net, n, nodes)
+    c = C.Client(net)
+    for v in (5, 9):
+        assert c.rpc("n0", {"type": "add", "element": v})["type"] == "add_ok"
+    r = c.rpc("n0", {"type": "read"})
+    assert r["type"] == "read_ok" and r["value"] == [5, 9] and "messages" not in r
+    net.sim.run(net.sim.now + 120_000_000)                            # two replication periods later
+    r = c.rpc("n2", {"type": "read"})
+    assert r["value"] == [5, 9]
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_lin_kv_read_returns_value(kind):
+    # demo/python/raft.py:158-192: read_ok {value}; workload/lin_kv.clj:12-38
+    net = _backend_for(kind, 3, O.W_RAFT)
+    nodes = ["n0", "n1", "n2"]
+    for n in nodes:
+        init_node(net, n, nodes)
+    net.sim.run(5_000_000_000)                                        # an election has happened by now
+    c = C.Client(net)
+    assert c.rpc("n1", {"type": "write", "key": 1, "value": 42})["type"] == "write_ok"
+    r = c.rpc("n2", {"type": "read", "key": 1})                       # proxied to the leader (raft.py:562-566)
+    assert r["type"] == "read_ok" and r["value"] == 42 and "messages" not in r
+    assert c.rpc("n0", {"type": "cas", "key": 1, "from": 42, "to": 43})["type"] == "cas_ok"
+    assert c.rpc("n0", {"type": "read", "key": 1})["value"] == 43
+    with pytest.raises(C.RPCError) as e:
+        c.rpc("n0", {"type": "read", "key": 7})
+    assert e.value.code == 20
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_late_reply_to_a_closed_client_and_client_churn(kind, caplog):
+    # Jepsen closes and reopens a client after every timeout (client.clj:55-59): the node's late
+    # reply goes to a name that is gone, which must not stop the network, and 300 reopenings must
+    # not exhaust the endpoint table (max_endpoints defaults to n_nodes + 256)
+    import logging
+    net = _backend_for(kind, 3, O.W_ECHO)
+    net.log_send = net.log_recv = True
+    with caplog.at_level(logging.INFO, logger="maelstrom.net"):
+        c = C.Client(net)
+        c.send({"dest": "n0", "body": {"type": "echo", "echo": "x"}})
+        c.close()                                                     # before n0 has answered
+        net.sim.run(3_000_000)
+        assert net.sim.undeliverable() == 1
+        for i in range(300):
+            c = C.Client(net)
+            assert c.rpc("n%d" % (i % 3), {"type": "echo", "echo": i})["echo"] == i
+            c.close()
+    assert any(":send" in r.getMessage() for r in caplog.records)      # net.clj:211
+    assert any(":recv" in r.getMessage() for r in caplog.records)      # net.clj:241

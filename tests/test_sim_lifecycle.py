@@ -61,7 +61,10 @@ def test_endpoint_and_node_lifecycle():
     assert g.send(c, 1, mb.body("read", msg_id=2)) == -1        # "Invalid source for message" (net.clj:172-173)
     assert L.ms_remove_endpoint(h, c) == -1                     # already gone: "No such node in network"
     c2 = g.add_endpoint("c1")
-    assert c2 == c + 1                                          # indices are never reused
+    assert c2 == c                                              # the slot of a removed client is recycled (lowest index first)
+    assert g.endpoint_index("c1") == c and g.endpoint_index("c0") == -1
+    oc = o.add_endpoint("c0"); o.remove_endpoint(oc)
+    assert o.add_endpoint("c1") == oc == c                      # same rule in the oracle
     assert L.ms_stop_nodes(h) == 0
     assert g.send(c2, 0, mb.body("read", msg_id=1)) == -1       # "Invalid dest for message" (net.clj:174-175)
 
