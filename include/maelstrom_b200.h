@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MS_ABI_VERSION 1
+#define MS_ABI_VERSION 2
 
 /* ------------------------------------------------------------------ records */
 
@@ -161,7 +161,11 @@ typedef struct ms_config {
   uint32_t threads_per_node; /* CTA size of the round kernel (0 = auto) */
   uint32_t n_shards;         /* GPUs the endpoints are sharded over (0/1 = single GPU), <= 8 */
   uint32_t shard_id;         /* this process's shard */
-  uint32_t reserved[6];      /* [0] = rounds of id history to keep (0 = default); [1] = 1: replay round batches from a CUDA graph; [2] = keys per service store / Raft KV (0 = 4096); [3] = Raft log capacity per node (0 = 4096) */
+  uint32_t reserved[6];      /* [0] = rounds of id history to keep (0 = default); [1] = 1: replay round batches from a CUDA graph; [2] = keys per service store / Raft KV (0 = 4096); [3] = Raft log capacity per node (0 = 4096); [4] = servers per Raft cluster: node_ids of a node's init = its block of g consecutive servers (0 = all servers, one cluster); [5] = pending-RPC table slots per Raft / txn node (0 = 4096) */
+  /* ABI 2.  Servers and the other endpoints (clients, hosts, services) may be sized apart: a
+   * service hears from every node, a node from a few.  0 = ring_cap / max_window. */
+  uint32_t server_ring_cap;  /* inbox ring capacity of the servers, power of two */
+  uint32_t server_max_window;/* max messages one server consumes per round */
 } ms_config;
 
 typedef struct ms_sim ms_sim;

@@ -34,7 +34,8 @@ class Config(C.Structure):
                 ("journal_discard", C.c_uint32), ("calendar_slots", C.c_uint32),
                 ("calendar_cap", C.c_uint32), ("mailbox_cap", C.c_uint32), ("inject_cap", C.c_uint32),
                 ("device", C.c_int32), ("threads_per_node", C.c_uint32), ("n_shards", C.c_uint32),
-                ("shard_id", C.c_uint32), ("reserved", C.c_uint32 * 6)]
+                ("shard_id", C.c_uint32), ("reserved", C.c_uint32 * 6),
+                ("server_ring_cap", C.c_uint32), ("server_max_window", C.c_uint32)]
 
 
 class Body(C.Structure):

@@ -98,9 +98,9 @@ struct Params {
   uint32_t* limit;           // snapshot of tail at the start of the round
   uint32_t* head;            // previous snapshot: window is [head, limit)
   uint64_t* ep_born;         // next-message-id when the endpoint slot was (re)registered: wheel records with a smaller id are not for it
-  uint4*    ring;            // n_ep * ring_cap * 3 vectors (48-B records)
-  uint32_t  ring_cap, ring_mask;
-  uint32_t  n_ep, n_servers, n_inj_tickets, max_window;
+  uint4*    ring;            // 48-B records (3 vectors): n_servers rings of ring_cap_s, then rings of ring_cap
+  uint32_t  ring_cap, ring_cap_s;      // per endpoint: others / servers (powers of two)
+  uint32_t  n_ep, n_servers, n_inj_tickets, max_window, max_window_s;
   // per-round history (ring of `hist` rows, stride t_max entries)
   RoundMeta* rmeta;
   uint32_t* rt_em;           // emissions per ticket, exclusive prefix once the round is committed
@@ -188,24 +188,27 @@ struct Params {
   uint4*    rf_log;          // [n_servers][rf_log_cap] entries, 2 vectors each
   uint32_t* rf_kv_val;       // [n_servers][rf_n_keys] KVStore (raft.py:151-192)
   uint8_t*  rf_kv_has;
-  int32_t*  rf_next;         // [n_servers][n_servers] next_index / match_index (leader state)
+  int32_t*  rf_next;         // [n_servers][rf_gmax] next_index / match_index by cluster member (leader state)
   int32_t*  rf_match;
-  int32_t*  rf_scratch;      // [n_servers][n_servers] median scratch
-  uint4*    rf_cb;           // [n_servers][kRaftCallbacks] pending RPC closures, 2 vectors each
-  uint32_t* rf_votes;        // [n_servers][ceil(n_servers / 32)]
+  int32_t*  rf_scratch;      // [n_servers][rf_gmax] median scratch
+  uint4*    rf_cb;           // [n_servers][rf_cb_mask + 1] pending RPC closures, 2 vectors each
+  uint32_t* rf_votes;        // [n_servers][rf_vote_words] by cluster member
   uint4*    rf_stage;        // [n_servers][rf_stage_cap] emissions of the node's step, 3 vectors each
   uint4*    rf_heap;         // append_entries payloads: ring of vectors
   unsigned long long* rf_heap_cursor;
   uint64_t* rf_ext_off;      // [n_servers][kRaftExt] heap offset of the sender's k-th append_entries
   uint32_t* rf_ext_tag;      // [n_servers][kRaftExt] k
   uint32_t  rf_log_cap, rf_n_keys, rf_stage_cap, rf_heap_mask, rf_vote_words;
+  uint32_t  rf_group;        // servers per Raft cluster (0 = one cluster of all servers)
+  uint32_t  rf_gmax;         // row stride of rf_next / rf_match / rf_scratch = largest cluster
+  uint32_t  rf_cb_mask;      // pending-RPC table slots per node - 1 (power of two)
   // append_entries payloads of every shard (index = shard): read where the sender wrote them
   uint4*    rf_heap_sh[8];
   uint64_t* rf_ext_off_sh[8];
   uint32_t* rf_ext_tag_sh[8];
 };
 
-constexpr uint32_t kRaftCallbacks = 4096;       // pending-RPC table slots per node (oracle: same constant)
+constexpr uint32_t kRaftCallbacks = 4096;       // default pending-RPC table slots per node (ms_config.reserved[5]; oracle: same)
 constexpr uint32_t kRaftExt = 1024;             // append_entries payload handles kept per sender
 constexpr int64_t  kElectionTimeoutNs = 2000000000;   // raft.py:199
 constexpr int64_t  kHeartbeatNs = 1000000000;         // raft.py:200
@@ -218,7 +221,8 @@ struct RaftDev {
   int32_t  voted_for, leader;          // -1 = none
   uint32_t commit_index, last_applied;
   int64_t  election_deadline, step_down_deadline, last_replication;
-  uint32_t next_msg_id, log_size, appends, n_votes, kv_size, pad;
+  uint32_t next_msg_id, log_size, appends, n_votes, kv_size;
+  uint32_t busy;                       // leader with a follower behind its log (or a next_index <= 0): see rf_timer_due
 };
 
 constexpr uint32_t kSeqBuffer = 32;             // (sequential 32 ...), service.clj:206-208

@@ -50,10 +50,17 @@ static uint32_t pow2_at_least(uint32_t x) {
   return p;
 }
 
+// rows of per-round history: 24 B per (round, ticket), kept under ~2 GB; < 2^15 (entry tags)
+static uint32_t history_rows(uint32_t wanted, uint32_t t_max) {
+  uint32_t hist = wanted ? std::min<uint32_t>(pow2_at_least(wanted), 16384u) : 4096;
+  while (hist > 64 && (uint64_t)hist * t_max * 24 > (2ull << 30)) hist >>= 1;
+  return hist;
+}
+
 static const char* dev_error_text(uint32_t code) {
   switch (code) {
-    case E_RING_OVERFLOW: return "inbox ring overflow (raise ms_config.ring_cap) at endpoint";
-    case E_WINDOW_OVERFLOW: return "per-round window exceeds ms_config.max_window at endpoint";
+    case E_RING_OVERFLOW: return "inbox ring overflow (raise ms_config.ring_cap / server_ring_cap) at endpoint";
+    case E_WINDOW_OVERFLOW: return "per-round window exceeds ms_config.max_window / server_max_window at endpoint";
     case E_JOURNAL_OVERFLOW: return "journal ring overflow (drain more often or raise journal_cap_log2)";
     case E_INVALID_DEST: return "Invalid dest for message (net.clj:174): endpoint";
     case E_HISTORY: return "message older than the round history (raise ms_config.reserved[0] = history rounds): round";
@@ -440,6 +447,13 @@ static int build_sim(ms_sim* s, const ms_config* in) {
   // 25 B of dynamic shared memory per window slot + ~3 KB static, 227 KB per CTA on sm_100a
   if (c.max_window > 8192) { set_err("max_window must be <= 8192 (25 B of shared memory per slot, 227 KB per CTA)"); return MS_ERR_ARG; }
   if (c.max_window > c.ring_cap) c.max_window = c.ring_cap;
+  c.server_ring_cap = c.server_ring_cap ? pow2_at_least(c.server_ring_cap) : c.ring_cap;
+  c.server_max_window = c.server_max_window ? pow2_at_least(c.server_max_window) : std::min(c.max_window, c.server_ring_cap);
+  if (c.server_max_window > c.server_ring_cap) c.server_max_window = c.server_ring_cap;
+  if (c.server_max_window > c.max_window) {   // the round kernel's size classes are cut for max_window
+    set_err("server_max_window must not exceed max_window");
+    return MS_ERR_ARG;
+  }
   if (!c.journal_cap_log2) c.journal_cap_log2 = 22;
   if (c.journal_level > 2) c.journal_level = 2;
   if (!c.mailbox_cap) c.mailbox_cap = 1u << 16;
@@ -449,6 +463,11 @@ static int build_sim(ms_sim* s, const ms_config* in) {
   if (s->use_calendar) {
     c.calendar_slots = pow2_at_least(c.calendar_slots ? c.calendar_slots
                                                       : std::min<uint32_t>(16384u, std::max<uint32_t>(64u, 32u * c.latency_mean_ms)));
+    // a record's order key is turned into its dense id when its slot first comes up, i.e. within
+    // calendar_slots ticks of the send: keep that inside the round history (longer latencies
+    // simply wait more turns, so the wheel's span is a tuning knob, not a limit)
+    const uint32_t hist = history_rows(c.reserved[0], c.max_endpoints + 8u);
+    while (c.calendar_slots > 4 && c.calendar_slots > hist / 4) c.calendar_slots >>= 1;
     if (!c.calendar_cap) c.calendar_cap = 1u << 16;
   }
   if (c.n_shards == 0) c.n_shards = 1;
@@ -494,24 +513,24 @@ static int build_sim(ms_sim* s, const ms_config* in) {
   if ((rc = s->dalloc(&P.ep_born, M))) return rc;
   {
     void* ptr = nullptr;
-    CK(cudaMalloc(&ptr, (size_t)M * c.ring_cap * 48));
+    CK(cudaMalloc(&ptr, ((size_t)c.n_nodes * c.server_ring_cap + (size_t)(M - c.n_nodes) * c.ring_cap) * 48));
     s->allocs.push_back(ptr);
     P.ring = (uint4*)ptr;
   }
   P.ring_cap = c.ring_cap;
-  P.ring_mask = c.ring_cap - 1;
+  P.ring_cap_s = c.server_ring_cap;
   P.n_servers = c.n_nodes;
   P.n_ep = c.n_nodes;
   P.n_inj_tickets = 8;
   P.max_window = c.max_window;
+  P.max_window_s = c.server_max_window;
   s->use_graph = c.reserved[1] == 1;
   P.n_shards = c.n_shards;
   P.shard_id = c.shard_id;
   {
     // per-round history: 16 B per (round, ticket); keep it under ~1 GB
     P.t_max = M + P.n_inj_tickets;
-    uint32_t hist = c.reserved[0] ? std::min<uint32_t>(pow2_at_least(c.reserved[0]), 16384u) : 4096;   // < 2^15: entry tags
-    while (hist > 64 && (uint64_t)hist * P.t_max * 24 > (1ull << 30)) hist >>= 1;
+    const uint32_t hist = history_rows(c.reserved[0], P.t_max);
     P.hist = hist;
     P.hist_mask = hist - 1;
     if ((rc = s->dalloc(&P.rmeta, hist))) return rc;
@@ -572,8 +591,9 @@ static int build_sim(ms_sim* s, const ms_config* in) {
     // the sequential step (csrc/ms_raft.cuh)
     // (nothing here is read across nodes: sharded runs need no extra mapping)
     const size_t N = c.n_nodes;
-    P.rf_stage_cap = c.max_window + 16u;
-    if ((rc = s->dalloc(&P.rf_node, N)) || (rc = s->dalloc(&P.rf_cb, N * kRaftCallbacks * 2)) ||
+    P.rf_stage_cap = c.server_max_window + 16u;
+    P.rf_cb_mask = pow2_at_least(c.reserved[5] ? c.reserved[5] : kRaftCallbacks) - 1u;
+    if ((rc = s->dalloc(&P.rf_node, N)) || (rc = s->dalloc(&P.rf_cb, N * ((size_t)P.rf_cb_mask + 1) * 2)) ||
         (rc = s->dalloc(&P.rf_stage, N * P.rf_stage_cap * 3)))
       return rc;
   }
@@ -583,14 +603,22 @@ static int build_sim(ms_sim* s, const ms_config* in) {
     const size_t N = c.n_nodes;
     P.rf_n_keys = c.reserved[2] ? c.reserved[2] : 4096u;
     P.rf_log_cap = c.reserved[3] ? c.reserved[3] : 4096u;
-    P.rf_stage_cap = c.max_window + 2u * c.n_nodes + P.rf_log_cap + 16u;
-    P.rf_vote_words = (c.n_nodes + 31u) / 32u;
-    const uint32_t heap_words = pow2_at_least(std::max<uint32_t>(1u << 16, 8u * P.rf_log_cap));
+    // reserved[4] = g: independent Raft clusters of g consecutive servers (0 = one cluster of all)
+    P.rf_group = (c.reserved[4] && c.reserved[4] < c.n_nodes) ? c.reserved[4] : 0u;
+    P.rf_gmax = P.rf_group ? P.rf_group : c.n_nodes;
+    P.rf_cb_mask = pow2_at_least(c.reserved[5] ? c.reserved[5] : kRaftCallbacks) - 1u;
+    P.rf_stage_cap = c.server_max_window + 2u * P.rf_gmax + P.rf_log_cap + 16u;
+    P.rf_vote_words = (P.rf_gmax + 31u) / 32u;
+    // append_entries payloads live in one ring heap per shard until they are read: room for a
+    // heartbeat wave of every cluster, a few times over
+    const uint64_t heap_want = std::max<uint64_t>(std::max<uint64_t>(1u << 16, 8ull * P.rf_log_cap), 64ull * c.n_nodes);
+    if (heap_want > (1ull << 30)) { set_err("Raft payload heap too large"); return MS_ERR_ARG; }
+    const uint32_t heap_words = pow2_at_least((uint32_t)heap_want);
     P.rf_heap_mask = heap_words - 1u;
     if ((rc = s->dalloc(&P.rf_node, N)) || (rc = s->dalloc(&P.rf_log, N * P.rf_log_cap * 2)) ||
         (rc = s->dalloc(&P.rf_kv_val, N * P.rf_n_keys)) || (rc = s->dalloc(&P.rf_kv_has, N * P.rf_n_keys)) ||
-        (rc = s->dalloc(&P.rf_next, N * N)) || (rc = s->dalloc(&P.rf_match, N * N)) ||
-        (rc = s->dalloc(&P.rf_scratch, N * N)) || (rc = s->dalloc(&P.rf_cb, N * kRaftCallbacks * 2)) ||
+        (rc = s->dalloc(&P.rf_next, N * P.rf_gmax)) || (rc = s->dalloc(&P.rf_match, N * P.rf_gmax)) ||
+        (rc = s->dalloc(&P.rf_scratch, N * P.rf_gmax)) || (rc = s->dalloc(&P.rf_cb, N * ((size_t)P.rf_cb_mask + 1) * 2)) ||
         (rc = s->dalloc(&P.rf_votes, N * P.rf_vote_words)) || (rc = s->dalloc(&P.rf_stage, N * P.rf_stage_cap * 3)) ||
         (rc = s->dalloc(&P.rf_heap, (size_t)heap_words)) || (rc = s->dalloc(&P.rf_heap_cursor, 1)) ||
         (rc = s->dalloc(&P.rf_ext_off, N * kRaftExt + (N * kRaftExt + 1) / 2)))   // offsets, then the u32 tags
@@ -611,7 +639,11 @@ static int build_sim(ms_sim* s, const ms_config* in) {
     // replicate_full payloads: a snapshot stays resident while its messages can be in flight,
     // i.e. at most calendar_slots ticks; one run every gset_interval_ms (g_set.rb:34)
     P.gs_interval_ms = c.gset_interval_ms;
-    P.gs_slots = pow2_at_least((s->use_calendar ? c.calendar_slots / c.gset_interval_ms : 0u) + 2u);
+    // (the exponential law is unbounded: 48 means = a tail of e^-48; beyond that, e.g. after slow!, a
+    // replicate_full that outlives its snapshot row is reported as E_SNAPSHOT)
+    const uint32_t span_ms = !s->use_calendar ? 0u
+        : std::max<uint32_t>(c.calendar_slots, c.latency_dist == MS_DIST_EXPONENTIAL ? 48u * c.latency_mean_ms : 2u * c.latency_mean_ms);
+    P.gs_slots = std::min<uint32_t>(pow2_at_least(span_ms / c.gset_interval_ms + 2u), 1024u);
     const size_t rows = (size_t)c.n_nodes * P.gs_slots;
     if ((rc = s->dalloc(&P.gs_init, c.n_nodes))) return rc;
     if ((rc = s->dalloc(&P.gs_next_fire, c.n_nodes))) return rc;
@@ -1141,7 +1173,7 @@ int ms_shard_handles(ms_sim* s, void* blob_out) {
   memset(&b, 0, sizeof b);
   b.magic = 0x4253534Du;
   b.shard_id = s->P.shard_id; b.n_shards = s->P.n_shards; b.t_max = s->P.t_max;
-  b.max_endpoints = s->cfg.max_endpoints; b.ring_cap = s->P.ring_cap; b.hist = s->P.hist;
+  b.max_endpoints = s->cfg.max_endpoints; b.ring_cap = s->P.ring_cap ^ (s->P.ring_cap_s << 1); b.hist = s->P.hist;
   CK(cudaIpcGetMemHandle(&b.ring, s->P.ring));
   CK(cudaIpcGetMemHandle(&b.tail, s->P.tail));
   CK(cudaIpcGetMemHandle(&b.head, s->P.head));
@@ -1167,7 +1199,7 @@ int ms_shard_connect(ms_sim* s, uint32_t peer, const void* blob) {
   ShardBlob b;
   memcpy(&b, blob, sizeof b);
   if (b.magic != 0x4253534Du || b.shard_id != peer || peer >= s->P.n_shards || b.n_shards != s->P.n_shards ||
-      b.t_max != s->P.t_max || b.max_endpoints != s->cfg.max_endpoints || b.ring_cap != s->P.ring_cap ||
+      b.t_max != s->P.t_max || b.max_endpoints != s->cfg.max_endpoints || b.ring_cap != (s->P.ring_cap ^ (s->P.ring_cap_s << 1)) ||
       b.hist != s->P.hist) {
     set_err("ms_shard_connect: peer blob does not match this simulation's configuration");
     return MS_ERR_ARG;

@@ -119,6 +119,17 @@ __device__ __forceinline__ Rec rec_unpack(uint4 a, uint4 b, uint4 c) {
   return r;
 }
 
+// Inbox ring of endpoint e: servers have rings of ring_cap_s records, every other endpoint
+// (clients, hosts, services -- a service hears from every node) of ring_cap records.
+__device__ __forceinline__ uint32_t ring_cap_of(const Params& p, uint32_t e) { return e < p.n_servers ? p.ring_cap_s : p.ring_cap; }
+__device__ __forceinline__ size_t ring_base(const Params& p, uint32_t e) {
+  return e < p.n_servers ? (size_t)e * p.ring_cap_s
+                         : (size_t)p.n_servers * p.ring_cap_s + (size_t)(e - p.n_servers) * p.ring_cap;
+}
+__device__ __forceinline__ uint4* ring_slot(const Params& p, uint4* ring, uint32_t e, uint32_t pos) {
+  return ring + (ring_base(p, e) + (pos & (ring_cap_of(p, e) - 1u))) * 3;
+}
+
 // dense id of (round, ticket, idx): id_base[round] + emit_prefix[round][ticket] + idx
 __device__ __forceinline__ uint64_t dense_base(const Params& p, DevState* st, uint64_t round, uint32_t ticket) {
   if (ticket == kResolvedTicket) return round << 32;   // the record already carries its id (k_release)
@@ -310,7 +321,7 @@ __device__ __forceinline__ void emit_one(const Params& p, DevState* st, const Ne
       cx.c_zero++;
       if (has_direct) {
         uint4* ring_o = p.ring_sh[owner_of(r.dest, p.n_servers, p.n_shards)];
-        rec_store(ring_o + ((size_t)r.dest * p.ring_cap + (direct_pos & p.ring_mask)) * 3, r);
+        rec_store(ring_slot(p, ring_o, r.dest, direct_pos), r);
       } else {
         push = true;
       }
@@ -341,15 +352,17 @@ __device__ __forceinline__ void emit_one(const Params& p, DevState* st, const Ne
   base = __shfl_sync(FULL, base, leader);
   if (push) {
     const uint32_t pos = base + rank;
-    if ((uint32_t)(pos - p.head_sh[o][r.dest]) >= p.ring_cap) {
+    if ((uint32_t)(pos - p.head_sh[o][r.dest]) >= ring_cap_of(p, r.dest)) {
       latch_error(st, E_RING_OVERFLOW, r.dest);
     } else {
-      rec_store(p.ring_sh[o] + ((size_t)r.dest * p.ring_cap + (pos & p.ring_mask)) * 3, r);
+      rec_store(ring_slot(p, p.ring_sh[o], r.dest, pos), r);
     }
   }
 }
 
 __global__ void k_set_bit(uint32_t* words, size_t word, uint32_t bit) { atomicOr(words + word, 1u << bit); }
+
+#include "ms_raft.cuh"
 
 // ------------------------------------------------------------------ k_barrier (sharded runs)
 // Cross-GPU barrier over NVLink peer memory: every shard stores the epoch into its slot of
@@ -403,10 +416,10 @@ __global__ void k_snapshot(Params p) {
     p.limit[e] = l;
     const uint32_t n = ((p.kind[e] & kRemoved)) ? 0u : l - h;
     // g-set: a node whose periodic replication task is due emits even with an empty window
-    // Raft: a node's election / heartbeat / commit actions are evaluated every round
+    // Raft: a node whose election / step-down / replication timers are due acts on an empty window too
     const bool timer_due = e < p.n_servers && p.kind[e] == MS_KIND_SERVER &&
                            ((p.workload == MS_W_GSET && p.gs_init[e] && st->now >= p.gs_next_fire[e]) ||
-                            p.workload == MS_W_RAFT);
+                            (p.workload == MS_W_RAFT && rf_timer_due(p.rf_node[e], st->now)));
     if (n == 0 && !timer_due) {
       // nothing to receive, hence nothing to emit: the ticket is finished right here
       const uint32_t t = p.n_inj_tickets + e;
@@ -514,10 +527,10 @@ __global__ void k_release(Params p) {
     if (valid) {
       const uint32_t pos = base + rank;
       // the previous window is fully consumed by now: the whole ring past `head` is writable
-      if ((uint32_t)(pos - p.head_sh[o][dest]) >= p.ring_cap) {
+      if ((uint32_t)(pos - p.head_sh[o][dest]) >= ring_cap_of(p, dest)) {
         latch_error(st, E_RING_OVERFLOW, dest);
       } else {
-        uint4* dst = p.ring_sh[o] + ((size_t)dest * p.ring_cap + (pos & p.ring_mask)) * 3;
+        uint4* dst = ring_slot(p, p.ring_sh[o], dest, pos);
         st_v4(dst, a); st_v4(dst + 1, b); st_v4(dst + 2, c);
       }
     }
@@ -959,7 +972,6 @@ __device__ void service_handle(const Params& p, uint32_t svc, const SvReq& q, ui
   }
 }
 
-#include "ms_raft.cuh"
 
 // WL = node-program families compiled in: bit 0 g-set, bit 2 Raft (else echo / broadcast), bit 1 services.
 template <int CLS, int WL>
@@ -1108,11 +1120,12 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
     const uint8_t kind = p.kind[e];
     const uint32_t head = p.head[e];
     uint32_t n = ((kind & kRemoved)) ? 0u : (p.limit[e] - head);
-    if (n > cap || n > p.max_window) {
+    if (n > cap || n > (e < p.n_servers ? p.max_window_s : p.max_window)) {
       if (tid == 0) latch_error(st, E_WINDOW_OVERFLOW, e);
       n = 0;
     }
-    const uint4* myring = p.ring + (size_t)e * p.ring_cap * 3;
+    const uint4* myring = p.ring + ring_base(p, e) * 3;
+    const uint32_t my_mask = ring_cap_of(p, e) - 1u;
     const bool is_server = (kind == MS_KIND_SERVER);
     const bool bcast = !GS && is_server && p.workload == MS_W_BROADCAST;
     // g-set periodic task (g_set.rb:34-39), evaluated before the node's receives: when due, the
@@ -1142,7 +1155,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
         for (int q = 0; q < 2; q++) {
           const int i = base + q * nt + tid;
           if (i < (int)n) {
-            const uint4* rp = myring + (size_t)((head + i) & p.ring_mask) * 3;
+            const uint4* rp = myring + (size_t)((head + i) & my_mask) * 3;
             a[q] = rp[0]; b[q] = rp[1]; c[q] = rp[2];
           }
         }
@@ -1370,15 +1383,16 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
       if (is_server) {
         if (tid == 0) {
           RaftCtx c{p, st, e, now, round, p.rf_node + e, p.rf_log + (size_t)e * p.rf_log_cap * 2,
-                    p.rf_cb + (size_t)e * kRaftCallbacks * 2, p.rf_stage + (size_t)e * p.rf_stage_cap * 3, 0u, 0u};
+                    p.rf_cb + (size_t)e * (p.rf_cb_mask + 1u) * 2, p.rf_stage + (size_t)e * p.rf_stage_cap * 3, 0u, 0u, 0u, 0u};
+          rf_group_of(p, e, c.gbase, c.gn);
           for (uint32_t pos = 0; pos < n; pos++) {
             const uint32_t i = ord[pos];
             if (!(vals[i] & V_RECV)) continue;
-            const uint4* rp = myring + (size_t)((head + i) & p.ring_mask) * 3;
+            const uint4* rp = myring + (size_t)((head + i) & my_mask) * 3;
             if (p.workload == MS_W_RAFT) rf_handle(c, rec_unpack(rp[0], rp[1], rp[2]));
             else txn_handle(c, rec_unpack(rp[0], rp[1], rp[2]));
           }
-          if (p.workload == MS_W_RAFT) rf_actions(c);
+          if (p.workload == MS_W_RAFT) { rf_actions(c); rf_note_busy(c); }
           s_misc[2] = c.n_stage;
         }
         __syncthreads();
@@ -1389,6 +1403,19 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
       // ---- service endpoint: requests are handled one at a time in dequeue order (service.clj:147-156,
       //      245-263) by one thread; the reply is parked in vals[] / keyB[] for the emit phase
       if (kind == MS_KIND_SERVICE) {
+        // the request fields the sequential walk needs, staged in sorted order by all threads (the
+        // ordering keys are dead by now): p1 in reg1, the key in tab (as u32), type | flags << 8 in meta
+        uint32_t* skey = reinterpret_cast<uint32_t*>(tab);
+        for (uint32_t pos = tid; pos < n; pos += nt) {
+          const uint32_t i = ord[pos];
+          const uint4* rp = myring + (size_t)((head + i) & my_mask) * 3;
+          const uint4 vc = rp[2];
+          reg1[pos] = (uint64_t)vc.z | ((uint64_t)vc.w << 32);
+          skey[pos] = vc.y;
+          const uint32_t ty = vc.x & 0xFFFFu;                       // types the device does not know (>= 256) stay unknown
+          meta[i] = (uint16_t)((ty < 0xFFu ? ty : 0xFFu) | ((vc.x >> 8) & 0xFF00u));
+        }
+        __syncthreads();
         if (tid == 0) {
           uint32_t svc = 0;
           while (svc < 4 && p.sv_ep[svc] != e) svc++;
@@ -1396,11 +1423,12 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
           for (uint32_t pos = 0; pos < n && svc < 4; pos++) {
             const uint32_t i = ord[pos];
             if (!(vals[i] & V_RECV)) continue;
-            const uint4* rp = myring + (size_t)((head + i) & p.ring_mask) * 3;
-            const uint4 vb = rp[1], vc = rp[2];
             SvReq q;
-            q.src = vb.x; q.type = vc.x & 0xFFFFu; q.flags = vc.x >> 16; q.key = vc.y;
-            q.p1 = (uint64_t)vc.z | ((uint64_t)vc.w << 32);
+            q.type = meta[i] & 0xFFu; q.flags = meta[i] >> 8; q.key = skey[pos];
+            q.p1 = reg1[pos];
+            q.src = 0;
+            if (svc == MS_SVC_SEQ_KV)                               // per-client view (service.clj:162-166)
+              q.src = (myring + (size_t)((head + i) & my_mask) * 3)[1].x;
             const bool keyed = q.type == MS_T_READ || q.type == MS_T_WRITE || q.type == MS_T_CAS;
             if (svc != MS_SVC_LIN_TSO && keyed && q.key >= p.sv_n_keys) { latch_error(st, E_VALUE_RANGE, q.key); continue; }
             uint32_t x[4] = {0, 0, 0, 0};
@@ -1594,7 +1622,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
       if (total) {
         const uint32_t o = owner_of(nb, p.n_servers, p.n_shards);
         base = atomicAdd(&p.tail_sh[o][nb], total);
-        if ((uint32_t)(base + total - p.head_sh[o][nb]) > p.ring_cap) latch_error(st, E_RING_OVERFLOW, nb);
+        if ((uint32_t)(base + total - p.head_sh[o][nb]) > ring_cap_of(p, nb)) latch_error(st, E_RING_OVERFLOW, nb);
       }
       s_nbbase[tid] = base;
     }
@@ -1621,7 +1649,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
       const uint32_t mt = meta[i];
       const uint32_t sslot = mt & M_SRCSLOT;
       if (full_recv || !nb_smem || sslot == 0) {
-        const uint4* rp = myring + (size_t)((head + i) & p.ring_mask) * 3;
+        const uint4* rp = myring + (size_t)((head + i) & my_mask) * 3;
         Rec m = rec_unpack(rp[0], rp[1], rp[2]);
         const uint64_t id = (use_blocks ? s_bbase[blk[pos]] : dense_base(p, st, m.round, m.ticket)) + m.idx;
         journal_raw(p, cx.chunk + k, id, true, m);
@@ -1719,7 +1747,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
             has_direct = true;
           }
         } else {
-          const uint4* rp = myring + (size_t)((head + i) & p.ring_mask) * 3;
+          const uint4* rp = myring + (size_t)((head + i) & my_mask) * 3;
           const uint4 vb = rp[1], vc = rp[2];
           MsgView w;
           w.src = vb.x; w.msg_id = vb.z; w.tf = vc.x; w.p0 = vc.y;

@@ -21,7 +21,17 @@ struct RaftCtx {
   uint4* stage;
   uint32_t n_stage;
   uint32_t draws;
+  // the node's Raft cluster = node_ids of its init (raft.py:447-459): servers [gbase, gbase + gn).
+  // One cluster of all servers by default; ms_config.reserved[4] = g runs independent clusters of g
+  // consecutive servers (the leader tables and vote bitmaps are per cluster member).
+  uint32_t gbase, gn;
 };
+
+__device__ __forceinline__ void rf_group_of(const Params& p, uint32_t e, uint32_t& gbase, uint32_t& gn) {
+  const uint32_t G = p.rf_group ? p.rf_group : p.n_servers;
+  gbase = (e / G) * G;
+  gn = min(G, p.n_servers - gbase);
+}
 
 struct RaftEntry {     // {'term': t, 'op': body + 'client'}  (raft.py:118-121,553-556)
   uint32_t term, tf, key, client;
@@ -93,7 +103,7 @@ __device__ __forceinline__ void rf_maybe_step_down(RaftCtx& c, uint32_t remote_t
 __device__ __forceinline__ void rf_rpc(RaftCtx& c, uint32_t dest, uint32_t type, uint32_t p0, uint64_t p1,
                                        uint32_t kind, uint32_t cb_node, int32_t cb_ni, uint32_t cb_n) {
   const uint32_t id = c.r->next_msg_id++;
-  uint4* slot = c.cb + 2 * (size_t)(id % kRaftCallbacks);
+  uint4* slot = c.cb + 2 * (size_t)(id & c.p.rf_cb_mask);
   slot[0] = make_uint4(id, kind, c.r->term, cb_node);
   slot[1] = make_uint4((uint32_t)cb_ni, cb_n, 0u, 0u);
   Rec r;
@@ -114,10 +124,10 @@ __device__ void rf_become_candidate(RaftCtx& c) {                               
   rf_reset_step_down_deadline(c);
   uint32_t* votes = c.p.rf_votes + (size_t)c.e * c.p.rf_vote_words;
   for (uint32_t w = 0; w < c.p.rf_vote_words; w++) votes[w] = 0;
-  votes[c.e >> 5] |= 1u << (c.e & 31);
+  votes[(c.e - c.gbase) >> 5] |= 1u << ((c.e - c.gbase) & 31);
   r->n_votes = 1;
   const uint64_t last = (uint64_t)r->log_size | ((uint64_t)rf_log_term(c, r->log_size) << 32);
-  for (uint32_t n = 0; n < c.p.n_servers; n++)                                    // brpc, :243-246
+  for (uint32_t n = c.gbase; n < c.gbase + c.gn; n++)                             // brpc, :243-246
     if (n != c.e) rf_rpc(c, n, MS_T_REQUEST_VOTE, r->term, last, 1u, 0u, 0, 0u);
 }
 
@@ -126,9 +136,9 @@ __device__ void rf_become_leader(RaftCtx& c) {                                  
   r->state = RAFT_LEADER;
   r->leader = -1;
   r->last_replication = 0;
-  int32_t* next = c.p.rf_next + (size_t)c.e * c.p.n_servers;
-  int32_t* match = c.p.rf_match + (size_t)c.e * c.p.n_servers;
-  for (uint32_t n = 0; n < c.p.n_servers; n++) { next[n] = (int32_t)r->log_size + 1; match[n] = 0; }
+  int32_t* next = c.p.rf_next + (size_t)c.e * c.p.rf_gmax;
+  int32_t* match = c.p.rf_match + (size_t)c.e * c.p.rf_gmax;
+  for (uint32_t n = 0; n < c.gn; n++) { next[n] = (int32_t)r->log_size + 1; match[n] = 0; }
   rf_reset_step_down_deadline(c);
 }
 
@@ -138,7 +148,7 @@ __device__ void rf_handle(RaftCtx& c, const Rec& m) {
   RaftDev* r = c.r;
   const uint32_t type = m.tf & 0xFFFFu, flags = m.tf >> 16;
   if (flags & MS_F_REPLY) {                                                       // :97-101
-    uint4* slot = c.cb + 2 * (size_t)(m.in_reply_to % kRaftCallbacks);
+    uint4* slot = c.cb + 2 * (size_t)(m.in_reply_to & c.p.rf_cb_mask);
     const uint4 s0 = slot[0], s1 = slot[1];
     if (s0.y == 0 || s0.x != m.in_reply_to) return;                               // KeyError
     slot[0] = make_uint4(0u, 0u, 0u, 0u);                                         // del self.callbacks[m]
@@ -146,24 +156,28 @@ __device__ void rf_handle(RaftCtx& c, const Rec& m) {
     if (s0.y == 1) {                                                              // request_votes' handle, :282-303
       rf_reset_step_down_deadline(c);
       rf_maybe_step_down(c, m.p0);
-      if (r->state == RAFT_CANDIDATE && r->term == cb_term && m.p0 == r->term && m.p1 != 0 && m.src < c.p.n_servers) {
+      if (r->state == RAFT_CANDIDATE && r->term == cb_term && m.p0 == r->term && m.p1 != 0 &&
+          m.src >= c.gbase && m.src < c.gbase + c.gn) {
         uint32_t* votes = c.p.rf_votes + (size_t)c.e * c.p.rf_vote_words;
-        const uint32_t bit = 1u << (m.src & 31);
-        if (!(votes[m.src >> 5] & bit)) { votes[m.src >> 5] |= bit; r->n_votes++; }
-        if (c.p.n_servers / 2 + 1 <= r->n_votes) rf_become_leader(c);
+        const uint32_t v = m.src - c.gbase, bit = 1u << (v & 31);
+        if (!(votes[v >> 5] & bit)) { votes[v >> 5] |= bit; r->n_votes++; }
+        if (c.gn / 2 + 1 <= r->n_votes) rf_become_leader(c);
       }
     } else {                                                                      // replicate_log's handler, :413-426
       rf_maybe_step_down(c, m.p0);
       if (r->state == RAFT_LEADER && cb_term == r->term) {
         rf_reset_step_down_deadline(c);
-        int32_t* next = c.p.rf_next + (size_t)c.e * c.p.n_servers;
-        int32_t* match = c.p.rf_match + (size_t)c.e * c.p.n_servers;
+        int32_t* next = c.p.rf_next + (size_t)c.e * c.p.rf_gmax;
+        int32_t* match = c.p.rf_match + (size_t)c.e * c.p.rf_gmax;
         const int32_t ni = (int32_t)s1.x, ne = (int32_t)s1.y;
-        if (m.p1 != 0) {
-          if (next[cb_node] < ni + ne) next[cb_node] = ni + ne;
-          if (match[cb_node] < ni - 1 + ne) match[cb_node] = ni - 1 + ne;
-        } else {
-          next[cb_node] -= 1;
+        const uint32_t cn = cb_node - c.gbase;                                  // member index of the closure's node
+        if (cn < c.gn) {
+          if (m.p1 != 0) {
+            if (next[cn] < ni + ne) next[cn] = ni + ne;
+            if (match[cn] < ni - 1 + ne) match[cn] = ni - 1 + ne;
+          } else {
+            next[cn] -= 1;
+          }
         }
       }
     }
@@ -280,7 +294,7 @@ __device__ Rec rf_apply(RaftCtx& c, const RaftEntry& op) {
 // priority order; time is frozen inside a round, so each is idle again right after it ran.
 __device__ void rf_actions(RaftCtx& c) {
   RaftDev* r = c.r;
-  const uint32_t N = c.p.n_servers;
+  const uint32_t N = c.gn;                                                                // cluster size
   if (r->state == RAFT_LEADER && r->step_down_deadline < c.now) rf_become_follower(c);   // :371-376
   {                                                                                       // replicate_log, :387-441
     const int64_t elapsed = c.now - r->last_replication;
@@ -289,10 +303,10 @@ __device__ void rf_actions(RaftCtx& c) {
     uint32_t last_node = 0, last_n = 0;
     int32_t last_ni = 0;
     if (r->state == RAFT_LEADER && kMinReplicationNs < elapsed) {
-      const int32_t* next = c.p.rf_next + (size_t)c.e * N;
-      for (uint32_t n = 0; n < N; n++) {
+      const int32_t* next = c.p.rf_next + (size_t)c.e * c.p.rf_gmax;
+      for (uint32_t n = c.gbase; n < c.gbase + N; n++) {
         if (n == c.e) continue;
-        const int32_t ni = next[n];
+        const int32_t ni = next[n - c.gbase];
         if (ni <= 0) { aborted = true; break; }                                           // from_index raises (:147-148): the
                                                                                           // iteration ends, later ones raise again
         const int32_t n_entries = (int32_t)r->log_size - ni + 1 > 0 ? (int32_t)r->log_size - ni + 1 : 0;
@@ -323,7 +337,7 @@ __device__ void rf_actions(RaftCtx& c) {
     // frame of this replicate_log call when the reply arrives, i.e. the values of the LAST node the
     // pass sent to, for every RPC of the pass (pinned by tests/test_raft_reference.py)
     for (uint32_t id = first_rpc; id != r->next_msg_id; id++) {
-      uint4* slot = c.cb + 2 * (size_t)(id % kRaftCallbacks);
+      uint4* slot = c.cb + 2 * (size_t)(id & c.p.rf_cb_mask);
       if (slot[0].y == 2u && slot[0].x == id) {
         slot[0].w = last_node;
         slot[1] = make_uint4((uint32_t)last_ni, last_n, 0u, 0u);
@@ -337,10 +351,10 @@ __device__ void rf_actions(RaftCtx& c) {
     else rf_reset_election_deadline(c);
   }
   if (r->state == RAFT_LEADER) {                                                          // advance_commit_index, :378-385
-    int32_t* xs = c.p.rf_scratch + (size_t)c.e * N;
-    const int32_t* match = c.p.rf_match + (size_t)c.e * N;
+    int32_t* xs = c.p.rf_scratch + (size_t)c.e * c.p.rf_gmax;
+    const int32_t* match = c.p.rf_match + (size_t)c.e * c.p.rf_gmax;
     for (uint32_t n = 0; n < N; n++) {                                                    // insertion sort of match_index()
-      const int32_t v = n == c.e ? (int32_t)r->log_size : match[n];
+      const int32_t v = n == c.e - c.gbase ? (int32_t)r->log_size : match[n];
       uint32_t j = n;
       while (j > 0 && xs[j - 1] > v) { xs[j] = xs[j - 1]; j--; }
       xs[j] = v;
@@ -356,6 +370,30 @@ __device__ void rf_actions(RaftCtx& c) {
   }
 }
 
+// After a node's step: does replicate_log have a reason to run again before the heartbeat interval
+// (a follower behind the log, or a next_index that makes it raise)?  k_snapshot uses it, with the
+// node's deadlines, to skip the rounds in which the node's step would do nothing.
+__device__ void rf_note_busy(RaftCtx& c) {
+  RaftDev* r = c.r;
+  uint32_t busy = 0;
+  if (r->state == RAFT_LEADER) {
+    const int32_t* next = c.p.rf_next + (size_t)c.e * c.p.rf_gmax;
+    for (uint32_t n = 0; n < c.gn && !busy; n++)
+      if (n != c.e - c.gbase && (next[n] <= 0 || next[n] <= (int32_t)r->log_size)) busy = 1;
+  }
+  r->busy = busy;
+}
+
+// k_snapshot: would this node's step do anything in a round at time `now` with an empty inbox?
+// The conditions are the guards of rf_actions, verbatim (a skipped step must be a no-op).
+__device__ __forceinline__ bool rf_timer_due(const RaftDev& r, int64_t now) {
+  if (r.election_deadline < now) return true;                                             // election (also a nascent node's reset)
+  if (r.state != RAFT_LEADER) return false;
+  if (r.step_down_deadline < now) return true;
+  const int64_t elapsed = now - r.last_replication;
+  return kMinReplicationNs < elapsed && (r.busy || kHeartbeatNs < elapsed);
+}
+
 // ------------------------------------------------------------------ txn-list-append, single key
 // demo/clojure/single_key_txn.clj: the whole database is one value under key "root" (key 0) of
 // the lin-kv service (:134-141).  handle-txn! (:163-173) = read the root, apply-txn, cas the
@@ -369,7 +407,7 @@ __device__ void txn_handle(RaftCtx& c, const Rec& m) {
   const uint32_t type = m.tf & 0xFFFFu, flags = m.tf >> 16;
   const uint32_t lin_kv = c.p.sv_ep[MS_SVC_LIN_KV];
   if (flags & MS_F_REPLY) {                                                       // handle-reply!, :60-68
-    uint4* slot = c.cb + 2 * (size_t)(m.in_reply_to % kRaftCallbacks);
+    uint4* slot = c.cb + 2 * (size_t)(m.in_reply_to & c.p.rf_cb_mask);
     const uint4 s0 = slot[0], s1 = slot[1];
     if (s0.y == 0 || s0.x != m.in_reply_to) return;                               // no such future
     slot[0] = make_uint4(0u, 0u, 0u, 0u);
@@ -385,7 +423,7 @@ __device__ void txn_handle(RaftCtx& c, const Rec& m) {
       if (s1.y) new_v = 2u + c.e + c.p.n_servers * (r->appends++);               // an append: a value nobody has seen
       else new_v = old_v == 0 ? 1u : old_v;                                       // reads only: unchanged ({} for nil)
       const uint32_t id = ++r->next_msg_id;                                       // (swap! next-message-id inc), :54
-      uint4* s2 = c.cb + 2 * (size_t)(id % kRaftCallbacks);
+      uint4* s2 = c.cb + 2 * (size_t)(id & c.p.rf_cb_mask);
       s2[0] = make_uint4(id, 4u, s0.z, s0.w);
       s2[1] = make_uint4(old_v, new_v, 0u, 0u);
       Rec q;                                                                      // cas-service!, :152-161
@@ -411,7 +449,7 @@ __device__ void txn_handle(RaftCtx& c, const Rec& m) {
   if (type == MS_T_TXN) {                                                         // handle-txn!, :163-173
     if (lin_kv == 0xFFFFFFFFu) { latch_error(c.st, E_INVALID_DEST, lin_kv); return; }   // no lin-kv service
     const uint32_t id = ++r->next_msg_id;
-    uint4* s2 = c.cb + 2 * (size_t)(id % kRaftCallbacks);
+    uint4* s2 = c.cb + 2 * (size_t)(id & c.p.rf_cb_mask);
     s2[0] = make_uint4(id, 3u, m.msg_id, m.src);
     s2[1] = make_uint4(0u, (flags & MS_F_APPENDS) ? 1u : 0u, 0u, 0u);
     Rec q;

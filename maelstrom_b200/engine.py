@@ -55,6 +55,11 @@ class Sim:
         cfg.p_loss = p_loss
         cfg.n_values = n_values
         cfg.journal_level = 2
+        # named spellings of ms_config.reserved[]
+        for name, slot in (("history_rounds", 0), ("use_graph", 1), ("n_keys", 2), ("raft_log_cap", 3),
+                           ("raft_group", 4), ("rpc_table", 5)):
+            if name in sizing:
+                cfg.reserved[slot] = int(sizing.pop(name))
         for k, v in sizing.items():
             if not hasattr(cfg, k):
                 raise TypeError("unknown ms_config field %r" % k)

@@ -321,7 +321,7 @@ struct RaftNode {
   std::vector<RaftEntry> log = std::vector<RaftEntry>(1);        // the default entry {term 0, op None} (raft.py:121)
   std::map<uint32_t, uint32_t> kv;
   std::vector<int64_t> next_index, match_index;
-  std::vector<RaftCb> callbacks = std::vector<RaftCb>(kRaftCallbacks);
+  std::vector<RaftCb> callbacks;                                 // sized by or_create (cfg.rpc_table)
   std::set<uint32_t> votes;
   uint64_t appends = 0;
   uint32_t draws = 0;                                            // random draws made in the current round
@@ -552,7 +552,14 @@ struct or_sim {
   // ------------------------------------------------------------- Raft (demo/python/raft.py)
   std::map<std::pair<uint32_t, uint64_t>, RaftAppend> raft_appends;   // (sender, k) -> append_entries payload
 
-  uint32_t raft_majority() const { return cfg.n_nodes / 2 + 1; }                 // raft.py:25-27
+  uint32_t cb_slots = kRaftCallbacks;
+  // the node's cluster = node_ids of its init (raft.py:447-459): [gbase, gbase + gn)
+  uint32_t raft_gbase(uint32_t e) const { const uint32_t G = cfg.raft_group ? cfg.raft_group : cfg.n_nodes; return (e / G) * G; }
+  uint32_t raft_gn(uint32_t e) const {
+    const uint32_t G = cfg.raft_group ? cfg.raft_group : cfg.n_nodes;
+    return std::min(G, cfg.n_nodes - raft_gbase(e));
+  }
+  uint32_t raft_majority(uint32_t e) const { return raft_gn(e) / 2 + 1; }        // raft.py:25-27
   // random.random() (raft.py:251): word 0 of Philox(0x80000000 | k, node, round), k-th draw of the node's step
   uint32_t raft_draw(uint32_t e) {
     RaftNode& r = eps[e].rn;
@@ -588,7 +595,7 @@ struct or_sim {
     const uint32_t id = r.next_msg_id++;
     RaftCb cb = closure;
     cb.msg_id = id;
-    r.callbacks[id % kRaftCallbacks] = cb;
+    r.callbacks[id % cb_slots] = cb;
     m.src = e; m.dest = dest; m.flags = OR_F_MSG_ID; m.msg_id = id;
     out.push_back(Emit(m));
   }
@@ -596,7 +603,7 @@ struct or_sim {
     RaftNode& r = eps[e].rn;
     r.votes.clear();
     r.votes.insert(e);
-    for (uint32_t n = 0; n < cfg.n_nodes; n++) {                                  // brpc, :243-246
+    for (uint32_t n = raft_gbase(e); n < raft_gbase(e) + raft_gn(e); n++) {       // brpc, :243-246
       if (n == e) continue;
       or_msg m; std::memset(&m, 0, sizeof m);
       m.type = OR_T_REQUEST_VOTE;
@@ -621,8 +628,8 @@ struct or_sim {
     r.state = RAFT_LEADER;
     r.leader = -1;
     r.last_replication = 0;
-    r.next_index.assign(cfg.n_nodes, (int64_t)r.log.size() + 1);
-    r.match_index.assign(cfg.n_nodes, 0);
+    r.next_index.assign(raft_gn(e), (int64_t)r.log.size() + 1);                   // by cluster member
+    r.match_index.assign(raft_gn(e), 0);
     raft_reset_step_down_deadline(e);
   }
   // KVStore.apply (raft.py:158-192); the reply goes to op['client'] with in_reply_to = op['msg_id']
@@ -650,26 +657,30 @@ struct or_sim {
   void node_raft(uint32_t e, const or_msg& m, std::vector<Emit>& out) {
     RaftNode& r = eps[e].rn;
     if (m.flags & OR_F_REPLY) {                                                   // :97-101 callback lookup
-      RaftCb& slot = r.callbacks[m.in_reply_to % kRaftCallbacks];
+      RaftCb& slot = r.callbacks[m.in_reply_to % cb_slots];
       if (slot.kind == 0 || slot.msg_id != m.in_reply_to) return;                 // KeyError
       const RaftCb cb = slot;
       slot.kind = 0;                                                              // del self.callbacks[m]
       if (cb.kind == 1) {                                                         // request_votes' handle, :282-303
         raft_reset_step_down_deadline(e);
         raft_maybe_step_down(e, m.p0);
-        if (r.state == RAFT_CANDIDATE && r.term == cb.term && m.p0 == r.term && m.p1 != 0) {
+        if (r.state == RAFT_CANDIDATE && r.term == cb.term && m.p0 == r.term && m.p1 != 0 &&
+            m.src >= raft_gbase(e) && m.src < raft_gbase(e) + raft_gn(e)) {
           r.votes.insert(m.src);
-          if (raft_majority() <= r.votes.size()) raft_become_leader(e);
+          if (raft_majority(e) <= r.votes.size()) raft_become_leader(e);
         }
       } else {                                                                    // replicate_log's handler, :413-426
         raft_maybe_step_down(e, m.p0);
         if (r.state == RAFT_LEADER && cb.term == r.term) {
           raft_reset_step_down_deadline(e);
-          if (m.p1 != 0) {
-            r.next_index[cb.node] = std::max(r.next_index[cb.node], cb.ni + (int64_t)cb.n_entries);
-            r.match_index[cb.node] = std::max(r.match_index[cb.node], cb.ni - 1 + (int64_t)cb.n_entries);
-          } else {
-            r.next_index[cb.node] -= 1;
+          const uint32_t cn = cb.node - raft_gbase(e);                            // member index
+          if (cn < raft_gn(e)) {
+            if (m.p1 != 0) {
+              r.next_index[cn] = std::max(r.next_index[cn], cb.ni + (int64_t)cb.n_entries);
+              r.match_index[cn] = std::max(r.match_index[cn], cb.ni - 1 + (int64_t)cb.n_entries);
+            } else {
+              r.next_index[cn] -= 1;
+            }
           }
         }
       }
@@ -756,9 +767,9 @@ struct or_sim {
       const uint32_t first_rpc = r.next_msg_id;            // RPCs of this pass: ids first_rpc .. next_msg_id - 1
       RaftCb last;                                          // what the pass's closures end up seeing (see below)
       if (r.state == RAFT_LEADER && kMinReplicationNs < elapsed) {
-        for (uint32_t n = 0; n < cfg.n_nodes && !aborted; n++) {
+        for (uint32_t n = raft_gbase(e); n < raft_gbase(e) + raft_gn(e) && !aborted; n++) {
           if (n == e) continue;
-          const int64_t ni = r.next_index[n];
+          const int64_t ni = r.next_index[n - raft_gbase(e)];
           if (ni <= 0) { aborted = true; break; }                                          // from_index raises, :147-148
           const int64_t n_entries = (int64_t)r.log.size() - ni + 1 > 0 ? (int64_t)r.log.size() - ni + 1 : 0;
           if (0 < n_entries || kHeartbeatNs < elapsed) {
@@ -786,7 +797,7 @@ struct or_sim {
       // pass sent to, for every RPC of the pass.  (A follower that is not last in other_nodes() only
       // advances in a pass where it alone has something to receive.)
       for (uint32_t id = first_rpc; id != r.next_msg_id; id++) {
-        RaftCb& slot = r.callbacks[id % kRaftCallbacks];
+        RaftCb& slot = r.callbacks[id % cb_slots];
         if (slot.kind == 2 && slot.msg_id == id) { slot.node = last.node; slot.ni = last.ni; slot.n_entries = last.n_entries; }
       }
       // an exception inside replicate_log ends this iteration of the main loop; every later
@@ -800,9 +811,9 @@ struct or_sim {
     }
     if (r.state == RAFT_LEADER) {                                                          // advance_commit_index, :378-385
       std::vector<int64_t> xs = r.match_index;
-      xs[e] = (int64_t)r.log.size();
+      xs[e - raft_gbase(e)] = (int64_t)r.log.size();
       std::sort(xs.begin(), xs.end());
-      const int64_t n = xs[xs.size() - raft_majority()];                                  // median, :29-33
+      const int64_t n = xs[xs.size() - raft_majority(e)];                                 // median, :29-33
       if ((int64_t)r.commit_index < n && r.log[(size_t)n - 1].term == r.term) r.commit_index = (uint32_t)n;
     }
     while (r.last_applied < r.commit_index) {                                              // advance_state_machine, :343-354
@@ -822,7 +833,7 @@ struct or_sim {
     for (uint32_t i = cfg.n_nodes; i < eps.size(); i++)
       if (eps[i].live && eps[i].kind == OR_KIND_SERVICE && eps[i].svc.type == OR_SVC_LIN_KV) lin_kv = (int)i;
     if (m.flags & OR_F_REPLY) {                                                  // handle-reply!, :60-68
-      RaftCb& slot = r.callbacks[m.in_reply_to % kRaftCallbacks];
+      RaftCb& slot = r.callbacks[m.in_reply_to % cb_slots];
       if (slot.kind == 0 || slot.msg_id != m.in_reply_to) return;                 // no such future
       const RaftCb cb = slot;
       slot.kind = 0;
@@ -843,7 +854,7 @@ struct or_sim {
         RaftCb n2; n2.kind = 4; n2.node = cb.node; n2.term = cb.term; n2.ni = (int64_t)old_v; n2.n_entries = new_v;
         const uint32_t id = ++r.next_msg_id;                                      // (swap! next-message-id inc), :54
         n2.msg_id = id;
-        r.callbacks[id % kRaftCallbacks] = n2;
+        r.callbacks[id % cb_slots] = n2;
         c.src = e; c.dest = (uint32_t)lin_kv; c.flags = OR_F_MSG_ID | OR_F_CREATE; c.msg_id = id;
         out.push_back(Emit(c));
       } else if (cb.kind == 4) {                                                  // :168-173
@@ -868,7 +879,7 @@ struct or_sim {
         RaftCb cb; cb.kind = 3; cb.node = m.src; cb.term = m.msg_id; cb.n_entries = (m.flags & OR_F_APPENDS) ? 1 : 0;
         const uint32_t id = ++r.next_msg_id;
         cb.msg_id = id;
-        r.callbacks[id % kRaftCallbacks] = cb;
+        r.callbacks[id % cb_slots] = cb;
         q.src = e; q.dest = (uint32_t)lin_kv; q.flags = OR_F_MSG_ID; q.msg_id = id;
         out.push_back(Emit(q));
         return;
@@ -976,7 +987,10 @@ or_sim* or_create(const or_config* cfg) {
   if (s->cfg.gset_interval_ms == 0) s->cfg.gset_interval_ms = 5000;   // g_set.rb:34
   s->loss_thresh = loss_threshold(cfg->p_loss);
   s->eps.resize(cfg->n_nodes);
+  if (s->cfg.rpc_table) { s->cb_slots = 1; while (s->cb_slots < s->cfg.rpc_table) s->cb_slots <<= 1; }
+  if (s->cfg.raft_group >= s->cfg.n_nodes) s->cfg.raft_group = 0;
   for (uint32_t i = 0; i < cfg->n_nodes; i++) {
+    if (cfg->workload == OR_W_RAFT || cfg->workload == OR_W_TXN) s->eps[i].rn.callbacks.resize(s->cb_slots);
     s->eps[i].name = "n" + std::to_string(i);          // core.clj:231-238
     s->eps[i].kind = OR_KIND_SERVER;
     s->eps[i].neighbors = topology_neighbors(cfg->topology, cfg->n_nodes, i);

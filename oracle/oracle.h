@@ -81,6 +81,9 @@ typedef struct or_config {
   double   p_loss;          /* initial loss probability (net.clj:100 => 0)   */
   uint32_t n_values;        /* capacity of the per-node value universe       */
   uint32_t gset_interval_ms;/* g-set replication period (g_set.rb:30: 5 s)   */
+  uint32_t raft_group;      /* servers per Raft cluster = node_ids of a node's init (raft.py:447-459): blocks of
+                               raft_group consecutive servers; 0 = one cluster of all servers                  */
+  uint32_t rpc_table;       /* pending-RPC closures kept per Raft / txn node (0 = 4096; the reference's dict is unbounded) */
 } or_config;
 
 enum { OR_W_ECHO = 0, OR_W_BROADCAST = 1, OR_W_GSET = 2,

@@ -43,7 +43,8 @@ class Config(C.Structure):
     _fields_ = [("n_nodes", C.c_uint32), ("workload", C.c_uint32), ("topology", C.c_uint32),
                 ("latency_dist", C.c_uint32), ("latency_mean_ms", C.c_uint32),
                 ("seed_lo", C.c_uint32), ("seed_hi", C.c_uint32), ("p_loss", C.c_double),
-                ("n_values", C.c_uint32), ("gset_interval_ms", C.c_uint32)]
+                ("n_values", C.c_uint32), ("gset_interval_ms", C.c_uint32),
+                ("raft_group", C.c_uint32), ("rpc_table", C.c_uint32)]
 
 
 class Body(C.Structure):
@@ -152,7 +153,8 @@ class Sim:
     """Thin object wrapper; method names follow the C ABI (include/maelstrom_b200.h)."""
 
     def __init__(self, n_nodes, workload=W_BROADCAST, topology="grid", latency_dist="constant",
-                 latency_mean_ms=0, seed=0x4D41454C, p_loss=0.0, n_values=1 << 16, gset_interval_ms=5000):
+                 latency_mean_ms=0, seed=0x4D41454C, p_loss=0.0, n_values=1 << 16, gset_interval_ms=5000,
+                 raft_group=0, rpc_table=0):
         cfg = Config()
         cfg.n_nodes = n_nodes
         cfg.workload = workload
@@ -164,6 +166,8 @@ class Sim:
         cfg.p_loss = p_loss
         cfg.n_values = n_values
         cfg.gset_interval_ms = gset_interval_ms
+        cfg.raft_group = raft_group
+        cfg.rpc_table = rpc_table
         self.L = lib()
         self.h = self.L.or_create(C.byref(cfg))
         self.n_nodes = n_nodes

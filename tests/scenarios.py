@@ -10,7 +10,8 @@ def make_pair(n_nodes, **kw):
     import maelstrom_b200 as mb
     sizing = {k: kw.pop(k) for k in list(kw) if k in (
         "max_endpoints", "ring_cap", "max_window", "journal_cap_log2", "journal_level",
-        "calendar_slots", "calendar_cap", "mailbox_cap", "inject_cap", "threads_per_node")}
+        "calendar_slots", "calendar_cap", "mailbox_cap", "inject_cap", "threads_per_node",
+        "n_keys", "raft_log_cap", "history_rounds", "server_ring_cap", "server_max_window")}
     workload = kw.pop("workload", "broadcast")
     g = mb.Sim(n_nodes, workload=workload, **kw, **sizing)
     o = O.Sim(n_nodes, workload={"echo": O.W_ECHO, "broadcast": O.W_BROADCAST, "g-set": O.W_GSET, "lin-kv": O.W_RAFT, "txn-list-append": O.W_TXN}[workload], **kw)

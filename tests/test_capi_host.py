@@ -71,7 +71,7 @@ int main(void) {
 
 def test_abi_version_and_loud_failure_without_gpu(lib):
     L = lib.lib()
-    assert L.ms_abi_version() == 1
+    assert L.ms_abi_version() == 2
     try:
         import torch
         if torch.cuda.is_available():

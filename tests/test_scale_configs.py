@@ -1,0 +1,162 @@
+"""BASELINE.json configs 3-5 at a sampled scale, engine vs oracle, journal bit for bit:
+  cfg 3  g-set, 10 % loss + exponential 100 ms latency        (full size: 16 384 nodes, bench.py --config gset16k)
+  cfg 4  lin-kv on Raft, partition nemesis                     (full size: 65 536 nodes, --config raft64k)
+  cfg 5  txn-list-append over the lin-kv service               (full size: 262 144 nodes, --config txn256k)
+[emul] runs a small instance in the CPU suite, [cuda] a larger one on the B200.  The full sizes are
+covered by size-independent properties in bench.py (message counts, convergence, reply counts)."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from scenarios import assert_same_journal, both, make_pair, ops_array
+
+pytestmark = pytest.mark.usefixtures("engine_backend")
+
+
+def gset_ops(n, clients, n_adds, horizon_ms, seed):
+    rng = np.random.default_rng(seed)
+    rows, mid = [], {c: 1 for c in clients}                         # msg_id 1 was the init
+    ts = np.sort(rng.integers(1, horizon_ms, size=n_adds))
+    for v, t in enumerate(ts):
+        c = clients[int(rng.integers(len(clients)))]
+        mid[c] += 1
+        kind = "read" if v % 7 == 6 else "add"
+        rows.append((int(t) * 1_000_000, c, int(rng.integers(n)), kind, mid[c], v))
+    return ops_array(rows)
+
+
+def test_cfg3_gset_loss_and_exponential_jitter(engine_backend):
+    # g_set.rb:34-39 ships the whole set to every other node each period; (p-loss 0.1, net.clj:214) and
+    # exponential latency mean 100 ms (net.clj:73-77): N x (N-1) replicate_full per period spread over
+    # hundreds of wheel slots, many of them beyond the wheel's span
+    n = 1024 if engine_backend == "cuda" else 96
+    period = 400
+    g, o = make_pair(n, workload="g-set", latency_dist="exponential", latency_mean_ms=100, p_loss=0.1,
+                     n_values=256, gset_interval_ms=period, max_endpoints=n + 8, ring_cap=1024, max_window=1024,
+                     journal_cap_log2=23 if n > 500 else 20, calendar_slots=256,
+                     calendar_cap=(n * n) // 64 + 256)
+
+    def scenario(s, body):
+        cs = [s.add_endpoint("c%d" % i, O.KIND_SIM_CLIENT) for i in range(4)]
+        init = ops_array([(0, cs[i % 4], i, "init", 1, 0) for i in range(n)])
+        init["body"]["msg_id"] = 1 + np.arange(n) // 4                # fresh msg ids per client
+        s.schedule(init)
+        ops = gset_ops(n, cs, 96, 2 * period, 5)
+        ops["body"]["msg_id"] += n                                    # after the inits
+        s.schedule(ops)
+        s.run(int(2.5 * period) * 1_000_000)
+        return [s.node_set(k).tolist() for k in (0, n // 2, n - 1)]
+
+    rg, ro = both(g, o, scenario)
+    assert rg == ro
+    ev, _ = assert_same_journal(g, o)
+    st = g.stats()["servers"]
+    assert st["send-count"] >= 2 * n * (n - 1)                        # two full replication rounds went out
+    assert 0.85 < st["recv-count"] / st["send-count"] < 0.95          # one in ten is lost (some still in flight)
+
+
+def kv_ops(n, clients, n_ops, t0_ms, t1_ms, n_keys, seed):
+    """open-loop lin-kv traffic (workload/lin_kv.clj:12-38): write / read / cas on random nodes"""
+    rng = np.random.default_rng(seed)
+    ts = np.sort(rng.integers(t0_ms, t1_ms, size=n_ops))
+    a = np.zeros(n_ops, dtype=O.OP_DTYPE)
+    mid = {c: 1000 for c in clients}
+    for i, t in enumerate(ts):
+        c = clients[int(rng.integers(len(clients)))]
+        mid[c] += 1
+        kind = ("write", "read", "cas")[int(rng.integers(3))]
+        a[i]["time_ns"] = int(t) * 1_000_000
+        a[i]["src"] = c
+        a[i]["dest"] = int(rng.integers(n))
+        a[i]["body"]["type"] = O.T[kind]
+        a[i]["body"]["flags"] = O.F_MSG_ID
+        a[i]["body"]["msg_id"] = mid[c]
+        a[i]["body"]["p0"] = int(rng.integers(n_keys))
+        v = int(rng.integers(1, 5))
+        a[i]["body"]["p1"] = v if kind == "write" else (v | (int(rng.integers(1, 5)) << 32))
+    return a
+
+
+@pytest.mark.parametrize("group", [5, 0])
+def test_cfg4_raft_groups_with_partition_nemesis(engine_backend, group):
+    # group = 5: many independent 5-node clusters side by side (node_ids of a node's init = its block,
+    # raft.py:447-459); group = 0: one cluster of all nodes.  Partition nemesis: every second the
+    # servers are re-split into two random components (bulk ms_net_partition), then healed.
+    if group:
+        n = 4096 if engine_backend == "cuda" else 40
+    else:
+        n = 64 if engine_backend == "cuda" else 12
+    g, o = make_pair(n, workload="lin-kv", latency_dist="uniform", latency_mean_ms=2, max_endpoints=n + 8,
+                     ring_cap=256 if group else 1024, max_window=128 if group else 512, raft_group=group,
+                     rpc_table=256, n_keys=8, raft_log_cap=256, journal_cap_log2=22, calendar_slots=16,
+                     calendar_cap=max(256, 8 * n))
+
+    def scenario(s, body):
+        cs = [s.add_endpoint("c%d" % i, O.KIND_SIM_CLIENT) for i in range(4)]
+        init = ops_array([(0, cs[i % 4], i, "init", 1 + i // 4, 0) for i in range(n)])
+        s.schedule(init)
+        s.schedule(kv_ops(n, cs, 6 * n if group else 40, 4200, 9000, 8, 23))
+        rng = np.random.default_rng(99)
+        s.run(4_500_000_000)                                           # first elections (2-4 s, raft.py:249-251)
+        for k in range(3):
+            s.partition(rng.integers(0, 2, size=n).astype(np.uint32))  # clients (index >= n) are never cut
+            s.run((5500 + 1500 * k) * 1_000_000)
+            s.heal()
+            s.run((6000 + 1500 * k) * 1_000_000)
+        s.run(11_000_000_000)
+        return [s.raft_state(i) for i in (0, n // 2, n - 1)], s.client_replies()
+
+    rg, ro = both(g, o, scenario)
+    assert rg == ro
+    assert rg[1] > 0                                                    # clients did get answers
+    assert_same_journal(g, o)
+    # one leader per cluster at the end (every partition was healed 2 s ago)
+    G = group or n
+    for base in range(0, min(n, 10 * G), G):
+        members = range(base, min(base + G, n))
+        if len(members) > 1:
+            assert sum(1 for i in members if g.raft_state(i)["state"] == 3) == 1
+
+
+def txn_ops(n, clients, n_ticks, per_tick, seed):
+    rng = np.random.default_rng(seed)
+    k = n_ticks * per_tick
+    a = np.zeros(k, dtype=O.OP_DTYPE)
+    i = np.arange(k)
+    a["time_ns"] = (1 + i // per_tick) * 1_000_000
+    a["src"] = np.asarray(clients, dtype=np.uint32)[i % len(clients)]
+    a["dest"] = rng.integers(0, n, size=k).astype(np.uint32)
+    a["body"]["type"] = O.T["txn"]
+    a["body"]["flags"] = O.F_MSG_ID | np.where(rng.integers(0, 3, size=k) > 0, O.F_APPENDS, 0).astype(np.uint16)
+    a["body"]["msg_id"] = (1 + i // len(clients)).astype(np.uint32)
+    a["body"]["p1"] = 1000 + i
+    return a
+
+
+def test_cfg5_txn_list_append_many_nodes(engine_backend):
+    # every node serves txns against ONE lin-kv service (single_key_txn.clj:134-173): the service's inbox
+    # sees all the traffic, a node's only its own, so the two are sized apart (server_ring_cap /
+    # server_max_window), and a node keeps few closures (rpc_table)
+    n = 16384 if engine_backend == "cuda" else 200
+    per_tick = 512 if engine_backend == "cuda" else 24
+    g, o = make_pair(n, workload="txn-list-append", max_endpoints=n + 16, ring_cap=4096, max_window=2048,
+                     server_ring_cap=32, server_max_window=16, rpc_table=16, journal_cap_log2=22,
+                     latency_dist="constant", latency_mean_ms=1, calendar_slots=8, calendar_cap=4 * per_tick + 64)
+
+    def scenario(s, body):
+        kv = s.add_endpoint("lin-kv", O.KIND_SERVICE)
+        cs = [s.add_endpoint("c%d" % i, O.KIND_SIM_CLIENT) for i in range(8)]
+        s.schedule(txn_ops(n, cs, 30, per_tick, 77))
+        s.run(45_000_000)
+        return s.client_replies()
+
+    rg, ro = both(g, o, scenario)
+    assert rg == ro == 30 * per_tick                                     # every txn was answered (txn_ok or error 30)
+    ev, bd = assert_same_journal(g, o)
+    sends = (ev["event_id"] >> np.uint64(63)) == 0
+    oks = bd[(bd["type"] == O.T["txn_ok"]) & sends]
+    conflicts = bd[(bd["type"] == O.T["error"]) & sends & (ev["src"] < n)]
+    assert len(oks) > 0 and len(conflicts) > 0 and set(int(c) for c in conflicts["p0"]) == {30}
+    # committed writes form one chain of versions
+    written = [(int(p) & 0xFFFFFFFF, int(p) >> 32) for p in oks["p1"] if (int(p) & 0xFFFFFFFF) != (int(p) >> 32)]
+    assert len({w[0] for w in written}) == len(written)
