@@ -227,6 +227,40 @@ int ms_journal_close(ms_sim* sim);
 int ms_journal_drain(ms_sim* sim, ms_event* events, ms_jbody* bodies, size_t cap, size_t* n_out);
 uint64_t ms_journal_written(ms_sim* sim);
 
+/* Streaming the journal to a throughput-bound consumer (the writer side of net/journal.clj:205-239).
+ * ms_run_streamed advances the simulation like ms_run and hands the journal over in batches while the
+ * next rounds are already running: the device packs events, in event-id order, straight into pinned
+ * host memory (two buffers in turn, written over PCIe by the packing kernel), and `sink` is called
+ * once per batch from the calling thread.  Event k of a batch has event id first_event + k; its round
+ * (hence its virtual time) is the last row of `rounds` whose ev_base is <= that id.
+ *   MS_JFMT_EVENT  32-B ms_event, as ms_journal_drain returns them
+ *   MS_JFMT_12     96 bits: id (47) | recv (1) in words 0-1, src (24) and dest (24) in words 1-2:
+ *                  w0 = id[31:0]; w1 = id[46:32] | recv << 15 | src[15:0] << 16; w2 = src[23:16] | dest << 8
+ *   MS_JFMT_8      64 bits: recv << 63 | src << 47 | dest << 31 | (id - id_ref of the round); needs
+ *                  endpoint indices < 65536 and every message received within 2^30 ids of the newest
+ *                  one: otherwise the batch header has overflow = 1 and the call fails with MS_ERR_CAPACITY
+ * ms_journal_decode expands a batch into ms_event records (lazily, on the host). */
+enum { MS_JFMT_EVENT = 32, MS_JFMT_12 = 12, MS_JFMT_8 = 8 };
+typedef struct ms_jround {   /* one row per round that has events in the batch */
+  uint64_t round;
+  int64_t  time_ns;          /* Event.time of every event of the round */
+  uint64_t ev_base;          /* event id of the round's first event */
+  uint64_t id_ref;           /* MS_JFMT_8: message id = id_ref + the record's low 31 bits */
+} ms_jround;
+typedef struct ms_jbatch {
+  uint64_t first_event, n_events;
+  uint64_t n_rounds;
+  int64_t  now;              /* simulation state when the batch was cut */
+  uint64_t round, next_event;
+  uint32_t format, overflow, more, error;
+} ms_jbatch;
+typedef int (*ms_journal_sink)(void* ctx, const ms_jbatch* batch, const ms_jround* rounds, const void* events);
+/* buf_events = capacity of each of the two host buffers in events (0 = 1 << 24).  A non-zero return
+ * of `sink` stops the run (MS_ERR_ARG).  Returns 0 when `until_virtual_ns` is reached. */
+int ms_run_streamed(ms_sim* sim, int64_t until_virtual_ns, int format, size_t buf_events,
+                    ms_journal_sink sink, void* ctx);
+int ms_journal_decode(const ms_jbatch* batch, const ms_jround* rounds, const void* events, ms_event* out);
+
 /* net.checker/basic-stats (net/checker.clj:28-41) folded on the device:
  * out[9] = {all, clients, servers} x {send-count, recv-count, msg-count}. */
 int ms_stats(ms_sim* sim, uint64_t out[9]);

@@ -43,6 +43,16 @@ class Body(C.Structure):
                 ("in_reply_to", C.c_uint32), ("p0", C.c_uint32), ("p1", C.c_uint64)]
 
 
+class JBatch(C.Structure):      # ms_jbatch
+    _fields_ = [("first_event", C.c_uint64), ("n_events", C.c_uint64), ("n_rounds", C.c_uint64),
+                ("now", C.c_int64), ("round", C.c_uint64), ("next_event", C.c_uint64),
+                ("format", C.c_uint32), ("overflow", C.c_uint32), ("more", C.c_uint32), ("error", C.c_uint32)]
+
+
+JROUND_DTYPE = np.dtype([("round", "<u8"), ("time_ns", "<i8"), ("ev_base", "<u8"), ("id_ref", "<u8")])
+JOURNAL_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(JBatch), C.c_void_p, C.c_void_p)
+JFMT_EVENT, JFMT_12, JFMT_8 = 32, 12, 8
+
 # every symbol include/maelstrom_b200.h declares: (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -73,6 +83,8 @@ SYMBOLS = {
     "ms_journal_close": (C.c_int, [_P]),
     "ms_journal_drain": (C.c_int, [_P, _P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "ms_journal_written": (C.c_uint64, [_P]),
+    "ms_run_streamed": (C.c_int, [_P, C.c_int64, C.c_int, C.c_size_t, JOURNAL_SINK, _P]),
+    "ms_journal_decode": (C.c_int, [C.POINTER(JBatch), _P, _P, _P]),
     "ms_stats": (C.c_int, [_P, _P]),
     "ms_node_set": (C.c_size_t, [_P, C.c_uint32, _P, C.c_size_t]),
     "ms_client_replies": (C.c_uint64, [_P]),

@@ -29,6 +29,10 @@ void msk_set_bit(uint32_t* words, size_t word, uint32_t bit, cudaStream_t s);
 void msk_barrier(const msd::Params* p, cudaStream_t s);
 void msk_journal_expand(const msd::Params* p, uint64_t r0, uint32_t n_rounds, uint64_t first, uint64_t count,
                         void* out_ev, void* out_body, int n_sms, cudaStream_t s);
+size_t msk_stream_plan_bytes();
+void msk_stream_batch(const msd::Params* p, void* plan, uint64_t cap_events, uint32_t cap_rounds, ms_jround* rows,
+                      void* out, ms_jbatch* hdr, int format, int n_sms, cudaStream_t s);
+void msk_stream_apply(const msd::Params* p, const void* plan, cudaStream_t s);
 }
 
 static thread_local std::string g_err;
@@ -158,6 +162,14 @@ struct ms_sim {
   bool use_graph = false;   // opt-in (ms_config.reserved[1] = 1): instantiating the forked graph costs more
                             // than it saves unless the kernel parameters stay fixed for many batches
   std::vector<void*> peer_ptrs;     // opened IPC mappings
+  // journal streaming (ms_run_streamed): two pinned host buffers written by the packing kernel
+  cudaStream_t jstream = nullptr;
+  cudaEvent_t j_rounds_done[2] = {nullptr, nullptr}, j_packed[2] = {nullptr, nullptr};
+  unsigned char* jhost[2] = {nullptr, nullptr};   // [ms_jbatch | rows | events]
+  size_t jhost_events = 0;
+  int jhost_format = 0;
+  void* jplan = nullptr;
+  static constexpr uint32_t kStreamRows = 4096;   // rounds per batch at most
   // timing
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   bool profiling = false;
@@ -762,6 +774,12 @@ void ms_destroy(ms_sim* s) {
   if (s->stream) cudaStreamSynchronize(s->stream);
   for (void* p : s->peer_ptrs) cudaIpcCloseMemHandle(p);
   for (void* p : s->allocs) cudaFree(p);
+  for (int k = 0; k < 2; k++) {
+    if (s->jhost[k]) cudaFreeHost(s->jhost[k]);
+    if (s->j_rounds_done[k]) cudaEventDestroy(s->j_rounds_done[k]);
+    if (s->j_packed[k]) cudaEventDestroy(s->j_packed[k]);
+  }
+  if (s->jstream) cudaStreamDestroy(s->jstream);
   if (s->stage_ev) cudaFree(s->stage_ev);
   if (s->stage_body) cudaFree(s->stage_body);
   if (s->d_sched) cudaFree(s->d_sched);
@@ -1102,6 +1120,131 @@ int ms_journal_drain(ms_sim* s, ms_event* ev, ms_jbody* bodies, size_t cap, size
 }
 
 uint64_t ms_journal_written(ms_sim* s) { std::lock_guard<std::mutex> g(s->mu); return s->hs.next_event; }
+
+static size_t stream_hdr_bytes() { return 256 + (size_t)ms_sim::kStreamRows * sizeof(ms_jround); }
+
+int ms_run_streamed(ms_sim* s, int64_t until, int format, size_t buf_events, ms_journal_sink sink, void* ctx) {
+  std::lock_guard<std::mutex> g(s->mu);
+  cudaSetDevice(s->device);
+  if (format != MS_JFMT_EVENT && format != MS_JFMT_12 && format != MS_JFMT_8) { set_err("ms_run_streamed: unknown format"); return MS_ERR_ARG; }
+  if (!sink) { set_err("ms_run_streamed: null sink"); return MS_ERR_ARG; }
+  if (s->cfg.journal_level == 0 || s->cfg.journal_discard) { set_err("ms_run_streamed: the journal is off (journal_level 0 or journal_discard)"); return MS_ERR_ARG; }
+  if (!buf_events) buf_events = (size_t)1 << 24;
+  if (!s->jstream) {
+    CK(cudaStreamCreateWithFlags(&s->jstream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+      CK(cudaEventCreateWithFlags(&s->j_rounds_done[k], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&s->j_packed[k], cudaEventDisableTiming));
+    }
+    void* ptr = nullptr;
+    CK(cudaMalloc(&ptr, msk_stream_plan_bytes()));
+    s->allocs.push_back(ptr);
+    s->jplan = ptr;
+  }
+  if (s->jhost_events < buf_events || s->jhost_format < format) {
+    for (int k = 0; k < 2; k++) {
+      if (s->jhost[k]) cudaFreeHost(s->jhost[k]);
+      s->jhost[k] = nullptr;
+      void* ptr = nullptr;
+      CK(cudaHostAlloc(&ptr, stream_hdr_bytes() + buf_events * (size_t)format, cudaHostAllocMapped | cudaHostAllocPortable));
+      s->jhost[k] = (unsigned char*)ptr;
+    }
+    s->jhost_events = buf_events;
+    s->jhost_format = format;
+  }
+  int rc;
+  if ((rc = s->stage_injections())) return rc;
+  if ((rc = s->set_stop(until))) return rc;
+  // the shadow counters start from what has been drained so far
+  {
+    struct { uint64_t first, count, r0, n_rounds, jd, dr, jr; uint32_t ov, more; } init = {0, 0, 0, 0, s->hs.journal_drained, s->hs.drain_round, s->hs.jraw_drained, 0, 0};
+    static_assert(sizeof(init) == 64, "StreamPlan layout");
+    CK(cudaMemcpyAsync(s->jplan, &init, sizeof init, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+  }
+  // rounds per batch: enough work to hide the launch gaps, little enough that a batch of events fits
+  // the host buffer and the raw ring; the device skips rounds by itself when the raw ring is half full
+  const uint64_t batch_rounds = 8;
+  bool launching = true;
+  int64_t seen_now = s->hs.now, stall_now = s->hs.now;
+  uint64_t seen_round = s->hs.round, stall_round = s->hs.round;
+  uint64_t idle_batches = 0;
+  int result = MS_OK;
+  for (uint64_t i = 0;; i++) {
+    const int b = (int)(i & 1);
+    if (launching) s->launch_rounds(batch_rounds);
+    CK(cudaEventRecord(s->j_rounds_done[b], s->stream));
+    CK(cudaStreamWaitEvent(s->jstream, s->j_rounds_done[b], 0));
+    ms_jbatch* hdr = (ms_jbatch*)s->jhost[b];
+    msk_stream_batch(&s->P, s->jplan, s->jhost_events, ms_sim::kStreamRows, (ms_jround*)(s->jhost[b] + 256),
+                     s->jhost[b] + stream_hdr_bytes(), hdr, format, s->n_sms, s->jstream);
+    CK(cudaEventRecord(s->j_packed[b], s->jstream));
+    if (i == 0) continue;
+    // batch i-1: packed while the rounds of batch i run; its counters reach the round kernels after them
+    const int pb = b ^ 1;
+    CK(cudaStreamWaitEvent(s->stream, s->j_packed[pb], 0));
+    msk_stream_apply(&s->P, s->jplan, s->stream);
+    CK(cudaEventSynchronize(s->j_packed[pb]));
+    const ms_jbatch* ph = (const ms_jbatch*)s->jhost[pb];
+    if (ph->overflow) { set_err("ms_run_streamed: MS_JFMT_8 / MS_JFMT_12 cannot hold this batch (endpoint index or id range): use a wider format"); result = MS_ERR_CAPACITY; break; }
+    if (ph->n_events && sink(ctx, ph, (const ms_jround*)(s->jhost[pb] + 256), s->jhost[pb] + stream_hdr_bytes())) {
+      set_err("ms_run_streamed: stopped by the sink");
+      result = MS_ERR_ARG;
+      break;
+    }
+    if (ph->error) break;                       // sync_state below reports it
+    const bool progressed = ph->round != seen_round || ph->n_events != 0;
+    seen_round = ph->round;
+    seen_now = ph->now;
+    if (seen_now != stall_now) { stall_now = seen_now; stall_round = seen_round; }
+    else if (seen_round - stall_round > kMaxDeltaRounds) {
+      set_err("virtual time is not advancing: 2^20 delta rounds at the same instant");
+      result = MS_ERR_SIM;
+      break;
+    }
+    if (seen_now >= until) launching = false;
+    if (!launching && !ph->more && !progressed) break;      // nothing ran and nothing is left to pack
+    idle_batches = progressed ? 0 : idle_batches + 1;
+    if (idle_batches > 64) { set_err("simulation made no progress (device refuses to run rounds)"); result = MS_ERR_SIM; break; }
+  }
+  // everything packed is accounted for before the regular drain counters are trusted again
+  CK(cudaStreamSynchronize(s->jstream));
+  msk_stream_apply(&s->P, s->jplan, s->stream);
+  rc = s->sync_state();
+  return rc ? rc : result;
+}
+
+int ms_journal_decode(const ms_jbatch* b, const ms_jround* rounds, const void* events, ms_event* out) {
+  if (!b || !rounds || !events || !out) return MS_ERR_ARG;
+  size_t r = 0;
+  for (uint64_t k = 0; k < b->n_events; k++) {
+    const uint64_t g = b->first_event + k;
+    while (r + 1 < b->n_rounds && rounds[r + 1].ev_base <= g) r++;
+    ms_event e;
+    uint64_t id; uint32_t src, dest; bool recv;
+    if (b->format == MS_JFMT_8) {
+      const uint64_t w = ((const uint64_t*)events)[k];
+      recv = (w >> 63) != 0; src = (uint32_t)(w >> 47) & 0xFFFFu; dest = (uint32_t)(w >> 31) & 0xFFFFu;
+      id = rounds[r].id_ref + (w & 0x7FFFFFFFull);
+    } else if (b->format == MS_JFMT_12) {
+      const uint32_t* w = (const uint32_t*)events + 3 * k;
+      id = (uint64_t)w[0] | ((uint64_t)(w[1] & 0x7FFFu) << 32);
+      recv = (w[1] & 0x8000u) != 0;
+      src = (w[1] >> 16) | ((w[2] & 0xFFu) << 16);
+      dest = w[2] >> 8;
+    } else if (b->format == MS_JFMT_EVENT) {
+      out[k] = ((const ms_event*)events)[k];
+      continue;
+    } else {
+      return MS_ERR_ARG;
+    }
+    e.event_id = g | (recv ? MS_EVENT_RECV : 0ull);
+    e.time_ns = rounds[r].time_ns;
+    e.msg_id = id; e.src = src; e.dest = dest;
+    out[k] = e;
+  }
+  return MS_OK;
+}
 
 int ms_stats(ms_sim* s, uint64_t out[9]) {
   std::lock_guard<std::mutex> g(s->mu);

@@ -1899,6 +1899,128 @@ __global__ void k_journal_expand(Params p, uint64_t r0, uint32_t n_rounds, uint6
   }
 }
 
+// ------------------------------------------------------------------ journal streaming (ms_run_streamed)
+// What has been packed so far lives in StreamPlan (a shadow of DevState's drain counters): the
+// round kernels only ever see the counters k_stream_apply copies over between two rounds, so every
+// kernel of a round takes the same back-pressure decision (round_skipped).
+struct StreamPlan {
+  uint64_t first, count, r0, n_rounds;
+  uint64_t journal_drained, drain_round, jraw_drained;
+  uint32_t overflow, more;
+};
+
+__global__ void k_stream_plan(Params p, StreamPlan* plan, uint64_t cap_events, uint32_t cap_rounds, ms_jround* rows) {
+  if (threadIdx.x || blockIdx.x) return;
+  const DevState* st = p.st;
+  const uint64_t first = plan->journal_drained;
+  uint64_t count = st->next_event - first;
+  if (count > cap_events) count = cap_events;
+  const uint64_t r0 = plan->drain_round;
+  uint64_t r1 = r0;
+  while (r1 < st->round) {
+    const RoundMeta* m = p.rmeta + ((uint32_t)r1 & p.hist_mask);
+    if (m->round != r1 || m->ev_base >= first + count) break;
+    if (r1 - r0 >= cap_rounds) { count = m->ev_base - first; break; }   // the rows table is full: cut at the round boundary
+    ms_jround row;
+    row.round = r1; row.time_ns = m->now; row.ev_base = m->ev_base;
+    row.id_ref = m->id_base > (1ull << 30) ? m->id_base - (1ull << 30) : 0ull;
+    rows[r1 - r0] = row;
+    r1++;
+  }
+  plan->first = first; plan->count = count; plan->r0 = r0; plan->n_rounds = r1 - r0;
+  plan->overflow = 0;
+}
+
+template <int FMT>
+__global__ void k_journal_pack(Params p, StreamPlan* plan, unsigned char* out) {
+  const uint64_t first = plan->first, count = plan->count, r0 = plan->r0;
+  const uint32_t n_rounds = (uint32_t)plan->n_rounds;
+  if (count == 0) return;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warp_global = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint64_t n_chunks = (uint64_t)n_rounds * p.t_max;
+  bool bad = false;
+  for (uint64_t c = warp_global; c < n_chunks; c += n_warps) {
+    const uint64_t r = r0 + c / p.t_max;
+    const uint32_t t = (uint32_t)(c % p.t_max);
+    const uint32_t row = (uint32_t)r & p.hist_mask;
+    const RoundMeta* m = p.rmeta + row;
+    if (m->round != r || t >= m->n_tickets) continue;
+    if (owner_of_ticket(t, p.n_inj_tickets, p.n_servers, p.n_shards) != p.shard_id) continue;
+    const uint32_t* ev = p.rt_ev + (size_t)row * p.t_max;
+    const uint64_t off = ev[t];
+    const uint64_t end = (t + 1 < m->n_tickets) ? ev[t + 1] : m->ev_total;
+    if (end == off) continue;
+    const uint64_t g0 = m->ev_base + off;
+    const uint64_t cnt = end - off;
+    if (g0 + cnt <= first || g0 >= first + count) continue;
+    const uint64_t chunk = p.rt_chunk[(size_t)row * p.t_max + t];
+    const uint64_t send_base = m->id_base + p.rt_em[(size_t)row * p.t_max + t];
+    const uint64_t id_ref = m->id_base > (1ull << 30) ? m->id_base - (1ull << 30) : 0ull;
+    const int64_t tnow = m->now;
+    for (uint64_t k = lane; k < cnt; k += 32) {
+      const uint64_t g = g0 + k;
+      if (g < first || g >= first + count) continue;
+      const uint4 raw = p.jraw[(chunk + k) & p.jmask];
+      const uint64_t v = (uint64_t)raw.x | ((uint64_t)raw.y << 32);
+      const bool recv = (v & RECV_BIT) != 0;
+      const uint64_t id = recv ? (v & ~RECV_BIT) : send_base + v;
+      if (FMT == 8) {
+        const uint64_t d = id - id_ref;
+        if (id < id_ref || d >= (1ull << 31) || raw.z > 0xFFFFu || raw.w > 0xFFFFu) bad = true;
+        const uint64_t w = (recv ? RECV_BIT : 0ull) | ((uint64_t)(raw.z & 0xFFFFu) << 47) |
+                           ((uint64_t)(raw.w & 0xFFFFu) << 31) | (d & 0x7FFFFFFFull);
+        reinterpret_cast<unsigned long long*>(out)[g - first] = w;
+      } else if (FMT == 12) {
+        if (id >= (1ull << 47) || raw.z > 0xFFFFFFu || raw.w > 0xFFFFFFu) bad = true;
+        uint32_t* o = reinterpret_cast<uint32_t*>(out) + (g - first) * 3;
+        o[0] = (uint32_t)id;
+        o[1] = (uint32_t)((id >> 32) & 0x7FFFu) | (recv ? 0x8000u : 0u) | ((raw.z & 0xFFFFu) << 16);
+        o[2] = ((raw.z >> 16) & 0xFFu) | (raw.w << 8);
+      } else {
+        const uint64_t eid = g | (recv ? MS_EVENT_RECV : 0ull);
+        uint4* o = reinterpret_cast<uint4*>(out) + (g - first) * 2;
+        o[0] = make_uint4((uint32_t)eid, (uint32_t)(eid >> 32), (uint32_t)tnow, (uint32_t)((uint64_t)tnow >> 32));
+        o[1] = make_uint4((uint32_t)id, (uint32_t)(id >> 32), raw.z, raw.w);
+      }
+    }
+  }
+  if (bad) atomicOr(&plan->overflow, 1u);
+}
+
+__global__ void k_stream_finish(Params p, StreamPlan* plan, ms_jbatch* hdr, uint32_t format) {
+  if (threadIdx.x || blockIdx.x) return;
+  const DevState* st = p.st;
+  plan->journal_drained = plan->first + plan->count;
+  uint64_t dr = plan->drain_round;
+  while (dr < st->round) {
+    const RoundMeta* m = p.rmeta + ((uint32_t)dr & p.hist_mask);
+    if (m->round != dr || m->ev_base + m->ev_total > plan->journal_drained) break;
+    dr++;
+  }
+  plan->drain_round = dr;
+  plan->jraw_drained = dr < st->round ? p.rmeta[(uint32_t)dr & p.hist_mask].raw_base
+                                      : *reinterpret_cast<const volatile uint64_t*>(&st->jraw_cursor);
+  plan->more = st->next_event > plan->journal_drained ? 1u : 0u;
+  ms_jbatch b;
+  b.first_event = plan->first; b.n_events = plan->count; b.n_rounds = plan->n_rounds;
+  b.now = st->now; b.round = st->round; b.next_event = st->next_event;
+  b.format = format; b.overflow = plan->overflow; b.more = plan->more; b.error = st->error;
+  *hdr = b;
+  __threadfence_system();
+}
+
+// on the engine's own stream, between two rounds: the round kernels now see what has been packed
+__global__ void k_stream_apply(Params p, const StreamPlan* plan) {
+  if (threadIdx.x || blockIdx.x) return;
+  DevState* st = p.st;
+  const uint64_t a = plan->journal_drained, b = plan->drain_round, c = plan->jraw_drained;
+  if (a > st->journal_drained) st->journal_drained = a;
+  if (b > st->drain_round) st->drain_round = b;
+  if (c > st->jraw_drained) st->jraw_drained = c;
+}
+
 }  // namespace msd
 
 // ------------------------------------------------------------------ host-callable launchers
@@ -1979,6 +2101,22 @@ void msk_launch_round(const msd::Params* p, int n_classes, const uint32_t* caps,
 }
 
 void msk_barrier(const msd::Params* p, cudaStream_t s) { MS_LAUNCH(msd::k_barrier, 1, 32, 0, s, *p); }
+
+size_t msk_stream_plan_bytes() { return sizeof(msd::StreamPlan); }
+// plan -> pack -> finish: one batch of the journal into (host-mapped) `out`, header into `hdr`
+void msk_stream_batch(const msd::Params* p, void* plan, uint64_t cap_events, uint32_t cap_rounds, ms_jround* rows,
+                      void* out, ms_jbatch* hdr, int format, int n_sms, cudaStream_t s) {
+  msd::StreamPlan* pl = (msd::StreamPlan*)plan;
+  MS_LAUNCH(msd::k_stream_plan, 1, 32, 0, s, *p, pl, cap_events, cap_rounds, rows);
+  const unsigned blocks = (unsigned)n_sms * 16;
+  if (format == MS_JFMT_8) MS_LAUNCH(msd::k_journal_pack<8>, blocks, 256, 0, s, *p, pl, (unsigned char*)out);
+  else if (format == MS_JFMT_12) MS_LAUNCH(msd::k_journal_pack<12>, blocks, 256, 0, s, *p, pl, (unsigned char*)out);
+  else MS_LAUNCH(msd::k_journal_pack<32>, blocks, 256, 0, s, *p, pl, (unsigned char*)out);
+  MS_LAUNCH(msd::k_stream_finish, 1, 32, 0, s, *p, pl, hdr, (uint32_t)format);
+}
+void msk_stream_apply(const msd::Params* p, const void* plan, cudaStream_t s) {
+  MS_LAUNCH(msd::k_stream_apply, 1, 32, 0, s, *p, (const msd::StreamPlan*)plan);
+}
 
 void msk_journal_expand(const msd::Params* p, uint64_t r0, uint32_t n_rounds, uint64_t first, uint64_t count,
                         void* out_ev, void* out_body, int n_sms, cudaStream_t s) {

@@ -204,6 +204,45 @@ class Sim:
         bd = (np.concatenate(bds) if bds else np.zeros(0, dtype=JBODY_DTYPE)) if bodies else None
         return ev, bd
 
+    def run_streamed(self, until_ns, sink=None, fmt=_lib.JFMT_8, buf_events=0, decode=False):
+        """ms_run_streamed: run to until_ns while the journal streams into pinned host memory.
+        sink(batch_dict, rounds, events) is called per batch with numpy views that are only valid
+        during the call (rounds: JROUND_DTYPE; events: u64 / 3 x u32 / EVENT_DTYPE by format);
+        decode=True hands over EVENT_DTYPE records expanded by ms_journal_decode instead.
+        Returns (events, bytes) streamed."""
+        tot = [0, 0]
+        err = []
+
+        def _cb(ctx, bp, rounds_p, events_p):
+            try:
+                b = bp.contents
+                n = int(b.n_events)
+                tot[0] += n
+                tot[1] += n * int(b.format)
+                if sink is not None:
+                    rounds = np.ctypeslib.as_array(C.cast(rounds_p, C.POINTER(C.c_uint8)),
+                                                   (int(b.n_rounds) * 32,)).view(_lib.JROUND_DTYPE)
+                    if decode:
+                        ev = np.zeros(n, dtype=EVENT_DTYPE)
+                        self._chk(self.L.ms_journal_decode(bp, rounds_p, events_p, ev.ctypes.data))
+                    else:
+                        raw = np.ctypeslib.as_array(C.cast(events_p, C.POINTER(C.c_uint8)), (n * int(b.format),))
+                        ev = (raw.view("<u8") if b.format == 8 else raw.view("<u4").reshape(n, 3) if b.format == 12
+                              else raw.view(EVENT_DTYPE))
+                    info = {k: int(getattr(b, k)) for k, _ in _lib.JBatch._fields_}
+                    sink(info, rounds, ev)
+                return 0
+            except Exception as e:   # noqa: BLE001 -- must not propagate through the C frame
+                err.append(e)
+                return 1
+
+        cb = _lib.JOURNAL_SINK(_cb)
+        rc = self.L.ms_run_streamed(self.h, until_ns, fmt, buf_events, cb, None)
+        if err:
+            raise err[0]
+        self._chk(rc)
+        return tot[0], tot[1]
+
     def journal_written(self):
         return int(self.L.ms_journal_written(self.h))
 

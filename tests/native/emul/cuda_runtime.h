@@ -152,6 +152,9 @@ cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int dev);
 cudaError_t cudaMalloc(void** p, size_t bytes);
 template <class T> static inline cudaError_t cudaMalloc(T** p, size_t bytes) { return cudaMalloc((void**)p, bytes); }
 cudaError_t cudaFree(void* p);
+enum { cudaHostAllocDefault = 0, cudaHostAllocPortable = 1, cudaHostAllocMapped = 2 };
+static inline cudaError_t cudaHostAlloc(void** p, size_t bytes, unsigned) { *p = malloc(bytes); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind);
 cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr);
 cudaError_t cudaMemset(void* d, int v, size_t n);
