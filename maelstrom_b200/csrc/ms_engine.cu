@@ -678,7 +678,8 @@ static int build_sim(ms_sim* s, const ms_config* in) {
     if (blocks64 > (1ull << 30)) { set_err("timing wheel: calendar_slots x calendar_cap too large"); return MS_ERR_ARG; }
     P.cal_blk_log2 = blk_log2;
     P.cal_blocks = (uint32_t)blocks64;
-    P.cal_tab_cap = std::min<uint32_t>(P.cal_blocks, 4096u);
+    // chain table: 2 generations x slots x cal_tab_cap entries of 4 B, about 128 MB at most
+    P.cal_tab_cap = std::min<uint32_t>(P.cal_blocks, std::max<uint32_t>(4096u, (1u << 24) / c.calendar_slots));
     P.cal_slots = c.calendar_slots;
     void* ptr = nullptr;
     CK(cudaMalloc(&ptr, ((size_t)P.cal_blocks << blk_log2) * 48));
