@@ -705,9 +705,10 @@ def gpu_arm(args, rank, world, local_rank):
 
     # ---- arm B: end to end through host buffers (ops in from host memory, journal out to pinned host memory)
     e2e = None
-    if not args.no_e2e and world == 1:
+    if not args.no_e2e:
         total_b = R + W + K + 1
         sim, c0 = make_sim(mb, wl, total_b, False, local_rank, world)
+        lstats = (lambda: sim.sim.stats()["all"]) if world > 1 else (lambda: sim.stats()["all"])
         fmt = _lib.JFMT_8 if wl.n_nodes + wl.n_clients + 8 <= 65536 else _lib.JFMT_12
         pro = wl.prologue_ops(OP_DTYPE, c0, TYPES, flags)
         host_ops = [wl.ops(OP_DTYPE, t, 1, c0, TYPES, flags) for t in range(total_b)]
@@ -729,7 +730,9 @@ def gpu_arm(args, rank, world, local_rank):
             sim.schedule(host_ops[st])
             sim.run_streamed((st + 1) * step_ns, None, fmt=fmt, buf_events=args.stream_events)
         torch.cuda.synchronize()
-        s0 = sim.stats()["all"]["recv-count"]
+        if dist:
+            dist.barrier()
+        s0 = lstats()["recv-count"]
         t0 = time.perf_counter()
         for st in range(R + W, R + W + K):
             wl.between_steps(sim, st)
@@ -739,8 +742,10 @@ def gpu_arm(args, rank, world, local_rank):
                                          buf_events=args.stream_events)   # device -> host: the step's journal
             d2h += n_b
         torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
         t_e2e = time.perf_counter() - t0
-        msgs_e2e = sim.stats()["all"]["recv-count"] - s0
+        msgs_e2e = lstats()["recv-count"] - s0
         sim.close()
         e2e = {"seconds": t_e2e, "msgs": msgs_e2e, "h2d": h2d // max(K, 1), "d2h": d2h // max(K, 1), "fmt": fmt}
 
@@ -750,12 +755,16 @@ def gpu_arm(args, rank, world, local_rank):
 
     # ---- aggregate over ranks (max time, sum of work)
     if dist:
-        t = torch.tensor([ms_value, k_ms], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms_value, k_ms, e2e["seconds"] if e2e else 0.0], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        w = torch.tensor([recvs, sends, launches, alg_bytes, real_bytes], device="cuda", dtype=torch.float64)
+        w = torch.tensor([recvs, sends, launches, alg_bytes, real_bytes, e2e["msgs"] if e2e else 0,
+                          e2e["h2d"] if e2e else 0, e2e["d2h"] if e2e else 0], device="cuda", dtype=torch.float64)
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
         ms_value, k_ms = float(t[0]), float(t[1])
-        recvs, sends, launches, alg_bytes, real_bytes = (int(x) for x in w.tolist())
+        recvs, sends, launches, alg_bytes, real_bytes = (int(x) for x in w.tolist()[:5])
+        if e2e:
+            e2e["seconds"] = float(t[2])
+            e2e["msgs"], e2e["h2d"], e2e["d2h"] = (int(x) for x in w.tolist()[5:])
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9 / world if k_ms > 0 else 0.0     # per GPU
 
     if rank != 0:
@@ -792,10 +801,12 @@ def gpu_arm(args, rank, world, local_rank):
     if e2e:
         line["e2e"] = {"value": e2e["msgs"] / e2e["seconds"], "unit": "msgs/s", "h2d_bytes_per_step": e2e["h2d"],
                        "d2h_bytes_per_step": e2e["d2h"],
-                       "note": "host op buffers in every step (ms_schedule_ops); the whole journal of the step streamed into "
-                               "pinned host memory (ms_run_streamed, %d bytes per event = %d per message, packed on the device, "
-                               "double-buffered behind the running rounds); lazily expandable with ms_journal_decode"
-                               % (e2e["fmt"], 2 * e2e["fmt"])}
+                       "note": ("host op buffers in every step (ms_schedule_ops); the whole journal of the step streamed into "
+                                "pinned host memory (ms_run_streamed, %d bytes per event, packed on the device, copied out by "
+                                "the DMA engine behind the running rounds); lazily expandable with ms_journal_decode"
+                                % (e2e["fmt"] if world == 1 else 16)) +
+                               ("" if world == 1 else "; every rank uploads the ops and streams its own shard's events (event id + "
+                                "packed word each) over its own PCIe link: bytes are summed over the ranks")}
     if verify:
         line["verify"] = verify
         line["parity_digest_ok"] = verify["parity_digest_ok"]

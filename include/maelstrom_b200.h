@@ -197,6 +197,16 @@ int64_t ms_send(ms_sim* sim, uint32_t src, uint32_t dest, const ms_body* body);
  * timeout elapsed, <0 error.  Advances the simulation while waiting. */
 int ms_recv(ms_sim* sim, uint32_t endpoint, int64_t timeout_virtual_ns, ms_msg* out);
 
+/* The same two calls with the protocol's JSON envelope (doc/protocol.md:36-45), for callers that hold what a
+ * node process prints and reads.  ms_send_json = process/parse-msg + net/check-message (process.clj:26-66,
+ * net.clj:27-37: {"src","dest","body"} + optional integer "id", nothing else; a malformed line is MS_ERR_ARG
+ * with the reference's message) + net/send!.  ms_recv_json = net/recv! + the line process/stdin-thread would
+ * write (process.clj:162): {"id","src","dest","body"} with the body's keys sorted; returns 1 / 0 / <0 like
+ * ms_recv.  Payloads the device does not interpret (an echo string, a txn's micro-ops, extra keys) are kept
+ * on the host and re-attached on delivery. */
+int64_t ms_send_json(ms_sim* sim, const char* line);
+int     ms_recv_json(ms_sim* sim, uint32_t endpoint, int64_t timeout_virtual_ns, char* out, size_t cap);
+
 /* Upload a time-sorted schedule of client ops (appends). */
 int ms_schedule_ops(ms_sim* sim, const ms_op* ops, size_t n);
 
@@ -220,7 +230,10 @@ int ms_net_set_loss(ms_sim* sim, double p);
 int ms_net_partition(ms_sim* sim, const uint32_t* component_id, size_t n);
 
 /* ------------------------------------------------------------------ journal: jepsen-os + net.journal */
-/* j/journal + j/close! (net.clj:128-137): stream drained events to a file. */
+/* j/journal + j/close! (net.clj:128-137): stream drained events to a file.  A path ending in
+ * ".fressian" gets the reference's own format -- Fressian `Event{id time type message}` objects as
+ * net/journal.clj:55-92 writes them, one stripe (net-journal/0.fressian), needs journal_level 2 --
+ * anything else the raw ms_event / ms_jbody records behind a 16-byte header. */
 int ms_journal_open(ms_sim* sim, const char* path);
 int ms_journal_close(ms_sim* sim);
 /* Copy the next events (event_id order) into caller buffers; bodies may be NULL. */
@@ -229,9 +242,10 @@ uint64_t ms_journal_written(ms_sim* sim);
 
 /* Streaming the journal to a throughput-bound consumer (the writer side of net/journal.clj:205-239).
  * ms_run_streamed advances the simulation like ms_run and hands the journal over in batches while the
- * next rounds are already running: the device packs events, in event-id order, straight into pinned
- * host memory (two buffers in turn, written over PCIe by the packing kernel), and `sink` is called
- * once per batch from the calling thread.  Event k of a batch has event id first_event + k; its round
+ * next rounds are already running: the device packs events, in event-id order, into staging buffers
+ * that the copy engine moves into pinned host memory (two buffers in turn), and `sink` is called once
+ * per batch from the calling thread (rounds of batch i, copy of batch i-1 and the sink on batch i-2
+ * overlap).  Event k of a batch has event id first_event + k; its round
  * (hence its virtual time) is the last row of `rounds` whose ev_base is <= that id.
  *   MS_JFMT_EVENT  32-B ms_event, as ms_journal_drain returns them
  *   MS_JFMT_12     96 bits: id (47) | recv (1) in words 0-1, src (24) and dest (24) in words 1-2:
@@ -239,8 +253,10 @@ uint64_t ms_journal_written(ms_sim* sim);
  *   MS_JFMT_8      64 bits: recv << 63 | src << 47 | dest << 31 | (id - id_ref of the round); needs
  *                  endpoint indices < 65536 and every message received within 2^30 ids of the newest
  *                  one: otherwise the batch header has overflow = 1 and the call fails with MS_ERR_CAPACITY
- * ms_journal_decode expands a batch into ms_event records (lazily, on the host). */
-enum { MS_JFMT_EVENT = 32, MS_JFMT_12 = 12, MS_JFMT_8 = 8 };
+ * ms_journal_decode expands a batch into ms_event records (lazily, on the host); a sharded batch comes
+ * out in the order it was packed (sort by event_id, or scatter by event_id - first_event, to merge shards). */
+enum { MS_JFMT_EVENT = 32, MS_JFMT_12 = 12, MS_JFMT_8 = 8,
+       MS_JFMT_16 = 16 };  /* what a sharded run hands over for MS_JFMT_8 / MS_JFMT_12: {event id | recv << 63, the MS_JFMT_8 word} */
 typedef struct ms_jround {   /* one row per round that has events in the batch */
   uint64_t round;
   int64_t  time_ns;          /* Event.time of every event of the round */
@@ -253,6 +269,9 @@ typedef struct ms_jbatch {
   int64_t  now;              /* simulation state when the batch was cut */
   uint64_t round, next_event;
   uint32_t format, overflow, more, error;
+  uint64_t range_events;     /* events [first_event, first_event + range_events) are covered by this batch; == n_events on
+                                one GPU.  Sharded runs: n_events counts this shard's events only, in no particular order,
+                                each with its event id (MS_JFMT_16, or MS_JFMT_EVENT); the shards' batches partition the range */
 } ms_jbatch;
 typedef int (*ms_journal_sink)(void* ctx, const ms_jbatch* batch, const ms_jround* rounds, const void* events);
 /* buf_events = capacity of each of the two host buffers in events (0 = 1 << 24).  A non-zero return

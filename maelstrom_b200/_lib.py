@@ -46,12 +46,13 @@ class Body(C.Structure):
 class JBatch(C.Structure):      # ms_jbatch
     _fields_ = [("first_event", C.c_uint64), ("n_events", C.c_uint64), ("n_rounds", C.c_uint64),
                 ("now", C.c_int64), ("round", C.c_uint64), ("next_event", C.c_uint64),
-                ("format", C.c_uint32), ("overflow", C.c_uint32), ("more", C.c_uint32), ("error", C.c_uint32)]
+                ("format", C.c_uint32), ("overflow", C.c_uint32), ("more", C.c_uint32), ("error", C.c_uint32),
+                ("range_events", C.c_uint64)]
 
 
 JROUND_DTYPE = np.dtype([("round", "<u8"), ("time_ns", "<i8"), ("ev_base", "<u8"), ("id_ref", "<u8")])
 JOURNAL_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(JBatch), C.c_void_p, C.c_void_p)
-JFMT_EVENT, JFMT_12, JFMT_8 = 32, 12, 8
+JFMT_EVENT, JFMT_12, JFMT_8, JFMT_16 = 32, 12, 8, 16
 
 # every symbol include/maelstrom_b200.h declares: (restype, argtypes)
 _P = C.c_void_p
@@ -67,6 +68,8 @@ SYMBOLS = {
     "ms_endpoint_index": (C.c_int, [_P, C.c_char_p]),
     "ms_send": (C.c_int64, [_P, C.c_uint32, C.c_uint32, C.POINTER(Body)]),
     "ms_recv": (C.c_int, [_P, C.c_uint32, C.c_int64, _P]),
+    "ms_send_json": (C.c_int64, [_P, C.c_char_p]),
+    "ms_recv_json": (C.c_int, [_P, C.c_uint32, C.c_int64, C.c_char_p, C.c_size_t]),
     "ms_schedule_ops": (C.c_int, [_P, _P, C.c_size_t]),
     "ms_step": (C.c_int, [_P, C.c_uint64]),
     "ms_run": (C.c_int, [_P, C.c_int64]),

@@ -86,7 +86,7 @@ struct NetParams {
   uint32_t scale;            // 10^k after k slow! calls
   uint32_t pair_active;      // any drop! since the last heal!
   uint32_t comp_active;      // bulk partition installed
-  uint32_t pad;
+  uint32_t any_removed;      // some endpoint has been removed (remove-node! / stop-node!): sends check their endpoints' kinds
 };
 
 struct Params {
@@ -116,6 +116,9 @@ struct Params {
   uint64_t* rt_cnt_sh[8];
   uint32_t* bar_sh[8];       // bar_sh[g][s] = last barrier epoch shard s signalled to shard g
   uint32_t  hist, hist_mask, t_max, n_classes;
+  uint32_t  split_commit;    // the round is committed by its own launch(es) after the round kernels (sharded runs, very many tickets)
+  uint64_t* cm_blk;          // three-phase commit: per-block sums / offsets (nullptr = single-CTA k_commit)
+  uint32_t* cm_flags;        // [0] zero-latency pending, [1] row being committed, [2] phase B committed
   uint32_t* cls_list;        // [2][4][t_max] tickets per size class
   uint32_t  cls_cap[4];      // ascending window capacities of the classes
   // raw journal: 16-B records, chunk per (round, ticket); bodies (level 2) 32 B at the same index

@@ -15,6 +15,8 @@
 #include <vector>
 
 #include "ms_device.cuh"
+#include "ms_fressian.h"
+#include "ms_json.h"
 
 using namespace msd;
 
@@ -31,11 +33,22 @@ void msk_journal_expand(const msd::Params* p, uint64_t r0, uint32_t n_rounds, ui
                         void* out_ev, void* out_body, int n_sms, cudaStream_t s);
 size_t msk_stream_plan_bytes();
 void msk_stream_batch(const msd::Params* p, void* plan, uint64_t cap_events, uint32_t cap_rounds, ms_jround* rows,
-                      void* out, ms_jbatch* hdr, int format, int n_sms, cudaStream_t s);
-void msk_stream_apply(const msd::Params* p, const void* plan, cudaStream_t s);
+                      void* out, ms_jbatch* hdr, int format, int n_sms, cudaStream_t s, uint32_t parity);
+void msk_stream_apply(const msd::Params* p, const void* plan, cudaStream_t s, uint32_t parity);
 }
 
 static thread_local std::string g_err;
+
+// body.type names of the protocol (doc/workloads.md, doc/services.md)
+static const struct { uint16_t code; const char* name; } kTypeNames[] = {
+    {MS_T_INIT, "init"}, {MS_T_INIT_OK, "init_ok"}, {MS_T_ERROR, "error"}, {MS_T_ECHO, "echo"}, {MS_T_ECHO_OK, "echo_ok"},
+    {MS_T_TOPOLOGY, "topology"}, {MS_T_TOPOLOGY_OK, "topology_ok"}, {MS_T_BROADCAST, "broadcast"},
+    {MS_T_BROADCAST_OK, "broadcast_ok"}, {MS_T_READ, "read"}, {MS_T_READ_OK, "read_ok"}, {MS_T_ADD, "add"},
+    {MS_T_ADD_OK, "add_ok"}, {MS_T_REPLICATE_ONE, "replicate_one"}, {MS_T_REPLICATE_FULL, "replicate_full"},
+    {MS_T_WRITE, "write"}, {MS_T_WRITE_OK, "write_ok"}, {MS_T_CAS, "cas"}, {MS_T_CAS_OK, "cas_ok"}, {MS_T_TS, "ts"},
+    {MS_T_TS_OK, "ts_ok"}, {MS_T_REQUEST_VOTE, "request_vote"}, {MS_T_REQUEST_VOTE_RES, "request_vote_res"},
+    {MS_T_APPEND_ENTRIES, "append_entries"}, {MS_T_APPEND_ENTRIES_RES, "append_entries_res"}, {MS_T_TXN, "txn"},
+    {MS_T_TXN_OK, "txn_ok"}};
 
 static void set_err(const std::string& s) { g_err = s; }
 
@@ -139,7 +152,28 @@ struct ms_sim {
   uint32_t* d_tick_off = nullptr;
   size_t d_sched_cap = 0, d_tick_cap = 0;
   bool pair_alloc = false;
+  // JSON data plane (ms_send_json / ms_recv_json): payloads the device does not interpret stay here,
+  // keyed by the handle that travels in p1; types without a device handler get codes from 1000 up
+  std::unordered_map<uint64_t, std::string> blobs;
+  uint64_t next_blob = 0;
+  std::unordered_map<std::string, uint16_t> dyn_types;
+  std::vector<std::string> dyn_names;
+  std::string type_name(uint16_t code) const {
+    for (const auto& t : kTypeNames) if (t.code == code) return t.name;
+    if (code >= 1000 && (size_t)(code - 1000) < dyn_names.size()) return dyn_names[code - 1000];
+    return "type-" + std::to_string(code);
+  }
+  uint16_t type_code(const std::string& name) {
+    for (const auto& t : kTypeNames) if (name == t.name) return t.code;
+    auto it = dyn_types.find(name);
+    if (it != dyn_types.end()) return it->second;
+    const uint16_t code = (uint16_t)(1000 + dyn_names.size());
+    dyn_types[name] = code;
+    dyn_names.push_back(name);
+    return code;
+  }
   FILE* jfile = nullptr;
+  msf::Writer* jfress = nullptr;    // non-null: the journal file is a Fressian stripe (net/journal.clj)
   // journal expansion (K3) staging
   void* stage_ev = nullptr;
   void* stage_body = nullptr;
@@ -164,8 +198,11 @@ struct ms_sim {
   std::vector<void*> peer_ptrs;     // opened IPC mappings
   // journal streaming (ms_run_streamed): two pinned host buffers written by the packing kernel
   cudaStream_t jstream = nullptr;
-  cudaEvent_t j_rounds_done[2] = {nullptr, nullptr}, j_packed[2] = {nullptr, nullptr};
-  unsigned char* jhost[2] = {nullptr, nullptr};   // [ms_jbatch | rows | events]
+  cudaEvent_t j_rounds_done[2] = {nullptr, nullptr}, j_copied[2] = {nullptr, nullptr};
+  cudaEvent_t j_packed[4] = {nullptr, nullptr, nullptr, nullptr};
+  unsigned char* jdev[2] = {nullptr, nullptr};    // device staging: [ms_jbatch | rows | events]
+  unsigned char* jhost[2] = {nullptr, nullptr};   // pinned: events of a batch
+  unsigned char* jhdr[4] = {nullptr, nullptr, nullptr, nullptr};   // pinned: [ms_jbatch | rows] of a batch
   size_t jhost_events = 0;
   int jhost_format = 0;
   void* jplan = nullptr;
@@ -287,7 +324,7 @@ struct ms_sim {
       for (int c = 0; c < n_classes; c++) grids[c] = std::max(1, std::min(class_grid[c], T));
       if (P.n_shards <= 1) {
         msk_launch_round(&P, n_classes, class_cap, class_threads, grids, use_calendar ? 1 : 0, stream, a, b, 15, aux_streams, aux_events);
-        if (!capturing()) launches += (use_calendar ? 2 : 1) + n_classes;
+        if (!capturing()) launches += (use_calendar ? 2 : 1) + n_classes + (P.split_commit ? (P.cm_blk ? 3 : 1) : 0);
       } else {
         // sharded: [release (peer writes) | barrier] snapshot | barrier | round kernels (peer writes) | barrier | commit
         if (use_calendar) {
@@ -381,12 +418,58 @@ struct ms_sim {
       if (rc) return rc;
       if (!n) break;
       for (size_t i = 0; i < n; i++) {
+        if (jfress) { write_fressian_event(ev[i], bd[i]); continue; }
         fwrite(&ev[i], sizeof(ms_event), 1, jfile);
         if (!bd.empty()) fwrite(&bd[i], sizeof(ms_jbody), 1, jfile);
       }
     }
     fflush(jfile);
     return MS_OK;
+  }
+
+  // Event{id time type message} as maelstrom.net.journal writes it (journal.clj:70-92).  The body map
+  // is rebuilt from the fixed-size record: reserved keys as they are (doc/protocol.md:36-45), the
+  // payload under the key the workload's schema gives it (doc/workloads.md); what the device only
+  // holds a handle or a size for is journaled as that handle / size.
+  void write_fressian_event(const ms_event& e, const ms_jbody& b) {
+    const std::string tname = type_name(b.type);
+    std::vector<msf::Writer::KV> kv;
+    kv.push_back({"type", true, 0, tname});
+    if (b.flags & MS_F_MSG_ID) kv.push_back({"msg_id", false, (int64_t)b.msg_id, ""});
+    if (b.flags & MS_F_REPLY) kv.push_back({"in_reply_to", false, (int64_t)b.in_reply_to, ""});
+    const bool kv_peer = (e.src < kinds.size() && (kinds[e.src] & 0x7F) == MS_KIND_SERVICE) ||
+                         (e.dest < kinds.size() && (kinds[e.dest] & 0x7F) == MS_KIND_SERVICE) || cfg.workload == MS_W_RAFT;
+    const int64_t lo = (int64_t)(b.p1 & 0xFFFFFFFFull), hi = (int64_t)(b.p1 >> 32);
+    switch (b.type) {
+      case MS_T_BROADCAST: kv.push_back({"message", false, (int64_t)b.p0, ""}); break;
+      case MS_T_ADD: case MS_T_REPLICATE_ONE: kv.push_back({"element", false, (int64_t)b.p0, ""}); break;
+      case MS_T_ERROR: kv.push_back({"code", false, (int64_t)b.p0, ""}); break;
+      case MS_T_ECHO: case MS_T_ECHO_OK: kv.push_back({"echo_handle", false, (int64_t)b.p1, ""}); break;
+      case MS_T_READ: if (kv_peer) kv.push_back({"key", false, (int64_t)b.p0, ""}); break;
+      case MS_T_READ_OK:
+        if (kv_peer) kv.push_back({"value", false, (int64_t)b.p1, ""});
+        else kv.push_back({"count", false, (int64_t)b.p0, ""});
+        break;
+      case MS_T_WRITE: kv.push_back({"key", false, (int64_t)b.p0, ""}); kv.push_back({"value", false, lo, ""}); break;
+      case MS_T_CAS:
+        kv.push_back({"key", false, (int64_t)b.p0, ""}); kv.push_back({"from", false, lo, ""}); kv.push_back({"to", false, hi, ""});
+        break;
+      case MS_T_TS_OK: kv.push_back({"ts", false, (int64_t)b.p1, ""}); break;
+      case MS_T_REPLICATE_FULL: kv.push_back({"count", false, (int64_t)b.p0, ""}); kv.push_back({"snapshot", false, (int64_t)b.p1, ""}); break;
+      case MS_T_REQUEST_VOTE:
+        kv.push_back({"term", false, (int64_t)b.p0, ""}); kv.push_back({"last_log_index", false, lo, ""});
+        kv.push_back({"last_log_term", false, hi, ""});
+        break;
+      case MS_T_REQUEST_VOTE_RES: kv.push_back({"term", false, (int64_t)b.p0, ""}); kv.push_back({"vote_granted", false, lo, ""}); break;
+      case MS_T_APPEND_ENTRIES: kv.push_back({"term", false, (int64_t)b.p0, ""}); kv.push_back({"entries_handle", false, (int64_t)b.p1, ""}); break;
+      case MS_T_APPEND_ENTRIES_RES: kv.push_back({"term", false, (int64_t)b.p0, ""}); kv.push_back({"success", false, lo, ""}); break;
+      case MS_T_TXN: kv.push_back({"txn_handle", false, (int64_t)b.p1, ""}); break;
+      case MS_T_TXN_OK: kv.push_back({"read_version", false, lo, ""}); kv.push_back({"written_version", false, hi, ""}); break;
+      default: break;
+    }
+    auto name_of = [&](uint32_t i) { return i < names.size() ? names[i] : std::to_string(i); };
+    jfress->write_event((int64_t)(e.event_id & ~MS_EVENT_RECV), e.time_ns, (e.event_id & MS_EVENT_RECV) != 0, (int64_t)e.msg_id,
+                        name_of(e.src), name_of(e.dest), kv);
   }
 
   // Uploads only ops[first..) (the schedule is append-only) and refreshes tick_off.
@@ -490,7 +573,9 @@ static int build_sim(ms_sim* s, const ms_config* in) {
   }
   {
     const uint32_t ladder[4] = {128, 512, 2048, 32768};
-    const int thr[4] = {64, 128, 256, 512};
+    // g-set: a node's step ORs whole bitmap rows (one word per thread and pass): wide CTAs even for short windows
+    const int thr_default[4] = {64, 128, 256, 512}, thr_gset[4] = {256, 256, 256, 512};
+    const int* thr = c.workload == MS_W_GSET ? thr_gset : thr_default;
     s->n_classes = 0;
     for (int k = 0; k < 4; k++) {
       const uint32_t cap = std::min(ladder[k], c.max_window);
@@ -733,6 +818,13 @@ static int build_sim(ms_sim* s, const ms_config* in) {
     for (int k = 0; k < s->n_classes; k++)
       s->class_grid[k] = s->n_sms * msk_round_occupancy(s->class_threads[k], msk_round_smem_bytes(s->class_cap[k]));
     if ((rc = s->dalloc(&P.cls_list, (size_t)2 * 4 * P.t_max))) return rc;
+    // who commits a round: the last ticket inside k_round (one GPU, a few thousand tickets), or
+    // launches of their own after the round kernels (sharded runs; tens of thousands of tickets)
+    P.split_commit = (c.n_shards > 1 || P.t_max > 16384u) ? 1u : 0u;
+    if (P.t_max > 16384u) {
+      if ((rc = s->dalloc(&P.cm_blk, (size_t)(P.t_max + 1023) / 1024 + 1))) return rc;
+      if ((rc = s->dalloc(&P.cm_flags, 4))) return rc;
+    }
     for (int g = 0; g < 8; g++) { P.ring_sh[g] = nullptr; P.tail_sh[g] = nullptr; P.head_sh[g] = nullptr; P.rt_cnt_sh[g] = nullptr; }
     P.ring_sh[c.shard_id] = P.ring;
     P.tail_sh[c.shard_id] = P.tail;
@@ -777,7 +869,12 @@ void ms_destroy(ms_sim* s) {
   for (void* p : s->allocs) cudaFree(p);
   for (int k = 0; k < 2; k++) {
     if (s->jhost[k]) cudaFreeHost(s->jhost[k]);
+    if (s->jdev[k]) cudaFree(s->jdev[k]);
     if (s->j_rounds_done[k]) cudaEventDestroy(s->j_rounds_done[k]);
+    if (s->j_copied[k]) cudaEventDestroy(s->j_copied[k]);
+  }
+  for (int k = 0; k < 4; k++) {
+    if (s->jhdr[k]) cudaFreeHost(s->jhdr[k]);
     if (s->j_packed[k]) cudaEventDestroy(s->j_packed[k]);
   }
   if (s->jstream) cudaStreamDestroy(s->jstream);
@@ -811,7 +908,8 @@ int ms_stop_nodes(ms_sim* s) {
     if (!(s->kinds[i] & kRemoved)) { s->by_name.erase(s->names[i]); s->kinds[i] |= kRemoved; }
   }
   CK(cudaMemcpy(s->P.kind, s->kinds.data(), s->cfg.n_nodes, cudaMemcpyHostToDevice));
-  return MS_OK;
+  s->np.any_removed = 1;
+  return s->push_np();
 }
 
 int ms_add_endpoint(ms_sim* s, const char* id, int kind) {
@@ -881,7 +979,8 @@ int ms_remove_endpoint(ms_sim* s, uint32_t idx) {
   s->by_name.erase(s->names[idx]);
   s->kinds[idx] |= kRemoved;   // the kind stays readable: a removed "c*" endpoint is still a client by name (util.clj:7-16)
   CK(cudaMemcpy(s->P.kind + idx, &s->kinds[idx], 1, cudaMemcpyHostToDevice));
-  return MS_OK;
+  s->np.any_removed = 1;
+  return s->push_np();
 }
 
 int ms_endpoint_index(ms_sim* s, const char* id) {
@@ -891,8 +990,14 @@ int ms_endpoint_index(ms_sim* s, const char* id) {
   return (int)it->second;
 }
 
+static int64_t send_locked(ms_sim* s, uint32_t src, uint32_t dest, const ms_body* b);
+
 int64_t ms_send(ms_sim* s, uint32_t src, uint32_t dest, const ms_body* b) {
   std::lock_guard<std::mutex> g(s->mu);
+  return send_locked(s, src, dest, b);
+}
+
+static int64_t send_locked(ms_sim* s, uint32_t src, uint32_t dest, const ms_body* b) {
   if (src >= s->P.n_ep || (s->kinds[src] & kRemoved)) { set_err("Invalid source for message"); return MS_ERR_NODE_NOT_FOUND; }
   if (dest >= s->P.n_ep || (s->kinds[dest] & kRemoved)) { set_err("Invalid dest for message"); return MS_ERR_NODE_NOT_FOUND; }
   if (!b) { set_err("null body"); return MS_ERR_ARG; }
@@ -995,8 +1100,7 @@ int ms_run(ms_sim* s, int64_t until) {
   return MS_OK;
 }
 
-int ms_recv(ms_sim* s, uint32_t e, int64_t timeout, ms_msg* out) {
-  std::lock_guard<std::mutex> g(s->mu);
+static int recv_locked(ms_sim* s, uint32_t e, int64_t timeout, ms_msg* out) {
   if (e >= s->P.n_ep || (s->kinds[e] & kRemoved)) { set_err("No such node in network"); return MS_ERR_NODE_NOT_FOUND; }
   const int64_t give_up = (timeout > INT64_MAX - s->hs.now) ? INT64_MAX : s->hs.now + timeout;
   int64_t stall_now = s->hs.now;
@@ -1016,6 +1120,157 @@ int ms_recv(ms_sim* s, uint32_t e, int64_t timeout, ms_msg* out) {
     if (!rc && s->hs.rounds_run == r0) { set_err("simulation made no progress (device refuses to run rounds)"); return MS_ERR_SIM; }
     if (rc) return rc;
   }
+}
+
+int ms_recv(ms_sim* s, uint32_t e, int64_t timeout, ms_msg* out) {
+  std::lock_guard<std::mutex> g(s->mu);
+  return recv_locked(s, e, timeout, out);
+}
+
+// ------------------------------------------------------------------ JSON data plane
+
+// parse-msg + check-message (process.clj:26-66, net.clj:27-37), then the body's fixed-size encoding
+int64_t ms_send_json(ms_sim* s, const char* line) {
+  std::lock_guard<std::mutex> g(s->mu);
+  if (!line) { set_err("null line"); return MS_ERR_ARG; }
+  msj::Value m;
+  std::string perr;
+  if (!msj::Parser(line).parse(m, perr)) {
+    set_err(std::string("Node printed a line to STDOUT which was not well-formed JSON (") + perr + "):\n" + line +
+            "\nDid you mean to encode this line as JSON? Or was this line intended for STDERR? See doc/protocol.md for more guidance.");
+    return MS_ERR_ARG;
+  }
+  // the Message schema: {:src NodeId, :dest NodeId, :body Any, (optional-key :id) Int}, nothing else
+  std::string why;
+  if (m.kind != msj::Value::Obj) why = "(not (map? message))";
+  else {
+    for (const auto& kv : m.obj)
+      if (kv.first != "src" && kv.first != "dest" && kv.first != "body" && kv.first != "id") why += "{:" + kv.first + " disallowed-key} ";
+    const msj::Value* v;
+    if (!(v = m.get("src"))) why += "{:src missing-required-key} "; else if (v->kind != msj::Value::Str) why += "{:src (not (instance? java.lang.String))} ";
+    if (!(v = m.get("dest"))) why += "{:dest missing-required-key} "; else if (v->kind != msj::Value::Str) why += "{:dest (not (instance? java.lang.String))} ";
+    if (!m.get("body")) why += "{:body missing-required-key} ";
+    if ((v = m.get("id")) && v->kind != msj::Value::Int) why += "{:id (not (integer? id))} ";
+  }
+  const msj::Value* body = why.empty() ? m.get("body") : nullptr;
+  if (why.empty() && (body->kind != msj::Value::Obj || !body->get("type") || body->get("type")->kind != msj::Value::Str))
+    why = "{:body (not a map with a string :type, doc/protocol.md:36-45)}";
+  if (!why.empty()) {
+    set_err(std::string("Malformed network message. Node tried to send the following message via STDOUT:\n\n") + line +
+            "\n\nThis is malformed because:\n\n" + why + "\n\nSee doc/protocol.md for more guidance.");
+    return MS_ERR_ARG;
+  }
+  auto idx = [&](const std::string& name, const char* what) -> int64_t {
+    auto it = s->by_name.find(name);
+    if (it == s->by_name.end()) { set_err(std::string("Invalid ") + what + " for message " + line); return MS_ERR_NODE_NOT_FOUND; }   // net.clj:172-175
+    return it->second;
+  };
+  const int64_t src = idx(m.get("src")->s, "source"), dest = src < 0 ? src : idx(m.get("dest")->s, "dest");
+  if (src < 0 || dest < 0) return MS_ERR_NODE_NOT_FOUND;
+  const std::string t = body->get("type")->s;
+  ms_body b;
+  memset(&b, 0, sizeof b);
+  b.type = s->type_code(t);
+  std::map<std::string, std::string> rest;          // what no fixed field carries
+  for (const auto& kv : body->obj) {
+    const msj::Value& v = kv.second;
+    const bool is_int = v.kind == msj::Value::Int;
+    if (kv.first == "type") continue;
+    if (kv.first == "msg_id" && is_int) { b.flags |= MS_F_MSG_ID; b.msg_id = (uint32_t)v.i; }
+    else if (kv.first == "in_reply_to" && is_int) { b.flags |= MS_F_REPLY; b.in_reply_to = (uint32_t)v.i; }
+    else if (t == "broadcast" && kv.first == "message" && is_int) b.p0 = (uint32_t)v.i;
+    else if ((t == "add" || t == "replicate_one") && kv.first == "element" && is_int) b.p0 = (uint32_t)v.i;
+    else if (t == "error" && kv.first == "code" && is_int) b.p0 = (uint32_t)v.i;
+    else if ((t == "read" || t == "write" || t == "cas") && kv.first == "key" && is_int) b.p0 = (uint32_t)v.i;
+    else if (t == "write" && kv.first == "value" && is_int) b.p1 = (b.p1 & ~0xFFFFFFFFull) | (uint32_t)v.i;
+    else if (t == "cas" && kv.first == "from" && is_int) b.p1 = (b.p1 & ~0xFFFFFFFFull) | (uint32_t)v.i;
+    else if (t == "cas" && kv.first == "to" && is_int) b.p1 = (b.p1 & 0xFFFFFFFFull) | ((uint64_t)(uint32_t)v.i << 32);
+    else if (t == "cas" && kv.first == "create_if_not_exists") { if (v.kind == msj::Value::Bool && v.b) b.flags |= MS_F_CREATE; }
+    else {
+      if (t == "txn" && kv.first == "txn" && v.kind == msj::Value::Arr)
+        for (const msj::Value& op : v.arr)
+          if (op.kind == msj::Value::Arr && !op.arr.empty() && op.arr[0].kind == msj::Value::Str && op.arr[0].s == "append") b.flags |= MS_F_APPENDS;
+      rest[kv.first] = v.text;
+    }
+  }
+  if (!rest.empty()) {
+    if (t == "write" || t == "cas") { set_err("write / cas bodies carry key, value / from, to only"); return MS_ERR_ARG; }
+    b.p1 = ++s->next_blob;
+    s->blobs[b.p1] = msj::object(rest);
+  }
+  return send_locked(s, (uint32_t)src, (uint32_t)dest, &b);
+}
+
+// the line a node process would read from STDIN (process.clj:162): {"id","src","dest","body"}
+int ms_recv_json(ms_sim* s, uint32_t e, int64_t timeout, char* out, size_t cap) {
+  std::lock_guard<std::mutex> g(s->mu);
+  ms_msg m;
+  const int rc = recv_locked(s, e, timeout, &m);
+  if (rc != 1) return rc;
+  std::map<std::string, std::string> body;
+  const std::string t = s->type_name(m.type);
+  body["type"] = msj::quote(t);
+  if (m.flags & MS_F_MSG_ID) body["msg_id"] = std::to_string(m.msg_id);
+  if (m.flags & MS_F_REPLY) body["in_reply_to"] = std::to_string(m.in_reply_to);
+  const bool kv_peer = (m.src < s->kinds.size() && (s->kinds[m.src] & 0x7F) == MS_KIND_SERVICE) || s->cfg.workload == MS_W_RAFT;
+  const uint32_t lo = (uint32_t)m.p1, hi = (uint32_t)(m.p1 >> 32);
+  bool blob_ok = true;
+  switch (m.type) {
+    case MS_T_BROADCAST: body["message"] = std::to_string(m.p0); break;
+    case MS_T_ADD: case MS_T_REPLICATE_ONE: body["element"] = std::to_string(m.p0); break;
+    case MS_T_ERROR: {
+      static const struct { uint32_t code; const char* text; } kErr[] = {   // resources/errors.edn
+          {0, "timeout"}, {1, "node-not-found"}, {10, "not-supported"}, {11, "temporarily-unavailable"}, {12, "malformed-request"},
+          {13, "crash"}, {14, "abort"}, {20, "key-does-not-exist"}, {21, "key-already-exists"}, {22, "precondition-failed"}, {30, "txn-conflict"}};
+      body["code"] = std::to_string(m.p0);
+      const char* text = "unknown";
+      for (const auto& x : kErr) if (x.code == m.p0) text = x.text;
+      body["text"] = msj::quote(text);
+      break;
+    }
+    case MS_T_READ: if (kv_peer || (m.dest < s->kinds.size() && (s->kinds[m.dest] & 0x7F) == MS_KIND_SERVICE)) body["key"] = std::to_string(m.p0); break;
+    case MS_T_WRITE: body["key"] = std::to_string(m.p0); body["value"] = std::to_string(lo); blob_ok = false; break;
+    case MS_T_CAS:
+      body["key"] = std::to_string(m.p0); body["from"] = std::to_string(lo); body["to"] = std::to_string(hi); blob_ok = false;
+      if (m.flags & MS_F_CREATE) body["create_if_not_exists"] = "true";
+      break;
+    case MS_T_TS_OK: body["ts"] = std::to_string(m.p1); blob_ok = false; break;
+    case MS_T_TXN_OK: body["versions"] = "[" + std::to_string(lo) + "," + std::to_string(hi) + "]"; blob_ok = false; break;
+    case MS_T_READ_OK:
+      if (kv_peer) { body["value"] = std::to_string(lo); blob_ok = false; }
+      else if (m.src < s->cfg.n_nodes && s->P.bitmap) {
+        // the device message carries the set size; the members are read back from the node
+        // (broadcast: `messages`, workload/broadcast.clj:33-35; g-set: `value`, g_set.rb:14)
+        std::vector<uint32_t> w(s->P.bm_words);
+        if (cudaMemcpy(w.data(), s->P.bitmap + (size_t)m.src * s->P.bm_words, w.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess) {
+          set_err("ms_recv_json: cannot read the node's set"); return MS_ERR_CUDA;
+        }
+        std::string list = "[";
+        uint32_t n = 0;
+        for (uint32_t i = 0; i < s->P.bm_words && n < m.p0; i++)
+          for (uint32_t bit = 0; bit < 32 && n < m.p0; bit++)
+            if ((w[i] >> bit) & 1u) { list += (n ? "," : "") + std::to_string(i * 32 + bit); n++; }
+        body[s->cfg.workload == MS_W_GSET ? "value" : "messages"] = list + "]";
+        blob_ok = false;
+      }
+      break;
+    default: break;
+  }
+  if (blob_ok && m.p1) {
+    auto it = s->blobs.find(m.p1);
+    if (it != s->blobs.end()) {                      // merge the stored object's members
+      msj::Value v;
+      std::string perr;
+      if (msj::Parser(it->second).parse(v, perr) && v.kind == msj::Value::Obj)
+        for (const auto& kv : v.obj) if (!body.count(kv.first)) body[kv.first] = kv.second.text;
+    }
+  }
+  auto name_of = [&](uint32_t i) { return i < s->names.size() ? s->names[i] : std::to_string(i); };
+  const std::string line = "{\"id\":" + std::to_string(m.id) + ",\"src\":" + msj::quote(name_of(m.src)) + ",\"dest\":" +
+                           msj::quote(name_of(m.dest)) + ",\"body\":" + msj::object(body) + "}";
+  if (!out || line.size() + 1 > cap) { set_err("ms_recv_json: buffer too small for " + std::to_string(line.size() + 1) + " bytes"); return MS_ERR_CAPACITY; }
+  memcpy(out, line.c_str(), line.size() + 1);
+  return 1;
 }
 
 int64_t ms_now(ms_sim* s) { std::lock_guard<std::mutex> g(s->mu); return s->hs.now; }
@@ -1093,9 +1348,20 @@ int ms_net_partition(ms_sim* s, const uint32_t* comp, size_t n) {
 
 int ms_journal_open(ms_sim* s, const char* path) {
   std::lock_guard<std::mutex> g(s->mu);
-  if (s->jfile) fclose(s->jfile);
+  if (s->jfile) { fclose(s->jfile); delete s->jfress; s->jfress = nullptr; }
   s->jfile = fopen(path, "wb");
   if (!s->jfile) { set_err(std::string("cannot open journal file ") + path); return MS_ERR_ARG; }
+  const size_t plen = strlen(path);
+  if (plen > 9 && !strcmp(path + plen - 9, ".fressian")) {
+    // a stripe of net-journal/<stripe>.fressian (journal.clj:118-127): Fressian objects, no header
+    if (s->cfg.journal_level < 2) {
+      fclose(s->jfile); s->jfile = nullptr;
+      set_err("a .fressian journal needs journal_level 2 (message bodies)");
+      return MS_ERR_ARG;
+    }
+    s->jfress = new msf::Writer(s->jfile);
+    return MS_OK;
+  }
   const uint32_t hdr[4] = {0x314A534Du /* "MSJ1" */, s->cfg.journal_level, (uint32_t)sizeof(ms_event), (uint32_t)sizeof(ms_jbody)};
   fwrite(hdr, sizeof hdr, 1, s->jfile);
   return MS_OK;
@@ -1108,6 +1374,8 @@ int ms_journal_close(ms_sim* s) {
   const int rc = s->flush_journal_file();
   fclose(s->jfile);
   s->jfile = nullptr;
+  delete s->jfress;
+  s->jfress = nullptr;
   return rc;
 }
 
@@ -1131,11 +1399,18 @@ int ms_run_streamed(ms_sim* s, int64_t until, int format, size_t buf_events, ms_
   if (!sink) { set_err("ms_run_streamed: null sink"); return MS_ERR_ARG; }
   if (s->cfg.journal_level == 0 || s->cfg.journal_discard) { set_err("ms_run_streamed: the journal is off (journal_level 0 or journal_discard)"); return MS_ERR_ARG; }
   if (!buf_events) buf_events = (size_t)1 << 24;
+  const size_t hdr_bytes = stream_hdr_bytes();
   if (!s->jstream) {
     CK(cudaStreamCreateWithFlags(&s->jstream, cudaStreamNonBlocking));
     for (int k = 0; k < 2; k++) {
       CK(cudaEventCreateWithFlags(&s->j_rounds_done[k], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&s->j_copied[k], cudaEventDisableTiming));
+    }
+    for (int k = 0; k < 4; k++) {
       CK(cudaEventCreateWithFlags(&s->j_packed[k], cudaEventDisableTiming));
+      void* ptr = nullptr;
+      CK(cudaHostAlloc(&ptr, hdr_bytes, cudaHostAllocPortable));
+      s->jhdr[k] = (unsigned char*)ptr;
     }
     void* ptr = nullptr;
     CK(cudaMalloc(&ptr, msk_stream_plan_bytes()));
@@ -1145,10 +1420,14 @@ int ms_run_streamed(ms_sim* s, int64_t until, int format, size_t buf_events, ms_
   if (s->jhost_events < buf_events || s->jhost_format < format) {
     for (int k = 0; k < 2; k++) {
       if (s->jhost[k]) cudaFreeHost(s->jhost[k]);
-      s->jhost[k] = nullptr;
+      if (s->jdev[k]) cudaFree(s->jdev[k]);
+      s->jhost[k] = nullptr; s->jdev[k] = nullptr;
       void* ptr = nullptr;
-      CK(cudaHostAlloc(&ptr, stream_hdr_bytes() + buf_events * (size_t)format, cudaHostAllocMapped | cudaHostAllocPortable));
+      const size_t rec = (s->P.n_shards > 1 && format < 16) ? 16 : (size_t)format;   // sharded: MS_JFMT_16 records
+      CK(cudaHostAlloc(&ptr, buf_events * rec, cudaHostAllocPortable));
       s->jhost[k] = (unsigned char*)ptr;
+      CK(cudaMalloc(&ptr, hdr_bytes + buf_events * rec));
+      s->jdev[k] = (unsigned char*)ptr;
     }
     s->jhost_events = buf_events;
     s->jhost_format = format;
@@ -1158,60 +1437,94 @@ int ms_run_streamed(ms_sim* s, int64_t until, int format, size_t buf_events, ms_
   if ((rc = s->set_stop(until))) return rc;
   // the shadow counters start from what has been drained so far
   {
-    struct { uint64_t first, count, r0, n_rounds, jd, dr, jr; uint32_t ov, more; } init = {0, 0, 0, 0, s->hs.journal_drained, s->hs.drain_round, s->hs.jraw_drained, 0, 0};
-    static_assert(sizeof(init) == 64, "StreamPlan layout");
+    struct { uint64_t first, count, r0, n_rounds, jd, dr, jr; uint32_t ov, more; uint64_t local_n, hist[2][3], pad; } init =
+        {0, 0, 0, 0, s->hs.journal_drained, s->hs.drain_round, s->hs.jraw_drained, 0, 0, 0,
+         {{s->hs.journal_drained, s->hs.drain_round, s->hs.jraw_drained}, {s->hs.journal_drained, s->hs.drain_round, s->hs.jraw_drained}}, 0};
+    static_assert(sizeof(init) == 128, "StreamPlan layout");
     CK(cudaMemcpyAsync(s->jplan, &init, sizeof init, cudaMemcpyHostToDevice, s->stream));
     CK(cudaStreamSynchronize(s->stream));
   }
-  // rounds per batch: enough work to hide the launch gaps, little enough that a batch of events fits
-  // the host buffer and the raw ring; the device skips rounds by itself when the raw ring is half full
+  // Three batches are in flight: the rounds of batch i run (engine stream) while batch i-1 is packed
+  // into device staging and copied out by the DMA engine (journal stream) and the caller's sink
+  // looks at batch i-2 in pinned host memory.  The device skips rounds by itself when the raw ring is
+  // half full, so a slow sink only slows the simulation down.
   const uint64_t batch_rounds = 8;
   bool launching = true;
-  int64_t seen_now = s->hs.now, stall_now = s->hs.now;
+  int64_t stall_now = s->hs.now;
   uint64_t seen_round = s->hs.round, stall_round = s->hs.round;
-  uint64_t idle_batches = 0;
+  uint64_t idle_batches = 0, last_applied = 0;
   int result = MS_OK;
   for (uint64_t i = 0;; i++) {
-    const int b = (int)(i & 1);
+    const int b = (int)(i & 1), hb = (int)(i & 3);
     if (launching) s->launch_rounds(batch_rounds);
     CK(cudaEventRecord(s->j_rounds_done[b], s->stream));
     CK(cudaStreamWaitEvent(s->jstream, s->j_rounds_done[b], 0));
-    ms_jbatch* hdr = (ms_jbatch*)s->jhost[b];
-    msk_stream_batch(&s->P, s->jplan, s->jhost_events, ms_sim::kStreamRows, (ms_jround*)(s->jhost[b] + 256),
-                     s->jhost[b] + stream_hdr_bytes(), hdr, format, s->n_sms, s->jstream);
-    CK(cudaEventRecord(s->j_packed[b], s->jstream));
-    if (i == 0) continue;
-    // batch i-1: packed while the rounds of batch i run; its counters reach the round kernels after them
-    const int pb = b ^ 1;
-    CK(cudaStreamWaitEvent(s->stream, s->j_packed[pb], 0));
-    msk_stream_apply(&s->P, s->jplan, s->stream);
-    CK(cudaEventSynchronize(s->j_packed[pb]));
-    const ms_jbatch* ph = (const ms_jbatch*)s->jhost[pb];
+    msk_stream_batch(&s->P, s->jplan, s->jhost_events, ms_sim::kStreamRows, (ms_jround*)(s->jdev[b] + 256),
+                     s->jdev[b] + hdr_bytes, (ms_jbatch*)s->jdev[b], format, s->n_sms, s->jstream, (uint32_t)b);
+    CK(cudaMemcpyAsync(s->jhdr[hb], s->jdev[b], hdr_bytes, cudaMemcpyDeviceToHost, s->jstream));
+    CK(cudaEventRecord(s->j_packed[hb], s->jstream));
+    if (i >= 1) {
+      // batch i-1 is packed (its rounds ended a batch ago): now that its size is known, copy it out;
+      // its drain counters reach the round kernels behind the rounds of batch i
+      const uint64_t j = i - 1;
+      CK(cudaEventSynchronize(s->j_packed[j & 3]));
+      const ms_jbatch* hj = (const ms_jbatch*)s->jhdr[j & 3];
+      if (hj->n_events)
+        CK(cudaMemcpyAsync(s->jhost[j & 1], s->jdev[j & 1] + hdr_bytes, (size_t)hj->n_events * (size_t)hj->format,
+                           cudaMemcpyDeviceToHost, s->jstream));
+      CK(cudaEventRecord(s->j_copied[j & 1], s->jstream));
+      CK(cudaStreamWaitEvent(s->stream, s->j_packed[j & 3], 0));
+      msk_stream_apply(&s->P, s->jplan, s->stream, (uint32_t)(j & 1));
+      last_applied = j;
+    }
+    if (i < 2) continue;
+    const uint64_t k = i - 2;
+    CK(cudaEventSynchronize(s->j_copied[k & 1]));
+    const ms_jbatch* ph = (const ms_jbatch*)s->jhdr[k & 3];
     if (ph->overflow) { set_err("ms_run_streamed: MS_JFMT_8 / MS_JFMT_12 cannot hold this batch (endpoint index or id range): use a wider format"); result = MS_ERR_CAPACITY; break; }
-    if (ph->n_events && sink(ctx, ph, (const ms_jround*)(s->jhost[pb] + 256), s->jhost[pb] + stream_hdr_bytes())) {
+    if (ph->n_events && sink(ctx, ph, (const ms_jround*)(s->jhdr[k & 3] + 256), s->jhost[k & 1])) {
       set_err("ms_run_streamed: stopped by the sink");
       result = MS_ERR_ARG;
       break;
     }
     if (ph->error) break;                       // sync_state below reports it
-    const bool progressed = ph->round != seen_round || ph->n_events != 0;
+    // (decisions below use what is the same on every shard of a sharded run: the range, not the local count)
+    const bool progressed = ph->round != seen_round || ph->range_events != 0;
     seen_round = ph->round;
-    seen_now = ph->now;
-    if (seen_now != stall_now) { stall_now = seen_now; stall_round = seen_round; }
+    if (ph->now != stall_now) { stall_now = ph->now; stall_round = seen_round; }
     else if (seen_round - stall_round > kMaxDeltaRounds) {
       set_err("virtual time is not advancing: 2^20 delta rounds at the same instant");
       result = MS_ERR_SIM;
       break;
     }
-    if (seen_now >= until) launching = false;
+    if (ph->now >= until) launching = false;
     if (!launching && !ph->more && !progressed) break;      // nothing ran and nothing is left to pack
     idle_batches = progressed ? 0 : idle_batches + 1;
-    if (idle_batches > 64) { set_err("simulation made no progress (device refuses to run rounds)"); result = MS_ERR_SIM; break; }
+    if (idle_batches > 64) {
+      char buf[384];
+      snprintf(buf, sizeof buf, "simulation made no progress (device refuses to run rounds): streamed batch %llu now=%lld until=%lld "
+               "round=%llu next_event=%llu first=%llu n=%llu more=%u err=%u launching=%d", (unsigned long long)k, (long long)ph->now,
+               (long long)until, (unsigned long long)ph->round, (unsigned long long)ph->next_event, (unsigned long long)ph->first_event,
+               (unsigned long long)ph->n_events, ph->more, ph->error, (int)launching);
+      set_err(buf);
+      result = MS_ERR_SIM;
+      break;
+    }
   }
   // everything packed is accounted for before the regular drain counters are trusted again
   CK(cudaStreamSynchronize(s->jstream));
-  msk_stream_apply(&s->P, s->jplan, s->stream);
+  msk_stream_apply(&s->P, s->jplan, s->stream, (uint32_t)((last_applied + 1) & 1));
+  msk_stream_apply(&s->P, s->jplan, s->stream, (uint32_t)(last_applied & 1));
+  const std::string keep = g_err;
   rc = s->sync_state();
+  if (!rc && result == MS_ERR_SIM) {
+    char buf[256];
+    snprintf(buf, sizeof buf, " [state: now=%lld stop=%lld round=%llu jraw_cursor=%llu jraw_drained=%llu drain_round=%llu journal_drained=%llu next_event=%llu slot_open=%u]",
+             (long long)s->hs.now, (long long)s->hs.stop_ns, (unsigned long long)s->hs.round, (unsigned long long)s->hs.jraw_cursor,
+             (unsigned long long)s->hs.jraw_drained, (unsigned long long)s->hs.drain_round, (unsigned long long)s->hs.journal_drained,
+             (unsigned long long)s->hs.next_event, s->hs.slot_open);
+    set_err(keep + buf);
+  }
   return rc ? rc : result;
 }
 
@@ -1233,6 +1546,16 @@ int ms_journal_decode(const ms_jbatch* b, const ms_jround* rounds, const void* e
       recv = (w[1] & 0x8000u) != 0;
       src = (w[1] >> 16) | ((w[2] & 0xFFu) << 16);
       dest = w[2] >> 8;
+    } else if (b->format == MS_JFMT_16) {
+      const uint64_t* w = (const uint64_t*)events + 2 * k;
+      const uint64_t eid = w[0] & ~MS_EVENT_RECV;
+      size_t rr = 0;
+      while (rr + 1 < b->n_rounds && rounds[rr + 1].ev_base <= eid) rr++;
+      e.event_id = w[0]; e.time_ns = rounds[rr].time_ns;
+      e.msg_id = rounds[rr].id_ref + (w[1] & 0x7FFFFFFFull);
+      e.src = (uint32_t)(w[1] >> 47) & 0xFFFFu; e.dest = (uint32_t)(w[1] >> 31) & 0xFFFFu;
+      out[k] = e;
+      continue;
     } else if (b->format == MS_JFMT_EVENT) {
       out[k] = ((const ms_event*)events)[k];
       continue;

@@ -299,8 +299,8 @@ __device__ __forceinline__ void emit_one(const Params& p, DevState* st, const Ne
   // In the reference the assert only throws inside the sending node's stdout thread
   // (process.clj:148-150), after the id was taken (net.clj:197); the network keeps running.  Here
   // the id is consumed, the :send is journaled, the message is dropped and counted.
-  const bool undeliverable = valid && (r.dest >= p.n_ep || (p.kind[r.dest] & kRemoved) ||
-                                       r.src >= p.n_ep || (p.kind[r.src] & kRemoved));
+  const bool undeliverable = valid && (r.dest >= p.n_ep || r.src >= p.n_ep ||
+                                       (np.any_removed && ((p.kind[r.dest] | p.kind[r.src]) & kRemoved)));
   if (valid) {
     r.round = cx.round; r.ticket = cx.ticket; r.idx = local_idx;     // order key == id order (net.clj:197)
     uint32_t x[4] = {0xFFFFFFFFu, 0, 0, 0};
@@ -659,6 +659,63 @@ __device__ __forceinline__ int node_emit(const Params& p, uint32_t e, const MsgV
 }
 
 // ------------------------------------------------------------------ round commit
+// The scalar part of a round's commit (one thread): totals, next ids, time advance, next round's row.
+__device__ void commit_scalars(const Params& p, DevState* st, uint64_t total, uint32_t zp_any, uint32_t T) {
+  const int64_t now = st->now;
+  const uint64_t round = st->round;
+  const uint32_t row = (uint32_t)round & p.hist_mask;
+  {
+      const uint64_t ev_total = total >> 32, em_total = total & 0xFFFFFFFFull;
+      RoundMeta* m = p.rmeta + row;
+      m->ev_total = ev_total;
+      m->em_total = em_total;
+      m->n_tickets = T;
+      st->next_event += ev_total;
+      st->next_id += em_total;
+      const uint64_t tick = (uint64_t)(now / kTickNs);
+      uint32_t hi_s = (tick + 1 < p.n_tick_off) ? p.tick_off[tick + 1] : p.n_sched;
+      if (hi_s > st->sched_cursor) st->sched_cursor = hi_s;
+      st->inj_count = 0;
+      int64_t next_now = now;
+      if (zp_any == 0) {
+        next_now = now + kTickNs;
+        st->now = next_now;
+        st->time_advanced = 1;
+        if (p.cal) {
+          // the slot of the new tick is released before the next round; what is filed into it from
+          // now on (latencies of whole turns, re-filed laps) belongs to its next generation
+          const uint32_t slot = ((uint32_t)(tick + 1)) & (p.cal_slots - 1);
+          st->cal_release = slot + 1;
+          p.cal_par[slot] ^= 1u;
+        }
+      } else {
+        st->time_advanced = 0;
+      }
+      st->round = round + 1;
+      st->rounds_run += 1;
+      st->done = 0;
+      st->slot_open = 0;
+      const uint64_t raw_cur = *reinterpret_cast<volatile uint64_t*>(&st->jraw_cursor);
+      if (p.jdiscard || !p.jlevel) {
+        st->journal_drained = st->next_event;
+        st->jraw_drained = raw_cur;
+        st->drain_round = round + 1;
+      }
+      // open the next round's row
+      RoundMeta* nx = p.rmeta + ((uint32_t)(round + 1) & p.hist_mask);
+      nx->round = round + 1;
+      nx->now = next_now;
+      nx->id_base = st->next_id;
+      nx->ev_base = st->next_event;
+      nx->raw_base = raw_cur;
+      nx->n_tickets = 0;
+      nx->ev_total = 0;
+      nx->em_total = 0;
+      __threadfence();
+  }
+}
+
+
 // Commit of a round, executed by one whole CTA: turn the per-ticket
 // counts of every shard into exclusive prefixes, advance the id / event / time counters and
 // open the next round's row.  Single GPU: called by the last ticket inside k_round; sharded:
@@ -730,55 +787,7 @@ __device__ void commit_round(const Params& p, DevState* st, uint64_t* s_wtmp) {
     }
     const uint64_t total = s_wtmp[32];
     __syncthreads();
-    if (tid == 0) {
-      const uint64_t ev_total = total >> 32, em_total = total & 0xFFFFFFFFull;
-      RoundMeta* m = p.rmeta + row;
-      m->ev_total = ev_total;
-      m->em_total = em_total;
-      m->n_tickets = T;
-      st->next_event += ev_total;
-      st->next_id += em_total;
-      const uint64_t tick = (uint64_t)(now / kTickNs);
-      uint32_t hi_s = (tick + 1 < p.n_tick_off) ? p.tick_off[tick + 1] : p.n_sched;
-      if (hi_s > st->sched_cursor) st->sched_cursor = hi_s;
-      st->inj_count = 0;
-      int64_t next_now = now;
-      if (zp_any == 0) {
-        next_now = now + kTickNs;
-        st->now = next_now;
-        st->time_advanced = 1;
-        if (p.cal) {
-          // the slot of the new tick is released before the next round; what is filed into it from
-          // now on (latencies of whole turns, re-filed laps) belongs to its next generation
-          const uint32_t slot = ((uint32_t)(tick + 1)) & (p.cal_slots - 1);
-          st->cal_release = slot + 1;
-          p.cal_par[slot] ^= 1u;
-        }
-      } else {
-        st->time_advanced = 0;
-      }
-      st->round = round + 1;
-      st->rounds_run += 1;
-      st->done = 0;
-      st->slot_open = 0;
-      const uint64_t raw_cur = *reinterpret_cast<volatile uint64_t*>(&st->jraw_cursor);
-      if (p.jdiscard || !p.jlevel) {
-        st->journal_drained = st->next_event;
-        st->jraw_drained = raw_cur;
-        st->drain_round = round + 1;
-      }
-      // open the next round's row
-      RoundMeta* nx = p.rmeta + ((uint32_t)(round + 1) & p.hist_mask);
-      nx->round = round + 1;
-      nx->now = next_now;
-      nx->id_base = st->next_id;
-      nx->ev_base = st->next_event;
-      nx->raw_base = raw_cur;
-      nx->n_tickets = 0;
-      nx->ev_total = 0;
-      nx->em_total = 0;
-      __threadfence();
-    }
+    if (tid == 0) commit_scalars(p, st, total, zp_any, T);
 }
 
 __global__ void __launch_bounds__(512) k_commit(Params p) {
@@ -786,6 +795,149 @@ __global__ void __launch_bounds__(512) k_commit(Params p) {
   DevState* st = p.st;
   if (round_skipped(p, st) || !st->slot_open) return;
   commit_round(p, st, s_wtmp);
+}
+
+// Commit in three launches for simulations with very many endpoints (tens of thousands of tickets:
+// one CTA walking all of them would dominate a round).  A: every block of kCommitBlk tickets
+// validates and unpacks its entries and leaves its sum; B: one CTA scans the block sums and does the
+// scalar commit; C: every block turns its counts into prefixes.  Same results as commit_round.
+constexpr uint32_t kCommitBlk = 1024;
+
+__global__ void __launch_bounds__(256) k_commit_a(Params p) {
+  __shared__ uint64_t s_red[8];
+  __shared__ uint32_t s_zp;
+  DevState* st = p.st;
+  if (round_skipped(p, st) || !st->slot_open) return;
+  const uint32_t T = p.n_inj_tickets + p.n_ep;
+  const uint32_t row = (uint32_t)st->round & p.hist_mask;
+  const uint32_t tag = ((uint32_t)st->round & 0x7FFFu) + 1u;
+  uint32_t* em = p.rt_em + (size_t)row * p.t_max;
+  uint32_t* ev = p.rt_ev + (size_t)row * p.t_max;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_zp = 0;
+  __syncthreads();
+  uint64_t sum = 0;
+  uint32_t zp = 0;
+  uint64_t v[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const uint32_t i = blockIdx.x * kCommitBlk + q * 256 + tid;
+    v[q] = i < T ? __ldcg(reinterpret_cast<const unsigned long long*>(p.rt_cnt_sh[owner_of_ticket(i, p.n_inj_tickets, p.n_servers, p.n_shards)] + (size_t)row * p.t_max + i)) : ((uint64_t)tag << 48);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const uint32_t i = blockIdx.x * kCommitBlk + q * 256 + tid;
+    if (i >= T) continue;
+    for (uint32_t spin = 0; (uint32_t)(v[q] >> 48) != tag && spin < (1u << 22); spin++)
+      v[q] = __ldcg(reinterpret_cast<const unsigned long long*>(p.rt_cnt_sh[owner_of_ticket(i, p.n_inj_tickets, p.n_servers, p.n_shards)] + (size_t)row * p.t_max + i));
+    if ((uint32_t)(v[q] >> 48) != tag) latch_error(st, E_HISTORY, i);
+    zp |= (uint32_t)(v[q] >> 47) & 1u;
+    const uint32_t ve = (uint32_t)(v[q] >> 24) & 0x7FFFFFu, vm = (uint32_t)v[q] & 0xFFFFFFu;
+    ev[i] = ve; em[i] = vm;
+    sum += ((uint64_t)ve << 32) | vm;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(FULL, sum, d);
+  if (lane == 0) s_red[warp] = sum;
+  if (zp) s_zp = 1;
+  __syncthreads();
+  if (tid == 0) {
+    uint64_t t = 0;
+    for (int w = 0; w < 8; w++) t += s_red[w];
+    p.cm_blk[blockIdx.x] = t;
+    if (s_zp) atomicOr(&p.cm_flags[0], 1u);
+  }
+}
+
+__global__ void __launch_bounds__(512) k_commit_b(Params p, uint32_t nb) {
+  __shared__ uint64_t s_wtmp[34];
+  DevState* st = p.st;
+  if (round_skipped(p, st) || !st->slot_open) {
+    if (threadIdx.x == 0) p.cm_flags[2] = 0;
+    return;
+  }
+  // exclusive scan of the block sums in place (block_excl_scan wants shared memory: do it by hand)
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int c = ((int)nb + nt - 1) / nt;
+  const int lo = min(tid * c, (int)nb), hi = min(lo + c, (int)nb);
+  uint64_t sum = 0;
+  for (int i = lo; i < hi; i++) sum += p.cm_blk[i];
+  uint64_t incl = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint64_t y = __shfl_up_sync(FULL, incl, d);
+    if (lane >= d) incl += y;
+  }
+  if (lane == 31) s_wtmp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = nt >> 5;
+    const uint64_t w = lane < nw ? s_wtmp[lane] : 0;
+    uint64_t wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint64_t y = __shfl_up_sync(FULL, wi, d);
+      if (lane >= d) wi += y;
+    }
+    s_wtmp[lane] = wi - w;
+    if (lane == 31) s_wtmp[32] = wi;
+  }
+  __syncthreads();
+  uint64_t run = s_wtmp[warp] + incl - sum;
+  for (int i = lo; i < hi; i++) {
+    const uint64_t v = p.cm_blk[i];
+    p.cm_blk[i] = run;
+    run += v;
+  }
+  const uint64_t total = s_wtmp[32];
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t T = p.n_inj_tickets + p.n_ep;
+    p.cm_flags[1] = (uint32_t)st->round & p.hist_mask;      // phase C works on the row of the round being committed
+    p.cm_flags[2] = 1;
+    const uint32_t zp_any = p.cm_flags[0];
+    p.cm_flags[0] = 0;
+    commit_scalars(p, st, total, zp_any, T);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_commit_c(Params p) {
+  __shared__ uint64_t s_w[9];
+  if (!p.cm_flags[2]) return;
+  const uint32_t T = p.n_inj_tickets + p.n_ep;
+  const uint32_t row = p.cm_flags[1];
+  uint32_t* em = p.rt_em + (size_t)row * p.t_max;
+  uint32_t* ev = p.rt_ev + (size_t)row * p.t_max;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // thread t owns the 4 consecutive tickets base + 4t .. base + 4t + 3
+  const uint32_t i0 = blockIdx.x * kCommitBlk + 4 * tid;
+  uint64_t c[4], sum = 0;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const uint32_t i = i0 + q;
+    c[q] = i < T ? (((uint64_t)ev[i] << 32) | em[i]) : 0ull;
+    sum += c[q];
+  }
+  uint64_t incl = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint64_t y = __shfl_up_sync(FULL, incl, d);
+    if (lane >= d) incl += y;
+  }
+  if (lane == 31) s_w[warp] = incl;
+  __syncthreads();
+  if (tid == 0) {
+    uint64_t r = p.cm_blk[blockIdx.x];
+    for (int w = 0; w < 8; w++) { const uint64_t v = s_w[w]; s_w[w] = r; r += v; }
+  }
+  __syncthreads();
+  uint64_t run = s_w[warp] + incl - sum;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const uint32_t i = i0 + q;
+    if (i < T) { ev[i] = (uint32_t)(run >> 32); em[i] = (uint32_t)run; }
+    run += c[q];
+  }
 }
 
 // ------------------------------------------------------------------ k_round
@@ -1420,6 +1572,10 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
           uint32_t svc = 0;
           while (svc < 4 && p.sv_ep[svc] != e) svc++;
           uint32_t n_rep = 0;
+          // lin-kv: the binding of the key last touched stays in registers (single_key_txn.clj has every
+          // node hammer ONE key, the root): the walk is a dependent chain, keep memory out of it
+          uint32_t ck = 0xFFFFFFFFu, cval = 0;
+          bool chas = false, cdirty = false;
           for (uint32_t pos = 0; pos < n && svc < 4; pos++) {
             const uint32_t i = ord[pos];
             if (!(vals[i] & V_RECV)) continue;
@@ -1431,17 +1587,32 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
               q.src = (myring + (size_t)((head + i) & my_mask) * 3)[1].x;
             const bool keyed = q.type == MS_T_READ || q.type == MS_T_WRITE || q.type == MS_T_CAS;
             if (svc != MS_SVC_LIN_TSO && keyed && q.key >= p.sv_n_keys) { latch_error(st, E_VALUE_RANGE, q.key); continue; }
+            if (svc != MS_SVC_LIN_TSO && !keyed) continue;   // no clause of the store's `case` matches: logged, no reply (service.clj:262-263)
             uint32_t x[4] = {0, 0, 0, 0};
             if (svc == MS_SVC_SEQ_KV || svc == MS_SVC_LWW_KV)      // rand-int = word 3 of the reply's own draw
               philox4x32_10(n_rep, e, (uint32_t)round, (uint32_t)(round >> 32), p.seed_lo, p.seed_hi, x);
             SvRep r;
-            service_handle(p, svc, q, x[3], r);
+            if (svc == MS_SVC_LIN_KV) {
+              r.reply = false; r.otype = MS_T_ERROR; r.code = 0; r.value = 0;
+              if (keyed) {
+                if (q.key != ck) {
+                  if (cdirty) { p.sv_lin_has[ck] = chas ? 1 : 0; p.sv_lin_val[ck] = cval; }
+                  ck = q.key; chas = p.sv_lin_has[ck] != 0; cval = p.sv_lin_val[ck]; cdirty = false;
+                }
+                bool np_; uint32_t nv;
+                kv_eval(chas, cval, q, false, r, np_, nv);
+                if (r.reply) { cdirty = cdirty || np_ != chas || nv != cval; chas = np_; cval = nv; }
+              }
+            } else {
+              service_handle(p, svc, q, x[3], r);
+            }
             if (r.reply) {
               vals[i] |= SV_REPLY | (r.code << 16) | r.otype;
               keyB[pos] = r.value;
               n_rep++;
             }
           }
+          if (cdirty) { p.sv_lin_has[ck] = chas ? 1 : 0; p.sv_lin_val[ck] = cval; }
         }
         __syncthreads();
       }
@@ -1538,14 +1709,21 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
             // @set |= value (g_set.rb:29-31): every thread owns a strided set of words
             for (uint32_t w = tid; w < p.bm_words; w += nt) {
               uint32_t acc = 0;
-              for (uint32_t pos = seg_lo; pos < seg_hi; pos++) {
-                const uint32_t i = ord[pos];
-                const uint32_t val = vals[i], mt = meta[i];
-                if ((val & V_RECV) && !(mt & M_REPLY) && ((mt >> M_TC_SHIFT) & 7u) == GT_REPL_FULL) {
-                  const uint32_t srow = val & V_MASK;      // sender = srow / gs_slots; its shard holds the row
-                  const uint32_t* rows = p.gs_snap_sh[owner_of(srow / p.gs_slots, p.n_servers, p.n_shards)];
-                  acc |= __ldcg(rows + (size_t)srow * p.bm_words + w);
+              // four snapshot rows at a time: the loads are independent, keep them all in flight
+              for (uint32_t pos = seg_lo; pos < seg_hi; pos += 4) {
+                uint32_t x[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (uint32_t q = 0; q < 4; q++) {
+                  if (pos + q >= seg_hi) continue;
+                  const uint32_t i = ord[pos + q];
+                  const uint32_t val = vals[i], mt = meta[i];
+                  if ((val & V_RECV) && !(mt & M_REPLY) && ((mt >> M_TC_SHIFT) & 7u) == GT_REPL_FULL) {
+                    const uint32_t srow = val & V_MASK;    // sender = srow / gs_slots; its shard holds the row
+                    const uint32_t* rows = p.gs_snap_sh[owner_of(srow / p.gs_slots, p.n_servers, p.n_shards)];
+                    x[q] = __ldcg(rows + (size_t)srow * p.bm_words + w);
+                  }
                 }
+                acc |= x[0] | x[1] | x[2] | x[3];
               }
               if (acc) myset[w] = __ldcg(myset + w) | acc;   // the adds above were atomics: read at L2
             }
@@ -1836,7 +2014,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
            (unsigned long long)entry);
     // single GPU: the last ticket commits the round right here; sharded: k_commit does it
     // after the cross-shard barrier
-    s_misc[4] = (p.n_shards <= 1 && atomicAdd(&st->done, 1u) == T - 1) ? 1u : 0u;
+    s_misc[4] = (!p.split_commit && atomicAdd(&st->done, 1u) == T - 1) ? 1u : 0u;
     s_misc[5] = next_li;
   }
   __syncthreads();
@@ -1907,7 +2085,11 @@ struct StreamPlan {
   uint64_t first, count, r0, n_rounds;
   uint64_t journal_drained, drain_round, jraw_drained;
   uint32_t overflow, more;
+  unsigned long long local_n;   // sharded runs: events of this shard appended to the batch so far
+  uint64_t hist[2][3];          // the drain counters as of batch i, slot i & 1: what k_stream_apply(i) hands over
+  uint64_t pad;
 };
+static_assert(sizeof(StreamPlan) == 128, "StreamPlan is initialised from the host");
 
 __global__ void k_stream_plan(Params p, StreamPlan* plan, uint64_t cap_events, uint32_t cap_rounds, ms_jround* rows) {
   if (threadIdx.x || blockIdx.x) return;
@@ -1929,6 +2111,7 @@ __global__ void k_stream_plan(Params p, StreamPlan* plan, uint64_t cap_events, u
   }
   plan->first = first; plan->count = count; plan->r0 = r0; plan->n_rounds = r1 - r0;
   plan->overflow = 0;
+  plan->local_n = 0;
 }
 
 template <int FMT>
@@ -1959,6 +2142,14 @@ __global__ void k_journal_pack(Params p, StreamPlan* plan, unsigned char* out) {
     const uint64_t send_base = m->id_base + p.rt_em[(size_t)row * p.t_max + t];
     const uint64_t id_ref = m->id_base > (1ull << 30) ? m->id_base - (1ull << 30) : 0ull;
     const int64_t tnow = m->now;
+    // sharded runs: a shard holds only its own endpoints' events, so the batch is not positional: the
+    // chunk's events in range are appended (one claim per chunk) with their event ids spelled out
+    uint64_t slot0 = 0;
+    const uint64_t k_lo = g0 < first ? first - g0 : 0, k_hi = g0 + cnt > first + count ? first + count - g0 : cnt;
+    if (p.n_shards > 1) {
+      if (lane == 0) slot0 = atomicAdd(&plan->local_n, (unsigned long long)(k_hi - k_lo));
+      slot0 = __shfl_sync(FULL, slot0, 0);
+    }
     for (uint64_t k = lane; k < cnt; k += 32) {
       const uint64_t g = g0 + k;
       if (g < first || g >= first + count) continue;
@@ -1966,6 +2157,22 @@ __global__ void k_journal_pack(Params p, StreamPlan* plan, unsigned char* out) {
       const uint64_t v = (uint64_t)raw.x | ((uint64_t)raw.y << 32);
       const bool recv = (v & RECV_BIT) != 0;
       const uint64_t id = recv ? (v & ~RECV_BIT) : send_base + v;
+      if (p.n_shards > 1) {
+        const uint64_t at = slot0 + (k - k_lo);
+        const uint64_t eid = g | (recv ? MS_EVENT_RECV : 0ull);
+        if (FMT == 32) {
+          uint4* o = reinterpret_cast<uint4*>(out) + at * 2;
+          o[0] = make_uint4((uint32_t)eid, (uint32_t)(eid >> 32), (uint32_t)tnow, (uint32_t)((uint64_t)tnow >> 32));
+          o[1] = make_uint4((uint32_t)id, (uint32_t)(id >> 32), raw.z, raw.w);
+        } else {                                             // MS_JFMT_16: event id word + the MS_JFMT_8 word
+          const uint64_t d = id - id_ref;
+          if (id < id_ref || d >= (1ull << 31) || raw.z > 0xFFFFu || raw.w > 0xFFFFu) bad = true;
+          const uint64_t w = (recv ? RECV_BIT : 0ull) | ((uint64_t)(raw.z & 0xFFFFu) << 47) |
+                             ((uint64_t)(raw.w & 0xFFFFu) << 31) | (d & 0x7FFFFFFFull);
+          reinterpret_cast<uint4*>(out)[at] = make_uint4((uint32_t)eid, (uint32_t)(eid >> 32), (uint32_t)w, (uint32_t)(w >> 32));
+        }
+        continue;
+      }
       if (FMT == 8) {
         const uint64_t d = id - id_ref;
         if (id < id_ref || d >= (1ull << 31) || raw.z > 0xFFFFu || raw.w > 0xFFFFu) bad = true;
@@ -1989,7 +2196,7 @@ __global__ void k_journal_pack(Params p, StreamPlan* plan, unsigned char* out) {
   if (bad) atomicOr(&plan->overflow, 1u);
 }
 
-__global__ void k_stream_finish(Params p, StreamPlan* plan, ms_jbatch* hdr, uint32_t format) {
+__global__ void k_stream_finish(Params p, StreamPlan* plan, ms_jbatch* hdr, uint32_t format, uint32_t parity) {
   if (threadIdx.x || blockIdx.x) return;
   const DevState* st = p.st;
   plan->journal_drained = plan->first + plan->count;
@@ -2003,19 +2210,26 @@ __global__ void k_stream_finish(Params p, StreamPlan* plan, ms_jbatch* hdr, uint
   plan->jraw_drained = dr < st->round ? p.rmeta[(uint32_t)dr & p.hist_mask].raw_base
                                       : *reinterpret_cast<const volatile uint64_t*>(&st->jraw_cursor);
   plan->more = st->next_event > plan->journal_drained ? 1u : 0u;
+  plan->hist[parity][0] = plan->journal_drained;
+  plan->hist[parity][1] = plan->drain_round;
+  plan->hist[parity][2] = plan->jraw_drained;
   ms_jbatch b;
-  b.first_event = plan->first; b.n_events = plan->count; b.n_rounds = plan->n_rounds;
+  b.first_event = plan->first; b.n_events = p.n_shards > 1 ? (uint64_t)plan->local_n : plan->count; b.n_rounds = plan->n_rounds;
   b.now = st->now; b.round = st->round; b.next_event = st->next_event;
-  b.format = format; b.overflow = plan->overflow; b.more = plan->more; b.error = st->error;
+  b.format = (p.n_shards > 1 && format != MS_JFMT_EVENT) ? (uint32_t)MS_JFMT_16 : format;
+  b.overflow = plan->overflow; b.more = plan->more; b.error = st->error;
+  b.range_events = plan->count;
   *hdr = b;
   __threadfence_system();
 }
 
 // on the engine's own stream, between two rounds: the round kernels now see what has been packed
-__global__ void k_stream_apply(Params p, const StreamPlan* plan) {
+__global__ void k_stream_apply(Params p, const StreamPlan* plan, uint32_t parity) {
   if (threadIdx.x || blockIdx.x) return;
   DevState* st = p.st;
-  const uint64_t a = plan->journal_drained, b = plan->drain_round, c = plan->jraw_drained;
+  // the counters as of one given batch: every shard hands over the same drain_round at the same
+  // place of its launch sequence, so all shards keep taking the same back-pressure decisions
+  const uint64_t a = plan->hist[parity][0], b = plan->hist[parity][1], c = plan->hist[parity][2];
   if (a > st->journal_drained) st->journal_drained = a;
   if (b > st->drain_round) st->drain_round = b;
   if (c > st->jraw_drained) st->jraw_drained = c;
@@ -2097,7 +2311,17 @@ void msk_launch_round(const msd::Params* p, int n_classes, const uint32_t* caps,
       for (int c = 0; c < n_classes - 1; c++) cudaStreamWaitEvent(s, aux_ev[1 + c], 0);
     if (after_round) cudaEventRecord(after_round, s);
   }
-  if ((phases & 4) && p->n_shards > 1) MS_LAUNCH(msd::k_commit, 1, 512, 0, s, *p);
+  if ((phases & 4) && p->split_commit) {
+    const uint32_t T = p->n_inj_tickets + n_ep;
+    if (p->cm_blk) {          // many tickets: three parallel phases
+      const uint32_t nb = (T + msd::kCommitBlk - 1) / msd::kCommitBlk;
+      MS_LAUNCH(msd::k_commit_a, nb, 256, 0, s, *p);
+      MS_LAUNCH(msd::k_commit_b, 1, 512, 0, s, *p, nb);
+      MS_LAUNCH(msd::k_commit_c, nb, 256, 0, s, *p);
+    } else {
+      MS_LAUNCH(msd::k_commit, 1, 512, 0, s, *p);
+    }
+  }
 }
 
 void msk_barrier(const msd::Params* p, cudaStream_t s) { MS_LAUNCH(msd::k_barrier, 1, 32, 0, s, *p); }
@@ -2105,17 +2329,17 @@ void msk_barrier(const msd::Params* p, cudaStream_t s) { MS_LAUNCH(msd::k_barrie
 size_t msk_stream_plan_bytes() { return sizeof(msd::StreamPlan); }
 // plan -> pack -> finish: one batch of the journal into (host-mapped) `out`, header into `hdr`
 void msk_stream_batch(const msd::Params* p, void* plan, uint64_t cap_events, uint32_t cap_rounds, ms_jround* rows,
-                      void* out, ms_jbatch* hdr, int format, int n_sms, cudaStream_t s) {
+                      void* out, ms_jbatch* hdr, int format, int n_sms, cudaStream_t s, uint32_t parity) {
   msd::StreamPlan* pl = (msd::StreamPlan*)plan;
   MS_LAUNCH(msd::k_stream_plan, 1, 32, 0, s, *p, pl, cap_events, cap_rounds, rows);
   const unsigned blocks = (unsigned)n_sms * 16;
   if (format == MS_JFMT_8) MS_LAUNCH(msd::k_journal_pack<8>, blocks, 256, 0, s, *p, pl, (unsigned char*)out);
   else if (format == MS_JFMT_12) MS_LAUNCH(msd::k_journal_pack<12>, blocks, 256, 0, s, *p, pl, (unsigned char*)out);
   else MS_LAUNCH(msd::k_journal_pack<32>, blocks, 256, 0, s, *p, pl, (unsigned char*)out);
-  MS_LAUNCH(msd::k_stream_finish, 1, 32, 0, s, *p, pl, hdr, (uint32_t)format);
+  MS_LAUNCH(msd::k_stream_finish, 1, 32, 0, s, *p, pl, hdr, (uint32_t)format, parity);
 }
-void msk_stream_apply(const msd::Params* p, const void* plan, cudaStream_t s) {
-  MS_LAUNCH(msd::k_stream_apply, 1, 32, 0, s, *p, (const msd::StreamPlan*)plan);
+void msk_stream_apply(const msd::Params* p, const void* plan, cudaStream_t s, uint32_t parity) {
+  MS_LAUNCH(msd::k_stream_apply, 1, 32, 0, s, *p, (const msd::StreamPlan*)plan, parity);
 }
 
 void msk_journal_expand(const msd::Params* p, uint64_t r0, uint32_t n_rounds, uint64_t first, uint64_t count,

@@ -228,7 +228,7 @@ class Sim:
                     else:
                         raw = np.ctypeslib.as_array(C.cast(events_p, C.POINTER(C.c_uint8)), (n * int(b.format),))
                         ev = (raw.view("<u8") if b.format == 8 else raw.view("<u4").reshape(n, 3) if b.format == 12
-                              else raw.view(EVENT_DTYPE))
+                              else raw.view("<u8").reshape(n, 2) if b.format == 16 else raw.view(EVENT_DTYPE))
                     info = {k: int(getattr(b, k)) for k, _ in _lib.JBatch._fields_}
                     sink(info, rounds, ev)
                 return 0

@@ -13,7 +13,7 @@ uint64_t dm_neg_log2_q32(uint64_t x) { return msd::neg_log2_q32(x); }
 uint64_t dm_latency(uint32_t dist, uint32_t mean_ms, uint32_t scale, uint64_t exp_coeff, const uint32_t x[4]) {
   msd::NetParams np;
   np.loss_thresh = 0; np.exp_coeff = exp_coeff; np.dist = dist; np.mean_ms = mean_ms; np.scale = scale;
-  np.pair_active = 0; np.comp_active = 0; np.pad = 0;
+  np.pair_active = 0; np.comp_active = 0; np.any_removed = 0;
   return msd::latency_ms(np, x);
 }
 uint32_t dm_owner(uint32_t e, uint32_t n_servers, uint32_t g) { return msd::owner_of(e, n_servers, g); }

@@ -78,6 +78,6 @@ def test_engine_owner_function(dm):
 
 def test_bench_numpy_philox_matches_oracle():
     import bench
-    got = bench.philox_nodes(257, 1, offset=1000)
-    want = [O.philox([1000 + i, 0, 0, 0], [bench.SEED & 0xFFFFFFFF, 1])[0] % bench.N_NODES for i in range(257)]
+    got = bench.philox_u32(257, 1, offset=1000)
+    want = [O.philox([1000 + i, 0, 0, 0], [bench.SEED & 0xFFFFFFFF, 1])[0] for i in range(257)]
     assert got.tolist() == want

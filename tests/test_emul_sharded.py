@@ -235,3 +235,47 @@ def test_emulated_shards_raft():
         scenario)
     check_against_oracle(O.Sim(n, workload=O.W_RAFT, **kw), scenario, ev, st, now, rnd)
     assert st["servers"]["send-count"] > 30 and st["clients"]["recv-count"] > 150
+
+
+@pytest.mark.parametrize("world,fmt,latency", [(2, 8, 0), (3, 32, 0), (2, 8, 2)])
+def test_emulated_shards_stream_their_journal(world, fmt, latency):
+    # ms_run_streamed on every shard: each hands over only its own endpoints' events, with their event
+    # ids (MS_JFMT_16 / MS_JFMT_EVENT); all shards keep taking the same back-pressure decisions; the
+    # union over the shards is the oracle's journal
+    n = 36
+    kw = dict(n_values=2048, latency_dist="constant", latency_mean_ms=latency)
+    got = {}
+    lock = threading.Lock()
+
+    def scenario(s, body):
+        cs = [s.add_endpoint("c%d" % i, O.KIND_SIM_CLIENT) for i in range(3)]
+        ops, _ = random_broadcast_ops(n, cs, n_ticks=20, per_tick=12, seed=23)
+        s.schedule(ops)
+        if hasattr(s, "run_streamed"):
+            mine = []
+
+            def sink(info, rounds, ev):
+                assert info["range_events"] >= info["n_events"] and info["format"] in (16, 32)
+                mine.append(ev.copy())
+
+            s.run_streamed((25 + 80 * latency) * 1_000_000, sink, fmt=fmt, buf_events=1500, decode=True)
+            with lock:
+                got[s.cfg.shard_id] = np.concatenate(mine) if mine else np.zeros(0, dtype=O.EVENT_DTYPE)
+        else:
+            s.run((25 + 80 * latency) * 1_000_000)
+
+    ev_left, st, now, rnd = run_sharded_scenario(
+        world, n, dict(workload="broadcast", topology="grid", ring_cap=1024, max_window=512, journal_cap_log2=16,
+                       max_endpoints=n + 8, **kw), scenario)
+    assert len(ev_left) == 0                                     # everything went out through the streams
+    o = O.Sim(n, workload=O.W_BROADCAST, topology="grid", **kw)
+    scenario(o, O.body)
+    ev_o, _ = o.journal()
+    allv = np.concatenate([got[r] for r in range(world)])
+    assert len(allv) == len(ev_o) > 4000
+    order = np.argsort(allv["event_id"] & np.uint64((1 << 63) - 1), kind="stable")
+    merged = allv[order]
+    for f in ("event_id", "time_ns", "msg_id", "src", "dest"):
+        assert np.array_equal(merged[f], ev_o[f]), f
+    assert all(len(got[r]) > 0 for r in range(world))
+    assert st == o.stats() and now == o.now and rnd == o.round

@@ -151,3 +151,21 @@ def test_many_incremental_schedules_prefix_table():
     g.run(t + 3_000_000)
     o.run(t + 3_000_000)
     assert_same_journal(g, o)
+
+
+@pytest.mark.parametrize("latency", [0, 2])
+def test_three_phase_commit_with_many_tickets(latency):
+    # more than 16384 tickets: the round is committed by k_commit_a/b/c instead of the last ticket
+    n = 25
+    g, o = make_pair(n, topology="grid", n_values=512, max_endpoints=17000, ring_cap=256, max_window=256,
+                     latency_dist="constant", latency_mean_ms=latency, journal_cap_log2=18)
+
+    def scenario(s, body):
+        cs = [s.add_endpoint("c%d" % i) for i in range(3)]
+        ops, nv = random_broadcast_ops(n, cs, n_ticks=12, per_tick=6, seed=4)
+        s.schedule(ops)
+        s.run((14 + 60 * latency) * 1_000_000)
+
+    both(g, o, scenario)
+    ev, _ = assert_same_journal(g, o)
+    assert len(ev) > 3000

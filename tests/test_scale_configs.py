@@ -87,7 +87,8 @@ def test_cfg4_raft_groups_with_partition_nemesis(engine_backend, group):
     else:
         n = 64 if engine_backend == "cuda" else 12
     g, o = make_pair(n, workload="lin-kv", latency_dist="uniform", latency_mean_ms=2, max_endpoints=n + 8,
-                     ring_cap=256 if group else 1024, max_window=128 if group else 512, raft_group=group,
+                     ring_cap=2048, max_window=2048, server_ring_cap=256 if group else 1024,
+                     server_max_window=128 if group else 512, raft_group=group,
                      rpc_table=256, n_keys=8, raft_log_cap=256, journal_cap_log2=22, calendar_slots=16,
                      calendar_cap=max(256, 8 * n))
 
