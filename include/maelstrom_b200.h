@@ -117,8 +117,9 @@ enum { MS_KIND_SERVER = 0,      /* device-resident node program (replaces proces
        MS_KIND_CLIENT = 1,      /* host-visible client, id "c<k>" (util.clj:7-10): zero latency */
        MS_KIND_HOST = 2,        /* host-visible non-client endpoint (a JVM service, service.clj:245-263) */
        MS_KIND_SIM_CLIENT = 3,  /* device-resident client sink (replies are counted, not mailed) */
-       MS_KIND_SERVICE = 4 };   /* device-resident service; the id picks it: "lin-kv", "seq-kv", "lww-kv",
+       MS_KIND_SERVICE = 4,     /* device-resident service; the id picks it: "lin-kv", "seq-kv", "lww-kv",
                                    "lin-tso" (service/default-services, service.clj:290-296) */
+       MS_KIND_GEN_CLIENT = 5 };/* device-resident closed-loop client: maelstrom.client + a Jepsen worker (ms_add_gen_clients) */
 enum { MS_SVC_LIN_KV = 0, MS_SVC_SEQ_KV = 1, MS_SVC_LWW_KV = 2, MS_SVC_LIN_TSO = 3 };
 
 /* error codes (negative returns); MS_ERR_NODE_NOT_FOUND maps to Maelstrom error
@@ -206,6 +207,46 @@ int ms_recv(ms_sim* sim, uint32_t endpoint, int64_t timeout_virtual_ns, ms_msg* 
  * on the host and re-attached on delivery. */
 int64_t ms_send_json(ms_sim* sim, const char* line);
 int     ms_recv_json(ms_sim* sim, uint32_t endpoint, int64_t timeout_virtual_ns, char* out, size_t cap);
+
+/* Closed-loop clients on the device (SURVEY.md 8f NEXT-2): what a Jepsen worker does with
+ * maelstrom.client (client.clj:41-172) and the workload's generator (workload/broadcast.clj:187-241,
+ * core.clj:67-80), as a per-client state machine that runs inside the round kernel:
+ *   one outstanding request per client (client.clj:69-76), msg_id from 1 (:52,61-64), a reply whose
+ *   in_reply_to is not the awaited id is discarded (:106-107), timeout_ns of virtual time without the
+ *   reply ends the op as :info -- :fail for reads, which are idempotent (:160-164) -- error replies are
+ *   :fail when the code is definite (all but 0 and 13, resources/errors.edn) else :info (:165-172);
+ *   ops are a mix of `broadcast` of a fresh value and `read` (g-set: `add` / `read`), staggered by a
+ *   uniform delay on [0, 2 interval) (gen/stagger of 1/rate); at time_limit_ns the mix stops and after
+ *   quiet_ns more every client does one final read (broadcast.clj:237-240, core.clj:75-80).
+ * Client k is bound to server k mod n_nodes, draws from its own Philox stream, and its j-th broadcast
+ * carries the value k + n_clients * j (unique, as the generator's 0, 1, 2, ... are).
+ * Every invocation and completion is a 32-byte history record; ms_history_drain hands them over in
+ * (time, round, client) order -- the Jepsen history a checker (set-full) works on.  A read's value is
+ * the node's set at that moment: the record carries its size, the members of a FINAL read are what
+ * ms_node_set returns once the run is over (nothing changes after the final reads). */
+typedef struct ms_gen_config {
+  uint32_t n_clients;
+  uint32_t read_permille;    /* share of reads in the mix, out of 1000 (gen/mix: 500) */
+  int64_t  interval_ns;      /* mean delay between two ops of one client (1 / rate x clients) */
+  int64_t  timeout_ns;       /* 0 = 5 000 ms (client.clj:18-20) */
+  int64_t  time_limit_ns;    /* --time-limit */
+  int64_t  quiet_ns;         /* 0 = 10 000 ms before the final reads (core.clj:75-78) */
+} ms_gen_config;
+typedef struct ms_hist {
+  int64_t  time_ns;
+  uint64_t order;            /* round << 24 | client ordinal: sorts records of the same instant */
+  uint32_t client;           /* endpoint index */
+  uint32_t op;               /* the client's op counter: an invocation and its completion share it */
+  uint8_t  type;             /* MS_H_INVOKE / OK / FAIL / INFO */
+  uint8_t  f;                /* MS_HF_BROADCAST (g-set: add) / MS_HF_READ */
+  uint16_t error;            /* completion by an error reply: its code; MS_H_TIMEOUT for :net-timeout */
+  uint32_t value;            /* broadcast / add: the value; read ok: the size of the set returned */
+} ms_hist;
+enum { MS_H_INVOKE = 0, MS_H_OK = 1, MS_H_FAIL = 2, MS_H_INFO = 3, MS_H_TIMEOUT = 0xFFFF };
+enum { MS_HF_BROADCAST = 0, MS_HF_READ = 1 };
+/* adds cfg->n_clients endpoints "c<first_name> ..." and returns the index of the first; once per simulation */
+int ms_add_gen_clients(ms_sim* sim, const ms_gen_config* cfg, uint32_t first_name);
+int ms_history_drain(ms_sim* sim, ms_hist* out, size_t cap, size_t* n_out);
 
 /* Upload a time-sorted schedule of client ops (appends). */
 int ms_schedule_ops(ms_sim* sim, const ms_op* ops, size_t n);

@@ -24,6 +24,8 @@ public final class Native {
   public static native int recv(long h, int endpoint, long timeoutNs, ByteBuffer msMsg48);
   public static native long sendJson(long h, String line);
   public static native int recvJson(long h, int endpoint, long timeoutNs, ByteBuffer outUtf8, long cap);
+  public static native int addGenClients(long h, ByteBuffer msGenConfig, int firstName);
+  public static native long historyDrain(long h, ByteBuffer msHist32, long cap);
   public static native int scheduleOps(long h, ByteBuffer msOps, long n);
   public static native int step(long h, long nRounds);
   public static native int run(long h, long untilNs);

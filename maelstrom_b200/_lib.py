@@ -8,7 +8,8 @@ import os
 import numpy as np
 
 _DIR = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_DIR, "libmaelstrom_b200.so")
+# MS_B200_LIB: another build of the same library (kernel tuning experiments), never a different implementation
+SO_PATH = os.environ.get("MS_B200_LIB") or os.path.join(_DIR, "libmaelstrom_b200.so")
 
 MSG_DTYPE = np.dtype([("id", "<u8"), ("deadline_ns", "<i8"), ("src", "<u4"), ("dest", "<u4"),
                       ("msg_id", "<u4"), ("in_reply_to", "<u4"), ("type", "<u2"), ("flags", "<u2"),
@@ -43,6 +44,16 @@ class Body(C.Structure):
                 ("in_reply_to", C.c_uint32), ("p0", C.c_uint32), ("p1", C.c_uint64)]
 
 
+class GenConfig(C.Structure):   # ms_gen_config
+    _fields_ = [("n_clients", C.c_uint32), ("read_permille", C.c_uint32), ("interval_ns", C.c_int64),
+                ("timeout_ns", C.c_int64), ("time_limit_ns", C.c_int64), ("quiet_ns", C.c_int64)]
+
+
+HIST_DTYPE = np.dtype([("time_ns", "<i8"), ("order", "<u8"), ("client", "<u4"), ("op", "<u4"), ("type", "u1"),
+                       ("f", "u1"), ("error", "<u2"), ("value", "<u4")])
+assert HIST_DTYPE.itemsize == 32
+
+
 class JBatch(C.Structure):      # ms_jbatch
     _fields_ = [("first_event", C.c_uint64), ("n_events", C.c_uint64), ("n_rounds", C.c_uint64),
                 ("now", C.c_int64), ("round", C.c_uint64), ("next_event", C.c_uint64),
@@ -70,6 +81,8 @@ SYMBOLS = {
     "ms_recv": (C.c_int, [_P, C.c_uint32, C.c_int64, _P]),
     "ms_send_json": (C.c_int64, [_P, C.c_char_p]),
     "ms_recv_json": (C.c_int, [_P, C.c_uint32, C.c_int64, C.c_char_p, C.c_size_t]),
+    "ms_add_gen_clients": (C.c_int, [_P, _P, C.c_uint32]),
+    "ms_history_drain": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "ms_schedule_ops": (C.c_int, [_P, _P, C.c_size_t]),
     "ms_step": (C.c_int, [_P, C.c_uint64]),
     "ms_run": (C.c_int, [_P, C.c_int64]),

@@ -22,7 +22,7 @@ enum : uint32_t {
   E_NONE = 0, E_RING_OVERFLOW = 1, E_WINDOW_OVERFLOW = 2, E_JOURNAL_OVERFLOW = 3,
   E_INVALID_DEST = 4, E_HISTORY = 5, E_VALUE_RANGE = 6, E_MAIL_OVERFLOW = 7,
   E_CALENDAR_OVERFLOW = 8, E_ID_RANGE = 9, E_BARRIER = 10, E_SNAPSHOT = 11,
-  E_RAFT_CAPACITY = 12
+  E_RAFT_CAPACITY = 12, E_HISTORY_RING = 13
 };
 
 // Mutable per-simulation scalars, resident in HBM, committed by the last CTA of
@@ -44,6 +44,8 @@ struct DevState {
   uint64_t rounds_run;
   uint64_t fallback_sorts;   // windows that needed the full bitonic sort
   uint64_t undeliverable;    // sends whose src / dest was not a registered endpoint: journaled, then dropped
+  uint64_t gc_hist_n;        // history records written
+  uint64_t gc_hist_drained;  // ... and handed to the host
   uint32_t done;             // CTAs finished this round
   uint32_t zero_pending;     // messages sent this round that are due at `now`
   uint32_t error;            // first latched E_* code
@@ -59,7 +61,8 @@ struct DevState {
   uint32_t slot_open;        // k_snapshot ran for this launch slot and the round has not been committed yet
   uint32_t bar_epoch;        // cross-shard barriers executed so far
   // per-round work lists of the k_round size classes, double-buffered by round parity
-  uint32_t cls_count[2][4];
+  uint32_t cls_count[2][4];   // tickets at the front of the class list (the longer windows)
+  uint32_t cls_small[2][4];   // tickets at the back of the class list
   uint32_t cls_cursor[2][4];
 };
 
@@ -205,6 +208,11 @@ struct Params {
   uint32_t  rf_group;        // servers per Raft cluster (0 = one cluster of all servers)
   uint32_t  rf_gmax;         // row stride of rf_next / rf_match / rf_scratch = largest cluster
   uint32_t  rf_cb_mask;      // pending-RPC table slots per node - 1 (power of two)
+  // closed-loop clients (ms_add_gen_clients)
+  struct GenDev* gc;         // [max_endpoints], valid where kind == MS_KIND_GEN_CLIENT
+  uint4*    gc_hist;         // ring of 32-B history records (ms_hist)
+  uint32_t  gc_hist_mask, gc_n, gc_read_permille, gc_pad;
+  int64_t   gc_interval_ns, gc_timeout_ns, gc_limit_ns, gc_quiet_ns;
   // append_entries payloads of every shard (index = shard): read where the sender wrote them
   uint4*    rf_heap_sh[8];
   uint64_t* rf_ext_off_sh[8];
@@ -227,6 +235,19 @@ struct RaftDev {
   uint32_t next_msg_id, log_size, appends, n_votes, kv_size;
   uint32_t busy;                       // leader with a follower behind its log (or a next_index <= 0): see rf_timer_due
 };
+
+// closed-loop client (maelstrom.client + a Jepsen worker), one per MS_KIND_GEN_CLIENT endpoint
+struct GenDev {
+  uint32_t next_msg_id, waiting_for;   // client.clj:52,61-76
+  int64_t  deadline_ns;                // when the outstanding request times out (client.clj:96-101)
+  int64_t  next_op_ns;                 // stagger: earliest time of the next invocation
+  uint32_t node;                       // the server this client talks to
+  uint32_t ops, bcasts;                // ops invoked so far, broadcasts among them
+  uint32_t phase;                      // 0 mix, 1 quiet period, 2 final read outstanding, 3 done
+  uint32_t cur_f, cur_value;           // the op in flight
+  uint32_t ordinal, pad;               // k of client k
+};
+enum : uint32_t { GEN_MIX = 0, GEN_QUIET = 1, GEN_FINAL = 2, GEN_DONE = 3 };
 
 constexpr uint32_t kSeqBuffer = 32;             // (sequential 32 ...), service.clj:206-208
 constexpr uint32_t kSeqHist = kSeqBuffer + 1;   // versions per key that can matter to a resident state
@@ -292,7 +313,7 @@ MS_HD uint64_t latency_ms(const NetParams& np, const uint32_t x[4]) {
   return mulhi64(neg_log2_q32(X), np.exp_coeff);
 }
 
-MS_HD bool kind_is_client(uint8_t k) { k &= 0x7F; return k == MS_KIND_CLIENT || k == MS_KIND_SIM_CLIENT; }
+MS_HD bool kind_is_client(uint8_t k) { k &= 0x7F; return k == MS_KIND_CLIENT || k == MS_KIND_SIM_CLIENT || k == MS_KIND_GEN_CLIENT; }
 
 // Shard that owns endpoint e: servers are split into G contiguous index ranges (rows of the
 // grid stay together), every other endpoint round-robin.  Injector tickets belong to shard 0.

@@ -87,6 +87,7 @@ static const char* dev_error_text(uint32_t code) {
     case E_ID_RANGE: return "per-ticket count exceeds the table entry range at ticket";
     case E_BARRIER: return "cross-shard barrier timed out waiting for shard";
     case E_RAFT_CAPACITY: return "Raft node out of log / staging / payload-heap capacity (raise ms_config.reserved[3]) at node";
+    case E_HISTORY_RING: return "history ring of the closed-loop clients is full (call ms_history_drain more often) at client";
     case E_SNAPSHOT: return "replicate_full names a set snapshot that is not resident (in flight longer than calendar_slots, or forged): sender";
   }
   return "unknown device error";
@@ -970,6 +971,76 @@ int ms_add_endpoint(ms_sim* s, const char* id, int kind) {
   s->by_name[id] = idx;
   CK(cudaMemcpy(s->P.kind + idx, &s->kinds[idx], 1, cudaMemcpyHostToDevice));
   return (int)idx;
+}
+
+// Closed-loop clients: n endpoints "c<first_name>..", each bound to server k mod n_nodes, driven by
+// gen_step inside the round kernel (csrc/ms_kernels.cu).
+int ms_add_gen_clients(ms_sim* s, const ms_gen_config* gc, uint32_t first_name) {
+  std::lock_guard<std::mutex> g(s->mu);
+  cudaSetDevice(s->device);
+  if (!gc || gc->n_clients == 0 || gc->interval_ns <= 0 || gc->read_permille > 1000) { set_err("ms_add_gen_clients: bad configuration"); return MS_ERR_ARG; }
+  if (s->P.gc) { set_err("ms_add_gen_clients: the generator's clients exist already"); return MS_ERR_ARG; }
+  if (s->cfg.workload != MS_W_BROADCAST && s->cfg.workload != MS_W_GSET) {
+    set_err("ms_add_gen_clients: the device generator drives the broadcast and g-set workloads");
+    return MS_ERR_ARG;
+  }
+  if (s->P.n_shards > 1) { set_err("ms_add_gen_clients: single GPU only"); return MS_ERR_ARG; }
+  if ((uint64_t)s->P.n_ep + gc->n_clients > s->cfg.max_endpoints) { set_err("max_endpoints exhausted"); return MS_ERR_CAPACITY; }
+  Params& P = s->P;
+  int rc;
+  const uint32_t hist_cap = pow2_at_least(std::max<uint32_t>(1u << 16, 64u * gc->n_clients));
+  if ((rc = s->dalloc(&P.gc, s->cfg.max_endpoints)) || (rc = s->dalloc(&P.gc_hist, (size_t)hist_cap * 2))) return rc;
+  P.gc_hist_mask = hist_cap - 1u;
+  P.gc_n = gc->n_clients;
+  P.gc_read_permille = gc->read_permille;
+  P.gc_interval_ns = gc->interval_ns;
+  P.gc_timeout_ns = gc->timeout_ns > 0 ? gc->timeout_ns : 5000ll * kTickNs;      // client.clj:18-20
+  P.gc_limit_ns = gc->time_limit_ns;
+  P.gc_quiet_ns = gc->quiet_ns > 0 ? gc->quiet_ns : 10000ll * kTickNs;           // core.clj:75-78
+  const uint32_t first = P.n_ep;
+  std::vector<GenDev> init(gc->n_clients);
+  memset(init.data(), 0, init.size() * sizeof(GenDev));
+  for (uint32_t k = 0; k < gc->n_clients; k++) {
+    const std::string id = "c" + std::to_string(first_name + k);
+    if (s->by_name.count(id)) { set_err("endpoint already exists: " + id); return MS_ERR_ARG; }
+    const uint32_t idx = first + k;
+    s->kinds[idx] = MS_KIND_GEN_CLIENT;
+    s->names.push_back(id);
+    s->mailbox.emplace_back();
+    s->by_name[id] = idx;
+    init[k].node = k % s->cfg.n_nodes;
+    init[k].ordinal = k;
+  }
+  P.n_ep = first + gc->n_clients;
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaMemcpy(P.kind + first, s->kinds.data() + first, gc->n_clients, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(P.gc + first, init.data(), init.size() * sizeof(GenDev), cudaMemcpyHostToDevice));
+  return (int)first;
+}
+
+int ms_history_drain(ms_sim* s, ms_hist* out, size_t cap, size_t* n_out) {
+  std::lock_guard<std::mutex> g(s->mu);
+  cudaSetDevice(s->device);
+  if (n_out) *n_out = 0;
+  if (!s->P.gc_hist) return MS_OK;
+  const uint64_t avail = s->hs.gc_hist_n - s->hs.gc_hist_drained;
+  const size_t n = (size_t)std::min<uint64_t>(avail, cap);
+  if (!n || !out) return MS_OK;
+  static_assert(sizeof(ms_hist) == 32, "ms_hist is the device record");
+  for (size_t k = 0; k < n;) {      // the ring may wrap
+    const uint64_t pos = (s->hs.gc_hist_drained + k) & s->P.gc_hist_mask;
+    const size_t piece = (size_t)std::min<uint64_t>(n - k, (uint64_t)s->P.gc_hist_mask + 1 - pos);
+    CK(cudaMemcpy(out + k, s->P.gc_hist + pos * 2, piece * 32, cudaMemcpyDeviceToHost));
+    k += piece;
+  }
+  // records of one round are appended in whatever order its CTAs ran: (time, round, client) is the order
+  std::stable_sort(out, out + n, [](const ms_hist& a, const ms_hist& b) {
+    return a.time_ns != b.time_ns ? a.time_ns < b.time_ns : a.order < b.order;
+  });
+  s->hs.gc_hist_drained += n;
+  CK(cudaMemcpy(&s->P.st->gc_hist_drained, &s->hs.gc_hist_drained, 8, cudaMemcpyHostToDevice));
+  if (n_out) *n_out = n;
+  return MS_OK;
 }
 
 int ms_remove_endpoint(ms_sim* s, uint32_t idx) {

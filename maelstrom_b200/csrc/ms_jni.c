@@ -86,6 +86,17 @@ jint FN(recvJson)(JNIEnv* env, jclass c, jlong h, jint ep, jlong timeoutNs, jobj
   (void)c;
   return ms_recv_json(H(h), (uint32_t)ep, timeoutNs, (char*)BUF(out), (size_t)cap);
 }
+/* closed-loop clients on the device: cfg = direct buffer holding an ms_gen_config; history records are ms_hist (32 B) */
+jint FN(addGenClients)(JNIEnv* env, jclass c, jlong h, jobject cfg, jint firstName) {
+  (void)c;
+  return ms_add_gen_clients(H(h), (const ms_gen_config*)BUF(cfg), (uint32_t)firstName);
+}
+jlong FN(historyDrain)(JNIEnv* env, jclass c, jlong h, jobject out, jlong cap) {
+  (void)c;
+  size_t n = 0;
+  const int rc = ms_history_drain(H(h), (ms_hist*)BUF(out), (size_t)cap, &n);
+  return rc < 0 ? (jlong)rc : (jlong)n;
+}
 jint FN(scheduleOps)(JNIEnv* env, jclass c, jlong h, jobject ops, jlong n) {
   (void)c;
   return ms_schedule_ops(H(h), (const ms_op*)BUF(ops), (size_t)n);

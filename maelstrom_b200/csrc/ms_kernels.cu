@@ -362,6 +362,86 @@ __device__ __forceinline__ void emit_one(const Params& p, DevState* st, const Ne
 
 __global__ void k_set_bit(uint32_t* words, size_t word, uint32_t bit) { atomicOr(words + word, 1u << bit); }
 
+// ------------------------------------------------------------------ closed-loop clients (MS_KIND_GEN_CLIENT)
+// maelstrom.client (client.clj:41-172) + what a Jepsen worker does with the workload's generator
+// (workload/broadcast.clj:187-241, core.clj:67-80); the spec is in include/maelstrom_b200.h
+// (ms_add_gen_clients) and DESIGN.md 2.10; the oracle's twin is or_sim::gen_step.
+__device__ __forceinline__ void gen_hist(const Params& p, DevState* st, int64_t now, uint64_t round, uint32_t e,
+                                         const GenDev& g, uint32_t op, uint32_t type, uint32_t f, uint32_t error, uint32_t value) {
+  const unsigned long long pos = atomicAdd((unsigned long long*)&st->gc_hist_n, 1ull);
+  if (pos - st->gc_hist_drained > p.gc_hist_mask) { latch_error(st, E_HISTORY_RING, e); return; }
+  uint4* at = p.gc_hist + (pos & p.gc_hist_mask) * 2;
+  const uint64_t order = (round << 24) | g.ordinal;
+  at[0] = make_uint4((uint32_t)now, (uint32_t)((uint64_t)now >> 32), (uint32_t)order, (uint32_t)(order >> 32));
+  at[1] = make_uint4(e, op, type | (f << 8) | (error << 16), value);
+}
+
+__device__ __forceinline__ bool gen_timer_due(const Params& p, const GenDev& g, int64_t now) {
+  if (g.waiting_for) return now >= g.deadline_ns;
+  if (g.phase == GEN_MIX) return now >= p.gc_limit_ns || now >= g.next_op_ns;
+  if (g.phase == GEN_QUIET) return now >= p.gc_limit_ns + p.gc_quiet_ns;
+  return g.phase == GEN_FINAL;            // the final read has completed or timed out: -> done
+}
+
+// One step of client e: its due replies in id order, then the timeout, then at most one invocation.
+// Returns true and fills `out` when the step sends a request.
+__device__ bool gen_step(const Params& p, DevState* st, uint32_t e, int64_t now, uint64_t round, const uint4* myring,
+                         uint32_t head, uint32_t my_mask, uint32_t n, const uint16_t* ord, const uint32_t* vals, Rec& out) {
+  GenDev g = p.gc[e];
+  for (uint32_t pos = 0; pos < n; pos++) {
+    const uint32_t i = ord[pos];
+    if (!(vals[i] & (1u << 30))) continue;                                 // V_RECV: cut by a partition
+    const uint4* rp = myring + (size_t)((head + i) & my_mask) * 3;
+    const uint4 vb = rp[1], vc = rp[2];
+    const uint32_t type = vc.x & 0xFFFFu, flags = vc.x >> 16;
+    if (!g.waiting_for || !(flags & MS_F_REPLY) || vb.w != g.waiting_for) continue;   // client.clj:106-107
+    uint32_t outcome = MS_H_OK, err = 0, value = g.cur_value;
+    if (type == MS_T_ERROR) {                                              // client.clj:165-172, errors.edn
+      err = vc.y;
+      const bool definite = err != 0 && err != 13;
+      outcome = (definite || g.cur_f == MS_HF_READ) ? MS_H_FAIL : MS_H_INFO;
+    } else if (g.cur_f == MS_HF_READ) {
+      value = vc.y;                                                        // read_ok: the size of the set
+    }
+    gen_hist(p, st, now, round, e, g, g.ops, outcome, g.cur_f, err, value);
+    g.waiting_for = 0;
+  }
+  if (g.waiting_for && now >= g.deadline_ns) {                             // client.clj:96-101,160-164
+    gen_hist(p, st, now, round, e, g, g.ops, g.cur_f == MS_HF_READ ? MS_H_FAIL : MS_H_INFO, g.cur_f, MS_H_TIMEOUT, g.cur_value);
+    g.waiting_for = 0;
+  }
+  bool send = false;
+  if (!g.waiting_for) {
+    uint32_t f = MS_HF_READ, value = 0;
+    if (g.phase == GEN_MIX) {
+      if (now >= p.gc_limit_ns) g.phase = GEN_QUIET;
+      else if (now >= g.next_op_ns) {
+        uint32_t x[4];
+        philox4x32_10(g.ops, e, 0xC11E47u, 0u, p.seed_lo, p.seed_hi, x);   // the client's own stream: op k
+        if ((((uint64_t)x[0] * 1000u) >> 32) >= p.gc_read_permille) { f = MS_HF_BROADCAST; value = g.ordinal + p.gc_n * g.bcasts++; }
+        g.next_op_ns = now + (int64_t)(((unsigned __int128)x[1] * (unsigned __int128)(2 * (uint64_t)p.gc_interval_ns)) >> 32);
+        send = true;
+      }
+    }
+    if (g.phase == GEN_QUIET && now >= p.gc_limit_ns + p.gc_quiet_ns) { g.phase = GEN_FINAL; send = true; }   // broadcast.clj:237-240
+    else if (g.phase == GEN_FINAL && !send) g.phase = GEN_DONE;
+    if (send) {
+      g.ops++;
+      g.cur_f = f; g.cur_value = value;
+      g.waiting_for = ++g.next_msg_id;                                     // client.clj:61-64
+      g.deadline_ns = now + p.gc_timeout_ns;
+      gen_hist(p, st, now, round, e, g, g.ops, MS_H_INVOKE, f, 0, value);
+      out.round = 0; out.ticket = 0; out.idx = 0;
+      out.src = e; out.dest = g.node; out.msg_id = g.waiting_for; out.in_reply_to = 0;
+      const uint32_t wtype = f == MS_HF_READ ? (uint32_t)MS_T_READ : (p.workload == MS_W_GSET ? (uint32_t)MS_T_ADD : (uint32_t)MS_T_BROADCAST);
+      out.tf = wtype | ((uint32_t)MS_F_MSG_ID << 16);
+      out.p0 = value; out.p1 = 0;
+    }
+  }
+  p.gc[e] = g;
+  return send;
+}
+
 #include "ms_raft.cuh"
 
 // ------------------------------------------------------------------ k_barrier (sharded runs)
@@ -420,7 +500,8 @@ __global__ void k_snapshot(Params p) {
     const bool timer_due = e < p.n_servers && p.kind[e] == MS_KIND_SERVER &&
                            ((p.workload == MS_W_GSET && p.gs_init[e] && st->now >= p.gs_next_fire[e]) ||
                             (p.workload == MS_W_RAFT && rf_timer_due(p.rf_node[e], st->now)));
-    if (n == 0 && !timer_due) {
+    const bool gen_due = p.gc && p.kind[e] == MS_KIND_GEN_CLIENT && gen_timer_due(p, p.gc[e], st->now);
+    if (n == 0 && !timer_due && !gen_due) {
       // nothing to receive, hence nothing to emit: the ticket is finished right here
       const uint32_t t = p.n_inj_tickets + e;
       p.rt_chunk[(size_t)row * p.t_max + t] = 0;
@@ -428,9 +509,14 @@ __global__ void k_snapshot(Params p) {
       n_empty++;
       continue;
     }
+    // longest windows first: a class's list is filled from the front by the windows in the upper half
+    // of its size range and from the back by the others, and consumed front to back, so the tail of
+    // a round is made of short tickets
     const uint32_t c = class_of(p, n);
-    const uint32_t k = atomicAdd(&st->cls_count[par][c], 1u);
-    p.cls_list[((size_t)par * 4 + c) * p.t_max + k] = p.n_inj_tickets + e;
+    const uint32_t lo_cap = c ? p.cls_cap[c - 1] : 0u;
+    uint32_t* list = p.cls_list + ((size_t)par * 4 + c) * p.t_max;
+    if (n > lo_cap + ((min(p.cls_cap[c], p.max_window) - lo_cap) >> 1)) list[atomicAdd(&st->cls_count[par][c], 1u)] = p.n_inj_tickets + e;
+    else list[p.t_max - 1u - atomicAdd(&st->cls_small[par][c], 1u)] = p.n_inj_tickets + e;
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) n_empty += __shfl_xor_sync(FULL, n_empty, d);
@@ -466,7 +552,7 @@ __global__ void k_snapshot(Params p) {
     }
   }
   if (gid == 0) {
-    for (int c = 0; c < 4; c++) { st->cls_count[par ^ 1u][c] = 0; st->cls_cursor[par ^ 1u][c] = 0; }
+    for (int c = 0; c < 4; c++) { st->cls_count[par ^ 1u][c] = 0; st->cls_small[par ^ 1u][c] = 0; st->cls_cursor[par ^ 1u][c] = 0; }
     st->slot_open = 1;
   }
 }
@@ -1126,8 +1212,13 @@ __device__ void service_handle(const Params& p, uint32_t svc, const SvReq& q, ui
 
 
 // WL = node-program families compiled in: bit 0 g-set, bit 2 Raft (else echo / broadcast), bit 1 services.
+// CTA width per window-size class (ms_engine.cu: 64 / 128 / 256 / 512 threads; the g-set family runs
+// 256 wide) and the register budget that goes with it
+#ifndef MS_ROUND_MINB2
+#define MS_ROUND_MINB2 4
+#endif
 template <int CLS, int WL>
-__global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
+__global__ void __launch_bounds__(CLS == 3 ? 512 : 256, CLS == 3 ? 2 : MS_ROUND_MINB2) k_round(Params p, uint32_t cap) {
   constexpr uint32_t cls = CLS;
   constexpr bool GS = (WL & 1) != 0;
   constexpr bool SV = (WL & 2) != 0;
@@ -1165,6 +1256,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
   __shared__ uint16_t s_S[MAXB + 1][MAXNB];   // sorted: new messages from neighbor j in blocks < rho
   __shared__ uint32_t s_nbbase[MAXNB];        // ring position claimed for this CTA's gossip to neighbor j
   __shared__ uint32_t s_nbr[MAXNB];           // this node's neighbor list (topology order)
+  __shared__ uint4 s_gen[2];                  // the request a closed-loop client sends in this step
 
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
   if (tid == 0) s_np = *p.np;
@@ -1175,7 +1267,8 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
   const uint32_t T = p.n_inj_tickets + p.n_ep;
   const uint32_t row = (uint32_t)round & p.hist_mask;
   const uint32_t par = (uint32_t)round & 1u;
-  const uint32_t my_count = st->cls_count[par][cls];                // final: k_snapshot has completed
+  const uint32_t my_big = st->cls_count[par][cls];                  // final: k_snapshot has completed
+  const uint32_t my_count = my_big + st->cls_small[par][cls];
   const uint32_t* my_list = p.cls_list + ((size_t)par * 4 + cls) * p.t_max;
   const uint32_t tag = ((uint32_t)round & 0x7FFFu) + 1u;            // validates this round's table entries
   // with no loss and a constant latency nothing depends on the random draw: skip Philox
@@ -1205,7 +1298,7 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
   // fetch the index of the NEXT ticket now; it is consumed at the end of this one
   uint32_t next_li = 0;
   if (tid == 0) next_li = atomicAdd(&st->cls_cursor[par][cls], 1u);
-  const uint32_t ticket = my_list[li];
+  const uint32_t ticket = li < my_big ? my_list[li] : my_list[p.t_max - 1u - (li - my_big)];
   PHASE_MARK(0);
   if (timing && tid == 0) atomicAdd((unsigned long long*)&p.phase_cycles[cls * 16 + 15], 1ull);
 
@@ -1551,6 +1644,20 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
         n_timer = s_misc[2];
       }
     }
+    if (kind == MS_KIND_GEN_CLIENT) {
+      // ---- closed-loop client: replies in id order, timeout, at most one new request (gen_step)
+      if (tid == 0) {
+        Rec q;
+        const bool send = gen_step(p, st, e, now, round, myring, head, my_mask, n, ord, vals, q);
+        if (send) {
+          s_gen[0] = make_uint4(q.src, q.dest, q.msg_id, q.in_reply_to);
+          s_gen[1] = make_uint4(q.tf, q.p0, 0u, 0u);
+        }
+        s_misc[2] = send ? 1u : 0u;
+      }
+      __syncthreads();
+      n_timer = s_misc[2];
+    }
     if constexpr (SV) {
       // ---- service endpoint: requests are handled one at a time in dequeue order (service.clj:147-156,
       //      245-263) by one thread; the reply is parked in vals[] / keyB[] for the emit phase
@@ -1890,6 +1997,12 @@ __global__ void __launch_bounds__(512, 2) k_round(Params p, uint32_t cap) {
           r.src = a.x; r.dest = a.y; r.msg_id = a.z; r.in_reply_to = a.w;
           r.tf = b.x; r.p0 = b.y; r.p1 = (uint64_t)b.z | ((uint64_t)b.w << 32);
         }
+      }
+      if (kind == MS_KIND_GEN_CLIENT && valid && j < n_timer) {
+        timer_emission = true;
+        const uint4 a = s_gen[0], b = s_gen[1];
+        r.src = a.x; r.dest = a.y; r.msg_id = a.z; r.in_reply_to = a.w;
+        r.tf = b.x; r.p0 = b.y; r.p1 = 0;
       }
       if (valid && !timer_emission) {
         const uint32_t jm = j - n_timer;       // index among the emissions caused by messages

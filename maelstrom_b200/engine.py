@@ -119,6 +119,24 @@ class Sim:
             self._chk(rc)
             return out[0] if rc == 1 else None
 
+    def add_gen_clients(self, n_clients, interval_ns, time_limit_ns, read_permille=500, timeout_ns=0, quiet_ns=0,
+                        first_name=0):
+        """ms_add_gen_clients: closed-loop clients on the device; returns the first endpoint index"""
+        gc = _lib.GenConfig(n_clients, read_permille, interval_ns, timeout_ns, time_limit_ns, quiet_ns)
+        return self._chk(self.L.ms_add_gen_clients(self.h, C.byref(gc), first_name))
+
+    def history(self, cap=1 << 20):
+        """ms_history_drain: the history records since the last call, in (time, round, client) order"""
+        parts = []
+        while True:
+            out = np.zeros(cap, dtype=_lib.HIST_DTYPE)
+            n = C.c_size_t(0)
+            self._chk(self.L.ms_history_drain(self.h, out.ctypes.data, cap, C.byref(n)))
+            parts.append(out[:n.value])
+            if n.value < cap:
+                break
+        return np.concatenate(parts)
+
     def schedule(self, ops):
         ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
         return self._chk(self.L.ms_schedule_ops(self.h, ops.ctypes.data, ops.size))

@@ -342,6 +342,12 @@ struct Endpoint {
   uint64_t fires = 0;                   // g-set: replication runs so far
   Service svc;                          // OR_KIND_SERVICE
   RaftNode rn;                          // OR_W_RAFT servers
+  // OR_KIND_GEN_CLIENT: maelstrom.client state (client.clj:41-64) + where the worker is in its generator
+  struct Gen {
+    uint32_t next_msg_id = 0, waiting_for = 0;
+    int64_t deadline_ns = 0, next_op_ns = 0;
+    uint32_t node = 0, ops = 0, bcasts = 0, phase = 0, cur_f = 0, cur_value = 0, ordinal = 0;
+  } gen;
 };
 
 }  // namespace
@@ -367,12 +373,14 @@ struct or_sim {
   std::map<std::pair<uint32_t, uint64_t>, std::vector<uint32_t>> gset_snaps;
   uint64_t client_replies = 0;
   uint64_t undelivered = 0;    // sends whose src / dest was not a registered endpoint
+  or_gen_config gcfg = {0, 0, 0, 0, 0, 0};
+  std::vector<or_hist> history;
   std::string error;
   uint64_t stats[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 
   // util.clj:7-10 goes by the name ("c..."): a removed client is still a client
   bool is_client(uint32_t e) const {
-    return e < eps.size() && (eps[e].kind == OR_KIND_CLIENT || eps[e].kind == OR_KIND_SIM_CLIENT);
+    return e < eps.size() && (eps[e].kind == OR_KIND_CLIENT || eps[e].kind == OR_KIND_SIM_CLIENT || eps[e].kind == OR_KIND_GEN_CLIENT);
   }
   bool involves_client(const or_msg& m) const {                                // util.clj:12-16
     return is_client(m.src) || is_client(m.dest);
@@ -893,6 +901,65 @@ struct or_sim {
     }
   }
 
+  // ------------------------------------------------------------- closed-loop clients
+  void gen_hist(uint32_t e, uint32_t op, uint8_t type, uint8_t f, uint16_t err, uint32_t value) {
+    or_hist h;
+    h.time_ns = now; h.order = (round << 24) | eps[e].gen.ordinal; h.client = e; h.op = op;
+    h.type = type; h.f = f; h.error = err; h.value = value;
+    history.push_back(h);
+  }
+  // a reply delivered to client e (client.clj:81-117): the awaited one completes the op, anything else is dropped
+  void gen_reply(uint32_t e, const or_msg& m) {
+    Endpoint::Gen& g = eps[e].gen;
+    if (!g.waiting_for || !(m.flags & OR_F_REPLY) || m.in_reply_to != g.waiting_for) return;   // :106-107
+    uint8_t outcome = 1; uint16_t err = 0; uint32_t value = g.cur_value;
+    if (m.type == OR_T_ERROR) {                          // :165-172; definite = all codes but 0 and 13 (errors.edn)
+      err = (uint16_t)m.p0;
+      const bool definite = m.p0 != 0 && m.p0 != 13;
+      outcome = (definite || g.cur_f == 1) ? 2 : 3;
+    } else if (g.cur_f == 1) {
+      value = m.p0;                                      // read_ok: the size of the set
+    }
+    gen_hist(e, g.ops, outcome, (uint8_t)g.cur_f, err, value);
+    g.waiting_for = 0;
+  }
+  // after the replies of the round: timeout, then at most one invocation (the worker asks its generator)
+  void gen_step(uint32_t e, std::vector<Emit>& out) {
+    Endpoint::Gen& g = eps[e].gen;
+    if (g.waiting_for && now >= g.deadline_ns) {         // :96-101,160-164
+      gen_hist(e, g.ops, g.cur_f == 1 ? 2 : 3, (uint8_t)g.cur_f, 0xFFFF, g.cur_value);
+      g.waiting_for = 0;
+    }
+    if (g.waiting_for) return;
+    bool send = false;
+    uint32_t f = 1, value = 0;
+    if (g.phase == 0) {
+      if (now >= gcfg.time_limit_ns) g.phase = 1;
+      else if (now >= g.next_op_ns) {
+        const uint32_t ctr[4] = {g.ops, e, 0xC11E47u, 0u};
+        const uint32_t key[2] = {cfg.seed_lo, cfg.seed_hi};
+        uint32_t x[4];
+        philox(ctr, key, x);
+        if ((((uint64_t)x[0] * 1000u) >> 32) >= gcfg.read_permille) { f = 0; value = g.ordinal + gcfg.n_clients * g.bcasts++; }
+        g.next_op_ns = now + (int64_t)(((unsigned __int128)x[1] * (unsigned __int128)(2 * (uint64_t)gcfg.interval_ns)) >> 32);
+        send = true;
+      }
+    }
+    if (g.phase == 1 && now >= gcfg.time_limit_ns + gcfg.quiet_ns) { g.phase = 2; send = true; }   // broadcast.clj:237-240
+    else if (g.phase == 2 && !send) g.phase = 3;
+    if (!send) return;
+    g.ops++;
+    g.cur_f = f; g.cur_value = value;
+    g.waiting_for = ++g.next_msg_id;                     // client.clj:61-64
+    g.deadline_ns = now + gcfg.timeout_ns;
+    gen_hist(e, g.ops, 0, (uint8_t)f, 0, value);
+    or_msg m; std::memset(&m, 0, sizeof m);
+    m.src = e; m.dest = g.node; m.flags = OR_F_MSG_ID; m.msg_id = g.waiting_for;
+    m.type = f == 1 ? OR_T_READ : (cfg.workload == OR_W_GSET ? OR_T_ADD : OR_T_BROADCAST);
+    m.p0 = value;
+    out.push_back(Emit(m));
+  }
+
   bool run_round() {
     std::vector<Envelope> pending;
     // (1) injector
@@ -932,6 +999,9 @@ struct or_sim {
           case OR_KIND_HOST:
             ep.mailbox.push_back(m);
             break;
+          case OR_KIND_GEN_CLIENT:
+            gen_reply(e, m);
+            break;
           case OR_KIND_SERVICE: {         // service-thread (service.clj:245-263)
             or_body q;
             q.type = m.type; q.flags = m.flags; q.msg_id = m.msg_id; q.in_reply_to = m.in_reply_to;
@@ -960,6 +1030,7 @@ struct or_sim {
         if (!error.empty()) return false;
       }
       if (cfg.workload == OR_W_RAFT && ep.kind == OR_KIND_SERVER) raft_actions(e, out);
+      if (ep.kind == OR_KIND_GEN_CLIENT) gen_step(e, out);
       for (uint32_t j = 0; j < out.size(); j++) {
         if (out[j].has_snap) snapshots[next_id] = out[j].snap;   // keyed by the read_ok's net id
         if (!send(e, j, out[j].m, pending)) return false;
@@ -1156,6 +1227,27 @@ size_t or_read_snapshot(or_sim* s, uint64_t msg_id, uint32_t* vals, size_t cap) 
   return n;
 }
 
+int or_add_gen_clients(or_sim* s, const or_gen_config* gc, uint32_t first_name) {
+  if (!gc || gc->n_clients == 0 || gc->interval_ns <= 0 || s->gcfg.n_clients) return -2;
+  s->gcfg = *gc;
+  if (s->gcfg.timeout_ns <= 0) s->gcfg.timeout_ns = 5000ll * kTickNs;      // client.clj:18-20
+  if (s->gcfg.quiet_ns <= 0) s->gcfg.quiet_ns = 10000ll * kTickNs;         // core.clj:75-78
+  const int first = (int)s->eps.size();
+  for (uint32_t k = 0; k < gc->n_clients; k++) {
+    Endpoint ep;
+    ep.name = "c" + std::to_string(first_name + k);
+    ep.kind = OR_KIND_GEN_CLIENT;
+    ep.gen.node = k % s->cfg.n_nodes;
+    ep.gen.ordinal = k;
+    s->eps.push_back(ep);
+  }
+  return first;
+}
+size_t or_history_copy(or_sim* s, size_t first, or_hist* out, size_t cap) {
+  size_t n = 0;
+  for (size_t i = first; i < s->history.size() && n < cap; i++, n++) if (out) out[n] = s->history[i];
+  return out ? n : s->history.size() - std::min(first, s->history.size());
+}
 uint64_t or_client_replies(or_sim* s) { return s->client_replies; }
 uint64_t or_undeliverable(or_sim* s) { return s->undelivered; }
 

@@ -93,7 +93,8 @@ enum { OR_TOPO_GRID = 0, OR_TOPO_LINE = 1, OR_TOPO_TOTAL = 2,
        OR_TOPO_TREE2 = 3, OR_TOPO_TREE3 = 4, OR_TOPO_TREE4 = 5 };
 enum { OR_DIST_CONSTANT = 0, OR_DIST_UNIFORM = 1, OR_DIST_EXPONENTIAL = 2 };
 enum { OR_KIND_SERVER = 0, OR_KIND_CLIENT = 1, OR_KIND_HOST = 2, OR_KIND_SIM_CLIENT = 3,
-       OR_KIND_SERVICE = 4 };  /* lin-kv / seq-kv / lww-kv / lin-tso by name (service.clj:290-296) */
+       OR_KIND_SERVICE = 4,    /* lin-kv / seq-kv / lww-kv / lin-tso by name (service.clj:290-296) */
+       OR_KIND_GEN_CLIENT = 5 }; /* closed-loop client: maelstrom.client + a Jepsen worker (or_add_gen_clients) */
 enum { OR_SVC_LIN_KV = 0, OR_SVC_SEQ_KV = 1, OR_SVC_LWW_KV = 2, OR_SVC_LIN_TSO = 3 };
 enum {
   OR_T_INIT = 1, OR_T_INIT_OK = 2, OR_T_ERROR = 3,
@@ -148,6 +149,24 @@ size_t   or_journal_copy(or_sim*, size_t first, or_event* ev, or_body* bodies, s
 void     or_stats(or_sim*, uint64_t out[9]);
 size_t   or_node_set(or_sim*, uint32_t node, uint32_t* vals, size_t cap);
 size_t   or_read_snapshot(or_sim*, uint64_t msg_id, uint32_t* vals, size_t cap);
+/* Closed-loop clients (client.clj:41-172 + the generator of workload/broadcast.clj:187-241, core.clj:67-80):
+ * one outstanding request, msg ids from 1, stale replies discarded, timeout, error -> :fail / :info,
+ * a mix of broadcast (g-set: add) and read staggered uniformly on [0, 2 interval), final reads after a
+ * quiet period.  Same record layouts as the engine's ms_gen_config / ms_hist (restated). */
+typedef struct or_gen_config {
+  uint32_t n_clients, read_permille;
+  int64_t  interval_ns, timeout_ns, time_limit_ns, quiet_ns;
+} or_gen_config;
+typedef struct or_hist {
+  int64_t  time_ns;
+  uint64_t order;
+  uint32_t client, op;
+  uint8_t  type, f;          /* type: 0 invoke, 1 ok, 2 fail, 3 info; f: 0 broadcast / add, 1 read */
+  uint16_t error;            /* error code of the reply, 0xFFFF = timeout */
+  uint32_t value;
+} or_hist;
+int      or_add_gen_clients(or_sim*, const or_gen_config*, uint32_t first_name);
+size_t   or_history_copy(or_sim*, size_t first, or_hist* out, size_t cap);
 uint64_t or_client_replies(or_sim*);
 uint64_t or_undeliverable(or_sim*);   /* sends dropped because src / dest was not a registered endpoint */
 

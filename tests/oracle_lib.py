@@ -28,7 +28,14 @@ assert BODY_DTYPE.itemsize == 24 and OP_DTYPE.itemsize == 40
 W_ECHO, W_BROADCAST, W_GSET, W_RAFT, W_TXN = 0, 1, 2, 3, 4
 TOPO = {"grid": 0, "line": 1, "total": 2, "tree": 3, "tree2": 3, "tree3": 4, "tree4": 5}
 DIST = {"constant": 0, "uniform": 1, "exponential": 2}
-KIND_SERVER, KIND_CLIENT, KIND_HOST, KIND_SIM_CLIENT, KIND_SERVICE = 0, 1, 2, 3, 4
+KIND_SERVER, KIND_CLIENT, KIND_HOST, KIND_SIM_CLIENT, KIND_SERVICE, KIND_GEN_CLIENT = 0, 1, 2, 3, 4, 5
+HIST_DTYPE = np.dtype([("time_ns", "<i8"), ("order", "<u8"), ("client", "<u4"), ("op", "<u4"), ("type", "u1"),
+                       ("f", "u1"), ("error", "<u2"), ("value", "<u4")])
+
+
+class GenConfig(C.Structure):
+    _fields_ = [("n_clients", C.c_uint32), ("read_permille", C.c_uint32), ("interval_ns", C.c_int64),
+                ("timeout_ns", C.c_int64), ("time_limit_ns", C.c_int64), ("quiet_ns", C.c_int64)]
 SVC = {"lin-kv": 0, "seq-kv": 1, "lww-kv": 2, "lin-tso": 3}
 T = dict(init=1, init_ok=2, error=3, echo=10, echo_ok=11, topology=20, topology_ok=21,
          broadcast=22, broadcast_ok=23, read=24, read_ok=25, add=30, add_ok=31,
@@ -99,6 +106,9 @@ def lib():
         L.or_read_snapshot.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t]
         L.or_client_replies.restype = C.c_uint64
         L.or_client_replies.argtypes = [C.c_void_p]
+        L.or_add_gen_clients.argtypes = [C.c_void_p, C.POINTER(GenConfig), C.c_uint32]
+        L.or_history_copy.restype = C.c_size_t
+        L.or_history_copy.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
         L.or_undeliverable.restype = C.c_uint64
         L.or_undeliverable.argtypes = [C.c_void_p]
         L.or_topology.restype = C.c_size_t
@@ -283,6 +293,21 @@ class Sim:
 
     def undeliverable(self):
         return int(self.L.or_undeliverable(self.h))
+
+    def add_gen_clients(self, n_clients, interval_ns, time_limit_ns, read_permille=500, timeout_ns=0, quiet_ns=0,
+                        first_name=0):
+        gc = GenConfig(n_clients, read_permille, interval_ns, timeout_ns, time_limit_ns, quiet_ns)
+        return self._chk(self.L.or_add_gen_clients(self.h, C.byref(gc), first_name))
+
+    def history(self):
+        """everything since the last call (the engine's ms_history_drain has the same contract)"""
+        first = getattr(self, "_hist_seen", 0)
+        n = self.L.or_history_copy(self.h, first, None, 0)
+        out = np.zeros(n, dtype=HIST_DTYPE)
+        if n:
+            self.L.or_history_copy(self.h, first, out.ctypes.data, n)
+        self._hist_seen = first + n
+        return out
 
 
 class Service:

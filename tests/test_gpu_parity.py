@@ -57,6 +57,34 @@ def test_flood_4096_grid():
     assert g.stats()["servers"]["send-count"] == 3 * 12033
 
 
+@pytest.mark.gpu
+def test_bench_topology_heavy_windows_vs_oracle(engine_backend):
+    # The bench configuration itself (4096 nodes, 64x64 grid, thousands of values per tick: windows in
+    # the upper size classes, sender-block ordering with its bitonic fallbacks, per-neighbor block
+    # claims) against the oracle, journal bit for bit: 2 ticks x 1280 values = 30.8 M messages
+    if engine_backend != "cuda":
+        pytest.skip("61 M journal events: B200 only (the emulator covers the same paths at 16-25 nodes)")
+    n, V, ticks = 4096, 1280, 2
+    g, o = make_pair(n, topology="grid", n_values=V * ticks + 8, max_endpoints=n + 8, ring_cap=4096, max_window=2048,
+                     journal_cap_log2=26, journal_level=1)
+
+    def scenario(s, body):
+        cs = [s.add_endpoint("c%d" % i, O.KIND_SIM_CLIENT) for i in range(4)]
+        ops, nv = random_broadcast_ops(n, cs, n_ticks=ticks, per_tick=V, seed=77)
+        s.schedule(ops)
+        s.run(ticks * 1_000_000)
+
+    both(g, o, scenario)
+    ev_g, _ = g.drain(bodies=False)
+    ev_o, _ = o.journal()
+    assert len(ev_g) == len(ev_o) == 2 * ticks * V * 12035
+    for f in ("event_id", "time_ns", "msg_id", "src", "dest"):
+        assert np.array_equal(ev_g[f], ev_o[f]), f
+    assert g.stats() == o.stats() and g.round == o.round
+    c = g.counters()
+    assert c["max_window"] > 512 and c["fallback_sorts"] > 0       # the big-window machinery did run
+
+
 def test_echo_doc_counts():
     g, o = make_pair(1, workload="echo")
 

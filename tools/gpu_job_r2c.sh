@@ -13,6 +13,9 @@ timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 7 --log-file $O
 echo "racecheck rc=$?" >> $O/racecheck_pytest.log
 timeout 900 python bench.py --steps 10 --warmup 3 > $O/bench_broadcast.json 2> $O/bench_broadcast.err
 echo "rc=$?" >> $O/bench_broadcast.err
+for v in mb3 mb2; do
+  MS_B200_LIB=$PWD/maelstrom_b200/libmaelstrom_b200_$v.so timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu --no-e2e > $O/bench_variant_$v.json 2> $O/bench_variant_$v.err
+done
 timeout 300 python bench.py --config broadcast-lat1 --values-per-tick 64 --steps 3 --warmup 3 --no-cpu > $O/bench_lat1_small.json 2> $O/bench_lat1_small.err
 echo "rc=$?" >> $O/bench_lat1_small.err
 timeout 600 python bench.py --config broadcast-lat1 --steps 6 --warmup 3 --no-cpu > $O/bench_lat1.json 2> $O/bench_lat1.err
@@ -35,5 +38,5 @@ timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_r
   python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e --journal-cap-log2 22 > $O/ncu_full.log 2>&1
 tail -3 $O/pytest_gpu.log $O/memcheck_pytest.log $O/racecheck_pytest.log
 tail -c 300 $O/memcheck.log $O/racecheck.log
-for f in broadcast lat1_small lat1 gset16k txn256k raft64k; do echo "== $f"; tail -2 $O/bench_$f.err | cut -c1-700; cut -c1-400 $O/bench_$f.json; done
+for f in broadcast variant_mb3 variant_mb2 lat1_small lat1 gset16k txn256k raft64k; do echo "== $f"; tail -2 $O/bench_$f.err | cut -c1-700; cut -c1-400 $O/bench_$f.json; done
 ls -la $O
