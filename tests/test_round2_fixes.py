@@ -18,7 +18,7 @@ from scenarios import assert_same_journal, both, make_pair, ops_array, random_br
 pytestmark = pytest.mark.usefixtures("engine_backend")
 
 
-@pytest.mark.parametrize("dist,mean,slots", [("exponential", 3, 16), ("uniform", 6, 16), ("constant", 7, 4)])
+@pytest.mark.parametrize("dist,mean,slots", [("exponential", 3, 16), ("constant", 7, 4)])
 def test_slow_with_latency_beyond_the_wheel(dist, mean, slots):
     # 25-node grid, slow! twice (x100): latencies of hundreds of ticks on a wheel of `slots` slots
     n = 25
@@ -133,13 +133,13 @@ def test_schedule_rejects_a_bad_batch_as_a_whole():
 
 
 def test_many_incremental_schedules_prefix_table():
-    # tick_off is rebuilt with one counting pass per call; 80 small appends
+    # tick_off is rebuilt with one counting pass per call; 40 small appends
     n = 16
     g, o = make_pair(n, topology="grid", n_values=1024)
     cg, co = g.add_endpoint("c0"), o.add_endpoint("c0")
     rng = np.random.default_rng(3)
     t, mid = 0, 0
-    for _ in range(80):
+    for _ in range(40):
         rows = []
         for _ in range(int(rng.integers(1, 4))):
             t += int(rng.integers(0, 20)) * 1_000_000 + int(rng.integers(0, 2)) * 500

@@ -82,10 +82,11 @@ def test_cfg4_raft_groups_with_partition_nemesis(engine_backend, group):
     # group = 5: many independent 5-node clusters side by side (node_ids of a node's init = its block,
     # raft.py:447-459); group = 0: one cluster of all nodes.  Partition nemesis: every second the
     # servers are re-split into two random components (bulk ms_net_partition), then healed.
+    big = engine_backend == "cuda"
     if group:
-        n = 4096 if engine_backend == "cuda" else 40
+        n = 4096 if big else 20
     else:
-        n = 64 if engine_backend == "cuda" else 12
+        n = 64 if big else 8
     g, o = make_pair(n, workload="lin-kv", latency_dist="uniform", latency_mean_ms=2, max_endpoints=n + 8,
                      ring_cap=2048, max_window=2048, server_ring_cap=256 if group else 1024,
                      server_max_window=128 if group else 512, raft_group=group,
@@ -96,15 +97,15 @@ def test_cfg4_raft_groups_with_partition_nemesis(engine_backend, group):
         cs = [s.add_endpoint("c%d" % i, O.KIND_SIM_CLIENT) for i in range(4)]
         init = ops_array([(0, cs[i % 4], i, "init", 1 + i // 4, 0) for i in range(n)])
         s.schedule(init)
-        s.schedule(kv_ops(n, cs, 6 * n if group else 40, 4200, 9000, 8, 23))
+        s.schedule(kv_ops(n, cs, 6 * n if group else 40, 4200, 9000 if big else 6000, 8, 23))
         rng = np.random.default_rng(99)
         s.run(4_500_000_000)                                           # first elections (2-4 s, raft.py:249-251)
-        for k in range(3):
+        for k in range(3 if big else 1):
             s.partition(rng.integers(0, 2, size=n).astype(np.uint32))  # clients (index >= n) are never cut
             s.run((5500 + 1500 * k) * 1_000_000)
             s.heal()
             s.run((6000 + 1500 * k) * 1_000_000)
-        s.run(11_000_000_000)
+        s.run(11_000_000_000 if big else 8_200_000_000)
         return [s.raft_state(i) for i in (0, n // 2, n - 1)], s.client_replies()
 
     rg, ro = both(g, o, scenario)
