@@ -100,24 +100,29 @@ def test_cfg4_raft_groups_with_partition_nemesis(engine_backend, group):
         s.schedule(kv_ops(n, cs, 6 * n if group else 40, 4200, 9000 if big else 6000, 8, 23))
         rng = np.random.default_rng(99)
         s.run(4_500_000_000)                                           # first elections (2-4 s, raft.py:249-251)
-        for k in range(3 if big else 1):
+        # three cycles for the single 64-node cluster; one for the 5-node clusters: from the second cycle on some
+        # cluster of 819 reaches the reference's runaway regime (a next_index <= 0 makes replicate_log raise before
+        # it records the replication, raft.py:399-441, so the leader replicates again in every loop iteration;
+        # DESIGN.md 2.3) and the message count -- of the oracle too -- grows without bound
+        for k in range(3 if big and not group else 1):
             s.partition(rng.integers(0, 2, size=n).astype(np.uint32))  # clients (index >= n) are never cut
             s.run((5500 + 1500 * k) * 1_000_000)
             s.heal()
             s.run((6000 + 1500 * k) * 1_000_000)
-        s.run(11_000_000_000 if big else 8_200_000_000)
-        return [s.raft_state(i) for i in (0, n // 2, n - 1)], s.client_replies()
+        s.run(11_000_000_000 if big and not group else 8_200_000_000)
+        return [s.raft_state(i) for i in range(min(n, 64))], s.client_replies()
 
     rg, ro = both(g, o, scenario)
     assert rg == ro
     assert rg[1] > 0                                                    # clients did get answers
     assert_same_journal(g, o)
-    # one leader per cluster at the end (every partition was healed 2 s ago)
-    G = group or n
-    for base in range(0, min(n, 10 * G), G):
-        members = range(base, min(base + G, n))
-        if len(members) > 1:
-            assert sum(1 for i in members if g.raft_state(i)["state"] == 3) == 1
+    # 5-node clusters: one leader each at the end (the partition was healed 2 s ago).  The 64-node cluster is
+    # leaderless at that point in the reference's algorithm too (the old leader's log is ahead of every
+    # candidate's and nothing commits: the late-bound closures of replicate_log credit one follower per pass,
+    # DESIGN.md 2.8); its node states were compared with the oracle's above.
+    if group:
+        for base in range(0, min(n, 60), group):
+            assert sum(1 for i in range(base, base + group) if rg[0][i]["state"] == 3) == 1
 
 
 def txn_ops(n, clients, n_ticks, per_tick, seed):

@@ -1,0 +1,26 @@
+#!/usr/bin/env python
+"""Aggregates `ncu --page source --csv --print-source cuda,sass` output per CUDA source line:
+   warp instructions executed, thread instructions, stall samples.  usage: ncu_lines.py file.csv [top]"""
+import csv, sys, collections
+path = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 60
+cur_file = None; hdr = None
+agg = collections.defaultdict(lambda: [0, 0, 0, ""])   # (file, line) -> [inst, thread inst, samples, text]
+line_no = None; line_txt = ""
+for r in csv.reader(open(path)):
+    if not r: continue
+    if r[0] == "File Path": cur_file = r[1].split("/")[-1]; continue
+    if r[0] == "Function Name": continue
+    if r[0] == "Line No": hdr = r; iI = r.index("Instructions Executed"); iT = r.index("Thread Instructions Executed"); iS = r.index("# Samples"); continue
+    if r[0] != "":
+        line_no = int(r[0]); line_txt = r[1]; agg[(cur_file, line_no)][3] = line_txt; continue
+    if r[2] in ("...", "-") or hdr is None: continue
+    try:
+        a = agg[(cur_file, line_no)]
+        a[0] += int(r[iI]); a[1] += int(r[iT]); a[2] += int(r[iS])
+    except ValueError:
+        pass
+tot_i = sum(a[0] for a in agg.values()); tot_s = sum(a[2] for a in agg.values())
+print("total warp inst %d, samples %d" % (tot_i, tot_s))
+rows = sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]
+for (f, l), a in rows:
+    print("%5.2f%% inst %5.2f%% smp  thr/inst %4.1f  %s:%d  %s" % (100.0 * a[0] / tot_i, 100.0 * a[2] / max(tot_s, 1), a[1] / max(a[0], 1), f, l, a[3].strip()[:110]))
