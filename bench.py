@@ -750,7 +750,7 @@ def gpu_arm(args, rank, world, local_rank):
         e2e = {"seconds": t_e2e, "msgs": msgs_e2e, "h2d": h2d // max(K, 1), "d2h": d2h // max(K, 1), "fmt": fmt}
 
     verify = None
-    if args.verify:
+    if (args.verify or world > 1) and not args.no_verify:
         verify = sharded_verify(mb, world, rank, local_rank)
 
     # ---- aggregate over ranks (max time, sum of work)
@@ -835,7 +835,8 @@ def main():
     ap.add_argument("--stream-events", type=int, default=1 << 26, help="events per host buffer of ms_run_streamed")
     ap.add_argument("--raft-log-cap", type=int, default=1024)
     ap.add_argument("--touch", action="store_true", help="e2e: fold every streamed byte on the host inside the timed region")
-    ap.add_argument("--verify", action="store_true")
+    ap.add_argument("--verify", action="store_true", help="sharded parity digest (on by default when --gpus > 1)")
+    ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

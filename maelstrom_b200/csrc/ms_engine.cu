@@ -1117,8 +1117,27 @@ static int step_locked(ms_sim* s, uint64_t n_rounds, int64_t stop) {
   if ((rc = s->stage_injections())) return rc;
   if ((rc = s->set_stop(stop))) return rc;
   s->launch_rounds(n_rounds);
+  {
+    const cudaError_t le = cudaGetLastError();      // a launch that was refused never shows up in the stream
+    if (le != cudaSuccess) { set_err(std::string("kernel launch: ") + cudaGetErrorString(le)); return MS_ERR_CUDA; }
+  }
   if ((rc = s->sync_state())) return rc;
   return s->maybe_flush_journal_file();
+}
+
+// what the device state looks like when rounds stop advancing (appended to the error text)
+static std::string stall_report(const ms_sim* s) {
+  const DevState& h = s->hs;
+  char buf[320];
+  snprintf(buf, sizeof buf,
+           " [round %llu now %lld stop %lld done %u slot_open %u rounds_run %llu drain_round %llu raw %llu/%llu events %llu/%llu "
+           "lists %u+%u %u+%u %u+%u %u+%u]",
+           (unsigned long long)h.round, (long long)h.now, (long long)h.stop_ns, h.done, h.slot_open,
+           (unsigned long long)h.rounds_run, (unsigned long long)h.drain_round, (unsigned long long)h.jraw_drained,
+           (unsigned long long)h.jraw_cursor, (unsigned long long)h.journal_drained, (unsigned long long)h.next_event,
+           h.cls_count[h.round & 1][0], h.cls_small[h.round & 1][0], h.cls_count[h.round & 1][1], h.cls_small[h.round & 1][1],
+           h.cls_count[h.round & 1][2], h.cls_small[h.round & 1][2], h.cls_count[h.round & 1][3], h.cls_small[h.round & 1][3]);
+  return buf;
 }
 
 int ms_step(ms_sim* s, uint64_t n_rounds) {
@@ -1134,7 +1153,7 @@ int ms_step(ms_sim* s, uint64_t n_rounds) {
     const uint64_t r0 = s->hs.rounds_run;
     const int rc = step_locked(s, b, INT64_MAX);
     if (rc) return rc;
-    if (s->hs.rounds_run == r0) { set_err("simulation made no progress (device refuses to run rounds)"); return MS_ERR_SIM; }
+    if (s->hs.rounds_run == r0) { set_err("simulation made no progress (device refuses to run rounds)" + stall_report(s)); return MS_ERR_SIM; }
     n_rounds -= std::min<uint64_t>(n_rounds, s->hs.rounds_run - r0);
   }
   return MS_OK;
@@ -1164,7 +1183,7 @@ int ms_run(ms_sim* s, int64_t until) {
     if (s->hs.now != stall_now) { stall_now = s->hs.now; stall_round = s->hs.rounds_run; }
     else if (time_stalled(s, stall_now, stall_round)) return MS_ERR_SIM;
     if (s->hs.rounds_run == r0 && s->hs.now < until && !journal_blocked(s)) {
-      set_err("simulation made no progress (device refuses to run rounds)");
+      set_err("simulation made no progress (device refuses to run rounds)" + stall_report(s));
       return MS_ERR_SIM;
     }
   }

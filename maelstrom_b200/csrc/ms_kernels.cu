@@ -71,6 +71,16 @@ __device__ __forceinline__ uint4 ld_v4_stream(const uint4* p) {
   return v;
 }
 
+// Bulk prefetch of `bytes` (a multiple of 16) at a 16-byte aligned global address into L2: one instruction for
+// a whole ring window (cp.async.bulk.prefetch, the bulk-copy engine's path; a hint, nothing waits on it).
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
+#ifndef MS_EMUL
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+#else
+  (void)gptr; (void)bytes;
+#endif
+}
+
 __device__ __forceinline__ void latch_error(DevState* st, uint32_t code, uint32_t arg) {
   if (atomicCAS(&st->error, 0u, code) == 0u) st->error_arg = arg;
 }
@@ -644,10 +654,6 @@ constexpr uint32_t V_RECV = 1u << 30;   // passed the partition check
 constexpr uint32_t V_CAND = 1u << 29;   // carries a broadcast value that needs the seen-set test
 constexpr uint32_t V_MASK = (1u << 29) - 1u;
 
-__device__ __forceinline__ uint32_t hash32(uint32_t x) {
-  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
-  return x;
-}
 
 // neighbor list of the node held in shared memory when it is short (nl != nullptr)
 struct NbrList {
@@ -1217,9 +1223,19 @@ __device__ void service_handle(const Params& p, uint32_t svc, const SvReq& q, ui
 #ifndef MS_ROUND_MINB2
 #define MS_ROUND_MINB2 4
 #endif
-template <int CLS, int WL>
-__global__ void __launch_bounds__(CLS == 3 ? 512 : 256, CLS == 3 ? 2 : MS_ROUND_MINB2) k_round(Params p, uint32_t cap) {
+// Default shape of window-size class CLS (ms_engine.cu build_sim: ladder / thr_default).  The FIX instantiations
+// assume it, which turns every shared-memory array base and every loop stride into an immediate; a simulation
+// sized differently (max_window below the ladder, threads_per_node) runs the generic ones.
+template <int CLS> struct ClsShape {
+  static constexpr uint32_t cap = CLS == 0 ? 128u : CLS == 1 ? 512u : 2048u;
+  static constexpr int nt = CLS == 0 ? 64 : CLS == 1 ? 128 : CLS == 2 ? 256 : 512;
+};
+
+template <int CLS, int WL, bool FIX = false>
+__global__ void __launch_bounds__(CLS == 3 ? 512 : 256, CLS == 3 ? 2 : MS_ROUND_MINB2) k_round(Params p, uint32_t cap_arg) {
   constexpr uint32_t cls = CLS;
+  static_assert(!FIX || CLS < 3, "class 3 is sized by max_window");
+  const uint32_t cap = FIX ? ClsShape<CLS>::cap : cap_arg;
   constexpr bool GS = (WL & 1) != 0;
   constexpr bool SV = (WL & 2) != 0;
   constexpr bool RF = (WL & 4) != 0;
@@ -1258,7 +1274,7 @@ __global__ void __launch_bounds__(CLS == 3 ? 512 : 256, CLS == 3 ? 2 : MS_ROUND_
   __shared__ uint32_t s_nbr[MAXNB];           // this node's neighbor list (topology order)
   __shared__ uint4 s_gen[2];                  // the request a closed-loop client sends in this step
 
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+  const int tid = threadIdx.x, nt = FIX ? ClsShape<CLS>::nt : (int)blockDim.x, lane = tid & 31;
   if (tid == 0) s_np = *p.np;
   __syncthreads();
   const NetParams np = s_np;
@@ -1394,6 +1410,10 @@ __global__ void __launch_bounds__(CLS == 3 ? 512 : 256, CLS == 3 ? 2 : MS_ROUND_
       uint32_t err_val = 0xFFFFFFFFu;
       uint32_t snap_gone = 0xFFFFFFFFu;
       bool inj_srv = false;
+      // the node's (few) neighbors in registers: the source's slot is four compares, no shared-memory loop
+      const bool nb4 = nb_smem && deg <= 4;
+      const uint32_t nr0 = (nb4 && deg > 0) ? s_nbr[0] : 0xFFFFFFFFu, nr1 = (nb4 && deg > 1) ? s_nbr[1] : 0xFFFFFFFFu;
+      const uint32_t nr2 = (nb4 && deg > 2) ? s_nbr[2] : 0xFFFFFFFFu, nr3 = (nb4 && deg > 3) ? s_nbr[3] : 0xFFFFFFFFu;
       for (int base = 0; base < (int)n; base += 2 * nt) {
         uint4 a[2], b[2], c[2];
 #pragma unroll
@@ -1438,7 +1458,9 @@ __global__ void __launch_bounds__(CLS == 3 ? 512 : 256, CLS == 3 ? 2 : MS_ROUND_
           else if (type == MS_T_ECHO) tc = TC_ECHO;
           }
           uint32_t slot = 0;
-          if (nb_smem) {
+          if (nb4) {
+            slot = src == nr3 ? 4u : src == nr2 ? 3u : src == nr1 ? 2u : src == nr0 ? 1u : 0u;
+          } else if (nb_smem) {
             for (uint32_t j = 0; j < deg; j++) if (s_nbr[j] == src) slot = j + 1;
           } else if (bcast && src < p.n_servers && src != e) {
             slot = 15;
@@ -1490,6 +1512,21 @@ __global__ void __launch_bounds__(CLS == 3 ? 512 : 256, CLS == 3 ? 2 : MS_ROUND_
     }
     __syncthreads();
     PHASE_MARK(1);
+    // this CTA's NEXT ticket: pull its window from HBM into L2 now, behind this ticket's remaining phases
+    // (windows are frozen by k_snapshot, so head / limit are final; a window is contiguous up to the ring's wrap)
+    if (tid == 0 && next_li < my_count) {
+      const uint32_t t2 = next_li < my_big ? my_list[next_li] : my_list[p.t_max - 1u - (next_li - my_big)];
+      if (t2 >= p.n_inj_tickets) {
+        const uint32_t e2 = t2 - p.n_inj_tickets;
+        const uint32_t h2 = p.head[e2], n2 = p.limit[e2] - h2, cap2 = ring_cap_of(p, e2);
+        if (n2 > 0 && n2 <= cap2) {
+          const uint4* base2 = p.ring + ring_base(p, e2) * 3;
+          const uint32_t o2 = h2 & (cap2 - 1u), first = min(n2, cap2 - o2);
+          prefetch_l2_bulk(base2 + (size_t)o2 * 3, first * 48u);
+          if (n2 > first) prefetch_l2_bulk(base2, (n2 - first) * 48u);
+        }
+      }
+    }
 
     // PB: order the due set by (round, ticket, idx) == message id order (all due
     //     deadlines equal `now`; the reference's PriorityBlockingQueue leaves ties
@@ -1503,12 +1540,26 @@ __global__ void __launch_bounds__(CLS == 3 ? 512 : 256, CLS == 3 ? 2 : MS_ROUND_
       const int c = ((int)n + nt - 1) / nt;
       const int lo = min(tid * c, (int)n), hi = min(lo + c, (int)n);
       uint32_t nf = 0;
-      for (int i = lo; i < hi; i++)
-        if (i == 0 || keyA[i] != keyA[i - 1] || keyB[i] <= keyB[i - 1]) nf++;
+      uint32_t fmask = 0;                       // block starts of this thread's segment (when it has <= 32 slots)
+      const bool use_mask = c <= 32;
+      if (lo < hi) {
+        uint64_t pa = lo ? keyA[lo - 1] : 0ull;
+        uint32_t pb = lo ? keyB[lo - 1] : 0u;
+        for (int i = lo; i < hi; i++) {
+          const uint64_t ka = keyA[i];
+          const uint32_t kb = keyB[i];
+          if (i == 0 || ka != pa || kb <= pb) { nf++; fmask |= 1u << ((i - lo) & 31); }
+          pa = ka; pb = kb;
+        }
+      }
       uint32_t off = block_excl_scan_u32(nf, &R, s_wcnt);
       if (R <= MAXB) {
-        for (int i = lo; i < hi; i++)
-          if (i == 0 || keyA[i] != keyA[i - 1] || keyB[i] <= keyB[i - 1]) s_bstart[off++] = (uint16_t)i;
+        if (use_mask) {
+          while (fmask) { s_bstart[off++] = (uint16_t)(lo + __ffs(fmask) - 1); fmask &= fmask - 1u; }
+        } else {
+          for (int i = lo; i < hi; i++)
+            if (i == 0 || keyA[i] != keyA[i - 1] || keyB[i] <= keyB[i - 1]) s_bstart[off++] = (uint16_t)i;
+        }
         if (tid == 0) s_bstart[R] = (uint16_t)n;
         __syncthreads();
         // rank blocks by their first key
@@ -1594,14 +1645,21 @@ __global__ void __launch_bounds__(CLS == 3 ? 512 : 256, CLS == 3 ? 2 : MS_ROUND_
     int npad = 1;
     while (npad < (int)n) npad <<= 1;
     const int tsz = 2 * npad;
+    const uint32_t hshift = (uint32_t)__clz(tsz) + 1u;          // 32 - log2(tsz); tsz >= 2
+#define TAB_SLOT(v) (((v) * 0x9E3779B1u) >> hshift)
     if (bcast && n > 0) {
-      for (int i = tid; i < tsz; i += nt) tab[i] = 0xFFFF;
+      if (tsz >= 4) {                                            // tab is 8-byte aligned (16 * cap + 8 bytes into the buffer)
+        uint64_t* t8 = reinterpret_cast<uint64_t*>(tab);
+        for (int i = tid; i < (tsz >> 2); i += nt) t8[i] = 0xFFFFFFFFFFFFFFFFull;
+      } else {
+        for (int i = tid; i < tsz; i += nt) tab[i] = 0xFFFF;
+      }
       __syncthreads();
       for (int pos = tid; pos < (int)n; pos += nt) {
         const uint32_t val = vals[ord[pos]];
         if (val & V_FRESH) {
           const uint32_t v = val & V_MASK;
-          uint32_t h = hash32(v) & (tsz - 1);
+          uint32_t h = TAB_SLOT(v);
           for (int probe = 0; probe < tsz; probe++) {   // the table is at most half full
             uint32_t cur = *reinterpret_cast<volatile uint16_t*>(&tab[h]);
             if (cur == 0xFFFFu) {
@@ -1732,7 +1790,7 @@ __global__ void __launch_bounds__(CLS == 3 ? 512 : 256, CLS == 3 ? 2 : MS_ROUND_
       bool is_new = false;
       if (val & V_FRESH) {
         const uint32_t v = val & V_MASK;
-        uint32_t h = hash32(v) & (tsz - 1);
+        uint32_t h = TAB_SLOT(v);
         uint32_t win = tab[h];
         for (int probe = 0; probe < tsz && win != 0xFFFFu && (vals[ord[win]] & V_MASK) != v; probe++) {
           h = (h + 1) & (tsz - 1);   // the entry exists: probing ends on it
@@ -1980,6 +2038,7 @@ __global__ void __launch_bounds__(CLS == 3 ? 512 : 256, CLS == 3 ? 2 : MS_ROUND_
       r.dest = 0; r.src = e;
       uint32_t direct = 0;
       bool has_direct = false;
+      bool fast = false;
       bool timer_emission = false;
       if constexpr (GS) {
         if (valid && j < n_timer) {
@@ -2037,6 +2096,7 @@ __global__ void __launch_bounds__(CLS == 3 ? 512 : 256, CLS == 3 ? 2 : MS_ROUND_
             direct = s_nbbase[js] + new_before - (f & 0xFFFFu);
             has_direct = true;
           }
+          fast = has_direct && !np.any_removed;
         } else {
           const uint4* rp = myring + (size_t)((head + i) & my_mask) * 3;
           const uint4 vb = rp[1], vc = rp[2];
@@ -2070,7 +2130,17 @@ __global__ void __launch_bounds__(CLS == 3 ? 512 : 256, CLS == 3 ? 2 : MS_ROUND_
           }
         }
       }
-      emit_one(p, st, np, cx, valid, r, j, direct, has_direct);
+      if (fast) {
+        // server -> neighbor gossip into ring space this CTA already claimed: what emit_one does for it, without
+        // the general case's lookups (both ends are live servers, zero constant latency, no loss: agg_ok)
+        r.round = round; r.ticket = ticket; r.idx = j;                         // order key == id order (net.clj:197)
+        journal_raw(p, cx.chunk + n_recv + j, j, false, r);                    // net.clj:208
+        cx.c_send_sv++;
+        cx.c_zero++;
+        uint4* ring_o = p.ring_sh[owner_of(r.dest, p.n_servers, p.n_shards)];
+        rec_store(ring_o + ((size_t)r.dest * p.ring_cap_s + (direct & (p.ring_cap_s - 1u))) * 3, r);
+      }
+      if (__any_sync(FULL, valid && !fast)) emit_one(p, st, np, cx, valid && !fast, r, j, direct, has_direct);
     }
     if (tid == 0 && is_server) {
       if (p.workload == MS_W_ECHO && p.next_msg_id && n_emit) p.next_msg_id[e] = msg_id_base + n_emit;
@@ -2139,6 +2209,7 @@ __global__ void __launch_bounds__(CLS == 3 ? 512 : 256, CLS == 3 ? 2 : MS_ROUND_
   }
  }   // persistent loop
 #undef PHASE_MARK
+#undef TAB_SLOT
 }
 
 // ------------------------------------------------------------------ k_journal_expand (K3)
@@ -2354,8 +2425,13 @@ __global__ void k_stream_apply(Params p, const StreamPlan* plan, uint32_t parity
 extern "C" {
 
 typedef void (*msk_round_fn)(msd::Params, uint32_t);
-// round kernel of (node-program families: bit 0 g-set, bit 1 services; window-size class)
-static msk_round_fn msk_round_kernel(uint32_t family, int cls) {
+// round kernel of (node-program families: bit 0 g-set, bit 1 services; window-size class); fixed = the class has
+// its default shape (ClsShape) and the family has a shape-specialised instantiation (echo / broadcast: family 0)
+static msk_round_fn msk_round_kernel(uint32_t family, int cls, bool fixed = false) {
+  if (fixed && (family & 7u) == 0 && cls < 3) {
+    static const msk_round_fn fx[3] = {msd::k_round<0, 0, true>, msd::k_round<1, 0, true>, msd::k_round<2, 0, true>};
+    return fx[cls];
+  }
   static const msk_round_fn tab[8][4] = {
       {msd::k_round<0, 0>, msd::k_round<1, 0>, msd::k_round<2, 0>, msd::k_round<3, 0>},
       {msd::k_round<0, 1>, msd::k_round<1, 1>, msd::k_round<2, 1>, msd::k_round<3, 1>},
@@ -2374,6 +2450,8 @@ cudaError_t msk_round_smem_attr(size_t bytes) {
     for (int c = 0; c < 4 && e == cudaSuccess; c++)
       if (msk_round_kernel(f, c))
         e = cudaFuncSetAttribute(msk_round_kernel(f, c), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  for (int c = 0; c < 3 && e == cudaSuccess; c++)
+    e = cudaFuncSetAttribute(msk_round_kernel(0, c, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   return e;
 }
 
@@ -2416,7 +2494,10 @@ void msk_launch_round(const msd::Params* p, int n_classes, const uint32_t* caps,
       const size_t sm = msk_round_smem_bytes(caps[c]);
       cudaStream_t sc = (fork && c != n_classes - 1) ? aux[c] : s;
       if (sc != s) cudaStreamWaitEvent(sc, aux_ev[0], 0);
-      const msk_round_fn kern = msk_round_kernel(p->family, c < 3 ? c : 3);
+      const int kc = c < 3 ? c : 3;
+      const bool fixed = kc < 3 && caps[c] == (kc == 0 ? 128u : kc == 1 ? 512u : 2048u) &&
+                         threads[c] == (kc == 0 ? 64 : kc == 1 ? 128 : 256);
+      const msk_round_fn kern = msk_round_kernel(p->family, kc, fixed);
       MS_LAUNCH(kern, grids[c], threads[c], sm, sc, *p, caps[c]);
       if (sc != s) cudaEventRecord(aux_ev[1 + c], sc);
     }

@@ -82,6 +82,7 @@ static inline unsigned __ballot_sync(unsigned m, int p) {
 }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
+static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 static inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long)x) : 64; }
 static inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) {
   return (unsigned long long)(((unsigned __int128)a * b) >> 64);

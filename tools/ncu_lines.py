@@ -24,3 +24,22 @@ print("total warp inst %d, samples %d" % (tot_i, tot_s))
 rows = sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]
 for (f, l), a in rows:
     print("%5.2f%% inst %5.2f%% smp  thr/inst %4.1f  %s:%d  %s" % (100.0 * a[0] / tot_i, 100.0 * a[2] / max(tot_s, 1), a[1] / max(a[0], 1), f, l, a[3].strip()[:110]))
+
+# phase buckets of ms_kernels.cu (line ranges of the current tree; adjust when the file moves)
+if len(sys.argv) > 3 and sys.argv[3] == "phases":
+    B = [(35, 146, "helpers (st_v4, rec, ring_slot, dense_base)"), (147, 207, "block scan / bitonic"), (208, 234, "journal_raw"),
+         (235, 291, "wheel"), (292, 362, "emit_one"), (626, 746, "node programs"), (747, 878, "commit"), (1040, 1130, "small scans"),
+         (1220, 1318, "prologue + ticket fetch"), (1319, 1362, "injector"), (1363, 1390, "endpoint setup"), (1391, 1473, "PA1 load"),
+         (1474, 1493, "PA2 seen test"), (1494, 1592, "PB ordering"), (1593, 1625, "PC first-sight insert"), (1626, 1726, "seq families"),
+         (1727, 1774, "winners + counts"), (1775, 1850, "scan + gset"), (1851, 1925, "PD claims"), (1926, 1964, "PE1 recv records"),
+         (1965, 1975, "own_map"), (1976, 2094, "PE2 emissions"), (2095, 2143, "epilogue")]
+    ph = collections.defaultdict(lambda: [0, 0])
+    for (f, l), a in agg.items():
+        name = "other:" + f
+        if f == "ms_kernels.cu":
+            for lo, hi, nm in B:
+                if lo <= l <= hi: name = nm; break
+        ph[name][0] += a[0]; ph[name][1] += a[2]
+    print("==== phases")
+    for nm, a in sorted(ph.items(), key=lambda kv: -kv[1][0]):
+        print("%5.1f%% inst %5.1f%% smp  %s" % (100.0 * a[0] / tot_i, 100.0 * a[1] / max(tot_s, 1), nm))
