@@ -667,6 +667,8 @@ def gpu_arm(args, rank, world, local_rank):
             run_to(sim, step * step_ns)
 
     do_steps(R + W)
+    if args.phase_cycles and world == 1:
+        sim.phase_cycles(True)          # diagnostic: clock64() between the phases of every ticket (slows the kernels)
     before = lstats()
     c_before = sim.counters()
     sampler = ClockSampler(local_rank)
@@ -682,6 +684,18 @@ def gpu_arm(args, rank, world, local_rank):
     after = lstats()
     c_after = sim.counters()
     clocks = sampler.stop()
+    if args.phase_cycles and world == 1:
+        pc = sim.phase_cycles(False)
+        names = ["fetch", "load+seen (PA)", "order (PB)", "first-sight+counts (PC)", "scan", "claims (PD)", "records+emissions (PE)",
+                 "epilogue", "commit"]
+        for c in range(4):
+            nt = int(pc[c][15])
+            if not nt:
+                continue
+            tot = sum(int(pc[c][k]) for k in range(9))
+            sys.stderr.write("class %d: %d tickets, %.0f cycles per ticket (thread 0's clock64 between phases)\n" % (c, nt, tot / nt))
+            for k in range(9):
+                sys.stderr.write("   %-26s %8.0f cycles/ticket  %5.1f %%\n" % (names[k], int(pc[c][k]) / nt, 100.0 * int(pc[c][k]) / max(tot, 1)))
     recvs = after["recv-count"] - before["recv-count"]
     sends = after["send-count"] - before["send-count"]
     launches = c_after["launches"] - c_before["launches"]
@@ -838,6 +852,7 @@ def main():
     ap.add_argument("--verify", action="store_true", help="sharded parity digest (on by default when --gpus > 1)")
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--phase-cycles", action="store_true", help="diagnostic: per-phase cycles per ticket on stderr; not a bench run")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

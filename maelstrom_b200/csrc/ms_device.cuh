@@ -27,6 +27,17 @@ enum : uint32_t {
 
 // Mutable per-simulation scalars, resident in HBM, committed by the last CTA of
 // every round (net.clj:92-103's atom, minus the queues).
+// default CTA widths of the four window-size classes of k_round (windows <= 128 / 512 / 2048 / max_window);
+// ms_engine.cu sizes the launches with them, ms_kernels.cu's shape-specialised instantiations assume them
+#ifndef MS_CLS0_NT
+#define MS_CLS0_NT 64
+#endif
+#ifndef MS_CLS1_NT
+#define MS_CLS1_NT 128
+#endif
+constexpr int kClsThreads[4] = {MS_CLS0_NT, MS_CLS1_NT, 256, 512};
+constexpr uint32_t kClsLadder[4] = {128u, 512u, 2048u, 32768u};
+
 struct DevState {
   int64_t  now;              // virtual time, ns
   int64_t  stop_ns;          // rounds are no-ops once now >= stop_ns

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -141,6 +142,10 @@ struct ms_sim {
   int n_sms = 148;
   bool use_calendar = false;
   uint64_t launches = 0;
+  // ms_run sizes its batches of rounds from what the previous call needed (rounds until `until` was reached):
+  // a fixed batch wastes launches on rounds past the stop time and a blocking read-back per batch
+  uint64_t run_hint = 0;
+  bool mail_seen = false;          // host-visible deliveries happened: keep the batches short (mail_cap)
 
   std::vector<uint8_t> kinds;
   std::vector<std::string> names;
@@ -238,6 +243,7 @@ struct ms_sim {
     CK(cudaStreamSynchronize(stream));
     if (prof_used) collect_profile();
     if (hs.mail_count) {
+      mail_seen = true;
       const uint32_t n = std::min(hs.mail_count, P.mail_cap);
       std::vector<ms_msg> buf(n);
       CK(cudaMemcpy(buf.data(), P.mail, (size_t)n * sizeof(ms_msg), cudaMemcpyDeviceToHost));
@@ -573,10 +579,10 @@ static int build_sim(ms_sim* s, const ms_config* in) {
     return MS_ERR_ARG;
   }
   {
-    const uint32_t ladder[4] = {128, 512, 2048, 32768};
+    const uint32_t* ladder = kClsLadder;
     // g-set: a node's step ORs whole bitmap rows (one word per thread and pass): wide CTAs even for short windows
-    const int thr_default[4] = {64, 128, 256, 512}, thr_gset[4] = {256, 256, 256, 512};
-    const int* thr = c.workload == MS_W_GSET ? thr_gset : thr_default;
+    const int thr_gset[4] = {256, 256, 256, 512};
+    const int* thr = c.workload == MS_W_GSET ? thr_gset : kClsThreads;
     s->n_classes = 0;
     for (int k = 0; k < 4; k++) {
       const uint32_t cap = std::min(ladder[k], c.max_window);
@@ -1175,11 +1181,29 @@ int ms_run(ms_sim* s, int64_t until) {
   std::lock_guard<std::mutex> g(s->mu);
   int64_t stall_now = s->hs.now;
   uint64_t stall_round = s->hs.rounds_run;
+  // batch sizing: nothing to hand to the host between rounds (no mailbox traffic, journal discarded or streamed
+  // elsewhere) -> start from the previous call's round count, then grow while whole batches are productive
+  const bool adaptive = !s->mail_seen && s->pending.empty() && (s->cfg.journal_discard || s->cfg.journal_level == 0) &&
+                        s->P.n_shards <= 1;
+  const uint64_t entry_rounds = s->hs.rounds_run;
+  uint64_t batch = 32;
+  if (adaptive) batch = s->run_hint > 36 ? std::min<uint64_t>(s->run_hint - 2, 1024) : 32;
   while (s->hs.now < until) {
     if (journal_blocked(s)) return 1;   // drain (ms_journal_drain) and call again
     const uint64_t r0 = s->hs.rounds_run;
-    const int rc = step_locked(s, 32, until);
+    static const bool dbg_stall = getenv("MS_DEBUG_STALL") != nullptr;   // diagnostic: one round per batch, state on stderr
+    if (dbg_stall) batch = 1;
+    const int rc = step_locked(s, batch, until);
     if (rc) return rc;
+    if (dbg_stall && (s->hs.rounds_run == r0 || s->hs.round < 4))
+      fprintf(stderr, "MS_DEBUG_STALL advanced=%d%s cursors %u %u %u %u\n", (int)(s->hs.rounds_run - r0), stall_report(s).c_str(),
+              s->hs.cls_cursor[s->hs.round & 1][0], s->hs.cls_cursor[s->hs.round & 1][1], s->hs.cls_cursor[s->hs.round & 1][2],
+              s->hs.cls_cursor[s->hs.round & 1][3]);
+    if (adaptive) {
+      const bool full = s->hs.rounds_run - r0 == batch;
+      batch = s->mail_seen ? 32 : (full ? std::min<uint64_t>(std::max<uint64_t>(2 * batch, 4), 256) : 4);
+      if (full && s->run_hint > 36 && s->hs.rounds_run - entry_rounds <= s->run_hint) batch = 4;   // the call's last rounds
+    }
     if (s->hs.now != stall_now) { stall_now = s->hs.now; stall_round = s->hs.rounds_run; }
     else if (time_stalled(s, stall_now, stall_round)) return MS_ERR_SIM;
     if (s->hs.rounds_run == r0 && s->hs.now < until && !journal_blocked(s)) {
@@ -1187,6 +1211,7 @@ int ms_run(ms_sim* s, int64_t until) {
       return MS_ERR_SIM;
     }
   }
+  if (adaptive) s->run_hint = s->hs.rounds_run - entry_rounds;
   return MS_OK;
 }
 

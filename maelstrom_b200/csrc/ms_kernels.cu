@@ -102,6 +102,11 @@ __device__ __forceinline__ bool round_skipped(const Params& p, const DevState* s
   return false;
 }
 
+// DevState.slot_open: 0 = no round open (committed / not snapshotted yet), else the tag of the open round.
+// k_round's CTAs may start at any time while their launch is alive -- also while, or after, another CTA commits
+// the round -- so "is my round still open" must be ONE consistent decision per CTA: the tag names the round.
+__device__ __forceinline__ uint32_t slot_tag(uint64_t round) { return 0x80000000u | (uint32_t)(round & 0x7FFFFFFFull); }
+
 // ------------------------------------------------------------------ ring records
 // 48-B inbox record: v0 = order key {idx, ticket, round}, v1 = {src, dest,
 // msg_id, in_reply_to}, v2 = {type | flags << 16, p0, p1}.
@@ -525,8 +530,14 @@ __global__ void k_snapshot(Params p) {
     const uint32_t c = class_of(p, n);
     const uint32_t lo_cap = c ? p.cls_cap[c - 1] : 0u;
     uint32_t* list = p.cls_list + ((size_t)par * 4 + c) * p.t_max;
-    if (n > lo_cap + ((min(p.cls_cap[c], p.max_window) - lo_cap) >> 1)) list[atomicAdd(&st->cls_count[par][c], 1u)] = p.n_inj_tickets + e;
-    else list[p.t_max - 1u - atomicAdd(&st->cls_small[par][c], 1u)] = p.n_inj_tickets + e;
+    // (k < t_max always holds for a round that is snapshotted once; the bound keeps a stuck round from writing wild)
+    if (n > lo_cap + ((min(p.cls_cap[c], p.max_window) - lo_cap) >> 1)) {
+      const uint32_t k = atomicAdd(&st->cls_count[par][c], 1u);
+      if (k < p.t_max) list[k] = p.n_inj_tickets + e;
+    } else {
+      const uint32_t k = atomicAdd(&st->cls_small[par][c], 1u);
+      if (k < p.t_max) list[p.t_max - 1u - k] = p.n_inj_tickets + e;
+    }
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) n_empty += __shfl_xor_sync(FULL, n_empty, d);
@@ -536,7 +547,7 @@ __global__ void k_snapshot(Params p) {
   if (gid < p.n_inj_tickets && p.shard_id == 0) {   // injector slices run in the widest class (shard 0)
     const uint32_t c = p.n_classes - 1;
     const uint32_t k = atomicAdd(&st->cls_count[par][c], 1u);
-    p.cls_list[((size_t)par * 4 + c) * p.t_max + k] = gid;
+    if (k < p.t_max) p.cls_list[((size_t)par * 4 + c) * p.t_max + k] = gid;
   }
   if (blockIdx.x == 0) {
     // timing wheel housekeeping, one CTA (nothing pops blocks while this kernel runs): the chain
@@ -563,7 +574,7 @@ __global__ void k_snapshot(Params p) {
   }
   if (gid == 0) {
     for (int c = 0; c < 4; c++) { st->cls_count[par ^ 1u][c] = 0; st->cls_small[par ^ 1u][c] = 0; st->cls_cursor[par ^ 1u][c] = 0; }
-    st->slot_open = 1;
+    st->slot_open = slot_tag(st->round);
   }
 }
 
@@ -1227,8 +1238,8 @@ __device__ void service_handle(const Params& p, uint32_t svc, const SvReq& q, ui
 // assume it, which turns every shared-memory array base and every loop stride into an immediate; a simulation
 // sized differently (max_window below the ladder, threads_per_node) runs the generic ones.
 template <int CLS> struct ClsShape {
-  static constexpr uint32_t cap = CLS == 0 ? 128u : CLS == 1 ? 512u : 2048u;
-  static constexpr int nt = CLS == 0 ? 64 : CLS == 1 ? 128 : CLS == 2 ? 256 : 512;
+  static constexpr uint32_t cap = kClsLadder[CLS < 3 ? CLS : 2];
+  static constexpr int nt = kClsThreads[CLS];
 };
 
 template <int CLS, int WL, bool FIX = false>
@@ -1240,7 +1251,6 @@ __global__ void __launch_bounds__(CLS == 3 ? 512 : 256, CLS == 3 ? 2 : MS_ROUND_
   constexpr bool SV = (WL & 2) != 0;
   constexpr bool RF = (WL & 4) != 0;
   DevState* st = p.st;
-  if (round_skipped(p, st) || !st->slot_open) return;
 
 #ifdef MS_EMUL
   unsigned char* smem_raw = simt::dyn_smem();
@@ -1273,13 +1283,30 @@ __global__ void __launch_bounds__(CLS == 3 ? 512 : 256, CLS == 3 ? 2 : MS_ROUND_
   __shared__ uint32_t s_nbbase[MAXNB];        // ring position claimed for this CTA's gossip to neighbor j
   __shared__ uint32_t s_nbr[MAXNB];           // this node's neighbor list (topology order)
   __shared__ uint4 s_gen[2];                  // the request a closed-loop client sends in this step
+  __shared__ uint64_t s_round0;               // the round this CTA works on (0: none, see below)
+  __shared__ int64_t s_now0;
+  __shared__ uint32_t s_go;
 
   const int tid = threadIdx.x, nt = FIX ? ClsShape<CLS>::nt : (int)blockDim.x, lane = tid & 31;
-  if (tid == 0) s_np = *p.np;
+  if (tid == 0) {
+    s_np = *p.np;
+    // Is this launch's round still open?  Decided once per CTA, by one thread: a CTA of a persistent grid may
+    // start late (its class queues behind the others for SM resources), even while the last ticket of the round
+    // is committing it.  The commit stores round + 1 and then clears slot_open; reading slot_open first and
+    // the round second, a CTA either sees the open round's tag with its own round, or leaves: it can never take
+    // a ticket cursor of the NEXT round's parity, and its threads never disagree about leaving.
+    const uint32_t so = ld_volatile_u32(&st->slot_open);
+    __threadfence();
+    const uint64_t r = *reinterpret_cast<const volatile uint64_t*>(&st->round);
+    s_round0 = r;
+    s_now0 = *reinterpret_cast<const volatile int64_t*>(&st->now);
+    s_go = (so == slot_tag(r) && !round_skipped(p, st)) ? 1u : 0u;
+  }
   __syncthreads();
+  if (!s_go) return;
   const NetParams np = s_np;
-  const int64_t now = st->now;
-  const uint64_t round = st->round;
+  const int64_t now = s_now0;
+  const uint64_t round = s_round0;
   const uint32_t T = p.n_inj_tickets + p.n_ep;
   const uint32_t row = (uint32_t)round & p.hist_mask;
   const uint32_t par = (uint32_t)round & 1u;
@@ -2495,8 +2522,7 @@ void msk_launch_round(const msd::Params* p, int n_classes, const uint32_t* caps,
       cudaStream_t sc = (fork && c != n_classes - 1) ? aux[c] : s;
       if (sc != s) cudaStreamWaitEvent(sc, aux_ev[0], 0);
       const int kc = c < 3 ? c : 3;
-      const bool fixed = kc < 3 && caps[c] == (kc == 0 ? 128u : kc == 1 ? 512u : 2048u) &&
-                         threads[c] == (kc == 0 ? 64 : kc == 1 ? 128 : 256);
+      const bool fixed = kc < 3 && caps[c] == msd::kClsLadder[kc] && threads[c] == msd::kClsThreads[kc];
       const msk_round_fn kern = msk_round_kernel(p->family, kc, fixed);
       MS_LAUNCH(kern, grids[c], threads[c], sm, sc, *p, caps[c]);
       if (sc != s) cudaEventRecord(aux_ev[1 + c], sc);
