@@ -723,7 +723,10 @@ def gpu_arm(args, rank, world, local_rank):
         total_b = R + W + K + 1
         sim, c0 = make_sim(mb, wl, total_b, False, local_rank, world)
         lstats = (lambda: sim.sim.stats()["all"]) if world > 1 else (lambda: sim.stats()["all"])
-        fmt = _lib.JFMT_8 if wl.n_nodes + wl.n_clients + 8 <= 65536 else _lib.JFMT_12
+        n_ep = wl.n_nodes + wl.n_clients + 8
+        fmt = _lib.JFMT_4 if n_ep <= 32768 else _lib.JFMT_8 if n_ep <= 65536 else _lib.JFMT_12
+        if args.stream_format:
+            fmt = args.stream_format
         pro = wl.prologue_ops(OP_DTYPE, c0, TYPES, flags)
         host_ops = [wl.ops(OP_DTYPE, t, 1, c0, TYPES, flags) for t in range(total_b)]
         if pro is not None:                     # the inits belong to step 0
@@ -817,7 +820,7 @@ def gpu_arm(args, rank, world, local_rank):
                        "d2h_bytes_per_step": e2e["d2h"],
                        "note": ("host op buffers in every step (ms_schedule_ops); the whole journal of the step streamed into "
                                 "pinned host memory (ms_run_streamed, %d bytes per event, packed on the device, copied out by "
-                                "the DMA engine behind the running rounds); lazily expandable with ms_journal_decode"
+                                "the DMA engine behind the running rounds); lazily expandable with ms_journal_decode / ms_jdecoder"
                                 % (e2e["fmt"] if world == 1 else 16)) +
                                ("" if world == 1 else "; every rank uploads the ops and streams its own shard's events (event id + "
                                 "packed word each) over its own PCIe link: bytes are summed over the ranks")}
@@ -848,6 +851,7 @@ def main():
     ap.add_argument("--journal-cap-log2", type=int, default=28)
     ap.add_argument("--stream-events", type=int, default=1 << 26, help="events per host buffer of ms_run_streamed")
     ap.add_argument("--raft-log-cap", type=int, default=1024)
+    ap.add_argument("--stream-format", type=int, default=0, choices=[0, 4, 8, 12, 32], help="e2e: bytes per journal event (0 = smallest that fits)")
     ap.add_argument("--touch", action="store_true", help="e2e: fold every streamed byte on the host inside the timed region")
     ap.add_argument("--verify", action="store_true", help="sharded parity digest (on by default when --gpus > 1)")
     ap.add_argument("--no-verify", action="store_true")

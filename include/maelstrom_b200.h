@@ -294,9 +294,15 @@ uint64_t ms_journal_written(ms_sim* sim);
  *   MS_JFMT_8      64 bits: recv << 63 | src << 47 | dest << 31 | (id - id_ref of the round); needs
  *                  endpoint indices < 65536 and every message received within 2^30 ids of the newest
  *                  one: otherwise the batch header has overflow = 1 and the call fails with MS_ERR_CAPACITY
+ *   MS_JFMT_4      32 bits: a :send is 0 << 31 | src << 16 | dest -- sends appear in the journal in id order (the two
+ *                  counters of net.clj:197 and journal.clj:228 run in step), so the j-th send of a round has id
+ *                  id_ref + j (id_ref of an MS_JFMT_4 row = the round's first id); a :recv is 1 << 31 | (id_ref - 1 - id)
+ *                  -- its src and dest are those of the :send with that id, earlier in the stream.  Needs
+ *                  src < 32768, dest < 65536 and receives within 2^31 ids (else overflow, as above); one GPU
+ *                  (sharded runs hand over MS_JFMT_16).  Expanding it takes the stream's history: ms_jdecoder.
  * ms_journal_decode expands a batch into ms_event records (lazily, on the host); a sharded batch comes
  * out in the order it was packed (sort by event_id, or scatter by event_id - first_event, to merge shards). */
-enum { MS_JFMT_EVENT = 32, MS_JFMT_12 = 12, MS_JFMT_8 = 8,
+enum { MS_JFMT_EVENT = 32, MS_JFMT_12 = 12, MS_JFMT_8 = 8, MS_JFMT_4 = 4,
        MS_JFMT_16 = 16 };  /* what a sharded run hands over for MS_JFMT_8 / MS_JFMT_12: {event id | recv << 63, the MS_JFMT_8 word} */
 typedef struct ms_jround {   /* one row per round that has events in the batch */
   uint64_t round;
@@ -320,6 +326,17 @@ typedef int (*ms_journal_sink)(void* ctx, const ms_jbatch* batch, const ms_jroun
 int ms_run_streamed(ms_sim* sim, int64_t until_virtual_ns, int format, size_t buf_events,
                     ms_journal_sink sink, void* ctx);
 int ms_journal_decode(const ms_jbatch* batch, const ms_jround* rounds, const void* events, ms_event* out);
+/* Stateful expansion for MS_JFMT_4 (any other format goes through as with ms_journal_decode): the decoder
+ * remembers src / dest of the last 2^log2_window sends (16 B each).  Feed it the batches in stream order;
+ * events obtained another way in between (ms_journal_drain) are told to it with ms_jdecoder_note.  A :recv
+ * whose :send it has not seen, or a batch that starts inside a round it has not followed, is MS_ERR_ARG
+ * (ms_jdecoder_error has the text). */
+typedef struct ms_jdecoder ms_jdecoder;
+ms_jdecoder* ms_jdecoder_create(uint32_t log2_window);
+void ms_jdecoder_destroy(ms_jdecoder* dec);
+int ms_jdecoder_decode(ms_jdecoder* dec, const ms_jbatch* batch, const ms_jround* rounds, const void* events, ms_event* out);
+int ms_jdecoder_note(ms_jdecoder* dec, const ms_event* events, size_t n);
+const char* ms_jdecoder_error(const ms_jdecoder* dec);
 
 /* net.checker/basic-stats (net/checker.clj:28-41) folded on the device:
  * out[9] = {all, clients, servers} x {send-count, recv-count, msg-count}. */

@@ -44,6 +44,11 @@ public final class Native {
   public static native long journalWritten(long h);
   public static native int runStreamed(long h, long untilNs, int format, long bufEvents, JournalSink sink);
   public static native int journalDecode(ByteBuffer batch, ByteBuffer rounds, ByteBuffer events, ByteBuffer outEvents);
+  public static native long jdecoderCreate(int log2Window);
+  public static native void jdecoderDestroy(long decoder);
+  public static native int jdecoderDecode(long decoder, ByteBuffer batch, ByteBuffer rounds, ByteBuffer events, ByteBuffer outEvents);
+  public static native int jdecoderNote(long decoder, ByteBuffer events, long n);
+  public static native String jdecoderError(long decoder);
   public static native int stats(long h, ByteBuffer out9);
   public static native long nodeSet(long h, int node, ByteBuffer values, long cap);
   public static native long clientReplies(long h);

@@ -63,7 +63,7 @@ class JBatch(C.Structure):      # ms_jbatch
 
 JROUND_DTYPE = np.dtype([("round", "<u8"), ("time_ns", "<i8"), ("ev_base", "<u8"), ("id_ref", "<u8")])
 JOURNAL_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(JBatch), C.c_void_p, C.c_void_p)
-JFMT_EVENT, JFMT_12, JFMT_8, JFMT_16 = 32, 12, 8, 16
+JFMT_EVENT, JFMT_12, JFMT_8, JFMT_16, JFMT_4 = 32, 12, 8, 16, 4
 
 # every symbol include/maelstrom_b200.h declares: (restype, argtypes)
 _P = C.c_void_p
@@ -101,6 +101,11 @@ SYMBOLS = {
     "ms_journal_written": (C.c_uint64, [_P]),
     "ms_run_streamed": (C.c_int, [_P, C.c_int64, C.c_int, C.c_size_t, JOURNAL_SINK, _P]),
     "ms_journal_decode": (C.c_int, [C.POINTER(JBatch), _P, _P, _P]),
+    "ms_jdecoder_create": (_P, [C.c_uint32]),
+    "ms_jdecoder_destroy": (None, [_P]),
+    "ms_jdecoder_decode": (C.c_int, [_P, C.POINTER(JBatch), _P, _P, _P]),
+    "ms_jdecoder_note": (C.c_int, [_P, _P, C.c_size_t]),
+    "ms_jdecoder_error": (C.c_char_p, [_P]),
     "ms_stats": (C.c_int, [_P, _P]),
     "ms_node_set": (C.c_size_t, [_P, C.c_uint32, _P, C.c_size_t]),
     "ms_client_replies": (C.c_uint64, [_P]),

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <deque>
 #include <mutex>
+#include <new>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -1510,7 +1511,7 @@ static size_t stream_hdr_bytes() { return 256 + (size_t)ms_sim::kStreamRows * si
 int ms_run_streamed(ms_sim* s, int64_t until, int format, size_t buf_events, ms_journal_sink sink, void* ctx) {
   std::lock_guard<std::mutex> g(s->mu);
   cudaSetDevice(s->device);
-  if (format != MS_JFMT_EVENT && format != MS_JFMT_12 && format != MS_JFMT_8) { set_err("ms_run_streamed: unknown format"); return MS_ERR_ARG; }
+  if (format != MS_JFMT_EVENT && format != MS_JFMT_12 && format != MS_JFMT_8 && format != MS_JFMT_4) { set_err("ms_run_streamed: unknown format"); return MS_ERR_ARG; }
   if (!sink) { set_err("ms_run_streamed: null sink"); return MS_ERR_ARG; }
   if (s->cfg.journal_level == 0 || s->cfg.journal_discard) { set_err("ms_run_streamed: the journal is off (journal_level 0 or journal_discard)"); return MS_ERR_ARG; }
   if (!buf_events) buf_events = (size_t)1 << 24;
@@ -1596,7 +1597,7 @@ int ms_run_streamed(ms_sim* s, int64_t until, int format, size_t buf_events, ms_
     const uint64_t k = i - 2;
     CK(cudaEventSynchronize(s->j_copied[k & 1]));
     const ms_jbatch* ph = (const ms_jbatch*)s->jhdr[k & 3];
-    if (ph->overflow) { set_err("ms_run_streamed: MS_JFMT_8 / MS_JFMT_12 cannot hold this batch (endpoint index or id range): use a wider format"); result = MS_ERR_CAPACITY; break; }
+    if (ph->overflow) { set_err("ms_run_streamed: MS_JFMT_4 / MS_JFMT_8 / MS_JFMT_12 cannot hold this batch (endpoint index or id range): use a wider format"); result = MS_ERR_CAPACITY; break; }
     if (ph->n_events && sink(ctx, ph, (const ms_jround*)(s->jhdr[k & 3] + 256), s->jhost[k & 1])) {
       set_err("ms_run_streamed: stopped by the sink");
       result = MS_ERR_ARG;
@@ -1682,6 +1683,85 @@ int ms_journal_decode(const ms_jbatch* b, const ms_jround* rounds, const void* e
     e.msg_id = id; e.src = src; e.dest = dest;
     out[k] = e;
   }
+  return MS_OK;
+}
+
+// ------------------------------------------------------------------ ms_jdecoder (MS_JFMT_4 needs the stream's history)
+struct ms_jdecoder {
+  std::vector<uint64_t> tag, sd;     // per remembered send: its id + 1 (0 = empty), src | dest << 32
+  uint64_t mask = 0;
+  uint64_t next_send = 0;            // id of the next :send in stream order
+  uint64_t expect_event = 0;         // event id right after the last event seen
+  bool have = false;
+  std::string err;
+};
+
+ms_jdecoder* ms_jdecoder_create(uint32_t log2_window) {
+  if (log2_window < 4 || log2_window > 34) return nullptr;
+  ms_jdecoder* d = new (std::nothrow) ms_jdecoder();
+  if (!d) return nullptr;
+  try {
+    d->tag.assign((size_t)1 << log2_window, 0ull);
+    d->sd.assign((size_t)1 << log2_window, 0ull);
+  } catch (...) { delete d; return nullptr; }
+  d->mask = ((uint64_t)1 << log2_window) - 1;
+  return d;
+}
+void ms_jdecoder_destroy(ms_jdecoder* d) { delete d; }
+const char* ms_jdecoder_error(const ms_jdecoder* d) { return d ? d->err.c_str() : "no decoder"; }
+
+int ms_jdecoder_note(ms_jdecoder* d, const ms_event* ev, size_t n) {
+  if (!d || (!ev && n)) return MS_ERR_ARG;
+  for (size_t i = 0; i < n; i++) {
+    const uint64_t g = ev[i].event_id & ~MS_EVENT_RECV;
+    if (!(ev[i].event_id & MS_EVENT_RECV)) {
+      d->tag[ev[i].msg_id & d->mask] = ev[i].msg_id + 1;
+      d->sd[ev[i].msg_id & d->mask] = (uint64_t)ev[i].src | ((uint64_t)ev[i].dest << 32);
+      d->next_send = ev[i].msg_id + 1;
+    }
+    d->expect_event = g + 1;
+    d->have = true;
+  }
+  return MS_OK;
+}
+
+int ms_jdecoder_decode(ms_jdecoder* d, const ms_jbatch* b, const ms_jround* rounds, const void* events, ms_event* out) {
+  if (!d || !b || !rounds || !events || !out) return MS_ERR_ARG;
+  if (b->format != MS_JFMT_4) {
+    const int rc = ms_journal_decode(b, rounds, events, out);
+    return rc ? rc : ms_jdecoder_note(d, out, (size_t)b->n_events);
+  }
+  const uint32_t* w = (const uint32_t*)events;
+  size_t r = 0;
+  for (uint64_t k = 0; k < b->n_events; k++) {
+    const uint64_t g = b->first_event + k;
+    while (r + 1 < b->n_rounds && rounds[r + 1].ev_base <= g) r++;
+    if (g == rounds[r].ev_base) {
+      d->next_send = rounds[r].id_ref;                   // a round starts: its sends count up from its first id
+    } else if (k == 0 && (!d->have || d->expect_event != g)) {
+      d->err = "ms_jdecoder: batch starts inside a round the decoder has not followed (event " + std::to_string(g) + ")";
+      return MS_ERR_ARG;
+    }
+    ms_event e;
+    e.time_ns = rounds[r].time_ns;
+    if (w[k] & 0x80000000u) {
+      const uint64_t id = rounds[r].id_ref - 1ull - (uint64_t)(w[k] & 0x7FFFFFFFu);
+      if (d->tag[id & d->mask] != id + 1) {
+        d->err = "ms_jdecoder: the :send of message " + std::to_string(id) + " is not in the decoder's window";
+        return MS_ERR_ARG;
+      }
+      const uint64_t sd = d->sd[id & d->mask];
+      e.event_id = g | MS_EVENT_RECV; e.msg_id = id; e.src = (uint32_t)sd; e.dest = (uint32_t)(sd >> 32);
+    } else {
+      const uint64_t id = d->next_send++;
+      e.event_id = g; e.msg_id = id; e.src = (w[k] >> 16) & 0x7FFFu; e.dest = w[k] & 0xFFFFu;
+      d->tag[id & d->mask] = id + 1;
+      d->sd[id & d->mask] = (uint64_t)e.src | ((uint64_t)e.dest << 32);
+    }
+    out[k] = e;
+  }
+  d->expect_event = b->first_event + b->n_events;
+  d->have = true;
   return MS_OK;
 }
 

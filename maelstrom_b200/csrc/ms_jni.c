@@ -163,6 +163,19 @@ jint FN(journalDecode)(JNIEnv* env, jclass c, jobject batch, jobject rounds, job
   (void)c;
   return ms_journal_decode((const ms_jbatch*)BUF(batch), (const ms_jround*)BUF(rounds), BUF(events), (ms_event*)BUF(out));
 }
+/* MS_JFMT_4 batches are expanded by a decoder object that follows the stream */
+jlong FN(jdecoderCreate)(JNIEnv* env, jclass c, jint log2Window) { (void)env; (void)c; return (jlong)(intptr_t)ms_jdecoder_create((uint32_t)log2Window); }
+void FN(jdecoderDestroy)(JNIEnv* env, jclass c, jlong d) { (void)env; (void)c; ms_jdecoder_destroy((ms_jdecoder*)(intptr_t)d); }
+jint FN(jdecoderDecode)(JNIEnv* env, jclass c, jlong d, jobject batch, jobject rounds, jobject events, jobject out) {
+  (void)c;
+  return ms_jdecoder_decode((ms_jdecoder*)(intptr_t)d, (const ms_jbatch*)BUF(batch), (const ms_jround*)BUF(rounds), BUF(events),
+                            (ms_event*)BUF(out));
+}
+jint FN(jdecoderNote)(JNIEnv* env, jclass c, jlong d, jobject events, jlong n) {
+  (void)c;
+  return ms_jdecoder_note((ms_jdecoder*)(intptr_t)d, (const ms_event*)BUF(events), (size_t)n);
+}
+jstring FN(jdecoderError)(JNIEnv* env, jclass c, jlong d) { (void)c; return (*env)->NewStringUTF(env, ms_jdecoder_error((const ms_jdecoder*)(intptr_t)d)); }
 
 /* read-backs: out = direct buffer of u64 */
 jint FN(stats)(JNIEnv* env, jclass c, jlong h, jobject out9) { (void)c; return ms_stats(H(h), (uint64_t*)BUF(out9)); }

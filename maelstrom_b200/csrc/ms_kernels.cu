@@ -2302,7 +2302,7 @@ struct StreamPlan {
 };
 static_assert(sizeof(StreamPlan) == 128, "StreamPlan is initialised from the host");
 
-__global__ void k_stream_plan(Params p, StreamPlan* plan, uint64_t cap_events, uint32_t cap_rounds, ms_jround* rows) {
+__global__ void k_stream_plan(Params p, StreamPlan* plan, uint64_t cap_events, uint32_t cap_rounds, ms_jround* rows, uint32_t format) {
   if (threadIdx.x || blockIdx.x) return;
   const DevState* st = p.st;
   const uint64_t first = plan->journal_drained;
@@ -2316,7 +2316,9 @@ __global__ void k_stream_plan(Params p, StreamPlan* plan, uint64_t cap_events, u
     if (r1 - r0 >= cap_rounds) { count = m->ev_base - first; break; }   // the rows table is full: cut at the round boundary
     ms_jround row;
     row.round = r1; row.time_ns = m->now; row.ev_base = m->ev_base;
-    row.id_ref = m->id_base > (1ull << 30) ? m->id_base - (1ull << 30) : 0ull;
+    // MS_JFMT_4 (one GPU): the round's first message id -- its sends count up from it, its receives down from it
+    row.id_ref = (format == MS_JFMT_4 && p.n_shards <= 1) ? m->id_base
+                                                          : (m->id_base > (1ull << 30) ? m->id_base - (1ull << 30) : 0ull);
     rows[r1 - r0] = row;
     r1++;
   }
@@ -2390,6 +2392,20 @@ __global__ void k_journal_pack(Params p, StreamPlan* plan, unsigned char* out) {
         const uint64_t w = (recv ? RECV_BIT : 0ull) | ((uint64_t)(raw.z & 0xFFFFu) << 47) |
                            ((uint64_t)(raw.w & 0xFFFFu) << 31) | (d & 0x7FFFFFFFull);
         reinterpret_cast<unsigned long long*>(out)[g - first] = w;
+      } else if (FMT == 4) {
+        // 32 bits per event.  A :send is {0, src (15), dest (16)}: sends appear in the journal in id order (both
+        // counters are handed out in journal order, net.clj:197, journal.clj:228), so its id is implied by its
+        // position.  A :recv is {1, id_base - 1 - id (31)}: src and dest are those of the :send with that id.
+        uint32_t w;
+        if (recv) {
+          const uint64_t d = m->id_base - 1ull - id;
+          if (id >= m->id_base || d >= (1ull << 31)) bad = true;
+          w = 0x80000000u | (uint32_t)(d & 0x7FFFFFFFull);
+        } else {
+          if (raw.z > 0x7FFFu || raw.w > 0xFFFFu) bad = true;
+          w = ((raw.z & 0x7FFFu) << 16) | (raw.w & 0xFFFFu);
+        }
+        reinterpret_cast<uint32_t*>(out)[g - first] = w;
       } else if (FMT == 12) {
         if (id >= (1ull << 47) || raw.z > 0xFFFFFFu || raw.w > 0xFFFFFFu) bad = true;
         uint32_t* o = reinterpret_cast<uint32_t*>(out) + (g - first) * 3;
@@ -2551,9 +2567,10 @@ size_t msk_stream_plan_bytes() { return sizeof(msd::StreamPlan); }
 void msk_stream_batch(const msd::Params* p, void* plan, uint64_t cap_events, uint32_t cap_rounds, ms_jround* rows,
                       void* out, ms_jbatch* hdr, int format, int n_sms, cudaStream_t s, uint32_t parity) {
   msd::StreamPlan* pl = (msd::StreamPlan*)plan;
-  MS_LAUNCH(msd::k_stream_plan, 1, 32, 0, s, *p, pl, cap_events, cap_rounds, rows);
+  MS_LAUNCH(msd::k_stream_plan, 1, 32, 0, s, *p, pl, cap_events, cap_rounds, rows, (uint32_t)format);
   const unsigned blocks = (unsigned)n_sms * 16;
-  if (format == MS_JFMT_8) MS_LAUNCH(msd::k_journal_pack<8>, blocks, 256, 0, s, *p, pl, (unsigned char*)out);
+  if (format == MS_JFMT_4) MS_LAUNCH(msd::k_journal_pack<4>, blocks, 256, 0, s, *p, pl, (unsigned char*)out);
+  else if (format == MS_JFMT_8) MS_LAUNCH(msd::k_journal_pack<8>, blocks, 256, 0, s, *p, pl, (unsigned char*)out);
   else if (format == MS_JFMT_12) MS_LAUNCH(msd::k_journal_pack<12>, blocks, 256, 0, s, *p, pl, (unsigned char*)out);
   else MS_LAUNCH(msd::k_journal_pack<32>, blocks, 256, 0, s, *p, pl, (unsigned char*)out);
   MS_LAUNCH(msd::k_stream_finish, 1, 32, 0, s, *p, pl, hdr, (uint32_t)format, parity);

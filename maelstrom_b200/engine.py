@@ -41,6 +41,39 @@ def body(type, msg_id=None, in_reply_to=None, p0=0, p1=0, create=False, appends=
     return b
 
 
+class JournalDecoder:
+    """ms_jdecoder: expands MS_JFMT_4 batches (32 bits per event) into EVENT_DTYPE records.  It follows the
+    stream: a :recv's src / dest are those of the :send with the same id, seen earlier."""
+
+    def __init__(self, log2_window=22):
+        self.L = _lib.lib()
+        self.h = self.L.ms_jdecoder_create(log2_window)
+        if not self.h:
+            raise MemoryError("ms_jdecoder_create")
+
+    def close(self):
+        if self.h:
+            self.L.ms_jdecoder_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def _chk(self, rc):
+        if rc < 0:
+            raise SimError(rc, self.L.ms_jdecoder_error(self.h).decode())
+
+    def decode_raw(self, batch_p, rounds_p, events_p, n):
+        ev = np.zeros(n, dtype=EVENT_DTYPE)
+        self._chk(self.L.ms_jdecoder_decode(self.h, batch_p, rounds_p, events_p, ev.ctypes.data))
+        return ev
+
+    def note(self, events):
+        """events (EVENT_DTYPE) obtained outside the stream, e.g. from Sim.drain()"""
+        ev = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
+        self._chk(self.L.ms_jdecoder_note(self.h, ev.ctypes.data, len(ev)))
+
+
 class Sim:
     def __init__(self, n_nodes, workload="broadcast", topology="grid", latency_dist="constant",
                  latency_mean_ms=0, seed=0x4D41454C, p_loss=0.0, n_values=1 << 16, **sizing):
@@ -203,6 +236,8 @@ class Sim:
         self._stash = []
         ev = np.concatenate([p[0] for p in parts])
         bd = np.concatenate([p[1] for p in parts]) if bodies else None
+        if getattr(self, "_jdecoder", None) is not None and len(ev):
+            self._jdecoder.note(ev)          # the MS_JFMT_4 stream continues after these events
         return ev, bd
 
     def _drain_now(self, cap=1 << 20, bodies=True):
@@ -222,14 +257,20 @@ class Sim:
         bd = (np.concatenate(bds) if bds else np.zeros(0, dtype=JBODY_DTYPE)) if bodies else None
         return ev, bd
 
-    def run_streamed(self, until_ns, sink=None, fmt=_lib.JFMT_8, buf_events=0, decode=False):
+    def run_streamed(self, until_ns, sink=None, fmt=_lib.JFMT_8, buf_events=0, decode=False, decoder=None):
         """ms_run_streamed: run to until_ns while the journal streams into pinned host memory.
         sink(batch_dict, rounds, events) is called per batch with numpy views that are only valid
-        during the call (rounds: JROUND_DTYPE; events: u64 / 3 x u32 / EVENT_DTYPE by format);
-        decode=True hands over EVENT_DTYPE records expanded by ms_journal_decode instead.
+        during the call (rounds: JROUND_DTYPE; events: u32 / u64 / 3 x u32 / EVENT_DTYPE by format);
+        decode=True hands over EVENT_DTYPE records instead, expanded by ms_journal_decode or, for
+        MS_JFMT_4, by `decoder` (a JournalDecoder that follows the stream; by default one kept with the Sim,
+        which also hears about what drain() returns in between).
         Returns (events, bytes) streamed."""
         tot = [0, 0]
         err = []
+        if decode and fmt == _lib.JFMT_4 and decoder is None:
+            if getattr(self, "_jdecoder", None) is None:
+                self._jdecoder = JournalDecoder()
+            decoder = self._jdecoder
 
         def _cb(ctx, bp, rounds_p, events_p):
             try:
@@ -240,12 +281,15 @@ class Sim:
                 if sink is not None:
                     rounds = np.ctypeslib.as_array(C.cast(rounds_p, C.POINTER(C.c_uint8)),
                                                    (int(b.n_rounds) * 32,)).view(_lib.JROUND_DTYPE)
-                    if decode:
+                    if decode and decoder is not None:
+                        ev = decoder.decode_raw(bp, rounds_p, events_p, n)
+                    elif decode:
                         ev = np.zeros(n, dtype=EVENT_DTYPE)
                         self._chk(self.L.ms_journal_decode(bp, rounds_p, events_p, ev.ctypes.data))
                     else:
                         raw = np.ctypeslib.as_array(C.cast(events_p, C.POINTER(C.c_uint8)), (n * int(b.format),))
-                        ev = (raw.view("<u8") if b.format == 8 else raw.view("<u4").reshape(n, 3) if b.format == 12
+                        ev = (raw.view("<u4") if b.format == 4 else
+                              raw.view("<u8") if b.format == 8 else raw.view("<u4").reshape(n, 3) if b.format == 12
                               else raw.view("<u8").reshape(n, 2) if b.format == 16 else raw.view(EVENT_DTYPE))
                     info = {k: int(getattr(b, k)) for k, _ in _lib.JBatch._fields_}
                     sink(info, rounds, ev)

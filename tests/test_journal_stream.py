@@ -1,6 +1,6 @@
 """ms_run_streamed (include/maelstrom_b200.h): the journal handed over in batches through pinned host
-memory while the simulation keeps running, in the 8-, 12- and 32-byte formats, expanded on the host by
-ms_journal_decode.  Whatever the batch size and the size of the device's raw ring (back-pressure),
+memory while the simulation keeps running, in the 4-, 8-, 12- and 32-byte formats, expanded on the host by
+ms_journal_decode (4-byte records: by an ms_jdecoder, which follows the stream).  Whatever the batch size and the size of the device's raw ring (back-pressure),
 the stream must be the journal ms_journal_drain returns, i.e. the oracle's, event for event."""
 import numpy as np
 import pytest
@@ -12,7 +12,8 @@ pytestmark = pytest.mark.usefixtures("engine_backend")
 
 
 @pytest.mark.parametrize("fmt,buf_events,jcap,latency", [
-    (8, 1 << 12, 20, 0), (12, 777, 20, 0), (32, 1 << 14, 20, 2), (8, 300, 11, 0), (8, 1 << 16, 20, 3)])
+    (8, 1 << 12, 20, 0), (12, 777, 20, 0), (32, 1 << 14, 20, 2), (8, 300, 11, 0), (8, 1 << 16, 20, 3),
+    (4, 1 << 12, 20, 0), (4, 300, 11, 0), (4, 1 << 16, 20, 3), (4, 901, 20, 1)])
 def test_stream_equals_oracle(fmt, buf_events, jcap, latency):
     n = 25
     g, o = make_pair(n, topology="grid", n_values=4096, ring_cap=512, max_window=256, journal_cap_log2=jcap,
@@ -59,4 +60,21 @@ def test_stream_format8_reports_what_it_cannot_hold():
     with pytest.raises(mb.SimError) as e:
         g.run_streamed(2_000_000, lambda *a: None, fmt=8)
     assert "wider format" in str(e.value)
+    g.close()
+
+
+def test_stream_format4_decoder_needs_the_history():
+    # a decoder that joins the stream late cannot name the senders of what was sent before it joined
+    import maelstrom_b200 as mb
+    from maelstrom_b200.engine import JournalDecoder
+    g = mb.Sim(9, workload="broadcast", topology="grid", n_values=64, ring_cap=64, max_window=32, journal_level=1,
+               latency_dist="constant", latency_mean_ms=3)                                # messages in flight across the cut
+    c = g.add_endpoint("c0", O.KIND_SIM_CLIENT)
+    ops, _ = random_broadcast_ops(9, [c], n_ticks=4, per_tick=3, seed=3)
+    g.schedule(ops)
+    g.run_streamed(2_000_000, lambda *a: None, fmt=4, decode=True)                     # the Sim's own decoder follows
+    late = JournalDecoder(log2_window=10)
+    with pytest.raises(mb.SimError) as e:
+        g.run_streamed(30_000_000, lambda *a: None, fmt=4, decode=True, decoder=late)
+    assert "ms_jdecoder" in str(e.value)
     g.close()
