@@ -1184,8 +1184,16 @@ int ms_run(ms_sim* s, int64_t until) {
   uint64_t stall_round = s->hs.rounds_run;
   // batch sizing: nothing to hand to the host between rounds (no mailbox traffic, journal discarded or streamed
   // elsewhere) -> start from the previous call's round count, then grow while whole batches are productive
-  const bool adaptive = !s->mail_seen && s->pending.empty() && (s->cfg.journal_discard || s->cfg.journal_level == 0) &&
-                        s->P.n_shards <= 1;
+  // Sharded runs: every shard must issue the same launch sequence (the barriers pair up), so the decision may only
+  // use what is identical on all shards -- the configuration, the endpoint table and the round counter -- and is
+  // taken only when no endpoint has a host mailbox at all.
+  bool adaptive = s->cfg.journal_discard || s->cfg.journal_level == 0;
+  if (s->P.n_shards <= 1) {
+    adaptive = adaptive && !s->mail_seen && s->pending.empty();
+  } else {
+    for (uint8_t k : s->kinds)
+      if (!(k & kRemoved) && ((k & 0x7F) == MS_KIND_CLIENT || (k & 0x7F) == MS_KIND_HOST)) adaptive = false;
+  }
   const uint64_t entry_rounds = s->hs.rounds_run;
   uint64_t batch = 32;
   if (adaptive) batch = s->run_hint > 36 ? std::min<uint64_t>(s->run_hint - 2, 1024) : 32;
@@ -1202,7 +1210,7 @@ int ms_run(ms_sim* s, int64_t until) {
               s->hs.cls_cursor[s->hs.round & 1][3]);
     if (adaptive) {
       const bool full = s->hs.rounds_run - r0 == batch;
-      batch = s->mail_seen ? 32 : (full ? std::min<uint64_t>(std::max<uint64_t>(2 * batch, 4), 256) : 4);
+      batch = (s->mail_seen && s->P.n_shards <= 1) ? 32 : (full ? std::min<uint64_t>(std::max<uint64_t>(2 * batch, 4), 256) : 4);
       if (full && s->run_hint > 36 && s->hs.rounds_run - entry_rounds <= s->run_hint) batch = 4;   // the call's last rounds
     }
     if (s->hs.now != stall_now) { stall_now = s->hs.now; stall_round = s->hs.rounds_run; }

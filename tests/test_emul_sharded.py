@@ -279,3 +279,24 @@ def test_emulated_shards_stream_their_journal(world, fmt, latency):
         assert np.array_equal(merged[f], ev_o[f]), f
     assert all(len(got[r]) > 0 for r in range(world))
     assert st == o.stats() and now == o.now and rnd == o.round
+
+
+def test_emulated_shards_discarded_journal_adaptive_batches():
+    # journal_discard + no mailbox endpoints: ms_run sizes its batches of rounds from the previous call (also on
+    # shards, where every shard must take the same decision or the barriers would not pair up); state vs the oracle
+    world, n = 3, 30
+    kw = dict(topology="grid", n_values=512, seed=77)
+
+    def scenario(s, body):
+        cs = [s.add_endpoint("c%d" % i, O.KIND_SIM_CLIENT) for i in range(3)]
+        ops, _ = random_broadcast_ops(n, cs, n_ticks=20, per_tick=6, seed=12)
+        s.schedule(ops)
+        for t in (5, 10, 15, 20, 24):
+            s.run(t * 1_000_000)
+
+    ev, st, now, rnd = run_sharded_scenario(world, n, dict(workload="broadcast", ring_cap=512, max_window=256, journal_discard=1,
+                                                            max_endpoints=n + 8, **kw), scenario)
+    o = O.Sim(n, workload=O.W_BROADCAST, **kw)
+    scenario(o, O.body)
+    assert len(ev) == 0 and st == o.stats() and now == o.now and rnd == o.round
+    assert st["servers"]["recv-count"] > 5000

@@ -7,9 +7,19 @@ import os
 import numpy as np
 import pytest
 
+import contextlib
+
 import emul_lib
 import oracle_lib as O
 from scenarios import assert_same_journal, both, make_pair
+
+
+def backend():
+    """MS_FUZZ_BACKEND=cuda runs the single-GPU modes on the product library of the GPU box (profiles/ has the
+    log of such a run); the default is the kernel sources under the CPU SIMT emulator."""
+    if os.environ.get("MS_FUZZ_BACKEND") == "cuda":
+        return contextlib.nullcontext()
+    return emul_lib.use()
 
 
 def seeds():
@@ -141,7 +151,7 @@ def test_random_scenario(seed):
             got.append((int(m["id"]), int(m["type"]), int(m["src"]), int(m["in_reply_to"]), int(m["p0"]), int(m["p1"])))
         return got, s.client_replies()
 
-    with emul_lib.use():
+    with backend():
         g, o = make_pair(n, workload=workload, **kw, **sizing)
         rg, ro = both(g, o, scenario)
         assert rg == ro
@@ -193,7 +203,7 @@ def test_random_heavy_broadcast(seed):
         if mean:
             s.run((ticks + 2 + 600 * mean) * 1_000_000)
 
-    with emul_lib.use():
+    with backend():
         import maelstrom_b200 as mb
         g, o = make_pair(n, workload="broadcast", **kw, **sizing)
         try:
@@ -311,7 +321,7 @@ def test_random_raft(seed):
             s.run(t_ms * 1_000_000)
         return [s.raft_state(i) for i in range(n)], s.client_replies()
 
-    with emul_lib.use():
+    with backend():
         g, o = make_pair(n, workload="lin-kv", max_endpoints=n + 8, ring_cap=1024, max_window=512,
                          journal_cap_log2=19, calendar_slots=256, calendar_cap=4096, **kw)
         rg, ro = both(g, o, scenario)
