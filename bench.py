@@ -683,7 +683,6 @@ def gpu_arm(args, rank, world, local_rank):
     torch.cuda.synchronize()
     after = lstats()
     c_after = sim.counters()
-    clocks = sampler.stop()
     if args.phase_cycles and world == 1:
         pc = sim.phase_cycles(False)
         names = ["fetch", "load+seen (PA)", "order (PB)", "first-sight+counts (PC)", "scan", "claims (PD)", "records+emissions (PE)",
@@ -709,6 +708,15 @@ def gpu_arm(args, rank, world, local_rank):
     a2 = lstats()
     k_ms, k_launches = sim.profile_read()
     sim.profile(False)
+    # the sampler ran through the timed steps and the identical profiled steps; short multi-GPU runs can be over before
+    # nvidia-smi's first row: the GPU is still under the same load pattern, wait for one
+    t_wait = time.time()
+    late = not sampler.rows
+    while not sampler.rows and time.time() - t_wait < 3.0:
+        time.sleep(0.05)
+    clocks = sampler.stop()
+    if late:
+        clocks["note"] = "run shorter than nvidia-smi's start-up: first row taken right after the profiled steps"
     p_sends, p_recvs = a2["send-count"] - b2["send-count"], a2["recv-count"] - b2["recv-count"]
     alg_bytes = wl.alg_bytes(p_sends, p_recvs)
     real_bytes = wl.real_bytes(p_sends, p_recvs)

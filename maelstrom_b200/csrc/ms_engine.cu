@@ -315,6 +315,8 @@ struct ms_sim {
   }
 
   void launch_rounds_direct(uint64_t n) {
+    // sharded, no timing wheel, the engine's own barrier, few enough endpoints for one CTA: one glue launch between rounds
+    const bool glue = P.n_shards > 1 && !use_calendar && !barrier && !P.cm_blk && P.n_ep <= 32768 && !getenv("MS_NO_GLUE");
     for (uint64_t i = 0; i < n; i++) {
       cudaEvent_t a = nullptr, b = nullptr;
       if (profiling) {
@@ -333,6 +335,11 @@ struct ms_sim {
       if (P.n_shards <= 1) {
         msk_launch_round(&P, n_classes, class_cap, class_threads, grids, use_calendar ? 1 : 0, stream, a, b, 15, aux_streams, aux_events);
         if (!capturing()) launches += (use_calendar ? 2 : 1) + n_classes + (P.split_commit ? (P.cm_blk ? 3 : 1) : 0);
+      } else if (glue) {
+        // sharded: glue (barrier | commit of the previous round | snapshot | barrier) | round kernels (peer writes)
+        msk_launch_round(&P, n_classes, class_cap, class_threads, grids, 0, stream, a, b, 16, aux_streams, aux_events);
+        msk_launch_round(&P, n_classes, class_cap, class_threads, grids, 0, stream, a, b, 2, aux_streams, aux_events);
+        if (!capturing()) launches += 1 + n_classes;
       } else {
         // sharded: [release (peer writes) | barrier] snapshot | barrier | round kernels (peer writes) | barrier | commit
         if (use_calendar) {
@@ -346,6 +353,11 @@ struct ms_sim {
         msk_launch_round(&P, n_classes, class_cap, class_threads, grids, 0, stream, a, b, 4, aux_streams, aux_events);
         if (!capturing()) launches += (use_calendar ? 2 : 1) + n_classes + (use_calendar ? 4 : 3);
       }
+    }
+    if (glue && n) {     // close the batch: the last round's commit
+      int grids[4] = {1, 1, 1, 1};
+      msk_launch_round(&P, n_classes, class_cap, class_threads, grids, 0, stream, nullptr, nullptr, 32, aux_streams, aux_events);
+      if (!capturing()) launches += 1;
     }
   }
 

@@ -464,25 +464,33 @@ __device__ bool gen_step(const Params& p, DevState* st, uint32_t e, int64_t now,
 // every peer's flag array, then waits until all peers have stored it into its own.  Kernels
 // of one shard are stream-ordered around it, so everything a shard wrote into peer inbox
 // rings before the barrier is visible to the owner after it.
-__global__ void k_barrier(Params p) {
-  __shared__ uint32_t s_epoch;
+// Called by every thread of ONE CTA (the only CTA of its kernel); returns after a __syncthreads().
+__device__ void barrier_body(const Params& p, uint32_t* s_epoch) {
   // the epoch lives on the device so that the launch sequence can be replayed from a CUDA graph;
   // all shards execute the same number of barriers, so their counters agree
-  if (threadIdx.x == 0) s_epoch = ++p.st->bar_epoch;
+  __syncthreads();                     // everything this CTA did before the barrier is done
+  if (threadIdx.x == 0) *s_epoch = ++p.st->bar_epoch;
   __syncthreads();
-  const uint32_t epoch = s_epoch;
+  const uint32_t epoch = *s_epoch;
   const uint32_t g = threadIdx.x;
-  if (g >= p.n_shards) return;
-  __threadfence_system();
-  *reinterpret_cast<volatile uint32_t*>(&p.bar_sh[g][p.shard_id]) = epoch;
-  __threadfence_system();
-  const volatile uint32_t* mine = p.bar_sh[p.shard_id] + g;
-  uint32_t spins = 0;
-  while ((int32_t)(*mine - epoch) < 0) {
-    if (++spins > (1u << 27)) { latch_error(p.st, E_BARRIER, g); break; }   // a peer died: do not hang the GPU
-    __nanosleep(40);
+  if (g < p.n_shards) {
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t*>(&p.bar_sh[g][p.shard_id]) = epoch;
+    __threadfence_system();
+    const volatile uint32_t* mine = p.bar_sh[p.shard_id] + g;
+    uint32_t spins = 0;
+    while ((int32_t)(*mine - epoch) < 0) {
+      if (++spins > (1u << 27)) { latch_error(p.st, E_BARRIER, g); break; }   // a peer died: do not hang the GPU
+      __nanosleep(40);
+    }
+    __threadfence_system();
   }
-  __threadfence_system();
+  __syncthreads();
+}
+
+__global__ void k_barrier(Params p) {
+  __shared__ uint32_t s_epoch;
+  barrier_body(p, &s_epoch);
 }
 
 // ------------------------------------------------------------------ k_snapshot
@@ -495,12 +503,47 @@ __device__ __forceinline__ uint32_t class_of(const Params& p, uint32_t n) {
   return c;
 }
 
+// The per-endpoint part of k_snapshot for the threads gid, gid + stride, ...: also run by the single CTA of
+// k_glue (sharded runs), right after it has committed the previous round.
+__device__ void snapshot_endpoints(const Params& p, DevState* st, uint32_t gid, uint32_t stride);
+
 __global__ void k_snapshot(Params p) {
   DevState* st = p.st;
   if (round_skipped(p, st)) return;
+  snapshot_endpoints(p, st, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
   const uint32_t par = (uint32_t)st->round & 1u;
-  const uint32_t stride = gridDim.x * blockDim.x;
   const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.x == 0) {
+    // timing wheel housekeeping, one CTA (nothing pops blocks while this kernel runs): the chain
+    // k_release has just emptied goes back to the pool, and so do blocks that lost a publish race
+    if (p.cal && st->cal_release) {
+      const uint32_t slot = st->cal_release - 1;
+      const uint32_t gen = p.cal_par[slot] ^ 1u;                        // the generation that was released
+      uint32_t* cnt = p.cal_count + (size_t)gen * p.cal_slots + slot;
+      uint32_t* tab = p.cal_tab + ((size_t)gen * p.cal_slots + slot) * p.cal_tab_cap;
+      const uint32_t nb = min((*cnt + (1u << p.cal_blk_log2) - 1u) >> p.cal_blk_log2, p.cal_tab_cap);
+      for (uint32_t j = threadIdx.x; j < nb; j += blockDim.x) {
+        const uint32_t b = tab[j];
+        if (b) { p.cal_free[atomicAdd(&st->cal_free_n, 1u)] = b - 1u; tab[j] = 0; }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) { *cnt = 0; st->cal_release = 0; }
+    }
+    if (p.cal) {
+      const uint32_t nr = st->cal_ret_n;
+      for (uint32_t i = threadIdx.x; i < nr; i += blockDim.x) p.cal_free[atomicAdd(&st->cal_free_n, 1u)] = p.cal_ret[i];
+      __syncthreads();
+      if (threadIdx.x == 0) st->cal_ret_n = 0;
+    }
+  }
+  if (gid == 0) {
+    for (int c = 0; c < 4; c++) { st->cls_count[par ^ 1u][c] = 0; st->cls_small[par ^ 1u][c] = 0; st->cls_cursor[par ^ 1u][c] = 0; }
+    st->slot_open = slot_tag(st->round);
+  }
+}
+
+__device__ void snapshot_endpoints(const Params& p, DevState* st, uint32_t gid, uint32_t stride) {
+  const uint32_t par = (uint32_t)st->round & 1u;
   const uint32_t row = (uint32_t)st->round & p.hist_mask;
   const uint64_t empty_entry = (uint64_t)(((uint32_t)st->round & 0x7FFFu) + 1u) << 48;   // tag | 0 events | 0 emissions
   uint32_t n_empty = 0;
@@ -548,33 +591,6 @@ __global__ void k_snapshot(Params p) {
     const uint32_t c = p.n_classes - 1;
     const uint32_t k = atomicAdd(&st->cls_count[par][c], 1u);
     if (k < p.t_max) p.cls_list[((size_t)par * 4 + c) * p.t_max + k] = gid;
-  }
-  if (blockIdx.x == 0) {
-    // timing wheel housekeeping, one CTA (nothing pops blocks while this kernel runs): the chain
-    // k_release has just emptied goes back to the pool, and so do blocks that lost a publish race
-    if (p.cal && st->cal_release) {
-      const uint32_t slot = st->cal_release - 1;
-      const uint32_t gen = p.cal_par[slot] ^ 1u;                        // the generation that was released
-      uint32_t* cnt = p.cal_count + (size_t)gen * p.cal_slots + slot;
-      uint32_t* tab = p.cal_tab + ((size_t)gen * p.cal_slots + slot) * p.cal_tab_cap;
-      const uint32_t nb = min((*cnt + (1u << p.cal_blk_log2) - 1u) >> p.cal_blk_log2, p.cal_tab_cap);
-      for (uint32_t j = threadIdx.x; j < nb; j += blockDim.x) {
-        const uint32_t b = tab[j];
-        if (b) { p.cal_free[atomicAdd(&st->cal_free_n, 1u)] = b - 1u; tab[j] = 0; }
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) { *cnt = 0; st->cal_release = 0; }
-    }
-    if (p.cal) {
-      const uint32_t nr = st->cal_ret_n;
-      for (uint32_t i = threadIdx.x; i < nr; i += blockDim.x) p.cal_free[atomicAdd(&st->cal_free_n, 1u)] = p.cal_ret[i];
-      __syncthreads();
-      if (threadIdx.x == 0) st->cal_ret_n = 0;
-    }
-  }
-  if (gid == 0) {
-    for (int c = 0; c < 4; c++) { st->cls_count[par ^ 1u][c] = 0; st->cls_small[par ^ 1u][c] = 0; st->cls_cursor[par ^ 1u][c] = 0; }
-    st->slot_open = slot_tag(st->round);
   }
 }
 
@@ -898,6 +914,32 @@ __global__ void __launch_bounds__(512) k_commit(Params p) {
   DevState* st = p.st;
   if (round_skipped(p, st) || !st->slot_open) return;
   commit_round(p, st, s_wtmp);
+}
+
+// Sharded runs, one launch between two rounds instead of four (k_barrier | k_commit | k_snapshot | k_barrier):
+// barrier A -- every shard's round kernels are done and their peer writes visible; commit of the open round (all
+// shards compute the same prefixes from all shards' counts); snapshot of this shard's endpoints for the next round
+// unless it is skipped; barrier B -- nobody writes into a peer's ring before that peer has frozen its windows.
+// open_next = 0 closes a batch of rounds: barrier A and the commit only.  Not used with the timing wheel (k_release
+// and its barrier come between commit and snapshot) nor with many endpoints (one CTA walks them).
+__global__ void __launch_bounds__(512) k_glue(Params p, uint32_t open_next) {
+  __shared__ uint64_t s_wtmp[34];
+  __shared__ uint32_t s_epoch;
+  DevState* st = p.st;
+  barrier_body(p, &s_epoch);
+  if (!round_skipped(p, st) && st->slot_open) commit_round(p, st, s_wtmp);
+  __syncthreads();
+  if (!open_next) return;
+  if (!round_skipped(p, st)) {                         // the state the commit has just left behind
+    snapshot_endpoints(p, st, threadIdx.x, blockDim.x);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const uint32_t par = (uint32_t)st->round & 1u;
+      for (int c = 0; c < 4; c++) { st->cls_count[par ^ 1u][c] = 0; st->cls_small[par ^ 1u][c] = 0; st->cls_cursor[par ^ 1u][c] = 0; }
+      st->slot_open = slot_tag(st->round);
+    }
+  }
+  barrier_body(p, &s_epoch);
 }
 
 // Commit in three launches for simulations with very many endpoints (tens of thousands of tickets:
@@ -2513,12 +2555,15 @@ int msk_round_occupancy(int threads, size_t smem) {
 // One round = [k_release] k_snapshot | one persistent k_round grid per window-size class
 // (caps ascending; every ticket is taken by exactly one class) | k_commit (sharded runs only;
 // a single GPU commits inside k_round).  `phases` is a bit mask so that a sharded host can
-// put its barriers in between: 1 = timing-wheel release, 8 = snapshot, 2 = round kernels, 4 = commit.
+// put its barriers in between: 1 = timing-wheel release, 8 = snapshot, 2 = round kernels, 4 = commit;
+// 16 / 32 = k_glue opening the next round / closing a batch (sharded runs without the timing wheel).
 void msk_launch_round(const msd::Params* p, int n_classes, const uint32_t* caps, const int* threads,
                       const int* grids, int with_release, cudaStream_t s, cudaEvent_t before_round,
                       cudaEvent_t after_round, int phases, const cudaStream_t* aux, const cudaEvent_t* aux_ev) {
   const uint32_t n_ep = p->n_ep;
   // two CTAs per SM on a B200 (the class-0 grid is SMs x occupancy >= 296 there)
+  if (phases & 16) MS_LAUNCH(msd::k_glue, 1, 512, 0, s, *p, 1u);
+  if (phases & 32) MS_LAUNCH(msd::k_glue, 1, 512, 0, s, *p, 0u);
   if ((phases & 1) && with_release) MS_LAUNCH(msd::k_release, grids[0] < 296 ? grids[0] : 296, 256, 0, s, *p);
   if (phases & 8) {
     const int sb = 256;
