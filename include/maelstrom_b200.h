@@ -108,6 +108,14 @@ enum {
 
 enum { MS_W_ECHO = 0, MS_W_BROADCAST = 1, MS_W_GSET = 2,                     /* --workload, core.clj:36-47 */
        MS_W_RAFT = 3,    /* lin-kv served by Raft nodes (demo/python/raft.py) */
+       MS_W_TXN_TREE = 5,  /* txn-list-append on a persistent hash tree: immutable tree nodes in lww-kv, the root pointer in
+                             lin-kv (demo/ruby/datomic_list_append.rb).  Needs the lin-kv and lww-kv services.  A txn carries
+                             up to four micro-ops in p1, 16 bits each: valid << 15 | append << 14 | key (< 16384); p0 is the
+                             caller's handle.  txn_ok: p1 = root pointer read | root pointer written << 32 (the caller replays
+                             apply_txn over the chain of roots).  Pointer "n<e>-<p>" = 2 + e * reserved[3] + (p - 1), "empty" = 1;
+                             ms_config.reserved[3] = pointers a node may mint (default 256), reserved[4] = tree nodes a node
+                             may cache (default 1024), reserved[2] (service keys) defaults to cover every pointer.
+                             Promise time-outs (promise.rb, 5 s) are not modelled: p_loss must be 0. */
        MS_W_TXN = 4 };   /* txn-list-append, whole database in one lin-kv key (demo/clojure/single_key_txn.clj);
                             needs the "lin-kv" service endpoint */
 enum { MS_TOPO_GRID = 0, MS_TOPO_LINE = 1, MS_TOPO_TOTAL = 2,                /* --topology, broadcast.clj:169-178 */

@@ -219,6 +219,12 @@ struct Params {
   uint32_t  rf_group;        // servers per Raft cluster (0 = one cluster of all servers)
   uint32_t  rf_gmax;         // row stride of rf_next / rf_match / rf_scratch = largest cluster
   uint32_t  rf_cb_mask;      // pending-RPC table slots per node - 1 (power of two)
+  // MS_W_TXN_TREE (csrc/ms_tree.h, tt_handle in csrc/ms_raft.cuh)
+  struct TreeDev* tt_node;   // [n_servers]
+  unsigned char* tt_recs;    // [1 + n_servers * tt_per_node] 64-B tree node records by pointer - 1
+  uint32_t* tt_cache;        // [n_servers][tt_cache_mask + 1] pointers in the node's @@cache (open addressing, 0 = empty)
+  uint4*    tt_queue;        // [n_servers][kTreeQueue] txn requests waiting for the node's txn_lock
+  uint32_t  tt_per_node, tt_cache_mask;
   // closed-loop clients (ms_add_gen_clients)
   struct GenDev* gc;         // [max_endpoints], valid where kind == MS_KIND_GEN_CLIENT
   uint4*    gc_hist;         // ring of 32-B history records (ms_hist)
@@ -245,6 +251,18 @@ struct RaftDev {
   int64_t  election_deadline, step_down_deadline, last_replication;
   uint32_t next_msg_id, log_size, appends, n_votes, kv_size;
   uint32_t busy;                       // leader with a follower behind its log (or a next_index <= 0): see rf_timer_due
+};
+
+// MS_W_TXN_TREE node (demo/ruby/datomic_list_append.rb DatomicListAppendNode, :322-417)
+constexpr uint32_t kTreeQueue = 64;
+struct TreeDev {
+  uint32_t ptr_counter;                // @ptr (:355-358)
+  uint32_t phase;                      // 0 idle, 1 root read out, 2 tree node read out, 3 writes out, 4 cas out
+  uint32_t cur_src, cur_msg_id;        // the txn request holding @txn_lock
+  uint64_t cur_ops;
+  uint32_t root1, root2, start_counter, writes_left, write_failed, load_ptr;
+  uint32_t q_head, q_tail;             // requests waiting for the lock
+  uint32_t init_src, init_msg_id;      // the init request (first node: answered after the initial state is written)
 };
 
 // closed-loop client (maelstrom.client + a Jepsen worker), one per MS_KIND_GEN_CLIENT endpoint

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "ms_device.cuh"
+#include "ms_tree.h"
 #include "ms_fressian.h"
 #include "ms_json.h"
 
@@ -545,7 +546,7 @@ static int build_sim(ms_sim* s, const ms_config* in) {
   ms_config& c = s->cfg;
   c = *in;
   if (c.n_nodes == 0) { set_err("n_nodes must be positive (--node-count)"); return MS_ERR_ARG; }
-  if (c.workload > MS_W_TXN || c.topology > MS_TOPO_TREE4 || c.latency_dist > MS_DIST_EXPONENTIAL) {
+  if (c.workload > MS_W_TXN_TREE || c.topology > MS_TOPO_TREE4 || c.latency_dist > MS_DIST_EXPONENTIAL) {
     set_err("bad workload/topology/latency_dist");
     return MS_ERR_ARG;
   }
@@ -703,12 +704,30 @@ static int build_sim(ms_sim* s, const ms_config* in) {
     if ((rc = s->dalloc(&P.next_msg_id, c.n_nodes))) return rc;
   }
   P.family = c.workload == MS_W_GSET ? 1u : (c.workload >= MS_W_RAFT ? 4u : 0u);
-  if (c.workload == MS_W_TXN) {
+  if (c.workload == MS_W_TXN_TREE) {
+    // hash-tree txn-list-append (csrc/ms_tree.h): tree node records by pointer, per-node cache, lock queue
+    if (c.p_loss > 0.0) { set_err("MS_W_TXN_TREE: promise time-outs are not modelled, p_loss must be 0"); return MS_ERR_ARG; }
+    if (c.n_shards > 1) { set_err("MS_W_TXN_TREE runs on one GPU (tree records are read across nodes)"); return MS_ERR_ARG; }
+    const size_t N = c.n_nodes;
+    P.tt_per_node = c.reserved[3] ? c.reserved[3] : 256u;
+    P.tt_cache_mask = pow2_at_least(c.reserved[4] ? c.reserved[4] : 1024u) - 1u;
+    const uint64_t n_ptrs = 2ull + (uint64_t)N * P.tt_per_node;
+    if (n_ptrs > (1ull << 31)) { set_err("MS_W_TXN_TREE: n_nodes x reserved[3] pointers do not fit"); return MS_ERR_ARG; }
+    if (!c.reserved[2]) c.reserved[2] = (uint32_t)n_ptrs;           // lww-kv is keyed by pointer
+    if ((rc = s->dalloc(&P.tt_node, N)) || (rc = s->dalloc(&P.tt_recs, (size_t)n_ptrs * 64)) ||
+        (rc = s->dalloc(&P.tt_cache, N * ((size_t)P.tt_cache_mask + 1))) || (rc = s->dalloc(&P.tt_queue, N * kTreeQueue)))
+      return rc;
+    mst::Rec empty{};                                               // Tree.empty: a leaf over the whole ring, no keys
+    empty.type = 1; empty.lo = 0; empty.hi = (uint8_t)mst::kRing; empty.n = 0;
+    CK(cudaMemcpyAsync(P.tt_recs + (size_t)(mst::kPtrEmpty - 1u) * 64, &empty, sizeof empty, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+  }
+  if (c.workload == MS_W_TXN || c.workload == MS_W_TXN_TREE) {
     // txn-list-append nodes: message ids, the table of pending RPC closures and the staging rows of
     // the sequential step (csrc/ms_raft.cuh)
     // (nothing here is read across nodes: sharded runs need no extra mapping)
     const size_t N = c.n_nodes;
-    P.rf_stage_cap = c.server_max_window + 16u;
+    P.rf_stage_cap = c.workload == MS_W_TXN_TREE ? c.server_max_window * (mst::kMaxWrites + 2u) + 64u : c.server_max_window + 16u;
     P.rf_cb_mask = pow2_at_least(c.reserved[5] ? c.reserved[5] : kRaftCallbacks) - 1u;
     if ((rc = s->dalloc(&P.rf_node, N)) || (rc = s->dalloc(&P.rf_cb, N * ((size_t)P.rf_cb_mask + 1) * 2)) ||
         (rc = s->dalloc(&P.rf_stage, N * P.rf_stage_cap * 3)))

@@ -457,6 +457,7 @@ __device__ bool gen_step(const Params& p, DevState* st, uint32_t e, int64_t now,
   return send;
 }
 
+#include "ms_tree.h"
 #include "ms_raft.cuh"
 
 // ------------------------------------------------------------------ k_barrier (sharded runs)
@@ -1762,6 +1763,7 @@ __global__ void __launch_bounds__(CLS == 3 ? 512 : 256, CLS == 3 ? 2 : MS_ROUND_
             if (!(vals[i] & V_RECV)) continue;
             const uint4* rp = myring + (size_t)((head + i) & my_mask) * 3;
             if (p.workload == MS_W_RAFT) rf_handle(c, rec_unpack(rp[0], rp[1], rp[2]));
+            else if (p.workload == MS_W_TXN_TREE) tt_handle(c, rec_unpack(rp[0], rp[1], rp[2]));
             else txn_handle(c, rec_unpack(rp[0], rp[1], rp[2]));
           }
           if (p.workload == MS_W_RAFT) { rf_actions(c); rf_note_busy(c); }

@@ -464,3 +464,185 @@ __device__ void txn_handle(RaftCtx& c, const Rec& m) {
   er.p0 = 10;
   rf_emit(c, er);
 }
+
+// ------------------------------------------------------------------ txn-list-append on a persistent hash tree
+// demo/ruby/datomic_list_append.rb.  The database is a tree of immutable nodes stored in lww-kv under
+// unique pointers; lin-kv holds the pointer to the root (key "root" = key 0 here).  A txn (:340-353, under
+// @txn_lock: one at a time per node, here in arrival order): read the root pointer, load the tree lazily
+// (Tree.load :83-101: cache, else read lww-kv until it answers read_ok), apply the micro-ops (path copying,
+// csrc/ms_tree.h), and if the tree changed write every new node to lww-kv, wait for all write_oks, then cas the
+// root from the pointer read to the new one: cas_ok -> txn_ok, anything else -> error 30.  A root that cannot
+// be read is error 14 (abort, :361-368).  sync_rpc! is a blocked thread in the reference; here the node is a
+// state machine and the blocked evaluation is redone after every load (same result, see ms_tree.h).
+// Promise time-outs (promise.rb) are not modelled (ms_create refuses p_loss > 0 for this workload).
+struct TreeStore {
+  const Params& p;
+  uint32_t e;
+  __device__ mst::Rec* rec(uint32_t ptr) const { return reinterpret_cast<mst::Rec*>(p.tt_recs) + (ptr - 1u); }
+  __device__ bool cached(uint32_t ptr) const {
+    const uint32_t* tab = p.tt_cache + (size_t)e * (p.tt_cache_mask + 1u);
+    for (uint32_t h = (ptr * 0x9E3779B1u) & p.tt_cache_mask, n = 0; n <= p.tt_cache_mask; n++, h = (h + 1u) & p.tt_cache_mask) {
+      if (tab[h] == ptr) return true;
+      if (tab[h] == 0u) return false;
+    }
+    return false;
+  }
+};
+
+__device__ void tt_cache_insert(RaftCtx& c, uint32_t ptr) {                       // @@cache[ptr] = tree, :95
+  uint32_t* tab = c.p.tt_cache + (size_t)c.e * (c.p.tt_cache_mask + 1u);
+  uint32_t h = (ptr * 0x9E3779B1u) & c.p.tt_cache_mask;
+  for (uint32_t n = 0; n < c.p.tt_cache_mask; n++, h = (h + 1u) & c.p.tt_cache_mask) {   // one slot always stays empty
+    if (tab[h] == ptr) return;
+    if (tab[h] == 0u) { tab[h] = ptr; return; }
+  }
+  latch_error(c.st, E_RAFT_CAPACITY, c.e);
+}
+
+// Node#rpc! (node.rb:95-102): msg_id = @next_msg_id += 1, remember the handler, send
+__device__ void tt_rpc(RaftCtx& c, uint32_t dest, uint32_t type, uint32_t p0, uint64_t p1, uint32_t kind, uint32_t arg) {
+  if (dest == 0xFFFFFFFFu) { latch_error(c.st, E_INVALID_DEST, dest); return; }   // the workload needs lin-kv and lww-kv
+  const uint32_t id = ++c.r->next_msg_id;
+  uint4* slot = c.cb + 2 * (size_t)(id & c.p.rf_cb_mask);
+  slot[0] = make_uint4(id, kind, arg, 0u);
+  slot[1] = make_uint4(0u, 0u, 0u, 0u);
+  Rec r;
+  r.round = 0; r.ticket = 0; r.idx = 0;
+  r.src = c.e; r.dest = dest; r.msg_id = id; r.in_reply_to = 0;
+  r.tf = type | ((uint32_t)MS_F_MSG_ID << 16);
+  r.p0 = p0; r.p1 = p1;
+  rf_emit(c, r);
+}
+
+__device__ void tt_start(RaftCtx& c, TreeDev* t, uint32_t src, uint32_t msg_id, uint64_t ops);
+
+__device__ void tt_finish(RaftCtx& c, TreeDev* t) {                               // @txn_lock released: the next waiter runs
+  t->phase = 0;
+  if (t->q_head != t->q_tail) {
+    const uint4 q = c.p.tt_queue[(size_t)c.e * kTreeQueue + (t->q_head % kTreeQueue)];
+    t->q_head++;
+    tt_start(c, t, q.x, q.y, (uint64_t)q.z | ((uint64_t)q.w << 32));
+  }
+}
+
+__device__ void tt_answer(RaftCtx& c, TreeDev* t, uint32_t type, uint32_t code, uint64_t p1) {
+  Rec req;
+  req.round = 0; req.ticket = 0; req.idx = 0;
+  req.src = t->cur_src; req.dest = c.e; req.msg_id = t->cur_msg_id; req.in_reply_to = 0; req.tf = MS_T_TXN; req.p0 = 0; req.p1 = 0;
+  Rec a = rf_reply_to(c, req, type);
+  a.p0 = code; a.p1 = p1;
+  rf_emit(c, a);
+  tt_finish(c, t);
+}
+
+__device__ void tt_start(RaftCtx& c, TreeDev* t, uint32_t src, uint32_t msg_id, uint64_t ops) {
+  t->cur_src = src; t->cur_msg_id = msg_id; t->cur_ops = ops;
+  t->phase = 1;
+  tt_rpc(c, c.p.sv_ep[MS_SVC_LIN_KV], MS_T_READ, 0u, 0ull, 10u, 0u);             // current_tree, :361-368
+}
+
+// tree1 -> apply_txn -> (save!, advance_root!) -> reply, as far as the node can get without another read (:340-353)
+__device__ void tt_eval(RaftCtx& c, TreeDev* t) {
+  TreeStore S{c.p, c.e};
+  uint32_t counter = t->start_counter, root2 = 0, load_ptr = 0;
+  const mst::Status st = mst::apply_txn(S, c.e, c.p.tt_per_node, t->root1, t->cur_ops, t->start_counter, counter, root2, load_ptr);
+  if (st == mst::kCapacity) { latch_error(c.st, E_RAFT_CAPACITY, c.e); return; }
+  if (st == mst::kNeedLoad) {                                                     // Tree.load, :83-101
+    t->phase = 2; t->load_ptr = load_ptr;
+    tt_rpc(c, c.p.sv_ep[MS_SVC_LWW_KV], MS_T_READ, load_ptr, 0ull, 11u, load_ptr);
+    return;
+  }
+  t->ptr_counter = counter;
+  t->root2 = root2;
+  if (root2 == t->root1) {                                                        // nothing appended: no save, no cas
+    tt_answer(c, t, MS_T_TXN_OK, 0u, (uint64_t)t->root1 | ((uint64_t)t->root1 << 32));
+    return;
+  }
+  uint32_t out[mst::kMaxWrites], n = 0;
+  if (!mst::save_order(S, c.e, c.p.tt_per_node, t->start_counter, root2, out, n)) { latch_error(c.st, E_RAFT_CAPACITY, c.e); return; }
+  t->phase = 3; t->writes_left = n; t->write_failed = 0;
+  for (uint32_t i = 0; i < n; i++)                                                // save_this!, :128-145: value = the node's JSON
+    tt_rpc(c, c.p.sv_ep[MS_SVC_LWW_KV], MS_T_WRITE, out[i], (uint64_t)out[i], 12u, out[i]);
+}
+
+__device__ void tt_handle(RaftCtx& c, const Rec& m) {
+  TreeDev* t = c.p.tt_node + c.e;
+  const uint32_t type = m.tf & 0xFFFFu, flags = m.tf >> 16;
+  if (flags & MS_F_REPLY) {                                                       // node.rb:170-176
+    uint4* slot = c.cb + 2 * (size_t)(m.in_reply_to & c.p.rf_cb_mask);
+    const uint4 s0 = slot[0];
+    if (s0.y == 0 || s0.x != m.in_reply_to) return;                               // "Ignoring reply ... with no callback"
+    slot[0] = make_uint4(0u, 0u, 0u, 0u);
+    switch (s0.y) {
+      case 10:                                                                    // the root pointer
+        if (type == MS_T_READ_OK) {
+          t->root1 = (uint32_t)m.p1;
+          t->start_counter = t->ptr_counter;
+          tt_eval(c, t);
+        } else {
+          tt_answer(c, t, MS_T_ERROR, 14u, 0ull);                                 // RPCError.abort "Unsure how to handle", :367
+        }
+        return;
+      case 11:                                                                    // a tree node
+        if (type == MS_T_READ_OK) {
+          tt_cache_insert(c, s0.z);
+          tt_eval(c, t);
+        } else {                                                                  // "Retrying read of tree node", :97-99
+          tt_rpc(c, c.p.sv_ep[MS_SVC_LWW_KV], MS_T_READ, s0.z, 0ull, 11u, s0.z);
+        }
+        return;
+      case 12:                                                                    // one of save!'s writes
+        if (type != MS_T_WRITE_OK) t->write_failed = 1;
+        if (--t->writes_left == 0) {
+          if (t->write_failed) { tt_answer(c, t, MS_T_ERROR, 14u, 0ull); return; }   // "Couldn't save new tree", :347
+          t->phase = 4;                                                           // advance_root!, :372-379
+          tt_rpc(c, c.p.sv_ep[MS_SVC_LIN_KV], MS_T_CAS, 0u, (uint64_t)t->root1 | ((uint64_t)t->root2 << 32), 13u, 0u);
+        }
+        return;
+      case 13:
+        if (type == MS_T_CAS_OK) tt_answer(c, t, MS_T_TXN_OK, 0u, (uint64_t)t->root1 | ((uint64_t)t->root2 << 32));
+        else tt_answer(c, t, MS_T_ERROR, 30u, 0ull);                              // RPCError.txn_conflict, :378
+        return;
+      case 14: {                                                                  // the first node's initial state, :330-338
+        Rec req;
+        req.round = 0; req.ticket = 0; req.idx = 0;
+        req.src = t->init_src; req.dest = c.e; req.msg_id = t->init_msg_id; req.in_reply_to = 0; req.tf = MS_T_INIT; req.p0 = 0; req.p1 = 0;
+        if (type == MS_T_WRITE_OK) {
+          tt_rpc(c, c.p.sv_ep[MS_SVC_LIN_KV], MS_T_WRITE, 0u, (uint64_t)mst::kPtrEmpty, 15u, 0u);
+        } else {
+          Rec er = rf_reply_to(c, req, MS_T_ERROR);                               // "Couldn't write initial state"
+          er.p0 = 14;
+          rf_emit(c, er);
+        }
+        return;
+      }
+      case 15: {                                                                  // root written: reply! msg, type: "init_ok" (node.rb:31)
+        Rec req;
+        req.round = 0; req.ticket = 0; req.idx = 0;
+        req.src = t->init_src; req.dest = c.e; req.msg_id = t->init_msg_id; req.in_reply_to = 0; req.tf = MS_T_INIT; req.p0 = 0; req.p1 = 0;
+        rf_emit(c, rf_reply_to(c, req, MS_T_INIT_OK));
+        return;
+      }
+    }
+    return;
+  }
+  if (type == MS_T_INIT) {                                                        // node.rb:22-36 + :329-338
+    if (c.e == 0) {                                                               // @node.node_ids.first == @node.node_id
+      t->init_src = m.src; t->init_msg_id = m.msg_id;
+      tt_rpc(c, c.p.sv_ep[MS_SVC_LWW_KV], MS_T_WRITE, mst::kPtrEmpty, (uint64_t)mst::kPtrEmpty, 14u, 0u);
+    } else {
+      rf_emit(c, rf_reply_to(c, m, MS_T_INIT_OK));
+    }
+    return;
+  }
+  if (type == MS_T_TXN) {                                                         // :340-353
+    if (t->phase == 0) { tt_start(c, t, m.src, m.msg_id, m.p1); return; }
+    if (t->q_tail - t->q_head >= kTreeQueue) { latch_error(c.st, E_RAFT_CAPACITY, c.e); return; }
+    c.p.tt_queue[(size_t)c.e * kTreeQueue + (t->q_tail % kTreeQueue)] = make_uint4(m.src, m.msg_id, (uint32_t)m.p1, (uint32_t)(m.p1 >> 32));
+    t->q_tail++;
+    return;
+  }
+  Rec er = rf_reply_to(c, m, MS_T_ERROR);                                         // no handler: not supported
+  er.p0 = 10;
+  rf_emit(c, er);
+}

@@ -8,7 +8,7 @@ import numpy as np
 from . import _lib
 from ._lib import Body, Config, EVENT_DTYPE, JBODY_DTYPE, MSG_DTYPE, OP_DTYPE  # noqa: F401
 
-WORKLOADS = {"echo": 0, "broadcast": 1, "g-set": 2, "lin-kv": 3, "txn-list-append": 4}
+WORKLOADS = {"echo": 0, "broadcast": 1, "g-set": 2, "lin-kv": 3, "txn-list-append": 4, "txn-list-append-tree": 5}
 TOPOLOGIES = {"grid": 0, "line": 1, "total": 2, "tree": 3, "tree2": 3, "tree3": 4, "tree4": 5}
 DISTS = {"constant": 0, "uniform": 1, "exponential": 2}
 KIND_SERVER, KIND_CLIENT, KIND_HOST, KIND_SIM_CLIENT, KIND_SERVICE = 0, 1, 2, 3, 4
@@ -90,7 +90,7 @@ class Sim:
         cfg.journal_level = 2
         # named spellings of ms_config.reserved[]
         for name, slot in (("history_rounds", 0), ("use_graph", 1), ("n_keys", 2), ("raft_log_cap", 3),
-                           ("raft_group", 4), ("rpc_table", 5)):
+                           ("raft_group", 4), ("rpc_table", 5), ("tree_ptrs", 3), ("tree_cache", 4)):
             if name in sizing:
                 cfg.reserved[slot] = int(sizing.pop(name))
         for k, v in sizing.items():

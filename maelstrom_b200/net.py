@@ -92,10 +92,19 @@ class Net:
         create = False
         if t == "txn":                                                # workload/txn_list_append.clj
             ops = [list(op) for op in body["txn"]]
-            p1 = self._next_blob
+            handle = self._next_blob
             self._next_blob += 1
-            self._blobs[p1] = ops
-            return self._body(self._type_code(t), msg_id=body.get("msg_id"), p1=p1,
+            self._blobs[handle] = ops
+            if getattr(self.sim, "workload", 1) == 5:
+                # hash-tree node (datomic_list_append.rb): it looks at the keys, so they travel in the payload --
+                # up to four micro-ops of 16 bits: valid << 15 | append << 14 | key (include/maelstrom_b200.h)
+                if len(ops) > 4 or any(not (0 <= int(op[1]) < 16384) for op in ops):
+                    raise ValueError("txn-list-append-tree: at most 4 micro-ops on integer keys below 16384")
+                packed = 0
+                for i, op in enumerate(ops):
+                    packed |= (0x8000 | (0x4000 if op[0] == "append" else 0) | int(op[1])) << (16 * i)
+                return self._body(self._type_code(t), msg_id=body.get("msg_id"), p0=handle, p1=packed)
+            return self._body(self._type_code(t), msg_id=body.get("msg_id"), p1=handle,
                               appends=any(op[0] == "append" for op in ops))
         if "key" in body and t in ("read", "write", "cas"):           # service requests (doc/services.md)
             p0 = int(body["key"])

@@ -19,6 +19,7 @@
 //   (3) messages sent in round r become visible to receivers in round r+1.
 //   (4) if anything is due at now_r, the next round is a delta round at the same
 //       time, otherwise time advances by one tick (1 ms).
+#include "../maelstrom_b200/csrc/ms_tree.h"   // tree arithmetic of datomic_list_append.rb, shared with the engine (see its header)
 #include "oracle.h"
 
 #include <algorithm>
@@ -327,6 +328,17 @@ struct RaftNode {
   uint32_t draws = 0;                                            // random draws made in the current round
 };
 
+struct TreeNode {              // DatomicListAppendNode (datomic_list_append.rb:322-417)
+  uint32_t ptr_counter = 0;                                      // @ptr
+  int phase = 0;                                                 // 0 idle, 1 root read out, 2 tree node read out, 3 writes out, 4 cas out
+  uint32_t cur_src = 0, cur_msg_id = 0;
+  uint64_t cur_ops = 0;
+  uint32_t root1 = 0, root2 = 0, start_counter = 0, writes_left = 0, write_failed = 0;
+  std::deque<or_msg> waiting;                                    // threads blocked on @txn_lock, in arrival order
+  std::set<uint32_t> cache;                                      // @@cache
+  uint32_t init_src = 0, init_msg_id = 0;
+};
+
 struct Endpoint {
   std::string name;
   int kind = OR_KIND_SERVER;
@@ -342,6 +354,7 @@ struct Endpoint {
   uint64_t fires = 0;                   // g-set: replication runs so far
   Service svc;                          // OR_KIND_SERVICE
   RaftNode rn;                          // OR_W_RAFT servers
+  TreeNode tn;                          // OR_W_TXN_TREE servers
   // OR_KIND_GEN_CLIENT: maelstrom.client state (client.clj:41-64) + where the worker is in its generator
   struct Gen {
     uint32_t next_msg_id = 0, waiting_for = 0;
@@ -831,6 +844,138 @@ struct or_sim {
     }
   }
 
+  // ------------------------------------------------------------- txn-list-append on a hash tree (demo/ruby/datomic_list_append.rb)
+  // Immutable tree nodes live in lww-kv under unique pointers, lin-kv key "root" (0) holds the root pointer.
+  // handle txn (:340-353, one at a time under @txn_lock, arrival order): read root -> Tree.load lazily
+  // (cache, else read lww-kv until read_ok, :83-101) -> apply_txn (ms_tree.h) -> if the tree changed: write all
+  // new nodes, await every write_ok, cas root -> txn_ok | error 30.  Unreadable root -> error 14.
+  std::vector<mst::Rec> tt_recs;                 // contents by pointer - 1 (immutable once made)
+  uint32_t tt_per_node = 256;
+  struct TreeStore {
+    or_sim* s; uint32_t e;
+    mst::Rec* rec(uint32_t ptr) const { return &s->tt_recs[ptr - 1]; }
+    bool cached(uint32_t ptr) const { return s->eps[e].tn.cache.count(ptr) != 0; }
+  };
+  int svc_endpoint(int type) const {
+    for (uint32_t i = cfg.n_nodes; i < eps.size(); i++)
+      if (eps[i].live && eps[i].kind == OR_KIND_SERVICE && eps[i].svc.type == type) return (int)i;
+    return -1;
+  }
+  void tt_rpc(uint32_t e, int dest, uint16_t type, uint32_t p0, uint64_t p1, int kind, uint32_t arg, std::vector<Emit>& out) {
+    if (dest < 0) { error = "txn-list-append (hash tree) needs the lin-kv and lww-kv services"; return; }
+    RaftNode& r = eps[e].rn;
+    RaftCb cb; cb.kind = kind; cb.node = arg;
+    const uint32_t id = ++r.next_msg_id;                                          // node.rb:95-102
+    cb.msg_id = id;
+    r.callbacks[id % cb_slots] = cb;
+    or_msg q; std::memset(&q, 0, sizeof q);
+    q.type = type; q.p0 = p0; q.p1 = p1;
+    q.src = e; q.dest = (uint32_t)dest; q.flags = OR_F_MSG_ID; q.msg_id = id;
+    out.push_back(Emit(q));
+  }
+  void tt_start(uint32_t e, const or_msg& m, std::vector<Emit>& out) {
+    TreeNode& t = eps[e].tn;
+    t.cur_src = m.src; t.cur_msg_id = m.msg_id; t.cur_ops = m.p1;
+    t.phase = 1;
+    tt_rpc(e, svc_endpoint(OR_SVC_LIN_KV), OR_T_READ, 0, 0, 10, 0, out);          // current_tree, :361-368
+  }
+  void tt_answer(uint32_t e, uint16_t type, uint32_t code, uint64_t p1, std::vector<Emit>& out) {
+    TreeNode& t = eps[e].tn;
+    or_msg req; std::memset(&req, 0, sizeof req);
+    req.src = t.cur_src; req.dest = e; req.msg_id = t.cur_msg_id;
+    or_msg a = reply_to(req, type);
+    a.p0 = code; a.p1 = p1;
+    out.push_back(Emit(a));
+    t.phase = 0;                                                                  // the lock passes to the next waiter
+    if (!t.waiting.empty()) {
+      const or_msg next = t.waiting.front();
+      t.waiting.pop_front();
+      tt_start(e, next, out);
+    }
+  }
+  void tt_eval(uint32_t e, std::vector<Emit>& out) {
+    TreeNode& t = eps[e].tn;
+    TreeStore S{this, e};
+    uint32_t counter = t.start_counter, root2 = 0, load_ptr = 0;
+    const mst::Status st = mst::apply_txn(S, e, tt_per_node, t.root1, t.cur_ops, t.start_counter, counter, root2, load_ptr);
+    if (st == mst::kCapacity) { error = "hash tree: out of pointers / leaf or depth capacity"; return; }
+    if (st == mst::kNeedLoad) {                                                   // Tree.load, :83-101
+      t.phase = 2;
+      tt_rpc(e, svc_endpoint(OR_SVC_LWW_KV), OR_T_READ, load_ptr, 0, 11, load_ptr, out);
+      return;
+    }
+    t.ptr_counter = counter;
+    t.root2 = root2;
+    if (root2 == t.root1) { tt_answer(e, OR_T_TXN_OK, 0, (uint64_t)t.root1 | ((uint64_t)t.root1 << 32), out); return; }
+    uint32_t order[mst::kMaxWrites], n = 0;
+    if (!mst::save_order(S, e, tt_per_node, t.start_counter, root2, order, n)) { error = "hash tree: save walk too deep"; return; }
+    t.phase = 3; t.writes_left = n; t.write_failed = 0;
+    for (uint32_t i = 0; i < n; i++)                                              // save_this!, :128-145
+      tt_rpc(e, svc_endpoint(OR_SVC_LWW_KV), OR_T_WRITE, order[i], order[i], 12, order[i], out);
+  }
+  void node_txn_tree(uint32_t e, const or_msg& m, std::vector<Emit>& out) {
+    TreeNode& t = eps[e].tn;
+    RaftNode& r = eps[e].rn;
+    if (m.flags & OR_F_REPLY) {                                                  // node.rb:170-176
+      RaftCb& slot = r.callbacks[m.in_reply_to % cb_slots];
+      if (slot.kind == 0 || slot.msg_id != m.in_reply_to) return;                 // no callback
+      const RaftCb cb = slot;
+      slot.kind = 0;
+      or_msg init_req; std::memset(&init_req, 0, sizeof init_req);
+      init_req.src = t.init_src; init_req.dest = e; init_req.msg_id = t.init_msg_id;
+      switch (cb.kind) {
+        case 10:                                                                  // the root pointer
+          if (m.type == OR_T_READ_OK) { t.root1 = (uint32_t)m.p1; t.start_counter = t.ptr_counter; tt_eval(e, out); }
+          else tt_answer(e, OR_T_ERROR, 14, 0, out);                              // abort, :367
+          return;
+        case 11:                                                                  // a tree node
+          if (m.type == OR_T_READ_OK) { t.cache.insert(cb.node); tt_eval(e, out); }
+          else tt_rpc(e, svc_endpoint(OR_SVC_LWW_KV), OR_T_READ, cb.node, 0, 11, cb.node, out);   // retry, :97-99
+          return;
+        case 12:                                                                  // one of save!'s writes
+          if (m.type != OR_T_WRITE_OK) t.write_failed = 1;
+          if (--t.writes_left == 0) {
+            if (t.write_failed) { tt_answer(e, OR_T_ERROR, 14, 0, out); return; }  // "Couldn't save new tree"
+            t.phase = 4;                                                          // advance_root!, :372-379
+            tt_rpc(e, svc_endpoint(OR_SVC_LIN_KV), OR_T_CAS, 0, (uint64_t)t.root1 | ((uint64_t)t.root2 << 32), 13, 0, out);
+          }
+          return;
+        case 13:
+          if (m.type == OR_T_CAS_OK) tt_answer(e, OR_T_TXN_OK, 0, (uint64_t)t.root1 | ((uint64_t)t.root2 << 32), out);
+          else tt_answer(e, OR_T_ERROR, 30, 0, out);                              // txn_conflict, :378
+          return;
+        case 14:                                                                  // the first node's initial state, :330-338
+          if (m.type == OR_T_WRITE_OK) tt_rpc(e, svc_endpoint(OR_SVC_LIN_KV), OR_T_WRITE, 0, mst::kPtrEmpty, 15, 0, out);
+          else { or_msg er = reply_to(init_req, OR_T_ERROR); er.p0 = 14; out.push_back(Emit(er)); }
+          return;
+        case 15:
+          out.push_back(Emit(reply_to(init_req, OR_T_INIT_OK)));                  // node.rb:31
+          return;
+      }
+      return;
+    }
+    switch (m.type) {
+      case OR_T_INIT:                                                             // node.rb:22-36 + :329-338
+        if (e == 0) {                                                             // @node.node_ids.first == @node.node_id
+          t.init_src = m.src; t.init_msg_id = m.msg_id;
+          tt_rpc(e, svc_endpoint(OR_SVC_LWW_KV), OR_T_WRITE, mst::kPtrEmpty, mst::kPtrEmpty, 14, 0, out);
+        } else {
+          out.push_back(Emit(reply_to(m, OR_T_INIT_OK)));
+        }
+        return;
+      case OR_T_TXN:                                                              // :340-353
+        if (t.phase == 0) tt_start(e, m, out);
+        else t.waiting.push_back(m);
+        return;
+      default: {
+        or_msg er = reply_to(m, OR_T_ERROR);
+        er.p0 = 10;
+        out.push_back(Emit(er));
+        return;
+      }
+    }
+  }
+
   // ------------------------------------------------------------- txn-list-append (demo/clojure/single_key_txn.clj)
   // The whole database is one value under key "root" (key 0 here) of lin-kv (:134-141).  A
   // database value is carried as a version id (see oracle.h); apply-txn (:115-127) is a pure
@@ -1025,6 +1170,7 @@ struct or_sim {
             else if (cfg.workload == OR_W_GSET) node_gset(e, m, out);
             else if (cfg.workload == OR_W_RAFT) node_raft(e, m, out);
             else if (cfg.workload == OR_W_TXN) node_txn(e, m, out);
+            else if (cfg.workload == OR_W_TXN_TREE) node_txn_tree(e, m, out);
             else { error = "workload not implemented in oracle"; return false; }
         }
         if (!error.empty()) return false;
@@ -1051,6 +1197,8 @@ struct or_sim {
 
 extern "C" {
 
+uint32_t or_tree_key_hash(uint32_t key) { return mst::key_hash(key); }
+
 or_sim* or_create(const or_config* cfg) {
   or_sim* s = new or_sim();
   s->cfg = *cfg;
@@ -1060,8 +1208,14 @@ or_sim* or_create(const or_config* cfg) {
   s->eps.resize(cfg->n_nodes);
   if (s->cfg.rpc_table) { s->cb_slots = 1; while (s->cb_slots < s->cfg.rpc_table) s->cb_slots <<= 1; }
   if (s->cfg.raft_group >= s->cfg.n_nodes) s->cfg.raft_group = 0;
+  if (cfg->workload == OR_W_TXN_TREE) {
+    s->tt_per_node = s->cfg.tree_ptrs ? s->cfg.tree_ptrs : 256u;
+    s->tt_recs.assign(1 + (size_t)cfg->n_nodes * s->tt_per_node, mst::Rec{});
+    mst::Rec& empty = s->tt_recs[mst::kPtrEmpty - 1];                  // Tree.empty: a leaf over the whole ring
+    empty.type = 1; empty.lo = 0; empty.hi = (uint8_t)mst::kRing; empty.n = 0;
+  }
   for (uint32_t i = 0; i < cfg->n_nodes; i++) {
-    if (cfg->workload == OR_W_RAFT || cfg->workload == OR_W_TXN) s->eps[i].rn.callbacks.resize(s->cb_slots);
+    if (cfg->workload == OR_W_RAFT || cfg->workload == OR_W_TXN || cfg->workload == OR_W_TXN_TREE) s->eps[i].rn.callbacks.resize(s->cb_slots);
     s->eps[i].name = "n" + std::to_string(i);          // core.clj:231-238
     s->eps[i].kind = OR_KIND_SERVER;
     s->eps[i].neighbors = topology_neighbors(cfg->topology, cfg->n_nodes, i);

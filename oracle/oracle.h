@@ -84,11 +84,14 @@ typedef struct or_config {
   uint32_t raft_group;      /* servers per Raft cluster = node_ids of a node's init (raft.py:447-459): blocks of
                                raft_group consecutive servers; 0 = one cluster of all servers                  */
   uint32_t rpc_table;       /* pending-RPC closures kept per Raft / txn node (0 = 4096; the reference's dict is unbounded) */
+  uint32_t tree_ptrs;       /* OR_W_TXN_TREE: pointers a node may mint (0 = 256); pointer "n<e>-<p>" = 2 + e * tree_ptrs + (p - 1) */
 } or_config;
 
 enum { OR_W_ECHO = 0, OR_W_BROADCAST = 1, OR_W_GSET = 2,
        OR_W_RAFT = 3,     /* lin-kv workload served by Raft nodes (demo/python/raft.py) */
-       OR_W_TXN = 4 };    /* txn-list-append, whole database in one lin-kv key (demo/clojure/single_key_txn.clj) */
+       OR_W_TXN = 4,      /* txn-list-append, whole database in one lin-kv key (demo/clojure/single_key_txn.clj) */
+       OR_W_TXN_TREE = 5 };  /* txn-list-append on a persistent hash tree in lww-kv + a root pointer in lin-kv
+                                (demo/ruby/datomic_list_append.rb); tree arithmetic: maelstrom_b200/csrc/ms_tree.h */
 enum { OR_TOPO_GRID = 0, OR_TOPO_LINE = 1, OR_TOPO_TOTAL = 2,
        OR_TOPO_TREE2 = 3, OR_TOPO_TREE3 = 4, OR_TOPO_TREE4 = 5 };
 enum { OR_DIST_CONSTANT = 0, OR_DIST_UNIFORM = 1, OR_DIST_EXPONENTIAL = 2 };
@@ -122,6 +125,8 @@ enum { OR_F_MSG_ID = 1, OR_F_REPLY = 2, OR_F_CREATE = 4 /* cas create_if_not_exi
 typedef struct or_sim or_sim;
 
 or_sim*  or_create(const or_config* cfg);
+/* Tree.hash of demo/ruby/datomic_list_append.rb:59-61 as ms_tree.h computes it (known-answer tests) */
+uint32_t or_tree_key_hash(uint32_t key);
 void     or_destroy(or_sim*);
 const char* or_last_error(or_sim*);
 

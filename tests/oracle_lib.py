@@ -25,7 +25,7 @@ OP_DTYPE = np.dtype([("time_ns", "<i8"), ("src", "<u4"), ("dest", "<u4"), ("body
 assert MSG_DTYPE.itemsize == 48 and EVENT_DTYPE.itemsize == 32
 assert BODY_DTYPE.itemsize == 24 and OP_DTYPE.itemsize == 40
 
-W_ECHO, W_BROADCAST, W_GSET, W_RAFT, W_TXN = 0, 1, 2, 3, 4
+W_ECHO, W_BROADCAST, W_GSET, W_RAFT, W_TXN, W_TXN_TREE = 0, 1, 2, 3, 4, 5
 TOPO = {"grid": 0, "line": 1, "total": 2, "tree": 3, "tree2": 3, "tree3": 4, "tree4": 5}
 DIST = {"constant": 0, "uniform": 1, "exponential": 2}
 KIND_SERVER, KIND_CLIENT, KIND_HOST, KIND_SIM_CLIENT, KIND_SERVICE, KIND_GEN_CLIENT = 0, 1, 2, 3, 4, 5
@@ -51,7 +51,7 @@ class Config(C.Structure):
                 ("latency_dist", C.c_uint32), ("latency_mean_ms", C.c_uint32),
                 ("seed_lo", C.c_uint32), ("seed_hi", C.c_uint32), ("p_loss", C.c_double),
                 ("n_values", C.c_uint32), ("gset_interval_ms", C.c_uint32),
-                ("raft_group", C.c_uint32), ("rpc_table", C.c_uint32)]
+                ("raft_group", C.c_uint32), ("rpc_table", C.c_uint32), ("tree_ptrs", C.c_uint32)]
 
 
 class Body(C.Structure):
@@ -74,6 +74,8 @@ def lib():
             build()
         L = C.CDLL(_SO)
         L.or_create.restype = C.c_void_p
+        L.or_tree_key_hash.restype = C.c_uint32
+        L.or_tree_key_hash.argtypes = [C.c_uint32]
         L.or_create.argtypes = [C.POINTER(Config)]
         L.or_destroy.argtypes = [C.c_void_p]
         L.or_last_error.restype = C.c_char_p
@@ -164,7 +166,7 @@ class Sim:
 
     def __init__(self, n_nodes, workload=W_BROADCAST, topology="grid", latency_dist="constant",
                  latency_mean_ms=0, seed=0x4D41454C, p_loss=0.0, n_values=1 << 16, gset_interval_ms=5000,
-                 raft_group=0, rpc_table=0):
+                 raft_group=0, rpc_table=0, tree_ptrs=0):
         cfg = Config()
         cfg.n_nodes = n_nodes
         cfg.workload = workload
@@ -178,6 +180,7 @@ class Sim:
         cfg.gset_interval_ms = gset_interval_ms
         cfg.raft_group = raft_group
         cfg.rpc_table = rpc_table
+        cfg.tree_ptrs = tree_ptrs
         self.L = lib()
         self.h = self.L.or_create(C.byref(cfg))
         self.n_nodes = n_nodes

@@ -14,7 +14,8 @@ def make_pair(n_nodes, **kw):
         "n_keys", "raft_log_cap", "history_rounds", "server_ring_cap", "server_max_window")}
     workload = kw.pop("workload", "broadcast")
     g = mb.Sim(n_nodes, workload=workload, **kw, **sizing)
-    o = O.Sim(n_nodes, workload={"echo": O.W_ECHO, "broadcast": O.W_BROADCAST, "g-set": O.W_GSET, "lin-kv": O.W_RAFT, "txn-list-append": O.W_TXN}[workload], **kw)
+    o = O.Sim(n_nodes, workload={"echo": O.W_ECHO, "broadcast": O.W_BROADCAST, "g-set": O.W_GSET, "lin-kv": O.W_RAFT, "txn-list-append": O.W_TXN,
+                                 "txn-list-append-tree": O.W_TXN_TREE}[workload], **kw)
     return g, o
 
 
