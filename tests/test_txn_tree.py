@@ -142,3 +142,39 @@ def test_txn_tree_many_nodes_vs_oracle(engine_backend):
     sends = (ev["event_id"] >> np.uint64(63)) == 0
     assert int(((bd["type"] == O.T["txn_ok"]) & sends).sum()) > 300
     assert int(((bd["type"] == O.T["error"]) & sends & (ev["src"] < n) & (bd["p0"] == 30)).sum()) > 300
+
+
+def tree_seeds():
+    import os
+    a, b = (int(x) for x in os.environ.get("MS_FUZZ_TREE_SEEDS", "0:4").split(":"))
+    return list(range(a, b))
+
+
+@pytest.mark.parametrize("seed", tree_seeds())
+def test_txn_tree_random_scenarios(engine_backend, seed):
+    # seeded: node count, latency law, key universe (few keys = deep splits of one hash range, many = wide trees),
+    # request rate (queueing behind the txn lock), clients; journal equal to the oracle's
+    rng = np.random.default_rng(7000 + seed)
+    n = int(rng.integers(1, 20))
+    dist = ("constant", "constant", "uniform")[int(rng.integers(3))]
+    mean = 0 if dist == "constant" and rng.integers(2) else 1                 # (virtual seconds are slow on the emulator)
+    n_keys = int(rng.choice([6, 30, 150, 2000]))
+    per_tick = int(rng.integers(1, 7))
+    n_clients = int(rng.integers(1, 5))
+    g, o = make_pair(n, workload="txn-list-append-tree", latency_dist=dist, latency_mean_ms=mean, max_endpoints=n + 16,
+                     ring_cap=2048, max_window=1024, server_ring_cap=512, server_max_window=128, rpc_table=512,
+                     tree_ptrs=8192, journal_cap_log2=21, calendar_slots=32, calendar_cap=8192, seed=int(rng.integers(1 << 40)))
+
+    def scenario(s, body):
+        s.add_endpoint("lin-kv", O.KIND_SERVICE)
+        s.add_endpoint("lww-kv", O.KIND_SERVICE)
+        cs = [s.add_endpoint("c%d" % i, O.KIND_SIM_CLIENT) for i in range(n_clients)]
+        s.schedule(ops_array([(0, cs[i % n_clients], i, "init", 1 + i // n_clients, 0) for i in range(n)]))
+        r2 = np.random.default_rng(seed)
+        s.schedule(txn_ops(r2, n, cs, 30, 25, per_tick, n_keys, [100] * n_clients))
+        s.run((300 + 1200 * mean) * 1_000_000)
+        return s.client_replies()
+
+    rg, ro = both(g, o, scenario)
+    assert rg == ro and rg > n
+    assert_same_journal(g, o)
