@@ -18,7 +18,7 @@
            (java.nio ByteBuffer ByteOrder)))
 
 ;; ---------------------------------------------------------------- records (include/maelstrom_b200.h)
-(def workloads {:echo 0 :broadcast 1 :g-set 2 :lin-kv 3 :txn-list-append 4})
+(def workloads {:echo 0 :broadcast 1 :g-set 2 :lin-kv 3 :txn-list-append 4 :txn-list-append-tree 5})
 (def topologies {:grid 0 :line 1 :total 2 :tree 3 :tree2 3 :tree3 4 :tree4 5})
 (def dists {:constant 0 :uniform 1 :exponential 2})
 (def kinds {:client 1 :host 2 :sim-client 3 :service 4})

@@ -254,7 +254,7 @@ struct RaftDev {
 };
 
 // MS_W_TXN_TREE node (demo/ruby/datomic_list_append.rb DatomicListAppendNode, :322-417)
-constexpr uint32_t kTreeQueue = 64;
+constexpr uint32_t kTreeQueue = 256;     // txn requests that can wait for one node's @txn_lock (more = capacity error)
 struct TreeDev {
   uint32_t ptr_counter;                // @ptr (:355-358)
   uint32_t phase;                      // 0 idle, 1 root read out, 2 tree node read out, 3 writes out, 4 cas out

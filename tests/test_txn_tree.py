@@ -159,7 +159,7 @@ def test_txn_tree_random_scenarios(engine_backend, seed):
     dist = ("constant", "constant", "uniform")[int(rng.integers(3))]
     mean = 0 if dist == "constant" and rng.integers(2) else 1                 # (virtual seconds are slow on the emulator)
     n_keys = int(rng.choice([6, 30, 150, 2000]))
-    per_tick = int(rng.integers(1, 7))
+    per_tick = min(int(rng.integers(1, 7)), 2 * n)                              # (256 requests may wait for a node's txn lock)
     n_clients = int(rng.integers(1, 5))
     g, o = make_pair(n, workload="txn-list-append-tree", latency_dist=dist, latency_mean_ms=mean, max_endpoints=n + 16,
                      ring_cap=2048, max_window=1024, server_ring_cap=512, server_max_window=128, rpc_table=512,

@@ -25,20 +25,31 @@ rows = sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]
 for (f, l), a in rows:
     print("%5.2f%% inst %5.2f%% smp  thr/inst %4.1f  %s:%d  %s" % (100.0 * a[0] / tot_i, 100.0 * a[2] / max(tot_s, 1), a[1] / max(a[0], 1), f, l, a[3].strip()[:110]))
 
-# phase buckets of ms_kernels.cu (line ranges of the current tree; adjust when the file moves)
+# phase buckets of ms_kernels.cu: line ranges found from marker comments in the current source
 if len(sys.argv) > 3 and sys.argv[3] == "phases":
-    B = [(35, 146, "helpers (st_v4, rec, ring_slot, dense_base)"), (147, 207, "block scan / bitonic"), (208, 234, "journal_raw"),
-         (235, 291, "wheel"), (292, 362, "emit_one"), (626, 746, "node programs"), (747, 878, "commit"), (1040, 1130, "small scans"),
-         (1220, 1318, "prologue + ticket fetch"), (1319, 1362, "injector"), (1363, 1390, "endpoint setup"), (1391, 1473, "PA1 load"),
-         (1474, 1493, "PA2 seen test"), (1494, 1592, "PB ordering"), (1593, 1625, "PC first-sight insert"), (1626, 1726, "seq families"),
-         (1727, 1774, "winners + counts"), (1775, 1850, "scan + gset"), (1851, 1925, "PD claims"), (1926, 1964, "PE1 recv records"),
-         (1965, 1975, "own_map"), (1976, 2094, "PE2 emissions"), (2095, 2143, "epilogue")]
+    import os
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "maelstrom_b200", "csrc", "ms_kernels.cu")).read().split("\n")
+    marks = [("helpers (st_v4, rec, ring_slot, dense_base)", "namespace msd {"), ("block scan / bitonic", "__device__ uint64_t block_excl_scan("),
+             ("emit ctx / journal_raw", "struct EmitCtx {"), ("wheel", "timing wheel (pooled chains)"), ("emit_one", "void emit_one("),
+             ("gen clients / barrier / snapshot / release", "closed-loop clients (MS_KIND_GEN_CLIENT)"), ("node programs", "// ------------------------------------------------------------------ node programs"),
+             ("commit", "// ------------------------------------------------------------------ round commit"), ("small scans + services", "emit_count_meta(uint32_t workload"),
+             ("prologue + ticket fetch", "template <int CLS, int WL, bool FIX = false>"), ("injector", "injector slice"), ("endpoint setup", "endpoint CTA"),
+             ("PA1 load", "// PA1:"), ("PA2 seen test", "// PA2:"), ("PB ordering", "// PB:"), ("PC first-sight insert", "// PC:"),
+             ("seq families / services", "Raft / txn-list-append node: the step is sequential"), ("winners + counts", "resolve winners and publish packed counts"),
+             ("scan + gset", "const uint64_t tot = block_excl_scan(aux"), ("PD claims", "// PD:"), ("PE1 recv records", "// PE1:"), ("PE2 emissions", "// PE2:"),
+             ("epilogue", "ticket epilogue"), ("journal kernels", "k_journal_expand (K3)")]
+    B = []
+    for name, needle in marks:
+        ln = next((i + 1 for i, l in enumerate(src) if needle in l), None)
+        if ln: B.append([ln, name])
+    B.sort()
     ph = collections.defaultdict(lambda: [0, 0])
     for (f, l), a in agg.items():
         name = "other:" + f
         if f == "ms_kernels.cu":
-            for lo, hi, nm in B:
-                if lo <= l <= hi: name = nm; break
+            name = "other:ms_kernels.cu"
+            for lo, nm in B:
+                if l >= lo: name = nm
         ph[name][0] += a[0]; ph[name][1] += a[2]
     print("==== phases")
     for nm, a in sorted(ph.items(), key=lambda kv: -kv[1][0]):
