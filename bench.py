@@ -864,7 +864,7 @@ def main():
     ap.add_argument("--verify", action="store_true", help="sharded parity digest (on by default when --gpus > 1)")
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--phase-cycles", action="store_true", help="diagnostic: per-phase cycles per ticket on stderr; not a bench run")
+    ap.add_argument("--phase-cycles", action="store_true", help="diagnostic: per-phase cycles per ticket on stderr; needs a -DMS_PHASE_TIMING build (MS_B200_LIB=...); not a bench run")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

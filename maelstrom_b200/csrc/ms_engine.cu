@@ -1978,6 +1978,9 @@ int ms_profile(ms_sim* s, int enable) {
 
 int ms_debug_phase_cycles(ms_sim* s, int enable, uint64_t out[64]) {
   std::lock_guard<std::mutex> g(s->mu);
+#ifndef MS_PHASE_TIMING
+  if (enable) { set_err("this library was built without -DMS_PHASE_TIMING (the per-phase clock reads are compiled out of the product kernels)"); return MS_ERR_ARG; }
+#endif
   cudaSetDevice(s->device);
   if (enable && !s->P.phase_cycles) {
     int rc = s->dalloc(&s->P.phase_cycles, 512);

@@ -1360,8 +1360,13 @@ __global__ void __launch_bounds__(CLS == 3 ? 512 : 256, CLS == 3 ? 2 : MS_ROUND_
   // with no loss and a constant latency nothing depends on the random draw: skip Philox
   const bool need_rng = np.loss_thresh != 0 || np.dist != MS_DIST_CONSTANT;
   const uint64_t const_lat = (uint64_t)np.mean_ms * np.scale;
-  // optional per-phase cycle accounting (diagnostic, ms_debug_phase_cycles)
+  // optional per-phase cycle accounting (diagnostic, ms_debug_phase_cycles): only in builds with -DMS_PHASE_TIMING
+  // (__graft_entry__.build_variant("timing", ["MS_PHASE_TIMING"])); the product library carries none of it
+#ifdef MS_PHASE_TIMING
   const bool timing = p.phase_cycles != nullptr;
+#else
+  constexpr bool timing = false;
+#endif
   long long t_prev = timing ? clock64() : 0;
 #define PHASE_MARK(k)                                                                         \
   do {                                                                                        \

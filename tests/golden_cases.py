@@ -107,6 +107,40 @@ def _txn_three_nodes(s, body):
     s.run(40_000_000)
 
 
+def _txn_tree_four_nodes(s, body):
+    # datomic_list_append.rb: inits (the first node writes the empty tree and the root), then 90 txns of 1-3
+    # micro-ops on 24 keys: leaves split, paths are copied, roots collide
+    s.add_endpoint("lin-kv", O.KIND_SERVICE)
+    s.add_endpoint("lww-kv", O.KIND_SERVICE)
+    cs = [s.add_endpoint("c%d" % i, O.KIND_SIM_CLIENT) for i in range(3)]
+    rows = np.zeros(4 + 90, dtype=O.OP_DTYPE)
+    for i in range(4):
+        r = rows[i]
+        r["time_ns"] = 0
+        r["src"] = cs[i % 3]
+        r["dest"] = i
+        r["body"]["type"] = O.T["init"]
+        r["body"]["flags"] = O.F_MSG_ID
+        r["body"]["msg_id"] = 1 + i
+    for k in range(90):
+        r = rows[4 + k]
+        r["time_ns"] = (20 + k // 3) * 1_000_000
+        r["src"] = cs[k % 3]
+        r["dest"] = (k * 5) % 4
+        b = r["body"]
+        b["type"] = O.T["txn"]
+        b["flags"] = O.F_MSG_ID
+        b["msg_id"] = 100 + k
+        b["p0"] = k
+        w = 0
+        for j in range(1 + k % 3):
+            key = (k * 7 + j * 11) % 24
+            w |= (0x8000 | (0 if (k + j) % 4 == 0 else 0x4000) | key) << (16 * j)
+        b["p1"] = w
+    s.schedule(rows)
+    s.run(400_000_000)
+
+
 def _raft_three_nodes(s, body):
     cs = [s.add_endpoint("c%d" % i, O.KIND_SIM_CLIENT) for i in range(2)]
     for i in range(3):
@@ -137,13 +171,15 @@ CASES = {
     "txn_three_nodes": (dict(n_nodes=3, workload="txn-list-append", latency_dist="constant", latency_mean_ms=1),
                         _txn_three_nodes),
     "raft_three_nodes": (dict(n_nodes=3, workload="lin-kv"), _raft_three_nodes),
+    "txn_tree_four_nodes": (dict(n_nodes=4, workload="txn-list-append-tree", latency_dist="constant", latency_mean_ms=1),
+                            _txn_tree_four_nodes),
 }
 # cases checked against the engine by tests/test_golden_fixtures.py; the others by their workload's test file
 CORE_CASES = ("flood_grid25", "echo_12_ops", "latency_loss_partition")
 ENGINE_SIZING = dict(ring_cap=256, max_window=256, journal_cap_log2=18, max_endpoints=64,
                      calendar_slots=1024, calendar_cap=2048)
 W = {"echo": O.W_ECHO, "broadcast": O.W_BROADCAST, "g-set": O.W_GSET, "lin-kv": O.W_RAFT,
-     "txn-list-append": O.W_TXN}
+     "txn-list-append": O.W_TXN, "txn-list-append-tree": O.W_TXN_TREE}
 
 
 def make_oracle(name):

@@ -178,3 +178,9 @@ def test_txn_tree_random_scenarios(engine_backend, seed):
     rg, ro = both(g, o, scenario)
     assert rg == ro and rg > n
     assert_same_journal(g, o)
+
+
+def test_committed_golden_journal(engine_backend):
+    # tests/golden/journals.json["txn_tree_four_nodes"], generated from the oracle (tests/golden/make_golden.py)
+    import golden_cases as G
+    G.check_engine_against_fixture("txn_tree_four_nodes")
