@@ -419,13 +419,101 @@ class Txn256k(Workload):
         return s.stats()["all"]["recv-count"], dt, "txn-list-append %d nodes, 256 txns/tick x %d ticks" % (n, steps * w.step_ticks)
 
 
+class TxnTree(Txn256k):
+    """txn-list-append on the persistent hash tree (demo/ruby/datomic_list_append.rb): tree nodes in lww-kv, the root
+    pointer in lin-kv; 1-4 micro-ops per txn on a sliding window of keys.  Not a BASELINE config: a timing of the
+    MS_W_TXN_TREE node program at a size that fits one GPU's tree-record table."""
+    name = "txntree"
+
+    def __init__(self, args):
+        Txn256k.__init__(self, args)
+        self.n_nodes = args.nodes or 16384
+        self.txns_per_tick = getattr(args, "ops_per_tick", 0) or 256
+        self.ramp_steps = 1                      # step 0 carries the inits (the first node writes the empty tree and the root)
+        self.label = "txn-list-append on a persistent hash tree, %d nodes, lww-kv + lin-kv (datomic_list_append.rb)" % self.n_nodes
+
+    def sim_kwargs(self, n_steps, journal_discard):
+        n = self.n_nodes
+        return dict(workload="txn-list-append-tree", topology="grid", latency_dist="constant", latency_mean_ms=0, seed=SEED,
+                    max_endpoints=n + self.n_clients + 4, ring_cap=8192, max_window=4096,
+                    server_ring_cap=64, server_max_window=32, rpc_table=64, tree_ptrs=1024, tree_cache=2048,
+                    journal_level=1, journal_discard=1 if journal_discard else 0, journal_cap_log2=24)
+
+    def setup(self, sim, types):
+        from maelstrom_b200.engine import KIND_SERVICE
+        sim.add_endpoint("lin-kv", KIND_SERVICE)
+        sim.add_endpoint("lww-kv", KIND_SERVICE)
+        return Workload.setup(self, sim, types)
+
+    def prologue_ops(self, op_dtype, c0, types, flags):
+        n = self.n_nodes
+        ops = np.zeros(n, dtype=op_dtype)
+        i = np.arange(n, dtype=np.uint64)
+        ops["src"] = (c0 + (i % np.uint64(self.n_clients))).astype(np.uint32)
+        ops["dest"] = i.astype(np.uint32)
+        ops["body"]["type"] = types["init"]
+        ops["body"]["flags"] = flags["msg_id"]
+        ops["body"]["msg_id"] = (i // np.uint64(self.n_clients) + np.uint64(1)).astype(np.uint32)
+        return ops
+
+    def ops(self, op_dtype, first_step, n_steps, c0, types, flags):
+        per_tick = self.txns_per_tick
+        first_tick = max(first_step * self.step_ticks, self.step_ticks)          # clients start after the init step
+        n_ticks = (first_step + n_steps) * self.step_ticks - first_tick
+        if n_ticks <= 0:
+            return np.zeros(0, dtype=op_dtype)
+        n = n_ticks * per_tick
+        ops = np.zeros(n, dtype=op_dtype)
+        g = np.arange(n, dtype=np.uint64) + np.uint64(first_tick * per_tick)
+        r = philox_u32(n, 6, offset=first_tick * per_tick)
+        ops["time_ns"] = ((g // np.uint64(per_tick)) * np.uint64(TICK_NS)).astype(np.int64)
+        ops["src"] = (c0 + (g % np.uint64(self.n_clients))).astype(np.uint32)
+        ops["dest"] = (r % np.uint64(self.n_nodes)).astype(np.uint32)
+        ops["body"]["type"] = types["txn"]
+        ops["body"]["flags"] = flags["msg_id"]
+        ops["body"]["msg_id"] = (g // np.uint64(self.n_clients) + np.uint64(1000)).astype(np.uint32)
+        ops["body"]["p0"] = (g & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+        # 1-4 micro-ops, 2 of 3 appends, keys from a window of 64 that slides with time (Jepsen retires keys as it goes)
+        base = (g // np.uint64(per_tick * 64)) * np.uint64(16)
+        w = np.zeros(n, dtype=np.uint64)
+        n_ops = np.uint64(1) + (r >> np.uint64(8)) % np.uint64(4)
+        for j in range(4):
+            rj = philox_u32(n, 7 + j, offset=first_tick * per_tick)
+            key = (base + rj % np.uint64(64)) % np.uint64(16384)
+            app = np.where((rj >> np.uint64(16)) % np.uint64(3) > 0, np.uint64(0x4000), np.uint64(0))
+            w |= np.where(n_ops > np.uint64(j), (np.uint64(0x8000) | app | key) << np.uint64(16 * j), np.uint64(0))
+        ops["body"]["p1"] = w
+        return ops
+
+    def config_extra(self):
+        return {"latency": "constant 0 ms", "txns_per_tick": self.txns_per_tick, "step": "%d virtual ms" % self.step_ticks,
+                "l2_policy": "tree records 0.5 GB + per-node caches and closure tables + lww-kv replicas: larger than L2"}
+
+    def cpu_sample(self, O, scale, seed):
+        n = 1024
+        s = O.Sim(n, workload=O.W_TXN_TREE, seed=seed, rpc_table=64, tree_ptrs=512)
+        s.add_endpoint("lin-kv", O.KIND_SERVICE)
+        s.add_endpoint("lww-kv", O.KIND_SERVICE)
+        cs = [s.add_endpoint("c%d" % i, O.KIND_SIM_CLIENT) for i in range(8)]
+        w = TxnTree(self.args)
+        w.n_nodes, w.n_clients, w.txns_per_tick = n, 8, 64
+        steps = max(1, int(scale))
+        flags = {"msg_id": O.F_MSG_ID, "appends": O.F_APPENDS}
+        s.schedule(w.prologue_ops(O.OP_DTYPE, cs[0], O.T, flags))
+        s.schedule(w.ops(O.OP_DTYPE, 0, steps + 1, cs[0], O.T, flags))
+        t0 = time.perf_counter()
+        s.run(((steps + 1) * w.step_ticks + 2) * TICK_NS)
+        dt = time.perf_counter() - t0
+        return s.stats()["all"]["recv-count"], dt, "hash-tree txn-list-append %d nodes, 64 txns/tick x %d ticks" % (n, (steps + 1) * w.step_ticks)
+
+
 def make_workload(args):
     c = args.config
     if c == "broadcast":
         return Broadcast(args, args.latency_ms)
     if c == "broadcast-lat1":
         return Broadcast(args, 1)
-    return {"gset16k": GSet16k, "raft64k": Raft64k, "txn256k": Txn256k}[c](args)
+    return {"gset16k": GSet16k, "raft64k": Raft64k, "txn256k": Txn256k, "txntree": TxnTree}[c](args)
 
 
 # --------------------------------------------------------------------------- clocks
@@ -848,7 +936,7 @@ def main():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="broadcast", choices=["broadcast", "broadcast-lat1", "gset16k", "raft64k", "txn256k"])
+    ap.add_argument("--config", default="broadcast", choices=["broadcast", "broadcast-lat1", "gset16k", "raft64k", "txn256k", "txntree"])
     ap.add_argument("--values-per-tick", type=int, default=0)
     ap.add_argument("--latency-ms", type=int, default=0)
     ap.add_argument("--nodes", type=int, default=0, help="override the node count of gset16k / raft64k / txn256k")
