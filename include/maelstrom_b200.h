@@ -115,7 +115,7 @@ enum { MS_W_ECHO = 0, MS_W_BROADCAST = 1, MS_W_GSET = 2,                     /* 
                              apply_txn over the chain of roots).  Pointer "n<e>-<p>" = 2 + e * reserved[3] + (p - 1), "empty" = 1;
                              ms_config.reserved[3] = pointers a node may mint (default 256), reserved[4] = tree nodes a node
                              may cache (default 1024), reserved[2] (service keys) defaults to cover every pointer.
-                             Promise time-outs (promise.rb, 5 s) are not modelled: p_loss must be 0. */
+                             A sync RPC without a reply times out after 5 s (promise.rb): error 0 to the client. */
        MS_W_TXN = 4 };   /* txn-list-append, whole database in one lin-kv key (demo/clojure/single_key_txn.clj);
                             needs the "lin-kv" service endpoint */
 enum { MS_TOPO_GRID = 0, MS_TOPO_LINE = 1, MS_TOPO_TOTAL = 2,                /* --topology, broadcast.clj:169-178 */

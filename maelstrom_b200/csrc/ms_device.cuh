@@ -263,7 +263,13 @@ struct TreeDev {
   uint32_t root1, root2, start_counter, writes_left, write_failed, load_ptr;
   uint32_t q_head, q_tail;             // requests waiting for the lock
   uint32_t init_src, init_msg_id;      // the init request (first node: answered after the initial state is written)
+  uint32_t init_phase;                 // 0 none, 1 the empty tree's write is out, 2 the root's write is out
+  uint32_t gen;                        // transactions finished: a reply that belongs to an earlier one finds nobody waiting
+  uint32_t first_write, first_write_ok, root_is_leaf;   // save!: tasks[0] and whether it was delivered; Leaf#save! vs Branch#save!
+  uint32_t pad;
+  int64_t  deadline, init_deadline;    // Promise#await gives up after 5 s (promise.rb:6,24-31); 0 = nobody waits
 };
+constexpr int64_t kPromiseTimeoutNs = 5000000000ll;
 
 // closed-loop client (maelstrom.client + a Jepsen worker), one per MS_KIND_GEN_CLIENT endpoint
 struct GenDev {

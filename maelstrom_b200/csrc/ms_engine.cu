@@ -706,7 +706,6 @@ static int build_sim(ms_sim* s, const ms_config* in) {
   P.family = c.workload == MS_W_GSET ? 1u : (c.workload >= MS_W_RAFT ? 4u : 0u);
   if (c.workload == MS_W_TXN_TREE) {
     // hash-tree txn-list-append (csrc/ms_tree.h): tree node records by pointer, per-node cache, lock queue
-    if (c.p_loss > 0.0) { set_err("MS_W_TXN_TREE: promise time-outs are not modelled, p_loss must be 0"); return MS_ERR_ARG; }
     if (c.n_shards > 1) { set_err("MS_W_TXN_TREE runs on one GPU (tree records are read across nodes)"); return MS_ERR_ARG; }
     const size_t N = c.n_nodes;
     P.tt_per_node = c.reserved[3] ? c.reserved[3] : 256u;

@@ -558,7 +558,8 @@ __device__ void snapshot_endpoints(const Params& p, DevState* st, uint32_t gid, 
     // Raft: a node whose election / step-down / replication timers are due acts on an empty window too
     const bool timer_due = e < p.n_servers && p.kind[e] == MS_KIND_SERVER &&
                            ((p.workload == MS_W_GSET && p.gs_init[e] && st->now >= p.gs_next_fire[e]) ||
-                            (p.workload == MS_W_RAFT && rf_timer_due(p.rf_node[e], st->now)));
+                            (p.workload == MS_W_RAFT && rf_timer_due(p.rf_node[e], st->now)) ||
+                            (p.workload == MS_W_TXN_TREE && tt_timer_due(p.tt_node[e], st->now)));
     const bool gen_due = p.gc && p.kind[e] == MS_KIND_GEN_CLIENT && gen_timer_due(p, p.gc[e], st->now);
     if (n == 0 && !timer_due && !gen_due) {
       // nothing to receive, hence nothing to emit: the ticket is finished right here
@@ -1772,6 +1773,7 @@ __global__ void __launch_bounds__(CLS == 3 ? 512 : 256, CLS == 3 ? 2 : MS_ROUND_
             else txn_handle(c, rec_unpack(rp[0], rp[1], rp[2]));
           }
           if (p.workload == MS_W_RAFT) { rf_actions(c); rf_note_busy(c); }
+          if (p.workload == MS_W_TXN_TREE) tt_actions(c);
           s_misc[2] = c.n_stage;
         }
         __syncthreads();

@@ -474,7 +474,12 @@ __device__ void txn_handle(RaftCtx& c, const Rec& m) {
 // root from the pointer read to the new one: cas_ok -> txn_ok, anything else -> error 30.  A root that cannot
 // be read is error 14 (abort, :361-368).  sync_rpc! is a blocked thread in the reference; here the node is a
 // state machine and the blocked evaluation is redone after every load (same result, see ms_tree.h).
-// Promise time-outs (promise.rb) are not modelled (ms_create refuses p_loss > 0 for this workload).
+// Promise#await gives up after 5 s (promise.rb): a sync_rpc! that gets no reply raises RPCError.timeout, which the
+// handler thread turns into an error 0 reply (node.rb:187-189) and which releases the lock.  save! of a Branch waits in
+// a helper thread that turns a time-out into "false" (:297-309) while the handler waits 5 s for that verdict itself:
+// if the first write is still unanswered when both clocks run out the helper's "false" is taken to arrive first
+// (error 14, "Couldn't save new tree"), otherwise the handler's own time-out does (error 0).  A reply that arrives
+// after its waiter gave up finds a dead promise: ignored.
 struct TreeStore {
   const Params& p;
   uint32_t e;
@@ -504,7 +509,7 @@ __device__ void tt_rpc(RaftCtx& c, uint32_t dest, uint32_t type, uint32_t p0, ui
   if (dest == 0xFFFFFFFFu) { latch_error(c.st, E_INVALID_DEST, dest); return; }   // the workload needs lin-kv and lww-kv
   const uint32_t id = ++c.r->next_msg_id;
   uint4* slot = c.cb + 2 * (size_t)(id & c.p.rf_cb_mask);
-  slot[0] = make_uint4(id, kind, arg, 0u);
+  slot[0] = make_uint4(id, kind, arg, c.p.tt_node[c.e].gen);
   slot[1] = make_uint4(0u, 0u, 0u, 0u);
   Rec r;
   r.round = 0; r.ticket = 0; r.idx = 0;
@@ -518,6 +523,8 @@ __device__ void tt_start(RaftCtx& c, TreeDev* t, uint32_t src, uint32_t msg_id, 
 
 __device__ void tt_finish(RaftCtx& c, TreeDev* t) {                               // @txn_lock released: the next waiter runs
   t->phase = 0;
+  t->deadline = 0;
+  t->gen++;
   if (t->q_head != t->q_tail) {
     const uint4 q = c.p.tt_queue[(size_t)c.e * kTreeQueue + (t->q_head % kTreeQueue)];
     t->q_head++;
@@ -538,6 +545,7 @@ __device__ void tt_answer(RaftCtx& c, TreeDev* t, uint32_t type, uint32_t code, 
 __device__ void tt_start(RaftCtx& c, TreeDev* t, uint32_t src, uint32_t msg_id, uint64_t ops) {
   t->cur_src = src; t->cur_msg_id = msg_id; t->cur_ops = ops;
   t->phase = 1;
+  t->deadline = c.now + kPromiseTimeoutNs;
   tt_rpc(c, c.p.sv_ep[MS_SVC_LIN_KV], MS_T_READ, 0u, 0ull, 10u, 0u);             // current_tree, :361-368
 }
 
@@ -549,6 +557,7 @@ __device__ void tt_eval(RaftCtx& c, TreeDev* t) {
   if (st == mst::kCapacity) { latch_error(c.st, E_RAFT_CAPACITY, c.e); return; }
   if (st == mst::kNeedLoad) {                                                     // Tree.load, :83-101
     t->phase = 2; t->load_ptr = load_ptr;
+    t->deadline = c.now + kPromiseTimeoutNs;
     tt_rpc(c, c.p.sv_ep[MS_SVC_LWW_KV], MS_T_READ, load_ptr, 0ull, 11u, load_ptr);
     return;
   }
@@ -561,6 +570,8 @@ __device__ void tt_eval(RaftCtx& c, TreeDev* t) {
   uint32_t out[mst::kMaxWrites], n = 0;
   if (!mst::save_order(S, c.e, c.p.tt_per_node, t->start_counter, root2, out, n)) { latch_error(c.st, E_RAFT_CAPACITY, c.e); return; }
   t->phase = 3; t->writes_left = n; t->write_failed = 0;
+  t->deadline = c.now + kPromiseTimeoutNs;
+  t->first_write = out[0]; t->first_write_ok = 0; t->root_is_leaf = S.rec(root2)->type == 1 ? 1u : 0u;
   for (uint32_t i = 0; i < n; i++)                                                // save_this!, :128-145: value = the node's JSON
     tt_rpc(c, c.p.sv_ep[MS_SVC_LWW_KV], MS_T_WRITE, out[i], (uint64_t)out[i], 12u, out[i]);
 }
@@ -573,6 +584,8 @@ __device__ void tt_handle(RaftCtx& c, const Rec& m) {
     const uint4 s0 = slot[0];
     if (s0.y == 0 || s0.x != m.in_reply_to) return;                               // "Ignoring reply ... with no callback"
     slot[0] = make_uint4(0u, 0u, 0u, 0u);
+    if (s0.y >= 10 && s0.y <= 13 && (s0.w != t->gen || t->phase == 0)) return;    // its transaction is over: a dead promise
+    if ((s0.y == 14 && t->init_phase != 1) || (s0.y == 15 && t->init_phase != 2)) return;
     switch (s0.y) {
       case 10:                                                                    // the root pointer
         if (type == MS_T_READ_OK) {
@@ -588,14 +601,17 @@ __device__ void tt_handle(RaftCtx& c, const Rec& m) {
           tt_cache_insert(c, s0.z);
           tt_eval(c, t);
         } else {                                                                  // "Retrying read of tree node", :97-99
+          t->deadline = c.now + kPromiseTimeoutNs;
           tt_rpc(c, c.p.sv_ep[MS_SVC_LWW_KV], MS_T_READ, s0.z, 0ull, 11u, s0.z);
         }
         return;
       case 12:                                                                    // one of save!'s writes
         if (type != MS_T_WRITE_OK) t->write_failed = 1;
+        if (s0.z == t->first_write) t->first_write_ok = 1;
         if (--t->writes_left == 0) {
           if (t->write_failed) { tt_answer(c, t, MS_T_ERROR, 14u, 0ull); return; }   // "Couldn't save new tree", :347
           t->phase = 4;                                                           // advance_root!, :372-379
+          t->deadline = c.now + kPromiseTimeoutNs;
           tt_rpc(c, c.p.sv_ep[MS_SVC_LIN_KV], MS_T_CAS, 0u, (uint64_t)t->root1 | ((uint64_t)t->root2 << 32), 13u, 0u);
         }
         return;
@@ -608,8 +624,10 @@ __device__ void tt_handle(RaftCtx& c, const Rec& m) {
         req.round = 0; req.ticket = 0; req.idx = 0;
         req.src = t->init_src; req.dest = c.e; req.msg_id = t->init_msg_id; req.in_reply_to = 0; req.tf = MS_T_INIT; req.p0 = 0; req.p1 = 0;
         if (type == MS_T_WRITE_OK) {
+          t->init_phase = 2; t->init_deadline = c.now + kPromiseTimeoutNs;
           tt_rpc(c, c.p.sv_ep[MS_SVC_LIN_KV], MS_T_WRITE, 0u, (uint64_t)mst::kPtrEmpty, 15u, 0u);
         } else {
+          t->init_phase = 0;
           Rec er = rf_reply_to(c, req, MS_T_ERROR);                               // "Couldn't write initial state"
           er.p0 = 14;
           rf_emit(c, er);
@@ -620,6 +638,7 @@ __device__ void tt_handle(RaftCtx& c, const Rec& m) {
         Rec req;
         req.round = 0; req.ticket = 0; req.idx = 0;
         req.src = t->init_src; req.dest = c.e; req.msg_id = t->init_msg_id; req.in_reply_to = 0; req.tf = MS_T_INIT; req.p0 = 0; req.p1 = 0;
+        t->init_phase = 0;
         rf_emit(c, rf_reply_to(c, req, MS_T_INIT_OK));
         return;
       }
@@ -629,6 +648,7 @@ __device__ void tt_handle(RaftCtx& c, const Rec& m) {
   if (type == MS_T_INIT) {                                                        // node.rb:22-36 + :329-338
     if (c.e == 0) {                                                               // @node.node_ids.first == @node.node_id
       t->init_src = m.src; t->init_msg_id = m.msg_id;
+      t->init_phase = 1; t->init_deadline = c.now + kPromiseTimeoutNs;
       tt_rpc(c, c.p.sv_ep[MS_SVC_LWW_KV], MS_T_WRITE, mst::kPtrEmpty, (uint64_t)mst::kPtrEmpty, 14u, 0u);
     } else {
       rf_emit(c, rf_reply_to(c, m, MS_T_INIT_OK));
@@ -645,4 +665,26 @@ __device__ void tt_handle(RaftCtx& c, const Rec& m) {
   Rec er = rf_reply_to(c, m, MS_T_ERROR);                                         // no handler: not supported
   er.p0 = 10;
   rf_emit(c, er);
+}
+
+// Promise#await's 5 s (promise.rb:24-31), checked once per step after the step's messages: a reply that arrives in the
+// round the clock runs out still counts.  k_snapshot keeps a node's ticket alive when this would act (tt_timer_due).
+__device__ __forceinline__ bool tt_timer_due(const TreeDev& t, int64_t now) {
+  return (t.phase != 0 && t.deadline != 0 && now >= t.deadline) || (t.init_phase != 0 && now >= t.init_deadline);
+}
+__device__ void tt_actions(RaftCtx& c) {
+  TreeDev* t = c.p.tt_node + c.e;
+  if (t->init_phase != 0 && c.now >= t->init_deadline) {                          // the init handler's thread gives up
+    t->init_phase = 0;
+    Rec req;
+    req.round = 0; req.ticket = 0; req.idx = 0;
+    req.src = t->init_src; req.dest = c.e; req.msg_id = t->init_msg_id; req.in_reply_to = 0; req.tf = MS_T_INIT; req.p0 = 0; req.p1 = 0;
+    Rec er = rf_reply_to(c, req, MS_T_ERROR);
+    er.p0 = 0;                                                                    // RPCError.timeout
+    rf_emit(c, er);
+  }
+  if (t->phase != 0 && t->deadline != 0 && c.now >= t->deadline) {
+    const uint32_t code = (t->phase == 3 && !t->root_is_leaf && !t->first_write_ok) ? 14u : 0u;
+    tt_answer(c, t, MS_T_ERROR, code, 0ull);                                      // releases the lock: the next waiter starts
+  }
 }

@@ -337,7 +337,12 @@ struct TreeNode {              // DatomicListAppendNode (datomic_list_append.rb:
   std::deque<or_msg> waiting;                                    // threads blocked on @txn_lock, in arrival order
   std::set<uint32_t> cache;                                      // @@cache
   uint32_t init_src = 0, init_msg_id = 0;
+  int init_phase = 0;                                            // 0 none, 1 the empty tree's write is out, 2 the root's write is out
+  uint32_t gen = 0;                                              // transactions finished (a late reply finds a dead promise)
+  uint32_t first_write = 0; bool first_write_ok = false, root_is_leaf = false;   // save!: tasks[0]; Leaf#save! vs Branch#save!
+  int64_t deadline = 0, init_deadline = 0;                       // Promise#await gives up after 5 s (promise.rb:6,24-31)
 };
+static const int64_t kPromiseTimeoutNs = 5000000000ll;
 
 struct Endpoint {
   std::string name;
@@ -864,7 +869,7 @@ struct or_sim {
   void tt_rpc(uint32_t e, int dest, uint16_t type, uint32_t p0, uint64_t p1, int kind, uint32_t arg, std::vector<Emit>& out) {
     if (dest < 0) { error = "txn-list-append (hash tree) needs the lin-kv and lww-kv services"; return; }
     RaftNode& r = eps[e].rn;
-    RaftCb cb; cb.kind = kind; cb.node = arg;
+    RaftCb cb; cb.kind = kind; cb.node = arg; cb.term = eps[e].tn.gen;
     const uint32_t id = ++r.next_msg_id;                                          // node.rb:95-102
     cb.msg_id = id;
     r.callbacks[id % cb_slots] = cb;
@@ -877,6 +882,7 @@ struct or_sim {
     TreeNode& t = eps[e].tn;
     t.cur_src = m.src; t.cur_msg_id = m.msg_id; t.cur_ops = m.p1;
     t.phase = 1;
+    t.deadline = now + kPromiseTimeoutNs;
     tt_rpc(e, svc_endpoint(OR_SVC_LIN_KV), OR_T_READ, 0, 0, 10, 0, out);          // current_tree, :361-368
   }
   void tt_answer(uint32_t e, uint16_t type, uint32_t code, uint64_t p1, std::vector<Emit>& out) {
@@ -887,6 +893,8 @@ struct or_sim {
     a.p0 = code; a.p1 = p1;
     out.push_back(Emit(a));
     t.phase = 0;                                                                  // the lock passes to the next waiter
+    t.deadline = 0;
+    t.gen++;
     if (!t.waiting.empty()) {
       const or_msg next = t.waiting.front();
       t.waiting.pop_front();
@@ -901,6 +909,7 @@ struct or_sim {
     if (st == mst::kCapacity) { error = "hash tree: out of pointers / leaf or depth capacity"; return; }
     if (st == mst::kNeedLoad) {                                                   // Tree.load, :83-101
       t.phase = 2;
+      t.deadline = now + kPromiseTimeoutNs;
       tt_rpc(e, svc_endpoint(OR_SVC_LWW_KV), OR_T_READ, load_ptr, 0, 11, load_ptr, out);
       return;
     }
@@ -910,8 +919,27 @@ struct or_sim {
     uint32_t order[mst::kMaxWrites], n = 0;
     if (!mst::save_order(S, e, tt_per_node, t.start_counter, root2, order, n)) { error = "hash tree: save walk too deep"; return; }
     t.phase = 3; t.writes_left = n; t.write_failed = 0;
+    t.deadline = now + kPromiseTimeoutNs;
+    t.first_write = order[0]; t.first_write_ok = false; t.root_is_leaf = S.rec(root2)->type == 1;
     for (uint32_t i = 0; i < n; i++)                                              // save_this!, :128-145
       tt_rpc(e, svc_endpoint(OR_SVC_LWW_KV), OR_T_WRITE, order[i], order[i], 12, order[i], out);
+  }
+  // Promise#await's 5 s (promise.rb:24-31), checked once per step after the step's messages.  A handler thread that
+  // gives up raises RPCError.timeout: error 0 to the requester (node.rb:187-189), the lock is released.  Branch#save!
+  // waits in a helper thread (:297-309): if its first write is still unanswered when the clocks run out, its "false"
+  // is taken to reach the handler first (error 14), otherwise the handler's own time-out does (error 0).
+  void tt_actions(uint32_t e, std::vector<Emit>& out) {
+    TreeNode& t = eps[e].tn;
+    if (t.init_phase != 0 && now >= t.init_deadline) {
+      t.init_phase = 0;
+      or_msg init_req; std::memset(&init_req, 0, sizeof init_req);
+      init_req.src = t.init_src; init_req.dest = e; init_req.msg_id = t.init_msg_id;
+      or_msg er = reply_to(init_req, OR_T_ERROR);
+      er.p0 = 0;
+      out.push_back(Emit(er));
+    }
+    if (t.phase != 0 && t.deadline != 0 && now >= t.deadline)
+      tt_answer(e, OR_T_ERROR, (t.phase == 3 && !t.root_is_leaf && !t.first_write_ok) ? 14 : 0, 0, out);
   }
   void node_txn_tree(uint32_t e, const or_msg& m, std::vector<Emit>& out) {
     TreeNode& t = eps[e].tn;
@@ -921,6 +949,8 @@ struct or_sim {
       if (slot.kind == 0 || slot.msg_id != m.in_reply_to) return;                 // no callback
       const RaftCb cb = slot;
       slot.kind = 0;
+      if (cb.kind >= 10 && cb.kind <= 13 && (cb.term != t.gen || t.phase == 0)) return;   // its transaction is over: a dead promise
+      if ((cb.kind == 14 && t.init_phase != 1) || (cb.kind == 15 && t.init_phase != 2)) return;
       or_msg init_req; std::memset(&init_req, 0, sizeof init_req);
       init_req.src = t.init_src; init_req.dest = e; init_req.msg_id = t.init_msg_id;
       switch (cb.kind) {
@@ -930,13 +960,15 @@ struct or_sim {
           return;
         case 11:                                                                  // a tree node
           if (m.type == OR_T_READ_OK) { t.cache.insert(cb.node); tt_eval(e, out); }
-          else tt_rpc(e, svc_endpoint(OR_SVC_LWW_KV), OR_T_READ, cb.node, 0, 11, cb.node, out);   // retry, :97-99
+          else { t.deadline = now + kPromiseTimeoutNs; tt_rpc(e, svc_endpoint(OR_SVC_LWW_KV), OR_T_READ, cb.node, 0, 11, cb.node, out); }   // retry, :97-99
           return;
         case 12:                                                                  // one of save!'s writes
           if (m.type != OR_T_WRITE_OK) t.write_failed = 1;
+          if (cb.node == t.first_write) t.first_write_ok = true;
           if (--t.writes_left == 0) {
             if (t.write_failed) { tt_answer(e, OR_T_ERROR, 14, 0, out); return; }  // "Couldn't save new tree"
             t.phase = 4;                                                          // advance_root!, :372-379
+            t.deadline = now + kPromiseTimeoutNs;
             tt_rpc(e, svc_endpoint(OR_SVC_LIN_KV), OR_T_CAS, 0, (uint64_t)t.root1 | ((uint64_t)t.root2 << 32), 13, 0, out);
           }
           return;
@@ -945,10 +977,16 @@ struct or_sim {
           else tt_answer(e, OR_T_ERROR, 30, 0, out);                              // txn_conflict, :378
           return;
         case 14:                                                                  // the first node's initial state, :330-338
-          if (m.type == OR_T_WRITE_OK) tt_rpc(e, svc_endpoint(OR_SVC_LIN_KV), OR_T_WRITE, 0, mst::kPtrEmpty, 15, 0, out);
-          else { or_msg er = reply_to(init_req, OR_T_ERROR); er.p0 = 14; out.push_back(Emit(er)); }
+          if (m.type == OR_T_WRITE_OK) {
+            t.init_phase = 2; t.init_deadline = now + kPromiseTimeoutNs;
+            tt_rpc(e, svc_endpoint(OR_SVC_LIN_KV), OR_T_WRITE, 0, mst::kPtrEmpty, 15, 0, out);
+          } else {
+            t.init_phase = 0;
+            or_msg er = reply_to(init_req, OR_T_ERROR); er.p0 = 14; out.push_back(Emit(er));
+          }
           return;
         case 15:
+          t.init_phase = 0;
           out.push_back(Emit(reply_to(init_req, OR_T_INIT_OK)));                  // node.rb:31
           return;
       }
@@ -958,6 +996,7 @@ struct or_sim {
       case OR_T_INIT:                                                             // node.rb:22-36 + :329-338
         if (e == 0) {                                                             // @node.node_ids.first == @node.node_id
           t.init_src = m.src; t.init_msg_id = m.msg_id;
+          t.init_phase = 1; t.init_deadline = now + kPromiseTimeoutNs;
           tt_rpc(e, svc_endpoint(OR_SVC_LWW_KV), OR_T_WRITE, mst::kPtrEmpty, mst::kPtrEmpty, 14, 0, out);
         } else {
           out.push_back(Emit(reply_to(m, OR_T_INIT_OK)));
@@ -1176,6 +1215,7 @@ struct or_sim {
         if (!error.empty()) return false;
       }
       if (cfg.workload == OR_W_RAFT && ep.kind == OR_KIND_SERVER) raft_actions(e, out);
+      if (cfg.workload == OR_W_TXN_TREE && ep.kind == OR_KIND_SERVER) tt_actions(e, out);
       if (ep.kind == OR_KIND_GEN_CLIENT) gen_step(e, out);
       for (uint32_t j = 0; j < out.size(); j++) {
         if (out[j].has_snap) snapshots[next_id] = out[j].snap;   // keyed by the read_ok's net id
