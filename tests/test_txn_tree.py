@@ -61,7 +61,7 @@ def test_txn_tree_vs_oracle(engine_backend, n, dist, mean, seed):
         s.schedule(ops_array([(0, cs[i % 4], i, "init", 1 + i // 4, 0) for i in range(n)]))
         rng = np.random.default_rng(seed)
         s.schedule(txn_ops(rng, n, cs, 40, 60, 3, 40, [100] * 4))
-        s.run((400 + 2500 * mean) * 1_000_000)
+        s.run((400 + 1300 * mean) * 1_000_000)
         return s.client_replies()
 
     rg, ro = both(g, o, scenario)
@@ -106,7 +106,7 @@ def test_txn_tree_promise_timeouts_under_loss(engine_backend):
         s.schedule(ops_array([(0, cs[i], i, "init", 1, 0) for i in range(n)]))
         rng = np.random.default_rng(5)
         s.schedule(txn_ops(rng, n, cs, 20, 12, 3, 30, [100] * 3))
-        s.run(11_500_000_000)
+        s.run(7_500_000_000)
         return s.client_replies()
 
     rg, ro = both(g, o, scenario)
