@@ -14,7 +14,8 @@ OUT_DIR = os.path.join(HERE, "native", "_build")
 OUT = os.path.join(OUT_DIR, "libmaelstrom_b200_emul.so")
 SOURCES = [os.path.join(CSRC, "ms_kernels.cu"), os.path.join(CSRC, "ms_engine.cu"),
            os.path.join(EMUL, "simt.cpp")]
-DEPS = SOURCES + [os.path.join(CSRC, "ms_device.cuh"), os.path.join(CSRC, "ms_raft.cuh"), os.path.join(EMUL, "cuda_runtime.h"),
+DEPS = SOURCES + [os.path.join(CSRC, "ms_device.cuh"), os.path.join(CSRC, "ms_raft.cuh"), os.path.join(CSRC, "ms_tree.h"),
+                  os.path.join(CSRC, "ms_json.h"), os.path.join(CSRC, "ms_fressian.h"), os.path.join(EMUL, "cuda_runtime.h"),
                   os.path.join(ROOT, "include", "maelstrom_b200.h")]
 _lib = None
 
