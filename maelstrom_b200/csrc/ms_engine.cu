@@ -728,6 +728,8 @@ static int build_sim(ms_sim* s, const ms_config* in) {
     const size_t N = c.n_nodes;
     P.rf_stage_cap = c.workload == MS_W_TXN_TREE ? c.server_max_window * (mst::kMaxWrites + 2u) + 64u : c.server_max_window + 16u;
     P.rf_cb_mask = pow2_at_least(c.reserved[5] ? c.reserved[5] : kRaftCallbacks) - 1u;
+    // one save! has up to mst::kMaxWrites writes in flight, each with its closure (the oracle applies the same floor)
+    if (c.workload == MS_W_TXN_TREE && P.rf_cb_mask + 1u < 128u) P.rf_cb_mask = 127u;
     if ((rc = s->dalloc(&P.rf_node, N)) || (rc = s->dalloc(&P.rf_cb, N * ((size_t)P.rf_cb_mask + 1) * 2)) ||
         (rc = s->dalloc(&P.rf_stage, N * P.rf_stage_cap * 3)))
       return rc;
@@ -1684,6 +1686,8 @@ int ms_run_streamed(ms_sim* s, int64_t until, int format, size_t buf_events, ms_
 
 int ms_journal_decode(const ms_jbatch* b, const ms_jround* rounds, const void* events, ms_event* out) {
   if (!b || !rounds || !events || !out) return MS_ERR_ARG;
+  if (b->n_events && !b->n_rounds) return MS_ERR_ARG;                     // every event belongs to a round row
+  if (b->format == MS_JFMT_4) return MS_ERR_ARG;                         // needs the stream's history: ms_jdecoder_decode
   size_t r = 0;
   for (uint64_t k = 0; k < b->n_events; k++) {
     const uint64_t g = b->first_event + k;
@@ -1765,6 +1769,7 @@ int ms_jdecoder_note(ms_jdecoder* d, const ms_event* ev, size_t n) {
 
 int ms_jdecoder_decode(ms_jdecoder* d, const ms_jbatch* b, const ms_jround* rounds, const void* events, ms_event* out) {
   if (!d || !b || !rounds || !events || !out) return MS_ERR_ARG;
+  if (b->n_events && !b->n_rounds) { d->err = "ms_jdecoder: batch without round rows"; return MS_ERR_ARG; }
   if (b->format != MS_JFMT_4) {
     const int rc = ms_journal_decode(b, rounds, events, out);
     return rc ? rc : ms_jdecoder_note(d, out, (size_t)b->n_events);

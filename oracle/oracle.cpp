@@ -1249,6 +1249,7 @@ or_sim* or_create(const or_config* cfg) {
   if (s->cfg.rpc_table) { s->cb_slots = 1; while (s->cb_slots < s->cfg.rpc_table) s->cb_slots <<= 1; }
   if (s->cfg.raft_group >= s->cfg.n_nodes) s->cfg.raft_group = 0;
   if (cfg->workload == OR_W_TXN_TREE) {
+    if (s->cb_slots < 128) s->cb_slots = 128;                          // one save! has up to mst::kMaxWrites closures in flight
     s->tt_per_node = s->cfg.tree_ptrs ? s->cfg.tree_ptrs : 256u;
     s->tt_recs.assign(1 + (size_t)cfg->n_nodes * s->tt_per_node, mst::Rec{});
     mst::Rec& empty = s->tt_recs[mst::kPtrEmpty - 1];                  // Tree.empty: a leaf over the whole ring
