@@ -1606,7 +1606,8 @@ int ms_run_streamed(ms_sim* s, int64_t until, int format, size_t buf_events, ms_
   // half full, so a slow sink only slows the simulation down.
   // rounds launched per batch: 32 measured 9 % faster end to end than 8 on the broadcast bench (profiles/r2zz); three
   // batches are in flight, so stay well inside the round history
-  uint64_t batch_rounds = std::min<uint64_t>(32, std::max<uint64_t>(8, s->P.hist / 8));
+  // (sharded runs have no raw-ring back-pressure -- the ring must hold what three batches write -- so they keep 8)
+  uint64_t batch_rounds = s->P.n_shards > 1 ? 8 : std::min<uint64_t>(32, std::max<uint64_t>(8, s->P.hist / 8));
   if (const char* br = getenv("MS_STREAM_BATCH_ROUNDS")) {            // tuning aid
     const long v = atol(br);
     if (v >= 1 && v <= 1024) batch_rounds = (uint64_t)v;
