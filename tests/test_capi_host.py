@@ -106,3 +106,31 @@ def test_type_codes_agree_between_header_engine_and_oracle(lib):
     for name, code in TYPES.items():
         m = re.search(r"MS_T_%s\s*=\s*(\d+)" % name.upper(), src)
         assert m and int(m.group(1)) == code == O.T[name]
+
+
+def test_journal_decoders_refuse_malformed_batches():
+    # host-only entry points: no device involved
+    import ctypes as C
+    import numpy as np
+    from maelstrom_b200 import _lib
+    from maelstrom_b200._lib import EVENT_DTYPE, JBatch
+    L = _lib.lib()
+    b = JBatch()
+    b.first_event, b.n_events, b.n_rounds, b.format = 0, 1, 0, 8          # an event but no round row
+    rounds = np.zeros(1, dtype=_lib.JROUND_DTYPE)
+    events = np.zeros(1, dtype="<u8")
+    out = np.zeros(1, dtype=EVENT_DTYPE)
+    assert L.ms_journal_decode(C.byref(b), rounds.ctypes.data, events.ctypes.data, out.ctypes.data) < 0
+    b.n_rounds, b.format = 1, 4                                          # MS_JFMT_4 needs the stream's history
+    assert L.ms_journal_decode(C.byref(b), rounds.ctypes.data, events.ctypes.data, out.ctypes.data) < 0
+    d = L.ms_jdecoder_create(8)
+    assert d
+    e4 = np.array([0x80000000 | 5], dtype="<u4")                        # a :recv of a message the decoder never saw sent
+    rounds[0]["id_ref"] = 100
+    assert L.ms_jdecoder_decode(d, C.byref(b), rounds.ctypes.data, e4.ctypes.data, out.ctypes.data) < 0
+    assert b"window" in L.ms_jdecoder_error(d)
+    e4[0] = (3 << 16) | 7                                               # a :send n3 -> n7: its id is the round's first id
+    assert L.ms_jdecoder_decode(d, C.byref(b), rounds.ctypes.data, e4.ctypes.data, out.ctypes.data) == 0
+    assert (int(out[0]["msg_id"]), int(out[0]["src"]), int(out[0]["dest"])) == (100, 3, 7)
+    L.ms_jdecoder_destroy(d)
+    assert L.ms_jdecoder_create(2) is None                              # window too small
