@@ -300,3 +300,21 @@ def test_emulated_shards_discarded_journal_adaptive_batches():
     scenario(o, O.body)
     assert len(ev) == 0 and st == o.stats() and now == o.now and rnd == o.round
     assert st["servers"]["recv-count"] > 5000
+
+
+def test_emulated_eight_shards_broadcast_glue_path():
+    # the shard count of the driver's scaling run: 8 shards, no timing wheel -> one k_glue launch between rounds
+    world, n = 8, 64
+    kw = dict(topology="grid", n_values=512, seed=5)
+
+    def scenario(s, body):
+        cs = [s.add_endpoint("c%d" % i, O.KIND_SIM_CLIENT) for i in range(4)]
+        ops, _ = random_broadcast_ops(n, cs, n_ticks=6, per_tick=12, seed=21)
+        s.schedule(ops)
+        s.run(4_000_000)
+        s.run(9_000_000)
+
+    ev, st, now, rnd = run_sharded_scenario(world, n, dict(workload="broadcast", ring_cap=1024, max_window=512, journal_cap_log2=19,
+                                                            max_endpoints=n + 8, **kw), scenario)
+    check_against_oracle(O.Sim(n, workload=O.W_BROADCAST, **kw), scenario, ev, st, now, rnd)
+    assert len(ev) > 20000
