@@ -248,7 +248,15 @@ __device__ __forceinline__ void journal_raw(const Params& p, uint64_t pos, uint6
 }
 
 // ------------------------------------------------------------------ timing wheel (pooled chains)
-__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+// A word another thread publishes with an atomic (wheel block ids, slot_open): a relaxed atomic load.  On the GPU a
+// volatile 32-bit load is exactly that; the emulator build says so in C++ terms (ThreadSanitizer checks it).
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+#ifdef MS_EMUL
+  return __atomic_load_n(p, __ATOMIC_RELAXED);
+#else
+  return *reinterpret_cast<const volatile uint32_t*>(p);
+#endif
+}
 
 // Block `j` of the chain of (generation, slot): its pool index, allocating it on first use.  The
 // thread that filed the first record of the block is its designated allocator; everybody else
