@@ -490,13 +490,13 @@ class TxnTree(Txn256k):
                 "l2_policy": "tree records 0.5 GB + per-node caches and closure tables + lww-kv replicas: larger than L2"}
 
     def cpu_sample(self, O, scale, seed):
-        n = 1024
+        n = 256                     # (the oracle visits every endpoint in every round: a sparse workload is slow on it)
         s = O.Sim(n, workload=O.W_TXN_TREE, seed=seed, rpc_table=64, tree_ptrs=512)
         s.add_endpoint("lin-kv", O.KIND_SERVICE)
         s.add_endpoint("lww-kv", O.KIND_SERVICE)
         cs = [s.add_endpoint("c%d" % i, O.KIND_SIM_CLIENT) for i in range(8)]
         w = TxnTree(self.args)
-        w.n_nodes, w.n_clients, w.txns_per_tick = n, 8, 64
+        w.n_nodes, w.n_clients, w.txns_per_tick = n, 8, 16
         steps = max(1, int(scale))
         flags = {"msg_id": O.F_MSG_ID, "appends": O.F_APPENDS}
         s.schedule(w.prologue_ops(O.OP_DTYPE, cs[0], O.T, flags))
@@ -504,7 +504,7 @@ class TxnTree(Txn256k):
         t0 = time.perf_counter()
         s.run(((steps + 1) * w.step_ticks + 2) * TICK_NS)
         dt = time.perf_counter() - t0
-        return s.stats()["all"]["recv-count"], dt, "hash-tree txn-list-append %d nodes, 64 txns/tick x %d ticks" % (n, (steps + 1) * w.step_ticks)
+        return s.stats()["all"]["recv-count"], dt, "hash-tree txn-list-append %d nodes, 16 txns/tick x %d ticks" % (n, (steps + 1) * w.step_ticks)
 
 
 def make_workload(args):
@@ -580,7 +580,7 @@ def _arg_dict(args):
                                           "threads", "nodes", "raft_log_cap", "config", "ops_per_tick")}
 
 
-CPU_SCALE = {"broadcast": 1536, "broadcast-lat1": 1536, "gset16k": 4, "raft64k": 40, "txn256k": 400, "txntree": 4}
+CPU_SCALE = {"broadcast": 1536, "broadcast-lat1": 1536, "gset16k": 4, "raft64k": 40, "txn256k": 400, "txntree": 20}
 
 
 def cpu_baseline_single(args):
