@@ -580,7 +580,7 @@ def _arg_dict(args):
                                           "threads", "nodes", "raft_log_cap", "config", "ops_per_tick")}
 
 
-CPU_SCALE = {"broadcast": 1536, "broadcast-lat1": 1536, "gset16k": 4, "raft64k": 40, "txn256k": 400, "txntree": 20}
+CPU_SCALE = {"broadcast": 1536, "broadcast-lat1": 1536, "gset16k": 4, "raft64k": 40, "txn256k": 400, "txntree": 5}
 
 
 def cpu_baseline_single(args):
